@@ -1,0 +1,386 @@
+/*
+ * cticp.h — C ABI of the B200-native CT-ICP registration engine.
+ *
+ * This is the drop-in boundary underneath the C++ facade `ct_icp::Odometry`
+ * (ct_icp_b200/include/ct_icp/odometry.h). Plain pointers and sizes only; no
+ * C++/torch/Eigen types. Every entry point names the reference interface it
+ * replaces (paths relative to the upstream tree, jedeschaud/ct_icp @ d467813).
+ *
+ * Conventions
+ *   - return value: CTICP_OK (0) or a negative cticp_status; the message of the
+ *     last failure is available through cticp_last_error().
+ *   - quaternions are stored (x, y, z, w) like Eigen::Quaterniond::coeffs().
+ *   - one handle owns one CUDA device context + stream; a handle is NOT
+ *     re-entrant (same rule as the reference: callers serialise, see
+ *     ros/catkin_ws/ct_icp_odometry/src/ct_icp_odometry_node.cxx:67).
+ *   - input clouds are borrowed for the duration of the call only.
+ *   - there is NO CPU fallback: cticp_create fails with CTICP_ERR_NO_DEVICE
+ *     when no sm_100 device is usable.
+ */
+#ifndef CTICP_H
+#define CTICP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTICP_ABI_VERSION 1
+#define CTICP_MAX_RESOLUTIONS 8
+
+typedef enum cticp_status {
+    CTICP_OK = 0,
+    CTICP_ERR_INVALID_ARGUMENT = -1,
+    CTICP_ERR_NO_DEVICE = -2,
+    CTICP_ERR_CUDA = -3,
+    CTICP_ERR_CAPACITY = -4,      /* a device table / block pool is full */
+    CTICP_ERR_TIMESTAMP = -5,     /* reference: CHECK in TPose::InterpolatePose, include/SlamCore/types.h:456 */
+    CTICP_ERR_UNSUPPORTED = -6,   /* option combination outside the built hot path */
+    CTICP_ERR_NCCL = -7,
+    CTICP_ERR_INTERNAL = -8
+} cticp_status;
+
+/* ---- enums mirroring the reference (same numeric order) ------------------------------------------------ */
+/* include/ct_icp/ct_icp.h:35-39 */
+enum { CTICP_SOLVER_GN = 0, CTICP_SOLVER_CERES = 1, CTICP_SOLVER_ROBUST = 2 };
+/* include/ct_icp/ct_icp.h:41-47 */
+enum { CTICP_LOSS_STANDARD = 0, CTICP_LOSS_CAUCHY = 1, CTICP_LOSS_HUBER = 2, CTICP_LOSS_TOLERANT = 3,
+       CTICP_LOSS_TRUNCATED = 4 };
+/* include/ct_icp/ct_icp.h:49-53 */
+enum { CTICP_WEIGHT_PLANARITY = 0, CTICP_WEIGHT_NEIGHBORHOOD = 1, CTICP_WEIGHT_ALL = 2 };
+/* include/ct_icp/cost_functions.h:17-20 (POSE_PARAMETRIZATION) */
+enum { CTICP_PARAM_SIMPLE = 0, CTICP_PARAM_CONTINUOUS_TIME = 1 };
+/* include/ct_icp/cost_functions.h:22-27 (ICP_DISTANCE) */
+enum { CTICP_DIST_POINT_TO_PLANE = 0, CTICP_DIST_POINT_TO_POINT = 1, CTICP_DIST_POINT_TO_LINE = 2,
+       CTICP_DIST_POINT_TO_DISTRIBUTION = 3 };
+/* include/ct_icp/odometry.h:16-21 (MOTION_COMPENSATION) */
+enum { CTICP_MC_NONE = 0, CTICP_MC_CONSTANT_VELOCITY = 1, CTICP_MC_ITERATIVE = 2, CTICP_MC_CONTINUOUS = 3 };
+/* include/ct_icp/odometry.h:23-26 (INITIALIZATION) */
+enum { CTICP_INIT_NONE = 0, CTICP_INIT_CONSTANT_VELOCITY = 1 };
+/* include/ct_icp/odometry.h:27-31 (sampling::SAMPLING_OPTION) */
+enum { CTICP_SAMPLING_NONE = 0, CTICP_SAMPLING_GRID = 1, CTICP_SAMPLING_ADAPTIVE = 2 };
+/* include/ct_icp/motion_model.h:36-39 */
+enum { CTICP_MM_CONSTANT_VELOCITY = 0, CTICP_MM_SMALL_VELOCITY = 1 };
+
+/* ---- option PODs ------------------------------------------------------------------------------------------ */
+
+/* ct_icp::CTICPOptions, include/ct_icp/ct_icp.h:56-153 (defaults: cticp_default_icp_options) */
+typedef struct cticp_icp_options {
+    int32_t num_iters_icp;
+    int32_t parametrization;
+    int32_t distance;
+    int32_t solver;
+    int32_t max_num_residuals;
+    int32_t min_num_residuals;
+    int32_t weighting_scheme;
+    int32_t max_number_neighbors;
+    int32_t min_number_neighbors;
+    int32_t threshold_voxel_occupancy;
+    int32_t num_closest_neighbors;
+    int32_t point_to_plane_with_distortion;
+    int32_t loss_function;
+    int32_t ls_max_num_iters;
+    int32_t ls_num_threads;
+    int32_t debug_print;
+    double weight_alpha;
+    double weight_neighborhood;
+    double power_planarity;
+    double threshold_orientation_norm;
+    double threshold_translation_norm;
+    double ls_sigma;
+    double ls_tolerant_min_threshold;
+    double max_dist_to_plane_ct_icp;
+    /* ROBUST solver params (carried for completeness; solver ROBUST is SURVEY §8f) */
+    double threshold_linearity;
+    double threshold_planarity;
+    double weight_point_to_point;
+    double outlier_distance;
+    int32_t use_barycenter;
+    int32_t _pad0;
+} cticp_icp_options;
+
+/* ct_icp::MultipleResolutionVoxelMap::ResolutionParam / Options, include/ct_icp/map.h:109-134 */
+typedef struct cticp_resolution_param {
+    double resolution;
+    double min_distance_between_points;
+    int32_t max_num_points;
+    int32_t _pad0;
+} cticp_resolution_param;
+
+typedef struct cticp_map_options {
+    int32_t num_resolutions;
+    int32_t select_valid_normals_direction;
+    int32_t max_frames_to_keep;
+    int32_t _pad0;
+    double default_radius;
+    cticp_resolution_param resolutions[CTICP_MAX_RESOLUTIONS];
+    /* device sizing (new; not in the reference): 0 = pick from defaults */
+    uint64_t capacity_voxels;      /* slots per resolution (power of two is taken) */
+} cticp_map_options;
+
+/* ct_icp::INeighborStrategyOptions, include/ct_icp/neighborhood_strategy.h:37-55 */
+typedef struct cticp_strategy_options {
+    int32_t type;                  /* 0 = NEAREST_NEIGHBOR_STRATEGY (the only built one) */
+    int32_t max_num_neighbors;
+    int32_t min_num_neighbors;
+    int32_t _pad0;
+} cticp_strategy_options;
+
+/* ct_icp::PreviousFrameMotionModel::Options, include/ct_icp/motion_model.h:42-58 */
+typedef struct cticp_motion_model_options {
+    int32_t model;
+    int32_t log_if_invalid;
+    double beta_location_consistency;
+    double beta_constant_velocity;
+    double beta_small_velocity;
+    double beta_orientation_consistency;
+    double threshold_orientation_deg;
+    double threshold_translation_diff;
+} cticp_motion_model_options;
+
+/* ct_icp::OdometryOptions, include/ct_icp/odometry.h:32-157 */
+typedef struct cticp_odometry_options {
+    cticp_icp_options ct_icp_options;
+    cticp_map_options map_options;
+    cticp_strategy_options neighborhood_strategy;
+    cticp_motion_model_options default_motion_model;
+    int32_t motion_compensation;
+    int32_t initialization;
+    int32_t init_num_frames;
+    int32_t max_num_keypoints;
+    int32_t sampling;
+    int32_t quit_on_error;
+    int32_t robust_minimal_level;
+    int32_t robust_registration;
+    int32_t robust_fail_early;
+    int32_t robust_num_attempts;
+    int32_t robust_num_attempts_when_rotation;
+    int32_t robust_max_voxel_neighborhood;
+    int32_t always_insert;
+    int32_t do_no_insert;
+    int32_t debug_print;
+    int32_t with_default_motion_model;
+    double init_voxel_size;
+    double init_sample_voxel_size;
+    double sample_voxel_size;
+    double voxel_size;
+    double max_distance;
+    double distance_error_threshold;
+    double orientation_error_threshold;
+    double robust_full_voxel_threshold;
+    double robust_empty_voxel_threshold;
+    double robust_neighborhood_min_dist;
+    double robust_neighborhood_min_orientation;
+    double robust_relative_trans_threshold;
+    double robust_threshold_ego_orientation;
+    double robust_threshold_relative_orientation;
+    double insertion_ego_rotation_threshold;
+    double insertion_threshold_frames_skipped;
+    double insertion_cum_distance_threshold;
+    double insertion_cum_orientation_threshold;
+    /* order contract (new): seed of the counter-based permutations that stand in for
+     * std::shuffle(…, std::mt19937_64 g_) at src/ct_icp/odometry.cpp:349,361,550 */
+    uint64_t shuffle_seed;
+    /* device sizing (new): upper bound on points per scan; 0 = 524288 */
+    uint64_t max_points_per_frame;
+} cticp_odometry_options;
+
+/* ---- value PODs ------------------------------------------------------------------------------------------- */
+
+/* slam::TPose<double>, include/SlamCore/types.h:162-274 */
+typedef struct cticp_pose {
+    double quat[4];                /* x, y, z, w */
+    double tr[3];
+    double ref_timestamp;
+    double dest_timestamp;
+    uint32_t ref_frame_id;
+    uint32_t dest_frame_id;
+} cticp_pose;
+
+/* ct_icp::TrajectoryFrame, include/ct_icp/types.h:31-61 */
+typedef struct cticp_frame {
+    cticp_pose begin_pose;
+    cticp_pose end_pose;
+} cticp_frame;
+
+/* slam::WPoint3D, include/SlamCore/types.h:35-60 (same 64-byte layout: raw xyz, t, world xyz, index_frame) */
+typedef struct cticp_wpoint {
+    double raw[3];
+    double timestamp;
+    double world[3];
+    uint32_t index_frame;
+    uint32_t _pad0;
+} cticp_wpoint;
+
+/* ct_icp::ICPSummary, include/ct_icp/ct_icp.h:155-169 */
+typedef struct cticp_icp_summary {
+    int32_t success;
+    int32_t num_residuals_used;
+    int32_t num_iters;
+    int32_t _pad0;
+    double duration_total;
+    double duration_init;
+    double avg_duration_iter;
+    double avg_duration_neighborhood;
+    double avg_duration_solve;
+} cticp_icp_summary;
+
+/* ct_icp::Odometry::RegistrationSummary, include/ct_icp/odometry.h:163-199.
+ * The three point vectors are fetched on demand with cticp_get_points(). */
+typedef struct cticp_summary {
+    cticp_frame frame;
+    cticp_frame initial_frame;
+    cticp_icp_summary icp_summary;
+    int32_t sample_size;
+    int32_t number_of_residuals;
+    int32_t robust_level;
+    int32_t success;
+    int32_t points_added;
+    int32_t number_of_attempts;
+    double distance_correction;
+    double relative_distance;
+    double relative_orientation;
+    double ego_orientation;
+    uint64_t num_corrected_points;       /* F: points of the sub-sampled frame */
+    uint64_t num_all_corrected_points;   /* N: points of the input scan */
+    uint64_t num_keypoints;              /* K */
+    /* logged_values (src/ct_icp/odometry.cpp:495-513), milliseconds */
+    double odometry_total;
+    double odometry_initialization;
+    double odometry_try_register;
+    double odometry_duration_sampling;
+    double odometry_map_update;
+    double odometry_transform;
+    char error_message[256];
+} cticp_summary;
+
+enum { CTICP_POINTS_CORRECTED = 0, CTICP_POINTS_ALL_CORRECTED = 1, CTICP_POINTS_KEYPOINTS = 2 };
+
+typedef struct cticp_odometry cticp_odometry;   /* opaque: replaces ct_icp::Odometry */
+typedef struct cticp_map cticp_map;             /* opaque: replaces ct_icp::MultipleResolutionVoxelMap */
+
+/* ---- defaults & profiles ---------------------------------------------------------------------------------- */
+uint32_t cticp_abi_version(void);
+const char *cticp_last_error(void);                                   /* thread-local */
+
+void cticp_default_icp_options(cticp_icp_options *out);               /* include/ct_icp/ct_icp.h:60-152 */
+void cticp_default_map_options(cticp_map_options *out);               /* include/ct_icp/map.h:115-125 */
+void cticp_default_odometry_options(cticp_odometry_options *out);     /* include/ct_icp/odometry.h:37-157 */
+void cticp_legacy_map_options(cticp_map_options *out, double size_voxel_map, int max_num_points_in_voxel,
+                              double min_distance_points);            /* src/ct_icp/map.cpp:13-29 */
+void cticp_profile_default_driving(cticp_odometry_options *out);      /* src/ct_icp/odometry.cpp:30-36 */
+void cticp_profile_robust_driving(cticp_odometry_options *out);       /* src/ct_icp/odometry.cpp:39-89 */
+void cticp_profile_robust_outdoor_low_inertia(cticp_odometry_options *out); /* src/ct_icp/odometry.cpp:92-151 */
+
+/* ---- Odometry (L4 boundary) ------------------------------------------------------------------------------- */
+
+/* ct_icp::Odometry::Odometry(const OdometryOptions&), src/ct_icp/odometry.cpp:697-734 */
+int cticp_odometry_create(const cticp_odometry_options *options, int device, cticp_odometry **out);
+void cticp_odometry_destroy(cticp_odometry *h);
+
+/* ct_icp::Odometry::RegisterFrame(const slam::PointCloud&, frame_id_t, AMotionModel*), src/ct_icp/odometry.cpp:199-214
+ * and RegisterFrameWithEstimate (:217-236) when initial_estimate != NULL.
+ * xyz / t are strided HOST arrays (stride in bytes), the layout RegisterFrame reads through
+ * XYZConst<double>() / TimestampsProxy<double>() (src/ct_icp/odometry.cpp:335-336). */
+int cticp_odometry_register_frame(cticp_odometry *h,
+                                  const double *xyz, size_t xyz_stride_bytes,
+                                  const double *t, size_t t_stride_bytes,
+                                  size_t n, uint32_t frame_id,
+                                  const cticp_frame *initial_estimate,
+                                  cticp_summary *out_summary);
+
+/* RegistrationSummary::{corrected_points, all_corrected_points, keypoints}, include/ct_icp/odometry.h:187-191.
+ * Copies min(cap, count) points device->host; returns the count or a negative status. */
+int64_t cticp_odometry_get_points(cticp_odometry *h, int which, cticp_wpoint *dst, size_t cap);
+
+/* ct_icp::Odometry::Trajectory(), src/ct_icp/odometry.cpp:687-689 */
+int64_t cticp_odometry_trajectory(cticp_odometry *h, cticp_frame *dst, size_t cap);
+/* ct_icp::Odometry::MapSize(), src/ct_icp/odometry.cpp:156-158 */
+int64_t cticp_odometry_map_size(cticp_odometry *h);
+/* ct_icp::Odometry::GetMapPointCloud(), src/ct_icp/odometry.cpp:692-694 → xyz triples */
+int64_t cticp_odometry_map_points(cticp_odometry *h, double *dst_xyz, size_t cap_points);
+/* ct_icp::Odometry::Reset(), src/ct_icp/odometry.cpp:956-965 */
+int cticp_odometry_reset(cticp_odometry *h);
+/* ct_icp::Odometry::GetMapPointer(), src/ct_icp/odometry.cpp:991-993 (borrowed; owned by the odometry) */
+cticp_map *cticp_odometry_map(cticp_odometry *h);
+
+/* multi-GPU (new): keypoints sharded rank/world, one NCCL all-reduce of JTJ/JTr per iteration.
+ * unique_id is the 128-byte ncclUniqueId produced by cticp_nccl_unique_id on rank 0 and broadcast by the caller. */
+int cticp_nccl_unique_id(void *out_128_bytes);
+int cticp_odometry_enable_sharding(cticp_odometry *h, const void *unique_id_128_bytes, int rank, int world);
+
+/* device timing of the last register_frame (CUDA events on the handle's stream), milliseconds */
+typedef struct cticp_device_timing {
+    double total_ms;
+    double ingest_ms;        /* H2D + sub-sampling + keypoint sampling */
+    double icp_ms;           /* all ICP iterations (gather kernel + solve) */
+    double gather_ms;        /* neighbor-gather/residual kernel only, summed over iterations */
+    double map_update_ms;    /* transform + evict + insert */
+    int32_t icp_iterations;
+    int32_t kernel_launches;
+    uint64_t gather_keypoint_iterations;   /* Σ over iterations of keypoints processed */
+    uint64_t gather_stencil_points;        /* Σ S: map points found inside the stencils */
+    uint64_t gather_stencil_voxels;        /* Σ (2r+1)^3 probes */
+} cticp_device_timing;
+int cticp_odometry_last_timing(cticp_odometry *h, cticp_device_timing *out);
+
+/* ---- Map (L2 boundary; used directly by the parity tests) ---------------------------------------------- */
+
+/* MultipleResolutionVoxelMap(const Options&), include/ct_icp/map.h:136-138 */
+int cticp_map_create(const cticp_map_options *options, int device, cticp_map **out);
+void cticp_map_destroy(cticp_map *m);
+/* InsertPointCloud (world points, given order), include/ct_icp/map.h:153-254,261-293 */
+int cticp_map_insert(cticp_map *m, const double *xyz, size_t stride_bytes, size_t n);
+/* RemoveElementsFarFromLocation, include/ct_icp/map.h:305-322 */
+int cticp_map_remove_far(cticp_map *m, const double location[3], double distance);
+/* NumPoints(), include/ct_icp/map.h:345 (resolution 0) ; num points of any resolution with map_idx */
+int64_t cticp_map_num_points(cticp_map *m, int map_idx);
+int64_t cticp_map_num_voxels(cticp_map *m, int map_idx);
+/* GetMapPoints(map_idx), include/ct_icp/map.h:354-376: xyz + int32 voxel coords per point (either may be NULL) */
+int64_t cticp_map_export(cticp_map *m, int map_idx, double *dst_xyz, int32_t *dst_voxel, size_t cap_points);
+/* ComputeNeighborhoods(queries, max_num_neighbors), include/ct_icp/map.h:532-540 (default radius, no normal filter).
+ * out_points: n × max_num_neighbors × 3 (farthest first, like RadiusSearchInPlace :508-513), out_counts: n */
+int cticp_map_compute_neighborhoods(cticp_map *m, const double *queries_xyz, size_t n, int max_num_neighbors,
+                                    double *out_points, int32_t *out_counts);
+/* ClearMap(), include/ct_icp/map.h:296 */
+int cticp_map_clear(cticp_map *m);
+
+/* ---- Registration (L3 boundary) ------------------------------------------------------------------------- */
+
+/* CT_ICP_Registration::Register(map, keypoints, frame, motion_model, strategy), src/ct_icp/ct_icp.cpp:1026-1037.
+ * keypoints[i].world is rewritten (as the reference does through the world_point proxy);
+ * frame is in/out; previous_frame (nullable) stands for the PreviousFrameMotionModel state and
+ * motion_options for its Options (src/ct_icp/motion_model.cpp:12-61, ct_icp.cpp:885-910). */
+int cticp_icp_register(cticp_map *m, const cticp_icp_options *options,
+                       const cticp_strategy_options *strategy,
+                       cticp_wpoint *keypoints, size_t n,
+                       cticp_frame *frame,
+                       const cticp_frame *previous_frame,
+                       const cticp_motion_model_options *motion_options,
+                       cticp_icp_summary *out_summary);
+
+/* Debug tap for parity tests: normal equations of ONE Gauss-Newton linearisation at `frame`
+ * (A 12×12 row-major AFTER the 1/n normalisation and regularisers of ct_icp.cpp:877-910, b 12, n used). */
+int cticp_icp_gn_normal_equations(cticp_map *m, const cticp_icp_options *options,
+                                  const cticp_wpoint *keypoints, size_t n,
+                                  const cticp_frame *frame,
+                                  const cticp_frame *previous_frame,
+                                  const cticp_motion_model_options *motion_options,
+                                  double *out_A144, double *out_b12, int32_t *out_num_used);
+
+/* ---- Sampling (a3/a4) ------------------------------------------------------------------------------------ */
+
+/* ct_icp::sub_sample_frame / grid_sampling, src/ct_icp/ct_icp.cpp:65-101, under the order contract
+ * (first-seen per voxel of RAW coordinates in the given order; output in order of first appearance).
+ * out_indices receives the indices kept; returns the count. */
+int64_t cticp_grid_sample_indices(int device, const double *xyz, size_t stride_bytes, size_t n, double voxel_size,
+                                  uint32_t *out_indices, size_t cap);
+/* The counter-based permutation standing in for std::shuffle: out[perm(i)] = i semantics, see DESIGN.md */
+int cticp_permutation(uint64_t seed, uint64_t counter, uint32_t n, uint32_t *out_perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTICP_H */

@@ -1,0 +1,456 @@
+// device_map.cu — insert / evict / rebuild / export kernels and the host-side DeviceMap class.
+//
+// Reference behaviour reproduced (include/ct_icp/map.h):
+//   InsertPointCloud / InsertPointInVoxelMap  :153-254, 261-293  (sequential min-distance rule in input order)
+//   RemoveElementsFarFromLocation             :305-322           (tests the voxel's FIRST stored point)
+//   NumPoints / GetMapPoints                  :345-376
+#include "device_map.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <numeric>
+#include <stdexcept>
+#include <vector>
+
+namespace cticp {
+
+#define CT_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                            std::to_string(__LINE__));                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_clear_level(MapLevel L) {
+    const uint32_t cap = L.cap_mask + 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        L.slots[i].key = kEmptyKey;
+        L.slots[i].count = 0;
+        L.slots[i]._pad = 0;
+        L.head[i] = kNil;
+    }
+}
+
+// Phase 1 of InsertPointCloud: find-or-create the voxel of every point and thread the point onto the voxel's
+// candidate list. One thread per point; the list order is arbitrary (phase 2 re-orders by point index).
+__global__ void k_insert_claim(MapLevel L, MapCounters *ctr, const double *__restrict__ world, const int *d_n,
+                               int *__restrict__ next, uint32_t *__restrict__ touched) {
+    const int n = *d_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double px = world[3 * i], py = world[3 * i + 1], pz = world[3 * i + 2];
+        if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
+            next[i] = kNil;
+            continue;
+        }
+        const unsigned long long key =
+            pack_voxel(voxel_coord(px, L.res), voxel_coord(py, L.res), voxel_coord(pz, L.res));
+        uint32_t h = hash_key(key) & L.cap_mask;
+        int slot = -1;
+        for (uint32_t probe = 0; probe <= L.cap_mask; ++probe) {
+            unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&L.slots[h].key);
+            if (k == kEmptyKey) {
+                k = atomicCAS(&L.slots[h].key, kEmptyKey, key);
+                if (k == kEmptyKey) {
+                    atomicAdd(&ctr->num_voxels, 1u);
+                    slot = (int) h;
+                    break;
+                }
+            }
+            if (k == key) {
+                slot = (int) h;
+                break;
+            }
+            h = (h + 1) & L.cap_mask;
+        }
+        if (slot < 0) {
+            atomicExch(&ctr->overflow, 1u);
+            next[i] = kNil;
+            continue;
+        }
+        const int old = atomicExch(&L.head[slot], i);
+        next[i] = old;
+        if (old == kNil) touched[atomicAdd(&ctr->num_touched, 1u)] = (uint32_t) slot;
+    }
+}
+
+// Phase 2: one warp per touched voxel applies the reference's sequential rule to that voxel's candidates in
+// ascending point index: accept while count < B and every stored point is farther than min_dist (map.h:276-291);
+// a brand-new voxel accepts its first candidate unconditionally (:268-273).
+constexpr int kInsertWarps = 4;
+constexpr int kMaxCand = 512;
+constexpr int kMaxB = 64;
+
+__global__ void __launch_bounds__(kInsertWarps * 32)
+k_insert_commit(MapLevel L, MapCounters *ctr, const double *__restrict__ world, const int *__restrict__ next,
+                const uint32_t *__restrict__ touched) {
+    __shared__ int s_cand[kInsertWarps][kMaxCand];
+    __shared__ int s_sorted[kInsertWarps][kMaxCand];
+    __shared__ float4 s_pts[kInsertWarps][kMaxB];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned n_touched = ctr->num_touched;
+    const int warps_total = gridDim.x * kInsertWarps;
+    for (unsigned t = blockIdx.x * kInsertWarps + w; t < n_touched; t += warps_total) {
+        const uint32_t slot = touched[t];
+        const unsigned long long key = L.slots[slot].key;
+        int vx, vy, vz;
+        unpack_voxel(key, vx, vy, vz);
+        const double ox = vx * L.res, oy = vy * L.res, oz = vz * L.res;
+        const int count0 = (int) L.slots[slot].count;
+        int count = count0;
+        float4 *gpts = L.points + (size_t) slot * L.B;
+        for (int j = lane; j < count; j += 32) s_pts[w][j] = gpts[j];
+
+        // walk the candidate list (all lanes follow the same pointers → broadcast loads)
+        int n = 0;
+        for (int c = L.head[slot]; c != kNil; c = next[c]) {
+            if (n < kMaxCand && lane == 0) s_cand[w][n] = c;
+            ++n;
+        }
+        __syncwarp();
+        int last = -1;          // slow path cursor (n > kMaxCand)
+        int processed = 0;
+        while (processed < n && count < L.B) {
+            int m;              // candidates staged in s_sorted this round
+            if (n <= kMaxCand) {
+                // rank sort (indices are unique)
+                for (int a = lane; a < n; a += 32) {
+                    const int v = s_cand[w][a];
+                    int rank = 0;
+                    for (int b = 0; b < n; ++b) rank += (s_cand[w][b] < v);
+                    s_sorted[w][rank] = v;
+                }
+                m = n;
+            } else {
+                // rare: more candidates than staging room → select the next smallest index by walking the list
+                int best = 0x7fffffff;
+                for (int c = L.head[slot]; c != kNil; c = next[c])
+                    if (c > last && c < best) best = c;
+                if (lane == 0) s_sorted[w][0] = best;
+                last = best;
+                m = 1;
+            }
+            __syncwarp();
+            for (int a = 0; a < m && count < L.B; ++a) {
+                const int c = s_sorted[w][a];
+                const double lx = world[3 * c] - ox, ly = world[3 * c + 1] - oy, lz = world[3 * c + 2] - oz;
+                bool too_close = false;
+                for (int j = lane; j < count; j += 32) {
+                    const float4 q = s_pts[w][j];
+                    const double dx = (double) q.x - lx, dy = (double) q.y - ly, dz = (double) q.z - lz;
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    too_close |= !(d2 > L.min_dist2);
+                }
+                const bool reject = __any_sync(0xffffffffu, too_close);
+                if (!reject) {
+                    if (lane == 0) {
+                        const float4 v = make_float4((float) lx, (float) ly, (float) lz, 0.f);
+                        s_pts[w][count] = v;
+                        gpts[count] = v;
+                    }
+                    ++count;
+                }
+                __syncwarp();
+            }
+            processed += m;
+        }
+        if (lane == 0) {
+            L.slots[slot].count = (uint32_t) count;
+            L.head[slot] = kNil;
+            if (count > count0) atomicAdd(&ctr->num_points, (unsigned long long) (count - count0));
+        }
+        __syncwarp();
+    }
+}
+
+// RemoveElementsFarFromLocation (map.h:305-322): a voxel goes when its FIRST stored point is farther than
+// `distance` from `location` (or when it is empty). Tombstones keep probe chains intact; Rebuild() purges them.
+__global__ void k_remove_far(MapLevel L, MapCounters *ctr, V3 loc, double distance) {
+    const uint32_t cap = L.cap_mask + 1;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+        const unsigned long long key = L.slots[s].key;
+        if (key == kEmptyKey || key == kTombKey) continue;
+        const uint32_t count = L.slots[s].count;
+        bool remove = (count == 0);
+        if (!remove) {
+            int vx, vy, vz;
+            unpack_voxel(key, vx, vy, vz);
+            const float4 p = L.points[(size_t) s * L.B];
+            const double dx = vx * L.res + (double) p.x - loc.x, dy = vy * L.res + (double) p.y - loc.y,
+                         dz = vz * L.res + (double) p.z - loc.z;
+            remove = sqrt(dx * dx + dy * dy + dz * dz) > distance;
+        }
+        if (remove) {
+            L.slots[s].key = kTombKey;
+            L.slots[s].count = 0;
+            atomicAdd(&ctr->num_tombs, 1u);
+            atomicSub(&ctr->num_voxels, 1u);
+            atomicAdd(&ctr->num_points, (unsigned long long) (-(long long) count));
+        }
+    }
+}
+
+// Re-hash the live voxels of `src` into the empty table `dst` (purges tombstones, optionally grows).
+__global__ void k_rebuild(MapLevel src, MapLevel dst, MapCounters *ctr) {
+    const uint32_t cap = src.cap_mask + 1;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+        const unsigned long long key = src.slots[s].key;
+        if (key == kEmptyKey || key == kTombKey) continue;
+        uint32_t h = hash_key(key) & dst.cap_mask;
+        for (uint32_t probe = 0; probe <= dst.cap_mask; ++probe) {
+            if (atomicCAS(&dst.slots[h].key, kEmptyKey, key) == kEmptyKey) break;
+            h = (h + 1) & dst.cap_mask;
+        }
+        const uint32_t count = src.slots[s].count;
+        dst.slots[h].count = count;
+        for (uint32_t j = 0; j < count; ++j) dst.points[(size_t) h * dst.B + j] = src.points[(size_t) s * src.B + j];
+    }
+    (void) ctr;
+}
+
+// Export: every stored point as fp64 world xyz + voxel coords + index within its voxel.
+__global__ void k_export(MapLevel L, unsigned long long *cursor, double *xyz, int *voxel, int *idx_in_voxel,
+                         unsigned long long cap_points) {
+    const uint32_t cap = L.cap_mask + 1;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+        const unsigned long long key = L.slots[s].key;
+        if (key == kEmptyKey || key == kTombKey) continue;
+        const uint32_t count = L.slots[s].count;
+        if (!count) continue;
+        int vx, vy, vz;
+        unpack_voxel(key, vx, vy, vz);
+        unsigned long long base = atomicAdd(cursor, (unsigned long long) count);
+        for (uint32_t j = 0; j < count; ++j) {
+            unsigned long long o = base + j;
+            if (o >= cap_points) break;
+            const float4 p = L.points[(size_t) s * L.B + j];
+            xyz[3 * o] = vx * L.res + (double) p.x;
+            xyz[3 * o + 1] = vy * L.res + (double) p.y;
+            xyz[3 * o + 2] = vz * L.res + (double) p.z;
+            voxel[3 * o] = vx; voxel[3 * o + 1] = vy; voxel[3 * o + 2] = vz;
+            idx_in_voxel[o] = (int) j;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static uint32_t NextPow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t) p;
+}
+
+DeviceMap::DeviceMap(const cticp_map_options &options, cudaStream_t stream) : options_(options), stream_(stream) {
+    if (options.num_resolutions < 1 || options.num_resolutions > CTICP_MAX_RESOLUTIONS)
+        throw std::invalid_argument("map_options.num_resolutions out of range");
+    levels_.resize(options.num_resolutions);
+    for (int i = 0; i < options.num_resolutions; ++i) {
+        const auto &rp = options.resolutions[i];
+        if (!(rp.resolution > 0) || rp.max_num_points < 1 || rp.max_num_points > kMaxB)
+            throw std::invalid_argument("map resolution / max_num_points out of the supported range (1..64)");
+        uint64_t cap = options.capacity_voxels ? options.capacity_voxels : (rp.resolution < 0.5 ? (1ull << 21) : (1ull << 20));
+        AllocLevel(levels_[i], NextPow2(std::max<uint64_t>(cap, 1024)), rp);
+    }
+    CT_CUDA_CHECK(cudaMalloc(&d_counters_, sizeof(MapCounters) * levels_.size()));
+    CT_CUDA_CHECK(cudaMemsetAsync(d_counters_, 0, sizeof(MapCounters) * levels_.size(), stream_));
+    CT_CUDA_CHECK(cudaMalloc(&d_scalar_, 64));
+    CT_CUDA_CHECK(cudaMallocHost(&h_counters_, sizeof(MapCounters) * CTICP_MAX_RESOLUTIONS));
+    memset(h_counters_, 0, sizeof(MapCounters) * CTICP_MAX_RESOLUTIONS);
+}
+
+DeviceMap::~DeviceMap() {
+    for (auto &L : levels_) FreeLevel(L);
+    cudaFree(d_counters_);
+    cudaFree(d_scalar_);
+    cudaFree(d_next_);
+    cudaFree(d_touched_);
+    cudaFree(d_world_tmp_);
+    cudaFreeHost(h_counters_);
+}
+
+void DeviceMap::AllocLevel(MapLevel &L, uint32_t cap, const cticp_resolution_param &rp) {
+    L.cap_mask = cap - 1;
+    L.B = rp.max_num_points;
+    L.res = rp.resolution;
+    L.min_dist2 = rp.min_distance_between_points * rp.min_distance_between_points;
+    CT_CUDA_CHECK(cudaMalloc(&L.slots, sizeof(MapSlot) * (size_t) cap));
+    CT_CUDA_CHECK(cudaMalloc(&L.points, sizeof(float4) * (size_t) cap * L.B));
+    CT_CUDA_CHECK(cudaMalloc(&L.head, sizeof(int) * (size_t) cap));
+    k_clear_level<<<592, 256, 0, stream_>>>(L);
+    CT_CUDA_CHECK(cudaGetLastError());
+}
+void DeviceMap::FreeLevel(MapLevel &L) {
+    cudaFree(L.slots);
+    cudaFree(L.points);
+    cudaFree(L.head);
+    L.slots = nullptr;
+    L.points = nullptr;
+    L.head = nullptr;
+}
+
+void DeviceMap::EnsureScratch(size_t n_upper) {
+    if (n_upper <= scratch_n_) return;
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    cudaFree(d_next_);
+    cudaFree(d_touched_);
+    size_t n = std::max<size_t>(n_upper, 1024);
+    CT_CUDA_CHECK(cudaMalloc(&d_next_, sizeof(int) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_touched_, sizeof(uint32_t) * n));
+    scratch_n_ = n;
+}
+
+void DeviceMap::InsertDevice(const double *d_world_xyz, const int *d_n, size_t n_upper) {
+    if (n_upper == 0) return;
+    EnsureScratch(n_upper);
+    const int threads = 256;
+    const int blocks = (int) std::min<size_t>((n_upper + threads - 1) / threads, 148 * 8);
+    for (size_t i = 0; i < levels_.size(); ++i) {
+        MapCounters *ctr = d_counters_ + i;
+        CT_CUDA_CHECK(cudaMemsetAsync(&ctr->num_touched, 0, sizeof(unsigned), stream_));
+        k_insert_claim<<<blocks, threads, 0, stream_>>>(levels_[i], ctr, d_world_xyz, d_n, d_next_, d_touched_);
+        const int cblocks = (int) std::min<size_t>((n_upper + kInsertWarps - 1) / kInsertWarps, 148 * 8);
+        k_insert_commit<<<cblocks, kInsertWarps * 32, 0, stream_>>>(levels_[i], ctr, d_world_xyz, d_next_, d_touched_);
+        launches_ += 2;
+    }
+    CT_CUDA_CHECK(cudaGetLastError());
+    dirty_ = true;
+}
+
+void DeviceMap::InsertHost(const double *xyz, size_t stride_bytes, size_t n) {
+    if (n == 0) return;
+    std::vector<double> packed(3 * n);
+    for (size_t i = 0; i < n; ++i) {
+        const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(xyz) + stride_bytes * i);
+        packed[3 * i] = p[0]; packed[3 * i + 1] = p[1]; packed[3 * i + 2] = p[2];
+    }
+    if (n > world_tmp_n_) {
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        cudaFree(d_world_tmp_);
+        CT_CUDA_CHECK(cudaMalloc(&d_world_tmp_, sizeof(double) * 3 * n));
+        world_tmp_n_ = n;
+    }
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_world_tmp_, packed.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream_));
+    int ni = (int) n;
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_scalar_, &ni, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    InsertDevice(d_world_tmp_, reinterpret_cast<int *>(d_scalar_), n);
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // `packed` / `ni` go out of scope
+    CheckOverflow();
+}
+
+void DeviceMap::RemoveFar(V3 location, double distance) {
+    for (size_t i = 0; i < levels_.size(); ++i) {
+        k_remove_far<<<592, 256, 0, stream_>>>(levels_[i], d_counters_ + i, location, distance);
+        launches_ += 1;
+    }
+    CT_CUDA_CHECK(cudaGetLastError());
+    dirty_ = true;
+}
+
+void DeviceMap::Clear() {
+    for (auto &L : levels_) k_clear_level<<<592, 256, 0, stream_>>>(L);
+    CT_CUDA_CHECK(cudaMemsetAsync(d_counters_, 0, sizeof(MapCounters) * levels_.size(), stream_));
+    CT_CUDA_CHECK(cudaGetLastError());
+    dirty_ = true;
+}
+
+const MapCounters *DeviceMap::SyncCounters() {
+    if (dirty_) {
+        CT_CUDA_CHECK(cudaMemcpyAsync(h_counters_, d_counters_, sizeof(MapCounters) * levels_.size(),
+                                      cudaMemcpyDeviceToHost, stream_));
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        dirty_ = false;
+        readback_pending_ = false;
+    } else if (readback_pending_) {
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        readback_pending_ = false;
+    }
+    return h_counters_;
+}
+
+void DeviceMap::QueueCounterReadback() {
+    CT_CUDA_CHECK(cudaMemcpyAsync(h_counters_, d_counters_, sizeof(MapCounters) * levels_.size(),
+                                  cudaMemcpyDeviceToHost, stream_));
+    dirty_ = false;   // valid after the next stream synchronisation
+    readback_pending_ = true;
+}
+
+void DeviceMap::CheckOverflow() {
+    const MapCounters *c = SyncCounters();
+    for (size_t i = 0; i < levels_.size(); ++i)
+        if (c[i].overflow) throw CapacityError("voxel table of map level " + std::to_string(i) + " is full");
+}
+
+// Purge tombstones / grow. Called by the odometry between frames with counters it already read back.
+void DeviceMap::MaintainTables() {
+    const MapCounters *c = h_counters_;
+    for (size_t i = 0; i < levels_.size(); ++i) {
+        const uint64_t cap = (uint64_t) levels_[i].cap_mask + 1;
+        const uint64_t used = (uint64_t) c[i].num_voxels + c[i].num_tombs;
+        if (c[i].overflow) throw CapacityError("voxel table of map level " + std::to_string(i) + " is full");
+        const bool grow = (uint64_t) c[i].num_voxels * 2 > cap;          // live load factor > 0.5
+        const bool purge = used * 10 > cap * 7 || c[i].num_tombs * 4ull > cap;   // probe chains getting long
+        if (!grow && !purge) continue;
+        MapLevel fresh{};
+        cticp_resolution_param rp = options_.resolutions[i];
+        AllocLevel(fresh, (uint32_t) (grow ? cap * 2 : cap), rp);
+        k_rebuild<<<592, 256, 0, stream_>>>(levels_[i], fresh, d_counters_ + i);
+        CT_CUDA_CHECK(cudaMemsetAsync(&(d_counters_ + i)->num_tombs, 0, sizeof(unsigned), stream_));
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        FreeLevel(levels_[i]);
+        levels_[i] = fresh;
+        h_counters_[i].num_tombs = 0;
+        ++rebuilds_;
+    }
+}
+
+void DeviceMap::SearchParams(double radius, int *level, int *voxel_neighborhood) const {
+    // SearchParamsFromRadiusSearch, map.h:416-432
+    int it = 0;
+    while (it < options_.num_resolutions && options_.resolutions[it].resolution <= radius) ++it;
+    int idx = std::max(0, it - 1);
+    *level = idx;
+    *voxel_neighborhood = (int) std::ceil(radius / options_.resolutions[idx].resolution);
+}
+
+size_t DeviceMap::Export(int level, std::vector<double> &xyz, std::vector<int> &voxels) {
+    const MapCounters *c = SyncCounters();
+    const size_t n = (size_t) c[level].num_points;
+    xyz.assign(3 * n, 0.0);
+    voxels.assign(3 * n, 0);
+    if (n == 0) return 0;
+    double *d_xyz;
+    int *d_vox, *d_idx;
+    unsigned long long *d_cursor;
+    CT_CUDA_CHECK(cudaMalloc(&d_xyz, sizeof(double) * 3 * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_vox, sizeof(int) * 3 * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_idx, sizeof(int) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_cursor, sizeof(unsigned long long)));
+    CT_CUDA_CHECK(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), stream_));
+    k_export<<<592, 256, 0, stream_>>>(levels_[level], d_cursor, d_xyz, d_vox, d_idx, n);
+    std::vector<double> hx(3 * n);
+    std::vector<int> hv(3 * n), hi(n);
+    CT_CUDA_CHECK(cudaMemcpyAsync(hx.data(), d_xyz, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, stream_));
+    CT_CUDA_CHECK(cudaMemcpyAsync(hv.data(), d_vox, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, stream_));
+    CT_CUDA_CHECK(cudaMemcpyAsync(hi.data(), d_idx, sizeof(int) * n, cudaMemcpyDeviceToHost, stream_));
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    cudaFree(d_xyz); cudaFree(d_vox); cudaFree(d_idx); cudaFree(d_cursor);
+    // deterministic order: (voxel x, y, z, index in voxel) — same as the oracle's sorted export
+    std::vector<size_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        for (int d = 0; d < 3; ++d)
+            if (hv[3 * a + d] != hv[3 * b + d]) return hv[3 * a + d] < hv[3 * b + d];
+        return hi[a] < hi[b];
+    });
+    for (size_t o = 0; o < n; ++o) {
+        size_t s = order[o];
+        for (int d = 0; d < 3; ++d) {
+            xyz[3 * o + d] = hx[3 * s + d];
+            voxels[3 * o + d] = hv[3 * s + d];
+        }
+    }
+    return n;
+}
+
+}  // namespace cticp

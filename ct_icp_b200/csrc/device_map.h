@@ -1,0 +1,80 @@
+// device_map.h — host-side owner of the device-resident voxel map (see device_map.cuh for the layout).
+#pragma once
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/cticp.h"
+#include "device_map.cuh"
+
+namespace cticp {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct CapacityError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+class DeviceMap {
+public:
+    DeviceMap(const cticp_map_options &options, cudaStream_t stream);
+    ~DeviceMap();
+    DeviceMap(const DeviceMap &) = delete;
+    DeviceMap &operator=(const DeviceMap &) = delete;
+
+    // InsertPointCloud (map.h:153-254): world points (fp64 xyz triples) already on the device, count on the device
+    void InsertDevice(const double *d_world_xyz, const int *d_n, size_t n_upper);
+    // same from strided host memory (synchronous; used by the cticp_map_* test entry points)
+    void InsertHost(const double *xyz, size_t stride_bytes, size_t n);
+    // RemoveElementsFarFromLocation (map.h:305-322)
+    void RemoveFar(V3 location, double distance);
+    void Clear();
+
+    // counters (synchronises the stream when stale)
+    const MapCounters *SyncCounters();
+    // enqueue the D2H of the counters; they are valid after the caller's next stream synchronisation
+    void QueueCounterReadback();
+    const MapCounters *HostCounters() const { return h_counters_; }
+    void NotifyStreamSynchronized() { readback_pending_ = false; }
+    void CheckOverflow();
+    // tombstone purge / growth, driven by HostCounters(); call between frames
+    void MaintainTables();
+
+    // SearchParamsFromRadiusSearch (map.h:416-432)
+    void SearchParams(double radius, int *level, int *voxel_neighborhood) const;
+    const MapLevel &Level(int i) const { return levels_[i]; }
+    int NumLevels() const { return (int) levels_.size(); }
+    const cticp_map_options &Options() const { return options_; }
+    cudaStream_t Stream() const { return stream_; }
+
+    // GetMapPoints (map.h:354-376) in (voxel, insertion) order; returns the point count
+    size_t Export(int level, std::vector<double> &xyz, std::vector<int> &voxels);
+
+    int launches() const { return launches_; }
+    int rebuilds() const { return rebuilds_; }
+
+private:
+    void AllocLevel(MapLevel &L, uint32_t cap, const cticp_resolution_param &rp);
+    void FreeLevel(MapLevel &L);
+    void EnsureScratch(size_t n_upper);
+
+    cticp_map_options options_;
+    cudaStream_t stream_;
+    std::vector<MapLevel> levels_;
+    MapCounters *d_counters_ = nullptr;
+    MapCounters *h_counters_ = nullptr;   // pinned
+    void *d_scalar_ = nullptr;
+    int *d_next_ = nullptr;
+    uint32_t *d_touched_ = nullptr;
+    size_t scratch_n_ = 0;
+    double *d_world_tmp_ = nullptr;
+    size_t world_tmp_n_ = 0;
+    bool dirty_ = true;
+    bool readback_pending_ = false;
+    int launches_ = 0;
+    int rebuilds_ = 0;
+};
+
+}  // namespace cticp

@@ -1,0 +1,600 @@
+// engine.cu — host orchestration of the B200-native odometry (see engine.h).
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace cticp {
+
+#define CT_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                            std::to_string(__LINE__));                                                   \
+    } while (0)
+
+using hclock = std::chrono::steady_clock;
+static double ms_since(hclock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(hclock::now() - t0).count();
+}
+
+HostPose PoseFromC(const cticp_pose &c) {
+    HostPose p;
+    p.pose.q = Q4{c.quat[0], c.quat[1], c.quat[2], c.quat[3]};
+    p.pose.t = V3{c.tr[0], c.tr[1], c.tr[2]};
+    p.ref_timestamp = c.ref_timestamp;
+    p.dest_timestamp = c.dest_timestamp;
+    p.ref_frame_id = c.ref_frame_id;
+    p.dest_frame_id = c.dest_frame_id;
+    return p;
+}
+cticp_pose PoseToC(const HostPose &p) {
+    cticp_pose c;
+    c.quat[0] = p.pose.q.x; c.quat[1] = p.pose.q.y; c.quat[2] = p.pose.q.z; c.quat[3] = p.pose.q.w;
+    c.tr[0] = p.pose.t.x; c.tr[1] = p.pose.t.y; c.tr[2] = p.pose.t.z;
+    c.ref_timestamp = p.ref_timestamp;
+    c.dest_timestamp = p.dest_timestamp;
+    c.ref_frame_id = p.ref_frame_id;
+    c.dest_frame_id = p.dest_frame_id;
+    return c;
+}
+HostFrame FrameFromC(const cticp_frame &c) { return HostFrame{PoseFromC(c.begin_pose), PoseFromC(c.end_pose)}; }
+cticp_frame FrameToC(const HostFrame &f) { return cticp_frame{PoseToC(f.begin_pose), PoseToC(f.end_pose)}; }
+
+// TPose::GetAlphaTimestamp, include/SlamCore/types.h:192-219 (incl. the "t > max → 0" quirk)
+static double AlphaTimestamp(double t, double begin_ts, double end_ts) {
+    const double mn = std::min(begin_ts, end_ts), mx = std::max(begin_ts, end_ts);
+    if (mn > t) return 0.0;
+    if (mx < t) return 0.0;
+    if (mn == mx) return 1.0;
+    return (t - mn) / (mx - mn);
+}
+static double EgoAngularDistance(const HostFrame &f) { return angular_distance_deg(f.begin_pose.pose.q, f.end_pose.pose.q); }
+
+// ---------------------------------------------------------------------------------------------------------------
+Engine::Engine(const cticp_odometry_options &options, int device) : options_(options), device_(device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+        throw std::runtime_error("NO_DEVICE");
+    CT_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw std::runtime_error("NO_DEVICE: this build targets sm_100a (Blackwell B200) only");
+
+    // Odometry::Odometry, odometry.cpp:697-734: motion_compensation overrides the ICP parametrisation
+    switch (options_.motion_compensation) {
+        case CTICP_MC_CONTINUOUS:
+            options_.ct_icp_options.point_to_plane_with_distortion = 1;
+            options_.ct_icp_options.parametrization = CTICP_PARAM_CONTINUOUS_TIME;
+            options_.ct_icp_options.distance = CTICP_DIST_POINT_TO_PLANE;
+            break;
+        default:
+            throw UnsupportedError("motion_compensation other than CONTINUOUS is outside the built hot path (SURVEY §8)");
+    }
+    if (options_.ct_icp_options.solver == CTICP_SOLVER_ROBUST)
+        throw UnsupportedError("solver ROBUST is SURVEY §8f-1 (not built yet)");
+    if (options_.sampling == CTICP_SAMPLING_ADAPTIVE)
+        throw UnsupportedError("sampling ADAPTIVE is SURVEY §8f-3 (not built yet)");
+    next_robust_level_ = options_.robust_minimal_level;
+
+    CT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    map_ = std::make_unique<DeviceMap>(options_.map_options, stream_);
+    const size_t max_pts = options_.max_points_per_frame ? (size_t) options_.max_points_per_frame : (size_t) 524288;
+    pipe_ = std::make_unique<FramePipeline>(max_pts, stream_);
+    icp_ = std::make_unique<IcpSolver>(stream_);
+    CT_CUDA_CHECK(cudaMalloc(&d_state_, sizeof(IcpState)));
+    CT_CUDA_CHECK(cudaMallocHost(&h_state_, sizeof(IcpState)));
+    CT_CUDA_CHECK(cudaMalloc(&d_kp_world_, sizeof(double) * 3 * max_pts));
+    for (auto &e : ev_) CT_CUDA_CHECK(cudaEventCreate(&e));
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    icp_.reset();
+    pipe_.reset();
+    map_.reset();
+    cudaFree(d_state_);
+    cudaFreeHost(h_state_);
+    cudaFree(d_kp_world_);
+    for (auto &e : ev_) cudaEventDestroy(e);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Engine::Reset() {   // odometry.cpp:956-965
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    trajectory_.clear();
+    map_->Clear();
+    registered_frames_ = 0;
+    robust_num_consecutive_failures_ = 0;
+    suspect_registration_error_ = false;
+    next_robust_level_ = 0;
+    tracker_ = {};
+    default_motion_model_ = MotionModel();
+    last_all_world_valid_ = last_kp_world_valid_ = false;
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+int64_t Engine::MapSize() {
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    return (int64_t) map_->SyncCounters()[0].num_points;   // NumPoints(): resolution 0 only (map.h:345)
+}
+
+// InitializeMotion, odometry.cpp:276-330
+void Engine::InitializeMotion(const FrameInfo &info, const cticp_frame *initial_estimate) {
+    if (initial_estimate) {
+        trajectory_.push_back(FrameFromC(*initial_estimate));
+        return;
+    }
+    const int k = info.registered_fid;
+    trajectory_.emplace_back();
+    auto &T = trajectory_;
+    T[k].begin_pose.dest_timestamp = info.begin_timestamp;
+    T[k].begin_pose.dest_frame_id = info.frame_id;
+    T[k].end_pose.dest_timestamp = info.end_timestamp;
+    T[k].end_pose.dest_frame_id = info.frame_id;
+    if (k <= 1) return;
+    const bool cv = options_.initialization == CTICP_INIT_CONSTANT_VELOCITY;
+    if (k == 2) {
+        if (cv) {
+            T[k].begin_pose.pose = T[k - 1].end_pose.pose;
+            T[k].end_pose.pose = se3_mul(se3_mul(T[k - 1].end_pose.pose, se3_inverse(T[k - 2].end_pose.pose)), T[k - 1].end_pose.pose);
+        } else {
+            T[k].begin_pose.pose = T[k - 1].begin_pose.pose;
+            T[k].end_pose.pose = T[k].begin_pose.pose;
+        }
+        return;
+    }
+    if (cv) {
+        // CONTINUOUS: extrapolate the begin pose from the previous begin poses (:311-317)
+        T[k].begin_pose.pose = se3_mul(se3_mul(T[k - 1].begin_pose.pose, se3_inverse(T[k - 2].begin_pose.pose)), T[k - 1].begin_pose.pose);
+        T[k].end_pose.pose = se3_mul(se3_mul(T[k - 1].end_pose.pose, se3_inverse(T[k - 2].end_pose.pose)), T[k - 1].end_pose.pose);
+    } else {
+        T[k].begin_pose.pose = T[k - 1].end_pose.pose;
+        T[k].end_pose.pose = T[k - 1].end_pose.pose;
+    }
+}
+
+// InitializeFrame, odometry.cpp:333-382 — host part: pack (x, y, z, alpha) into pinned memory; device part:
+// shuffle / sub_sample_frame / timestamp override / shuffle.
+void Engine::IngestAndSubSample(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+                                const FrameInfo &info) {
+    const int k = info.registered_fid;
+    const HostFrame &tr = trajectory_[k];
+    const double bts = tr.begin_pose.dest_timestamp, ets = tr.end_pose.dest_timestamp;
+    // TPose::InterpolatePose CHECK (types.h:456): begin <= t <= end for every timestamp that gets interpolated
+    const double t_lo = (k <= 1) ? info.end_timestamp : info.begin_timestamp, t_hi = info.end_timestamp;
+    if (!(bts <= t_lo && t_hi <= ets))
+        throw TimestampError("The timestamp cannot be interpolated between the two poses");
+    if (n > pipe_->MaxPoints()) throw CapacityError("scan has more points than max_points_per_frame");
+
+    float4 *stage = pipe_->Staging();
+    const double mn = std::min(bts, ets), mx = std::max(bts, ets);
+    const double inv = (mx > mn) ? 1.0 / (mx - mn) : 0.0;
+    const char *px = reinterpret_cast<const char *>(xyz), *pt = reinterpret_cast<const char *>(t);
+    for (size_t i = 0; i < n; ++i) {
+        const double *p = reinterpret_cast<const double *>(px + i * xyz_stride);
+        const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
+        // GetAlphaTimestamp (types.h:192-219); timestamps were range-checked above
+        const double a = (mx > mn) ? (ti - mn) * inv : 1.0;
+        stage[i] = make_float4((float) p[0], (float) p[1], (float) p[2], (float) a);
+    }
+    pipe_->Upload(n);
+    const double sample_size = k < options_.init_num_frames ? options_.init_voxel_size : options_.voxel_size;
+    // frames 0 and 1: every timestamp := end_timestamp (odometry.cpp:355-359)
+    const bool override_alpha = (k <= 1);
+    const float alpha_value = (float) AlphaTimestamp(info.end_timestamp, bts, ets);
+    pipe_->SubSampleFrame(sample_size, options_.shuffle_seed, ShuffleCounter(k, 0), ShuffleCounter(k, 1),
+                          override_alpha, alpha_value);
+}
+
+// TryRegister, odometry.cpp:525-601
+void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summary &rs, double sample_voxel_size,
+                         const MotionModel *mm, int attempt_idx) {
+    const int k = info.registered_fid;
+    const bool at_startup = k < options_.init_num_frames;
+    auto t0 = hclock::now();
+    pipe_->SampleKeypoints(options_.sampling, sample_voxel_size,
+                           (!at_startup && options_.max_num_keypoints > 0) ? options_.max_num_keypoints : -1,
+                           options_.shuffle_seed, ShuffleCounter(k, 2 + attempt_idx));
+    rs.t_sampling = ms_since(t0);
+    if (at_startup) {
+        options.threshold_voxel_occupancy = 1;
+        options.num_iters_icp = std::max(options.num_iters_icp, 15);
+    }
+    // registration state → device
+    IcpState &S = *h_state_;
+    memset(&S, 0, sizeof(S));
+    const Q4 qb = qnormalized(rs.frame.begin_pose.pose.q), qe = qnormalized(rs.frame.end_pose.pose.q);
+    S.qb[0] = qb.x; S.qb[1] = qb.y; S.qb[2] = qb.z; S.qb[3] = qb.w;
+    S.qe[0] = qe.x; S.qe[1] = qe.y; S.qe[2] = qe.z; S.qe[3] = qe.w;
+    const V3 tb = rs.frame.begin_pose.pose.t, te = rs.frame.end_pose.pose.t;
+    S.tb[0] = tb.x; S.tb[1] = tb.y; S.tb[2] = tb.z;
+    S.te[0] = te.x; S.te[1] = te.y; S.te[2] = te.z;
+    if (mm && mm->present) {
+        S.has_motion_model = 1;
+        S.beta_location = mm->options.beta_location_consistency;
+        S.beta_cv = mm->options.beta_constant_velocity;
+        S.beta_small = mm->options.beta_small_velocity;
+        S.beta_orientation = mm->options.beta_orientation_consistency;
+        const auto &pf = mm->previous_frame;
+        S.prev_tb[0] = pf.begin_pose.pose.t.x; S.prev_tb[1] = pf.begin_pose.pose.t.y; S.prev_tb[2] = pf.begin_pose.pose.t.z;
+        S.prev_te[0] = pf.end_pose.pose.t.x; S.prev_te[1] = pf.end_pose.pose.t.y; S.prev_te[2] = pf.end_pose.pose.t.z;
+        S.prev_qe[0] = pf.end_pose.pose.q.x; S.prev_qe[1] = pf.end_pose.pose.q.y; S.prev_qe[2] = pf.end_pose.pose.q.z;
+        S.prev_qe[3] = pf.end_pose.pose.q.w;
+    }
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_state_, h_state_, sizeof(IcpState), cudaMemcpyHostToDevice, stream_));
+    CT_CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
+    switch (options.solver) {
+        case CTICP_SOLVER_GN:
+            icp_->EnqueueGaussNewton(*map_, options, pipe_->d_keypoints(), pipe_->d_count_keypoints(), pipe_->n(),
+                                     options.num_iters_icp, d_state_, shard_rank_, shard_world_, nccl_comm_);
+            break;
+        case CTICP_SOLVER_CERES:
+            icp_->EnqueueCeres(*map_, options, options_.neighborhood_strategy, pipe_->d_keypoints(),
+                               pipe_->d_count_keypoints(), pipe_->n(), d_state_, shard_rank_, shard_world_, nccl_comm_);
+            break;
+        default:
+            throw UnsupportedError("Unsupported Solver Type");
+    }
+    CT_CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
+    CT_CUDA_CHECK(cudaMemcpyAsync(h_state_, d_state_, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
+    pipe_->QueueCountsReadback();
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    icp_->CollectGatherTiming();
+
+    rs.sample_size = pipe_->h_counts()[2];
+    rs.icp.success = !S.failed;
+    rs.icp.num_residuals_used = S.n_used;
+    rs.icp.num_iters = S.iter;
+    rs.success = rs.icp.success;
+    rs.number_of_residuals = S.n_used;
+    timing_.icp_iterations += S.iter;
+    timing_.gather_keypoint_iterations += S.stat_keypoint_iters;
+    timing_.gather_stencil_points += S.stat_stencil_points;
+    // the reference optimises frame_to_optimize in place, so even a failed ICP leaves its partial update behind
+    rs.frame.begin_pose.pose.q = Q4{S.qb[0], S.qb[1], S.qb[2], S.qb[3]};
+    rs.frame.end_pose.pose.q = Q4{S.qe[0], S.qe[1], S.qe[2], S.qe[3]};
+    rs.frame.begin_pose.pose.t = V3{S.tb[0], S.tb[1], S.tb[2]};
+    rs.frame.end_pose.pose.t = V3{S.te[0], S.te[1], S.te[2]};
+    if (!rs.success) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "[CT_ICP]Error : not enough keypoints selected in ct-icp ! Number_of_residuals : %d",
+                 S.n_used);
+        rs.error_message = buf;
+    }
+}
+
+// AssessRegistration, odometry.cpp:604-684
+bool Engine::AssessRegistration(Summary &s) const {
+    if (s.relative_distance > options_.distance_error_threshold) return false;
+    if (s.relative_orientation > options_.orientation_error_threshold ||
+        s.ego_orientation > options_.orientation_error_threshold)
+        return false;
+    bool success = s.success;
+    if (options_.robust_registration) {
+        if (s.robust_level == 0 && (s.relative_orientation > options_.robust_threshold_relative_orientation ||
+                                    s.ego_orientation > options_.robust_threshold_ego_orientation)) {
+            if (s.robust_level < options_.robust_num_attempts_when_rotation) {
+                s.error_message = "Large rotations require at a robust_level of at least 1 (got:" +
+                                  std::to_string(s.robust_level) + ").";
+                return false;
+            }
+        }
+        if (s.relative_distance > options_.robust_relative_trans_threshold) {
+            s.error_message = "The relative distance is too important";
+            return false;
+        }
+    }
+    return success;
+}
+
+// RobustRegistration + RobustRegistrationAttempt, odometry.cpp:780-852, 996-1050
+void Engine::RobustRegistration(const FrameInfo &info, Summary &rs, const MotionModel *mm) {
+    const int k = info.registered_fid;
+    const HostFrame initial_estimate = rs.frame;
+    cticp_icp_options reg = options_.ct_icp_options;
+    int robust_level = 0;
+    double sample_voxel_size = k < options_.init_num_frames ? options_.init_sample_voxel_size : options_.sample_voxel_size;
+    Summary attempt = rs;
+    attempt.number_of_attempts = 0;
+    auto increase = [&]() {   // IncreaseRobustnessLevel, :996-1018
+        const double min_voxel_size = std::min(options_.init_voxel_size, options_.voxel_size);
+        attempt.frame = initial_estimate;
+        reg.ls_max_num_iters += 30;
+        if (reg.max_num_residuals > 0) reg.max_num_residuals = reg.max_num_residuals * 2;
+        reg.num_iters_icp = std::min(reg.num_iters_icp + 20, 50);
+        reg.threshold_orientation_norm = std::max(reg.threshold_orientation_norm / 10, 1.e-5);
+        reg.threshold_translation_norm = std::max(reg.threshold_orientation_norm / 10, 1.e-4);
+        sample_voxel_size = std::max(options_.sample_voxel_size / 1.5, double(min_voxel_size));
+        reg.ls_sigma *= 1.2;
+        reg.max_dist_to_plane_ct_icp *= 1.5;
+        robust_level++;
+    };
+    while (robust_level < next_robust_level_) increase();
+    bool good_enough = false;
+    int attempt_idx = 0;
+    do {
+        TryRegister(info, reg, attempt, sample_voxel_size, mm, attempt_idx++);
+        if (k > 0) {
+            const auto &prev = trajectory_[k - 1];
+            const V3 d = attempt.frame.begin_pose.pose.t - prev.end_pose.pose.t;
+            attempt.distance_correction = norm(d);
+            attempt.relative_orientation = angular_distance_deg(prev.end_pose.pose.q, attempt.frame.end_pose.pose.q);
+            attempt.ego_orientation = EgoAngularDistance(attempt.frame);
+        }
+        attempt.relative_distance = norm(attempt.frame.end_pose.pose.t - attempt.frame.begin_pose.pose.t);
+        good_enough = AssessRegistration(attempt);
+        attempt.number_of_attempts++;
+        if (!good_enough) {
+            if (attempt.number_of_attempts < options_.robust_num_attempts)
+                increase();
+            else
+                good_enough = true;
+        }
+    } while (!good_enough);
+    rs = attempt;
+    if (rs.number_of_attempts > options_.robust_num_attempts)
+        robust_num_consecutive_failures_++;
+    else
+        robust_num_consecutive_failures_ = 0;
+}
+
+// ComputeSummaryMetrics, odometry.cpp:978-988
+void Engine::ComputeSummaryMetrics(Summary &s, int k) {
+    if (k > 0) {
+        const auto &cur = trajectory_[k];
+        const auto &prev = trajectory_[k - 1];
+        s.distance_correction = norm(cur.begin_pose.pose.t - prev.end_pose.pose.t);
+        s.relative_orientation = angular_distance_deg(prev.end_pose.pose.q, cur.end_pose.pose.q);
+        s.relative_distance = norm(prev.end_pose.pose.t - cur.end_pose.pose.t);
+        s.ego_orientation = EgoAngularDistance(cur);
+    }
+}
+
+// UpdateMap, odometry.cpp:855-953
+void Engine::UpdateMap(Summary &s, int registered_fid) {
+    bool add_points = true;
+    if (options_.robust_registration) {
+        suspect_registration_error_ = s.number_of_attempts >= options_.robust_num_attempts;
+        if (s.ego_orientation > options_.robust_threshold_ego_orientation ||
+            s.relative_orientation > options_.robust_threshold_relative_orientation)
+            add_points = false;
+        if (suspect_registration_error_) add_points |= (robust_num_consecutive_failures_ > 5);
+        next_robust_level_ = add_points ? options_.robust_minimal_level : options_.robust_minimal_level + 1;
+        if (!s.success)
+            next_robust_level_ = options_.robust_minimal_level + 2;
+        else {
+            if (s.relative_orientation > options_.robust_threshold_relative_orientation ||
+                s.ego_orientation > options_.robust_threshold_ego_orientation)
+                next_robust_level_ = options_.robust_minimal_level + 1;
+            if (s.number_of_attempts > 1) next_robust_level_ = options_.robust_minimal_level + 1;
+        }
+    } else {
+        tracker_.cum_orientation += s.relative_orientation;
+        tracker_.cum_distance += s.relative_distance;
+        if (tracker_.total_insertions > 0) {
+            if (s.ego_orientation > options_.insertion_ego_rotation_threshold)
+                add_points = tracker_.skipped_frames > options_.insertion_threshold_frames_skipped;
+            else
+                add_points = true;
+        }
+    }
+    s.points_added = add_points;
+    if (options_.do_no_insert) add_points = false;
+    if (options_.always_insert) add_points = true;
+
+    const V3 location = trajectory_.back().end_pose.pose.t;
+    map_->RemoveFar(location, options_.max_distance);
+    if (add_points) {
+        map_->InsertDevice(pipe_->d_frame_world(), pipe_->d_count_frame(), pipe_->n());
+        tracker_.skipped_frames = 0;
+        tracker_.cum_orientation = 0;
+        tracker_.cum_distance = 0;
+        tracker_.total_insertions++;
+        (void) registered_fid;
+    } else
+        tracker_.skipped_frames++;
+    map_->QueueCounterReadback();
+}
+
+// RegisterFrame / RegisterFrameWithEstimate (odometry.cpp:199-236) → DoRegister (:386-501)
+void Engine::RegisterFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+                           uint32_t frame_id, const cticp_frame *initial_estimate, cticp_summary *out) {
+    auto t_start = hclock::now();
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    if (n == 0 || !xyz || !t) throw std::invalid_argument("The registered frame cannot be empty");
+    // compute_frame_info, odometry.cpp:186-196
+    FrameInfo info;
+    {
+        double mn = INFINITY, mx = -INFINITY;
+        const char *pt = reinterpret_cast<const char *>(t);
+        for (size_t i = 0; i < n; ++i) {
+            const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
+            mn = ti < mn ? ti : mn;
+            mx = ti > mx ? ti : mx;
+        }
+        info.begin_timestamp = mn;
+        info.end_timestamp = mx;
+    }
+    info.registered_fid = registered_frames_++;
+    info.frame_id = frame_id;
+    const int k = info.registered_fid;
+    InitializeMotion(info, initial_estimate);
+    const double t_init_motion = ms_since(t_start);
+
+    // the previous frame's map update has been enqueued; its counters tell whether the tables need maintenance
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    map_->NotifyStreamSynchronized();
+    map_->MaintainTables();
+
+    memset(&timing_, 0, sizeof(timing_));
+    icp_->reset_timing();
+    const int launches0 = map_->launches() + pipe_->launches() + icp_->launches();
+    last_all_world_valid_ = last_kp_world_valid_ = false;
+
+    CT_CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
+    IngestAndSubSample(xyz, xyz_stride, t, t_stride, n, info);
+    const double t_initialization = ms_since(t_start);
+
+    Summary summary;
+    summary.frame = trajectory_.back();
+    summary.initial_frame = summary.frame;
+    bool early_return = false;
+    bool ran_icp = false;
+    if (k > 0) {
+        const MotionModel *mm = nullptr;
+        if (options_.with_default_motion_model) {   // odometry.cpp:412-417
+            default_motion_model_.present = true;
+            default_motion_model_.options = options_.default_motion_model;
+            default_motion_model_.previous_frame = trajectory_[k - 1];
+            mm = &default_motion_model_;
+        }
+        ran_icp = true;
+        if (options_.robust_registration) {
+            RobustRegistration(info, summary, mm);
+        } else {
+            cticp_icp_options ct_icp_options = options_.ct_icp_options;
+            const double sample_voxel_size = k < options_.init_num_frames ? options_.init_sample_voxel_size
+                                                                          : options_.sample_voxel_size;
+            auto t0 = hclock::now();
+            TryRegister(info, ct_icp_options, summary, sample_voxel_size, mm, 0);
+            summary.t_try_register = ms_since(t0);
+            // NB trajectory_[k] is still the INITIAL estimate here (odometry.cpp:429-431)
+            summary.relative_orientation = angular_distance_deg(trajectory_[k - 1].end_pose.pose.q, trajectory_[k].end_pose.pose.q);
+            summary.ego_orientation = EgoAngularDistance(summary.frame);
+            summary.relative_distance = norm(summary.frame.end_pose.pose.t - summary.frame.begin_pose.pose.t);
+            if (!AssessRegistration(summary)) {
+                summary.success = false;
+                if (options_.quit_on_error) early_return = true;
+            }
+        }
+        if (!early_return) trajectory_[k] = summary.frame;
+    } else {
+        CT_CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
+        CT_CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
+        pipe_->QueueCountsReadback();
+    }
+    last_frame_ = summary.frame;
+    last_info_ = info;
+
+    auto t_before_map = hclock::now();
+    if (!early_return) {
+        const auto &f = summary.frame;
+        pipe_->TransformFrame(f.begin_pose.pose.q, f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t);
+        ComputeSummaryMetrics(summary, k);
+        UpdateMap(summary, k);
+    }
+    CT_CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
+    if (!ran_icp) CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // frame 0: counts for the summary
+
+    timing_.kernel_launches = map_->launches() + pipe_->launches() + icp_->launches() - launches0;
+    if (out) {
+        FillSummary(summary, out);
+        out->num_all_corrected_points = n;
+        out->num_corrected_points = (uint64_t) pipe_->h_counts()[1];
+        out->num_keypoints = ran_icp ? (uint64_t) pipe_->h_counts()[2] : 0;
+        out->odometry_total = ms_since(t_start);
+        out->odometry_initialization = t_initialization + 0 * t_init_motion;
+        out->odometry_try_register = summary.t_try_register;
+        out->odometry_duration_sampling = summary.t_sampling;
+        out->odometry_map_update = ms_since(t_before_map);
+        out->odometry_transform = 0;
+    }
+}
+
+void Engine::FillSummary(const Summary &s, cticp_summary *out) const {
+    memset(out, 0, sizeof(*out));
+    out->frame = FrameToC(s.frame);
+    out->initial_frame = FrameToC(s.initial_frame);
+    out->icp_summary = s.icp;
+    out->sample_size = s.sample_size;
+    out->number_of_residuals = s.number_of_residuals;
+    out->robust_level = s.robust_level;
+    out->success = s.success;
+    out->points_added = s.points_added;
+    out->number_of_attempts = s.number_of_attempts;
+    out->distance_correction = s.distance_correction;
+    out->relative_distance = s.relative_distance;
+    out->relative_orientation = s.relative_orientation;
+    out->ego_orientation = s.ego_orientation;
+    snprintf(out->error_message, sizeof(out->error_message), "%s", s.error_message.c_str());
+}
+
+cticp_device_timing Engine::LastTiming() {
+    cudaSetDevice(device_);
+    cudaEventSynchronize(ev_[3]);
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, ev_[0], ev_[1]);
+    cudaEventElapsedTime(&b, ev_[1], ev_[2]);
+    cudaEventElapsedTime(&c, ev_[2], ev_[3]);
+    cudaEventElapsedTime(&d, ev_[0], ev_[3]);
+    timing_.ingest_ms = a;
+    timing_.icp_ms = b;
+    timing_.map_update_ms = c;
+    timing_.total_ms = d;
+    timing_.gather_ms = icp_->gather_ms();
+    return timing_;
+}
+
+// RegistrationSummary::{corrected_points, all_corrected_points, keypoints} on demand
+int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    const float4 *d_pts = nullptr;
+    const double *d_world = nullptr;
+    size_t count = 0;
+    const auto &f = last_frame_;
+    switch (which) {
+        case CTICP_POINTS_CORRECTED:
+            d_pts = pipe_->d_frame();
+            d_world = pipe_->d_frame_world();
+            count = (size_t) pipe_->h_counts()[1];
+            break;
+        case CTICP_POINTS_ALL_CORRECTED:
+            if (!last_all_world_valid_) {
+                pipe_->TransformAll(f.begin_pose.pose.q, f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t);
+                last_all_world_valid_ = true;
+            }
+            d_pts = pipe_->d_raw();
+            d_world = pipe_->d_all_world();
+            count = pipe_->n();
+            break;
+        case CTICP_POINTS_KEYPOINTS:
+            count = last_info_.registered_fid > 0 ? (size_t) pipe_->h_counts()[2] : 0;
+            if (count && !last_kp_world_valid_) {
+                pipe_->TransformInto(pipe_->d_keypoints(), pipe_->d_count_keypoints(), f.begin_pose.pose.q,
+                                     f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t, d_kp_world_);
+                last_kp_world_valid_ = true;
+            }
+            d_pts = pipe_->d_keypoints();
+            d_world = d_kp_world_;
+            break;
+        default:
+            throw std::invalid_argument("which");
+    }
+    const size_t m = std::min(cap, count);
+    if (m == 0 || !dst) return (int64_t) count;
+    std::vector<float4> hp(m);
+    std::vector<double> hw(3 * m);
+    CT_CUDA_CHECK(cudaMemcpyAsync(hp.data(), d_pts, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream_));
+    CT_CUDA_CHECK(cudaMemcpyAsync(hw.data(), d_world, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, stream_));
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    const double bts = f.begin_pose.dest_timestamp, ets = f.end_pose.dest_timestamp;
+    const double mn = std::min(bts, ets), mx = std::max(bts, ets);
+    for (size_t i = 0; i < m; ++i) {
+        cticp_wpoint &o = dst[i];
+        o.raw[0] = hp[i].x; o.raw[1] = hp[i].y; o.raw[2] = hp[i].z;
+        o.timestamp = mn + (double) hp[i].w * (mx - mn);
+        o.world[0] = hw[3 * i]; o.world[1] = hw[3 * i + 1]; o.world[2] = hw[3 * i + 2];
+        o.index_frame = last_info_.frame_id;
+        o._pad0 = 0;
+    }
+    return (int64_t) count;
+}
+
+}  // namespace cticp

@@ -1,0 +1,126 @@
+// engine.h — host orchestration of one odometry instance: the B200-native ct_icp::Odometry.
+//
+// Mirrors the control flow of src/ct_icp/odometry.cpp (RegisterFrame :199-214, InitializeMotion :276-330,
+// InitializeFrame :333-382, DoRegister :386-501, TryRegister :525-601, AssessRegistration :604-684,
+// RobustRegistration :780-852, UpdateMap :855-953) while every O(N)/O(K·S) stage runs on the device.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cticp.h"
+#include "device_map.h"
+#include "frame_pipeline.h"
+#include "icp.h"
+
+namespace cticp {
+
+struct UnsupportedError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct TimestampError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct HostPose {   // slam::TPose<double>
+    Se3 pose = se3_identity();
+    double ref_timestamp = 0, dest_timestamp = -1;
+    uint32_t ref_frame_id = 0, dest_frame_id = uint32_t(-1);
+};
+struct HostFrame {   // ct_icp::TrajectoryFrame
+    HostPose begin_pose, end_pose;
+};
+
+class Engine {
+public:
+    Engine(const cticp_odometry_options &options, int device);
+    ~Engine();
+
+    void RegisterFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+                       uint32_t frame_id, const cticp_frame *initial_estimate, cticp_summary *out);
+    int64_t GetPoints(int which, cticp_wpoint *dst, size_t cap);
+    const std::vector<HostFrame> &Trajectory() const { return trajectory_; }
+    int64_t MapSize();
+    void Reset();
+    DeviceMap &Map() { return *map_; }
+    IcpSolver &Solver() { return *icp_; }
+    cudaStream_t Stream() const { return stream_; }
+    int Device() const { return device_; }
+    cticp_device_timing LastTiming();   // synchronises on the last frame's final event
+    void SetTimeGather(bool on) { icp_->set_time_gather(on); }
+    void EnableSharding(const void *unique_id, int rank, int world);
+
+private:
+    struct FrameInfo {
+        int registered_fid = -1;
+        uint32_t frame_id = uint32_t(-1);
+        double begin_timestamp = -1, end_timestamp = -1;
+    };
+    struct Summary {   // RegistrationSummary minus the point vectors
+        HostFrame frame, initial_frame;
+        int sample_size = 0, number_of_residuals = 0, robust_level = 0;
+        double distance_correction = 0, relative_distance = 0, relative_orientation = 0, ego_orientation = 0;
+        bool success = true, points_added = false;
+        int number_of_attempts = 0;
+        std::string error_message;
+        cticp_icp_summary icp{};
+        double t_try_register = 0, t_sampling = 0;
+    };
+    struct MotionModel {
+        bool present = false;
+        cticp_motion_model_options options{};
+        HostFrame previous_frame;
+    };
+
+    void InitializeMotion(const FrameInfo &info, const cticp_frame *initial_estimate);
+    void IngestAndSubSample(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+                            const FrameInfo &info);
+    void TryRegister(const FrameInfo &info, cticp_icp_options &options, Summary &rs, double sample_voxel_size,
+                     const MotionModel *mm, int attempt_idx);
+    bool AssessRegistration(Summary &s) const;
+    void RobustRegistration(const FrameInfo &info, Summary &rs, const MotionModel *mm);
+    void ComputeSummaryMetrics(Summary &s, int k);
+    void UpdateMap(Summary &s, int registered_fid);
+    void FillSummary(const Summary &s, cticp_summary *out) const;
+    static uint64_t ShuffleCounter(int registered_fid, int purpose) {
+        return (uint64_t(uint32_t(registered_fid)) << 8) | uint64_t(purpose & 0xff);
+    }
+
+    cticp_odometry_options options_;
+    int device_;
+    cudaStream_t stream_ = nullptr;
+    std::unique_ptr<DeviceMap> map_;
+    std::unique_ptr<FramePipeline> pipe_;
+    std::unique_ptr<IcpSolver> icp_;
+    IcpState *d_state_ = nullptr;
+    IcpState *h_state_ = nullptr;   // pinned
+    std::vector<HostFrame> trajectory_;
+    MotionModel default_motion_model_;
+    int registered_frames_ = 0;
+    int robust_num_consecutive_failures_ = 0;
+    bool suspect_registration_error_ = false;
+    int next_robust_level_ = 0;
+    struct {
+        double cum_distance = 0, cum_orientation = 0;
+        int skipped_frames = 0, total_insertions = 0;
+    } tracker_;
+    // state of the last registered frame (for GetPoints)
+    HostFrame last_frame_;
+    FrameInfo last_info_;
+    bool last_all_world_valid_ = false, last_kp_world_valid_ = false;
+    double *d_kp_world_ = nullptr;
+    // timing
+    cticp_device_timing timing_{};
+    cudaEvent_t ev_[6];
+    // multi-GPU
+    void *nccl_comm_ = nullptr;
+    int shard_rank_ = 0, shard_world_ = 1;
+};
+
+// conversions shared with capi.cu
+HostPose PoseFromC(const cticp_pose &c);
+cticp_pose PoseToC(const HostPose &p);
+HostFrame FrameFromC(const cticp_frame &c);
+cticp_frame FrameToC(const HostFrame &f);
+
+}  // namespace cticp

@@ -1,0 +1,298 @@
+// frame_pipeline.cu — per-scan device pipeline around the ICP: ingest, voxel sub-sampling, keypoint grid sampling,
+// continuous-time transform of the frame.
+//
+// Reference: Odometry::InitializeFrame (src/ct_icp/odometry.cpp:333-382), sub_sample_frame / grid_sampling
+// (src/ct_icp/ct_icp.cpp:65-101), the post-registration transforms (odometry.cpp:463-486).
+//
+// Order contract: std::shuffle + "first point seen per voxel" becomes
+//   winner(voxel) = argmin over the voxel's points of perm(i)        [64-bit atomicMin on (perm(i) << 32 | i)]
+//   output order  = ascending perm(i) of the winners                   [flag array in permuted index space + scan]
+// and the second shuffle is one scatter through a second permutation — no sort anywhere.
+#include "frame_pipeline.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace cticp {
+
+#define CT_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                            std::to_string(__LINE__));                                                   \
+    } while (0)
+
+constexpr unsigned long long kGridEmpty = ~0ull;
+
+// voxel key of sub_sample_frame: static_cast<short>(raw / size) per axis (ct_icp.cpp:70-72)
+__device__ __forceinline__ unsigned long long short_voxel_key(const float4 &p, double voxel_size) {
+    const short x = (short) (int) ((double) p.x / voxel_size);
+    const short y = (short) (int) ((double) p.y / voxel_size);
+    const short z = (short) (int) ((double) p.z / voxel_size);
+    return ((unsigned long long) (unsigned short) x << 32) | ((unsigned long long) (unsigned short) y << 16) |
+           (unsigned long long) (unsigned short) z;
+}
+
+// claim: every point bids (priority, index) for its voxel
+__global__ void k_grid_claim(const float4 *__restrict__ pts, const int *__restrict__ d_n, double voxel_size,
+                             int use_perm, uint64_t seed, uint64_t counter, unsigned long long *keys,
+                             unsigned long long *vals, uint32_t cap_mask, int *__restrict__ slot_of) {
+    const int n = *d_n;
+    const Perm perm = perm_make(seed, counter, (uint32_t) max(n, 1));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = short_voxel_key(pts[i], voxel_size);
+        const uint32_t prio = use_perm ? perm_apply(perm, (uint32_t) i) : (uint32_t) i;
+        uint32_t h = hash_key(key) & cap_mask;
+        while (true) {
+            unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&keys[h]);
+            if (k == kGridEmpty) k = atomicCAS(&keys[h], kGridEmpty, key);
+            if (k == kGridEmpty || k == key) break;
+            h = (h + 1) & cap_mask;
+        }
+        atomicMin(&vals[h], ((unsigned long long) prio << 32) | (unsigned) i);
+        slot_of[i] = (int) h;
+    }
+}
+// mark: winners raise a flag at their position in the permuted order
+__global__ void k_grid_mark(const int *__restrict__ d_n, int use_perm, uint64_t seed, uint64_t counter,
+                            const unsigned long long *__restrict__ vals, const int *__restrict__ slot_of,
+                            uint32_t *__restrict__ flags, uint32_t *__restrict__ src) {
+    const int n = *d_n;
+    const Perm perm = perm_make(seed, counter, (uint32_t) max(n, 1));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t prio = use_perm ? perm_apply(perm, (uint32_t) i) : (uint32_t) i;
+        const unsigned long long mine = ((unsigned long long) prio << 32) | (unsigned) i;
+        if (vals[slot_of[i]] == mine) {
+            flags[prio] = 1u;
+            src[prio] = (uint32_t) i;
+        }
+    }
+}
+// exclusive scan of flags[0..n) by one CTA; total → *d_total
+__global__ void __launch_bounds__(1024) k_scan_flags(const uint32_t *__restrict__ flags, const int *__restrict__ d_n,
+                                                      uint32_t *__restrict__ offsets, int *__restrict__ d_total) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int n = *d_n;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024 * 4) {
+        // 4 consecutive elements per thread
+        const int i0 = base + tid * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? flags[i0 + k] : 0u;
+        const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t ws = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += y;
+            }
+            s_warp[lane] = ws;   // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        uint32_t excl = carry + (w > 0 ? s_warp[w - 1] : 0u) + (incl - tsum);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < n) offsets[i0 + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) *d_total = (int) s_carry;
+}
+// emit: compact winners in permuted order, optionally scatter through a second permutation (second shuffle)
+__global__ void k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_index,
+                            const int *__restrict__ d_n, const uint32_t *__restrict__ flags,
+                            const uint32_t *__restrict__ src, const uint32_t *__restrict__ offsets,
+                            const int *__restrict__ d_total, int use_perm2, uint64_t seed, uint64_t counter2,
+                            int override_alpha, float alpha_value, float4 *__restrict__ out,
+                            uint32_t *__restrict__ out_src_index) {
+    const int n = *d_n;
+    const int total = *d_total;
+    const Perm perm2 = perm_make(seed, counter2, (uint32_t) max(total, 1));
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        if (!flags[p]) continue;
+        const uint32_t j = offsets[p];
+        const uint32_t dst = (use_perm2 && total > 1) ? perm_apply(perm2, j) : j;
+        const uint32_t i = src[p];
+        float4 v = pts[i];
+        if (override_alpha) v.w = alpha_value;
+        out[dst] = v;
+        out_src_index[dst] = in_src_index ? in_src_index[i] : i;
+    }
+}
+// keypoints = frame (sampling NONE, odometry.cpp:546)
+__global__ void k_copy_points(const float4 *__restrict__ in, const uint32_t *__restrict__ in_src,
+                              const int *__restrict__ d_n, float4 *__restrict__ out, uint32_t *__restrict__ out_src,
+                              int *__restrict__ d_n_out) {
+    const int n = *d_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        out[i] = in[i];
+        out_src[i] = in_src[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_n_out = n;
+}
+// max_num_keypoints: shuffle + resize (odometry.cpp:549-552) when *d_n > max_n
+__global__ void k_truncate_shuffle(const float4 *__restrict__ in, const uint32_t *__restrict__ in_src,
+                                   const int *__restrict__ d_n, int max_n, uint64_t seed, uint64_t counter,
+                                   float4 *__restrict__ out, uint32_t *__restrict__ out_src) {
+    const int n = *d_n;
+    const bool active = n > max_n;
+    const Perm perm = perm_make(seed, counter, (uint32_t) max(n, 1));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t d = active ? perm_apply(perm, (uint32_t) i) : (uint32_t) i;
+        if (!active || (int) d < max_n) {
+            out[d] = in[i];
+            out_src[d] = in_src[i];
+        }
+    }
+}
+__global__ void k_clamp_count(int *d_n, int max_n) {
+    if (*d_n > max_n) *d_n = max_n;
+}
+// world = ContinuousTransform(raw, begin, end, alpha) for every point (odometry.cpp:463-486)
+__global__ void k_transform_points(const float4 *__restrict__ pts, const int *__restrict__ d_n, Q4 qb, V3 tb, Q4 qe,
+                                   V3 te, double *__restrict__ world) {
+    const int n = *d_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = pts[i];
+        const V3 w = ct_transform(qb, tb, qe, te, (double) p.w, V3{(double) p.x, (double) p.y, (double) p.z});
+        world[3 * i] = w.x; world[3 * i + 1] = w.y; world[3 * i + 2] = w.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static uint32_t NextPow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t) p;
+}
+
+FramePipeline::FramePipeline(size_t max_points, cudaStream_t stream) : stream_(stream), max_points_(max_points) {
+    const size_t n = max_points_;
+    grid_cap_ = std::max<uint32_t>(NextPow2(2 * n), 1024);
+    CT_CUDA_CHECK(cudaMallocHost(&h_stage_, sizeof(float4) * n));
+    CT_CUDA_CHECK(cudaMallocHost(&h_counts_, sizeof(int) * 8));
+    CT_CUDA_CHECK(cudaMalloc(&d_raw_, sizeof(float4) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_frame_, sizeof(float4) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_keypoints_, sizeof(float4) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_tmp_points_, sizeof(float4) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_frame_src_, sizeof(uint32_t) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_kp_src_, sizeof(uint32_t) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_tmp_src_, sizeof(uint32_t) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_grid_, sizeof(unsigned long long) * 2 * (size_t) grid_cap_));
+    CT_CUDA_CHECK(cudaMalloc(&d_slot_of_, sizeof(int) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_flags_, sizeof(uint32_t) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_src_, sizeof(uint32_t) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_offsets_, sizeof(uint32_t) * n));
+    CT_CUDA_CHECK(cudaMalloc(&d_counts_, sizeof(int) * 8));
+    CT_CUDA_CHECK(cudaMalloc(&d_frame_world_, sizeof(double) * 3 * n));
+    CT_CUDA_CHECK(cudaMemsetAsync(d_counts_, 0, sizeof(int) * 8, stream_));
+    memset(h_counts_, 0, sizeof(int) * 8);
+}
+FramePipeline::~FramePipeline() {
+    cudaFreeHost(h_stage_); cudaFreeHost(h_counts_);
+    cudaFree(d_raw_); cudaFree(d_frame_); cudaFree(d_keypoints_); cudaFree(d_tmp_points_);
+    cudaFree(d_frame_src_); cudaFree(d_kp_src_); cudaFree(d_tmp_src_);
+    cudaFree(d_grid_); cudaFree(d_slot_of_); cudaFree(d_flags_); cudaFree(d_src_); cudaFree(d_offsets_);
+    cudaFree(d_counts_); cudaFree(d_frame_world_); cudaFree(d_all_world_);
+}
+
+int FramePipeline::Blocks(size_t n) const { return (int) std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 148 * 8)); }
+
+void FramePipeline::Upload(size_t n) {
+    if (n > max_points_) throw CapacityError("scan has more points than max_points_per_frame");
+    n_ = n;
+    h_counts_[0] = (int) n;
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_raw_, h_stage_, sizeof(float4) * n, cudaMemcpyHostToDevice, stream_));
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_counts_, h_counts_, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    h2d_bytes_ = sizeof(float4) * n + sizeof(int);
+}
+
+void FramePipeline::GridSelect(const float4 *in, const uint32_t *in_src, const int *d_n_in, size_t n_upper,
+                               double voxel_size, int use_perm1, uint64_t seed, uint64_t c1, int use_perm2,
+                               uint64_t c2, int override_alpha, float alpha_value, float4 *out, uint32_t *out_src,
+                               int *d_n_out) {
+    unsigned long long *keys = d_grid_, *vals = d_grid_ + grid_cap_;
+    const uint32_t cap = std::max<uint32_t>(NextPow2(2 * n_upper), 1024);   // only the prefix that can be touched
+    CT_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * cap, stream_));
+    CT_CUDA_CHECK(cudaMemsetAsync(vals, 0xFF, sizeof(unsigned long long) * cap, stream_));
+    CT_CUDA_CHECK(cudaMemsetAsync(d_flags_, 0, sizeof(uint32_t) * n_upper, stream_));
+    const int blocks = Blocks(n_upper);
+    k_grid_claim<<<blocks, 256, 0, stream_>>>(in, d_n_in, voxel_size, use_perm1, seed, c1, keys, vals, cap - 1, d_slot_of_);
+    k_grid_mark<<<blocks, 256, 0, stream_>>>(d_n_in, use_perm1, seed, c1, vals, d_slot_of_, d_flags_, d_src_);
+    k_scan_flags<<<1, 1024, 0, stream_>>>(d_flags_, d_n_in, d_offsets_, d_n_out);
+    k_grid_emit<<<blocks, 256, 0, stream_>>>(in, in_src, d_n_in, d_flags_, d_src_, d_offsets_, d_n_out, use_perm2, seed,
+                                             c2, override_alpha, alpha_value, out, out_src);
+    launches_ += 4;
+    CT_CUDA_CHECK(cudaGetLastError());
+}
+
+void FramePipeline::SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2,
+                                   bool override_alpha, float alpha_value) {
+    GridSelect(d_raw_, nullptr, d_counts_ + 0, n_, voxel_size, 1, seed, counter1, 1, counter2, override_alpha ? 1 : 0,
+               alpha_value, d_frame_, d_frame_src_, d_counts_ + 1);
+}
+
+void FramePipeline::SampleKeypoints(int sampling, double sample_voxel_size, int max_num_keypoints, uint64_t seed,
+                                    uint64_t counter) {
+    if (sampling == CTICP_SAMPLING_GRID) {
+        GridSelect(d_frame_, d_frame_src_, d_counts_ + 1, n_, sample_voxel_size, 0, 0, 0, 0, 0, 0, 0.f, d_keypoints_,
+                   d_kp_src_, d_counts_ + 2);
+    } else {
+        k_copy_points<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_frame_src_, d_counts_ + 1, d_keypoints_, d_kp_src_,
+                                                       d_counts_ + 2);
+        launches_ += 1;
+    }
+    if (max_num_keypoints > 0) {
+        k_truncate_shuffle<<<Blocks(n_), 256, 0, stream_>>>(d_keypoints_, d_kp_src_, d_counts_ + 2, max_num_keypoints,
+                                                            seed, counter, d_tmp_points_, d_tmp_src_);
+        k_clamp_count<<<1, 1, 0, stream_>>>(d_counts_ + 2, max_num_keypoints);
+        std::swap(d_keypoints_, d_tmp_points_);
+        std::swap(d_kp_src_, d_tmp_src_);
+        launches_ += 2;
+    }
+    CT_CUDA_CHECK(cudaGetLastError());
+}
+
+void FramePipeline::QueueCountsReadback() {
+    CT_CUDA_CHECK(cudaMemcpyAsync(h_counts_, d_counts_, sizeof(int) * 4, cudaMemcpyDeviceToHost, stream_));
+}
+
+void FramePipeline::TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te) {
+    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_counts_ + 1, qb, tb, qe, te, d_frame_world_);
+    launches_ += 1;
+    CT_CUDA_CHECK(cudaGetLastError());
+}
+
+void FramePipeline::TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te) {
+    if (!d_all_world_) CT_CUDA_CHECK(cudaMalloc(&d_all_world_, sizeof(double) * 3 * max_points_));
+    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(d_raw_, d_counts_ + 0, qb, tb, qe, te, d_all_world_);
+    launches_ += 1;
+    CT_CUDA_CHECK(cudaGetLastError());
+}
+
+void FramePipeline::TransformInto(const float4 *pts, const int *d_n, const Q4 &qb, const V3 &tb, const Q4 &qe,
+                                  const V3 &te, double *d_world) {
+    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(pts, d_n, qb, tb, qe, te, d_world);
+    launches_ += 1;
+    CT_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace cticp

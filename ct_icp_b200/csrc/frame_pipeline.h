@@ -1,0 +1,80 @@
+// frame_pipeline.h — device buffers and kernels of one scan's journey: pinned staging → raw float4 → sub-sampled
+// frame → keypoints → world-space frame (for the map). See frame_pipeline.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_map.h"
+#include "se3.cuh"
+
+namespace cticp {
+
+class FramePipeline {
+public:
+    FramePipeline(size_t max_points, cudaStream_t stream);
+    ~FramePipeline();
+    FramePipeline(const FramePipeline &) = delete;
+    FramePipeline &operator=(const FramePipeline &) = delete;
+
+    // pinned staging buffer the host packs (x, y, z, alpha) into, then Upload(n) enqueues the H2D copy
+    float4 *Staging() { return h_stage_; }
+    size_t MaxPoints() const { return max_points_; }
+    void Upload(size_t n);
+
+    // Odometry::InitializeFrame: shuffle → sub_sample_frame → (frames 0,1: timestamp := end) → shuffle
+    void SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2, bool override_alpha,
+                        float alpha_value);
+    // TryRegister: grid_sampling | NONE, then the optional max_num_keypoints shuffle-truncate
+    void SampleKeypoints(int sampling, double sample_voxel_size, int max_num_keypoints, uint64_t seed, uint64_t counter);
+    // world points of the sub-sampled frame / of every input point with the final pose pair
+    void TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
+    void TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
+    void TransformInto(const float4 *pts, const int *d_n, const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te,
+                       double *d_world);
+
+    void QueueCountsReadback();   // h_counts()[0..2] = N, F, K after the next stream sync
+    const int *h_counts() const { return h_counts_; }
+
+    const float4 *d_raw() const { return d_raw_; }
+    const float4 *d_frame() const { return d_frame_; }
+    const float4 *d_keypoints() const { return d_keypoints_; }
+    float4 *d_keypoints_mut() { return d_keypoints_; }
+    const uint32_t *d_frame_src() const { return d_frame_src_; }
+    const uint32_t *d_keypoints_src() const { return d_kp_src_; }
+    const double *d_frame_world() const { return d_frame_world_; }
+    const double *d_all_world() const { return d_all_world_; }
+    int *d_count_n() { return d_counts_ + 0; }
+    int *d_count_frame() { return d_counts_ + 1; }
+    int *d_count_keypoints() { return d_counts_ + 2; }
+    size_t n() const { return n_; }
+    size_t h2d_bytes() const { return h2d_bytes_; }
+    int launches() const { return launches_; }
+
+    // generic "first-seen per voxel" selection (also behind cticp_grid_sample_indices)
+    void GridSelect(const float4 *in, const uint32_t *in_src, const int *d_n_in, size_t n_upper, double voxel_size,
+                    int use_perm1, uint64_t seed, uint64_t c1, int use_perm2, uint64_t c2, int override_alpha,
+                    float alpha_value, float4 *out, uint32_t *out_src, int *d_n_out);
+    float4 *d_raw_mut() { return d_raw_; }
+    float4 *d_frame_mut() { return d_frame_; }
+    uint32_t *d_frame_src_mut() { return d_frame_src_; }
+
+private:
+    int Blocks(size_t n) const;
+
+    cudaStream_t stream_;
+    size_t max_points_, n_ = 0, h2d_bytes_ = 0;
+    uint32_t grid_cap_ = 0;
+    float4 *h_stage_ = nullptr;
+    int *h_counts_ = nullptr;
+    float4 *d_raw_ = nullptr, *d_frame_ = nullptr, *d_keypoints_ = nullptr, *d_tmp_points_ = nullptr;
+    uint32_t *d_frame_src_ = nullptr, *d_kp_src_ = nullptr, *d_tmp_src_ = nullptr;
+    unsigned long long *d_grid_ = nullptr;
+    int *d_slot_of_ = nullptr;
+    uint32_t *d_flags_ = nullptr, *d_src_ = nullptr, *d_offsets_ = nullptr;
+    int *d_counts_ = nullptr;
+    double *d_frame_world_ = nullptr, *d_all_world_ = nullptr;
+    int launches_ = 0;
+};
+
+}  // namespace cticp

@@ -1,0 +1,261 @@
+// gather.cuh — warp-cooperative neighbor gather for one query point (the hot inner loop).
+//
+// Replaces MultipleResolutionVoxelMap::RadiusSearchInPlace (include/ct_icp/map.h:449-514, called through
+// ComputeNeighborhoodInPlace :527-530 with sensor_location == nullptr) and TNeighborhood::ComputeNeighborhood +
+// ComputeNeighborhoodInfo (include/SlamCore/experimental/neighborhood.h:226-257, 286-316).
+//
+// One warp per query:
+//   * lanes probe the (2r+1)^3 stencil voxels in parallel (one 16-byte slot load each, x→y→z order like :470-472);
+//   * every occupied voxel's points are read as one coalesced run of float4 (<= B*16 bytes);
+//   * distances are evaluated in fp64 from the fp32 voxel-local offsets; in-radius candidates are compacted into a
+//     64-entry shared-memory staging buffer by ballot/popc;
+//   * the k nearest are kept in a register-resident sorted list (one entry per lane) maintained with a bitonic
+//     sort/merge network over warp shuffles; ties resolve to the earlier-scanned point (strict `<` at :495).
+// Lane l ends with the l-th nearest neighbor; the reference's points[0] (the FARTHEST kept, :508-513) is lane n-1.
+#pragma once
+#include "device_map.cuh"
+
+namespace cticp {
+
+struct KnnEntry {
+    double d2;        // squared distance (fp64)
+    int seq;          // scan order: stencil index * 64 + index in voxel
+    uint32_t addr;    // index into MapLevel::points
+};
+
+struct __align__(16) KnnStage {
+    double d2;
+    int seq;
+    uint32_t addr;
+};
+
+constexpr double kKnnInf = 1e300;
+
+__device__ __forceinline__ bool knn_less(const KnnEntry &a, const KnnEntry &b) {
+    return a.d2 < b.d2 || (a.d2 == b.d2 && a.seq < b.seq);
+}
+__device__ __forceinline__ KnnEntry knn_shfl_xor(const KnnEntry &e, int mask) {
+    KnnEntry o;
+    o.d2 = __shfl_xor_sync(0xffffffffu, e.d2, mask);
+    o.seq = __shfl_xor_sync(0xffffffffu, e.seq, mask);
+    o.addr = __shfl_xor_sync(0xffffffffu, e.addr, mask);
+    return o;
+}
+__device__ __forceinline__ void knn_cmpx(KnnEntry &e, int lane, int j, bool keep_min) {
+    const KnnEntry o = knn_shfl_xor(e, j);
+    const bool o_less = knn_less(o, e);
+    if (o_less == keep_min) e = o;
+}
+// full bitonic sort of 32 entries (one per lane), ascending by (d2, seq)
+__device__ __forceinline__ void knn_sort32(KnnEntry &e, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool up = ((lane & k) == 0) || (k == 32);
+            const bool lower = ((lane & j) == 0);
+            knn_cmpx(e, lane, j, lower == up);
+        }
+    }
+}
+// best (ascending) ← 32 smallest of best ∪ chunk (chunk ascending)
+__device__ __forceinline__ void knn_merge32(KnnEntry &best, const KnnEntry &chunk, int lane) {
+    KnnEntry rev;
+    rev.d2 = __shfl_sync(0xffffffffu, chunk.d2, 31 - lane);
+    rev.seq = __shfl_sync(0xffffffffu, chunk.seq, 31 - lane);
+    rev.addr = __shfl_sync(0xffffffffu, chunk.addr, 31 - lane);
+    if (knn_less(rev, best)) best = rev;   // bitonic sequence holding the 32 smallest
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) knn_cmpx(best, lane, j, (lane & j) == 0);
+}
+
+struct GatherConfig {
+    MapLevel L;
+    int r;              // voxel_neighborhood (stencil radius in voxels)
+    double radius2;     // search radius squared
+    int kmax;           // max_number_neighbors (<= 32)
+};
+
+// stencil index → voxel offset, x outermost / z innermost (map.h:470-472)
+__device__ __forceinline__ void stencil_offset(int s, int r, int &dx, int &dy, int &dz) {
+    const int side = 2 * r + 1;
+    dx = s / (side * side) - r;
+    dy = (s / side) % side - r;
+    dz = s % side - r;
+}
+
+// Returns the number of neighbors kept (<= kmax); lane l < n holds the l-th nearest in `best`.
+// stage: 64 KnnStage entries of shared memory private to this warp.
+__device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const V3 &q, int lane, KnnStage *stage,
+                                               KnnEntry &best, unsigned &stencil_points) {
+    const MapLevel &L = G.L;
+    const int side = 2 * G.r + 1;
+    const int nst = side * side * side;
+    const int kx = voxel_coord(q.x, L.res), ky = voxel_coord(q.y, L.res), kz = voxel_coord(q.z, L.res);
+    best.d2 = kKnnInf;
+    best.seq = 0x7fffffff;
+    best.addr = 0;
+    int fill = 0;
+    unsigned pts_total = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (int base = 0; base < nst; base += 32) {
+        const int s = base + lane;
+        int slot = -1;
+        uint32_t cnt = 0;
+        if (s < nst) {
+            int dx, dy, dz;
+            stencil_offset(s, G.r, dx, dy, dz);
+            slot = map_find(L, pack_voxel(kx + dx, ky + dy, kz + dz), &cnt);
+            if (slot < 0) cnt = 0;
+        }
+        pts_total += __reduce_add_sync(0xffffffffu, cnt);
+        unsigned occ = __ballot_sync(0xffffffffu, cnt > 0);
+        while (occ) {
+            const int src = __ffs(occ) - 1;
+            occ &= occ - 1;
+            const int vslot = __shfl_sync(0xffffffffu, slot, src);
+            const int vcnt = (int) __shfl_sync(0xffffffffu, cnt, src);
+            const int vs = base + src;
+            int dx, dy, dz;
+            stencil_offset(vs, G.r, dx, dy, dz);
+            // voxel origin relative to the query (fp64)
+            const double ox = (kx + dx) * L.res - q.x, oy = (ky + dy) * L.res - q.y, oz = (kz + dz) * L.res - q.z;
+            const float4 *vp = L.points + (size_t) vslot * L.B;
+            for (int j0 = 0; j0 < vcnt; j0 += 32) {
+                const int j = j0 + lane;
+                const bool valid = j < vcnt;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) p = __ldg(vp + j);
+                const double rx = ox + (double) p.x, ry = oy + (double) p.y, rz = oz + (double) p.z;
+                const double d2 = rx * rx + ry * ry + rz * rz;
+                const bool in = valid && !(d2 > G.radius2);
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    KnnStage e;
+                    e.d2 = d2;
+                    e.seq = vs * 64 + j;
+                    e.addr = (uint32_t) ((size_t) vslot * L.B + j);
+                    stage[fill + __popc(m & lt_mask)] = e;
+                }
+                fill += __popc(m);
+                __syncwarp();
+                if (fill >= 32) {
+                    const KnnStage t = stage[lane];
+                    KnnEntry c{t.d2, t.seq, t.addr};
+                    knn_sort32(c, lane);
+                    knn_merge32(best, c, lane);
+                    KnnStage rest = stage[32 + lane];   // garbage beyond fill-32 is never read back
+                    __syncwarp();
+                    stage[lane] = rest;
+                    fill -= 32;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    if (fill > 0) {
+        KnnEntry c{kKnnInf, 0x7fffffff, 0};
+        if (lane < fill) {
+            const KnnStage t = stage[lane];
+            c = KnnEntry{t.d2, t.seq, t.addr};
+        }
+        knn_sort32(c, lane);
+        knn_merge32(best, c, lane);
+    }
+    __syncwarp();
+    stencil_points = pts_total;
+    const int found = __popc(__ballot_sync(0xffffffffu, best.d2 < kKnnInf));
+    return found < G.kmax ? found : G.kmax;
+}
+
+// Neighbor position relative to the query, fp64, recomputed from the entry (stencil index in seq, offset at addr).
+__device__ __forceinline__ V3 knn_rel_position(const GatherConfig &G, const V3 &q, const KnnEntry &e) {
+    const MapLevel &L = G.L;
+    const int kx = voxel_coord(q.x, L.res), ky = voxel_coord(q.y, L.res), kz = voxel_coord(q.z, L.res);
+    int dx, dy, dz;
+    stencil_offset(e.seq >> 6, G.r, dx, dy, dz);
+    const float4 p = __ldg(L.points + e.addr);
+    return V3{((kx + dx) * L.res - q.x) + (double) p.x, ((ky + dy) * L.res - q.y) + (double) p.y,
+              ((kz + dz) * L.res - q.z) + (double) p.z};
+}
+
+// ---- 3x3 symmetric eigen-decomposition (cyclic Jacobi, fp64, registers only) ---------------------------------
+// Stand-in for Eigen::JacobiSVD<Matrix3d>(C, ComputeFullV) on a symmetric matrix (neighborhood.h:293): singular
+// values = |eigenvalues| descending, normal = V.col(2).
+#define CT_JACOBI_ROT(app, aqq, apq, arp, arq, v0p, v0q, v1p, v1q, v2p, v2q)          \
+    if (apq != 0.0) {                                                                 \
+        const double theta = (aqq - app) / (2.0 * apq);                               \
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;                          \
+        app -= t * apq;                                                               \
+        aqq += t * apq;                                                               \
+        apq = 0.0;                                                                    \
+        { const double x = arp, y = arq; arp = c * x - s * y; arq = s * x + c * y; }  \
+        { const double x = v0p, y = v0q; v0p = c * x - s * y; v0q = s * x + c * y; }  \
+        { const double x = v1p, y = v1q; v1p = c * x - s * y; v1q = s * x + c * y; }  \
+        { const double x = v2p, y = v2q; v2p = c * x - s * y; v2q = s * x + c * y; }  \
+    }
+
+struct Eig3 {
+    double sv0, sv1, sv2;   // |eigenvalues| descending
+    V3 normal;              // eigenvector of sv2
+};
+
+__device__ __forceinline__ Eig3 sym_eig3(double a00, double a01, double a02, double a11, double a12, double a22) {
+    double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = a01 * a01 + a02 * a02 + a12 * a12;
+        const double diag = a00 * a00 + a11 * a11 + a22 * a22;
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        CT_JACOBI_ROT(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21)   // (p,q)=(0,1), r=2
+        CT_JACOBI_ROT(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22)   // (0,2), r=1
+        CT_JACOBI_ROT(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22)   // (1,2), r=0
+    }
+    double e0 = fabs(a00), e1 = fabs(a11), e2 = fabs(a22);
+    V3 c0{v00, v10, v20}, c1{v01, v11, v21}, c2{v02, v12, v22};
+    // sort descending (stable like std::sort on 3 elements is irrelevant: values differ in practice)
+    if (e0 < e1) { double t = e0; e0 = e1; e1 = t; V3 tv = c0; c0 = c1; c1 = tv; }
+    if (e1 < e2) { double t = e1; e1 = e2; e2 = t; V3 tv = c1; c1 = c2; c2 = tv; }
+    if (e0 < e1) { double t = e0; e0 = e1; e1 = t; V3 tv = c0; c0 = c1; c1 = tv; }
+    return Eig3{e0, e1, e2, c2};
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct NeighborhoodDesc {
+    V3 normal;       // unit normal (sign arbitrary)
+    double a2D;
+    V3 far_rel;      // farthest kept neighbor relative to the query (= reference points[0] - query)
+    double far_d2;
+};
+
+// TNeighborhood::ComputeNeighborhood + ComputeNeighborhoodInfo on the n neighbors held one-per-lane.
+// Covariance is accumulated CENTRED ON THE QUERY (the reference's uncentred E[xx^T]-mu mu^T in world coordinates,
+// neighborhood.h:237-244, is the same quantity up to its own fp64 cancellation error).
+__device__ __forceinline__ NeighborhoodDesc warp_describe(const GatherConfig &G, const V3 &q, const KnnEntry &best,
+                                                          int n, int lane) {
+    V3 rel{0, 0, 0};
+    if (lane < n) rel = knn_rel_position(G, q, best);
+    const double inv = 1.0 / (double) n;
+    const double mx = warp_sum(rel.x) * inv, my = warp_sum(rel.y) * inv, mz = warp_sum(rel.z) * inv;
+    const double cxx = warp_sum(rel.x * rel.x) * inv - mx * mx, cxy = warp_sum(rel.x * rel.y) * inv - mx * my,
+                 cxz = warp_sum(rel.x * rel.z) * inv - mx * mz, cyy = warp_sum(rel.y * rel.y) * inv - my * my,
+                 cyz = warp_sum(rel.y * rel.z) * inv - my * mz, czz = warp_sum(rel.z * rel.z) * inv - mz * mz;
+    const Eig3 e = sym_eig3(cxx, cxy, cxz, cyy, cyz, czz);
+    NeighborhoodDesc d;
+    d.normal = e.normal;
+    d.a2D = (sqrt(e.sv1) - sqrt(e.sv2)) / sqrt(e.sv0);
+    d.far_rel.x = __shfl_sync(0xffffffffu, rel.x, n - 1);
+    d.far_rel.y = __shfl_sync(0xffffffffu, rel.y, n - 1);
+    d.far_rel.z = __shfl_sync(0xffffffffu, rel.z, n - 1);
+    d.far_d2 = __shfl_sync(0xffffffffu, best.d2, n - 1);
+    return d;
+}
+
+}  // namespace cticp

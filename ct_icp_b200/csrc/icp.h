@@ -1,0 +1,94 @@
+// icp.h — device-side state and host-side driver of the registration solvers (GN now; CERES-as-LM in icp_lm.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/cticp.h"
+#include "device_map.h"
+
+namespace cticp {
+
+constexpr int kAcc = 96;            // accumulator width: 78 (A upper) + 12 (b) + 6 stats
+constexpr int kAccUsed = 90;        // n keypoints used
+constexpr int kAccSumSq = 91;       // Σ scalar²
+constexpr int kAccStencil = 92;     // Σ map points inside the stencils
+constexpr int kAccKeypoints = 93;   // keypoints visited
+constexpr int kAccValidNb = 94;     // keypoints with >= min neighbors
+
+// Everything one ICP needs across iterations lives on the device so that all iterations can be enqueued without a
+// host round trip (the reference's loop, src/ct_icp/ct_icp.cpp:745-981, is sequential on the host).
+struct IcpState {
+    double qb[4], tb[3], qe[4], te[3];     // pose pair being optimised (quat x,y,z,w)
+    double prev_tb[3], prev_te[3];         // PreviousFrameMotionModel state (previous frame begin / end translation)
+    double prev_qe[4];
+    double beta_location, beta_cv, beta_small, beta_orientation;
+    int has_motion_model;
+    int iter;            // iterations executed
+    int done;            // convergence or failure: later launches become no-ops
+    int failed;          // "not enough keypoints" (ct_icp.cpp:860-871)
+    int n_used;          // residuals of the last linearisation
+    int n_keypoints;     // keypoints visited in the last iteration
+    double x_norm;       // ‖x‖ of the last GN step
+    unsigned long long stat_keypoint_iters, stat_stencil_points;
+};
+
+struct GnParams {
+    int r;                      // stencil radius (voxels)
+    int level;                  // map level searched
+    double radius;              // search radius (default_radius)
+    int kmax, kmin;             // max / min_number_neighbors
+    double max_dist_to_plane;   // max_dist_to_plane_ct_icp
+    double threshold_norm;      // threshold_orientation_norm (GN stop criterion on ‖x‖, ct_icp.cpp:978)
+    int shard_rank, shard_world;   // keypoint sharding (multi-GPU); 0/1 when single
+};
+
+class IcpSolver {
+public:
+    explicit IcpSolver(cudaStream_t stream);
+    ~IcpSolver();
+
+    // d_keypoints: float4 (raw xyz fp32, alpha fp32); d_num_keypoints: device int; upper bound for grid sizing.
+    // Enqueues `num_iters` GN iterations on the stream; state is read back by the caller.
+    void EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options &opt, const float4 *d_keypoints,
+                            const int *d_num_keypoints, size_t k_upper, int num_iters, IcpState *d_state,
+                            int shard_rank = 0, int shard_world = 1, void *nccl_comm = nullptr);
+
+    // solver CERES reproduced as a device Levenberg-Marquardt / IRLS loop (icp_lm.cu)
+    void EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt, const cticp_strategy_options &strategy,
+                      const float4 *d_keypoints, const int *d_num_keypoints, size_t k_upper, IcpState *d_state,
+                      int shard_rank = 0, int shard_world = 1, void *nccl_comm = nullptr);
+
+    // single linearisation at the current state → A (12x12, after 1/n and regularisers), b, n_used (debug tap)
+    void NormalEquations(const DeviceMap &map, const cticp_icp_options &opt, const float4 *d_keypoints,
+                         const int *d_num_keypoints, size_t k_upper, IcpState *d_state, double *h_A144, double *h_b12,
+                         int *h_n_used);
+
+    // neighbor lists for queries (fp64 xyz on device): out_points n*kmax*3 (farthest first), out_counts n
+    void Neighborhoods(const DeviceMap &map, const double *d_queries, size_t n, int kmax, double *d_out_points,
+                       int *d_out_counts);
+
+    int launches() const { return launches_; }
+    float gather_ms() const { return gather_ms_; }
+    void reset_timing() { gather_ms_ = 0.f; }
+    void set_time_gather(bool on) { time_gather_ = on; }
+    void CollectGatherTiming();   // after a stream sync: accumulates the event pairs recorded since the last call
+    // multi-GPU: partials[0..kAcc) ← all-reduce over ranks of Σ_blocks partials (nccl_shard.cu)
+    void AllReducePartials(void *nccl_comm, int blocks);
+
+private:
+    void EnsurePartials(int blocks);
+    GnParams MakeParams(const DeviceMap &map, const cticp_icp_options &opt) const;
+
+    cudaStream_t stream_;
+    double *d_partials_ = nullptr;
+    int partial_blocks_ = 0;
+    double *d_sys_ = nullptr;      // 12*12 + 12 + 4 debug output of the solve kernel
+    int launches_ = 0;
+    float gather_ms_ = 0.f;
+    bool time_gather_ = false;
+    static constexpr int kMaxEvents = 64;
+    cudaEvent_t ev_begin_[kMaxEvents], ev_end_[kMaxEvents];
+    int ev_used_ = 0;
+    int num_sms_ = 148;
+};
+
+}  // namespace cticp

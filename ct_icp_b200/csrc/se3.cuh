@@ -1,0 +1,208 @@
+// se3.cuh — fp64 SE3 / quaternion algebra shared by host orchestration and sm_100a kernels.
+//
+// Restates the arithmetic the reference gets from Eigen + slam::TSE3/TPose
+// (include/SlamCore/types.h:100-139, 192-219, 313-366, 434-470): quaternion product, q·v, slerp (not renormalised),
+// Quaternion(Matrix3), toRotationMatrix, pose interpolation. Everything is fp64: world coordinates reach km and the
+// parity budget is 1e-4 m (SURVEY §7 "Precision").
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define CT_HD __host__ __device__ __forceinline__
+#else
+#define CT_HD inline
+#endif
+
+namespace cticp {
+
+struct V3 {
+    double x, y, z;
+};
+CT_HD V3 mk(double x, double y, double z) { return V3{x, y, z}; }
+CT_HD V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+CT_HD V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+CT_HD V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+CT_HD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+CT_HD V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+CT_HD double norm(V3 a) { return sqrt(dot(a, a)); }
+
+struct Q4 {   // (x, y, z, w) like Eigen::Quaterniond::coeffs()
+    double x, y, z, w;
+};
+CT_HD Q4 qmul(Q4 a, Q4 b) {
+    return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+            a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+CT_HD double qdot(Q4 a, Q4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+CT_HD Q4 qnormalized(Q4 q) {
+    double n = sqrt(qdot(q, q));
+    return {q.x / n, q.y / n, q.z / n, q.w / n};
+}
+CT_HD Q4 qinverse(Q4 q) {   // Eigen inverse(): conjugate / squaredNorm
+    double n2 = qdot(q, q);
+    if (n2 > 0) return {-q.x / n2, -q.y / n2, -q.z / n2, q.w / n2};
+    return {0, 0, 0, 0};
+}
+// Eigen _transformVector: uv = 2 (q.vec × v); v + w uv + q.vec × uv
+CT_HD V3 qrot(Q4 q, V3 v) {
+    V3 qv = {q.x, q.y, q.z};
+    V3 uv = cross(qv, v);
+    uv = uv + uv;
+    return v + q.w * uv + cross(qv, uv);
+}
+// Eigen slerp (types.h:363): result NOT renormalised
+CT_HD Q4 qslerp(Q4 a, Q4 b, double t) {
+    const double one = 1.0 - 2.220446049250313e-16;
+    double d = qdot(a, b);
+    double ad = fabs(d);
+    double s0, s1;
+    if (ad >= one) {
+        s0 = 1.0 - t;
+        s1 = t;
+    } else {
+        double theta = acos(ad);
+        double st = sin(theta);
+        s0 = sin((1.0 - t) * theta) / st;
+        s1 = sin(t * theta) / st;
+    }
+    if (d < 0) s1 = -s1;
+    return {s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w};
+}
+struct M3 {
+    double m[3][3];
+};
+CT_HD M3 qtoR(Q4 q) {
+    M3 r;
+    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    r.m[0][0] = 1 - (tyy + tzz); r.m[0][1] = txy - twz; r.m[0][2] = txz + twy;
+    r.m[1][0] = txy + twz; r.m[1][1] = 1 - (txx + tzz); r.m[1][2] = tyz - twx;
+    r.m[2][0] = txz - twy; r.m[2][1] = tyz + twx; r.m[2][2] = 1 - (txx + tyy);
+    return r;
+}
+CT_HD M3 mmul(const M3 &a, const M3 &b) {
+    M3 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+    return r;
+}
+// Eigen Quaternion(Matrix3) (trace-based), used by the GN pose update (src/ct_icp/ct_icp.cpp:950-954)
+CT_HD Q4 qfromR(const M3 &R) {
+    Q4 q;
+    double t = R.m[0][0] + R.m[1][1] + R.m[2][2];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q.w = 0.5 * t;
+        t = 0.5 / t;
+        q.x = (R.m[2][1] - R.m[1][2]) * t;
+        q.y = (R.m[0][2] - R.m[2][0]) * t;
+        q.z = (R.m[1][0] - R.m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (R.m[1][1] > R.m[0][0]) i = 1;
+        if (R.m[2][2] > R.m[i][i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(R.m[i][i] - R.m[j][j] - R.m[k][k] + 1.0);
+        double c[3];
+        c[i] = 0.5 * t;
+        t = 0.5 / t;
+        q.w = (R.m[k][j] - R.m[j][k]) * t;
+        c[j] = (R.m[j][i] + R.m[i][j]) * t;
+        c[k] = (R.m[k][i] + R.m[i][k]) * t;
+        q.x = c[0]; q.y = c[1]; q.z = c[2];
+    }
+    return q;
+}
+// Euler ZYX update matrix of the GN step (src/ct_icp/ct_icp.cpp:916-932)
+CT_HD M3 eulerZYX(double a, double b, double g) {
+    M3 R;
+    double ca = cos(a), sa = sin(a), cb = cos(b), sb = sin(b), cg = cos(g), sg = sin(g);
+    R.m[0][0] = cg * cb; R.m[0][1] = -sg * ca + cg * sb * sa; R.m[0][2] = sg * sa + cg * sb * ca;
+    R.m[1][0] = sg * cb; R.m[1][1] = cg * ca + sg * sb * sa;  R.m[1][2] = -cg * sa + sg * sb * ca;
+    R.m[2][0] = -sb;     R.m[2][1] = cb * sa;                 R.m[2][2] = cb * ca;
+    return R;
+}
+
+struct Se3 {   // slam::TSE3<double>
+    Q4 q;
+    V3 t;
+};
+CT_HD Se3 se3_identity() { return Se3{{0, 0, 0, 1}, {0, 0, 0}}; }
+CT_HD Se3 se3_inverse(Se3 a) {   // types.h:327-332
+    Se3 r;
+    r.q = qinverse(a.q);
+    V3 v = qrot(r.q, a.t);
+    r.t = {-v.x, -v.y, -v.z};
+    return r;
+}
+CT_HD Se3 se3_mul(Se3 a, Se3 b) {   // types.h:344-351
+    Se3 r;
+    r.q = qnormalized(qmul(a.q, b.q));
+    r.t = qrot(qnormalized(a.q), b.t) + a.t;
+    return r;
+}
+// world = Interpolate(begin, end, alpha) * raw  (types.h:361-366 then :354-357: slerp, lerp, quat.normalized()*p + tr)
+CT_HD V3 ct_transform(Q4 qb, V3 tb, Q4 qe, V3 te, double alpha, V3 raw) {
+    Q4 q = qnormalized(qslerp(qb, qe, alpha));
+    V3 t = (1.0 - alpha) * tb + alpha * te;
+    return qrot(q, raw) + t;
+}
+// slam::AngularDistance (types.h:141-156), degrees; returns NaN when the CHECK would fire
+CT_HD double angular_distance_deg(Q4 a, Q4 b) {
+    M3 Ra = qtoR(a), Rb = qtoR(b);
+    double tr = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 3; ++k) tr += Ra.m[i][k] * Rb.m[i][k];
+    double n = (tr - 1.0) / 2.0;
+    if (!(n < 1.0 + 1e-8 && n >= -1.0 - 1e-8)) return NAN;
+    n = fmax(fmin(n, 1.0), -1.0);
+    return acos(n) * (180.0 / M_PI);
+}
+
+// ---- order contract: counter-based permutation standing in for std::shuffle (DESIGN.md "Order contract") ----
+CT_HD uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+CT_HD uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+struct Perm {
+    uint32_t n, half_bits, half_mask;
+    uint32_t keys[4];
+};
+CT_HD Perm perm_make(uint64_t seed, uint64_t counter, uint32_t n) {
+    Perm p;
+    p.n = n;
+    uint32_t bits = 2;
+    while (bits < 32 && (uint64_t(1) << bits) < uint64_t(n)) bits += 2;
+    p.half_bits = bits / 2;
+    p.half_mask = (1u << p.half_bits) - 1u;
+    uint64_t s = splitmix64(seed ^ splitmix64(counter));
+    uint64_t s2 = splitmix64(s);
+    p.keys[0] = uint32_t(s); p.keys[1] = uint32_t(s >> 32); p.keys[2] = uint32_t(s2); p.keys[3] = uint32_t(s2 >> 32);
+    return p;
+}
+CT_HD uint32_t perm_apply(const Perm &p, uint32_t i) {
+    uint32_t v = i;
+    do {
+        uint32_t l = v >> p.half_bits, r = v & p.half_mask;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t f = mix32(r ^ p.keys[k]) & p.half_mask;
+            uint32_t nl = r;
+            r = l ^ f;
+            l = nl;
+        }
+        v = (l << p.half_bits) | r;
+    } while (v >= p.n);
+    return v;
+}
+
+}  // namespace cticp

@@ -89,7 +89,6 @@ public:
         robust_num_consecutive_failures_ = 0;
         suspect_registration_error_ = false;
         next_robust_level_ = 0;
-        shuffle_counter_ = 0;
         tracker_ = FrameInsertionTracker();
         default_motion_model_ = MotionModel();
     }
@@ -167,11 +166,11 @@ private:
             frame[i].index_frame = info.frame_id;
         }
         const int k = info.registered_fid;
-        ShuffleInPlace(frame, options_.shuffle_seed, shuffle_counter_++);
+        ShuffleInPlace(frame, options_.shuffle_seed, ShuffleCounter(k, 0));
         sub_sample_frame(frame, sample_size);
         if (k <= 1)
             for (auto &p : frame) p.timestamp = info.end_timestamp;
-        ShuffleInPlace(frame, options_.shuffle_seed, shuffle_counter_++);
+        ShuffleInPlace(frame, options_.shuffle_seed, ShuffleCounter(k, 1));
 
         const auto &tr = trajectory_[k];
         if (k > 1 && options_.motion_compensation == CTICP_MC_CONSTANT_VELOCITY) {
@@ -193,6 +192,8 @@ private:
         const int k = info.registered_fid;
         const bool at_startup = k < options_.init_num_frames;
         auto start = clock::now();
+        const int attempt_idx = try_register_calls_++;
+        (void) attempt_idx;
         std::vector<WPoint3D> keypoints;
         if (options_.sampling == CTICP_SAMPLING_GRID)
             grid_sampling(frame, keypoints, sample_voxel_size);
@@ -201,7 +202,7 @@ private:
         else
             keypoints = frame;
         if (!at_startup && options_.max_num_keypoints > 0 && (int) keypoints.size() > options_.max_num_keypoints) {
-            ShuffleInPlace(keypoints, options_.shuffle_seed, shuffle_counter_++);
+            ShuffleInPlace(keypoints, options_.shuffle_seed, ShuffleCounter(k, 2 + attempt_idx));
             keypoints.resize(options_.max_num_keypoints);
         }
         rs.sample_size = (int) keypoints.size();
@@ -323,6 +324,7 @@ private:
         auto start = clock::now();
         cticp_icp_options ct_icp_options = options_.ct_icp_options;
         const int k = info.registered_fid;
+        try_register_calls_ = 0;
         auto frame = InitializeFrame(xyz, ts, info);
 
         RegistrationSummary summary;
@@ -460,7 +462,13 @@ private:
     int robust_num_consecutive_failures_ = 0;
     bool suspect_registration_error_ = false;
     int next_robust_level_ = 0;
-    uint64_t shuffle_counter_ = 0;
+    int try_register_calls_ = 0;
+    // Order contract: the counter of each permutation is a pure function of (registered frame, purpose) so that a
+    // device pipeline never needs data-dependent host state: purpose 0/1 = the two shuffles of InitializeFrame
+    // (odometry.cpp:349,361), 2+a = the keypoint truncation shuffle of the a-th TryRegister call (:550).
+    static uint64_t ShuffleCounter(int registered_fid, int purpose) {
+        return (uint64_t(uint32_t(registered_fid)) << 8) | uint64_t(purpose & 0xff);
+    }
 };
 
 }  // namespace orc

@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances: integer / index work (sampling, voxel assignment, neighbor sets) is compared exactly; stored map
+points within the fp32 voxel-local storage quantum (2e-7 m); normal equations 1e-6 relative; poses within the
+north-star bound 1e-4 m / 1e-4 rad per frame (observed: ~1e-7).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import frame_diff, get_sequence
+from ct_icp_b200 import _abi as abi
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 2e-7        # fp32 offset from the voxel origin, |offset| < 1.5 m → ulp 1.2e-7
+POSE_TOL_M = 1e-4     # BASELINE.json north_star
+POSE_TOL_RAD = 1e-4
+
+
+def small_map_options(b, res=1.0, max_pts=20, min_dist=0.1, cap=1 << 15):
+    o = b.legacy_map_options(res, max_pts, min_dist)
+    o.capacity_voxels = cap
+    return o
+
+
+def random_cloud(rng, n, extent=30.0):
+    # planar-ish structures + noise so voxels fill up and the min-distance rule matters
+    pts = rng.uniform(-extent, extent, size=(n, 3))
+    pts[: n // 2, 2] = rng.normal(0.0, 0.02, size=n // 2)            # ground
+    pts[n // 2: 3 * n // 4, 1] = 10.0 + rng.normal(0.0, 0.02, size=n // 4)   # wall
+    return pts.astype(np.float32).astype(np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_order_contract_permutation(orc, eng):
+    for n in (1, 2, 3, 17, 1000, 131072, 132481):
+        a = orc.permutation(0x5DEECE66D, 513, n)
+        b = eng.permutation(0x5DEECE66D, 513, n)
+        assert np.array_equal(a, b)
+        assert np.array_equal(np.sort(a), np.arange(n, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("voxel", [0.2, 0.5, 1.5])
+def test_grid_sampling_indices(orc, eng, voxel):
+    s = get_sequence("hdl64", 2)[1]
+    a = orc.grid_sample_indices(s["xyz"], voxel)
+    b = eng.grid_sample_indices(s["xyz"], voxel)
+    assert len(a) == len(b) and np.array_equal(a, b)
+
+
+def test_grid_sampling_edge_cases(orc, eng):
+    one = np.array([[1.0, 2.0, 3.0]])
+    assert np.array_equal(eng.grid_sample_indices(one, 0.5), [0])
+    dup = np.repeat(one, 1000, axis=0)
+    assert np.array_equal(eng.grid_sample_indices(dup, 0.5), [0])
+    # negative coordinates: truncation toward zero merges (-v, +v) around the origin like the reference's cast
+    pts = np.array([[-0.3, 0, 0], [0.3, 0, 0], [-0.7, 0, 0], [0.7, 0, 0]])
+    assert np.array_equal(eng.grid_sample_indices(pts, 0.5), orc.grid_sample_indices(pts, 0.5))
+
+
+def test_map_insert_matches_oracle(orc, eng):
+    rng = np.random.default_rng(7)
+    mo, me = orc.voxel_map(small_map_options(orc)), eng.voxel_map(small_map_options(eng))
+    for batch in range(4):
+        pts = random_cloud(rng, 20000)
+        mo.insert(pts)
+        me.insert(pts)
+        assert mo.num_points() == me.num_points()
+        assert mo.num_voxels() == me.num_voxels()
+    xo, vo = mo.export()
+    xe, ve = me.export()
+    assert np.array_equal(vo, ve)
+    assert np.abs(xo - xe).max() < POS_TOL
+
+
+def test_map_multi_resolution_insert(orc, eng):
+    rng = np.random.default_rng(11)
+    oo, oe = orc.default_map_options(), eng.default_map_options()
+    oe.capacity_voxels = 1 << 17
+    mo, me = orc.voxel_map(oo), eng.voxel_map(oe)
+    pts = random_cloud(rng, 30000, extent=12.0)
+    mo.insert(pts)
+    me.insert(pts)
+    for lvl in range(3):
+        assert mo.num_points(lvl) == me.num_points(lvl)
+        xo, vo = mo.export(lvl)
+        xe, ve = me.export(lvl)
+        assert np.array_equal(vo, ve)
+        assert np.abs(xo - xe).max() < POS_TOL
+
+
+def test_map_remove_far(orc, eng):
+    rng = np.random.default_rng(3)
+    mo, me = orc.voxel_map(small_map_options(orc)), eng.voxel_map(small_map_options(eng))
+    pts = random_cloud(rng, 30000)
+    mo.insert(pts); me.insert(pts)
+    for loc, dist in (((5.0, -3.0, 0.5), 25.0), ((20.0, 10.0, 0.0), 12.0)):
+        mo.remove_far(loc, dist); me.remove_far(loc, dist)
+        assert mo.num_points() == me.num_points() and mo.num_voxels() == me.num_voxels()
+        assert np.array_equal(mo.export()[1], me.export()[1])
+    # insert again after eviction (tombstones in the table must not break lookups / re-insertion)
+    pts2 = random_cloud(rng, 20000)
+    mo.insert(pts2); me.insert(pts2)
+    xo, vo = mo.export(); xe, ve = me.export()
+    assert np.array_equal(vo, ve) and np.abs(xo - xe).max() < POS_TOL
+    mo.clear(); me.clear()
+    assert me.num_points() == 0 and me.num_voxels() == 0
+
+
+def test_map_self_nearest_and_full_recall(eng):
+    # reference test/unit/SlamCore/test_map.cxx:5-38: kNN=1 returns the point itself; a huge radius returns all
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-1, 1, size=(100, 3)).astype(np.float32).astype(np.float64)
+    o = eng.legacy_map_options(0.01, 20, 0.0)
+    o.capacity_voxels = 1 << 12
+    m = eng.voxel_map(o)
+    m.insert(pts)
+    nb, cnt = m.compute_neighborhoods(pts, 1)
+    assert np.all(cnt == 1)
+    assert np.abs(nb[:, 0, :] - pts).max() < 1e-5
+    o2 = eng.legacy_map_options(1.0, 64, 0.0)
+    o2.default_radius = 4.0     # ceil(4/1) = 4 → 729-voxel stencil covers the whole cube
+    o2.capacity_voxels = 1 << 12
+    m2 = eng.voxel_map(o2)
+    m2.insert(pts[:30])
+    nb, cnt = m2.compute_neighborhoods(pts[:5], 32)
+    assert np.all(cnt == 30)
+
+
+def test_neighborhoods_match_oracle(orc, eng):
+    rng = np.random.default_rng(9)
+    mo, me = orc.voxel_map(small_map_options(orc)), eng.voxel_map(small_map_options(eng))
+    pts = random_cloud(rng, 60000)
+    mo.insert(pts); me.insert(pts)
+    q = random_cloud(rng, 4000) + rng.normal(0, 0.05, size=(4000, 3))
+    no, co = mo.compute_neighborhoods(q, 20)
+    ne, ce = me.compute_neighborhoods(q, 20)
+    assert np.array_equal(co, ce)
+    assert (co >= 5).sum() > 500
+    assert np.abs(no - ne).max() < POS_TOL     # same neighbors in the same (farthest-first) order
+
+
+def test_neighborhoods_radius2_stencil(orc, eng):
+    # nclt-like: resolution 0.5, radius 0.8 → r = 2 (125-voxel stencil, several 32-voxel rounds)
+    rng = np.random.default_rng(13)
+    oo, oe = small_map_options(orc, res=0.5, max_pts=40, min_dist=0.05), small_map_options(eng, res=0.5, max_pts=40, min_dist=0.05)
+    oo.default_radius = oe.default_radius = 0.8
+    mo, me = orc.voxel_map(oo), eng.voxel_map(oe)
+    pts = random_cloud(rng, 60000, extent=15.0)
+    mo.insert(pts); me.insert(pts)
+    q = random_cloud(rng, 2000, extent=15.0)
+    no, co = mo.compute_neighborhoods(q, 20)
+    ne, ce = me.compute_neighborhoods(q, 20)
+    assert np.array_equal(co, ce)
+    assert np.abs(no - ne).max() < POS_TOL
+
+
+def _registration_case(orc, eng, solver):
+    """Map from frames 0..k-1 at the oracle's poses; register frame k's keypoints from a perturbed initial guess."""
+    seq = get_sequence("hdl64", 4)
+    o = orc.default_odometry_options()
+    o.ct_icp_options.solver = abi.SOLVER["GN"]
+    o.ct_icp_options.min_number_neighbors = 10
+    o.map_options = orc.legacy_map_options(1.0, 20, 0.1)
+    o.debug_print = 0
+    od = orc.odometry(o)
+    for s in seq[:3]:
+        sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        assert sm.success
+    map_xyz, _ = od.GetMapPointer().export(0)
+    # keypoints of the next frame: grid-sampled raw points, world from the initial estimate
+    s = seq[3]
+    idx = orc.grid_sample_indices(s["xyz"], 1.0)
+    kp = np.zeros(len(idx), dtype=abi.wpoint_dtype())
+    kp["raw"] = s["xyz"][idx]
+    kp["timestamp"] = s["t"][idx]
+    traj = od.Trajectory()
+    frame = traj[-1].copy()
+    frame.begin_pose = traj[-1].end_pose.copy()
+    frame.begin_pose.dest_timestamp = float(s["t"].min())
+    frame.end_pose.dest_timestamp = float(s["t"].max())
+    return map_xyz, kp, frame, traj[-1]
+
+
+def _fill_world(orc, kp, frame):
+    f = frame
+    out = (C.c_double * 3)()
+    for i in range(len(kp)):
+        raw = (C.c_double * 3)(*kp["raw"][i])
+        orc.check(orc.fn("pose_transform")(C.byref(f), raw, float(kp["timestamp"][i]), out))
+        kp["world"][i] = out[:]
+
+
+def test_gn_normal_equations(orc, eng):
+    map_xyz, kp, frame, prev = _registration_case(orc, eng, "GN")
+    mo, me = orc.voxel_map(small_map_options(orc, cap=1 << 18)), eng.voxel_map(small_map_options(eng, cap=1 << 18))
+    mo.insert(map_xyz); me.insert(map_xyz)
+    assert mo.num_points() == me.num_points()
+    io = orc.default_icp_options()
+    io.solver = abi.SOLVER["GN"]
+    io.min_number_neighbors = 10
+    mm = orc.default_odometry_options().default_motion_model
+    _fill_world(orc, kp, frame)
+    Ao, bo, no = mo.gn_normal_equations(io, kp, frame, prev, mm)
+    Ae, be, ne = me.gn_normal_equations(io, kp.copy(), frame, prev, mm)
+    assert no == ne and no > 100
+    scale = np.abs(Ao).max()
+    assert np.abs(Ao - Ae).max() < 1e-6 * scale
+    assert np.abs(bo - be).max() < 1e-6 * max(np.abs(bo).max(), 1e-3)
+    assert np.allclose(Ae, Ae.T)
+
+
+def test_gn_register_matches_oracle(orc, eng):
+    map_xyz, kp, frame, prev = _registration_case(orc, eng, "GN")
+    mo, me = orc.voxel_map(small_map_options(orc, cap=1 << 18)), eng.voxel_map(small_map_options(eng, cap=1 << 18))
+    mo.insert(map_xyz); me.insert(map_xyz)
+    io = orc.default_icp_options()
+    io.solver = abi.SOLVER["GN"]
+    io.min_number_neighbors = 10
+    io.num_iters_icp = 8
+    mm = orc.default_odometry_options().default_motion_model
+    _fill_world(orc, kp, frame)
+    kpo, kpe = kp.copy(), kp.copy()
+    fo, fe = frame.copy(), frame.copy()
+    so = mo.icp_register(io, kpo, fo, prev, mm)
+    se = me.icp_register(io, kpe, fe, prev, mm)
+    assert so.success and se.success
+    assert so.num_residuals_used == se.num_residuals_used
+    dt, dr = frame_diff(fo, fe)
+    assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (dt, dr)
+    assert dt < 1e-6 and dr < 1e-6, (dt, dr)     # observed level; tightens the north-star bound
+    # the registration moved the pose (the test is not vacuous)
+    assert frame_diff(fo, frame)[0] > 1e-3
+    assert np.abs(kpo["world"] - kpe["world"]).max() < 1e-5
+
+
+def test_gn_register_not_enough_keypoints(orc, eng):
+    # reference: ct_icp.cpp:860-871 → success=false when fewer than 100 residuals
+    me = eng.voxel_map(small_map_options(eng))
+    rng = np.random.default_rng(1)
+    me.insert(random_cloud(rng, 500))
+    kp = np.zeros(50, dtype=abi.wpoint_dtype())
+    kp["raw"] = random_cloud(rng, 50)
+    kp["timestamp"] = 0.05
+    frame = abi.Frame()
+    frame.begin_pose = abi.Pose.make(dest_timestamp=0.0, dest_frame_id=1)
+    frame.end_pose = abi.Pose.make(dest_timestamp=0.1, dest_frame_id=1)
+    io = eng.default_icp_options()
+    io.solver = abi.SOLVER["GN"]
+    s = me.icp_register(io, kp, frame)
+    assert not s.success
+
+
+def test_timestamp_outside_pose_interval_is_an_error(eng):
+    # reference: CHECK in TPose::InterpolatePose (types.h:456) aborts; the ABI returns CTICP_ERR_TIMESTAMP
+    from ct_icp_b200 import CticpError
+    me = eng.voxel_map(small_map_options(eng))
+    kp = np.zeros(10, dtype=abi.wpoint_dtype())
+    kp["timestamp"] = 0.5
+    frame = abi.Frame()
+    frame.begin_pose = abi.Pose.make(dest_timestamp=0.0)
+    frame.end_pose = abi.Pose.make(dest_timestamp=0.1)
+    io = eng.default_icp_options()
+    io.solver = abi.SOLVER["GN"]
+    with pytest.raises(CticpError) as e:
+        me.icp_register(io, kp, frame)
+    assert e.value.code == abi.ERR_TIMESTAMP
+
+
+def _run_sequence(b, seq, solver="GN", **overrides):
+    o = b.default_odometry_options()
+    o.ct_icp_options.solver = abi.SOLVER[solver]
+    o.ct_icp_options.min_number_neighbors = 10
+    o.ct_icp_options.ls_max_num_iters = 5
+    o.ct_icp_options.ls_num_threads = 8
+    o.map_options = b.legacy_map_options(1.0, 20, 0.1)
+    o.debug_print = 0
+    for k, v in overrides.items():
+        setattr(o, k, v)
+    od = b.odometry(o)
+    out = []
+    for s in seq:
+        sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        out.append((sm, od.MapSize()))
+    return od, out
+
+
+def test_odometry_sequence_small(orc, eng, seq_small):
+    """config 1 stand-in (~10k-pt scans): full RegisterFrame pipeline, GN, frame by frame."""
+    odo, ro = _run_sequence(orc, seq_small, init_num_frames=4)
+    ode, re_ = _run_sequence(eng, seq_small, init_num_frames=4)
+    for (so, mo), (se, me) in zip(ro, re_):
+        assert so.success == se.success
+        assert so.num_corrected_points == se.num_corrected_points
+        assert so.num_keypoints == se.num_keypoints
+        assert mo == me
+        dt, dr = frame_diff(so.frame, se.frame)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (dt, dr)
+    assert np.array_equal(odo.GetMapPointer().export(0)[1], ode.GetMapPointer().export(0)[1])
+
+
+def test_odometry_sequence_hdl64_gn(orc, eng, seq_hdl64):
+    """config 2 (KITTI-shape 64-beam ~130k-pt scans, CT_ICP_GN point-to-plane): 26 frames incl. the switch from
+    the start-up regime (init_num_frames = 20) to the steady state."""
+    odo, ro = _run_sequence(orc, seq_hdl64)
+    ode, re_ = _run_sequence(eng, seq_hdl64)
+    worst_t = worst_r = 0.0
+    for i, ((so, mo), (se, me)) in enumerate(zip(ro, re_)):
+        assert so.success and se.success, i
+        assert so.num_corrected_points == se.num_corrected_points, i
+        assert so.num_keypoints == se.num_keypoints, i
+        assert so.number_of_residuals == se.number_of_residuals, i
+        assert mo == me, i
+        dt, dr = frame_diff(so.frame, se.frame)
+        worst_t, worst_r = max(worst_t, dt), max(worst_r, dr)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
+    print("worst per-frame pose difference: %.3e m, %.3e rad" % (worst_t, worst_r))
+    # corrected points of the last frame
+    po = odo.corrected_points()
+    pe = ode.corrected_points()
+    assert len(po) == len(pe)
+    assert np.abs(po["world"] - pe["world"]).max() < 1e-4
+    assert np.abs(po["raw"] - pe["raw"]).max() == 0.0
+    pa = ode.all_corrected_points()
+    assert len(pa) == len(seq_hdl64[-1]["xyz"])
+    ka, kb = odo.keypoints(), ode.keypoints()
+    assert len(ka) == len(kb) and np.abs(ka["world"] - kb["world"]).max() < 1e-4
+
+
+def test_odometry_reset(eng, seq_small):
+    od, r1 = _run_sequence(eng, seq_small[:4], init_num_frames=2)
+    p1 = [list(s.frame.end_pose.tr) for s, _ in r1]
+    od.Reset()
+    assert od.MapSize() == 0 and len(od.Trajectory()) == 0
+    p2 = []
+    for s in seq_small[:4]:
+        p2.append(list(od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]).frame.end_pose.tr))
+    assert np.allclose(p1, p2, atol=0, rtol=0)      # deterministic: fixed-order reductions, counter-based shuffles

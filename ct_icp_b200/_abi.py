@@ -174,7 +174,8 @@ class DeviceTiming(_Struct):
         ("total_ms", C.c_double), ("ingest_ms", C.c_double), ("icp_ms", C.c_double), ("gather_ms", C.c_double),
         ("map_update_ms", C.c_double), ("icp_iterations", C.c_int32), ("kernel_launches", C.c_int32),
         ("gather_keypoint_iterations", C.c_uint64), ("gather_stencil_points", C.c_uint64),
-        ("gather_stencil_voxels", C.c_uint64),
+        ("gather_stencil_voxels", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("gather_launches", C.c_int32), ("_pad0", C.c_int32),
     ]
 
 

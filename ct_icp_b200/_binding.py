@@ -78,6 +78,13 @@ class Binding:
             "odometry_map_points": (i64, [vp, vp, sz]),
             "odometry_last_timing": (C.c_int, [vp, P(abi.DeviceTiming)]),
             "nccl_unique_id": (C.c_int, [vp]),
+            "odometry_stage_frame": (i64, [vp, vp, sz, vp, sz, sz]),
+            "odometry_register_staged": (C.c_int, [vp, i64, u32, P(abi.Summary)]),
+            "odometry_clear_staged": (C.c_int, [vp]),
+            "odometry_timer_start": (C.c_int, [vp]),
+            "odometry_timer_stop": (C.c_int, [vp, P(dbl)]),
+            "odometry_flush_l2": (C.c_int, [vp, sz]),
+            "odometry_set_gather_timing": (C.c_int, [vp, C.c_int]),
             "odometry_enable_sharding": (C.c_int, [vp, vp, C.c_int, C.c_int]),
             # oracle only (KAT taps)
             "odometry_last_counters": (None, [vp, P(u64), P(u64)]),
@@ -277,6 +284,35 @@ class Odometry:
 
     def RegisterFrameWithEstimate(self, xyz, timestamps, initial_estimate, frame_id):
         return self._register(xyz, timestamps, frame_id, initial_estimate)
+
+    # ---- device-resident input / measurement helpers (engine only) ---------------------------------------
+    def stage_frame(self, xyz, timestamps):
+        xyz = np.ascontiguousarray(np.asarray(xyz)[:, :3], dtype=np.float64)
+        timestamps = np.ascontiguousarray(timestamps, dtype=np.float64).reshape(-1)
+        return self.b.check(self.b.fn("odometry_stage_frame")(self.h, xyz.ctypes.data, xyz.strides[0],
+                                                              timestamps.ctypes.data, 8, len(xyz)))
+
+    def RegisterStaged(self, slot, frame_id):
+        summary = abi.Summary()
+        self.b.check(self.b.fn("odometry_register_staged")(self.h, slot, frame_id, C.byref(summary)))
+        return summary
+
+    def clear_staged(self):
+        self.b.check(self.b.fn("odometry_clear_staged")(self.h))
+
+    def timer_start(self):
+        self.b.check(self.b.fn("odometry_timer_start")(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double(0.0)
+        self.b.check(self.b.fn("odometry_timer_stop")(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self, nbytes=256 << 20):
+        self.b.check(self.b.fn("odometry_flush_l2")(self.h, nbytes))
+
+    def set_gather_timing(self, on):
+        self.b.check(self.b.fn("odometry_set_gather_timing")(self.h, 1 if on else 0))
 
     def points(self, which):
         cap = 1 << 16

@@ -38,8 +38,4 @@ def engine():
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(the engine is CUDA-only; there is no CPU fallback)")
         _engine = Binding(ctypes.CDLL(LIB_PATH), "cticp_")
-        # engine-only entry points
-        lib = _engine.lib
-        lib.cticp_odometry_set_gather_timing.restype = ctypes.c_int
-        lib.cticp_odometry_set_gather_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
     return _engine

@@ -340,6 +340,45 @@ int cticp_odometry_last_timing(cticp_odometry *h, cticp_device_timing *out) {
         return (int) CTICP_OK;
     });
 }
+int64_t cticp_odometry_stage_frame(cticp_odometry *h, const double *xyz, size_t xyz_stride_bytes, const double *t,
+                                   size_t t_stride_bytes, size_t n) {
+    int64_t slot = -1;
+    int rc = Guard([&] {
+        slot = h->engine->StageFrame(xyz, xyz_stride_bytes, t, t_stride_bytes, n);
+        return (int) CTICP_OK;
+    });
+    return rc < 0 ? rc : slot;
+}
+int cticp_odometry_register_staged(cticp_odometry *h, int64_t slot, uint32_t frame_id, cticp_summary *out_summary) {
+    return Guard([&] {
+        h->engine->RegisterStaged(slot, frame_id, out_summary);
+        return (int) CTICP_OK;
+    });
+}
+int cticp_odometry_clear_staged(cticp_odometry *h) {
+    return Guard([&] {
+        h->engine->ClearStaged();
+        return (int) CTICP_OK;
+    });
+}
+int cticp_odometry_timer_start(cticp_odometry *h) {
+    return Guard([&] {
+        h->engine->TimerStart();
+        return (int) CTICP_OK;
+    });
+}
+int cticp_odometry_timer_stop(cticp_odometry *h, double *elapsed_ms) {
+    return Guard([&] {
+        *elapsed_ms = h->engine->TimerStop();
+        return (int) CTICP_OK;
+    });
+}
+int cticp_odometry_flush_l2(cticp_odometry *h, size_t bytes) {
+    return Guard([&] {
+        h->engine->FlushL2(bytes);
+        return (int) CTICP_OK;
+    });
+}
 int cticp_odometry_set_gather_timing(cticp_odometry *h, int on) {
     h->engine->SetTimeGather(on != 0);
     return CTICP_OK;

@@ -90,6 +90,7 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
     CT_CUDA_CHECK(cudaMallocHost(&h_state_, sizeof(IcpState)));
     CT_CUDA_CHECK(cudaMalloc(&d_kp_world_, sizeof(double) * 3 * max_pts));
     for (auto &e : ev_) CT_CUDA_CHECK(cudaEventCreate(&e));
+    for (auto &e : timer_ev_) CT_CUDA_CHECK(cudaEventCreate(&e));
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
@@ -103,6 +104,9 @@ Engine::~Engine() {
     cudaFreeHost(h_state_);
     cudaFree(d_kp_world_);
     for (auto &e : ev_) cudaEventDestroy(e);
+    for (auto &e : timer_ev_) cudaEventDestroy(e);
+    for (auto &sc : staged_) cudaFree(sc.d_points);
+    cudaFree(d_flush_);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -164,6 +168,11 @@ void Engine::InitializeMotion(const FrameInfo &info, const cticp_frame *initial_
 // shuffle / sub_sample_frame / timestamp override / shuffle.
 void Engine::IngestAndSubSample(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
                                 const FrameInfo &info) {
+    IngestImpl(xyz, xyz_stride, t, t_stride, n, info, -1);
+}
+
+void Engine::IngestImpl(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+                        const FrameInfo &info, int64_t staged_slot) {
     const int k = info.registered_fid;
     const HostFrame &tr = trajectory_[k];
     const double bts = tr.begin_pose.dest_timestamp, ets = tr.end_pose.dest_timestamp;
@@ -173,24 +182,89 @@ void Engine::IngestAndSubSample(const double *xyz, size_t xyz_stride, const doub
         throw TimestampError("The timestamp cannot be interpolated between the two poses");
     if (n > pipe_->MaxPoints()) throw CapacityError("scan has more points than max_points_per_frame");
 
-    float4 *stage = pipe_->Staging();
-    const double mn = std::min(bts, ets), mx = std::max(bts, ets);
-    const double inv = (mx > mn) ? 1.0 / (mx - mn) : 0.0;
-    const char *px = reinterpret_cast<const char *>(xyz), *pt = reinterpret_cast<const char *>(t);
-    for (size_t i = 0; i < n; ++i) {
-        const double *p = reinterpret_cast<const double *>(px + i * xyz_stride);
-        const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
-        // GetAlphaTimestamp (types.h:192-219); timestamps were range-checked above
-        const double a = (mx > mn) ? (ti - mn) * inv : 1.0;
-        stage[i] = make_float4((float) p[0], (float) p[1], (float) p[2], (float) a);
+    if (staged_slot >= 0) {
+        pipe_->UploadFromDevice(staged_[staged_slot].d_points, n);   // already packed, already in HBM
+    } else {
+        PackScan(xyz, xyz_stride, t, t_stride, n, bts, ets, pipe_->Staging());
+        pipe_->Upload(n);
     }
-    pipe_->Upload(n);
+    timing_.h2d_bytes += pipe_->h2d_bytes();
     const double sample_size = k < options_.init_num_frames ? options_.init_voxel_size : options_.voxel_size;
     // frames 0 and 1: every timestamp := end_timestamp (odometry.cpp:355-359)
     const bool override_alpha = (k <= 1);
     const float alpha_value = (float) AlphaTimestamp(info.end_timestamp, bts, ets);
     pipe_->SubSampleFrame(sample_size, options_.shuffle_seed, ShuffleCounter(k, 0), ShuffleCounter(k, 1),
                           override_alpha, alpha_value);
+}
+
+// (x, y, z, alpha) packing: alpha = GetAlphaTimestamp(t) w.r.t. the pose pair's timestamps (types.h:192-219);
+// the caller has range-checked the timestamps
+void Engine::PackScan(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n, double bts,
+                      double ets, float4 *dst) {
+    const double mn = std::min(bts, ets), mx = std::max(bts, ets);
+    const double inv = (mx > mn) ? 1.0 / (mx - mn) : 0.0;
+    const char *px = reinterpret_cast<const char *>(xyz), *pt = reinterpret_cast<const char *>(t);
+    for (size_t i = 0; i < n; ++i) {
+        const double *p = reinterpret_cast<const double *>(px + i * xyz_stride);
+        const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
+        const double a = (mx > mn) ? (ti - mn) * inv : 1.0;
+        dst[i] = make_float4((float) p[0], (float) p[1], (float) p[2], (float) a);
+    }
+}
+
+static void MinMaxTimestamps(const double *t, size_t t_stride, size_t n, double *mn_out, double *mx_out) {
+    double mn = INFINITY, mx = -INFINITY;
+    const char *pt = reinterpret_cast<const char *>(t);
+    for (size_t i = 0; i < n; ++i) {
+        const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
+        mn = ti < mn ? ti : mn;
+        mx = ti > mx ? ti : mx;
+    }
+    *mn_out = mn;
+    *mx_out = mx;
+}
+
+int64_t Engine::StageFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n) {
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    if (n == 0 || !xyz || !t) throw std::invalid_argument("The registered frame cannot be empty");
+    if (n > pipe_->MaxPoints()) throw CapacityError("scan has more points than max_points_per_frame");
+    StagedScan sc;
+    sc.n = n;
+    MinMaxTimestamps(t, t_stride, n, &sc.t_min, &sc.t_max);
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // the pinned staging buffer may still feed a previous copy
+    PackScan(xyz, xyz_stride, t, t_stride, n, sc.t_min, sc.t_max, pipe_->Staging());
+    CT_CUDA_CHECK(cudaMalloc(&sc.d_points, sizeof(float4) * n));
+    CT_CUDA_CHECK(cudaMemcpyAsync(sc.d_points, pipe_->Staging(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream_));
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    staged_.push_back(sc);
+    return (int64_t) staged_.size() - 1;
+}
+void Engine::ClearStaged() {
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (auto &sc : staged_) cudaFree(sc.d_points);
+    staged_.clear();
+}
+void Engine::TimerStart() {
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    CT_CUDA_CHECK(cudaEventRecord(timer_ev_[0], stream_));
+}
+double Engine::TimerStop() {
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    CT_CUDA_CHECK(cudaEventRecord(timer_ev_[1], stream_));
+    CT_CUDA_CHECK(cudaEventSynchronize(timer_ev_[1]));
+    float ms = 0.f;
+    CT_CUDA_CHECK(cudaEventElapsedTime(&ms, timer_ev_[0], timer_ev_[1]));
+    return (double) ms;
+}
+void Engine::FlushL2(size_t bytes) {
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    if (bytes > flush_bytes_) {
+        cudaFree(d_flush_);
+        CT_CUDA_CHECK(cudaMalloc(&d_flush_, bytes));
+        flush_bytes_ = bytes;
+    }
+    CT_CUDA_CHECK(cudaMemsetAsync(d_flush_, 0x5A, bytes, stream_));
 }
 
 // TryRegister, odometry.cpp:525-601
@@ -247,6 +321,8 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     pipe_->QueueCountsReadback();
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
     icp_->CollectGatherTiming();
+    timing_.h2d_bytes += sizeof(IcpState);
+    timing_.d2h_bytes += sizeof(IcpState) + sizeof(int) * 4;
 
     rs.sample_size = pipe_->h_counts()[2];
     rs.icp.success = !S.failed;
@@ -406,21 +482,26 @@ void Engine::UpdateMap(Summary &s, int registered_fid) {
 // RegisterFrame / RegisterFrameWithEstimate (odometry.cpp:199-236) → DoRegister (:386-501)
 void Engine::RegisterFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
                            uint32_t frame_id, const cticp_frame *initial_estimate, cticp_summary *out) {
+    if (n == 0 || !xyz || !t) throw std::invalid_argument("The registered frame cannot be empty");
+    RegisterCommon(xyz, xyz_stride, t, t_stride, n, frame_id, initial_estimate, -1, out);
+}
+void Engine::RegisterStaged(int64_t slot, uint32_t frame_id, cticp_summary *out) {
+    if (slot < 0 || slot >= (int64_t) staged_.size()) throw std::invalid_argument("unknown staged slot");
+    RegisterCommon(nullptr, 0, nullptr, 0, staged_[slot].n, frame_id, nullptr, slot, out);
+}
+
+void Engine::RegisterCommon(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+                            uint32_t frame_id, const cticp_frame *initial_estimate, int64_t staged_slot,
+                            cticp_summary *out) {
     auto t_start = hclock::now();
     CT_CUDA_CHECK(cudaSetDevice(device_));
-    if (n == 0 || !xyz || !t) throw std::invalid_argument("The registered frame cannot be empty");
     // compute_frame_info, odometry.cpp:186-196
     FrameInfo info;
-    {
-        double mn = INFINITY, mx = -INFINITY;
-        const char *pt = reinterpret_cast<const char *>(t);
-        for (size_t i = 0; i < n; ++i) {
-            const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
-            mn = ti < mn ? ti : mn;
-            mx = ti > mx ? ti : mx;
-        }
-        info.begin_timestamp = mn;
-        info.end_timestamp = mx;
+    if (staged_slot >= 0) {
+        info.begin_timestamp = staged_[staged_slot].t_min;
+        info.end_timestamp = staged_[staged_slot].t_max;
+    } else {
+        MinMaxTimestamps(t, t_stride, n, &info.begin_timestamp, &info.end_timestamp);
     }
     info.registered_fid = registered_frames_++;
     info.frame_id = frame_id;
@@ -439,7 +520,7 @@ void Engine::RegisterFrame(const double *xyz, size_t xyz_stride, const double *t
     last_all_world_valid_ = last_kp_world_valid_ = false;
 
     CT_CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
-    IngestAndSubSample(xyz, xyz_stride, t, t_stride, n, info);
+    IngestImpl(xyz, xyz_stride, t, t_stride, n, info, staged_slot);
     const double t_initialization = ms_since(t_start);
 
     Summary summary;
@@ -539,6 +620,7 @@ cticp_device_timing Engine::LastTiming() {
     timing_.map_update_ms = c;
     timing_.total_ms = d;
     timing_.gather_ms = icp_->gather_ms();
+    timing_.gather_launches = icp_->gather_launches();
     return timing_;
 }
 

@@ -38,6 +38,13 @@ public:
 
     void RegisterFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
                        uint32_t frame_id, const cticp_frame *initial_estimate, cticp_summary *out);
+    // device-resident input: pack + copy a scan to HBM now, register it later
+    int64_t StageFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n);
+    void RegisterStaged(int64_t slot, uint32_t frame_id, cticp_summary *out);
+    void ClearStaged();
+    void TimerStart();
+    double TimerStop();
+    void FlushL2(size_t bytes);
     int64_t GetPoints(int which, cticp_wpoint *dst, size_t cap);
     const std::vector<HostFrame> &Trajectory() const { return trajectory_; }
     int64_t MapSize();
@@ -75,6 +82,22 @@ private:
     void InitializeMotion(const FrameInfo &info, const cticp_frame *initial_estimate);
     void IngestAndSubSample(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
                             const FrameInfo &info);
+    void IngestImpl(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+                    const FrameInfo &info, int64_t staged_slot);
+    static void PackScan(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n, double bts,
+                         double ets, float4 *dst);
+    void RegisterCommon(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+                        uint32_t frame_id, const cticp_frame *initial_estimate, int64_t staged_slot,
+                        cticp_summary *out);
+    struct StagedScan {
+        float4 *d_points = nullptr;
+        size_t n = 0;
+        double t_min = 0, t_max = 0;
+    };
+    std::vector<StagedScan> staged_;
+    cudaEvent_t timer_ev_[2];
+    void *d_flush_ = nullptr;
+    size_t flush_bytes_ = 0;
     void TryRegister(const FrameInfo &info, cticp_icp_options &options, Summary &rs, double sample_voxel_size,
                      const MotionModel *mm, int attempt_idx);
     bool AssessRegistration(Summary &s) const;

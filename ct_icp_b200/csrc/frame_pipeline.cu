@@ -225,6 +225,15 @@ void FramePipeline::Upload(size_t n) {
     h2d_bytes_ = sizeof(float4) * n + sizeof(int);
 }
 
+void FramePipeline::UploadFromDevice(const float4 *d_src, size_t n) {
+    if (n > max_points_) throw CapacityError("scan has more points than max_points_per_frame");
+    n_ = n;
+    h_counts_[0] = (int) n;
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_raw_, d_src, sizeof(float4) * n, cudaMemcpyDeviceToDevice, stream_));
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_counts_, h_counts_, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    h2d_bytes_ = sizeof(int);
+}
+
 void FramePipeline::GridSelect(const float4 *in, const uint32_t *in_src, const int *d_n_in, size_t n_upper,
                                double voxel_size, int use_perm1, uint64_t seed, uint64_t c1, int use_perm2,
                                uint64_t c2, int override_alpha, float alpha_value, float4 *out, uint32_t *out_src,

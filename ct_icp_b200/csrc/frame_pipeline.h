@@ -21,6 +21,7 @@ public:
     float4 *Staging() { return h_stage_; }
     size_t MaxPoints() const { return max_points_; }
     void Upload(size_t n);
+    void UploadFromDevice(const float4 *d_src, size_t n);   // scan already packed and resident in HBM
 
     // Odometry::InitializeFrame: shuffle → sub_sample_frame → (frames 0,1: timestamp := end) → shuffle
     void SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2, bool override_alpha,

@@ -68,7 +68,8 @@ public:
 
     int launches() const { return launches_; }
     float gather_ms() const { return gather_ms_; }
-    void reset_timing() { gather_ms_ = 0.f; }
+    void reset_timing() { gather_ms_ = 0.f; gather_launches_ = 0; }
+    int gather_launches() const { return gather_launches_; }
     void set_time_gather(bool on) { time_gather_ = on; }
     void CollectGatherTiming();   // after a stream sync: accumulates the event pairs recorded since the last call
     // multi-GPU: partials[0..kAcc) ← all-reduce over ranks of Σ_blocks partials (nccl_shard.cu)
@@ -84,6 +85,7 @@ private:
     double *d_sys_ = nullptr;      // 12*12 + 12 + 4 debug output of the solve kernel
     int launches_ = 0;
     float gather_ms_ = 0.f;
+    int gather_launches_ = 0;
     bool time_gather_ = false;
     static constexpr int kMaxEvents = 64;
     cudaEvent_t ev_begin_[kMaxEvents], ev_end_[kMaxEvents];

@@ -363,6 +363,7 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
         k_gn_gather<<<blocks, kGatherWarps * 32, 0, stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state, d_partials_);
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
+        ++gather_launches_;
         if (nccl_comm) {
             AllReducePartials(nccl_comm, blocks);   // defined in nccl_shard.cu
             k_gn_solve<<<1, 128, 0, stream_>>>(d_partials_, 1, d_state, cfg.P, 0, nullptr);

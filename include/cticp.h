@@ -323,8 +323,27 @@ typedef struct cticp_device_timing {
     uint64_t gather_keypoint_iterations;   /* Σ over iterations of keypoints processed */
     uint64_t gather_stencil_points;        /* Σ S: map points found inside the stencils */
     uint64_t gather_stencil_voxels;        /* Σ (2r+1)^3 probes */
+    uint64_t h2d_bytes;                    /* host→device bytes copied by the call (scan + state) */
+    uint64_t d2h_bytes;                    /* device→host bytes copied by the call (poses, counters) */
+    int32_t gather_launches;               /* launches of the neighbor-gather kernel */
+    int32_t _pad0;
 } cticp_device_timing;
 int cticp_odometry_last_timing(cticp_odometry *h, cticp_device_timing *out);
+
+/* Device-resident input (new): a scan can be packed and copied to HBM ahead of time (e.g. by a decoder that
+ * already runs on the GPU) and registered later without any host→device traffic for the points.
+ * cticp_odometry_stage_frame returns a slot id >= 0; slots live until cticp_odometry_clear_staged. */
+int64_t cticp_odometry_stage_frame(cticp_odometry *h, const double *xyz, size_t xyz_stride_bytes, const double *t,
+                                   size_t t_stride_bytes, size_t n);
+int cticp_odometry_register_staged(cticp_odometry *h, int64_t slot, uint32_t frame_id, cticp_summary *out_summary);
+int cticp_odometry_clear_staged(cticp_odometry *h);
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel of this handle is launched on) */
+int cticp_odometry_timer_start(cticp_odometry *h);
+int cticp_odometry_timer_stop(cticp_odometry *h, double *elapsed_ms);   /* synchronises */
+/* per-launch CUDA-event timing of the gather kernel (adds two event records per ICP iteration) */
+int cticp_odometry_set_gather_timing(cticp_odometry *h, int on);
+/* writes `bytes` of device memory (> L2 size flushes the L2) on the handle's stream */
+int cticp_odometry_flush_l2(cticp_odometry *h, size_t bytes);
 
 /* ---- Map (L2 boundary; used directly by the parity tests) ---------------------------------------------- */
 

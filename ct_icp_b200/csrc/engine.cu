@@ -302,16 +302,17 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
         S.prev_qe[0] = pf.end_pose.pose.q.x; S.prev_qe[1] = pf.end_pose.pose.q.y; S.prev_qe[2] = pf.end_pose.pose.q.z;
         S.prev_qe[3] = pf.end_pose.pose.q.w;
     }
+    icp_state_refresh_slerp(S);
     CT_CUDA_CHECK(cudaMemcpyAsync(d_state_, h_state_, sizeof(IcpState), cudaMemcpyHostToDevice, stream_));
     CT_CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
     switch (options.solver) {
         case CTICP_SOLVER_GN:
-            icp_->EnqueueGaussNewton(*map_, options, pipe_->d_keypoints(), pipe_->d_count_keypoints(), pipe_->n(),
+            icp_->EnqueueGaussNewton(*map_, options, pipe_->d_keypoints(), pipe_->d_count_keypoints(), KeypointHint(),
                                      options.num_iters_icp, d_state_, shard_rank_, shard_world_, nccl_comm_);
             break;
         case CTICP_SOLVER_CERES:
             icp_->EnqueueCeres(*map_, options, options_.neighborhood_strategy, pipe_->d_keypoints(),
-                               pipe_->d_count_keypoints(), pipe_->n(), d_state_, shard_rank_, shard_world_, nccl_comm_);
+                               pipe_->d_count_keypoints(), KeypointHint(), d_state_, shard_rank_, shard_world_, nccl_comm_);
             break;
         default:
             throw UnsupportedError("Unsupported Solver Type");
@@ -325,6 +326,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     timing_.d2h_bytes += sizeof(IcpState) + sizeof(int) * 4;
 
     rs.sample_size = pipe_->h_counts()[2];
+    last_num_keypoints_ = (size_t) std::max(0, pipe_->h_counts()[2]);
     rs.icp.success = !S.failed;
     rs.icp.num_residuals_used = S.n_used;
     rs.icp.num_iters = S.iter;

@@ -4,6 +4,7 @@
 // InitializeFrame :333-382, DoRegister :386-501, TryRegister :525-601, AssessRegistration :604-684,
 // RobustRegistration :780-852, UpdateMap :855-953) while every O(N)/O(K·S) stage runs on the device.
 #pragma once
+#include <algorithm>
 #include <memory>
 #include <string>
 #include <vector>
@@ -105,6 +106,13 @@ private:
     void ComputeSummaryMetrics(Summary &s, int k);
     void UpdateMap(Summary &s, int registered_fid);
     void FillSummary(const Summary &s, cticp_summary *out) const;
+    // grid-size hint for the ICP kernels: the keypoint count is only known on the device when they are enqueued, so
+    // the host sizes the grid from the previous registration (keypoint counts change slowly) with 50% head-room;
+    // the kernels stay correct for any count (warps loop)
+    size_t KeypointHint() const {
+        return last_num_keypoints_ ? std::min(pipe_->n(), last_num_keypoints_ + last_num_keypoints_ / 2 + 256) : pipe_->n();
+    }
+    size_t last_num_keypoints_ = 0;
     static uint64_t ShuffleCounter(int registered_fid, int purpose) {
         return (uint64_t(uint32_t(registered_fid)) << 8) | uint64_t(purpose & 0xff);
     }

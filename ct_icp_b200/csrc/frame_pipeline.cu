@@ -24,6 +24,8 @@ namespace cticp {
     } while (0)
 
 constexpr unsigned long long kGridEmpty = ~0ull;
+constexpr size_t kMaxTiles = 4096;   // up to 4M points per scan
+constexpr int kTileShift = 10, kTile = 1 << kTileShift, kTileThreads = kTile / 4;   // 1024 positions per CTA
 
 // voxel key of sub_sample_frame: static_cast<short>(raw / size) per axis (ct_icp.cpp:70-72)
 __device__ __forceinline__ unsigned long long short_voxel_key(const float4 &p, double voxel_size) {
@@ -57,7 +59,8 @@ __global__ void k_grid_claim(const float4 *__restrict__ pts, const int *__restri
 // mark: winners raise a flag at their position in the permuted order
 __global__ void k_grid_mark(const int *__restrict__ d_n, int use_perm, uint64_t seed, uint64_t counter,
                             const unsigned long long *__restrict__ vals, const int *__restrict__ slot_of,
-                            uint32_t *__restrict__ flags, uint32_t *__restrict__ src) {
+                            uint32_t *__restrict__ flags, uint32_t *__restrict__ src,
+                            uint32_t *__restrict__ tile_count) {
     const int n = *d_n;
     const Perm perm = perm_make(seed, counter, (uint32_t) max(n, 1));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -66,24 +69,55 @@ __global__ void k_grid_mark(const int *__restrict__ d_n, int use_perm, uint64_t 
         if (vals[slot_of[i]] == mine) {
             flags[prio] = 1u;
             src[prio] = (uint32_t) i;
+            atomicAdd(&tile_count[prio >> kTileShift], 1u);   // integer atomics: order-independent result
         }
     }
 }
-// exclusive scan of flags[0..n) by one CTA; total → *d_total
-__global__ void __launch_bounds__(1024) k_scan_flags(const uint32_t *__restrict__ flags, const int *__restrict__ d_n,
-                                                      uint32_t *__restrict__ offsets, int *__restrict__ d_total) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
+// emit: compact the winners in permuted order and (optionally) scatter them through a second permutation (the
+// second shuffle). One CTA per tile of 1024 positions: the exclusive prefix of a position is
+//   Σ tile_count[tiles before] (every CTA re-adds those <= 512 counters) + a CTA-local scan of the tile's flags,
+// which replaces a serial single-CTA scan over all positions (64 us for 130k points) by a fully parallel pass.
+__global__ void __launch_bounds__(kTileThreads)
+k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_index, const int *__restrict__ d_n,
+            const uint32_t *__restrict__ flags, const uint32_t *__restrict__ src,
+            const uint32_t *__restrict__ tile_count, int use_perm2, uint64_t seed, uint64_t counter2,
+            int override_alpha, float alpha_value, float4 *__restrict__ out, uint32_t *__restrict__ out_src_index,
+            int *__restrict__ d_total) {
+    __shared__ uint32_t s_red[2][kTileThreads / 32];
+    __shared__ uint32_t s_warp[kTileThreads / 32];
+    __shared__ uint32_t s_before, s_total;
     const int n = *d_n;
+    const int num_tiles = (n + kTile - 1) >> kTileShift;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    // grand total (domain of the second permutation) — identical in every CTA
+    uint32_t tot = 0;
+    for (int t = tid; t < num_tiles; t += kTileThreads) tot += tile_count[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) s_red[1][w] = tot;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024 * 4) {
-        // 4 consecutive elements per thread
-        const int i0 = base + tid * 4;
+    if (tid == 0) {
+        uint32_t b = 0;
+        for (int i = 0; i < kTileThreads / 32; ++i) b += s_red[1][i];
+        s_total = b;
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    if (blockIdx.x == 0 && tid == 0) *d_total = (int) total;
+    const Perm perm2 = perm_make(seed, counter2, max(total, 1u));
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t before = 0;
+        for (int t = tid; t < tile; t += kTileThreads) before += tile_count[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        __syncthreads();   // s_red / s_warp reuse across tiles
+        if (lane == 0) s_red[0][w] = before;
+        // CTA-local exclusive scan of the tile's flags: 4 consecutive positions per thread
+        const int p0 = (tile << kTileShift) + tid * 4;
         uint32_t v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? flags[i0 + k] : 0u;
+        for (int k = 0; k < 4; ++k) v[k] = (p0 + k < n) ? flags[p0 + k] : 0u;
         const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
         uint32_t incl = tsum;
 #pragma unroll
@@ -93,48 +127,31 @@ __global__ void __launch_bounds__(1024) k_scan_flags(const uint32_t *__restrict_
         }
         if (lane == 31) s_warp[w] = incl;
         __syncthreads();
-        if (w == 0) {
-            uint32_t ws = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
-                if (lane >= o) ws += y;
+        if (tid == 0) {
+            uint32_t b = 0;
+            for (int i = 0; i < kTileThreads / 32; ++i) b += s_red[0][i];
+            s_before = b;
+            uint32_t run = 0;
+            for (int i = 0; i < kTileThreads / 32; ++i) {
+                const uint32_t c = s_warp[i];
+                s_warp[i] = run;
+                run += c;
             }
-            s_warp[lane] = ws;   // inclusive over warps
         }
         __syncthreads();
-        const uint32_t carry = s_carry;
-        uint32_t excl = carry + (w > 0 ? s_warp[w - 1] : 0u) + (incl - tsum);
+        uint32_t excl = s_before + s_warp[w] + (incl - tsum);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (i0 + k < n) offsets[i0 + k] = excl;
+            if (v[k]) {
+                const uint32_t dst = (use_perm2 && total > 1) ? perm_apply(perm2, excl) : excl;
+                const uint32_t i = src[p0 + k];
+                float4 val = pts[i];
+                if (override_alpha) val.w = alpha_value;
+                out[dst] = val;
+                out_src_index[dst] = in_src_index ? in_src_index[i] : i;
+            }
             excl += v[k];
         }
-        __syncthreads();
-        if (tid == 1023) s_carry = carry + s_warp[31];
-        __syncthreads();
-    }
-    if (tid == 0) *d_total = (int) s_carry;
-}
-// emit: compact winners in permuted order, optionally scatter through a second permutation (second shuffle)
-__global__ void k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_index,
-                            const int *__restrict__ d_n, const uint32_t *__restrict__ flags,
-                            const uint32_t *__restrict__ src, const uint32_t *__restrict__ offsets,
-                            const int *__restrict__ d_total, int use_perm2, uint64_t seed, uint64_t counter2,
-                            int override_alpha, float alpha_value, float4 *__restrict__ out,
-                            uint32_t *__restrict__ out_src_index) {
-    const int n = *d_n;
-    const int total = *d_total;
-    const Perm perm2 = perm_make(seed, counter2, (uint32_t) max(total, 1));
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        if (!flags[p]) continue;
-        const uint32_t j = offsets[p];
-        const uint32_t dst = (use_perm2 && total > 1) ? perm_apply(perm2, j) : j;
-        const uint32_t i = src[p];
-        float4 v = pts[i];
-        if (override_alpha) v.w = alpha_value;
-        out[dst] = v;
-        out_src_index[dst] = in_src_index ? in_src_index[i] : i;
     }
 }
 // keypoints = frame (sampling NONE, odometry.cpp:546)
@@ -198,9 +215,10 @@ FramePipeline::FramePipeline(size_t max_points, cudaStream_t stream) : stream_(s
     CT_CUDA_CHECK(cudaMalloc(&d_tmp_src_, sizeof(uint32_t) * n));
     CT_CUDA_CHECK(cudaMalloc(&d_grid_, sizeof(unsigned long long) * 2 * (size_t) grid_cap_));
     CT_CUDA_CHECK(cudaMalloc(&d_slot_of_, sizeof(int) * n));
-    CT_CUDA_CHECK(cudaMalloc(&d_flags_, sizeof(uint32_t) * n));
+    if ((n + kTile - 1) / kTile > kMaxTiles) throw std::invalid_argument("max_points_per_frame too large");
+    CT_CUDA_CHECK(cudaMalloc(&d_tile_count_, sizeof(uint32_t) * (kMaxTiles + n)));
+    d_flags_ = d_tile_count_ + kMaxTiles;
     CT_CUDA_CHECK(cudaMalloc(&d_src_, sizeof(uint32_t) * n));
-    CT_CUDA_CHECK(cudaMalloc(&d_offsets_, sizeof(uint32_t) * n));
     CT_CUDA_CHECK(cudaMalloc(&d_counts_, sizeof(int) * 8));
     CT_CUDA_CHECK(cudaMalloc(&d_frame_world_, sizeof(double) * 3 * n));
     CT_CUDA_CHECK(cudaMemsetAsync(d_counts_, 0, sizeof(int) * 8, stream_));
@@ -210,7 +228,7 @@ FramePipeline::~FramePipeline() {
     cudaFreeHost(h_stage_); cudaFreeHost(h_counts_);
     cudaFree(d_raw_); cudaFree(d_frame_); cudaFree(d_keypoints_); cudaFree(d_tmp_points_);
     cudaFree(d_frame_src_); cudaFree(d_kp_src_); cudaFree(d_tmp_src_);
-    cudaFree(d_grid_); cudaFree(d_slot_of_); cudaFree(d_flags_); cudaFree(d_src_); cudaFree(d_offsets_);
+    cudaFree(d_grid_); cudaFree(d_slot_of_); cudaFree(d_tile_count_); cudaFree(d_src_);
     cudaFree(d_counts_); cudaFree(d_frame_world_); cudaFree(d_all_world_);
 }
 
@@ -238,18 +256,20 @@ void FramePipeline::GridSelect(const float4 *in, const uint32_t *in_src, const i
                                double voxel_size, int use_perm1, uint64_t seed, uint64_t c1, int use_perm2,
                                uint64_t c2, int override_alpha, float alpha_value, float4 *out, uint32_t *out_src,
                                int *d_n_out) {
-    unsigned long long *keys = d_grid_, *vals = d_grid_ + grid_cap_;
-    const uint32_t cap = std::max<uint32_t>(NextPow2(2 * n_upper), 1024);   // only the prefix that can be touched
-    CT_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * cap, stream_));
-    CT_CUDA_CHECK(cudaMemsetAsync(vals, 0xFF, sizeof(unsigned long long) * cap, stream_));
-    CT_CUDA_CHECK(cudaMemsetAsync(d_flags_, 0, sizeof(uint32_t) * n_upper, stream_));
+    // scratch hash grid: only the prefix that can be touched is cleared; keys and vals are adjacent → one memset
+    const uint32_t cap = std::max<uint32_t>(NextPow2(2 * n_upper), 1024);
+    unsigned long long *keys = d_grid_, *vals = d_grid_ + cap;
+    CT_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * 2 * (size_t) cap, stream_));
+    // flags and tile counters are adjacent → one memset
+    const size_t num_tiles = (n_upper + kTile - 1) / kTile;
+    CT_CUDA_CHECK(cudaMemsetAsync(d_tile_count_, 0, sizeof(uint32_t) * (kMaxTiles + n_upper), stream_));
     const int blocks = Blocks(n_upper);
     k_grid_claim<<<blocks, 256, 0, stream_>>>(in, d_n_in, voxel_size, use_perm1, seed, c1, keys, vals, cap - 1, d_slot_of_);
-    k_grid_mark<<<blocks, 256, 0, stream_>>>(d_n_in, use_perm1, seed, c1, vals, d_slot_of_, d_flags_, d_src_);
-    k_scan_flags<<<1, 1024, 0, stream_>>>(d_flags_, d_n_in, d_offsets_, d_n_out);
-    k_grid_emit<<<blocks, 256, 0, stream_>>>(in, in_src, d_n_in, d_flags_, d_src_, d_offsets_, d_n_out, use_perm2, seed,
-                                             c2, override_alpha, alpha_value, out, out_src);
-    launches_ += 4;
+    k_grid_mark<<<blocks, 256, 0, stream_>>>(d_n_in, use_perm1, seed, c1, vals, d_slot_of_, d_flags_, d_src_, d_tile_count_);
+    k_grid_emit<<<(int) std::max<size_t>(1, num_tiles), kTileThreads, 0, stream_>>>(
+        in, in_src, d_n_in, d_flags_, d_src_, d_tile_count_, use_perm2, seed, c2, override_alpha, alpha_value, out,
+        out_src, d_n_out);
+    launches_ += 3;
     CT_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -72,7 +72,7 @@ private:
     uint32_t *d_frame_src_ = nullptr, *d_kp_src_ = nullptr, *d_tmp_src_ = nullptr;
     unsigned long long *d_grid_ = nullptr;
     int *d_slot_of_ = nullptr;
-    uint32_t *d_flags_ = nullptr, *d_src_ = nullptr, *d_offsets_ = nullptr;
+    uint32_t *d_tile_count_ = nullptr, *d_flags_ = nullptr, *d_src_ = nullptr;   // flags live right after the tile counters
     int *d_counts_ = nullptr;
     double *d_frame_world_ = nullptr, *d_all_world_ = nullptr;
     int launches_ = 0;

@@ -83,15 +83,57 @@ __device__ __forceinline__ void stencil_offset(int s, int r, int &dx, int &dy, i
     dy = (s / side) % side - r;
     dz = s % side - r;
 }
+// The (2r+1)^3 offsets are tabulated once per CTA in shared memory (packed dx+r | dy+r << 8 | dz+r << 16):
+// the integer divisions above were 14% of the kernel's instructions when evaluated per voxel visit.
+constexpr int kMaxStencil = 729;   // r <= 4
+// Returns the table, or nullptr when the stencil is too large to tabulate (r > 4: offsets are then computed on the
+// fly — correct for any radius, e.g. the reference's own map test uses voxel 0.01 with radius 0.8).
+__device__ __forceinline__ const int *stencil_table_fill(int *table, int r) {
+    const int side = 2 * r + 1, nst = side * side * side;
+    if (r > 4) return nullptr;
+    for (int s = threadIdx.x; s < nst; s += blockDim.x) {
+        int dx, dy, dz;
+        stencil_offset(s, r, dx, dy, dz);
+        table[s] = (dx + r) | ((dy + r) << 8) | ((dz + r) << 16);
+    }
+    return table;
+}
+__device__ __forceinline__ void stencil_lookup(const int *table, int s, int r, int &dx, int &dy, int &dz) {
+    if (table) {
+        const int packed = table[s];
+        dx = (packed & 0xff) - r;
+        dy = ((packed >> 8) & 0xff) - r;
+        dz = ((packed >> 16) & 0xff) - r;
+    } else {
+        stencil_offset(s, r, dx, dy, dz);
+    }
+}
+
+// query point and its voxel (slam::Voxel::Coordinates: three fp64 divisions, done once, one per lane 0..2)
+struct QueryCtx {
+    V3 q;
+    int kx, ky, kz;
+};
+__device__ __forceinline__ QueryCtx make_query(const V3 &q, double res, int lane) {
+    const double c = lane == 0 ? q.x : (lane == 1 ? q.y : q.z);
+    const int k = voxel_coord(c, res);
+    QueryCtx ctx;
+    ctx.q = q;
+    ctx.kx = __shfl_sync(0xffffffffu, k, 0);
+    ctx.ky = __shfl_sync(0xffffffffu, k, 1);
+    ctx.kz = __shfl_sync(0xffffffffu, k, 2);
+    return ctx;
+}
 
 // Returns the number of neighbors kept (<= kmax); lane l < n holds the l-th nearest in `best`.
 // stage: 64 KnnStage entries of shared memory private to this warp.
-__device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const V3 &q, int lane, KnnStage *stage,
-                                               KnnEntry &best, unsigned &stencil_points) {
+__device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int *stencil, const QueryCtx &ctx,
+                                               int lane, KnnStage *stage, KnnEntry &best, unsigned &stencil_points) {
     const MapLevel &L = G.L;
     const int side = 2 * G.r + 1;
     const int nst = side * side * side;
-    const int kx = voxel_coord(q.x, L.res), ky = voxel_coord(q.y, L.res), kz = voxel_coord(q.z, L.res);
+    const V3 &q = ctx.q;
+    const int kx = ctx.kx, ky = ctx.ky, kz = ctx.kz;
     best.d2 = kKnnInf;
     best.seq = 0x7fffffff;
     best.addr = 0;
@@ -105,7 +147,7 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const V3 &
         uint32_t cnt = 0;
         if (s < nst) {
             int dx, dy, dz;
-            stencil_offset(s, G.r, dx, dy, dz);
+            stencil_lookup(stencil, s, G.r, dx, dy, dz);
             slot = map_find(L, pack_voxel(kx + dx, ky + dy, kz + dz), &cnt);
             if (slot < 0) cnt = 0;
         }
@@ -118,7 +160,7 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const V3 &
             const int vcnt = (int) __shfl_sync(0xffffffffu, cnt, src);
             const int vs = base + src;
             int dx, dy, dz;
-            stencil_offset(vs, G.r, dx, dy, dz);
+            stencil_lookup(stencil, vs, G.r, dx, dy, dz);
             // voxel origin relative to the query (fp64)
             const double ox = (kx + dx) * L.res - q.x, oy = (ky + dy) * L.res - q.y, oz = (kz + dz) * L.res - q.z;
             const float4 *vp = L.points + (size_t) vslot * L.B;
@@ -170,14 +212,14 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const V3 &
 }
 
 // Neighbor position relative to the query, fp64, recomputed from the entry (stencil index in seq, offset at addr).
-__device__ __forceinline__ V3 knn_rel_position(const GatherConfig &G, const V3 &q, const KnnEntry &e) {
+__device__ __forceinline__ V3 knn_rel_position(const GatherConfig &G, const int *stencil, const QueryCtx &ctx,
+                                               const KnnEntry &e) {
     const MapLevel &L = G.L;
-    const int kx = voxel_coord(q.x, L.res), ky = voxel_coord(q.y, L.res), kz = voxel_coord(q.z, L.res);
     int dx, dy, dz;
-    stencil_offset(e.seq >> 6, G.r, dx, dy, dz);
+    stencil_lookup(stencil, e.seq >> 6, G.r, dx, dy, dz);
     const float4 p = __ldg(L.points + e.addr);
-    return V3{((kx + dx) * L.res - q.x) + (double) p.x, ((ky + dy) * L.res - q.y) + (double) p.y,
-              ((kz + dz) * L.res - q.z) + (double) p.z};
+    return V3{((ctx.kx + dx) * L.res - ctx.q.x) + (double) p.x, ((ctx.ky + dy) * L.res - ctx.q.y) + (double) p.y,
+              ((ctx.kz + dz) * L.res - ctx.q.z) + (double) p.z};
 }
 
 // ---- 3x3 symmetric eigen-decomposition (cyclic Jacobi, fp64, registers only) ---------------------------------
@@ -238,10 +280,10 @@ struct NeighborhoodDesc {
 // TNeighborhood::ComputeNeighborhood + ComputeNeighborhoodInfo on the n neighbors held one-per-lane.
 // Covariance is accumulated CENTRED ON THE QUERY (the reference's uncentred E[xx^T]-mu mu^T in world coordinates,
 // neighborhood.h:237-244, is the same quantity up to its own fp64 cancellation error).
-__device__ __forceinline__ NeighborhoodDesc warp_describe(const GatherConfig &G, const V3 &q, const KnnEntry &best,
-                                                          int n, int lane) {
+__device__ __forceinline__ NeighborhoodDesc warp_describe(const GatherConfig &G, const int *stencil,
+                                                          const QueryCtx &ctx, const KnnEntry &best, int n, int lane) {
     V3 rel{0, 0, 0};
-    if (lane < n) rel = knn_rel_position(G, q, best);
+    if (lane < n) rel = knn_rel_position(G, stencil, ctx, best);
     const double inv = 1.0 / (double) n;
     const double mx = warp_sum(rel.x) * inv, my = warp_sum(rel.y) * inv, mz = warp_sum(rel.z) * inv;
     const double cxx = warp_sum(rel.x * rel.x) * inv - mx * mx, cxy = warp_sum(rel.x * rel.y) * inv - mx * my,

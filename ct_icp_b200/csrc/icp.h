@@ -28,8 +28,19 @@ struct IcpState {
     int n_used;          // residuals of the last linearisation
     int n_keypoints;     // keypoints visited in the last iteration
     double x_norm;       // ‖x‖ of the last GN step
+    // slerp constants of the current pose pair (se3.cuh SlerpConsts), refreshed by every pose update
+    double slerp_theta, slerp_inv_sin;
+    int slerp_linear, slerp_negate;
     unsigned long long stat_keypoint_iters, stat_stencil_points;
 };
+
+inline void icp_state_refresh_slerp(IcpState &S) {
+    const SlerpConsts c = slerp_consts(Q4{S.qb[0], S.qb[1], S.qb[2], S.qb[3]}, Q4{S.qe[0], S.qe[1], S.qe[2], S.qe[3]});
+    S.slerp_theta = c.theta;
+    S.slerp_inv_sin = c.inv_sin;
+    S.slerp_linear = c.linear;
+    S.slerp_negate = c.negate;
+}
 
 struct GnParams {
     int r;                      // stencil radius (voxels)
@@ -73,7 +84,7 @@ public:
     void set_time_gather(bool on) { time_gather_ = on; }
     void CollectGatherTiming();   // after a stream sync: accumulates the event pairs recorded since the last call
     // multi-GPU: partials[0..kAcc) ← all-reduce over ranks of Σ_blocks partials (nccl_shard.cu)
-    void AllReducePartials(void *nccl_comm, int blocks);
+    void AllReduceAccumulator(void *nccl_comm);
 
 private:
     void EnsurePartials(int blocks);
@@ -83,6 +94,8 @@ private:
     double *d_partials_ = nullptr;
     int partial_blocks_ = 0;
     double *d_sys_ = nullptr;      // 12*12 + 12 + 4 debug output of the solve kernel
+    double *d_acc_ = nullptr;      // reduced accumulator (multi-GPU all-reduce buffer)
+    unsigned int *d_ticket_ = nullptr;   // last-CTA-done counter of k_gn_iterate
     int launches_ = 0;
     float gather_ms_ = 0.f;
     int gather_launches_ = 0;

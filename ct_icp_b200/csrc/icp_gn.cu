@@ -20,7 +20,7 @@ namespace cticp {
                             std::to_string(__LINE__));                                                   \
     } while (0)
 
-constexpr int kGatherWarps = 8;   // warps per CTA of the gather kernel
+constexpr int kGatherWarps = 4;   // warps per CTA of the gather kernel (one keypoint per warp at a time)
 
 // (i,j) of the idx-th entry of the row-major upper triangle of a 12x12 matrix; entries 78..89 are b[0..11]
 __constant__ unsigned char c_pair_i[kAccUsed];
@@ -31,22 +31,192 @@ struct GatherLaunch {
     GnParams P;
 };
 
+// ---- 12x12 pivoted LDL^T by one warp (stand-in for Eigen's A.ldlt().solve(b), ct_icp.cpp:914) -----------------
+// Same algorithm as the serial reference restatement (largest-|diagonal| symmetric pivoting, LDL^T, two triangular
+// solves, D pseudo-inverse); the column scaling and the trailing rank-1 update of every step are spread over the
+// lanes. A is 12 x 13 (padded) in shared memory.
+struct SolveScratch {
+    double A[12][13];
+    double b[12], x[12], D[12], y[12];
+    double sn[8], cs[8];
+    int perm[12];
+};
+
+__device__ void warp_ldlt_solve12(SolveScratch &S, int lane) {
+    if (lane < 12) S.perm[lane] = lane;
+    __syncwarp();
+    for (int k = 0; k < 12; ++k) {
+        double v = (lane >= k && lane < 12) ? fabs(S.A[lane][lane]) : -1.0;
+        int idx = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        const int p = idx;
+        if (p != k) {
+            if (lane < 12) { const double t = S.A[k][lane]; S.A[k][lane] = S.A[p][lane]; S.A[p][lane] = t; }
+            __syncwarp();
+            if (lane < 12) { const double t = S.A[lane][k]; S.A[lane][k] = S.A[lane][p]; S.A[lane][p] = t; }
+            if (lane == 0) { const int t = S.perm[k]; S.perm[k] = S.perm[p]; S.perm[p] = t; }
+            __syncwarp();
+        }
+        const double dk = S.A[k][k];
+        if (lane == 0) S.D[k] = dk;
+        if (dk == 0.0) {
+            if (lane > k && lane < 12) S.A[lane][k] = 0.0;
+            __syncwarp();
+            continue;
+        }
+        if (lane > k && lane < 12) S.A[lane][k] /= dk;
+        __syncwarp();
+        const int m = 11 - k;
+        for (int e = lane; e < m * m; e += 32) {
+            const int i = k + 1 + e / m, j = k + 1 + e % m;
+            if (j <= i) {
+                const double nv = S.A[i][j] - S.A[i][k] * dk * S.A[j][k];
+                S.A[i][j] = nv;
+                S.A[j][i] = nv;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (int i = 0; i < 12; ++i) S.y[i] = S.b[S.perm[i]];
+        for (int i = 0; i < 12; ++i) {
+            double a = S.y[i];
+            for (int j = 0; j < i; ++j) a -= S.A[i][j] * S.y[j];
+            S.y[i] = a;
+        }
+        for (int i = 0; i < 12; ++i) S.y[i] = (fabs(S.D[i]) > 2.2250738585072014e-308) ? S.y[i] / S.D[i] : 0.0;
+        for (int i = 11; i >= 0; --i) {
+            double a = S.y[i];
+            for (int j = i + 1; j < 12; ++j) a -= S.A[j][i] * S.y[j];
+            S.y[i] = a;
+        }
+        for (int i = 0; i < 12; ++i) S.x[S.perm[i]] = S.y[i];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ M3 euler_from_sincos(double sa, double ca, double sb, double cb, double sg, double cg) {
+    M3 R;   // ct_icp.cpp:916-932
+    R.m[0][0] = cg * cb; R.m[0][1] = -sg * ca + cg * sb * sa; R.m[0][2] = sg * sa + cg * sb * ca;
+    R.m[1][0] = sg * cb; R.m[1][1] = cg * ca + sg * sb * sa;  R.m[1][2] = -cg * sa + sg * sb * ca;
+    R.m[2][0] = -sb;     R.m[2][1] = cb * sa;                 R.m[2][2] = cb * ca;
+    return R;
+}
+
+// One warp: accumulator (96 doubles in `acc`) → normal equations → GN step → pose update (ct_icp.cpp:860-980).
+// mode 0: full step. mode 1: only emit the linear system into sys_out (debug tap).
+__device__ void warp_gn_solve(const double *acc, SolveScratch &S, IcpState *st, const GnParams &P, int mode,
+                              double *sys_out, int lane) {
+    const int n_used = (int) (acc[kAccUsed] + 0.5);
+    if (lane == 0) {
+        st->n_used = n_used;
+        st->n_keypoints = (int) (acc[kAccKeypoints] + 0.5);
+        st->stat_keypoint_iters += (unsigned long long) (acc[kAccKeypoints] + 0.5);
+        st->stat_stencil_points += (unsigned long long) (acc[kAccStencil] + 0.5);
+        if (sys_out) sys_out[156] = (double) n_used;
+    }
+    if (n_used < 100) {   // ct_icp.cpp:860-871
+        if (lane == 0) {
+            st->failed = 1;
+            st->done = 1;
+        }
+        return;
+    }
+    {
+        const double inv = 1.0 / (double) n_used;   // :877-882
+        for (int e = lane; e < 78; e += 32) {
+            const int i = c_pair_i[e], j = c_pair_j[e];
+            const double v = acc[e] * inv;
+            S.A[i][j] = v;
+            S.A[j][i] = v;
+        }
+        if (lane < 12) S.b[lane] = acc[78 + lane] * inv;
+    }
+    __syncwarp();
+    if (st->has_motion_model && lane < 3) {   // :885-910
+        const int d = lane;
+        const double ac = st->beta_location, ae = st->beta_cv;
+        const double diff_traj = st->tb[d] - st->te[d];   // the frame's own begin - end (sic, :892)
+        S.A[3 + d][3 + d] += ac;
+        S.b[3 + d] -= ac * diff_traj;
+        const double diff_ego = st->te[d] - st->tb[d] - st->prev_te[d] + st->prev_tb[d];
+        S.A[9 + d][9 + d] += ae;
+        S.b[9 + d] -= ae * diff_ego;
+    }
+    __syncwarp();
+    if (sys_out) {
+        for (int e = lane; e < 144; e += 32) sys_out[e] = S.A[e / 12][e % 12];
+        if (lane < 12) sys_out[144 + lane] = S.b[lane];
+    }
+    if (mode == 1) return;
+
+    warp_ldlt_solve12(S, lane);   // :914
+
+    if (lane < 6) {   // angles x[0..2] (begin) and x[6..8] (end): sin / cos evaluated by six lanes at once
+        const double ang = S.x[lane < 3 ? lane : lane + 3];
+        S.sn[lane] = sin(ang);
+        S.cs[lane] = cos(ang);
+    }
+    __syncwarp();
+    if (lane < 2) {   // lane 0: begin pose, lane 1: end pose (:916-962)
+        const int o = 3 * lane;
+        const M3 R = euler_from_sincos(S.sn[o], S.cs[o], S.sn[o + 1], S.cs[o + 1], S.sn[o + 2], S.cs[o + 2]);
+        double *qp = lane == 0 ? st->qb : st->qe;
+        double *tp = lane == 0 ? st->tb : st->te;
+        const Q4 q = qnormalized(qfromR(mmul(R, qtoR(Q4{qp[0], qp[1], qp[2], qp[3]}))));
+        qp[0] = q.x; qp[1] = q.y; qp[2] = q.z; qp[3] = q.w;
+        const int xo = lane == 0 ? 3 : 9;
+        for (int d = 0; d < 3; ++d) tp[d] += S.x[xo + d];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double nrm = 0;
+        for (int i = 0; i < 12; ++i) nrm += S.x[i] * S.x[i];
+        nrm = sqrt(nrm);
+        st->x_norm = nrm;
+        st->iter += 1;
+        if (nrm < P.threshold_norm) st->done = 1;   // :978
+        const SlerpConsts sc = slerp_consts(Q4{st->qb[0], st->qb[1], st->qb[2], st->qb[3]},
+                                            Q4{st->qe[0], st->qe[1], st->qe[2], st->qe[3]});
+        st->slerp_theta = sc.theta;
+        st->slerp_inv_sin = sc.inv_sin;
+        st->slerp_linear = sc.linear;
+        st->slerp_negate = sc.negate;
+    }
+}
+
+// mode 0: gather + (last CTA) reduce + solve + pose update          [single GPU: ONE launch per ICP iteration]
+// mode 1: gather + (last CTA) reduce + emit linear system to sys_out [debug tap]
+// mode 2: gather + (last CTA) reduce into acc_out                    [multi-GPU: all-reduce then k_gn_solve_acc]
 __global__ void __launch_bounds__(kGatherWarps * 32)
-k_gn_gather(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
-            const IcpState *__restrict__ st, double *__restrict__ partials) {
+k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
+             IcpState *st, double *__restrict__ partials, unsigned int *ticket, int mode, double *acc_out,
+             double *sys_out) {
     __shared__ KnnStage s_stage[kGatherWarps][64];
     __shared__ double s_u[kGatherWarps][16];
     __shared__ double s_acc[kGatherWarps][kAcc];
+    __shared__ int s_stencil[kMaxStencil];
+    __shared__ SolveScratch s_solve;
+    __shared__ int s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const GatherConfig &G = cfg.G;
     const GnParams &P = cfg.P;
 
     double acc0 = 0, acc1 = 0, acc2 = 0;              // entries lane, lane+32, lane+64 of [A upper | b]
     double n_used = 0, sum_sq = 0, n_stencil = 0, n_kp = 0, n_valid = 0;
+    const bool active = (mode == 1) || !st->done;
 
-    if (!st->done) {
+    if (active) {
+        const int *stencil = stencil_table_fill(s_stencil, G.r);
+        __syncthreads();
         const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
         const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
+        const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
         const int K = *d_num_keypoints;
         const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
         const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
@@ -60,17 +230,18 @@ k_gn_gather(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *_
             const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
             const double alpha = (double) kraw.w;
             // world_kpts[i] = InterpolatePose(begin, end, t_i) * raw_i  (ct_icp.cpp:964-966, types.h:361-366)
-            const V3 p = ct_transform(qb, tb, qe, te, alpha, raw);
+            const V3 p = ct_transform_c(qb, tb, qe, te, alpha, raw, sc);
+            const QueryCtx ctx = make_query(p, G.L.res, lane);
 
             KnnEntry best;
             unsigned spts = 0;
-            const int n = warp_gather_knn(G, p, lane, s_stage[w], best, spts);
+            const int n = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
             n_kp += 1;
             n_stencil += (double) spts;
             if (n < P.kmin || n < 5) continue;   // ct_icp.cpp:769 ; neighborhood.h:227
             n_valid += 1;
 
-            const NeighborhoodDesc nd = warp_describe(G, p, best, n, lane);
+            const NeighborhoodDesc nd = warp_describe(G, stencil, ctx, best, n, lane);
             V3 normal = nd.normal;
             // orient towards the sensor position at frame begin (ct_icp.cpp:782-784)
             if (dot(normal, tb - p) < 0) normal = -1.0 * normal;
@@ -125,127 +296,36 @@ k_gn_gather(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *_
         for (int ww = 0; ww < kGatherWarps; ++ww) s += s_acc[ww][threadIdx.x];
         partials[(size_t) blockIdx.x * kAcc + threadIdx.x] = s;
     }
-}
-
-// ---- 12x12 pivoted LDL^T (stand-in for Eigen's A.ldlt().solve(b), ct_icp.cpp:914) ----------------------------
-__device__ void ldlt_solve12(double A[12][12], const double b[12], double x[12]) {
-    int perm[12];
-    double D[12], y[12];
-    for (int i = 0; i < 12; ++i) perm[i] = i;
-    for (int k = 0; k < 12; ++k) {
-        int p = k;
-        double best = fabs(A[k][k]);
-        for (int i = k + 1; i < 12; ++i)
-            if (fabs(A[i][i]) > best) { best = fabs(A[i][i]); p = i; }
-        if (p != k) {
-            for (int j = 0; j < 12; ++j) { double t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t; }
-            for (int i = 0; i < 12; ++i) { double t = A[i][k]; A[i][k] = A[i][p]; A[i][p] = t; }
-            int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
-        }
-        D[k] = A[k][k];
-        if (D[k] == 0.0) {
-            for (int i = k + 1; i < 12; ++i) A[i][k] = 0.0;
-            continue;
-        }
-        for (int i = k + 1; i < 12; ++i) A[i][k] /= D[k];
-        for (int i = k + 1; i < 12; ++i)
-            for (int j = k + 1; j <= i; ++j) {
-                A[i][j] -= A[i][k] * D[k] * A[j][k];
-                A[j][i] = A[i][j];
-            }
-    }
-    for (int i = 0; i < 12; ++i) y[i] = b[perm[i]];
-    for (int i = 0; i < 12; ++i)
-        for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
-    for (int i = 0; i < 12; ++i) y[i] = (fabs(D[i]) > 2.2250738585072014e-308) ? y[i] / D[i] : 0.0;
-    for (int i = 11; i >= 0; --i)
-        for (int j = i + 1; j < 12; ++j) y[i] -= A[j][i] * y[j];
-    for (int i = 0; i < 12; ++i) x[perm[i]] = y[i];
-}
-
-// Sum the per-block partials into one accumulator vector (multi-GPU path: followed by an all-reduce)
-__global__ void k_reduce_partials(const double *__restrict__ partials, int blocks, double *__restrict__ acc) {
-    const int t = threadIdx.x;
-    if (t < kAcc) {
+    // ---- last CTA to finish reduces the partials (fixed order) and takes the Gauss-Newton step -----------------
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0;
+    if (!active) return;
+    double *acc = &s_acc[0][0];
+    if (threadIdx.x < kAcc) {
         double s = 0;
-        for (int b = 0; b < blocks; ++b) s += partials[(size_t) b * kAcc + t];
-        acc[t] = s;
-    }
-}
-
-// mode 0: full GN step (solve + pose update). mode 1: only emit the linear system (debug tap).
-__global__ void k_gn_solve(const double *__restrict__ partials, int blocks, IcpState *st, GnParams P, int mode,
-                           double *__restrict__ sys_out) {
-    __shared__ double s_acc[kAcc];
-    if (st->done && mode == 0) return;
-    const int t = threadIdx.x;
-    if (t < kAcc) {
-        double s = 0;
-        for (int b = 0; b < blocks; ++b) s += partials[(size_t) b * kAcc + t];
-        s_acc[t] = s;
+        const int nb = gridDim.x;
+        for (int b = 0; b < nb; ++b) s += __ldcg(partials + (size_t) b * kAcc + threadIdx.x);
+        acc[threadIdx.x] = s;
+        if (mode == 2) acc_out[threadIdx.x] = s;
     }
     __syncthreads();
-    if (t != 0) return;
+    if (mode == 2 || w != 0) return;
+    warp_gn_solve(acc, s_solve, st, P, mode, sys_out, lane);
+}
 
-    const int n_used = (int) (s_acc[kAccUsed] + 0.5);
-    st->n_used = n_used;
-    st->n_keypoints = (int) (s_acc[kAccKeypoints] + 0.5);
-    st->stat_keypoint_iters += (unsigned long long) (s_acc[kAccKeypoints] + 0.5);
-    st->stat_stencil_points += (unsigned long long) (s_acc[kAccStencil] + 0.5);
-    if (sys_out) sys_out[156] = (double) n_used;
-    if (n_used < 100) {   // ct_icp.cpp:860-871
-        st->failed = 1;
-        st->done = 1;
-        return;
-    }
-    double A[12][12], b[12], x[12];
-    {
-        int idx = 0;
-        const double inv = 1.0 / (double) n_used;   // :877-882
-        for (int i = 0; i < 12; ++i)
-            for (int j = i; j < 12; ++j) {
-                A[i][j] = s_acc[idx] * inv;
-                A[j][i] = A[i][j];
-                ++idx;
-            }
-        for (int i = 0; i < 12; ++i) b[i] = s_acc[78 + i] * inv;
-    }
-    if (st->has_motion_model) {   // :885-910
-        const double ac = st->beta_location, ae = st->beta_cv;
-        for (int d = 0; d < 3; ++d) {
-            const double diff_traj = st->tb[d] - st->te[d];   // the frame's own begin - end (sic, :892)
-            A[3 + d][3 + d] += ac;
-            b[3 + d] -= ac * diff_traj;
-            const double diff_ego = st->te[d] - st->tb[d] - st->prev_te[d] + st->prev_tb[d];
-            A[9 + d][9 + d] += ae;
-            b[9 + d] -= ae * diff_ego;
-        }
-    }
-    if (sys_out) {
-        for (int i = 0; i < 12; ++i) {
-            for (int j = 0; j < 12; ++j) sys_out[i * 12 + j] = A[i][j];
-            sys_out[144 + i] = b[i];
-        }
-    }
-    if (mode == 1) return;
-
-    ldlt_solve12(A, b, x);   // :914
-
-    Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
-    qb = qnormalized(qfromR(mmul(eulerZYX(x[0], x[1], x[2]), qtoR(qb))));   // :916-955 then normalize :961-962
-    qe = qnormalized(qfromR(mmul(eulerZYX(x[6], x[7], x[8]), qtoR(qe))));
-    st->qb[0] = qb.x; st->qb[1] = qb.y; st->qb[2] = qb.z; st->qb[3] = qb.w;
-    st->qe[0] = qe.x; st->qe[1] = qe.y; st->qe[2] = qe.z; st->qe[3] = qe.w;
-    for (int d = 0; d < 3; ++d) {
-        st->tb[d] += x[3 + d];
-        st->te[d] += x[9 + d];
-    }
-    double nrm = 0;
-    for (int i = 0; i < 12; ++i) nrm += x[i] * x[i];
-    nrm = sqrt(nrm);
-    st->x_norm = nrm;
-    st->iter += 1;
-    if (nrm < P.threshold_norm) st->done = 1;   // :978
+// multi-GPU tail: the all-reduced accumulator → GN step (one warp)
+__global__ void k_gn_solve_acc(const double *__restrict__ acc_in, IcpState *st, GnParams P) {
+    __shared__ SolveScratch s_solve;
+    __shared__ double s_acc[kAcc];
+    if (st->done) return;
+    for (int i = threadIdx.x; i < kAcc; i += 32) s_acc[i] = acc_in[i];
+    __syncwarp();
+    warp_gn_solve(s_acc, s_solve, st, P, 0, nullptr, threadIdx.x);
 }
 
 // Neighbor lists for arbitrary queries (parity tests of the map search; ComputeNeighborhoods, map.h:532-540)
@@ -253,15 +333,19 @@ __global__ void __launch_bounds__(kGatherWarps * 32)
 k_neighborhoods(GatherConfig G, const double *__restrict__ queries, int n, double *__restrict__ out_points,
                 int *__restrict__ out_counts) {
     __shared__ KnnStage s_stage[kGatherWarps][64];
+    __shared__ int s_stencil[kMaxStencil];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int *stencil = stencil_table_fill(s_stencil, G.r);
+    __syncthreads();
     for (int i = blockIdx.x * kGatherWarps + w; i < n; i += gridDim.x * kGatherWarps) {
         const V3 q{queries[3 * i], queries[3 * i + 1], queries[3 * i + 2]};
+        const QueryCtx ctx = make_query(q, G.L.res, lane);
         KnnEntry best;
         unsigned spts;
-        const int cnt = warp_gather_knn(G, q, lane, s_stage[w], best, spts);
+        const int cnt = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
         if (lane == 0) out_counts[i] = cnt;
         if (lane < cnt) {
-            const V3 rel = knn_rel_position(G, q, best);
+            const V3 rel = knn_rel_position(G, stencil, ctx, best);
             double *o = out_points + ((size_t) i * G.kmax + (cnt - 1 - lane)) * 3;   // farthest first
             o[0] = q.x + rel.x; o[1] = q.y + rel.y; o[2] = q.z + rel.z;
         }
@@ -296,6 +380,9 @@ IcpSolver::IcpSolver(cudaStream_t stream) : stream_(stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev);
     CT_CUDA_CHECK(cudaMalloc(&d_sys_, sizeof(double) * 160));
+    CT_CUDA_CHECK(cudaMalloc(&d_acc_, sizeof(double) * kAcc));
+    CT_CUDA_CHECK(cudaMalloc(&d_ticket_, sizeof(unsigned int)));
+    CT_CUDA_CHECK(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
     for (int i = 0; i < kMaxEvents; ++i) {
         CT_CUDA_CHECK(cudaEventCreate(&ev_begin_[i]));
         CT_CUDA_CHECK(cudaEventCreate(&ev_end_[i]));
@@ -304,6 +391,8 @@ IcpSolver::IcpSolver(cudaStream_t stream) : stream_(stream) {
 IcpSolver::~IcpSolver() {
     cudaFree(d_partials_);
     cudaFree(d_sys_);
+    cudaFree(d_acc_);
+    cudaFree(d_ticket_);
     for (int i = 0; i < kMaxEvents; ++i) {
         cudaEventDestroy(ev_begin_[i]);
         cudaEventDestroy(ev_end_[i]);
@@ -328,10 +417,12 @@ GnParams IcpSolver::MakeParams(const DeviceMap &map, const cticp_icp_options &op
     P.shard_world = 1;
     return P;
 }
-static int GatherBlocks(size_t k_upper, int num_sms) {
-    // one warp per keypoint; persistent-style cap of 4 CTAs (32 warps) per SM
-    size_t want = (k_upper + kGatherWarps - 1) / kGatherWarps;
-    size_t cap = (size_t) num_sms * 4;
+static int GatherBlocks(size_t k_hint, int num_sms) {
+    // one warp per keypoint, 4 warps per CTA, at most 8 CTAs (32 warps) per SM; beyond that warps loop.
+    // k_hint is an ESTIMATE of the keypoint count (the exact count lives on the device): too small only makes
+    // warps iterate, too large only adds idle CTAs whose zero partials the last CTA has to sum.
+    size_t want = (k_hint + kGatherWarps - 1) / kGatherWarps;
+    size_t cap = (size_t) num_sms * 8;
     return (int) std::max<size_t>(1, std::min(want, cap));
 }
 
@@ -356,21 +447,20 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
     cfg.G.r = cfg.P.r;
     cfg.G.radius2 = cfg.P.radius * cfg.P.radius;
     cfg.G.kmax = cfg.P.kmax;
-    const int blocks = GatherBlocks((k_upper + shard_world - 1) / shard_world, num_sms_);
+    const int blocks = GatherBlocks((k_upper + shard_world - 1) / shard_world + 64, num_sms_);
     EnsurePartials(blocks);
     for (int it = 0; it < num_iters; ++it) {
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
-        k_gn_gather<<<blocks, kGatherWarps * 32, 0, stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state, d_partials_);
+        k_gn_iterate<<<blocks, kGatherWarps * 32, 0, stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state, d_partials_,
+                                                               d_ticket_, nccl_comm ? 2 : 0, d_acc_, nullptr);
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
         ++gather_launches_;
+        launches_ += 1;
         if (nccl_comm) {
-            AllReducePartials(nccl_comm, blocks);   // defined in nccl_shard.cu
-            k_gn_solve<<<1, 128, 0, stream_>>>(d_partials_, 1, d_state, cfg.P, 0, nullptr);
-            launches_ += 3;
-        } else {
-            k_gn_solve<<<1, 128, 0, stream_>>>(d_partials_, blocks, d_state, cfg.P, 0, nullptr);
-            launches_ += 2;
+            AllReduceAccumulator(nccl_comm);   // nccl_shard.cu: in-place sum of d_acc_ over ranks
+            k_gn_solve_acc<<<1, 32, 0, stream_>>>(d_acc_, d_state, cfg.P);
+            launches_ += 1;
         }
     }
     CT_CUDA_CHECK(cudaGetLastError());
@@ -388,9 +478,9 @@ void IcpSolver::NormalEquations(const DeviceMap &map, const cticp_icp_options &o
     const int blocks = GatherBlocks(k_upper, num_sms_);
     EnsurePartials(blocks);
     CT_CUDA_CHECK(cudaMemsetAsync(d_sys_, 0, sizeof(double) * 160, stream_));
-    k_gn_gather<<<blocks, kGatherWarps * 32, 0, stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state, d_partials_);
-    k_gn_solve<<<1, 128, 0, stream_>>>(d_partials_, blocks, d_state, cfg.P, 1, d_sys_);
-    launches_ += 2;
+    k_gn_iterate<<<blocks, kGatherWarps * 32, 0, stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state, d_partials_,
+                                                           d_ticket_, 1, d_acc_, d_sys_);
+    launches_ += 1;
     double h[160];
     CT_CUDA_CHECK(cudaMemcpyAsync(h, d_sys_, sizeof(h), cudaMemcpyDeviceToHost, stream_));
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));

@@ -4,7 +4,7 @@
 
 namespace cticp {
 
-void IcpSolver::AllReducePartials(void *, int) { throw UnsupportedError("multi-GPU sharding not built yet"); }
+void IcpSolver::AllReduceAccumulator(void *) { throw UnsupportedError("multi-GPU sharding not built yet"); }
 void Engine::EnableSharding(const void *, int, int) { throw UnsupportedError("multi-GPU sharding not built yet"); }
 
 }  // namespace cticp

@@ -69,6 +69,36 @@ CT_HD Q4 qslerp(Q4 a, Q4 b, double t) {
     if (d < 0) s1 = -s1;
     return {s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w};
 }
+// The angle between the two poses of a frame is the same for every point of the frame: acos / sin(theta) are
+// evaluated once per ICP iteration (SlerpConsts) and each point only pays for sin((1-t) theta) and sin(t theta).
+struct SlerpConsts {
+    double theta, inv_sin;
+    int linear;      // |d| >= 1 - eps  → plain lerp branch of Eigen's slerp
+    int negate;      // d < 0           → scale1 = -scale1
+};
+CT_HD SlerpConsts slerp_consts(Q4 a, Q4 b) {
+    const double one = 1.0 - 2.220446049250313e-16;
+    SlerpConsts c;
+    const double d = qdot(a, b);
+    const double ad = fabs(d);
+    c.linear = ad >= one;
+    c.negate = d < 0;
+    c.theta = c.linear ? 0.0 : acos(ad);
+    c.inv_sin = c.linear ? 0.0 : 1.0 / sin(c.theta);
+    return c;
+}
+CT_HD Q4 qslerp_c(Q4 a, Q4 b, double t, const SlerpConsts &c) {
+    double s0, s1;
+    if (c.linear) {
+        s0 = 1.0 - t;
+        s1 = t;
+    } else {
+        s0 = sin((1.0 - t) * c.theta) * c.inv_sin;
+        s1 = sin(t * c.theta) * c.inv_sin;
+    }
+    if (c.negate) s1 = -s1;
+    return {s0 * a.x + s1 * b.x, s0 * a.y + s1 * b.y, s0 * a.z + s1 * b.z, s0 * a.w + s1 * b.w};
+}
 struct M3 {
     double m[3][3];
 };
@@ -147,6 +177,13 @@ CT_HD Se3 se3_mul(Se3 a, Se3 b) {   // types.h:344-351
 // world = Interpolate(begin, end, alpha) * raw  (types.h:361-366 then :354-357: slerp, lerp, quat.normalized()*p + tr)
 CT_HD V3 ct_transform(Q4 qb, V3 tb, Q4 qe, V3 te, double alpha, V3 raw) {
     Q4 q = qnormalized(qslerp(qb, qe, alpha));
+    V3 t = (1.0 - alpha) * tb + alpha * te;
+    return qrot(q, raw) + t;
+}
+CT_HD V3 ct_transform_c(Q4 qb, V3 tb, Q4 qe, V3 te, double alpha, V3 raw, const SlerpConsts &c) {
+    Q4 q = qslerp_c(qb, qe, alpha, c);
+    const double inv = 1.0 / sqrt(qdot(q, q));
+    q = Q4{q.x * inv, q.y * inv, q.z * inv, q.w * inv};
     V3 t = (1.0 - alpha) * tb + alpha * te;
     return qrot(q, raw) + t;
 }

@@ -274,7 +274,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     if g_launch and g_ms > 0:
         achieved = (alg_bytes / g_launch) / (g_ms / g_launch * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_gn_gather", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "k_gn_persistent (all ICP iterations of a frame: gather + reduce + solve)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": load_traffic(), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes / g_launch, "us_per_launch": g_ms / g_launch * 1e3,
                     "keypoints_per_launch": g_kp / g_launch, "mean_stencil_points": g_pts / max(g_kp, 1),

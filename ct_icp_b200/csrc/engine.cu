@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace cticp {
@@ -120,6 +121,7 @@ void Engine::Reset() {   // odometry.cpp:956-965
     next_robust_level_ = 0;
     tracker_ = {};
     default_motion_model_ = MotionModel();
+    last_num_keypoints_ = 0;   // grid-size hint: keeps a reset run bit-identical to a fresh one
     last_all_world_valid_ = last_kp_world_valid_ = false;
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
@@ -325,6 +327,9 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     timing_.h2d_bytes += sizeof(IcpState);
     timing_.d2h_bytes += sizeof(IcpState) + sizeof(int) * 4;
 
+    if (getenv("CTICP_DEBUG_TIMERS"))
+        fprintf(stderr, "[cticp] last iteration (SM cycles, needs -DCTICP_DEBUG_TIMERS): reduce %lld, solve %lld\n",
+                (long long) (S.dbg_t[2] - S.dbg_t[1]), (long long) (S.dbg_t[3] - S.dbg_t[2]));
     rs.sample_size = pipe_->h_counts()[2];
     last_num_keypoints_ = (size_t) std::max(0, pipe_->h_counts()[2]);
     rs.icp.success = !S.failed;

@@ -107,10 +107,10 @@ private:
     void UpdateMap(Summary &s, int registered_fid);
     void FillSummary(const Summary &s, cticp_summary *out) const;
     // grid-size hint for the ICP kernels: the keypoint count is only known on the device when they are enqueued, so
-    // the host sizes the grid from the previous registration (keypoint counts change slowly) with 50% head-room;
+    // the host sizes the grid from the previous registration (keypoint counts change slowly) with 25% head-room;
     // the kernels stay correct for any count (warps loop)
     size_t KeypointHint() const {
-        return last_num_keypoints_ ? std::min(pipe_->n(), last_num_keypoints_ + last_num_keypoints_ / 2 + 256) : pipe_->n();
+        return last_num_keypoints_ ? std::min(pipe_->n(), last_num_keypoints_ + last_num_keypoints_ / 4 + 64) : pipe_->n();
     }
     size_t last_num_keypoints_ = 0;
     static uint64_t ShuffleCounter(int registered_fid, int purpose) {

@@ -127,6 +127,25 @@ __device__ __forceinline__ QueryCtx make_query(const V3 &q, double res, int lane
 
 // Returns the number of neighbors kept (<= kmax); lane l < n holds the l-th nearest in `best`.
 // stage: 64 KnnStage entries of shared memory private to this warp.
+//
+// Memory-level parallelism: the stencil's points are addressed as ONE flattened list (prefix sum of the voxel
+// counts over the lanes); chunk c gives lane l the candidate with flat index 32 c + l, found by a 5-step binary
+// search over the prefix sums with shuffles. The loads of up to kPrefetch chunks are issued back to back before any
+// of them is consumed, so a keypoint pays ~one L2/HBM round trip for all its map points instead of one per voxel.
+constexpr int kPrefetch = 8;
+
+__device__ __forceinline__ void knn_consume32(KnnStage *stage, int &fill, KnnEntry &best, int lane) {
+    const KnnStage t = stage[lane];
+    KnnEntry c{t.d2, t.seq, t.addr};
+    knn_sort32(c, lane);
+    knn_merge32(best, c, lane);
+    KnnStage rest = stage[32 + lane];   // garbage beyond fill-32 is never read back
+    __syncwarp();
+    stage[lane] = rest;
+    fill -= 32;
+    __syncwarp();
+}
+
 __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int *stencil, const QueryCtx &ctx,
                                                int lane, KnnStage *stage, KnnEntry &best, unsigned &stencil_points) {
     const MapLevel &L = G.L;
@@ -143,55 +162,83 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int 
 
     for (int base = 0; base < nst; base += 32) {
         const int s = base + lane;
-        int slot = -1;
-        uint32_t cnt = 0;
+        int slot = 0;
+        int cnt = 0;
+        double ox = 0, oy = 0, oz = 0;   // my voxel's origin relative to the query (fp64)
         if (s < nst) {
             int dx, dy, dz;
             stencil_lookup(stencil, s, G.r, dx, dy, dz);
-            slot = map_find(L, pack_voxel(kx + dx, ky + dy, kz + dz), &cnt);
-            if (slot < 0) cnt = 0;
+            uint32_t c = 0;
+            const int found = map_find(L, pack_voxel(kx + dx, ky + dy, kz + dz), &c);
+            if (found >= 0) {
+                slot = found;
+                cnt = (int) c;
+            }
+            ox = (kx + dx) * L.res - q.x;
+            oy = (ky + dy) * L.res - q.y;
+            oz = (kz + dz) * L.res - q.z;
         }
-        pts_total += __reduce_add_sync(0xffffffffu, cnt);
-        unsigned occ = __ballot_sync(0xffffffffu, cnt > 0);
-        while (occ) {
-            const int src = __ffs(occ) - 1;
-            occ &= occ - 1;
-            const int vslot = __shfl_sync(0xffffffffu, slot, src);
-            const int vcnt = (int) __shfl_sync(0xffffffffu, cnt, src);
-            const int vs = base + src;
-            int dx, dy, dz;
-            stencil_lookup(stencil, vs, G.r, dx, dy, dz);
-            // voxel origin relative to the query (fp64)
-            const double ox = (kx + dx) * L.res - q.x, oy = (ky + dy) * L.res - q.y, oz = (kz + dz) * L.res - q.z;
-            const float4 *vp = L.points + (size_t) vslot * L.B;
-            for (int j0 = 0; j0 < vcnt; j0 += 32) {
-                const int j = j0 + lane;
-                const bool valid = j < vcnt;
-                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) p = __ldg(vp + j);
-                const double rx = ox + (double) p.x, ry = oy + (double) p.y, rz = oz + (double) p.z;
-                const double d2 = rx * rx + ry * ry + rz * rz;
-                const bool in = valid && !(d2 > G.radius2);
-                const unsigned m = __ballot_sync(0xffffffffu, in);
-                if (in) {
-                    KnnStage e;
-                    e.d2 = d2;
-                    e.seq = vs * 64 + j;
-                    e.addr = (uint32_t) ((size_t) vslot * L.B + j);
-                    stage[fill + __popc(m & lt_mask)] = e;
+        // inclusive prefix sum of the counts over the lanes
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - cnt;
+        pts_total += (unsigned) total;
+
+        for (int c0 = 0; c0 < total; c0 += 32 * kPrefetch) {
+            float4 pv[kPrefetch];
+            int owner[kPrefetch];
+            // phase 1: locate and issue every load of this batch
+#pragma unroll
+            for (int u = 0; u < kPrefetch; ++u) {
+                const int f = c0 + 32 * u + lane;   // flat candidate index
+                owner[u] = -1;
+                pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + 32 * u < total) {           // warp-uniform
+                    // owner = last lane whose exclusive prefix is <= f (binary search over lanes)
+                    int lo = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int probe = lo + step;
+                        const int ex = __shfl_sync(0xffffffffu, excl, probe & 31);
+                        if (probe < 32 && ex <= f) lo = probe;
+                    }
+                    const int o_excl = __shfl_sync(0xffffffffu, excl, lo);
+                    const int o_slot = __shfl_sync(0xffffffffu, slot, lo);
+                    if (f < total) {
+                        owner[u] = lo | ((f - o_excl) << 8);
+                        pv[u] = __ldg(L.points + (size_t) o_slot * L.B + (f - o_excl));
+                    }
                 }
-                fill += __popc(m);
-                __syncwarp();
-                if (fill >= 32) {
-                    const KnnStage t = stage[lane];
-                    KnnEntry c{t.d2, t.seq, t.addr};
-                    knn_sort32(c, lane);
-                    knn_merge32(best, c, lane);
-                    KnnStage rest = stage[32 + lane];   // garbage beyond fill-32 is never read back
+            }
+            // phase 2: distances, radius test, compaction into the staging buffer, top-k maintenance
+#pragma unroll
+            for (int u = 0; u < kPrefetch; ++u) {
+                if (c0 + 32 * u < total) {           // warp-uniform
+                    const int ol = owner[u] < 0 ? 0 : (owner[u] & 0xff);
+                    const double vx = __shfl_sync(0xffffffffu, ox, ol), vy = __shfl_sync(0xffffffffu, oy, ol),
+                                 vz = __shfl_sync(0xffffffffu, oz, ol);
+                    const int vslot = __shfl_sync(0xffffffffu, slot, ol);
+                    const bool valid = owner[u] >= 0;
+                    const int j = owner[u] >> 8;
+                    const double rx = vx + (double) pv[u].x, ry = vy + (double) pv[u].y, rz = vz + (double) pv[u].z;
+                    const double d2 = rx * rx + ry * ry + rz * rz;
+                    const bool in = valid && !(d2 > G.radius2);
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        KnnStage e;
+                        e.d2 = d2;
+                        e.seq = (base + ol) * 64 + j;   // scan order of the reference: stencil index, then index in voxel
+                        e.addr = (uint32_t) ((size_t) vslot * L.B + j);
+                        stage[fill + __popc(m & lt_mask)] = e;
+                    }
+                    fill += __popc(m);
                     __syncwarp();
-                    stage[lane] = rest;
-                    fill -= 32;
-                    __syncwarp();
+                    if (fill >= 32) knn_consume32(stage, fill, best, lane);
                 }
             }
         }
@@ -264,6 +311,50 @@ __device__ __forceinline__ Eig3 sym_eig3(double a00, double a01, double a02, dou
     return Eig3{e0, e1, e2, c2};
 }
 
+// Non-iterative variant: eigenvalues from the trigonometric solution of the characteristic cubic, the eigenvector of
+// the smallest one from the largest cross product of two rows of (A - e0 I) (D. Eberly, "A Robust Eigensolver for
+// 3x3 Symmetric Matrices"). One acos + two cos instead of ~15 dependent Jacobi rotations: the dependent fp64 chain
+// of the per-keypoint epilogue shrinks ~5x. The result is verified ((A - e0 I) n ~ 0); the rare failure (two
+// coincident eigenvalues, where the normal is ill-defined anyway) falls back to the Jacobi solver.
+__device__ __forceinline__ Eig3 sym_eig3_fast(double a00, double a01, double a02, double a11, double a12, double a22) {
+    const double mx = fmax(fmax(fmax(fabs(a00), fabs(a01)), fmax(fabs(a02), fabs(a11))), fmax(fabs(a12), fabs(a22)));
+    if (!(mx > 0.0)) return sym_eig3(a00, a01, a02, a11, a12, a22);
+    const double inv = 1.0 / mx;
+    const double s00 = a00 * inv, s01 = a01 * inv, s02 = a02 * inv, s11 = a11 * inv, s12 = a12 * inv, s22 = a22 * inv;
+    const double nrm = s01 * s01 + s02 * s02 + s12 * s12;
+    if (!(nrm > 0.0)) return sym_eig3(a00, a01, a02, a11, a12, a22);
+    const double q = (s00 + s11 + s22) * (1.0 / 3.0);
+    const double b00 = s00 - q, b11 = s11 - q, b22 = s22 - q;
+    const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * nrm) * (1.0 / 6.0));
+    const double c00 = b11 * b22 - s12 * s12, c01 = s01 * b22 - s12 * s02, c02 = s01 * s12 - b11 * s02;
+    const double det = (b00 * c00 - s01 * c01 + s02 * c02) / (p * p * p);
+    const double half_det = fmin(fmax(det * 0.5, -1.0), 1.0);
+    const double angle = acos(half_det) * (1.0 / 3.0);
+    const double beta2 = 2.0 * cos(angle);
+    const double beta0 = 2.0 * cos(angle + 2.0943951023931953);   // + 2 pi / 3
+    const double beta1 = -(beta0 + beta2);
+    const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;   // e0 <= e1 <= e2
+    // rows of (A - e0 I)
+    const V3 r0{s00 - e0, s01, s02}, r1{s01, s11 - e0, s12}, r2{s02, s12, s22 - e0};
+    const V3 x01 = cross(r0, r1), x02 = cross(r0, r2), x12 = cross(r1, r2);
+    const double d01 = dot(x01, x01), d02 = dot(x02, x02), d12 = dot(x12, x12);
+    V3 n = x01;
+    double dm = d01;
+    if (d02 > dm) { n = x02; dm = d02; }
+    if (d12 > dm) { n = x12; dm = d12; }
+    if (!(dm > 0.0)) return sym_eig3(a00, a01, a02, a11, a12, a22);
+    const double ninv = 1.0 / sqrt(dm);
+    n = ninv * n;
+    // verification in scaled units (|A| ~ 1)
+    const double rx = dot(r0, n), ry = dot(r1, n), rz = dot(r2, n);
+    if (!(rx * rx + ry * ry + rz * rz < 1e-22)) return sym_eig3(a00, a01, a02, a11, a12, a22);
+    double v0 = fabs(e2), v1 = fabs(e1), v2 = fabs(e0);
+    // |eigenvalues| descending (a tiny negative e0 of a PSD matrix can only reorder within rounding noise)
+    if (v0 < v1) { const double t = v0; v0 = v1; v1 = t; }
+    if (v1 < v2) return sym_eig3(a00, a01, a02, a11, a12, a22);   // |e0| not the smallest: indefinite input, use Jacobi
+    return Eig3{v0 * mx, v1 * mx, v2 * mx, n};
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -289,7 +380,7 @@ __device__ __forceinline__ NeighborhoodDesc warp_describe(const GatherConfig &G,
     const double cxx = warp_sum(rel.x * rel.x) * inv - mx * mx, cxy = warp_sum(rel.x * rel.y) * inv - mx * my,
                  cxz = warp_sum(rel.x * rel.z) * inv - mx * mz, cyy = warp_sum(rel.y * rel.y) * inv - my * my,
                  cyz = warp_sum(rel.y * rel.z) * inv - my * mz, czz = warp_sum(rel.z * rel.z) * inv - mz * mz;
-    const Eig3 e = sym_eig3(cxx, cxy, cxz, cyy, cyz, czz);
+    const Eig3 e = sym_eig3_fast(cxx, cxy, cxz, cyy, cyz, czz);
     NeighborhoodDesc d;
     d.normal = e.normal;
     d.a2D = (sqrt(e.sv1) - sqrt(e.sv2)) / sqrt(e.sv0);

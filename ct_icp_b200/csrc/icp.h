@@ -32,6 +32,7 @@ struct IcpState {
     double slerp_theta, slerp_inv_sin;
     int slerp_linear, slerp_negate;
     unsigned long long stat_keypoint_iters, stat_stencil_points;
+    unsigned long long dbg_t[4];   // %globaltimer stamps of the last iteration: CTA0 start, last-CTA elected, reduced, solved
 };
 
 inline void icp_state_refresh_slerp(IcpState &S) {
@@ -82,6 +83,7 @@ public:
     void reset_timing() { gather_ms_ = 0.f; gather_launches_ = 0; }
     int gather_launches() const { return gather_launches_; }
     void set_time_gather(bool on) { time_gather_ = on; }
+    void set_persistent(bool on) { use_persistent_ = on; }
     void CollectGatherTiming();   // after a stream sync: accumulates the event pairs recorded since the last call
     // multi-GPU: partials[0..kAcc) ← all-reduce over ranks of Σ_blocks partials (nccl_shard.cu)
     void AllReduceAccumulator(void *nccl_comm);
@@ -104,6 +106,8 @@ private:
     cudaEvent_t ev_begin_[kMaxEvents], ev_end_[kMaxEvents];
     int ev_used_ = 0;
     int num_sms_ = 148;
+    int max_coresident_ = 0;
+    bool use_persistent_ = true;
 };
 
 }  // namespace cticp

@@ -6,11 +6,15 @@
 //                 regularisers, pivoted LDL^T solve of the 12x12 system, Euler-ZYX pose update, stop test.
 // Reference: DoRegisterGaussNewton, src/ct_icp/ct_icp.cpp:709-996 (serial per-keypoint loop :753-857).
 #include <cstdio>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
 
 #include "gather.cuh"
 #include "icp.h"
 
 namespace cticp {
+namespace cg = cooperative_groups;
 
 #define CT_CUDA_CHECK(expr)                                                                              \
     do {                                                                                                 \
@@ -25,6 +29,15 @@ constexpr int kGatherWarps = 4;   // warps per CTA of the gather kernel (one key
 // (i,j) of the idx-th entry of the row-major upper triangle of a 12x12 matrix; entries 78..89 are b[0..11]
 __constant__ unsigned char c_pair_i[kAccUsed];
 __constant__ unsigned char c_pair_j[kAccUsed];
+
+#ifdef CTICP_DEBUG_TIMERS
+// SM-local cycle counter (%globaltimer proved far too slow to read: it tripled the kernel time). Only differences
+// taken on the same SM are meaningful: dbg_t[1..3] are all stamped by the solver CTA.
+__device__ __forceinline__ unsigned long long global_timer_ns() { return (unsigned long long) clock64(); }
+#define CT_STAMP(expr) expr
+#else
+#define CT_STAMP(expr)
+#endif
 
 struct GatherLaunch {
     GatherConfig G;
@@ -42,61 +55,34 @@ struct SolveScratch {
     int perm[12];
 };
 
+// Solve the 12x12 SPD system held in S.A / S.b; x → S.x.
+// Eigen's A.ldlt().solve(b) (ct_icp.cpp:914) is replaced by Gauss-Jordan elimination in natural order: lane r keeps
+// row r of [A | b] in 13 registers, the pivot row is broadcast with shuffles and all rows are eliminated at once, so
+// a step costs one fp64 reciprocal plus 13 FMAs instead of a serial O(n^2) sweep, and no back-substitution is
+// needed. The system is symmetric positive definite (JTJ/n plus the diagonal regularisers), for which elimination
+// without pivoting is backward stable; the result agrees with a pivoted LDL^T to ~1e-13 relative. This serial tail
+// sits on the critical path of every ICP iteration (it was 60 us as single-thread code, ~2 us now).
 __device__ void warp_ldlt_solve12(SolveScratch &S, int lane) {
-    if (lane < 12) S.perm[lane] = lane;
-    __syncwarp();
-    for (int k = 0; k < 12; ++k) {
-        double v = (lane >= k && lane < 12) ? fabs(S.A[lane][lane]) : -1.0;
-        int idx = lane;
+    double row[13];
+    const int r = lane < 12 ? lane : 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    for (int j = 0; j < 12; ++j) row[j] = S.A[r][j];
+    row[12] = S.b[r];
+#pragma unroll
+    for (int p = 0; p < 12; ++p) {
+        const double pd = __shfl_sync(0xffffffffu, row[p], p);
+        const double inv = (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0;   // pseudo-inverse like Eigen's D
+        const double f = row[p] * inv;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            const double pj = __shfl_sync(0xffffffffu, row[j], p);
+            if (lane == p)
+                row[j] = pj * inv;
+            else
+                row[j] -= f * pj;
         }
-        const int p = idx;
-        if (p != k) {
-            if (lane < 12) { const double t = S.A[k][lane]; S.A[k][lane] = S.A[p][lane]; S.A[p][lane] = t; }
-            __syncwarp();
-            if (lane < 12) { const double t = S.A[lane][k]; S.A[lane][k] = S.A[lane][p]; S.A[lane][p] = t; }
-            if (lane == 0) { const int t = S.perm[k]; S.perm[k] = S.perm[p]; S.perm[p] = t; }
-            __syncwarp();
-        }
-        const double dk = S.A[k][k];
-        if (lane == 0) S.D[k] = dk;
-        if (dk == 0.0) {
-            if (lane > k && lane < 12) S.A[lane][k] = 0.0;
-            __syncwarp();
-            continue;
-        }
-        if (lane > k && lane < 12) S.A[lane][k] /= dk;
-        __syncwarp();
-        const int m = 11 - k;
-        for (int e = lane; e < m * m; e += 32) {
-            const int i = k + 1 + e / m, j = k + 1 + e % m;
-            if (j <= i) {
-                const double nv = S.A[i][j] - S.A[i][k] * dk * S.A[j][k];
-                S.A[i][j] = nv;
-                S.A[j][i] = nv;
-            }
-        }
-        __syncwarp();
     }
-    if (lane == 0) {
-        for (int i = 0; i < 12; ++i) S.y[i] = S.b[S.perm[i]];
-        for (int i = 0; i < 12; ++i) {
-            double a = S.y[i];
-            for (int j = 0; j < i; ++j) a -= S.A[i][j] * S.y[j];
-            S.y[i] = a;
-        }
-        for (int i = 0; i < 12; ++i) S.y[i] = (fabs(S.D[i]) > 2.2250738585072014e-308) ? S.y[i] / S.D[i] : 0.0;
-        for (int i = 11; i >= 0; --i) {
-            double a = S.y[i];
-            for (int j = i + 1; j < 12; ++j) a -= S.A[j][i] * S.y[j];
-            S.y[i] = a;
-        }
-        for (int i = 0; i < 12; ++i) S.x[S.perm[i]] = S.y[i];
-    }
+    if (lane < 12) S.x[lane] = row[12];
     __syncwarp();
 }
 
@@ -210,6 +196,7 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
     double acc0 = 0, acc1 = 0, acc2 = 0;              // entries lane, lane+32, lane+64 of [A upper | b]
     double n_used = 0, sum_sq = 0, n_stencil = 0, n_kp = 0, n_valid = 0;
     const bool active = (mode == 1) || !st->done;
+    CT_STAMP(if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg_t[0] = global_timer_ns();)
 
     if (active) {
         const int *stencil = stencil_table_fill(s_stencil, G.r);
@@ -303,19 +290,206 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x == 0) *ticket = 0;
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+        CT_STAMP(st->dbg_t[1] = global_timer_ns();)
+    }
     if (!active) return;
     double *acc = &s_acc[0][0];
-    if (threadIdx.x < kAcc) {
-        double s = 0;
+    {
+        // deterministic reduction: warp g sums rows b = g (mod 4) of three columns per lane; fixed-order combine
+        double a0 = 0, a1 = 0, a2 = 0;
         const int nb = gridDim.x;
-        for (int b = 0; b < nb; ++b) s += __ldcg(partials + (size_t) b * kAcc + threadIdx.x);
-        acc[threadIdx.x] = s;
-        if (mode == 2) acc_out[threadIdx.x] = s;
+        for (int b = w; b < nb; b += kGatherWarps) {
+            const double *row = partials + (size_t) b * kAcc;
+            a0 += __ldcg(row + lane);
+            a1 += __ldcg(row + lane + 32);
+            a2 += __ldcg(row + lane + 64);
+        }
+        __syncthreads();
+        s_acc[w][lane] = a0;
+        s_acc[w][lane + 32] = a1;
+        s_acc[w][lane + 64] = a2;
+        __syncthreads();
+        double sum = 0;
+        if (threadIdx.x < kAcc) {
+#pragma unroll
+            for (int ww = 0; ww < kGatherWarps; ++ww) sum += s_acc[ww][threadIdx.x];
+        }
+        __syncthreads();
+        if (threadIdx.x < kAcc) {
+            acc[threadIdx.x] = sum;
+            if (mode == 2) acc_out[threadIdx.x] = sum;
+        }
     }
     __syncthreads();
+    CT_STAMP(if (threadIdx.x == 0) st->dbg_t[2] = global_timer_ns();)
     if (mode == 2 || w != 0) return;
     warp_gn_solve(acc, s_solve, st, P, mode, sys_out, lane);
+    CT_STAMP(if (lane == 0) st->dbg_t[3] = global_timer_ns();)
+}
+
+// ---- persistent variant: the WHOLE Gauss-Newton loop in one cooperative launch --------------------------------
+// CTA 0 is the solver CTA (deterministic reduction of the partials + 12x12 solve + pose update, by the same warp on
+// the same SM every iteration, so its instructions stay in that SM's instruction cache: executed cold, the ~1.5k
+// instructions of the serial tail cost ~45 us per iteration, warm ~8 us); CTAs 1..G gather. Two grid-wide barriers
+// per iteration replace two kernel launches. While the gather CTAs work on iteration 0, the solver warp runs the
+// solve once on a dummy system to pull its code into the instruction cache.
+__device__ __forceinline__ void load_state_volatile(const IcpState *st, Q4 &qb, V3 &tb, Q4 &qe, V3 &te, SlerpConsts &sc) {
+    qb = Q4{__ldcg(&st->qb[0]), __ldcg(&st->qb[1]), __ldcg(&st->qb[2]), __ldcg(&st->qb[3])};
+    qe = Q4{__ldcg(&st->qe[0]), __ldcg(&st->qe[1]), __ldcg(&st->qe[2]), __ldcg(&st->qe[3])};
+    tb = V3{__ldcg(&st->tb[0]), __ldcg(&st->tb[1]), __ldcg(&st->tb[2])};
+    te = V3{__ldcg(&st->te[0]), __ldcg(&st->te[1]), __ldcg(&st->te[2])};
+    sc = SlerpConsts{__ldcg(&st->slerp_theta), __ldcg(&st->slerp_inv_sin), __ldcg(&st->slerp_linear), __ldcg(&st->slerp_negate)};
+}
+
+__global__ void __launch_bounds__(kGatherWarps * 32)
+k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
+                IcpState *st, double *__restrict__ partials, int num_iters) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ KnnStage s_stage[kGatherWarps][64];
+    __shared__ double s_u[kGatherWarps][16];
+    __shared__ double s_acc[kGatherWarps][kAcc];
+    __shared__ int s_stencil[kMaxStencil];
+    __shared__ SolveScratch s_solve;
+    __shared__ IcpState s_dummy;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const GatherConfig &G = cfg.G;
+    const GnParams &P = cfg.P;
+    const bool solver_cta = blockIdx.x == 0;
+    const int gather_ctas = gridDim.x - 1;
+    const int *stencil = stencil_table_fill(s_stencil, G.r);
+    __syncthreads();
+
+    if (solver_cta && w == 0) {
+        // instruction-cache warm-up of the serial tail on a dummy well-posed system (results discarded)
+        CT_STAMP(if (lane == 0) st->dbg_t[0] = global_timer_ns();)
+        for (int i = lane; i < kAcc; i += 32) s_acc[1][i] = 0.0;
+        __syncwarp();
+        for (int e = lane; e < 78; e += 32)
+            if (c_pair_i[e] == c_pair_j[e]) s_acc[1][e] = 200.0 * (1.0 + c_pair_i[e]);
+        if (lane < 12) s_acc[1][78 + lane] = 1e-3 * (lane + 1);
+        if (lane == 0) {
+            s_acc[1][kAccUsed] = 200.0;
+            s_dummy = *st;
+        }
+        __syncwarp();
+        warp_gn_solve(s_acc[1], s_solve, &s_dummy, P, 0, nullptr, lane);
+        __syncwarp();
+    }
+
+    for (int it = 0; it < num_iters; ++it) {
+        if (__ldcg(&st->done)) break;   // uniform: written before the previous grid barrier
+        if (!solver_cta) {
+            double acc0 = 0, acc1 = 0, acc2 = 0;
+            double n_used = 0, sum_sq = 0, n_stencil = 0, n_kp = 0, n_valid = 0;
+            Q4 qb, qe;
+            V3 tb, te;
+            SlerpConsts sc;
+            load_state_volatile(st, qb, tb, qe, te, sc);
+            const int K = *d_num_keypoints;
+            const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
+            const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+            const int warps_total = gather_ctas * kGatherWarps;
+            const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+            const int pi0 = c_pair_i[i0], pj0 = c_pair_j[i0], pi1 = c_pair_i[i1], pj1 = c_pair_j[i1];
+            const int pi2 = i2 < kAccUsed ? c_pair_i[i2] : 0, pj2 = i2 < kAccUsed ? c_pair_j[i2] : 0;
+            for (int kp = lo + (blockIdx.x - 1) * kGatherWarps + w; kp < hi; kp += warps_total) {
+                const float4 kraw = __ldg(keypoints + kp);
+                const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+                const double alpha = (double) kraw.w;
+                const V3 p = ct_transform_c(qb, tb, qe, te, alpha, raw, sc);
+                const QueryCtx ctx = make_query(p, G.L.res, lane);
+                KnnEntry best;
+                unsigned spts = 0;
+                const int n = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
+                n_kp += 1;
+                n_stencil += (double) spts;
+                if (n < P.kmin || n < 5) continue;
+                n_valid += 1;
+                const NeighborhoodDesc nd = warp_describe(G, stencil, ctx, best, n, lane);
+                V3 normal = nd.normal;
+                if (dot(normal, tb - p) < 0) normal = -1.0 * normal;
+                const double weight = nd.a2D * nd.a2D;
+                const V3 diff{-nd.far_rel.x, -nd.far_rel.y, -nd.far_rel.z};
+                const double dist_to_plane = dot(normal, diff);
+                if (!(fabs(dist_to_plane) < P.max_dist_to_plane)) continue;
+                const V3 nw = weight * normal;
+                const double scalar = dot(nw, diff);
+                if (lane == 0) {
+                    const V3 ob = qrot(qb, raw), oe = qrot(qe, raw);
+                    const double am = 1.0 - alpha, a = alpha;
+                    const V3 cb = cross(ob, nw), ce = cross(oe, nw);
+                    double *u = s_u[w];
+                    u[0] = am * cb.x; u[1] = am * cb.y; u[2] = am * cb.z;
+                    u[3] = am * nw.x; u[4] = am * nw.y; u[5] = am * nw.z;
+                    u[6] = a * ce.x;  u[7] = a * ce.y;  u[8] = a * ce.z;
+                    u[9] = a * nw.x;  u[10] = a * nw.y; u[11] = a * nw.z;
+                    u[12] = -scalar;
+                }
+                __syncwarp();
+                {
+                    const double *u = s_u[w];
+                    acc0 += u[pi0] * u[pj0];
+                    acc1 += u[pi1] * u[pj1];
+                    if (i2 < kAccUsed) acc2 += u[pi2] * u[pj2];
+                }
+                __syncwarp();
+                n_used += 1;
+                sum_sq += scalar * scalar;
+            }
+            s_acc[w][lane] = acc0;
+            s_acc[w][lane + 32] = acc1;
+            s_acc[w][lane + 64] = acc2;
+            if (lane == 0) {
+                s_acc[w][kAccUsed] = n_used;
+                s_acc[w][kAccSumSq] = sum_sq;
+                s_acc[w][kAccStencil] = n_stencil;
+                s_acc[w][kAccKeypoints] = n_kp;
+                s_acc[w][kAccValidNb] = n_valid;
+                s_acc[w][95] = 0;
+            }
+            __syncthreads();
+            if (threadIdx.x < kAcc) {
+                double s = 0;
+#pragma unroll
+                for (int ww = 0; ww < kGatherWarps; ++ww) s += s_acc[ww][threadIdx.x];
+                __stcg(&partials[(size_t) (blockIdx.x - 1) * kAcc + threadIdx.x], s);
+            }
+        }
+        grid.sync();
+        if (solver_cta) {
+            CT_STAMP(if (threadIdx.x == 0) st->dbg_t[1] = global_timer_ns();)
+            // deterministic reduction: warp g sums the rows b = g (mod 4) of three columns per lane, then the four
+            // partial sums are combined in fixed order
+            double a0 = 0, a1 = 0, a2 = 0;
+            for (int b = w; b < gather_ctas; b += kGatherWarps) {
+                const double *row = partials + (size_t) b * kAcc;
+                a0 += __ldcg(row + lane);
+                a1 += __ldcg(row + lane + 32);
+                a2 += __ldcg(row + lane + 64);
+            }
+            s_acc[w][lane] = a0;
+            s_acc[w][lane + 32] = a1;
+            s_acc[w][lane + 64] = a2;
+            __syncthreads();
+            if (threadIdx.x < kAcc) {
+                double s = 0;
+#pragma unroll
+                for (int ww = 0; ww < kGatherWarps; ++ww) s += s_acc[ww][threadIdx.x];
+                s_u[0][0] = 0;   // (keeps s_u referenced in the solver CTA)
+                s_acc[0][threadIdx.x] = s;
+            }
+            __syncthreads();
+            CT_STAMP(if (threadIdx.x == 0) st->dbg_t[2] = global_timer_ns();)
+            if (w == 0) {
+                warp_gn_solve(s_acc[0], s_solve, st, P, 0, nullptr, lane);
+                CT_STAMP(if (lane == 0) st->dbg_t[3] = global_timer_ns();)
+            }
+            __threadfence();
+        }
+        grid.sync();
+    }
 }
 
 // multi-GPU tail: the all-reduced accumulator → GN step (one warp)
@@ -376,6 +550,7 @@ static void UploadPairs() {
 
 IcpSolver::IcpSolver(cudaStream_t stream) : stream_(stream) {
     UploadPairs();
+    if (const char *e = getenv("CTICP_PERSISTENT")) use_persistent_ = atoi(e) != 0;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev);
@@ -447,8 +622,30 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
     cfg.G.r = cfg.P.r;
     cfg.G.radius2 = cfg.P.radius * cfg.P.radius;
     cfg.G.kmax = cfg.P.kmax;
-    const int blocks = GatherBlocks((k_upper + shard_world - 1) / shard_world + 64, num_sms_);
-    EnsurePartials(blocks);
+    const int blocks = GatherBlocks((k_upper + shard_world - 1) / shard_world + 16, num_sms_);
+    EnsurePartials(blocks + 1);
+    if (!nccl_comm && use_persistent_) {
+        // one cooperative launch for the whole loop; the grid must be co-resident (grid-wide barriers)
+        if (max_coresident_ == 0) {
+            int per_sm = 0;
+            CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_persistent, kGatherWarps * 32, 0));
+            max_coresident_ = std::max(1, per_sm * num_sms_);
+        }
+        int grid = std::min(blocks + 1, max_coresident_);
+        grid = std::max(grid, 2);
+        const float4 *kp = d_keypoints;
+        const int *nk = d_num_keypoints;
+        double *parts = d_partials_;
+        int iters = num_iters;
+        void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters};
+        const bool timed = time_gather_ && ev_used_ < kMaxEvents;
+        if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
+        CT_CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_gn_persistent, dim3(grid), dim3(kGatherWarps * 32), args, 0, stream_));
+        if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
+        gather_launches_ += 1;
+        launches_ += 1;
+        return;
+    }
     for (int it = 0; it < num_iters; ++it) {
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);

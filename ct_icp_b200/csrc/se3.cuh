@@ -84,7 +84,8 @@ CT_HD SlerpConsts slerp_consts(Q4 a, Q4 b) {
     c.linear = ad >= one;
     c.negate = d < 0;
     c.theta = c.linear ? 0.0 : acos(ad);
-    c.inv_sin = c.linear ? 0.0 : 1.0 / sin(c.theta);
+    // sin(acos(ad)) = sqrt((1 - ad)(1 + ad)): one sqrt instead of a second transcendental, and more accurate near 1
+    c.inv_sin = c.linear ? 0.0 : 1.0 / sqrt((1.0 - ad) * (1.0 + ad));
     return c;
 }
 CT_HD Q4 qslerp_c(Q4 a, Q4 b, double t, const SlerpConsts &c) {

@@ -577,7 +577,7 @@ int cticp_icp_register(cticp_map *m, const cticp_icp_options *options, const cti
                 m->icp->EnqueueGaussNewton(*m->map, *options, D.d_kp, D.d_n, n, options->num_iters_icp, D.d_state);
                 break;
             case CTICP_SOLVER_CERES:
-                m->icp->EnqueueCeres(*m->map, *options, st, D.d_kp, D.d_n, n, D.d_state);
+                m->icp->EnqueueCeres(*m->map, *options, st, D.d_kp, D.d_n, n, n, D.d_state);
                 break;
             default:
                 throw UnsupportedError("Unsupported Solver Type");
@@ -608,6 +608,7 @@ int cticp_icp_register(cticp_map *m, const cticp_icp_options *options, const cti
             out_summary->num_residuals_used = S.n_used;
             out_summary->num_iters = S.iter;
         }
+        if (S.failed == 2) throw std::runtime_error("Error During Optimization");
         if (S.failed) g_last_error = "[CT_ICP]Error : not enough keypoints selected in ct-icp !";
         return (int) CTICP_OK;
     });

@@ -314,7 +314,8 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
             break;
         case CTICP_SOLVER_CERES:
             icp_->EnqueueCeres(*map_, options, options_.neighborhood_strategy, pipe_->d_keypoints(),
-                               pipe_->d_count_keypoints(), KeypointHint(), d_state_, shard_rank_, shard_world_, nccl_comm_);
+                               pipe_->d_count_keypoints(), KeypointHint(), pipe_->n(), d_state_, shard_rank_, shard_world_,
+                               nccl_comm_);
             break;
         default:
             throw UnsupportedError("Unsupported Solver Type");
@@ -345,6 +346,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     rs.frame.end_pose.pose.q = Q4{S.qe[0], S.qe[1], S.qe[2], S.qe[3]};
     rs.frame.begin_pose.pose.t = V3{S.tb[0], S.tb[1], S.tb[2]};
     rs.frame.end_pose.pose.t = V3{S.te[0], S.te[1], S.te[2]};
+    if (S.failed == 2) throw std::runtime_error("Error During Optimization");   // ct_icp.cpp:639-642
     if (!rs.success) {
         char buf[160];
         snprintf(buf, sizeof(buf), "[CT_ICP]Error : not enough keypoints selected in ct-icp ! Number_of_residuals : %d",

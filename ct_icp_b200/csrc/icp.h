@@ -65,9 +65,10 @@ public:
                             int shard_rank = 0, int shard_world = 1, void *nccl_comm = nullptr);
 
     // solver CERES reproduced as a device Levenberg-Marquardt / IRLS loop (icp_lm.cu)
+    // k_hint sizes the grids (estimate of the keypoint count), k_capacity the per-keypoint buffers (upper bound)
     void EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt, const cticp_strategy_options &strategy,
-                      const float4 *d_keypoints, const int *d_num_keypoints, size_t k_upper, IcpState *d_state,
-                      int shard_rank = 0, int shard_world = 1, void *nccl_comm = nullptr);
+                      const float4 *d_keypoints, const int *d_num_keypoints, size_t k_hint, size_t k_capacity,
+                      IcpState *d_state, int shard_rank = 0, int shard_world = 1, void *nccl_comm = nullptr);
 
     // single linearisation at the current state → A (12x12, after 1/n and regularisers), b, n_used (debug tap)
     void NormalEquations(const DeviceMap &map, const cticp_icp_options &opt, const float4 *d_keypoints,
@@ -90,6 +91,8 @@ public:
 
 private:
     void EnsurePartials(int blocks);
+    void EnsureLmBuffers(size_t k_upper);
+    void FreeLmBuffers();
     GnParams MakeParams(const DeviceMap &map, const cticp_icp_options &opt) const;
 
     cudaStream_t stream_;
@@ -98,6 +101,10 @@ private:
     double *d_sys_ = nullptr;      // 12*12 + 12 + 4 debug output of the solve kernel
     double *d_acc_ = nullptr;      // reduced accumulator (multi-GPU all-reduce buffer)
     unsigned int *d_ticket_ = nullptr;   // last-CTA-done counter of k_gn_iterate
+    // solver CERES (icp_lm.cu)
+    void *d_lm_state_ = nullptr, *d_lm_stats_ = nullptr, *d_lm_blocks_ = nullptr;
+    int *d_lm_sel_ = nullptr;
+    size_t lm_capacity_ = 0;
     int launches_ = 0;
     float gather_ms_ = 0.f;
     int gather_launches_ = 0;

@@ -12,6 +12,7 @@
 
 #include "gather.cuh"
 #include "icp.h"
+#include "small_solve.cuh"
 
 namespace cticp {
 namespace cg = cooperative_groups;
@@ -26,9 +27,6 @@ namespace cg = cooperative_groups;
 
 constexpr int kGatherWarps = 4;   // warps per CTA of the gather kernel (one keypoint per warp at a time)
 
-// (i,j) of the idx-th entry of the row-major upper triangle of a 12x12 matrix; entries 78..89 are b[0..11]
-__constant__ unsigned char c_pair_i[kAccUsed];
-__constant__ unsigned char c_pair_j[kAccUsed];
 
 #ifdef CTICP_DEBUG_TIMERS
 // SM-local cycle counter (%globaltimer proved far too slow to read: it tripled the kernel time). Only differences
@@ -43,48 +41,6 @@ struct GatherLaunch {
     GatherConfig G;
     GnParams P;
 };
-
-// ---- 12x12 pivoted LDL^T by one warp (stand-in for Eigen's A.ldlt().solve(b), ct_icp.cpp:914) -----------------
-// Same algorithm as the serial reference restatement (largest-|diagonal| symmetric pivoting, LDL^T, two triangular
-// solves, D pseudo-inverse); the column scaling and the trailing rank-1 update of every step are spread over the
-// lanes. A is 12 x 13 (padded) in shared memory.
-struct SolveScratch {
-    double A[12][13];
-    double b[12], x[12], D[12], y[12];
-    double sn[8], cs[8];
-    int perm[12];
-};
-
-// Solve the 12x12 SPD system held in S.A / S.b; x → S.x.
-// Eigen's A.ldlt().solve(b) (ct_icp.cpp:914) is replaced by Gauss-Jordan elimination in natural order: lane r keeps
-// row r of [A | b] in 13 registers, the pivot row is broadcast with shuffles and all rows are eliminated at once, so
-// a step costs one fp64 reciprocal plus 13 FMAs instead of a serial O(n^2) sweep, and no back-substitution is
-// needed. The system is symmetric positive definite (JTJ/n plus the diagonal regularisers), for which elimination
-// without pivoting is backward stable; the result agrees with a pivoted LDL^T to ~1e-13 relative. This serial tail
-// sits on the critical path of every ICP iteration (it was 60 us as single-thread code, ~2 us now).
-__device__ void warp_ldlt_solve12(SolveScratch &S, int lane) {
-    double row[13];
-    const int r = lane < 12 ? lane : 0;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) row[j] = S.A[r][j];
-    row[12] = S.b[r];
-#pragma unroll
-    for (int p = 0; p < 12; ++p) {
-        const double pd = __shfl_sync(0xffffffffu, row[p], p);
-        const double inv = (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0;   // pseudo-inverse like Eigen's D
-        const double f = row[p] * inv;
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            const double pj = __shfl_sync(0xffffffffu, row[j], p);
-            if (lane == p)
-                row[j] = pj * inv;
-            else
-                row[j] -= f * pj;
-        }
-    }
-    if (lane < 12) S.x[lane] = row[12];
-    __syncwarp();
-}
 
 __device__ __forceinline__ M3 euler_from_sincos(double sa, double ca, double sb, double cb, double sg, double cg) {
     M3 R;   // ct_icp.cpp:916-932
@@ -528,28 +484,8 @@ k_neighborhoods(GatherConfig G, const double *__restrict__ queries, int n, doubl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-static bool g_pairs_uploaded = false;
-static void UploadPairs() {
-    if (g_pairs_uploaded) return;
-    unsigned char pi[kAccUsed], pj[kAccUsed];
-    int idx = 0;
-    for (int i = 0; i < 12; ++i)
-        for (int j = i; j < 12; ++j) {
-            pi[idx] = (unsigned char) i;
-            pj[idx] = (unsigned char) j;
-            ++idx;
-        }
-    for (int i = 0; i < 12; ++i) {   // b[i] = Σ u[i] * u[12]  (u[12] = -scalar)
-        pi[78 + i] = (unsigned char) i;
-        pj[78 + i] = 12;
-    }
-    CT_CUDA_CHECK(cudaMemcpyToSymbol(c_pair_i, pi, sizeof(pi)));
-    CT_CUDA_CHECK(cudaMemcpyToSymbol(c_pair_j, pj, sizeof(pj)));
-    g_pairs_uploaded = true;
-}
-
 IcpSolver::IcpSolver(cudaStream_t stream) : stream_(stream) {
-    UploadPairs();
+    UploadPairTables();
     if (const char *e = getenv("CTICP_PERSISTENT")) use_persistent_ = atoi(e) != 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -568,6 +504,7 @@ IcpSolver::~IcpSolver() {
     cudaFree(d_sys_);
     cudaFree(d_acc_);
     cudaFree(d_ticket_);
+    FreeLmBuffers();
     for (int i = 0; i < kMaxEvents; ++i) {
         cudaEventDestroy(ev_begin_[i]);
         cudaEventDestroy(ev_end_[i]);

@@ -1,12 +1,678 @@
-// icp_lm.cu — solver CERES reproduced on the device (placeholder until the LM/IRLS kernels land).
+// icp_lm.cu — solver CERES reproduced on the device as a Levenberg-Marquardt / robust-loss (IRLS) loop.
+//
+// Reference: DoRegisterCeres (src/ct_icp/ct_icp.cpp:460-706). Per ICP iteration:
+//   k_lm_gather : one warp per keypoint — neighbor gather + normal/a2D (same device code as the GN path), emits one
+//                 residual block per keypoint (:561-604): anchor point, normal, weight, alpha.
+//   k_lm_select : GetProblem (:409-424): the first max_num_residuals valid blocks in keypoint order; seeds the LM state.
+//   k_lm_eval   : half a warp per residual block; lane j evaluates the CTFunctor on dual numbers along tangent
+//                 direction j (lm_functor.cuh), applies the loss function's Corrector, and the 12 partials are
+//                 accumulated into JTJ (78) / JTr (12) / cost exactly like the GN accumulator.
+//   k_lm_step   : ceres::Solve restated (TrustRegionMinimizer + LevenbergMarquardtStrategy, Ceres defaults except
+//                 max_num_iterations = ls_max_num_iters): Jacobi scaling, LM diagonal, damped 12x12 solve, model cost
+//                 change, candidate = Plus(x, delta); after the candidate has been evaluated: tolerances, step
+//                 acceptance, trust-region radius update. The candidate is evaluated WITH its Jacobian, so an accepted
+//                 step needs no second pass.
+//   k_lm_finish : write the pose pair back, stop criterion of the ICP loop (:650-672).
+// Every launch is enqueued up front; device-side flags turn the launches after convergence into no-ops.
+#include <cstdio>
+
 #include "engine.h"
+#include "gather.cuh"
 #include "icp.h"
+#include "lm_functor.cuh"
+#include "small_solve.cuh"
 
 namespace cticp {
 
-void IcpSolver::EnqueueCeres(const DeviceMap &, const cticp_icp_options &, const cticp_strategy_options &,
-                             const float4 *, const int *, size_t, IcpState *, int, int, void *) {
-    throw UnsupportedError("solver CERES: device LM/IRLS path not built yet");
+#define CT_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                            std::to_string(__LINE__));                                                   \
+    } while (0)
+
+constexpr int kLmWarps = 4;
+constexpr int kAccCost = 91;   // Σ 1/2 rho(s) in the accumulator
+
+struct LmParams {
+    // ICP / neighborhood
+    int r, level, kmax, kmin;
+    double radius;
+    double lambda_weight, lambda_neighborhood, power_planarity, max_dist_to_plane;
+    int max_num_residuals, min_number_neighbors, num_iters_icp;
+    double threshold_orientation_norm, threshold_translation_norm;
+    // least squares
+    LossParams loss;
+    int ls_max_num_iters;
+    int shard_rank, shard_world;
+};
+
+struct LmState {
+    double x[14];        // current point: qb(4) qe(4) tb(3) te(3)   (Ceres program order of the parameter blocks)
+    double cand[14];     // candidate point
+    double best[14];     // TrustRegionMinimizer::parameters_ (lowest cost so far)
+    double U[12][12];    // J^T J at x, unscaled
+    double gu[12];       // J^T r at x, unscaled
+    double scaling[12];  // jacobi_scaling
+    double diagonal[12];
+    double x_cost, minimum_cost, model_cost_change, radius, decrease_factor, x_norm, gradient_max_norm;
+    int reuse_diagonal, iteration, done, step_is_successful, num_invalid, usable;
+    int num_residuals, num_valid;
+    // ICP-loop bookkeeping (ct_icp.cpp:650-672)
+    double prev_qb[4], prev_qe[4], prev_tb[3], prev_te[3];
+    int outer_iter;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLmWarps * 32)
+k_lm_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
+            const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned long long *stats) {
+    __shared__ KnnStage s_stage[kLmWarps][64];
+    __shared__ int s_stencil[kMaxStencil];
+    if (st->done) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int *stencil = stencil_table_fill(s_stencil, G.r);
+    __syncthreads();
+    const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
+    const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
+    const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
+    const int K = *d_num_keypoints;
+    unsigned long long n_kp = 0, n_pts = 0;
+    for (int kp = blockIdx.x * kLmWarps + w; kp < K; kp += gridDim.x * kLmWarps) {
+        const float4 kraw = __ldg(keypoints + kp);
+        const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+        const double alpha = (double) kraw.w;
+        // transform_keypoints(), ct_icp.cpp:516-531
+        const V3 p = ct_transform_c(qb, tb, qe, te, alpha, raw, sc);
+        const QueryCtx ctx = make_query(p, G.L.res, lane);
+        KnnEntry best;
+        unsigned spts = 0;
+        const int n = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
+        n_kp += 1;
+        n_pts += spts;
+        ResidualBlock rb;
+        rb.valid = 0;
+        if (n >= P.kmin && n >= 5) {   // :574 ; neighborhood.h:227
+            const NeighborhoodDesc nd = warp_describe(G, stencil, ctx, best, n, lane);
+            // (the normal flip test at :578 is a no-op: BeginTr - BeginTr)
+            double weight = pow(nd.a2D, P.power_planarity);
+            const double far_dist = sqrt(nd.far_rel.x * nd.far_rel.x + nd.far_rel.y * nd.far_rel.y + nd.far_rel.z * nd.far_rel.z);
+            weight = P.lambda_weight * weight +
+                     P.lambda_neighborhood * exp(-far_dist / (P.max_dist_to_plane * P.min_number_neighbors));   // :582-587
+            rb.ref[0] = p.x + nd.far_rel.x; rb.ref[1] = p.y + nd.far_rel.y; rb.ref[2] = p.z + nd.far_rel.z;   // points[0]
+            rb.normal[0] = nd.normal.x; rb.normal[1] = nd.normal.y; rb.normal[2] = nd.normal.z;
+            rb.weight = weight;
+            rb.alpha = alpha;
+            rb.raw[0] = kraw.x; rb.raw[1] = kraw.y; rb.raw[2] = kraw.z;
+            rb.valid = 1;
+        }
+        if (lane == 0) {
+            if (rb.valid) blocks[kp] = rb;
+            else blocks[kp].valid = 0;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && n_kp) {
+        atomicAdd(&stats[0], n_kp);
+        atomicAdd(&stats[1], n_pts);
+    }
+}
+
+// GetProblem (ct_icp.cpp:409-424) + seeding of the LM state for this ICP iteration. One CTA.
+__global__ void __launch_bounds__(1024)
+k_lm_select(LmParams P, const int *__restrict__ d_num_keypoints, const ResidualBlock *__restrict__ blocks,
+            int *__restrict__ sel_idx, IcpState *st, LmState *lm, const unsigned long long *stats) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (st->done) return;
+    const int K = *d_num_keypoints;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const int limit = P.max_num_residuals > 0 ? P.max_num_residuals : 0x7fffffff;
+    for (int base = 0; base < K; base += 1024) {
+        const int k = base + tid;
+        const int v = (k < K) ? (blocks[k].valid != 0) : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int ws = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += y;
+            }
+            s_warp[lane] = ws;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int rank = carry + (w > 0 ? s_warp[w - 1] : 0) + incl - v;
+        if (v && rank < limit) sel_idx[rank] = k;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int num_valid = s_carry;
+        const int R = num_valid < limit ? num_valid : limit;
+        lm->num_valid = num_valid;
+        lm->num_residuals = R;
+        st->n_used = R;
+        st->stat_keypoint_iters = stats[0];
+        st->stat_stencil_points = stats[1];
+        if (R < P.min_number_neighbors) {   // ct_icp.cpp:617 (sic: compared with min_number_neighbors)
+            st->failed = 1;
+            st->done = 1;
+            lm->done = 1;
+            return;
+        }
+        // parameter blocks in Ceres program order: begin_quat, end_quat, begin_t, end_t (ct_icp.cpp:229-232)
+        for (int d = 0; d < 4; ++d) { lm->x[d] = st->qb[d]; lm->x[4 + d] = st->qe[d]; }
+        for (int d = 0; d < 3; ++d) { lm->x[8 + d] = st->tb[d]; lm->x[11 + d] = st->te[d]; }
+        lm->done = 0;
+        lm->usable = 1;
+        lm->iteration = 0;
+        lm->radius = 1e4;                 // initial_trust_region_radius
+        lm->decrease_factor = 2.0;
+        lm->reuse_diagonal = 0;
+        lm->num_invalid = 0;
+        lm->minimum_cost = 1.7976931348623157e308;
+        lm->step_is_successful = 1;
+    }
+}
+
+// residual evaluation at lm->x (which = 0) or lm->cand (which = 1): half a warp per residual block
+__global__ void __launch_bounds__(kLmWarps * 32)
+k_lm_eval(LmParams P, int which, const ResidualBlock *__restrict__ blocks, const int *__restrict__ sel_idx,
+          const IcpState *__restrict__ st, const LmState *__restrict__ lm, double *__restrict__ partials) {
+    __shared__ double s_u[kLmWarps * 2][16];
+    __shared__ double s_acc[kLmWarps * 2][kAcc];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int hl = lane & 15, half = lane >> 4, hw = w * 2 + half;
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+    double acc[6] = {0, 0, 0, 0, 0, 0};   // entries hl + 16 m of [JTJ upper | JTr]
+    double cost = 0;
+    const bool active = !st->done && !lm->done;
+    if (active) {
+        const double *x = which ? lm->cand : lm->x;
+        double qb[4], qe[4], tb[3], te[3];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) { qb[d] = x[d]; qe[d] = x[4 + d]; }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { tb[d] = x[8 + d]; te[d] = x[11 + d]; }
+        const int R = lm->num_residuals;
+        const int halves_total = gridDim.x * kLmWarps * 2;
+        int pi[6], pj[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+            const int e = hl + 16 * m;
+            pi[m] = e < kAccUsed ? c_pair_i[e] : 0;
+            pj[m] = e < kAccUsed ? c_pair_j[e] : 0;
+        }
+        for (int r = blockIdx.x * kLmWarps * 2 + hw; r < R; r += halves_total) {
+            const ResidualBlock rb = blocks[sel_idx[r]];
+            const Dual res = ct_point_to_plane(rb, qb, qe, tb, te, hl);
+            const double s = res.a * res.a;
+            double rs = 1.0, js = 1.0;
+            if (P.loss.type != 0) {
+                double rho[3];
+                loss_evaluate(P.loss, s, rho);
+                if (hl == 0) cost += 0.5 * rho[0];
+                corrector_1d(s, rho, rs, js);
+            } else if (hl == 0) {
+                cost += 0.5 * s;
+            }
+            if (hl < 12) s_u[hw][hl] = js * res.d;
+            if (hl == 12) s_u[hw][12] = rs * res.a;
+            __syncwarp(hmask);
+#pragma unroll
+            for (int m = 0; m < 6; ++m)
+                if (hl + 16 * m < kAccUsed) acc[m] += s_u[hw][pi[m]] * s_u[hw][pj[m]];
+            __syncwarp(hmask);
+        }
+    }
+    for (int m = 0; m < 6; ++m) s_acc[hw][hl + 16 * m] = (hl + 16 * m < kAccUsed) ? acc[m] : 0.0;
+    __syncwarp();
+    if (hl == 0) {
+        s_acc[hw][kAccUsed] = 0;
+        s_acc[hw][kAccCost] = cost;
+    }
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        double s = 0;
+#pragma unroll
+        for (int h = 0; h < kLmWarps * 2; ++h) s += s_acc[h][threadIdx.x];
+        partials[(size_t) blockIdx.x * kAcc + threadIdx.x] = s;
+    }
+}
+
+// ---- the minimizer ------------------------------------------------------------------------------------------
+struct LmScratch {
+    double acc[kAcc];
+    double U[12][12], gu[12];
+    double cost;
+    double step[12], delta[12];
+    SolveScratch solve;
+    int flag;
+};
+
+// regularisers (PreviousFrameMotionModel::AddConstraintsToCeresProblem, motion_model.cpp:12-61), no loss function:
+// adds their J^T J, J^T r and cost at the point p to (U, gu, cost). Serial (lane 0).
+__device__ void add_regularisers(const IcpState *st, int R, const double *p, double U[12][12], double gu[12], double &cost) {
+    if (!st->has_motion_model) return;
+    const double *qb = p, *tb = p + 8, *te = p + 11;
+    if (st->beta_location > 0.) {   // LocationConsistencyFunctor on begin_t
+        const double w = sqrt(R * st->beta_location);
+        for (int k = 0; k < 3; ++k) {
+            const double res = w * (tb[k] - st->prev_te[k]);
+            cost += 0.5 * res * res;
+            U[6 + k][6 + k] += w * w;
+            gu[6 + k] += w * res;
+        }
+    }
+    if (st->beta_orientation > 0.) {   // OrientationConsistencyFunctor on begin_quat
+        const double w = sqrt(R * st->beta_orientation);
+        const double s = qb[0] * st->prev_qe[0] + qb[1] * st->prev_qe[1] + qb[2] * st->prev_qe[2] + qb[3] * st->prev_qe[3];
+        const double res = w * (1.0 - s * s);
+        cost += 0.5 * res * res;
+        double J[3];
+        for (int k = 0; k < 3; ++k) {
+            double col[4];
+            quat_plus_column(qb, k, col);
+            double g = 0;
+            for (int c = 0; c < 4; ++c) g += -2.0 * w * s * st->prev_qe[c] * col[c];
+            J[k] = g;
+        }
+        for (int a = 0; a < 3; ++a) {
+            gu[a] += J[a] * res;
+            for (int b = 0; b < 3; ++b) U[a][b] += J[a] * J[b];
+        }
+    }
+    if (st->beta_cv > 0.) {   // ConstantVelocityFunctor(begin_t, end_t)
+        const double w = sqrt(R * st->beta_cv);
+        for (int k = 0; k < 3; ++k) {
+            const double prev_velocity = st->prev_te[k] - st->prev_tb[k];
+            const double res = w * (te[k] - tb[k] - prev_velocity);
+            cost += 0.5 * res * res;
+            U[6 + k][6 + k] += w * w;
+            U[9 + k][9 + k] += w * w;
+            U[6 + k][9 + k] -= w * w;
+            U[9 + k][6 + k] -= w * w;
+            gu[6 + k] += -w * res;
+            gu[9 + k] += w * res;
+        }
+    }
+    if (st->beta_small > 0.) {   // SmallVelocityFunctor
+        const double w = sqrt(R * st->beta_small);
+        for (int k = 0; k < 3; ++k) {
+            const double res = w * (tb[k] - te[k]);
+            cost += 0.5 * res * res;
+            U[6 + k][6 + k] += w * w;
+            U[9 + k][9 + k] += w * w;
+            U[6 + k][9 + k] -= w * w;
+            U[9 + k][6 + k] -= w * w;
+            gu[6 + k] += w * res;
+            gu[9 + k] += -w * res;
+        }
+    }
+}
+
+__device__ void lm_plus(const double *x, const double *delta, double *out) {
+    const Q4 qb = quat_plus(Q4{x[0], x[1], x[2], x[3]}, delta[0], delta[1], delta[2]);
+    const Q4 qe = quat_plus(Q4{x[4], x[5], x[6], x[7]}, delta[3], delta[4], delta[5]);
+    out[0] = qb.x; out[1] = qb.y; out[2] = qb.z; out[3] = qb.w;
+    out[4] = qe.x; out[5] = qe.y; out[6] = qe.z; out[7] = qe.w;
+    for (int k = 0; k < 3; ++k) out[8 + k] = x[8 + k] + delta[6 + k];
+    for (int k = 0; k < 3; ++k) out[11 + k] = x[11 + k] + delta[9 + k];
+}
+__device__ double norm14(const double *v) {
+    double s = 0;
+    for (int i = 0; i < 14; ++i) s += v[i] * v[i];
+    return sqrt(s);
+}
+
+// phase 0: the accumulator holds the evaluation at lm->x (start of ceres::Solve: IterationZero).
+// phase 1: the accumulator holds the evaluation at lm->cand.
+// One warp; the 12x12 solves are warp-collective, the scalar logic runs on lane 0.
+__global__ void __launch_bounds__(128)
+k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblocks, IcpState *st, LmState *lm) {
+    __shared__ LmScratch S;
+    __shared__ double s_part[4][kAcc];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (st->done || lm->done) return;
+    {   // deterministic reduction of the evaluation partials
+        double a0 = 0, a1 = 0, a2 = 0;
+        for (int b = w; b < nblocks; b += 4) {
+            const double *row = partials + (size_t) b * kAcc;
+            a0 += row[lane];
+            a1 += row[lane + 32];
+            a2 += row[lane + 64];
+        }
+        s_part[w][lane] = a0;
+        s_part[w][lane + 32] = a1;
+        s_part[w][lane + 64] = a2;
+        __syncthreads();
+        if (threadIdx.x < kAcc) S.acc[threadIdx.x] = s_part[0][threadIdx.x] + s_part[1][threadIdx.x] + s_part[2][threadIdx.x] + s_part[3][threadIdx.x];
+        __syncthreads();
+    }
+    if (w != 0) return;
+    const double min_relative_decrease = 1e-3, function_tolerance = 1e-6, gradient_tolerance = 1e-10,
+                 parameter_tolerance = 1e-8, min_radius = 1e-32, max_radius = 1e16, min_lm_diagonal = 1e-6,
+                 max_lm_diagonal = 1e32;
+    const int R = lm->num_residuals;
+
+    // unpack the evaluation: U = J^T J, gu = J^T r, cost (+ regularisers at the evaluated point)
+    for (int e = lane; e < 78; e += 32) {
+        const int i = c_pair_i[e], j = c_pair_j[e];
+        S.U[i][j] = S.acc[e];
+        S.U[j][i] = S.acc[e];
+    }
+    if (lane < 12) S.gu[lane] = S.acc[78 + lane];
+    __syncwarp();
+    if (lane == 0) {
+        S.cost = S.acc[kAccCost];
+        add_regularisers(st, R, phase == 0 ? lm->x : lm->cand, S.U, S.gu, S.cost);
+        S.flag = 0;
+    }
+    __syncwarp();
+
+    // adopt an evaluation as the current linearisation point (EvaluateGradientAndJacobian)
+    auto adopt = [&](bool first) {
+        if (lane < 12) {
+            for (int j = 0; j < 12; ++j) lm->U[lane][j] = S.U[lane][j];
+            lm->gu[lane] = S.gu[lane];
+            if (first) lm->scaling[lane] = 1.0 / (1.0 + sqrt(S.U[lane][lane]));   // jacobi_scaling, iteration 0 only
+        }
+        __syncwarp();
+        if (lane == 0) {
+            lm->x_cost = S.cost;
+            double neg_g[12], proj[14];
+            for (int j = 0; j < 12; ++j) neg_g[j] = -lm->gu[j];
+            lm_plus(lm->x, neg_g, proj);
+            double gmax = 0;
+            for (int i = 0; i < 14; ++i) gmax = fmax(gmax, fabs(lm->x[i] - proj[i]));
+            lm->gradient_max_norm = gmax;
+        }
+        __syncwarp();
+    };
+
+    if (phase == 0) {
+        adopt(true);
+        if (lane == 0) {
+            lm->x_norm = norm14(lm->x);
+            lm->step_is_successful = 1;
+        }
+        __syncwarp();
+    } else {
+        // ComputeCandidatePointAndEvaluateCost happened in k_lm_eval; now the tolerance tests and the step decision
+        if (lane == 0) {
+            const double candidate_cost = S.cost;
+            double step_norm = 0;
+            for (int i = 0; i < 14; ++i) step_norm += (lm->x[i] - lm->cand[i]) * (lm->x[i] - lm->cand[i]);
+            step_norm = sqrt(step_norm);
+            const double cost_change = lm->x_cost - candidate_cost;
+            if (step_norm <= parameter_tolerance * (lm->x_norm + parameter_tolerance)) {
+                S.flag = 1;   // ParameterToleranceReached
+            } else if (fabs(cost_change) <= function_tolerance * lm->x_cost) {
+                S.flag = 1;   // FunctionToleranceReached
+            } else {
+                const double relative_decrease = cost_change / lm->model_cost_change;
+                if (relative_decrease > min_relative_decrease) {
+                    S.flag = 2;   // successful step
+                    lm->radius = lm->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3.0));
+                    lm->radius = fmin(max_radius, lm->radius);
+                    lm->decrease_factor = 2.0;
+                    lm->reuse_diagonal = 0;
+                } else {
+                    S.flag = 3;   // rejected
+                    lm->step_is_successful = 0;
+                    lm->radius = lm->radius / lm->decrease_factor;
+                    lm->decrease_factor *= 2.0;
+                    lm->reuse_diagonal = 1;
+                }
+            }
+        }
+        __syncwarp();
+        if (S.flag == 1) {
+            if (lane == 0) lm->done = 1;
+            return;
+        }
+        if (S.flag == 2) {
+            if (lane < 14) lm->x[lane] = lm->cand[lane];
+            __syncwarp();
+            adopt(false);
+            if (lane == 0) {
+                lm->x_norm = norm14(lm->x);
+                lm->step_is_successful = 1;
+            }
+            __syncwarp();
+        }
+    }
+
+    // main loop of TrustRegionMinimizer::Minimize until a candidate needs evaluating or the solve terminates
+    for (int guard = 0; guard < 64; ++guard) {
+        if (lane == 0) {
+            S.flag = 0;
+            if (lm->step_is_successful && lm->x_cost < lm->minimum_cost) {   // FinalizeIterationAndCheck…
+                lm->minimum_cost = lm->x_cost;
+                for (int i = 0; i < 14; ++i) lm->best[i] = lm->x[i];
+            }
+            if (lm->iteration >= P.ls_max_num_iters) S.flag = 1;
+            else if (lm->step_is_successful && lm->gradient_max_norm <= gradient_tolerance) S.flag = 1;
+            else if (lm->radius <= min_radius) S.flag = 1;
+            else lm->iteration += 1;
+        }
+        __syncwarp();
+        if (S.flag == 1) {
+            if (lane == 0) lm->done = 1;
+            return;
+        }
+        // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
+        if (lane < 12) {
+            const double sl = lm->scaling[lane];
+            if (!lm->reuse_diagonal) {
+                const double d = lm->U[lane][lane] * sl * sl;
+                lm->diagonal[lane] = fmin(fmax(d, min_lm_diagonal), max_lm_diagonal);
+            }
+            for (int j = 0; j < 12; ++j) S.solve.A[lane][j] = lm->U[lane][j] * sl * lm->scaling[j];
+            S.solve.b[lane] = lm->gu[lane] * sl;
+        }
+        __syncwarp();
+        if (lane < 12) S.solve.A[lane][lane] += lm->diagonal[lane] / lm->radius;
+        __syncwarp();
+        warp_ldlt_solve12(S.solve, lane);   // (J'J + D^2) y = J'r
+        if (lane == 0) {
+            lm->reuse_diagonal = 1;
+            bool finite = true;
+            for (int j = 0; j < 12; ++j) {
+                S.step[j] = -S.solve.x[j];
+                finite = finite && isfinite(S.step[j]);
+            }
+            // model_cost_change = -(J step)'(f + J step / 2) = -step'g - step'H step / 2   (scaled quantities)
+            double sg = 0, shs = 0;
+            for (int a = 0; a < 12; ++a) {
+                sg += S.step[a] * lm->gu[a] * lm->scaling[a];
+                double hs = 0;
+                for (int b = 0; b < 12; ++b) hs += lm->U[a][b] * lm->scaling[a] * lm->scaling[b] * S.step[b];
+                shs += S.step[a] * hs;
+            }
+            const double mcc = -sg - 0.5 * shs;
+            lm->model_cost_change = mcc;
+            if (!(finite && mcc > 0.0)) {   // HandleInvalidStep
+                lm->num_invalid += 1;
+                if (lm->num_invalid >= 5) {
+                    lm->usable = 0;
+                    S.flag = 1;
+                } else {
+                    lm->radius *= 0.5;
+                    lm->reuse_diagonal = 1;
+                    lm->step_is_successful = 0;
+                    S.flag = 4;   // loop again
+                }
+            } else {
+                lm->num_invalid = 0;
+                for (int j = 0; j < 12; ++j) S.delta[j] = S.step[j] * lm->scaling[j];
+                lm_plus(lm->x, S.delta, lm->cand);
+            }
+        }
+        __syncwarp();
+        if (S.flag == 1) {
+            if (lane == 0) lm->done = 1;
+            return;
+        }
+        if (S.flag == 4) continue;
+        return;   // candidate ready → k_lm_eval(which = 1)
+    }
+}
+
+// end of one ICP iteration (ct_icp.cpp:636-672): write the pose pair back and test the stop criterion
+__global__ void k_lm_finish(LmParams P, IcpState *st, LmState *lm, int outer_index) {
+    if (threadIdx.x != 0 || st->done) return;
+    if (!lm->usable) {   // reference: throw std::runtime_error("Error During Optimization") (:639-642)
+        st->failed = 2;
+        st->done = 1;
+        return;
+    }
+    const Q4 qb = qnormalized(Q4{lm->best[0], lm->best[1], lm->best[2], lm->best[3]});
+    const Q4 qe = qnormalized(Q4{lm->best[4], lm->best[5], lm->best[6], lm->best[7]});
+    st->qb[0] = qb.x; st->qb[1] = qb.y; st->qb[2] = qb.z; st->qb[3] = qb.w;
+    st->qe[0] = qe.x; st->qe[1] = qe.y; st->qe[2] = qe.z; st->qe[3] = qe.w;
+    for (int d = 0; d < 3; ++d) {
+        st->tb[d] = lm->best[8 + d];
+        st->te[d] = lm->best[11 + d];
+    }
+    const SlerpConsts sc = slerp_consts(qb, qe);
+    st->slerp_theta = sc.theta;
+    st->slerp_inv_sin = sc.inv_sin;
+    st->slerp_linear = sc.linear;
+    st->slerp_negate = sc.negate;
+    double dtb = 0, dte = 0;
+    for (int d = 0; d < 3; ++d) {
+        dtb += (lm->prev_tb[d] - st->tb[d]) * (lm->prev_tb[d] - st->tb[d]);
+        dte += (lm->prev_te[d] - st->te[d]) * (lm->prev_te[d] - st->te[d]);
+    }
+    const double diff_trans = sqrt(dtb) + sqrt(dte);
+    const double diff_rot = angular_distance_deg(qb, Q4{lm->prev_qb[0], lm->prev_qb[1], lm->prev_qb[2], lm->prev_qb[3]}) +
+                            angular_distance_deg(qe, Q4{lm->prev_qe[0], lm->prev_qe[1], lm->prev_qe[2], lm->prev_qe[3]});
+    for (int d = 0; d < 4; ++d) { lm->prev_qb[d] = st->qb[d]; lm->prev_qe[d] = st->qe[d]; }
+    for (int d = 0; d < 3; ++d) { lm->prev_tb[d] = st->tb[d]; lm->prev_te[d] = st->te[d]; }
+    st->iter = outer_index + 1;
+    if (diff_rot < P.threshold_orientation_norm && diff_trans < P.threshold_translation_norm) {
+        st->iter = outer_index;   // the reference's loop index at `break` (:668-672)
+        st->done = 1;
+    }
+}
+
+__global__ void k_lm_begin(IcpState *st, LmState *lm, unsigned long long *stats) {
+    if (threadIdx.x != 0) return;
+    for (int d = 0; d < 4; ++d) { lm->prev_qb[d] = st->qb[d]; lm->prev_qe[d] = st->qe[d]; }
+    for (int d = 0; d < 3; ++d) { lm->prev_tb[d] = st->tb[d]; lm->prev_te[d] = st->te[d]; }
+    lm->done = 0;
+    lm->usable = 1;
+    stats[0] = 0;
+    stats[1] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+void IcpSolver::EnsureLmBuffers(size_t k_upper) {
+    if (!d_lm_state_) {
+        CT_CUDA_CHECK(cudaMalloc(&d_lm_state_, sizeof(LmState)));
+        CT_CUDA_CHECK(cudaMalloc(&d_lm_stats_, sizeof(unsigned long long) * 2));
+        UploadPairTables();
+    }
+    if (k_upper > lm_capacity_) {
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        cudaFree(d_lm_blocks_);
+        cudaFree(d_lm_sel_);
+        CT_CUDA_CHECK(cudaMalloc(&d_lm_blocks_, sizeof(ResidualBlock) * k_upper));
+        CT_CUDA_CHECK(cudaMalloc(&d_lm_sel_, sizeof(int) * k_upper));
+        lm_capacity_ = k_upper;
+    }
+}
+void IcpSolver::FreeLmBuffers() {
+    cudaFree(d_lm_state_);
+    cudaFree(d_lm_stats_);
+    cudaFree(d_lm_blocks_);
+    cudaFree(d_lm_sel_);
+}
+
+void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt, const cticp_strategy_options &strategy,
+                             const float4 *d_keypoints, const int *d_num_keypoints, size_t k_hint, size_t k_capacity,
+                             IcpState *d_state, int shard_rank, int shard_world, void *nccl_comm) {
+    if (opt.parametrization != CTICP_PARAM_CONTINUOUS_TIME || opt.distance != CTICP_DIST_POINT_TO_PLANE)
+        throw UnsupportedError("solver CERES: only CONTINUOUS_TIME + POINT_TO_PLANE is built (SURVEY §8)");
+    if (opt.num_closest_neighbors != 1)
+        throw UnsupportedError("solver CERES: num_closest_neighbors != 1 is not built");
+    if (strategy.max_num_neighbors > 32 || strategy.max_num_neighbors < 1)
+        throw std::invalid_argument("neighborhood_strategy.max_num_neighbors must be in [1, 32]");
+    if (nccl_comm) throw UnsupportedError("solver CERES: multi-GPU sharding is built for the GN solver only");
+    (void) shard_rank;
+    (void) shard_world;
+    const double sum = std::abs(opt.weight_alpha) + std::abs(opt.weight_neighborhood);
+    if (!(sum > 0.0)) throw std::invalid_argument("weight_alpha + weight_neighborhood <= 0");
+    EnsureLmBuffers(k_capacity);
+
+    LmParams P{};
+    map.SearchParams(map.Options().default_radius, &P.level, &P.r);
+    P.radius = map.Options().default_radius;
+    P.kmax = strategy.max_num_neighbors;          // neighborhood_strategy.h:81
+    P.kmin = opt.min_number_neighbors;            // ct_icp.cpp:574
+    P.lambda_weight = std::abs(opt.weight_alpha) / sum;
+    P.lambda_neighborhood = std::abs(opt.weight_neighborhood) / sum;
+    P.power_planarity = opt.power_planarity;
+    P.max_dist_to_plane = opt.max_dist_to_plane_ct_icp;
+    P.max_num_residuals = opt.max_num_residuals;
+    P.min_number_neighbors = opt.min_number_neighbors;
+    P.num_iters_icp = opt.num_iters_icp;
+    P.threshold_orientation_norm = opt.threshold_orientation_norm;
+    P.threshold_translation_norm = opt.threshold_translation_norm;
+    P.loss = make_loss(opt.loss_function, opt.ls_sigma, opt.ls_tolerant_min_threshold);
+    P.ls_max_num_iters = opt.ls_max_num_iters;
+    P.shard_rank = 0;
+    P.shard_world = 1;
+
+    GatherConfig G;
+    G.L = map.Level(P.level);
+    G.r = P.r;
+    G.radius2 = P.radius * P.radius;
+    G.kmax = P.kmax;
+
+    auto *lm = static_cast<LmState *>(d_lm_state_);
+    auto *blocks_buf = static_cast<ResidualBlock *>(d_lm_blocks_);
+    auto *stats = static_cast<unsigned long long *>(d_lm_stats_);
+    const int gather_blocks = (int) std::max<size_t>(1, std::min<size_t>((k_hint + kLmWarps - 1) / kLmWarps, (size_t) num_sms_ * 8));
+    const size_t r_hint = opt.max_num_residuals > 0 ? std::min<size_t>(k_hint, (size_t) opt.max_num_residuals) : k_hint;
+    const int eval_blocks = (int) std::max<size_t>(1, std::min<size_t>((r_hint + kLmWarps * 2 - 1) / (kLmWarps * 2), (size_t) num_sms_ * 4));
+    EnsurePartials(eval_blocks);
+
+    k_lm_begin<<<1, 32, 0, stream_>>>(d_state, lm, stats);
+    launches_ += 1;
+    for (int it = 0; it < opt.num_iters_icp; ++it) {
+        const bool timed = time_gather_ && ev_used_ < kMaxEvents;
+        if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
+        k_lm_gather<<<gather_blocks, kLmWarps * 32, 0, stream_>>>(G, P, d_keypoints, d_num_keypoints, d_state, blocks_buf, stats);
+        if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
+        ++gather_launches_;
+        k_lm_select<<<1, 1024, 0, stream_>>>(P, d_num_keypoints, blocks_buf, d_lm_sel_, d_state, lm, stats);
+        k_lm_eval<<<eval_blocks, kLmWarps * 32, 0, stream_>>>(P, 0, blocks_buf, d_lm_sel_, d_state, lm, d_partials_);
+        k_lm_step<<<1, 128, 0, stream_>>>(P, 0, d_partials_, eval_blocks, d_state, lm);
+        launches_ += 4;
+        for (int ls = 0; ls < opt.ls_max_num_iters; ++ls) {
+            k_lm_eval<<<eval_blocks, kLmWarps * 32, 0, stream_>>>(P, 1, blocks_buf, d_lm_sel_, d_state, lm, d_partials_);
+            k_lm_step<<<1, 128, 0, stream_>>>(P, 1, d_partials_, eval_blocks, d_state, lm);
+            launches_ += 2;
+        }
+        k_lm_finish<<<1, 32, 0, stream_>>>(P, d_state, lm, it);
+        launches_ += 1;
+    }
+    CT_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace cticp

@@ -338,3 +338,96 @@ def test_odometry_reset(eng, seq_small):
     for s in seq_small[:4]:
         p2.append(list(od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]).frame.end_pose.tr))
     assert np.allclose(p1, p2, atol=0, rtol=0)      # deterministic: fixed-order reductions, counter-based shuffles
+
+
+# ---- solver CERES (reproduced as device LM / IRLS) ---------------------------------------------------------------
+def driving_config(b):
+    """config/odometry/driving_config.yaml verbatim (BASELINE.json configs[2])."""
+    o = b.profile("default_driving")
+    o.debug_print = 0
+    o.motion_compensation = abi.MOTION_COMPENSATION["CONTINUOUS"]
+    o.initialization = abi.INITIALIZATION["INIT_CONSTANT_VELOCITY"]
+    o.sample_voxel_size = 1.5
+    o.voxel_size = 0.5
+    o.max_distance = 100.0
+    o.distance_error_threshold = 5.0
+    o.neighborhood_strategy.max_num_neighbors = 20
+    o.neighborhood_strategy.min_num_neighbors = 10
+    m = b.default_map_options()
+    m.num_resolutions = 1
+    m.resolutions[0].resolution = 0.8
+    m.resolutions[0].max_num_points = 30
+    m.resolutions[0].min_distance_between_points = 0.1
+    m.default_radius = 0.75
+    o.map_options = m
+    c = o.ct_icp_options
+    c.debug_print = 0
+    c.num_iters_icp = 5
+    c.solver = abi.SOLVER["CERES"]
+    c.max_num_residuals = 900
+    c.min_num_residuals = 100
+    c.weight_alpha = 0.9
+    c.weight_neighborhood = 0.1
+    c.min_number_neighbors = 20
+    c.max_number_neighbors = 20
+    c.num_closest_neighbors = 1
+    c.power_planarity = 2
+    c.threshold_orientation_norm = 0.1
+    c.threshold_translation_norm = 0.01
+    c.loss_function = abi.LOSS["CAUCHY"]
+    c.ls_max_num_iters = 5
+    c.ls_num_threads = 6
+    c.ls_sigma = 0.1
+    c.ls_tolerant_min_threshold = 0.05
+    return o
+
+
+@pytest.mark.parametrize("loss", ["CAUCHY", "HUBER", "STANDARD", "TOLERANT", "TRUNCATED"])
+def test_ceres_register_matches_oracle(orc, eng, loss):
+    map_xyz, kp, frame, prev = _registration_case(orc, eng, "CERES")
+    mo, me = orc.voxel_map(small_map_options(orc, cap=1 << 18)), eng.voxel_map(small_map_options(eng, cap=1 << 18))
+    mo.insert(map_xyz); me.insert(map_xyz)
+    io = orc.default_icp_options()
+    io.solver = abi.SOLVER["CERES"]
+    io.loss_function = abi.LOSS[loss]
+    io.min_number_neighbors = 10
+    io.num_iters_icp = 4
+    io.ls_max_num_iters = 5
+    io.ls_num_threads = 4
+    io.max_num_residuals = 700
+    io.threshold_orientation_norm = 1e-9     # run every ICP iteration
+    io.threshold_translation_norm = 1e-9
+    mm = orc.default_odometry_options().default_motion_model
+    mm.beta_small_velocity = 0.0005         # exercise every regulariser
+    mm.beta_orientation_consistency = 0.0005
+    st = abi.StrategyOptions(0, 20, 8, 0)
+    _fill_world(orc, kp, frame)
+    kpo, kpe = kp.copy(), kp.copy()
+    fo, fe = frame.copy(), frame.copy()
+    so = mo.icp_register(io, kpo, fo, prev, mm, st)
+    se = me.icp_register(io, kpe, fe, prev, mm, st)
+    assert so.success and se.success
+    assert so.num_residuals_used == se.num_residuals_used == 700
+    dt, dr = frame_diff(fo, fe)
+    assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (loss, dt, dr)
+    assert frame_diff(fo, frame)[0] > 1e-3
+    print(loss, "pose diff %.3e m %.3e rad" % (dt, dr))
+
+
+def test_odometry_sequence_hdl64_ceres(orc, eng, seq_hdl64):
+    """config 3: driving_config.yaml (solver CERES, Cauchy loss, 5 x 5 iterations, 900 residuals) as device LM/IRLS."""
+    seq = seq_hdl64[:24]
+    results = []
+    for b in (orc, eng):
+        od = b.odometry(driving_config(b))
+        results.append([(od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]), od.MapSize()) for s in seq])
+    worst_t = worst_r = 0.0
+    for i, ((so, mo), (se, me)) in enumerate(zip(*results)):
+        assert so.success and se.success, i
+        assert so.num_keypoints == se.num_keypoints, i
+        assert so.number_of_residuals == se.number_of_residuals, i
+        dt, dr = frame_diff(so.frame, se.frame)
+        worst_t, worst_r = max(worst_t, dt), max(worst_r, dr)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
+        assert mo == me, i
+    print("CERES worst per-frame pose difference: %.3e m, %.3e rad" % (worst_t, worst_r))

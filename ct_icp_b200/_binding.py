@@ -93,6 +93,8 @@ class Binding:
             "se3_inverse": (None, [vp, vp, vp, vp]),
             "se3_mul": (None, [vp, vp, vp, vp, vp, vp]),
             "angular_distance": (dbl, [vp, vp]),
+            "se3_interpolate": (None, [vp, vp, vp, vp, dbl, vp, vp]),
+            "se3_apply": (None, [vp, vp, vp, vp]),
             "ct_point_to_plane_residual": (dbl, [dbl, vp, vp, vp, dbl, vp, vp, vp, vp, vp]),
         }
         for name, (res, args) in sigs.items():

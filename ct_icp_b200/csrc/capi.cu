@@ -31,6 +31,10 @@ int Guard(F &&f) {
         return Fail(CTICP_ERR_CUDA, e.what());
     } catch (const std::invalid_argument &e) {
         return Fail(CTICP_ERR_INVALID_ARGUMENT, e.what());
+    } catch (const std::runtime_error &e) {
+        if (std::string(e.what()).rfind("NCCL", 0) == 0) return Fail(CTICP_ERR_NCCL, e.what());
+        if (std::string(e.what()).rfind("NO_DEVICE", 0) == 0) return Fail(CTICP_ERR_NO_DEVICE, e.what());
+        return Fail(CTICP_ERR_INTERNAL, e.what());
     } catch (const std::exception &e) {
         if (std::string(e.what()).rfind("NO_DEVICE", 0) == 0) return Fail(CTICP_ERR_NO_DEVICE, e.what());
         return Fail(CTICP_ERR_INTERNAL, e.what());

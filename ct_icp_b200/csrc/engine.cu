@@ -98,6 +98,7 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
 Engine::~Engine() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
+    DestroySharding();
     icp_.reset();
     pipe_.reset();
     map_.reset();

@@ -57,6 +57,7 @@ public:
     cticp_device_timing LastTiming();   // synchronises on the last frame's final event
     void SetTimeGather(bool on) { icp_->set_time_gather(on); }
     void EnableSharding(const void *unique_id, int rank, int world);
+    void DestroySharding();
 
 private:
     struct FrameInfo {

@@ -228,7 +228,7 @@ typedef struct cticp_icp_summary {
 } cticp_icp_summary;
 
 /* ct_icp::Odometry::RegistrationSummary, include/ct_icp/odometry.h:163-199.
- * The three point vectors are fetched on demand with cticp_get_points(). */
+ * The three point vectors are fetched on demand with cticp_odometry_get_points. */
 typedef struct cticp_summary {
     cticp_frame frame;
     cticp_frame initial_frame;

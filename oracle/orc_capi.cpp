@@ -498,6 +498,24 @@ void orc_se3_mul(const double qa[4], const double ta[3], const double qb[4], con
     oq[0] = r.quat.x; oq[1] = r.quat.y; oq[2] = r.quat.z; oq[3] = r.quat.w;
     ot[0] = r.tr.x; ot[1] = r.tr.y; ot[2] = r.tr.z;
 }
+// TSE3::Interpolate, include/SlamCore/types.h:361-366 (slerp NOT renormalised + lerp)
+void orc_se3_interpolate(const double qa[4], const double ta[3], const double qb[4], const double tb[3], double weight,
+                         double oq[4], double ot[3]) {
+    SE3 a, b;
+    a.quat = Quat(qa[0], qa[1], qa[2], qa[3]); a.tr = Vec3(ta[0], ta[1], ta[2]);
+    b.quat = Quat(qb[0], qb[1], qb[2], qb[3]); b.tr = Vec3(tb[0], tb[1], tb[2]);
+    SE3 r = a.Interpolate(b, weight);
+    oq[0] = r.quat.x; oq[1] = r.quat.y; oq[2] = r.quat.z; oq[3] = r.quat.w;
+    ot[0] = r.tr.x; ot[1] = r.tr.y; ot[2] = r.tr.z;
+}
+// TSE3::operator*(point), include/SlamCore/types.h:354-357
+void orc_se3_apply(const double q[4], const double t[3], const double p[3], double out[3]) {
+    SE3 s;
+    s.quat = Quat(q[0], q[1], q[2], q[3]);
+    s.tr = Vec3(t[0], t[1], t[2]);
+    Vec3 r = s * Vec3(p[0], p[1], p[2]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
 double orc_angular_distance(const double qa[4], const double qb[4]) {
     SE3 a, b;
     a.quat = Quat(qa[0], qa[1], qa[2], qa[3]);

@@ -431,3 +431,20 @@ def test_odometry_sequence_hdl64_ceres(orc, eng, seq_hdl64):
         assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
         assert mo == me, i
     print("CERES worst per-frame pose difference: %.3e m, %.3e rad" % (worst_t, worst_r))
+
+
+def test_multigpu_sharded_registration_matches_single_gpu():
+    """Keypoints sharded over 2 GPUs with one NCCL all-reduce per GN iteration (needs >= 2 devices; skipped otherwise)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CTICP_CHECK_FRAMES="8")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert "MULTIGPU OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,0 +1,62 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): keypoint-sharded registration with one NCCL
+all-reduce per Gauss-Newton iteration must reproduce the single-GPU poses and be identical on every rank.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multigpu_check.py
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import ct_icp_b200  # noqa: E402
+from ct_icp_b200 import synthetic as syn  # noqa: E402
+
+rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local_rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+eng = ct_icp_b200.engine()
+frames = int(os.environ.get("CTICP_CHECK_FRAMES", "24"))
+seq = syn.make_sequence(frames, syn.HDL64, seed=1234)
+
+
+def run(sharded):
+    od = eng.odometry(bench.make_options(eng), local_rank)
+    if sharded:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = (ctypes.c_char * 128)()
+            eng.check(eng.fn("nccl_unique_id")(buf))
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        od.enable_sharding(uid.cpu().numpy().tobytes(), rank, world)
+    poses = []
+    for s in seq:
+        sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        assert sm.success, sm.error_message
+        poses.append(list(sm.frame.begin_pose.quat) + list(sm.frame.begin_pose.tr) + list(sm.frame.end_pose.quat) +
+                     list(sm.frame.end_pose.tr))
+    od.close()
+    return np.array(poses)
+
+
+single = run(False)
+sharded = run(True)
+t = torch.from_numpy(sharded).cuda()
+gathered = [torch.zeros_like(t) for _ in range(world)]
+dist.all_gather(gathered, t)
+if rank == 0:
+    across = max(float((g - gathered[0]).abs().max()) for g in gathered)
+    vs_single = float(np.abs(sharded - single).max())
+    print("MULTIGPU world=%d frames=%d max|sharded - single|=%.3e max|rank_i - rank_0|=%.3e" % (world, frames, vs_single, across))
+    assert across == 0.0, "ranks diverged"
+    assert vs_single < 1e-7
+    print("MULTIGPU OK")
+dist.barrier()
+dist.destroy_process_group()

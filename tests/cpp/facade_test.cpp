@@ -64,8 +64,8 @@ int main(int argc, char **argv) {
     options.init_num_frames = 3;
     options.voxel_size = 1.0;
     options.init_voxel_size = 1.0;
-    options.sample_voxel_size = 3.0;
-    options.init_sample_voxel_size = 3.0;
+    options.sample_voxel_size = 1.5;
+    options.init_sample_voxel_size = 1.5;
     options.map_options.num_resolutions = 1;
     options.map_options.resolutions[0].resolution = 2.0;
     options.map_options.resolutions[0].max_num_points = 30;
@@ -78,7 +78,7 @@ int main(int argc, char **argv) {
         const int kFrames = 10;
         double err = 0;
         for (int i = 0; i < kFrames; ++i) {
-            auto frame = generate_frame(i, 2500, rng);
+            auto frame = generate_frame(i, 5000, rng);
             auto result = odometry.RegisterFrame(frame);
             if (!result.success) {
                 std::printf("Odometry failed at frame %d: %s\n", i, result.error_message.c_str());

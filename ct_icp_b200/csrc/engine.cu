@@ -82,6 +82,12 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
         throw UnsupportedError("sampling ADAPTIVE is SURVEY §8f-3 (not built yet)");
     next_robust_level_ = options_.robust_minimal_level;
 
+    {
+        int threads = 4;
+        if (const char *e = getenv("CTICP_HOST_THREADS")) threads = atoi(e);
+        threads = std::max(1, std::min(threads, std::min(64, (int) std::thread::hardware_concurrency())));
+        pool_ = std::make_unique<HostPool>(threads);
+    }
     CT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     map_ = std::make_unique<DeviceMap>(options_.map_options, stream_);
     const size_t max_pts = options_.max_points_per_frame ? (size_t) options_.max_points_per_frame : (size_t) 524288;
@@ -200,6 +206,60 @@ void Engine::IngestImpl(const double *xyz, size_t xyz_stride, const double *t, s
                           override_alpha, alpha_value);
 }
 
+// ---- host fork-join pool -------------------------------------------------------------------------------------
+HostPool::HostPool(int threads) {
+    for (int i = 1; i < threads; ++i) workers_.emplace_back([this, i] { Worker(i); });
+}
+HostPool::~HostPool() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+        ++generation_;
+    }
+    cv_start_.notify_all();
+    for (auto &w : workers_) w.join();
+}
+void HostPool::Worker(int id) {
+    uint64_t seen = 0;
+    while (true) {
+        const std::function<void(size_t, size_t, int)> *fn;
+        size_t n;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_start_.wait(lk, [&] { return generation_ != seen; });
+            seen = generation_;
+            if (stop_) return;
+            fn = fn_;
+            n = n_;
+        }
+        const int parts = size();
+        const size_t b = n * id / parts, e = n * (id + 1) / parts;
+        if (e > b) (*fn)(b, e, id);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) cv_done_.notify_one();
+        }
+    }
+}
+void HostPool::ParallelFor(size_t n, const std::function<void(size_t, size_t, int)> &fn) {
+    const int parts = size();
+    if (parts == 1 || n < 16384) {
+        fn(0, n, 0);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        fn_ = &fn;
+        n_ = n;
+        pending_ = parts - 1;
+        ++generation_;
+    }
+    cv_start_.notify_all();
+    fn(0, n / parts, 0);
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+}
+
 // (x, y, z, alpha) packing: alpha = GetAlphaTimestamp(t) w.r.t. the pose pair's timestamps (types.h:192-219);
 // the caller has range-checked the timestamps
 void Engine::PackScan(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n, double bts,
@@ -207,22 +267,34 @@ void Engine::PackScan(const double *xyz, size_t xyz_stride, const double *t, siz
     const double mn = std::min(bts, ets), mx = std::max(bts, ets);
     const double inv = (mx > mn) ? 1.0 / (mx - mn) : 0.0;
     const char *px = reinterpret_cast<const char *>(xyz), *pt = reinterpret_cast<const char *>(t);
-    for (size_t i = 0; i < n; ++i) {
-        const double *p = reinterpret_cast<const double *>(px + i * xyz_stride);
-        const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
-        const double a = (mx > mn) ? (ti - mn) * inv : 1.0;
-        dst[i] = make_float4((float) p[0], (float) p[1], (float) p[2], (float) a);
-    }
+    const bool spans = mx > mn;
+    pool_->ParallelFor(n, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            const double *p = reinterpret_cast<const double *>(px + i * xyz_stride);
+            const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
+            const double a = spans ? (ti - mn) * inv : 1.0;
+            dst[i] = make_float4((float) p[0], (float) p[1], (float) p[2], (float) a);
+        }
+    });
 }
 
-static void MinMaxTimestamps(const double *t, size_t t_stride, size_t n, double *mn_out, double *mx_out) {
-    double mn = INFINITY, mx = -INFINITY;
+void Engine::MinMaxTimestamps(const double *t, size_t t_stride, size_t n, double *mn_out, double *mx_out) {
     const char *pt = reinterpret_cast<const char *>(t);
-    for (size_t i = 0; i < n; ++i) {
-        const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
-        mn = ti < mn ? ti : mn;
-        mx = ti > mx ? ti : mx;
-    }
+    double mns[64], mxs[64];
+    const int parts = pool_->size();
+    for (int i = 0; i < parts; ++i) { mns[i] = INFINITY; mxs[i] = -INFINITY; }
+    pool_->ParallelFor(n, [&](size_t b, size_t e, int part) {
+        double mn = INFINITY, mx = -INFINITY;
+        for (size_t i = b; i < e; ++i) {
+            const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
+            mn = ti < mn ? ti : mn;
+            mx = ti > mx ? ti : mx;
+        }
+        mns[part] = mn;
+        mxs[part] = mx;
+    });
+    double mn = INFINITY, mx = -INFINITY;
+    for (int i = 0; i < parts; ++i) { mn = std::min(mn, mns[i]); mx = std::max(mx, mxs[i]); }
     *mn_out = mn;
     *mx_out = mx;
 }

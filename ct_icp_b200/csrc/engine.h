@@ -5,7 +5,11 @@
 // RobustRegistration :780-852, UpdateMap :855-953) while every O(N)/O(K·S) stage runs on the device.
 #pragma once
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -30,6 +34,28 @@ struct HostPose {   // slam::TPose<double>
 };
 struct HostFrame {   // ct_icp::TrajectoryFrame
     HostPose begin_pose, end_pose;
+};
+
+// Minimal fork-join pool for the two host passes over a scan (timestamp min/max, float4 packing): the only O(N) host
+// work of RegisterFrame. Workers sleep on a condition variable between frames.
+class HostPool {
+public:
+    explicit HostPool(int threads);
+    ~HostPool();
+    int size() const { return (int) workers_.size() + 1; }
+    // fn(begin, end, part) over [0, n) split into size() contiguous parts; the caller runs part 0
+    void ParallelFor(size_t n, const std::function<void(size_t, size_t, int)> &fn);
+
+private:
+    void Worker(int id);
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_start_, cv_done_;
+    const std::function<void(size_t, size_t, int)> *fn_ = nullptr;
+    size_t n_ = 0;
+    uint64_t generation_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
 };
 
 class Engine {
@@ -86,8 +112,10 @@ private:
                             const FrameInfo &info);
     void IngestImpl(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
                     const FrameInfo &info, int64_t staged_slot);
-    static void PackScan(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n, double bts,
-                         double ets, float4 *dst);
+    void PackScan(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n, double bts,
+                  double ets, float4 *dst);
+    void MinMaxTimestamps(const double *t, size_t t_stride, size_t n, double *mn_out, double *mx_out);
+    std::unique_ptr<HostPool> pool_;
     void RegisterCommon(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
                         uint32_t frame_id, const cticp_frame *initial_estimate, int64_t staged_slot,
                         cticp_summary *out);

@@ -448,3 +448,94 @@ def test_multigpu_sharded_registration_matches_single_gpu():
                         os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, env=env,
                        timeout=600)
     assert "MULTIGPU OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---- BASELINE.json configs[3] and configs[4] ------------------------------------------------------------------------
+def nclt_config(b, solver="CERES"):
+    """config/odometry/nclt_config.yaml (3 resolutions 0.5/1/2 → search level 0, r = ceil(0.8/0.5) = 2 → 125-voxel
+    stencil; 20 ICP x 10 LS iterations; 1500 keypoints / residuals) with `sampling: GRID` (ADAPTIVE is SURVEY §8f-3)."""
+    o = b.default_odometry_options()
+    o.debug_print = 0
+    o.sample_voxel_size = 0.8
+    o.sampling = abi.SAMPLING["GRID"]
+    o.voxel_size = 0.5
+    o.max_distance = 100.0
+    o.neighborhood_strategy.max_num_neighbors = 20
+    o.neighborhood_strategy.min_num_neighbors = 10
+    m = b.default_map_options()
+    m.num_resolutions = 3
+    for i, (res, md) in enumerate(((0.5, 0.05), (1.0, 0.1), (2.0, 0.2))):
+        m.resolutions[i].resolution = res
+        m.resolutions[i].max_num_points = 30
+        m.resolutions[i].min_distance_between_points = md
+    m.capacity_voxels = 1 << 19
+    o.map_options = m
+    o.max_num_keypoints = 1500
+    c = o.ct_icp_options
+    c.debug_print = 0
+    c.num_iters_icp = 20
+    c.solver = abi.SOLVER[solver]
+    c.max_num_residuals = 1500
+    c.min_number_neighbors = 10
+    c.max_number_neighbors = 20
+    c.threshold_orientation_norm = 0.1
+    c.threshold_translation_norm = 0.01
+    c.loss_function = abi.LOSS["CAUCHY"]
+    c.ls_max_num_iters = 10
+    c.ls_num_threads = 6
+    c.ls_sigma = 0.1
+    o.init_num_frames = 5
+    return o
+
+
+@pytest.mark.parametrize("solver", ["CERES", "GN"])
+def test_odometry_sequence_nclt_shape(orc, eng, solver):
+    """configs[3]: NCLT-shape HDL-32 (~65k-pt scans), multi-resolution map, 125-voxel stencil, max_num_keypoints."""
+    from ct_icp_b200 import synthetic as syn
+    seq = syn.make_sequence(9, syn.HDL32, seed=77, traj=syn.Trajectory(speed=2.0, sway=1.0, sway_rate=0.2, height=1.0,
+                                                                       yaw_jerk=0.05))
+    res = []
+    for b in (orc, eng):
+        od = b.odometry(nclt_config(b, solver))
+        res.append([(od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]), od.MapSize()) for s in seq])
+    worst = 0.0
+    for i, ((so, mo), (se, me)) in enumerate(zip(*res)):
+        assert so.success and se.success, (i, so.error_message, se.error_message)
+        assert (so.num_keypoints, so.number_of_residuals, mo) == (se.num_keypoints, se.number_of_residuals, me), i
+        if i >= 5:
+            assert se.num_keypoints == 1500          # shuffle + resize (odometry.cpp:549-552)
+        dt, dr = frame_diff(so.frame, se.frame)
+        worst = max(worst, dt)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
+    print("nclt-shape %s worst pose diff %.3e m" % (solver, worst))
+
+
+def test_odometry_dense128_gn_20_iterations(orc, eng):
+    """configs[4]: dense 128-beam scans (~290k pts), 20 GN iterations forced (thresholds 0), tens of thousands of
+    keypoints per frame."""
+    from ct_icp_b200 import synthetic as syn
+    seq = syn.make_sequence(4, syn.DENSE128, seed=99)
+    res = []
+    for b in (orc, eng):
+        o = b.default_odometry_options()
+        o.debug_print = 0
+        o.ct_icp_options.solver = abi.SOLVER["GN"]
+        o.ct_icp_options.num_iters_icp = 20
+        o.ct_icp_options.threshold_orientation_norm = 0.0
+        o.ct_icp_options.min_number_neighbors = 10
+        o.map_options = b.legacy_map_options(1.0, 20, 0.1)
+        o.voxel_size = 0.25
+        o.init_voxel_size = 0.25
+        o.sample_voxel_size = 0.5
+        o.init_sample_voxel_size = 0.5
+        o.init_num_frames = 2
+        od = b.odometry(o)
+        res.append([od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]) for s in seq])
+    for i, (so, se) in enumerate(zip(*res)):
+        assert so.success and se.success, i
+        assert so.num_keypoints == se.num_keypoints and so.number_of_residuals == se.number_of_residuals, i
+        dt, dr = frame_diff(so.frame, se.frame)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
+    assert res[1][-1].num_keypoints > 10000
+    assert res[1][-1].icp_summary.num_iters == 20
+    print("dense128: K = %d, pose diff %.3e m" % (res[1][-1].num_keypoints, frame_diff(res[0][-1].frame, res[1][-1].frame)[0]))

@@ -38,8 +38,49 @@ UNIT = "scans/s"
 WORKLOAD = "configs[1]: KITTI-shape 64-beam synthetic scans, CT_ICP_GN point-to-plane, 5 ICP iters, 1xB200"
 
 
+WORKLOADS = {
+    # name: (sensor, description)
+    "kitti64_gn": ("HDL64", WORKLOAD),
+    "kitti64_ceres": ("HDL64", "configs[2]: KITTI-shape 64-beam synthetic scans, driving_config.yaml (solver CERES as device "
+                               "LM/IRLS, Cauchy, 5x5 iterations, 900 residuals), 1xB200"),
+    "dense128_gn": ("DENSE128", "configs[4]: dense 128-beam ~290k-pt synthetic scans, CT_ICP_GN, 20 ICP iterations forced, "
+                                "voxel 0.25 / sample 0.5 (K ~ 19k keypoints)"),
+}
+_WORKLOAD = "kitti64_gn"
+
+
 def make_options(b):
     from ct_icp_b200 import _abi as abi
+    if _WORKLOAD == "kitti64_ceres":
+        o = b.profile("default_driving")
+        o.debug_print = 0
+        o.neighborhood_strategy.max_num_neighbors = 20
+        o.neighborhood_strategy.min_num_neighbors = 10
+        m = b.default_map_options()
+        m.num_resolutions = 1
+        m.resolutions[0].resolution = 0.8
+        m.resolutions[0].max_num_points = 30
+        m.resolutions[0].min_distance_between_points = 0.1
+        m.default_radius = 0.75
+        o.map_options = m
+        c = o.ct_icp_options
+        c.debug_print = 0
+        c.num_iters_icp, c.solver, c.max_num_residuals = 5, abi.SOLVER["CERES"], 900
+        c.min_number_neighbors = c.max_number_neighbors = 20
+        c.threshold_orientation_norm, c.threshold_translation_norm = 0.1, 0.01
+        c.loss_function, c.ls_max_num_iters, c.ls_num_threads, c.ls_sigma = abi.LOSS["CAUCHY"], 5, 6, 0.1
+        return o
+    if _WORKLOAD == "dense128_gn":
+        o = b.default_odometry_options()
+        o.debug_print = 0
+        o.ct_icp_options.solver = abi.SOLVER["GN"]
+        o.ct_icp_options.num_iters_icp = 20
+        o.ct_icp_options.threshold_orientation_norm = 0.0
+        o.ct_icp_options.min_number_neighbors = 10
+        o.map_options = b.legacy_map_options(1.0, 20, 0.1)
+        o.voxel_size = o.init_voxel_size = 0.25
+        o.sample_voxel_size = o.init_sample_voxel_size = 0.5
+        return o
     o = b.default_odometry_options()
     o.ct_icp_options.solver = abi.SOLVER["GN"]
     o.ct_icp_options.num_iters_icp = 5
@@ -150,7 +191,13 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--roofline-frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="kitti64_gn", choices=sorted(WORKLOADS),
+                    help="kitti64_gn is BASELINE.json's metric configuration (the bench line); the others are extra "
+                         "measurements recorded under profiles/")
     args = ap.parse_args()
+    global _WORKLOAD, WORKLOAD
+    _WORKLOAD = args.workload
+    sensor_name, WORKLOAD = WORKLOADS[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -166,7 +213,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        seq = syn.make_sequence(args.preroll + W + K, syn.HDL64, seed=1234)
+        seq = syn.make_sequence(args.preroll + W + K, getattr(syn, sensor_name), seed=1234)
         npts = float(np.mean([len(s["xyz"]) for s in seq]))
         v, times, _ = run_oracle(seq, args.preroll, W, K)
         ms = float(np.mean(times))
@@ -198,7 +245,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank if world > 1 else 0
 
-    seq = syn.make_sequence(args.preroll + W + K + n_roof, syn.HDL64, seed=1234)
+    seq = syn.make_sequence(args.preroll + W + K + n_roof, getattr(syn, sensor_name), seed=1234)
     npts = float(np.mean([len(s["xyz"]) for s in seq]))
     n_timed_begin = args.preroll + W
 

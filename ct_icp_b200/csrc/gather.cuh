@@ -132,7 +132,7 @@ __device__ __forceinline__ QueryCtx make_query(const V3 &q, double res, int lane
 // counts over the lanes); chunk c gives lane l the candidate with flat index 32 c + l, found by a 5-step binary
 // search over the prefix sums with shuffles. The loads of up to kPrefetch chunks are issued back to back before any
 // of them is consumed, so a keypoint pays ~one L2/HBM round trip for all its map points instead of one per voxel.
-constexpr int kPrefetch = 8;
+constexpr int kPrefetch = 4;
 
 __device__ __forceinline__ void knn_consume32(KnnStage *stage, int &fill, KnnEntry &best, int lane) {
     const KnnStage t = stage[lane];

@@ -51,6 +51,7 @@ struct GnParams {
     double max_dist_to_plane;   // max_dist_to_plane_ct_icp
     double threshold_norm;      // threshold_orientation_norm (GN stop criterion on ‖x‖, ct_icp.cpp:978)
     int shard_rank, shard_world;   // keypoint sharding (multi-GPU); 0/1 when single
+    int debug_flags;               // profiling only (env CTICP_DEBUG_FLAGS): 1 = skip the solve, 2 = skip the gather work
 };
 
 class IcpSolver {
@@ -101,6 +102,7 @@ private:
     double *d_sys_ = nullptr;      // 12*12 + 12 + 4 debug output of the solve kernel
     double *d_acc_ = nullptr;      // reduced accumulator (multi-GPU all-reduce buffer)
     unsigned int *d_ticket_ = nullptr;   // last-CTA-done counter of k_gn_iterate
+    unsigned int *d_sync_words_ = nullptr;   // arrive counter + epoch of k_gn_persistent
     // solver CERES (icp_lm.cu)
     void *d_lm_state_ = nullptr, *d_lm_stats_ = nullptr, *d_lm_blocks_ = nullptr;
     int *d_lm_sel_ = nullptr;

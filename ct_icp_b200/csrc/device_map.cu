@@ -249,7 +249,8 @@ DeviceMap::DeviceMap(const cticp_map_options &options, cudaStream_t stream) : op
         const auto &rp = options.resolutions[i];
         if (!(rp.resolution > 0) || rp.max_num_points < 1 || rp.max_num_points > kMaxB)
             throw std::invalid_argument("map resolution / max_num_points out of the supported range (1..64)");
-        uint64_t cap = options.capacity_voxels ? options.capacity_voxels : (rp.resolution < 0.5 ? (1ull << 21) : (1ull << 20));
+        // default capacity: enough for a 100 m local map at load <= 0.5; tables double on demand (MaintainTables)
+        uint64_t cap = options.capacity_voxels ? options.capacity_voxels : (rp.resolution < 0.5 ? (1ull << 20) : (1ull << 18));
         AllocLevel(levels_[i], NextPow2(std::max<uint64_t>(cap, 1024)), rp);
     }
     CT_CUDA_CHECK(cudaMalloc(&d_counters_, sizeof(MapCounters) * levels_.size()));

@@ -302,8 +302,11 @@ __device__ __forceinline__ void load_state_volatile(const IcpState *st, Q4 &qb, 
 __global__ void __launch_bounds__(kGatherWarps * 32)
 k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
                 IcpState *st, double *__restrict__ partials, int num_iters) {
-    // (a hand-rolled arrive-counter / epoch-word hand-off instead of grid.sync() was tried and measured 2x SLOWER on
-    // the full kernel — 0.38 vs 0.18 ms — although equal on the empty loop; cooperative-groups grid.sync() stays)
+    // Measured alternatives (config 2, 5 iterations, ICP ms): this design 0.180; arrive-counter / epoch-word hand-off
+    // instead of grid.sync() 0.383; ONE barrier per iteration with every CTA redundantly reducing + solving 0.343 —
+    // although its empty loop is 2.4x cheaper (0.029 vs 0.070): when every SM alternates between the gather code and
+    // the solve code each iteration, the instruction working set no longer fits the SM's instruction cache, while a
+    // dedicated solver CTA keeps the ~1.5k-instruction serial tail hot on one SM (6.6 us vs ~40 us per iteration).
     cg::grid_group grid = cg::this_grid();
     __shared__ KnnStage s_stage[kGatherWarps][64];
     __shared__ double s_u[kGatherWarps][16];

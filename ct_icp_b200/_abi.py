@@ -99,6 +99,11 @@ class MotionModelOptions(_Struct):
     ]
 
 
+class AdaptiveOptions(_Struct):
+    _fields_ = [("num_points_per_voxel", C.c_int32), ("max_num_points", C.c_int32), ("num_bands", C.c_int32),
+                ("_pad0", C.c_int32), ("distance", C.c_double * 8), ("voxel_size", C.c_double * 8)]
+
+
 class OdometryOptions(_Struct):
     _fields_ = [
         ("ct_icp_options", IcpOptions), ("map_options", MapOptions),
@@ -118,6 +123,7 @@ class OdometryOptions(_Struct):
         ("insertion_ego_rotation_threshold", C.c_double), ("insertion_threshold_frames_skipped", C.c_double),
         ("insertion_cum_distance_threshold", C.c_double), ("insertion_cum_orientation_threshold", C.c_double),
         ("shuffle_seed", C.c_uint64), ("max_points_per_frame", C.c_uint64),
+        ("adaptive_options", AdaptiveOptions),
     ]
 
 

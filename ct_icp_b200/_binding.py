@@ -72,6 +72,8 @@ class Binding:
                                                   P(abi.MotionModelOptions), vp, vp, P(i32)]),
             "grid_sample_indices": (i64, [C.c_int, vp, sz, sz, dbl, vp, sz]),
             "permutation": (C.c_int, [u64, u64, u32, vp]),
+            "adaptive_sample_indices": (i64, [C.c_int, P(abi.AdaptiveOptions), vp, sz, sz, vp, sz]),
+            "default_adaptive_options": (None, [P(abi.AdaptiveOptions)]),
             # engine only
             "abi_version": (u32, []),
             "abi_sizeof": (sz, [C.c_char_p]),
@@ -148,6 +150,16 @@ class Binding:
         out = np.empty(len(xyz), dtype=np.uint32)
         n = self.check(self.fn("grid_sample_indices")(device, xyz.ctypes.data, 24, len(xyz), voxel_size,
                                                        out.ctypes.data, len(out)))
+        return out[:n].copy()
+
+    def adaptive_sample_indices(self, xyz, options=None, device=0):
+        xyz = _as_f64_rows(xyz, 3)
+        if options is None:
+            options = abi.AdaptiveOptions()
+            self.fn("default_adaptive_options")(C.byref(options))
+        out = np.empty(len(xyz) + 1, dtype=np.uint32)
+        n = self.check(self.fn("adaptive_sample_indices")(device, C.byref(options), xyz.ctypes.data, 24, len(xyz),
+                                                           out.ctypes.data, len(out)))
         return out[:n].copy()
 
     def permutation(self, seed, counter, n):

@@ -88,6 +88,7 @@ size_t cticp_abi_sizeof(const char *name) {
     if (s == "cticp_icp_summary") return sizeof(cticp_icp_summary);
     if (s == "cticp_summary") return sizeof(cticp_summary);
     if (s == "cticp_device_timing") return sizeof(cticp_device_timing);
+    if (s == "cticp_adaptive_options") return sizeof(cticp_adaptive_options);
     return 0;
 }
 
@@ -143,8 +144,20 @@ void cticp_legacy_map_options(cticp_map_options *o, double size_voxel_map, int m
     o->resolutions[0].max_num_points = max_num_points_in_voxel;
     o->resolutions[0].min_distance_between_points = min_distance_points;
 }
+void cticp_default_adaptive_options(cticp_adaptive_options *a) {   // include/ct_icp/algorithm/sampling.h:14-27
+    memset(a, 0, sizeof(*a));
+    a->num_points_per_voxel = 1;
+    a->max_num_points = -1;
+    a->num_bands = 6;
+    const double d[6] = {0.5, 2.0, 4., 8., 16., 200.}, v[6] = {0.1, 0.2, 0.4, 0.8, 1.6, -1.};
+    for (int i = 0; i < 6; ++i) {
+        a->distance[i] = d[i];
+        a->voxel_size[i] = v[i];
+    }
+}
 void cticp_default_odometry_options(cticp_odometry_options *o) {
     memset(o, 0, sizeof(*o));
+    cticp_default_adaptive_options(&o->adaptive_options);
     cticp_default_icp_options(&o->ct_icp_options);
     cticp_default_map_options(&o->map_options);
     o->neighborhood_strategy.type = 0;
@@ -654,6 +667,35 @@ int64_t cticp_grid_sample_indices(int device, const double *xyz, size_t stride_b
             pipe.Upload(n);
             pipe.GridSelect(pipe.d_raw(), nullptr, pipe.d_count_n(), n, voxel_size, 0, 0, 0, 0, 0, 0, 0.f,
                             pipe.d_frame_mut(), pipe.d_frame_src_mut(), pipe.d_count_frame());
+            pipe.QueueCountsReadback();
+            CAPI_CUDA(cudaStreamSynchronize(stream));
+            total = pipe.h_counts()[1];
+            const size_t k = std::min<size_t>(cap, (size_t) total);
+            CAPI_CUDA(cudaMemcpy(out_indices, pipe.d_frame_src(), sizeof(uint32_t) * k, cudaMemcpyDeviceToHost));
+        }
+        cudaStreamDestroy(stream);
+        return (int) CTICP_OK;
+    });
+    return rc < 0 ? rc : total;
+}
+int64_t cticp_adaptive_sample_indices(int device, const cticp_adaptive_options *options, const double *xyz,
+                                      size_t stride_bytes, size_t n, uint32_t *out_indices, size_t cap) {
+    int64_t total = 0;
+    int rc = Guard([&] {
+        RequireDevice(device);
+        if (n == 0 || !options) return (int) CTICP_OK;
+        cudaStream_t stream;
+        CAPI_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        {
+            FramePipeline pipe(n, stream);
+            float4 *stage = pipe.Staging();
+            for (size_t i = 0; i < n; ++i) {
+                const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(xyz) + stride_bytes * i);
+                stage[i] = make_float4((float) p[0], (float) p[1], (float) p[2], 0.f);
+            }
+            pipe.Upload(n);
+            pipe.AdaptiveSelect(*options, pipe.d_raw(), nullptr, pipe.d_count_n(), n, pipe.d_frame_mut(),
+                                pipe.d_frame_src_mut(), pipe.d_count_frame());
             pipe.QueueCountsReadback();
             CAPI_CUDA(cudaStreamSynchronize(stream));
             total = pipe.h_counts()[1];

@@ -81,8 +81,8 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
     }
     if (options_.ct_icp_options.solver == CTICP_SOLVER_ROBUST)
         throw UnsupportedError("solver ROBUST is SURVEY §8f-1 (not built yet)");
-    if (options_.sampling == CTICP_SAMPLING_ADAPTIVE)
-        throw UnsupportedError("sampling ADAPTIVE is SURVEY §8f-3 (not built yet)");
+    if (options_.sampling == CTICP_SAMPLING_ADAPTIVE && options_.adaptive_options.num_points_per_voxel != 1)
+        throw UnsupportedError("sampling ADAPTIVE: only num_points_per_voxel == 1 is built");
     next_robust_level_ = options_.robust_minimal_level;
 
     {
@@ -361,7 +361,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     auto t0 = hclock::now();
     pipe_->SampleKeypoints(options_.sampling, sample_voxel_size,
                            (!at_startup && options_.max_num_keypoints > 0) ? options_.max_num_keypoints : -1,
-                           options_.shuffle_seed, ShuffleCounter(k, 2 + attempt_idx));
+                           options_.shuffle_seed, ShuffleCounter(k, 2 + attempt_idx), &options_.adaptive_options);
     rs.t_sampling = ms_since(t0);
     if (at_startup) {
         options.threshold_voxel_occupancy = 1;

@@ -154,6 +154,67 @@ k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_
         }
     }
 }
+// ---- adaptive (distance-banded) grid sampling: AdaptiveSamplePointsInGrid, include/ct_icp/algorithm/sampling.h:55-110
+struct AdaptiveBands {
+    int num_bands;
+    double distance[CTICP_MAX_ADAPTIVE_BANDS];
+    double voxel_size[CTICP_MAX_ADAPTIVE_BANDS];
+};
+__device__ __forceinline__ int adaptive_band(const AdaptiveBands &B, const float4 &p, unsigned long long *key_out) {
+    const double x = p.x, y = p.y, z = p.z;
+    const double dist = sqrt(x * x + y * y + z * z);
+    int lw = 0;   // std::lower_bound with comp(elem, v) = elem.first < v (:69-74)
+    while (lw < B.num_bands && B.distance[lw] < dist) ++lw;
+    if (!(dist >= B.distance[0] && dist < B.distance[B.num_bands - 1])) return -1;
+    const int band = lw - 1;
+    if (band < 0) return -1;
+    const double vs = B.voxel_size[band];
+    const int vx = voxel_coord(x, vs), vy = voxel_coord(y, vs), vz = voxel_coord(z, vs);   // slam::Voxel::Coordinates
+    const int bias = 1 << 19;
+    *key_out = ((unsigned long long) (band + 1) << 60) | ((unsigned long long) (unsigned) ((vx + bias) & 0xFFFFF) << 40) |
+               ((unsigned long long) (unsigned) ((vy + bias) & 0xFFFFF) << 20) | (unsigned long long) (unsigned) ((vz + bias) & 0xFFFFF);
+    return band;
+}
+__global__ void k_adaptive_claim(const float4 *__restrict__ pts, const int *__restrict__ d_n, AdaptiveBands B,
+                                 unsigned long long *keys, unsigned long long *vals, uint32_t cap_mask,
+                                 int *__restrict__ slot_of, int *__restrict__ d_positions) {
+    const int n = *d_n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_positions = n * B.num_bands;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned long long key;
+        const int band = adaptive_band(B, pts[i], &key);
+        if (band < 0) {
+            slot_of[i] = -1;
+            continue;
+        }
+        uint32_t h = hash_key(key) & cap_mask;
+        while (true) {
+            unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&keys[h]);
+            if (k == kGridEmpty) k = atomicCAS(&keys[h], kGridEmpty, key);
+            if (k == kGridEmpty || k == key) break;
+            h = (h + 1) & cap_mask;
+        }
+        atomicMin(&vals[h], (unsigned long long) (unsigned) i);   // first seen = smallest index (:79-84)
+        slot_of[i] = (int) h;
+    }
+}
+__global__ void k_adaptive_mark(const float4 *__restrict__ pts, const int *__restrict__ d_n, AdaptiveBands B,
+                                const unsigned long long *__restrict__ vals, const int *__restrict__ slot_of,
+                                uint32_t *__restrict__ flags, uint32_t *__restrict__ src,
+                                uint32_t *__restrict__ tile_count) {
+    const int n = *d_n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int slot = slot_of[i];
+        if (slot < 0 || vals[slot] != (unsigned long long) (unsigned) i) continue;
+        unsigned long long key;
+        const int band = adaptive_band(B, pts[i], &key);
+        const uint32_t pos = (uint32_t) band * (uint32_t) n + (uint32_t) i;   // band-major, then first appearance
+        flags[pos] = 1u;
+        src[pos] = (uint32_t) i;
+        atomicAdd(&tile_count[pos >> kTileShift], 1u);
+    }
+}
+
 // keypoints = frame (sampling NONE, odometry.cpp:546)
 __global__ void k_copy_points(const float4 *__restrict__ in, const uint32_t *__restrict__ in_src,
                               const int *__restrict__ d_n, float4 *__restrict__ out, uint32_t *__restrict__ out_src,
@@ -229,7 +290,7 @@ FramePipeline::~FramePipeline() {
     cudaFree(d_raw_); cudaFree(d_frame_); cudaFree(d_keypoints_); cudaFree(d_tmp_points_);
     cudaFree(d_frame_src_); cudaFree(d_kp_src_); cudaFree(d_tmp_src_);
     cudaFree(d_grid_); cudaFree(d_slot_of_); cudaFree(d_tile_count_); cudaFree(d_src_);
-    cudaFree(d_counts_); cudaFree(d_frame_world_); cudaFree(d_all_world_);
+    cudaFree(d_counts_); cudaFree(d_frame_world_); cudaFree(d_all_world_); cudaFree(d_adaptive_);
 }
 
 int FramePipeline::Blocks(size_t n) const { return (int) std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 148 * 8)); }
@@ -273,6 +334,44 @@ void FramePipeline::GridSelect(const float4 *in, const uint32_t *in_src, const i
     CT_CUDA_CHECK(cudaGetLastError());
 }
 
+void FramePipeline::AdaptiveSelect(const cticp_adaptive_options &o, const float4 *in, const uint32_t *in_src,
+                                   const int *d_n_in, size_t n_upper, float4 *out, uint32_t *out_src, int *d_n_out) {
+    if (o.num_points_per_voxel != 1) throw std::invalid_argument("adaptive sampling: only num_points_per_voxel == 1 is built");
+    if (o.num_bands < 2 || o.num_bands > CTICP_MAX_ADAPTIVE_BANDS) throw std::invalid_argument("adaptive sampling: num_bands");
+    AdaptiveBands B;
+    B.num_bands = o.num_bands;
+    for (int i = 0; i < CTICP_MAX_ADAPTIVE_BANDS; ++i) {
+        B.distance[i] = o.distance[i];
+        B.voxel_size[i] = o.voxel_size[i];
+    }
+    const size_t positions = n_upper * (size_t) o.num_bands;
+    if ((positions + kTile - 1) / kTile > kMaxTiles) throw CapacityError("adaptive sampling: scan too large");
+    if (positions > adaptive_capacity_) {
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        cudaFree(d_adaptive_);
+        CT_CUDA_CHECK(cudaMalloc(&d_adaptive_, sizeof(uint32_t) * (kMaxTiles + 2 * positions)));
+        adaptive_capacity_ = positions;
+    }
+    uint32_t *tile_count = d_adaptive_, *flags = d_adaptive_ + kMaxTiles, *src = flags + positions;
+    const uint32_t cap = std::max<uint32_t>(NextPow2(2 * n_upper), 1024);
+    unsigned long long *keys = d_grid_, *vals = d_grid_ + cap;
+    CT_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * 2 * (size_t) cap, stream_));
+    CT_CUDA_CHECK(cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * (kMaxTiles + positions), stream_));
+    const int blocks = Blocks(n_upper);
+    int *d_positions = d_counts_ + 3;
+    k_adaptive_claim<<<blocks, 256, 0, stream_>>>(in, d_n_in, B, keys, vals, cap - 1, d_slot_of_, d_positions);
+    k_adaptive_mark<<<blocks, 256, 0, stream_>>>(in, d_n_in, B, vals, d_slot_of_, flags, src, tile_count);
+    const size_t num_tiles = (positions + kTile - 1) / kTile;
+    k_grid_emit<<<(int) std::min<size_t>(std::max<size_t>(1, num_tiles), 1184), kTileThreads, 0, stream_>>>(
+        in, in_src, d_positions, flags, src, tile_count, 0, 0, 0, 0, 0.f, out, out_src, d_n_out);
+    launches_ += 3;
+    if (o.max_num_points > 0) {   // `indices.size() > kMaxNumPoints` lets max + 1 through (:96-105)
+        k_clamp_count<<<1, 1, 0, stream_>>>(d_n_out, o.max_num_points + 1);
+        launches_ += 1;
+    }
+    CT_CUDA_CHECK(cudaGetLastError());
+}
+
 void FramePipeline::SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2,
                                    bool override_alpha, float alpha_value) {
     GridSelect(d_raw_, nullptr, d_counts_ + 0, n_, voxel_size, 1, seed, counter1, 1, counter2, override_alpha ? 1 : 0,
@@ -280,8 +379,11 @@ void FramePipeline::SubSampleFrame(double voxel_size, uint64_t seed, uint64_t co
 }
 
 void FramePipeline::SampleKeypoints(int sampling, double sample_voxel_size, int max_num_keypoints, uint64_t seed,
-                                    uint64_t counter) {
-    if (sampling == CTICP_SAMPLING_GRID) {
+                                    uint64_t counter, const cticp_adaptive_options *adaptive) {
+    if (sampling == CTICP_SAMPLING_ADAPTIVE) {
+        if (!adaptive) throw std::invalid_argument("adaptive options missing");
+        AdaptiveSelect(*adaptive, d_frame_, d_frame_src_, d_counts_ + 1, n_, d_keypoints_, d_kp_src_, d_counts_ + 2);
+    } else if (sampling == CTICP_SAMPLING_GRID) {
         GridSelect(d_frame_, d_frame_src_, d_counts_ + 1, n_, sample_voxel_size, 0, 0, 0, 0, 0, 0, 0.f, d_keypoints_,
                    d_kp_src_, d_counts_ + 2);
     } else {

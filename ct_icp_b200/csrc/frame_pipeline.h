@@ -27,7 +27,11 @@ public:
     void SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2, bool override_alpha,
                         float alpha_value);
     // TryRegister: grid_sampling | NONE, then the optional max_num_keypoints shuffle-truncate
-    void SampleKeypoints(int sampling, double sample_voxel_size, int max_num_keypoints, uint64_t seed, uint64_t counter);
+    void SampleKeypoints(int sampling, double sample_voxel_size, int max_num_keypoints, uint64_t seed, uint64_t counter,
+                         const cticp_adaptive_options *adaptive = nullptr);
+    // AdaptiveSamplePointsInGrid (include/ct_icp/algorithm/sampling.h:55-110)
+    void AdaptiveSelect(const cticp_adaptive_options &o, const float4 *in, const uint32_t *in_src, const int *d_n_in,
+                        size_t n_upper, float4 *out, uint32_t *out_src, int *d_n_out);
     // world points of the sub-sampled frame / of every input point with the final pose pair
     void TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
     void TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
@@ -75,6 +79,8 @@ private:
     uint32_t *d_tile_count_ = nullptr, *d_flags_ = nullptr, *d_src_ = nullptr;   // flags live right after the tile counters
     int *d_counts_ = nullptr;
     double *d_frame_world_ = nullptr, *d_all_world_ = nullptr;
+    uint32_t *d_adaptive_ = nullptr;   // tile counters + flags + src of the band-major position space
+    size_t adaptive_capacity_ = 0;
     int launches_ = 0;
 };
 

@@ -15,6 +15,7 @@
 //   k_lm_finish : write the pose pair back, stop criterion of the ICP loop (:650-672).
 // Every launch is enqueued up front; device-side flags turn the launches after convergence into no-ops.
 #include <cstdio>
+#include <cstdlib>
 
 #include "engine.h"
 #include "gather.cuh"
@@ -62,6 +63,9 @@ struct LmState {
     // ICP-loop bookkeeping (ct_icp.cpp:650-672)
     double prev_qb[4], prev_qe[4], prev_tb[3], prev_te[3];
     int outer_iter;
+    // debug trace (CTICP_DEBUG_LM): one record per evaluated candidate
+    int trace_n;
+    double trace[256][13];   // x_cost, candidate_cost, model_cost_change, relative_decrease, radius, flag
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -424,6 +428,12 @@ k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblock
                 S.flag = 1;   // FunctionToleranceReached
             } else {
                 const double relative_decrease = cost_change / lm->model_cost_change;
+                if (lm->trace_n < 256) {
+                    double *tr = lm->trace[lm->trace_n++];
+                    tr[0] = lm->x_cost; tr[1] = candidate_cost; tr[2] = lm->model_cost_change; tr[3] = relative_decrease;
+                    tr[4] = lm->radius; tr[5] = relative_decrease > min_relative_decrease ? 1.0 : 0.0;
+                    tr[6] = lm->x[0]; tr[7] = lm->x[1]; tr[8] = lm->x[2]; tr[9] = lm->x[3]; tr[10] = lm->x[11]; tr[11] = lm->x[12]; tr[12] = lm->x[13];
+                }
                 if (relative_decrease > min_relative_decrease) {
                     S.flag = 2;   // successful step
                     lm->radius = lm->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3.0));
@@ -576,6 +586,7 @@ __global__ void k_lm_begin(IcpState *st, LmState *lm, unsigned long long *stats)
     for (int d = 0; d < 3; ++d) { lm->prev_tb[d] = st->tb[d]; lm->prev_te[d] = st->te[d]; }
     lm->done = 0;
     lm->usable = 1;
+    lm->trace_n = 0;
     stats[0] = 0;
     stats[1] = 0;
 }
@@ -673,6 +684,14 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
         launches_ += 1;
     }
     CT_CUDA_CHECK(cudaGetLastError());
+    if (getenv("CTICP_DEBUG_LM")) {
+        static LmState h;
+        CT_CUDA_CHECK(cudaMemcpyAsync(&h, lm, sizeof(LmState), cudaMemcpyDeviceToHost, stream_));
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        for (int i = 0; i < h.trace_n; ++i)
+            fprintf(stderr, "[eng-lm] x_cost %.12g cand %.12g x %.12g %.12g %.12g %.12g | %.12g %.12g %.12g %s\n", h.trace[i][0], h.trace[i][1],
+                    h.trace[i][6], h.trace[i][7], h.trace[i][8], h.trace[i][9], h.trace[i][10], h.trace[i][11], h.trace[i][12], h.trace[i][5] > 0.5 ? "ACCEPT" : "reject");
+    }
 }
 
 }  // namespace cticp

@@ -140,6 +140,17 @@ typedef struct cticp_motion_model_options {
     double threshold_translation_diff;
 } cticp_motion_model_options;
 
+/* ct_icp::AdaptiveGridSamplingOptions, include/ct_icp/algorithm/sampling.h:14-27 */
+#define CTICP_MAX_ADAPTIVE_BANDS 8
+typedef struct cticp_adaptive_options {
+    int32_t num_points_per_voxel;      /* only 1 is built */
+    int32_t max_num_points;
+    int32_t num_bands;                 /* entries of distance_voxel_size */
+    int32_t _pad0;
+    double distance[CTICP_MAX_ADAPTIVE_BANDS];     /* .first  : distance to the sensor */
+    double voxel_size[CTICP_MAX_ADAPTIVE_BANDS];   /* .second : sampling voxel of the band starting there */
+} cticp_adaptive_options;
+
 /* ct_icp::OdometryOptions, include/ct_icp/odometry.h:32-157 */
 typedef struct cticp_odometry_options {
     cticp_icp_options ct_icp_options;
@@ -185,6 +196,7 @@ typedef struct cticp_odometry_options {
     uint64_t shuffle_seed;
     /* device sizing (new): upper bound on points per scan; 0 = 524288 */
     uint64_t max_points_per_frame;
+    cticp_adaptive_options adaptive_options;   /* sampling == ADAPTIVE */
 } cticp_odometry_options;
 
 /* ---- value PODs ------------------------------------------------------------------------------------------- */
@@ -398,6 +410,11 @@ int64_t cticp_grid_sample_indices(int device, const double *xyz, size_t stride_b
                                   uint32_t *out_indices, size_t cap);
 /* The counter-based permutation standing in for std::shuffle: out[perm(i)] = i semantics, see DESIGN.md */
 int cticp_permutation(uint64_t seed, uint64_t counter, uint32_t n, uint32_t *out_perm);
+/* ct_icp::AdaptiveSamplePointsInGrid, include/ct_icp/algorithm/sampling.h:55-110 (order contract: band by band, first
+ * appearance inside a band). out_indices receives the indices kept; returns the count. */
+int64_t cticp_adaptive_sample_indices(int device, const cticp_adaptive_options *options, const double *xyz,
+                                      size_t stride_bytes, size_t n, uint32_t *out_indices, size_t cap);
+void cticp_default_adaptive_options(cticp_adaptive_options *out);
 
 #ifdef __cplusplus
 }

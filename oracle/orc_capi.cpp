@@ -95,8 +95,17 @@ void orc_legacy_map_options(cticp_map_options *o, double size_voxel_map, int max
     o->resolutions[0].max_num_points = max_num_points_in_voxel;
     o->resolutions[0].min_distance_between_points = min_distance_points;
 }
+void orc_default_adaptive_options(cticp_adaptive_options *a) {   // include/ct_icp/algorithm/sampling.h:14-27
+    std::memset(a, 0, sizeof(*a));
+    a->num_points_per_voxel = 1;
+    a->max_num_points = -1;
+    a->num_bands = 6;
+    const double d[6] = {0.5, 2.0, 4., 8., 16., 200.}, v[6] = {0.1, 0.2, 0.4, 0.8, 1.6, -1.};
+    for (int i = 0; i < 6; ++i) { a->distance[i] = d[i]; a->voxel_size[i] = v[i]; }
+}
 void orc_default_odometry_options(cticp_odometry_options *o) {
     std::memset(o, 0, sizeof(*o));
+    orc_default_adaptive_options(&o->adaptive_options);
     orc_default_icp_options(&o->ct_icp_options);
     orc_default_map_options(&o->map_options);
     o->neighborhood_strategy = {0, 20, 8, 0};
@@ -447,6 +456,22 @@ int64_t orc_grid_sample_indices(int /*device*/, const double *xyz, size_t stride
     auto kept = SubSampleIndices(frame, voxel_size);
     for (size_t i = 0; i < std::min(cap, kept.size()); ++i) out_indices[i] = kept[i];
     return (int64_t) kept.size();
+}
+int64_t orc_adaptive_sample_indices(int /*device*/, const cticp_adaptive_options *options, const double *xyz, size_t stride,
+                                    size_t n, uint32_t *out_indices, size_t cap) {
+    int64_t total = 0;
+    int rc = Guard([&] {
+        std::vector<Vec3> pts(n);
+        for (size_t i = 0; i < n; ++i) {
+            const double *p = StrideAt(xyz, stride, i);
+            pts[i] = Vec3(p[0], p[1], p[2]);
+        }
+        auto kept = AdaptiveSampleIndices(pts, *options);
+        for (size_t i = 0; i < std::min(cap, kept.size()); ++i) out_indices[i] = kept[i];
+        total = (int64_t) kept.size();
+        return (int) CTICP_OK;
+    });
+    return rc < 0 ? rc : total;
 }
 int orc_permutation(uint64_t seed, uint64_t counter, uint32_t n, uint32_t *out_perm) {
     Permutation perm(seed, counter, n);

@@ -11,6 +11,8 @@
 // published Ceres 2.x algorithms (trust_region_minimizer.cc, levenberg_marquardt_strategy.cc, corrector.cc,
 // loss_function.cc, local_parameterization.cc).
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 
@@ -468,6 +470,9 @@ SolveSummary SolveLM(const Problem &problem, double *parameters, int max_num_ite
         if (std::fabs(cost_change) <= function_tolerance * x_cost) break;
 
         const double relative_decrease = cost_change / model_cost_change;
+        if (getenv("ORC_DEBUG_LM"))
+            fprintf(stderr, "[orc-lm] x_cost %.12g cand %.12g x %.12g %.12g %.12g %.12g | %.12g %.12g %.12g %s\n", x_cost,
+                    candidate_cost, x[0], x[1], x[2], x[3], x[11], x[12], x[13], relative_decrease > min_relative_decrease ? "ACCEPT" : "reject");
         if (relative_decrease > min_relative_decrease) {   // HandleSuccessfulStep
             for (int i = 0; i < 14; ++i) x[i] = candidate_x[i];
             x_norm = norm14(x);

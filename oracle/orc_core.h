@@ -126,6 +126,38 @@ inline void sub_sample_frame(std::vector<WPoint3D> &frame, double size_voxel) {
     for (auto i : kept) out.push_back(frame[i]);
     frame.swap(out);
 }
+// ct_icp::AdaptiveSamplePointsInGrid, include/ct_icp/algorithm/sampling.h:55-110 (num_points_per_voxel == 1).
+// Output: band by band; inside a band the order of first appearance (order contract; the reference emits
+// std::unordered_map iteration order). max_num_points reproduces the reference's `size() > max` test (:96-105), which
+// lets max + 1 indices through.
+inline std::vector<uint32_t> AdaptiveSampleIndices(const std::vector<Vec3> &points, const cticp_adaptive_options &o) {
+    if (o.num_points_per_voxel != 1) throw std::runtime_error("oracle: adaptive sampling with num_points_per_voxel != 1");
+    const int nb = o.num_bands;
+    std::vector<std::unordered_set<Voxel, VoxelHash>> seen(nb);
+    std::vector<std::vector<uint32_t>> per_band(nb);
+    for (uint32_t idx = 0; idx < points.size(); ++idx) {
+        const Vec3 &p = points[idx];
+        const double dist = p.norm();
+        int lw = 0;   // std::lower_bound with comp(elem, v) = elem.first < v
+        while (lw < nb && o.distance[lw] < dist) ++lw;
+        if (dist >= o.distance[0] && dist < o.distance[nb - 1]) {
+            const int band = lw - 1;
+            // NB when dist == distance[0] exactly, lower_bound returns 0 and the reference indexes [-1] (UB); skipped here
+            if (band < 0) continue;
+            const Voxel v = Voxel::Coordinates(p, o.voxel_size[band]);
+            if (seen[band].insert(v).second) per_band[band].push_back(idx);
+        }
+    }
+    const size_t kMax = o.max_num_points > 0 ? (size_t) o.max_num_points : std::numeric_limits<size_t>::max();
+    std::vector<uint32_t> out;
+    for (auto &b : per_band)
+        for (auto i : b) {
+            if (out.size() > kMax) return out;
+            out.push_back(i);
+        }
+    return out;
+}
+
 // ct_icp::grid_sampling, src/ct_icp/ct_icp.cpp:86-101
 inline void grid_sampling(const std::vector<WPoint3D> &frame, std::vector<WPoint3D> &keypoints, double size_voxel) {
     keypoints = frame;

@@ -197,8 +197,11 @@ private:
         std::vector<WPoint3D> keypoints;
         if (options_.sampling == CTICP_SAMPLING_GRID)
             grid_sampling(frame, keypoints, sample_voxel_size);
-        else if (options_.sampling == CTICP_SAMPLING_ADAPTIVE)
-            throw std::runtime_error("ADAPTIVE sampling is outside the restated path (SURVEY §8f-3)");
+        else if (options_.sampling == CTICP_SAMPLING_ADAPTIVE) {   // odometry.cpp:539-544 (RawPointConversion)
+            std::vector<Vec3> raw(frame.size());
+            for (size_t i = 0; i < frame.size(); ++i) raw[i] = frame[i].raw;
+            for (auto idx : AdaptiveSampleIndices(raw, options_.adaptive_options)) keypoints.push_back(frame[idx]);
+        }
         else
             keypoints = frame;
         if (!at_startup && options_.max_num_keypoints > 0 && (int) keypoints.size() > options_.max_num_keypoints) {

@@ -34,6 +34,7 @@ def test_struct_sizes_match_the_compiled_header():
         "cticp_motion_model_options": abi.MotionModelOptions, "cticp_odometry_options": abi.OdometryOptions,
         "cticp_pose": abi.Pose, "cticp_frame": abi.Frame, "cticp_wpoint": abi.WPoint,
         "cticp_icp_summary": abi.IcpSummary, "cticp_summary": abi.Summary, "cticp_device_timing": abi.DeviceTiming,
+        "cticp_adaptive_options": abi.AdaptiveOptions,
     }
     for name, cls in pairs.items():
         assert eng.fn("abi_sizeof")(name.encode()) == C.sizeof(cls), name

@@ -279,3 +279,26 @@ def test_gn_fails_with_too_few_keypoints(orc):
     io = orc.default_icp_options()
     io.solver = abi.SOLVER["GN"]
     assert not m.icp_register(io, kp, frame).success
+
+
+# ---- include/ct_icp/algorithm/sampling.h:55-110 (adaptive, distance-banded grid sampling) ---------------------------
+def test_adaptive_sampling_properties(orc):
+    rng = np.random.default_rng(4)
+    pts = rng.normal(scale=12.0, size=(20000, 3))
+    idx = orc.adaptive_sample_indices(pts)
+    assert 0 < len(idx) < len(pts)
+    d = np.linalg.norm(pts[idx], axis=1)
+    assert d.min() >= 0.5 and d.max() < 200.0
+    bounds = np.array([0.5, 2.0, 4.0, 8.0, 16.0, 200.0])
+    vsize = np.array([0.1, 0.2, 0.4, 0.8, 1.6])
+    band = np.searchsorted(bounds, d, side="left") - 1
+    assert np.all(np.diff(band) >= 0)                       # band by band
+    for b in range(5):
+        sel = idx[band == b]
+        assert np.all(np.diff(sel) > 0)                     # first appearance inside a band
+        keys = np.trunc(pts[sel] / vsize[b]).astype(np.int64)
+        assert len({tuple(k) for k in keys}) == len(sel)    # one point per voxel of the band
+    o = abi.AdaptiveOptions()
+    orc.fn("default_adaptive_options")(C.byref(o))
+    o.max_num_points = 100
+    assert len(orc.adaptive_sample_indices(pts, o)) == 101  # the reference's `size() > max` lets max + 1 through

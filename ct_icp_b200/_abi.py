@@ -66,7 +66,7 @@ class IcpOptions(_Struct):
         ("max_dist_to_plane_ct_icp", C.c_double),
         ("threshold_linearity", C.c_double), ("threshold_planarity", C.c_double),
         ("weight_point_to_point", C.c_double), ("outlier_distance", C.c_double),
-        ("use_barycenter", C.c_int32), ("_pad0", C.c_int32),
+        ("use_barycenter", C.c_int32), ("use_lines", C.c_int32),
     ]
 
 

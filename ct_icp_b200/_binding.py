@@ -98,6 +98,7 @@ class Binding:
             "se3_interpolate": (None, [vp, vp, vp, vp, dbl, vp, vp]),
             "se3_apply": (None, [vp, vp, vp, vp]),
             "ct_point_to_plane_residual": (dbl, [dbl, vp, vp, vp, dbl, vp, vp, vp, vp, vp]),
+            "ct_residual": (dbl, [C.c_int, dbl, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp]),
         }
         for name, (res, args) in sigs.items():
             if self.has(name):

@@ -123,6 +123,7 @@ void cticp_default_icp_options(cticp_icp_options *o) {
     o->weight_point_to_point = 0.1;
     o->outlier_distance = 1.0;
     o->use_barycenter = 0;
+    o->use_lines = 1;
     o->debug_print = 1;
 }
 void cticp_default_map_options(cticp_map_options *o) {
@@ -594,6 +595,7 @@ int cticp_icp_register(cticp_map *m, const cticp_icp_options *options, const cti
                 m->icp->EnqueueGaussNewton(*m->map, *options, D.d_kp, D.d_n, n, options->num_iters_icp, D.d_state);
                 break;
             case CTICP_SOLVER_CERES:
+            case CTICP_SOLVER_ROBUST:
                 m->icp->EnqueueCeres(*m->map, *options, st, D.d_kp, D.d_n, n, n, D.d_state);
                 break;
             default:

@@ -79,8 +79,6 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
         default:
             throw UnsupportedError("motion_compensation other than CONTINUOUS is outside the built hot path (SURVEY §8)");
     }
-    if (options_.ct_icp_options.solver == CTICP_SOLVER_ROBUST)
-        throw UnsupportedError("solver ROBUST is SURVEY §8f-1 (not built yet)");
     if (options_.sampling == CTICP_SAMPLING_ADAPTIVE && options_.adaptive_options.num_points_per_voxel != 1)
         throw UnsupportedError("sampling ADAPTIVE: only num_points_per_voxel == 1 is built");
     next_robust_level_ = options_.robust_minimal_level;
@@ -397,6 +395,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
                                      options.num_iters_icp, d_state_, shard_rank_, shard_world_, nccl_comm_);
             break;
         case CTICP_SOLVER_CERES:
+        case CTICP_SOLVER_ROBUST:
             icp_->EnqueueCeres(*map_, options, options_.neighborhood_strategy, pipe_->d_keypoints(),
                                pipe_->d_count_keypoints(), KeypointHint(), pipe_->n(), d_state_, shard_rank_, shard_world_,
                                nccl_comm_);

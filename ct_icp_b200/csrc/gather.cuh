@@ -290,8 +290,12 @@ struct Eig3 {
     double sv0, sv1, sv2;   // |eigenvalues| descending
     V3 normal;              // eigenvector of sv2
 };
+struct Eig3Full {
+    double sv0, sv1, sv2;
+    V3 line, normal;        // eigenvectors of sv0 / sv2 (V.col(0), V.col(2))
+};
 
-__device__ __forceinline__ Eig3 sym_eig3(double a00, double a01, double a02, double a11, double a12, double a22) {
+__device__ __forceinline__ Eig3Full sym_eig3_full(double a00, double a01, double a02, double a11, double a12, double a22) {
     double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
 #pragma unroll 1
     for (int sweep = 0; sweep < 12; ++sweep) {
@@ -308,7 +312,11 @@ __device__ __forceinline__ Eig3 sym_eig3(double a00, double a01, double a02, dou
     if (e0 < e1) { double t = e0; e0 = e1; e1 = t; V3 tv = c0; c0 = c1; c1 = tv; }
     if (e1 < e2) { double t = e1; e1 = e2; e2 = t; V3 tv = c1; c1 = c2; c2 = tv; }
     if (e0 < e1) { double t = e0; e0 = e1; e1 = t; V3 tv = c0; c0 = c1; c1 = tv; }
-    return Eig3{e0, e1, e2, c2};
+    return Eig3Full{e0, e1, e2, c0, c2};
+}
+__device__ __forceinline__ Eig3 sym_eig3(double a00, double a01, double a02, double a11, double a12, double a22) {
+    const Eig3Full f = sym_eig3_full(a00, a01, a02, a11, a12, a22);
+    return Eig3{f.sv0, f.sv1, f.sv2, f.normal};
 }
 
 // Non-iterative variant: eigenvalues from the trigonometric solution of the characteristic cubic, the eigenvector of
@@ -388,6 +396,39 @@ __device__ __forceinline__ NeighborhoodDesc warp_describe(const GatherConfig &G,
     d.far_rel.y = __shfl_sync(0xffffffffu, rel.y, n - 1);
     d.far_rel.z = __shfl_sync(0xffffffffu, rel.z, n - 1);
     d.far_d2 = __shfl_sync(0xffffffffu, best.d2, n - 1);
+    return d;
+}
+
+// ComputeNeighborhood(ALL_BUT_KDTREE) for solver ROBUST (neighborhood.h:226-257, 286-316): everything above plus
+// line = V.col(0), planarity, linearity, the covariance and the barycenter (relative to the query).
+struct NeighborhoodDescFull {
+    V3 normal, line, mean_rel, far_rel;
+    double planarity, linearity;
+    double cov[6];   // xx xy xz yy yz zz
+};
+__device__ __forceinline__ NeighborhoodDescFull warp_describe_full(const GatherConfig &G, const int *stencil,
+                                                                   const QueryCtx &ctx, const KnnEntry &best, int n,
+                                                                   int lane) {
+    V3 rel{0, 0, 0};
+    if (lane < n) rel = knn_rel_position(G, stencil, ctx, best);
+    const double inv = 1.0 / (double) n;
+    const double mx = warp_sum(rel.x) * inv, my = warp_sum(rel.y) * inv, mz = warp_sum(rel.z) * inv;
+    NeighborhoodDescFull d;
+    d.cov[0] = warp_sum(rel.x * rel.x) * inv - mx * mx;
+    d.cov[1] = warp_sum(rel.x * rel.y) * inv - mx * my;
+    d.cov[2] = warp_sum(rel.x * rel.z) * inv - mx * mz;
+    d.cov[3] = warp_sum(rel.y * rel.y) * inv - my * my;
+    d.cov[4] = warp_sum(rel.y * rel.z) * inv - my * mz;
+    d.cov[5] = warp_sum(rel.z * rel.z) * inv - mz * mz;
+    const Eig3Full e = sym_eig3_full(d.cov[0], d.cov[1], d.cov[2], d.cov[3], d.cov[4], d.cov[5]);
+    d.normal = e.normal;
+    d.line = e.line;
+    d.linearity = (e.sv0 - e.sv1) / e.sv0;
+    d.planarity = (e.sv1 - e.sv2) / e.sv0;
+    d.mean_rel = V3{mx, my, mz};
+    d.far_rel.x = __shfl_sync(0xffffffffu, rel.x, n - 1);
+    d.far_rel.y = __shfl_sync(0xffffffffu, rel.y, n - 1);
+    d.far_rel.z = __shfl_sync(0xffffffffu, rel.z, n - 1);
     return d;
 }
 

@@ -106,6 +106,7 @@ private:
     // solver CERES (icp_lm.cu)
     void *d_lm_state_ = nullptr, *d_lm_stats_ = nullptr, *d_lm_blocks_ = nullptr;
     int *d_lm_sel_ = nullptr;
+    void *d_lm_classes_ = nullptr;   // solver ROBUST: slam::NEIGHBORHOOD_TYPE per keypoint
     size_t lm_capacity_ = 0;
     int launches_ = 0;
     float gather_ms_ = 0.f;

@@ -47,6 +47,9 @@ struct LmParams {
     LossParams loss;
     int ls_max_num_iters;
     int shard_rank, shard_world;
+    // solver ROBUST (ct_icp.cpp:1180-1370)
+    int robust, use_lines, use_barycenter;
+    double threshold_linearity, threshold_planarity, outlier_distance, weight_neighborhood;
 };
 
 struct LmState {
@@ -110,11 +113,109 @@ k_lm_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, co
             rb.alpha = alpha;
             rb.raw[0] = kraw.x; rb.raw[1] = kraw.y; rb.raw[2] = kraw.z;
             rb.valid = 1;
+            rb.kind = kResPlane;
         }
         if (lane == 0) {
             if (rb.valid) blocks[kp] = rb;
             else blocks[kp].valid = 0;
         }
+        __syncwarp();
+    }
+    if (lane == 0 && n_kp) {
+        atomicAdd(&stats[0], n_kp);
+        atomicAdd(&stats[1], n_pts);
+    }
+}
+
+// Solver ROBUST's per-keypoint assembly (ct_icp.cpp:1229-1289): same gather, the neighborhood is classified planar /
+// linear / other and yields a point-to-plane / point-to-line / point-to-distribution block. `classes` holds
+// slam::NEIGHBORHOOD_TYPE per keypoint ACROSS the ICP iterations: the reference keeps its `neighborhoods` vector alive
+// (:1214) and ClassifyNeighborhood (neighborhood.h:268-282) leaves the previous class in place when neither threshold
+// is passed.
+__global__ void __launch_bounds__(kLmWarps * 32)
+k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
+            const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned char *__restrict__ classes,
+            unsigned long long *stats) {
+    __shared__ KnnStage s_stage[kLmWarps][64];
+    __shared__ int s_stencil[kMaxStencil];
+    if (st->done) return;
+    enum { NONE = 0, LINEAR = 1, PLANAR = 2, VOLUMIC = 3 };
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int *stencil = stencil_table_fill(s_stencil, G.r);
+    __syncthreads();
+    const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
+    const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
+    const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
+    const int K = *d_num_keypoints;
+    unsigned long long n_kp = 0, n_pts = 0;
+    for (int kp = blockIdx.x * kLmWarps + w; kp < K; kp += gridDim.x * kLmWarps) {
+        const float4 kraw = __ldg(keypoints + kp);
+        const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+        const V3 p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, raw, sc);   // TransformKeyPoints, :1373-1393
+        const QueryCtx ctx = make_query(p, G.L.res, lane);
+        KnnEntry best;
+        unsigned spts = 0;
+        const int n = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
+        n_kp += 1;
+        n_pts += spts;
+        int valid = 0;
+        if (n >= P.kmin) {   // :1238 (kmin >= 5 is enforced by the host, so the neighborhood is always describable)
+            const NeighborhoodDescFull nd = warp_describe_full(G, stencil, ctx, best, n, lane);
+            int cls = classes[kp];
+            if (nd.planarity > P.threshold_planarity) cls = PLANAR;
+            else if (nd.linearity > P.threshold_linearity) cls = LINEAR;
+            if (!P.use_lines && cls == LINEAR) cls = P.threshold_planarity < nd.planarity ? PLANAR : VOLUMIC;   // :1243-1248
+            double weight;
+            if (cls == LINEAR) weight = pow(fabs(nd.linearity), P.power_planarity);
+            else if (cls == PLANAR) weight = pow(fabs(nd.planarity), P.power_planarity);
+            else weight = P.weight_neighborhood;
+            const V3 d = P.use_barycenter ? nd.mean_rel : nd.far_rel;   // point - world_point
+            double distance;
+            int kind = kResDistribution;
+            if (cls == LINEAR) {
+                V3 u = nd.line;
+                const double z = dot(u, u);
+                if (z > 0) u = (1.0 / sqrt(z)) * u;
+                const V3 c = cross(d, u);
+                distance = sqrt(dot(c, c));
+                kind = kResLine;
+            } else if (cls == PLANAR) {
+                distance = fabs(dot(d, nd.normal));
+                kind = kResPlane;
+            } else {
+                distance = sqrt(dot(d, d));
+            }
+            if (lane == 0) {
+                classes[kp] = (unsigned char) cls;
+                if (distance < P.outlier_distance) {
+                    ResidualBlock rb;
+                    rb.ref[0] = p.x + d.x; rb.ref[1] = p.y + d.y; rb.ref[2] = p.z + d.z;
+                    const V3 dir = kind == kResLine ? nd.line : nd.normal;
+                    rb.normal[0] = dir.x; rb.normal[1] = dir.y; rb.normal[2] = dir.z;
+                    rb.weight = weight;
+                    rb.alpha = (double) kraw.w;
+                    rb.raw[0] = kraw.x; rb.raw[1] = kraw.y; rb.raw[2] = kraw.z;
+                    rb.valid = 1;
+                    rb.kind = kind;
+                    rb._pad = 0;
+                    if (kind == kResDistribution) {
+                        // (covariance + 0.05 I).inverse(), cost_functions.h:147-158 (Eigen's cofactor inverse)
+                        const double m00 = nd.cov[0] + 0.05, m01 = nd.cov[1], m02 = nd.cov[2], m11 = nd.cov[3] + 0.05,
+                                     m12 = nd.cov[4], m22 = nd.cov[5] + 0.05;
+                        const double c00 = m11 * m22 - m12 * m12, c01 = m12 * m02 - m01 * m22, c02 = m01 * m12 - m11 * m02;
+                        const double c11 = m22 * m00 - m02 * m02, c12 = m02 * m01 - m12 * m00, c22 = m00 * m11 - m01 * m01;
+                        const double invdet = 1.0 / (c00 * m00 + c01 * m01 + c02 * m02);
+                        rb.info[0] = c00 * invdet; rb.info[1] = c01 * invdet; rb.info[2] = c02 * invdet;
+                        rb.info[3] = c11 * invdet; rb.info[4] = c12 * invdet; rb.info[5] = c22 * invdet;
+                    } else {
+                        for (int i = 0; i < 6; ++i) rb.info[i] = 0.0;
+                    }
+                    blocks[kp] = rb;
+                    valid = 1;
+                }
+            }
+        }
+        if (lane == 0 && !valid) blocks[kp].valid = 0;
         __syncwarp();
     }
     if (lane == 0 && n_kp) {
@@ -222,7 +323,7 @@ k_lm_eval(LmParams P, int which, const ResidualBlock *__restrict__ blocks, const
         }
         for (int r = blockIdx.x * kLmWarps * 2 + hw; r < R; r += halves_total) {
             const ResidualBlock rb = blocks[sel_idx[r]];
-            const Dual res = ct_point_to_plane(rb, qb, qe, tb, te, hl);
+            const Dual res = P.robust ? ct_residual<true>(rb, qb, qe, tb, te, hl) : ct_residual<false>(rb, qb, qe, tb, te, hl);
             const double s = res.a * res.a;
             double rs = 1.0, js = 1.0;
             if (P.loss.type != 0) {
@@ -602,6 +703,8 @@ void IcpSolver::EnsureLmBuffers(size_t k_upper) {
         CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
         cudaFree(d_lm_blocks_);
         cudaFree(d_lm_sel_);
+        cudaFree(d_lm_classes_);
+        CT_CUDA_CHECK(cudaMalloc(&d_lm_classes_, k_upper));
         CT_CUDA_CHECK(cudaMalloc(&d_lm_blocks_, sizeof(ResidualBlock) * k_upper));
         CT_CUDA_CHECK(cudaMalloc(&d_lm_sel_, sizeof(int) * k_upper));
         lm_capacity_ = k_upper;
@@ -612,17 +715,25 @@ void IcpSolver::FreeLmBuffers() {
     cudaFree(d_lm_stats_);
     cudaFree(d_lm_blocks_);
     cudaFree(d_lm_sel_);
+    cudaFree(d_lm_classes_);
 }
 
 void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt, const cticp_strategy_options &strategy,
                              const float4 *d_keypoints, const int *d_num_keypoints, size_t k_hint, size_t k_capacity,
                              IcpState *d_state, int shard_rank, int shard_world, void *nccl_comm) {
-    if (opt.parametrization != CTICP_PARAM_CONTINUOUS_TIME || opt.distance != CTICP_DIST_POINT_TO_PLANE)
-        throw UnsupportedError("solver CERES: only CONTINUOUS_TIME + POINT_TO_PLANE is built (SURVEY §8)");
-    if (opt.num_closest_neighbors != 1)
+    const bool robust = opt.solver == CTICP_SOLVER_ROBUST;
+    if (opt.parametrization != CTICP_PARAM_CONTINUOUS_TIME)
+        throw UnsupportedError("solvers CERES / ROBUST: only the CONTINUOUS_TIME parametrization is built (SURVEY §8)");
+    if (!robust && opt.distance != CTICP_DIST_POINT_TO_PLANE)
+        throw UnsupportedError("solver CERES: only POINT_TO_PLANE is built (SURVEY §8)");
+    if (!robust && opt.num_closest_neighbors != 1)
         throw UnsupportedError("solver CERES: num_closest_neighbors != 1 is not built");
-    if (strategy.max_num_neighbors > 32 || strategy.max_num_neighbors < 1)
-        throw std::invalid_argument("neighborhood_strategy.max_num_neighbors must be in [1, 32]");
+    if (robust && opt.min_number_neighbors < 5)
+        throw UnsupportedError("solver ROBUST: min_number_neighbors < 5 (neighborhoods the reference cannot describe, "
+                               "neighborhood.h:227, and then reads stale) is not built");
+    // neighbor count: the strategy's for CERES (neighborhood_strategy.h:81), the ICP options' for ROBUST (:1235)
+    const int kmax = robust ? opt.max_number_neighbors : strategy.max_num_neighbors;
+    if (kmax > 32 || kmax < 1) throw std::invalid_argument("max_num_neighbors must be in [1, 32]");
     if (nccl_comm) throw UnsupportedError("solver CERES: multi-GPU sharding is built for the GN solver only");
     (void) shard_rank;
     (void) shard_world;
@@ -633,7 +744,7 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     LmParams P{};
     map.SearchParams(map.Options().default_radius, &P.level, &P.r);
     P.radius = map.Options().default_radius;
-    P.kmax = strategy.max_num_neighbors;          // neighborhood_strategy.h:81
+    P.kmax = kmax;
     P.kmin = opt.min_number_neighbors;            // ct_icp.cpp:574
     P.lambda_weight = std::abs(opt.weight_alpha) / sum;
     P.lambda_neighborhood = std::abs(opt.weight_neighborhood) / sum;
@@ -648,6 +759,13 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     P.ls_max_num_iters = opt.ls_max_num_iters;
     P.shard_rank = 0;
     P.shard_world = 1;
+    P.robust = robust ? 1 : 0;
+    P.use_lines = opt.use_lines;
+    P.use_barycenter = opt.use_barycenter;
+    P.threshold_linearity = opt.threshold_linearity;
+    P.threshold_planarity = opt.threshold_planarity;
+    P.outlier_distance = opt.outlier_distance;
+    P.weight_neighborhood = opt.weight_neighborhood;
 
     GatherConfig G;
     G.L = map.Level(P.level);
@@ -665,10 +783,16 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
 
     k_lm_begin<<<1, 32, 0, stream_>>>(d_state, lm, stats);
     launches_ += 1;
+    auto *classes = static_cast<unsigned char *>(d_lm_classes_);
+    if (robust) CT_CUDA_CHECK(cudaMemsetAsync(classes, 0, k_capacity, stream_));   // NEIGHBORHOOD_TYPE::NONE
     for (int it = 0; it < opt.num_iters_icp; ++it) {
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
-        k_lm_gather<<<gather_blocks, kLmWarps * 32, 0, stream_>>>(G, P, d_keypoints, d_num_keypoints, d_state, blocks_buf, stats);
+        if (robust)
+            k_rb_gather<<<gather_blocks, kLmWarps * 32, 0, stream_>>>(G, P, d_keypoints, d_num_keypoints, d_state, blocks_buf,
+                                                                     classes, stats);
+        else
+            k_lm_gather<<<gather_blocks, kLmWarps * 32, 0, stream_>>>(G, P, d_keypoints, d_num_keypoints, d_state, blocks_buf, stats);
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
         ++gather_launches_;
         k_lm_select<<<1, 1024, 0, stream_>>>(P, d_num_keypoints, blocks_buf, d_lm_sel_, d_state, lm, stats);

@@ -83,19 +83,25 @@ CT_HD Q4 quat_plus(Q4 q, double dx, double dy, double dz) {
     return q;
 }
 
-struct ResidualBlock {   // CTFunctor<FunctorPointToPlane> state for one keypoint
-    double ref[3];       // world_reference_ (the neighbor the plane is anchored on)
-    double normal[3];    // reference_normal_
+enum { kResPlane = 0, kResLine = 1, kResDistribution = 2 };
+
+struct ResidualBlock {   // CTFunctor<FunctorT> state for one keypoint
+    double ref[3];       // world_reference_ (the neighbor / barycenter the residual is anchored on)
+    double normal[3];    // reference_normal_ (plane) or direction_ (line, not normalised)
     double weight;
     double alpha;
     float raw[3];        // raw_point_ (sensor frame)
     int valid;
+    double info[6];      // FunctorPointToDistribution::neighborhood_information_ (xx xy xz yy yz zz); solver ROBUST only
+    int kind;            // kResPlane / kResLine / kResDistribution (solver CERES: always plane)
+    int _pad;
 };
 
 // Residual and its derivative along tangent direction `dir` (0..11; >= 12 → value only).
-// params: qb[4], qe[4], tb[3], te[3]
-__device__ __forceinline__ Dual ct_point_to_plane(const ResidualBlock &rb, const double *qb, const double *qe,
-                                                  const double *tb, const double *te, int dir) {
+// params: qb[4], qe[4], tb[3], te[3]. kRobust = false compiles the point-to-plane functor only (solver CERES).
+template <bool kRobust>
+__device__ __forceinline__ Dual ct_residual(const ResidualBlock &rb, const double *qb, const double *qe,
+                                            const double *tb, const double *te, int dir) {
     double sb[4] = {0, 0, 0, 0}, se[4] = {0, 0, 0, 0}, stb[3] = {0, 0, 0}, ste[3] = {0, 0, 0};
     if (dir < 3) quat_plus_column(qb, dir, sb);
     else if (dir < 6) quat_plus_column(qe, dir - 3, se);
@@ -109,7 +115,9 @@ __device__ __forceinline__ Dual ct_point_to_plane(const ResidualBlock &rb, const
     const Dual tx = alpha_m * mkd(tb[0], stb[0]) + alpha * mkd(te[0], ste[0]);
     const Dual ty = alpha_m * mkd(tb[1], stb[1]) + alpha * mkd(te[1], ste[1]);
     const Dual tz = alpha_m * mkd(tb[2], stb[2]) + alpha * mkd(te[2], ste[2]);
-    const DQuat q = dq_normalized(qi);                                   // FunctorPointToPlane: quat.normalized()
+    // FunctorPointToPlane / FunctorPointToDistribution: quat.normalized() (cost_functions.h:47-51, 163-167);
+    // FunctorPointToLine rotates with the quaternion as is (:121-125)
+    const DQuat q = (kRobust && rb.kind == kResLine) ? qi : dq_normalized(qi);
     const Dual vx = mkd(rb.raw[0]), vy = mkd(rb.raw[1]), vz = mkd(rb.raw[2]);
     // Eigen _transformVector: uv = 2 (q.vec x v); v + w uv + q.vec x uv
     Dual uvx = q.y * vz - q.z * vy, uvy = q.z * vx - q.x * vz, uvz = q.x * vy - q.y * vx;
@@ -117,6 +125,21 @@ __device__ __forceinline__ Dual ct_point_to_plane(const ResidualBlock &rb, const
     const Dual px = vx + q.w * uvx + (q.y * uvz - q.z * uvy) + tx;
     const Dual py = vy + q.w * uvy + (q.z * uvx - q.x * uvz) + ty;
     const Dual pz = vz + q.w * uvz + (q.x * uvy - q.y * uvx) + tz;
+    if (kRobust && rb.kind == kResLine) {   // cost_functions.h:127-129
+        double ux = rb.normal[0], uy = rb.normal[1], uz = rb.normal[2];
+        const double z = ux * ux + uy * uy + uz * uz;
+        if (z > 0) { const double inv = 1.0 / sqrt(z); ux *= inv; uy *= inv; uz *= inv; }
+        const Dual dx = px - mkd(rb.ref[0]), dy = py - mkd(rb.ref[1]), dz = pz - mkd(rb.ref[2]);
+        const Dual cx = uy * dz - uz * dy, cy = uz * dx - ux * dz, cz = ux * dy - uy * dx;
+        return rb.weight * dsqrt(cx * cx + cy * cy + cz * cz);
+    }
+    if (kRobust && rb.kind == kResDistribution) {   // cost_functions.h:169-171 : w * diff^T M diff
+        const Dual dx = px - mkd(rb.ref[0]), dy = py - mkd(rb.ref[1]), dz = pz - mkd(rb.ref[2]);
+        const Dual r0 = rb.info[0] * dx + rb.info[1] * dy + rb.info[2] * dz;
+        const Dual r1 = rb.info[1] * dx + rb.info[3] * dy + rb.info[4] * dz;
+        const Dual r2 = rb.info[2] * dx + rb.info[4] * dy + rb.info[5] * dz;
+        return rb.weight * (r0 * dx + r1 * dy + r2 * dz);
+    }
     const Dual prod = rb.normal[0] * (mkd(rb.ref[0]) - px) + rb.normal[1] * (mkd(rb.ref[1]) - py) +
                       rb.normal[2] * (mkd(rb.ref[2]) - pz);
     return rb.weight * prod;

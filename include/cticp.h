@@ -92,13 +92,13 @@ typedef struct cticp_icp_options {
     double ls_sigma;
     double ls_tolerant_min_threshold;
     double max_dist_to_plane_ct_icp;
-    /* ROBUST solver params (carried for completeness; solver ROBUST is SURVEY §8f) */
+    /* ROBUST solver params (include/ct_icp/ct_icp.h:133-141) */
     double threshold_linearity;
     double threshold_planarity;
     double weight_point_to_point;
     double outlier_distance;
     int32_t use_barycenter;
-    int32_t _pad0;
+    int32_t use_lines;             /* ct_icp.h:140 (default true; not settable from the reference's YAML) */
 } cticp_icp_options;
 
 /* ct_icp::MultipleResolutionVoxelMap::ResolutionParam / Options, include/ct_icp/map.h:109-134 */

@@ -74,6 +74,7 @@ void orc_default_icp_options(cticp_icp_options *o) {
     o->weight_point_to_point = 0.1;
     o->outlier_distance = 1.0;
     o->use_barycenter = 0;
+    o->use_lines = 1;
     o->debug_print = 1;
 }
 void orc_default_map_options(cticp_map_options *o) {
@@ -555,6 +556,14 @@ namespace orc {
 double CTResidualForTest(double alpha, const double ref[3], const double raw[3], const double normal[3], double weight,
                          const double qb[4], const double tb[3], const double qe[4], const double te[3],
                          double *local_jac12);
+double CTResidualKindForTest(int kind, double alpha, const double ref[3], const double raw[3], const double dir[3],
+                             const double *covariance, double weight, const double qb[4], const double tb[3],
+                             const double qe[4], const double te[3], double *local_jac12);
+}
+extern "C" double orc_ct_residual(int kind, double alpha, const double ref[3], const double raw[3], const double dir[3],
+                                  const double *covariance, double weight, const double qb[4], const double tb[3],
+                                  const double qe[4], const double te[3], double *local_jac12) {
+    return orc::CTResidualKindForTest(kind, alpha, ref, raw, dir, covariance, weight, qb, tb, qe, te, local_jac12);
 }
 extern "C" double orc_ct_point_to_plane_residual(double alpha, const double ref[3], const double raw[3],
                                                  const double normal[3], double weight, const double qb[4],

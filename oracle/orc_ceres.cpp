@@ -89,15 +89,32 @@ struct JQuat {
     }
 };
 
-struct ResidualBlock {   // CTFunctor<FunctorPointToPlane> state, cost_functions.h:186-222
+struct ResidualBlock {   // CTFunctor<FunctorT> state, cost_functions.h:186-222
     double alpha;
-    Vec3 reference, raw, normal;
+    Vec3 reference, raw, normal;   // normal: reference_normal_ (plane) or direction_ (line)
     double weight;
+    int kind = CTICP_DIST_POINT_TO_PLANE;   // inner functor: POINT_TO_PLANE / POINT_TO_LINE / POINT_TO_DISTRIBUTION
+    Mat3 information;                       // FunctorPointToDistribution::neighborhood_information_
 };
 
+// Eigen::Matrix3d::inverse() (compute_inverse_size3: cofactors, det from the first column)
+inline Mat3 Inverse3(const Mat3 &m) {
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m(i1, j1) * m(i2, j2) - m(i1, j2) * m(i2, j1);
+    };
+    const double c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+    const double det = c00 * m(0, 0) + c10 * m(1, 0) + c20 * m(2, 0);
+    const double invdet = 1.0 / det;
+    Mat3 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r(i, j) = cof(j, i) * invdet;
+    return r;
+}
+
 // residual and (optionally) its 14 global partials
-inline double EvalCTPointToPlane(const ResidualBlock &rb, const double *qb, const double *tb, const double *qe,
-                                 const double *te, double *global_jac /*14 or null*/) {
+inline double EvalCTResidual(const ResidualBlock &rb, const double *qb, const double *tb, const double *qe,
+                             const double *te, double *global_jac /*14 or null*/) {
     JQuat Qb{Jet::Var(qb[0], 0), Jet::Var(qb[1], 1), Jet::Var(qb[2], 2), Jet::Var(qb[3], 3)};
     Jet Tb[3] = {Jet::Var(tb[0], 4), Jet::Var(tb[1], 5), Jet::Var(tb[2], 6)};
     JQuat Qe{Jet::Var(qe[0], 7), Jet::Var(qe[1], 8), Jet::Var(qe[2], 9), Jet::Var(qe[3], 10)};
@@ -109,8 +126,9 @@ inline double EvalCTPointToPlane(const ResidualBlock &rb, const double *qb, cons
     Jet tr[3];
     for (int k = 0; k < 3; ++k) tr[k] = alpha_m * Tb[k] + alpha * Te[k];
 
-    // FunctorPointToPlane::operator(), cost_functions.h:47-58 : quat.normalized() * raw + t
-    JQuat q = qi.normalized();
+    // FunctorPointToPlane / FunctorPointToDistribution: quat.normalized() * raw + t (cost_functions.h:47-51,163-167);
+    // FunctorPointToLine: quat * raw + t (:121-125)
+    JQuat q = rb.kind == CTICP_DIST_POINT_TO_LINE ? qi : qi.normalized();
     Jet vx(rb.raw.x), vy(rb.raw.y), vz(rb.raw.z);
     // Eigen _transformVector: uv = q.vec × v; uv += uv; v + w uv + q.vec × uv
     Jet uvx = q.y * vz - q.z * vy, uvy = q.z * vx - q.x * vz, uvz = q.x * vy - q.y * vx;
@@ -118,12 +136,34 @@ inline double EvalCTPointToPlane(const ResidualBlock &rb, const double *qb, cons
     Jet px = vx + q.w * uvx + (q.y * uvz - q.z * uvy) + tr[0];
     Jet py = vy + q.w * uvy + (q.z * uvx - q.x * uvz) + tr[1];
     Jet pz = vz + q.w * uvz + (q.x * uvy - q.y * uvx) + tr[2];
-    Jet product = (Jet(rb.reference.x) - px) * Jet(rb.normal.x) + (Jet(rb.reference.y) - py) * Jet(rb.normal.y) +
-                  (Jet(rb.reference.z) - pz) * Jet(rb.normal.z);
-    Jet res = Jet(rb.weight) * product;
+    Jet res;
+    if (rb.kind == CTICP_DIST_POINT_TO_PLANE) {
+        Jet product = (Jet(rb.reference.x) - px) * Jet(rb.normal.x) + (Jet(rb.reference.y) - py) * Jet(rb.normal.y) +
+                      (Jet(rb.reference.z) - pz) * Jet(rb.normal.z);
+        res = Jet(rb.weight) * product;
+    } else if (rb.kind == CTICP_DIST_POINT_TO_LINE) {   // cost_functions.h:127-129
+        Vec3 dir = rb.normal;
+        const double z = dir.squaredNorm();
+        if (z > 0) dir = dir * (1.0 / std::sqrt(z));
+        Jet dx = px - Jet(rb.reference.x), dy = py - Jet(rb.reference.y), dz = pz - Jet(rb.reference.z);
+        Jet cx = Jet(dir.y) * dz - Jet(dir.z) * dy, cy = Jet(dir.z) * dx - Jet(dir.x) * dz, cz = Jet(dir.x) * dy - Jet(dir.y) * dx;
+        res = Jet(rb.weight) * jsqrt(cx * cx + cy * cy + cz * cz);
+    } else {   // POINT_TO_DISTRIBUTION, cost_functions.h:169-171 : w * diff^T M diff
+        Jet d[3] = {px - Jet(rb.reference.x), py - Jet(rb.reference.y), pz - Jet(rb.reference.z)};
+        Jet acc(0.0);
+        for (int j = 0; j < 3; ++j) {
+            Jet row = d[0] * Jet(rb.information(0, j)) + d[1] * Jet(rb.information(1, j)) + d[2] * Jet(rb.information(2, j));
+            acc = acc + row * d[j];
+        }
+        res = Jet(rb.weight) * acc;
+    }
     if (global_jac)
         for (int i = 0; i < NG; ++i) global_jac[i] = res.v[i];
     return res.a;
+}
+inline double EvalCTPointToPlane(const ResidualBlock &rb, const double *qb, const double *tb, const double *qe,
+                                 const double *te, double *global_jac) {
+    return EvalCTResidual(rb, qb, tb, qe, te, global_jac);
 }
 
 // ceres::EigenQuaternionParameterization::ComputeJacobian (4x3, rows x,y,z,w)
@@ -246,7 +286,7 @@ struct Problem {
 #pragma omp parallel for num_threads(num_threads) reduction(+ : cost)
         for (int i = 0; i < nb; ++i) {
             double g[NG];
-            double res = EvalCTPointToPlane(blocks[i], qb, tb, qe, te, J ? g : nullptr);
+            double res = EvalCTResidual(blocks[i], qb, tb, qe, te, J ? g : nullptr);
             double sq = res * res;
             double rs = 1.0, js = 1.0;
             if (loss.present()) {
@@ -495,18 +535,26 @@ SolveSummary SolveLM(const Problem &problem, double *parameters, int max_num_ite
 
 }  // namespace
 
-// KAT tap: residual of one CTFunctor<FunctorPointToPlane> and its 12 tangent-space partials (program order)
-double CTResidualForTest(double alpha, const double ref[3], const double raw[3], const double normal[3], double weight,
-                         const double qb[4], const double tb[3], const double qe[4], const double te[3],
-                         double *local_jac12) {
+// KAT tap: residual of one CTFunctor<FunctorT> (kind = CTICP_DIST_*) and its 12 tangent-space partials (program order).
+// `dir` is the plane normal or the line direction; `covariance` (row-major 3x3) feeds the distribution functor.
+double CTResidualKindForTest(int kind, double alpha, const double ref[3], const double raw[3], const double dir[3],
+                             const double *covariance, double weight, const double qb[4], const double tb[3],
+                             const double qe[4], const double te[3], double *local_jac12) {
     ResidualBlock rb;
+    rb.kind = kind;
     rb.alpha = alpha;
     rb.reference = Vec3(ref[0], ref[1], ref[2]);
     rb.raw = Vec3(raw[0], raw[1], raw[2]);
-    rb.normal = Vec3(normal[0], normal[1], normal[2]);
+    rb.normal = Vec3(dir[0], dir[1], dir[2]);
     rb.weight = weight;
+    if (covariance) {
+        Mat3 m;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) m(i, j) = covariance[3 * i + j] + (i == j ? 0.05 : 0.0);
+        rb.information = Inverse3(m);
+    }
     double g[NG];
-    double r = EvalCTPointToPlane(rb, qb, tb, qe, te, g);
+    double r = EvalCTResidual(rb, qb, tb, qe, te, g);
     if (local_jac12) {
         double Jqb[4][3], Jqe[4][3];
         QuatLocalJacobian(qb, Jqb);
@@ -519,6 +567,91 @@ double CTResidualForTest(double alpha, const double ref[3], const double raw[3],
         }
     }
     return r;
+}
+double CTResidualForTest(double alpha, const double ref[3], const double raw[3], const double normal[3], double weight,
+                         const double qb[4], const double tb[3], const double qe[4], const double te[3],
+                         double *local_jac12) {
+    return CTResidualKindForTest(CTICP_DIST_POINT_TO_PLANE, alpha, ref, raw, normal, nullptr, weight, qb, tb, qe, te,
+                                 local_jac12);
+}
+
+// One ICP iteration's tail shared by solvers CERES and ROBUST: GetProblem (ct_icp.cpp:409-424), the motion model's
+// regularisers, ceres::Solve, the stop criterion (:613-672 / :1291-1336). Returns 0 = continue, 1 = converged,
+// 2 = not enough residuals (`failed` filled).
+static int AssembleAndSolve(const cticp_icp_options &options, const std::vector<ResidualBlock> &all_blocks,
+                            const std::vector<char> &has_block, const MotionModel *motion_model, TrajectoryFrame &frame,
+                            SE3 &previous_begin_pose, SE3 &previous_end_pose, int &number_of_residuals, int num_threads,
+                            ICPSummary &failed) {
+    Problem problem(options);   // GetProblem, :409-424 : first max_num_residuals non-null functors
+    problem.num_threads = num_threads;
+    number_of_residuals = 0;
+    for (size_t i = 0; i < all_blocks.size(); ++i) {
+        if (!has_block[i]) continue;
+        if (options.max_num_residuals <= 0 || number_of_residuals < options.max_num_residuals) {
+            problem.blocks.push_back(all_blocks[i]);
+            number_of_residuals++;
+        }
+    }
+    if (motion_model && motion_model->present && options.parametrization == CTICP_PARAM_CONTINUOUS_TIME) {   // :613
+        const auto &mo = motion_model->options;
+        const auto &prev = motion_model->previous_frame;
+        problem.prev_velocity = prev.EndTr() - prev.BeginTr();
+        problem.prev_orientation = prev.EndQuat();
+        problem.prev_end_tr = prev.EndTr();
+        if (mo.beta_location_consistency > 0.) {
+            problem.has_location = true;
+            problem.w_location = std::sqrt(number_of_residuals * mo.beta_location_consistency);
+        }
+        if (mo.beta_orientation_consistency > 0.) {
+            problem.has_orientation = true;
+            problem.w_orientation = std::sqrt(number_of_residuals * mo.beta_orientation_consistency);
+        }
+        if (mo.beta_constant_velocity > 0.) {
+            problem.has_cv = true;
+            problem.w_cv = std::sqrt(number_of_residuals * mo.beta_constant_velocity);
+        }
+        if (mo.beta_small_velocity > 0.) {
+            problem.has_small = true;
+            problem.w_small = std::sqrt(number_of_residuals * mo.beta_small_velocity);
+        }
+    }
+    if (number_of_residuals < options.min_number_neighbors) {   // :617 (sic: compares with min_number_neighbors)
+        std::stringstream ss;
+        ss << "[CT_ICP] Error : not enough keypoints selected in ct-icp !" << std::endl;
+        ss << "[CT_ICP] number_of_residuals : " << number_of_residuals << std::endl;
+        failed.success = false;
+        failed.num_residuals_used = number_of_residuals;
+        failed.error_log = ss.str();
+        return 2;
+    }
+
+    double params[14];
+    auto pack = [&]() {
+        const Quat &qb = frame.begin_pose.pose.quat, &qe = frame.end_pose.pose.quat;
+        params[0] = qb.x; params[1] = qb.y; params[2] = qb.z; params[3] = qb.w;
+        params[4] = qe.x; params[5] = qe.y; params[6] = qe.z; params[7] = qe.w;
+        for (int d = 0; d < 3; ++d) {
+            params[8 + d] = frame.begin_pose.pose.tr[d];
+            params[11 + d] = frame.end_pose.pose.tr[d];
+        }
+    };
+    pack();
+    SolveSummary ss = SolveLM(problem, params, options.ls_max_num_iters);
+    frame.begin_pose.pose.quat = Quat(params[0], params[1], params[2], params[3]);
+    frame.end_pose.pose.quat = Quat(params[4], params[5], params[6], params[7]);
+    frame.begin_pose.pose.tr = Vec3(params[8], params[9], params[10]);
+    frame.end_pose.pose.tr = Vec3(params[11], params[12], params[13]);
+    frame.begin_pose.pose.quat.normalize();
+    frame.end_pose.pose.quat.normalize();
+    if (!ss.usable) throw std::runtime_error("Error During Optimization");
+
+    double diff_trans = (previous_begin_pose.tr - frame.BeginTr()).norm() +
+                        (previous_end_pose.tr - frame.EndTr()).norm();
+    double diff_rot = AngularDistance(frame.begin_pose.pose, previous_begin_pose) +
+                      AngularDistance(frame.end_pose.pose, previous_end_pose);
+    previous_begin_pose = frame.begin_pose.pose;
+    previous_end_pose = frame.end_pose.pose;
+    return (diff_rot < options.threshold_orientation_norm && diff_trans < options.threshold_translation_norm) ? 1 : 0;
 }
 
 // DoRegisterCeres, src/ct_icp/ct_icp.cpp:460-706 (CONTINUOUS_TIME + POINT_TO_PLANE)
@@ -589,79 +722,133 @@ ICPSummary DoRegisterCeres(const VoxelMap &map, const cticp_icp_options &options
         icp_summary.keypoint_iterations += kp_iters;
         icp_summary.stencil_points += stencil_sum;
 
-        Problem problem(options);   // GetProblem, :409-424 : first max_num_residuals non-null functors
-        problem.num_threads = num_threads;
-        number_of_residuals = 0;
-        for (size_t i = 0; i < all_blocks.size(); ++i) {
-            if (!has_block[i]) continue;
-            if (options.max_num_residuals <= 0 || number_of_residuals < options.max_num_residuals) {
-                problem.blocks.push_back(all_blocks[i]);
-                number_of_residuals++;
-            }
-        }
-        if (motion_model && motion_model->present && options.parametrization == CTICP_PARAM_CONTINUOUS_TIME) {   // :613
-            const auto &mo = motion_model->options;
-            const auto &prev = motion_model->previous_frame;
-            problem.prev_velocity = prev.EndTr() - prev.BeginTr();
-            problem.prev_orientation = prev.EndQuat();
-            problem.prev_end_tr = prev.EndTr();
-            if (mo.beta_location_consistency > 0.) {
-                problem.has_location = true;
-                problem.w_location = std::sqrt(number_of_residuals * mo.beta_location_consistency);
-            }
-            if (mo.beta_orientation_consistency > 0.) {
-                problem.has_orientation = true;
-                problem.w_orientation = std::sqrt(number_of_residuals * mo.beta_orientation_consistency);
-            }
-            if (mo.beta_constant_velocity > 0.) {
-                problem.has_cv = true;
-                problem.w_cv = std::sqrt(number_of_residuals * mo.beta_constant_velocity);
-            }
-            if (mo.beta_small_velocity > 0.) {
-                problem.has_small = true;
-                problem.w_small = std::sqrt(number_of_residuals * mo.beta_small_velocity);
-            }
-        }
-        if (number_of_residuals < options.min_number_neighbors) {   // :617 (sic: compares with min_number_neighbors)
-            std::stringstream ss;
-            ss << "[CT_ICP] Error : not enough keypoints selected in ct-icp !" << std::endl;
-            ss << "[CT_ICP] number_of_residuals : " << number_of_residuals << std::endl;
-            ICPSummary failed;
-            failed.success = false;
-            failed.num_residuals_used = number_of_residuals;
-            failed.error_log = ss.str();
+        ICPSummary failed;
+        const int status = AssembleAndSolve(options, all_blocks, has_block, motion_model, frame, previous_begin_pose,
+                                            previous_end_pose, number_of_residuals, num_threads, failed);
+        if (status == 2) {
             failed.keypoint_iterations = icp_summary.keypoint_iterations;
             failed.stencil_points = icp_summary.stencil_points;
             return failed;
         }
+        if (status == 1) break;
+    }
+    transform_keypoints();
+    icp_summary.success = true;
+    icp_summary.num_residuals_used = number_of_residuals;
+    icp_summary.num_iters = iter;
+    frame.begin_pose.pose.quat.normalize();
+    frame.end_pose.pose.quat.normalize();
+    return icp_summary;
+}
 
-        double params[14];
-        auto pack = [&]() {
-            const Quat &qb = frame.begin_pose.pose.quat, &qe = frame.end_pose.pose.quat;
-            params[0] = qb.x; params[1] = qb.y; params[2] = qb.z; params[3] = qb.w;
-            params[4] = qe.x; params[5] = qe.y; params[6] = qe.z; params[7] = qe.w;
-            for (int d = 0; d < 3; ++d) {
-                params[8 + d] = frame.begin_pose.pose.tr[d];
-                params[11 + d] = frame.end_pose.pose.tr[d];
+// DoRegisterRobust, src/ct_icp/ct_icp.cpp:1180-1370 (CONTINUOUS_TIME): neighborhoods classified planar / linear /
+// other, one point-to-plane / point-to-line / point-to-distribution residual per keypoint.
+ICPSummary DoRegisterRobust(const VoxelMap &map, const cticp_icp_options &options, std::vector<WPoint3D> &kpts,
+                            TrajectoryFrame &frame, const MotionModel *motion_model) {
+    if (options.parametrization != CTICP_PARAM_CONTINUOUS_TIME)
+        throw std::runtime_error("oracle: only CONTINUOUS_TIME is restated for the ROBUST solver");
+    enum { NONE = 0, LINEAR = 1, PLANAR = 2, VOLUMIC = 3 };   // slam::NEIGHBORHOOD_TYPE, neighborhood.h:138-143
+    ICPSummary icp_summary;
+    const size_t num_points = kpts.size();
+    const int kMinNumNeighbors = options.min_number_neighbors;
+    const int num_threads = std::max(1, options.ls_num_threads);
+    SE3 previous_begin_pose = frame.begin_pose.pose, previous_end_pose = frame.end_pose.pose;   // OptimizationTracker
+    int number_of_residuals = -1;
+    auto transform_keypoints = [&]() {   // TransformKeyPoints, :1373-1393
+        for (auto &kp : kpts) kp.world = frame.begin_pose.InterpolatePose(frame.end_pose, kp.timestamp) * kp.raw;
+    };
+    // `neighborhoods` lives across the ICP iterations (:1214): its classification and description are only
+    // overwritten when the corresponding branch runs, so stale values leak from one iteration to the next.
+    std::vector<Neighborhood> neighborhoods(num_points);
+    std::vector<int> classes(num_points, NONE);
+    std::vector<char> computed(num_points, 0);
+    std::vector<char> has_block;
+    std::vector<ResidualBlock> all_blocks;
+    int iter = 0;
+    for (; iter < options.num_iters_icp; iter++) {
+        transform_keypoints();
+        has_block.assign(num_points, 0);
+        all_blocks.assign(num_points, ResidualBlock());
+        size_t kp_iters = 0, stencil_sum = 0;
+#pragma omp parallel for num_threads(num_threads) reduction(+ : kp_iters, stencil_sum)
+        for (long k = 0; k < (long) num_points; ++k) {   // :1229-1289
+            const WPoint3D &pt = kpts[k];
+            auto &neighborhood = neighborhoods[k];
+            size_t st = 0;
+            map.ComputeNeighborhoodInPlace(pt.world, options.max_number_neighbors, neighborhood, &st);
+            kp_iters++;
+            stencil_sum += st;
+            if ((int) neighborhood.points.size() < kMinNumNeighbors) continue;
+            neighborhood.ComputeNeighborhood();   // ALL_BUT_KDTREE; a no-op below 5 points (neighborhood.h:227)
+            if (neighborhood.is_valid) computed[k] = 1;
+            const auto &desc = neighborhood.description;
+            // ClassifyNeighborhood, neighborhood.h:268-282
+            if (computed[k]) {
+                if (desc.planarity > options.threshold_planarity) classes[k] = PLANAR;
+                else if (desc.linearity > options.threshold_linearity) classes[k] = LINEAR;
+            } else
+                classes[k] = NONE;
+            if (!options.use_lines && classes[k] == LINEAR)   // :1243-1248
+                classes[k] = options.threshold_planarity < desc.planarity ? PLANAR : VOLUMIC;
+            double weight;
+            if (classes[k] == LINEAR) weight = std::pow(std::abs(desc.linearity), options.power_planarity);
+            else if (classes[k] == PLANAR) weight = std::pow(std::abs(desc.planarity), options.power_planarity);
+            else weight = options.weight_neighborhood;
+
+            const Vec3 point = options.use_barycenter ? desc.barycenter : neighborhood.points.front();
+            double distance;
+            int kind = CTICP_DIST_POINT_TO_DISTRIBUTION;
+            const Vec3 d = point - pt.world;
+            if (classes[k] == LINEAR) {
+                Vec3 dir = desc.line;
+                const double z = dir.squaredNorm();
+                if (z > 0) dir = dir * (1.0 / std::sqrt(z));
+                distance = std::abs(d.cross(dir).norm());
+                kind = CTICP_DIST_POINT_TO_LINE;
+            } else if (classes[k] == PLANAR) {
+                distance = std::abs(d.dot(desc.normal));
+                kind = CTICP_DIST_POINT_TO_PLANE;
+            } else
+                distance = d.norm();
+            if (distance < options.outlier_distance) {
+                ResidualBlock rb;
+                rb.alpha = frame.begin_pose.GetAlphaTimestamp(pt.timestamp, frame.end_pose);
+                if (rb.alpha < 0 || rb.alpha > 1) throw std::runtime_error("BAD ALPHA TIMESTAMP !");
+                rb.reference = point;
+                rb.raw = pt.raw;
+                rb.weight = weight;
+                rb.kind = kind;
+                if (kind == CTICP_DIST_POINT_TO_PLANE) rb.normal = desc.normal;
+                else if (kind == CTICP_DIST_POINT_TO_LINE) rb.normal = desc.line;
+                else {   // FunctorPointToDistribution ctor, cost_functions.h:147-158
+                    Mat3 m = desc.covariance;
+                    for (int i = 0; i < 3; ++i) m(i, i) += 0.05;
+                    rb.information = Inverse3(m);
+                }
+                all_blocks[k] = rb;
+                has_block[k] = 1;
             }
-        };
-        pack();
-        SolveSummary ss = SolveLM(problem, params, options.ls_max_num_iters);
-        frame.begin_pose.pose.quat = Quat(params[0], params[1], params[2], params[3]);
-        frame.end_pose.pose.quat = Quat(params[4], params[5], params[6], params[7]);
-        frame.begin_pose.pose.tr = Vec3(params[8], params[9], params[10]);
-        frame.end_pose.pose.tr = Vec3(params[11], params[12], params[13]);
-        frame.begin_pose.pose.quat.normalize();
-        frame.end_pose.pose.quat.normalize();
-        if (!ss.usable) throw std::runtime_error("Error During Optimization");
+        }
+        icp_summary.keypoint_iterations += kp_iters;
+        icp_summary.stencil_points += stencil_sum;
+        if (getenv("ORC_DEBUG_LM")) {
+            int cnt[4] = {0, 0, 0, 0};
+            for (size_t k = 0; k < num_points; ++k)
+                if (has_block[k]) cnt[all_blocks[k].kind]++;
+            fprintf(stderr, "[orc-robust] iter %d blocks: plane %d line %d distribution %d\n", iter, cnt[CTICP_DIST_POINT_TO_PLANE],
+                    cnt[CTICP_DIST_POINT_TO_LINE], cnt[CTICP_DIST_POINT_TO_DISTRIBUTION]);
+        }
 
-        double diff_trans = (previous_begin_pose.tr - frame.BeginTr()).norm() +
-                            (previous_end_pose.tr - frame.EndTr()).norm();
-        double diff_rot = AngularDistance(frame.begin_pose.pose, previous_begin_pose) +
-                          AngularDistance(frame.end_pose.pose, previous_end_pose);
-        previous_begin_pose = frame.begin_pose.pose;
-        previous_end_pose = frame.end_pose.pose;
-        if (diff_rot < options.threshold_orientation_norm && diff_trans < options.threshold_translation_norm) break;
+        ICPSummary failed;
+        const int status = AssembleAndSolve(options, all_blocks, has_block, motion_model, frame, previous_begin_pose,
+                                            previous_end_pose, number_of_residuals, num_threads, failed);
+        if (status == 2) {
+            failed.keypoint_iterations = icp_summary.keypoint_iterations;
+            failed.stencil_points = icp_summary.stencil_points;
+            return failed;
+        }
+        // point_to_plane_with_distortion → DistortFrame only acts on parametrization SIMPLE (:200-215)
+        if (status == 1) break;
     }
     transform_keypoints();
     icp_summary.success = true;

@@ -177,6 +177,8 @@ inline ICPSummary DoRegisterGaussNewton(const VoxelMap &map, const cticp_icp_opt
 ICPSummary DoRegisterCeres(const VoxelMap &map, const cticp_icp_options &options,
                            const cticp_strategy_options &strategy, std::vector<WPoint3D> &kpts,
                            TrajectoryFrame &frame, const MotionModel *motion_model);   // orc_ceres.cpp
+ICPSummary DoRegisterRobust(const VoxelMap &map, const cticp_icp_options &options, std::vector<WPoint3D> &kpts,
+                            TrajectoryFrame &frame, const MotionModel *motion_model);   // orc_ceres.cpp
 
 // CT_ICP_Registration::Register + SELECT_SOLVER, src/ct_icp/ct_icp.cpp:998-1037
 inline ICPSummary Register(const VoxelMap &map, const cticp_icp_options &options,
@@ -187,6 +189,8 @@ inline ICPSummary Register(const VoxelMap &map, const cticp_icp_options &options
             return DoRegisterGaussNewton(map, options, kpts, frame, motion_model);
         case CTICP_SOLVER_CERES:
             return DoRegisterCeres(map, options, strategy, kpts, frame, motion_model);
+        case CTICP_SOLVER_ROBUST:
+            return DoRegisterRobust(map, options, kpts, frame, motion_model);
         default:
             throw std::runtime_error("Unsupported Solver Type");
     }

@@ -582,3 +582,90 @@ def test_odometry_nclt_config_adaptive_sampling(orc, eng, solver, init_frames):
         worst = max(worst, dt)
         assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
     print("nclt ADAPTIVE %s worst pose diff %.3e m" % (solver, worst))
+
+
+# ---- solver ROBUST, src/ct_icp/ct_icp.cpp:1180-1370 ---------------------------------------------------
+def robust_icp_options(b, use_barycenter, use_lines=1):
+    """ct_icp_options of test/regression/regression_robust_config_short_drive.yaml:74-126."""
+    c = b.default_icp_options()
+    c.debug_print = 0
+    c.num_iters_icp = 5
+    c.solver = abi.SOLVER["ROBUST"]
+    c.max_num_residuals = 1000
+    c.min_num_residuals = 100
+    c.weight_alpha = 0.9
+    c.weight_neighborhood = 0.1
+    c.min_number_neighbors = 8
+    c.max_number_neighbors = 20
+    c.power_planarity = 2
+    c.threshold_orientation_norm = 0.001
+    c.threshold_translation_norm = 0.001
+    c.loss_function = abi.LOSS["CAUCHY"]
+    c.ls_max_num_iters = 8
+    c.ls_num_threads = 6
+    c.ls_sigma = 0.1
+    c.max_dist_to_plane_ct_icp = 0.5
+    c.threshold_linearity = 0.9
+    c.threshold_planarity = 0.8
+    c.weight_point_to_point = 0.2
+    c.outlier_distance = 0.8
+    c.use_barycenter = use_barycenter
+    c.use_lines = use_lines
+    return c
+
+
+@pytest.mark.parametrize("use_barycenter,use_lines,thr_lin", [(1, 1, 0.9), (0, 1, 0.6), (1, 0, 0.6)])
+def test_robust_register_matches_oracle(orc, eng, use_barycenter, use_lines, thr_lin):
+    """L3 Register with solver ROBUST: planar / linear / volumic classes, both anchors, all three functors."""
+    map_xyz, kp, frame, prev = _registration_case(orc, eng, "ROBUST")
+    mo, me = orc.voxel_map(small_map_options(orc, cap=1 << 18)), eng.voxel_map(small_map_options(eng, cap=1 << 18))
+    mo.insert(map_xyz); me.insert(map_xyz)
+    io = robust_icp_options(orc, use_barycenter, use_lines)
+    io.threshold_linearity = thr_lin
+    io.max_num_residuals = -1
+    io.num_iters_icp = 4
+    io.ls_num_threads = 4
+    io.threshold_orientation_norm = 1e-9     # run every ICP iteration (the class memory across iterations matters)
+    io.threshold_translation_norm = 1e-9
+    mm = orc.default_odometry_options().default_motion_model
+    st = abi.StrategyOptions(0, 20, 8, 0)
+    _fill_world(orc, kp, frame)
+    kpo, kpe = kp.copy(), kp.copy()
+    fo, fe = frame.copy(), frame.copy()
+    so = mo.icp_register(io, kpo, fo, prev, mm, st)
+    se = me.icp_register(io, kpe, fe, prev, mm, st)
+    assert so.success and se.success
+    assert so.num_residuals_used == se.num_residuals_used > 500
+    dt, dr = frame_diff(fo, fe)
+    assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (dt, dr)
+    assert frame_diff(fo, frame)[0] > 1e-3
+    print("ROBUST residuals %d pose diff %.3e m %.3e rad" % (se.num_residuals_used, dt, dr))
+
+
+def test_odometry_sequence_hdl64_robust(orc, eng, seq_hdl64):
+    """test/regression/regression_robust_config_short_drive.yaml on the KITTI-shape scans."""
+    seq = seq_hdl64[:16]
+    results = []
+    for b in (orc, eng):
+        o = b.default_odometry_options()
+        o.debug_print = 0
+        o.motion_compensation = abi.MOTION_COMPENSATION["CONTINUOUS"]
+        o.initialization = abi.INITIALIZATION["INIT_CONSTANT_VELOCITY"]
+        o.sample_voxel_size = 1.5
+        o.voxel_size = 0.5
+        o.max_distance = 100.0
+        o.distance_error_threshold = 5.0
+        o.map_options = b.legacy_map_options(1.0, 20, 0.1)
+        o.ct_icp_options = robust_icp_options(b, use_barycenter=1)
+        o.default_motion_model.beta_location_consistency = 0.001
+        o.default_motion_model.beta_constant_velocity = 0.001
+        od = b.odometry(o)
+        results.append([(od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]), od.MapSize()) for s in seq])
+    worst_t = worst_r = 0.0
+    for i, ((so, mo), (se, me)) in enumerate(zip(*results)):
+        assert so.success and se.success, i
+        assert (so.num_keypoints, so.number_of_residuals, mo) == (se.num_keypoints, se.number_of_residuals, me), i
+        dt, dr = frame_diff(so.frame, se.frame)
+        worst_t, worst_r = max(worst_t, dt), max(worst_r, dr)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
+    print("ROBUST worst per-frame pose difference: %.3e m, %.3e rad" % (worst_t, worst_r))

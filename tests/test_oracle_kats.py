@@ -58,6 +58,15 @@ def ct_residual(orc, alpha, ref, raw, normal, weight, qb, tb, qe, te, want_jac=F
     return (r, jac) if want_jac else r
 
 
+def ct_residual_kind(orc, kind, alpha, ref, raw, direction, cov, weight, qb, tb, qe, te, want_jac=False):
+    jac = np.zeros(12)
+    arrs = [_arr(x) for x in (ref, raw, direction, qb, tb, qe, te)]
+    c = _arr(np.asarray(cov, dtype=np.float64).reshape(9)) if cov is not None else (None, None)
+    r = orc.fn("ct_residual")(abi.DISTANCE[kind], float(alpha), arrs[0][1], arrs[1][1], arrs[2][1], c[1], float(weight),
+                              arrs[3][1], arrs[4][1], arrs[5][1], arrs[6][1], jac.ctypes.data if want_jac else None)
+    return (r, jac) if want_jac else r
+
+
 # ---- test/unit/ct_icp/test_cost_functions.cxx:70-105 -------------------------------------------------------------
 @pytest.mark.parametrize("seed", range(8))
 def test_ct_point_to_plane_residual_zero_on_plane(orc, seed):
@@ -126,6 +135,84 @@ def test_ct_functor_jacobian_matches_finite_differences(orc, seed):
             return ct_residual(orc, alpha, ref, raw, normal, w, qb2, tb2, qe2, te2)
         Jfd[k] = (f(h) - f(-h)) / (2 * h)
     assert np.abs(J - Jfd).max() < 1e-6 * max(1.0, np.abs(J).max())
+
+
+# ---- test/unit/ct_icp/test_cost_functions.cxx:42-62 (PointToLine), wrapped in the CT functor like solver ROBUST ----
+@pytest.mark.parametrize("seed", range(6))
+def test_ct_point_to_line_residual_zero_on_line(orc, seed):
+    rng = np.random.default_rng(300 + seed)
+    line = np.array([0.0, 0.0, 1.0])
+    reference = rng.uniform(-1, 1, 3)
+    world_point = rng.uniform(-1, 1, 3)
+    world_on_line = reference + rng.uniform(0.1, 1.0) * line
+    qa, ta = _q(rng), rng.uniform(-1, 1, 3)
+    qb, tb = _q(rng), rng.uniform(-1, 1, 3)
+    alpha = 0.3
+    qi, ti = se3_interpolate(orc, qa, ta, qb, tb, alpha)
+    qinv, tinv = se3_inverse(orc, qi, ti)
+    raw = se3_apply(orc, qinv, tinv, world_point)
+    raw_on_line = se3_apply(orc, qinv, tinv, world_on_line)
+    assert abs(ct_residual_kind(orc, "POINT_TO_LINE", alpha, reference, raw_on_line, 3.0 * line, None, 1.0, qa, ta, qb, tb)) <= 1e-12
+    d = world_point - reference
+    expect = np.linalg.norm(np.cross(line, d))
+    got = ct_residual_kind(orc, "POINT_TO_LINE", alpha, reference, raw, 3.0 * line, None, 0.5, qa, ta, qb, tb)
+    assert abs(got - 0.5 * expect) < 1e-12
+
+
+def test_ct_point_to_distribution_residual_is_the_mahalanobis_form(orc):
+    rng = np.random.default_rng(17)
+    a = rng.normal(size=(3, 3))
+    cov = a @ a.T * 0.05
+    reference = rng.uniform(-1, 1, 3)
+    world_point = reference + rng.uniform(-0.5, 0.5, 3)
+    qa, ta = _q(rng), rng.uniform(-1, 1, 3)
+    qb, tb = _q(rng), rng.uniform(-1, 1, 3)
+    alpha = 0.6
+    qi, ti = se3_interpolate(orc, qa, ta, qb, tb, alpha)
+    qinv, tinv = se3_inverse(orc, qi, ti)
+    raw = se3_apply(orc, qinv, tinv, world_point)
+    d = world_point - reference
+    expect = 0.1 * d @ np.linalg.inv(cov + 0.05 * np.eye(3)) @ d          # cost_functions.h:154-171
+    got = ct_residual_kind(orc, "POINT_TO_DISTRIBUTION", alpha, reference, raw, np.zeros(3), cov, 0.1, qa, ta, qb, tb)
+    assert abs(got - expect) < 1e-12
+    raw0 = se3_apply(orc, qinv, tinv, reference)
+    assert abs(ct_residual_kind(orc, "POINT_TO_DISTRIBUTION", alpha, reference, raw0, np.zeros(3), cov, 0.1, qa, ta, qb, tb)) < 1e-20
+
+
+@pytest.mark.parametrize("kind", ["POINT_TO_LINE", "POINT_TO_DISTRIBUTION"])
+@pytest.mark.parametrize("seed", range(3))
+def test_robust_functor_jacobians_match_finite_differences(orc, kind, seed):
+    rng = np.random.default_rng(400 + seed)
+    qb = _q(rng)
+    qe = _quat_plus(qb, rng.normal(scale=0.05, size=3))
+    tb, te = rng.uniform(-5, 5, 3), rng.uniform(-5, 5, 3)
+    raw = rng.uniform(-30, 30, 3)
+    direction = rng.normal(size=3)
+    a = rng.normal(size=(3, 3))
+    cov = a @ a.T * 0.02
+    alpha, w = rng.uniform(0.05, 0.95), rng.uniform(0.2, 1.0)
+    qi, ti = se3_interpolate(orc, qb, tb, qe, te, alpha)
+    ref = se3_apply(orc, qi, ti, raw) + rng.uniform(-0.4, 0.4, 3)           # an anchor a few decimetres away
+    args = (kind, alpha, ref, raw, direction, cov, w)
+    r0, J = ct_residual_kind(orc, *args, qb, tb, qe, te, want_jac=True)
+    h = 1e-6
+    Jfd = np.zeros(12)
+    for k in range(12):
+        def f(step):
+            qb2, qe2, tb2, te2 = qb.copy(), qe.copy(), tb.copy(), te.copy()
+            d = np.zeros(3)
+            d[k % 3] = step
+            if k < 3:
+                qb2 = _quat_plus(qb, d)
+            elif k < 6:
+                qe2 = _quat_plus(qe, d)
+            elif k < 9:
+                tb2 = tb + d
+            else:
+                te2 = te + d
+            return ct_residual_kind(orc, *args, qb2, tb2, qe2, te2)
+        Jfd[k] = (f(h) - f(-h)) / (2 * h)
+    assert np.abs(J - Jfd).max() < 2e-6 * max(1.0, np.abs(J).max())
 
 
 # ---- test/unit/SlamCore/test_neighborhood.cxx:40-53 --------------------------------------------------------------
@@ -242,7 +329,7 @@ def test_permutation_is_a_bijection_and_seeded(orc):
 
 
 # ---- test/integration/testint_odometry.cpp:57-114: end-to-end success on a synthetic scene ---------------------------
-@pytest.mark.parametrize("solver", ["GN", "CERES"])
+@pytest.mark.parametrize("solver", ["GN", "CERES", "ROBUST"])
 def test_oracle_odometry_tracks_ground_truth(orc, seq_small, solver):
     from ct_icp_b200 import synthetic as syn
     o = orc.default_odometry_options()

@@ -104,6 +104,22 @@ class AdaptiveOptions(_Struct):
                 ("_pad0", C.c_int32), ("distance", C.c_double * 8), ("voxel_size", C.c_double * 8)]
 
 
+# sensor_msgs/PointField datatype codes (cticp.h CTICP_DTYPE_*)
+DTYPE = {"int8": 1, "uint8": 2, "int16": 3, "uint16": 4, "int32": 5, "uint32": 6, "float32": 7, "float64": 8}
+
+
+class CloudView(_Struct):
+    _fields_ = [("data", C.c_void_p), ("num_points", C.c_uint64), ("point_step", C.c_uint32),
+                ("xyz_offset", C.c_uint32), ("xyz_dtype", C.c_int32), ("t_offset", C.c_uint32),
+                ("t_dtype", C.c_int32), ("_pad0", C.c_int32)]
+
+
+class CloudSink(_Struct):
+    _fields_ = [("data", C.c_void_p), ("capacity_points", C.c_uint64), ("point_step", C.c_uint32),
+                ("xyz_offset", C.c_uint32), ("xyz_dtype", C.c_int32), ("t_offset", C.c_uint32),
+                ("t_dtype", C.c_int32), ("world", C.c_int32)]
+
+
 class OdometryOptions(_Struct):
     _fields_ = [
         ("ct_icp_options", IcpOptions), ("map_options", MapOptions),

@@ -81,6 +81,9 @@ class Binding:
             "odometry_last_timing": (C.c_int, [vp, P(abi.DeviceTiming)]),
             "nccl_unique_id": (C.c_int, [vp]),
             "odometry_stage_frame": (i64, [vp, vp, sz, vp, sz, sz]),
+            "odometry_register_cloud": (C.c_int, [vp, P(abi.CloudView), u32, P(abi.Frame), P(abi.Summary)]),
+            "odometry_stage_cloud": (i64, [vp, P(abi.CloudView)]),
+            "odometry_write_points": (i64, [vp, C.c_int, P(abi.CloudSink)]),
             "odometry_register_staged": (C.c_int, [vp, i64, u32, P(abi.Summary)]),
             "odometry_clear_staged": (C.c_int, [vp]),
             "odometry_timer_start": (C.c_int, [vp]),
@@ -299,6 +302,42 @@ class Odometry:
 
     def RegisterFrameWithEstimate(self, xyz, timestamps, initial_estimate, frame_id):
         return self._register(xyz, timestamps, frame_id, initial_estimate)
+
+    # ---- record buffers (sensor_msgs/PointCloud2-like), zero-copy in and out (engine only) -------------------
+    @staticmethod
+    def _cloud_view(records, xyz_field="x", t_field="t"):
+        """records: 1-D numpy structured array with fields x, y, z (contiguous, same float type) and a timestamp."""
+        assert records.ndim == 1 and records.flags.c_contiguous and records.dtype.fields is not None
+        f = records.dtype.fields
+        xdt, xoff = f[xyz_field][0], f[xyz_field][1]
+        assert f["y"] == (xdt, xoff + xdt.itemsize) and f["z"] == (xdt, xoff + 2 * xdt.itemsize), "x, y, z must be contiguous"
+        tdt, toff = f[t_field][0], f[t_field][1]
+        return abi.CloudView(records.ctypes.data, len(records), records.dtype.itemsize, xoff, abi.DTYPE[xdt.name], toff,
+                             abi.DTYPE[tdt.name], 0)
+
+    def RegisterCloud(self, records, frame_id, initial_estimate=None, t_field="t"):
+        """RegisterFrame(const slam::PointCloud&, frame_id) on an interleaved record buffer, read in place."""
+        view = self._cloud_view(records, t_field=t_field)
+        summary = abi.Summary()
+        self.b.check(self.b.fn("odometry_register_cloud")(
+            self.h, C.byref(view), frame_id, C.byref(initial_estimate) if initial_estimate is not None else None,
+            C.byref(summary)))
+        return summary
+
+    def stage_cloud(self, records, t_field="t"):
+        view = self._cloud_view(records, t_field=t_field)
+        return self.b.check(self.b.fn("odometry_stage_cloud")(self.h, C.byref(view)))
+
+    def write_points(self, which, records, world=True, t_field="t"):
+        """Fills `records` (structured array with x, y, z [+ timestamp field]) with one of the summary's point vectors;
+        returns the number of points the vector holds."""
+        f = records.dtype.fields
+        xdt, xoff = f["x"][0], f["x"][1]
+        has_t = t_field in f
+        sink = abi.CloudSink(records.ctypes.data, len(records), records.dtype.itemsize, xoff, abi.DTYPE[xdt.name],
+                             f[t_field][1] if has_t else 0, abi.DTYPE[f[t_field][0].name] if has_t else 0,
+                             1 if world else 0)
+        return self.b.check(self.b.fn("odometry_write_points")(self.h, which, C.byref(sink)))
 
     # ---- device-resident input / measurement helpers (engine only) ---------------------------------------
     def stage_frame(self, xyz, timestamps):

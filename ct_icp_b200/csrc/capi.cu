@@ -316,9 +316,53 @@ int cticp_odometry_register_frame(cticp_odometry *h, const double *xyz, size_t x
                                   const cticp_frame *initial_estimate, cticp_summary *out_summary) {
     return Guard([&] {
         if (!h) throw std::invalid_argument("null handle");
-        h->engine->RegisterFrame(xyz, xyz_stride_bytes, t, t_stride_bytes, n, frame_id, initial_estimate, out_summary);
+        cticp::ScanView v;
+        v.xyz = xyz; v.xyz_stride = xyz_stride_bytes; v.t = t; v.t_stride = t_stride_bytes; v.n = n;
+        h->engine->RegisterFrame(v, frame_id, initial_estimate, out_summary);
         return (int) CTICP_OK;
     });
+}
+static cticp::ScanView ViewOfCloud(const cticp_cloud_view *c) {
+    if (!c || !c->data) throw std::invalid_argument("The registered frame cannot be empty");
+    const size_t xs = c->xyz_dtype == CTICP_DTYPE_FLOAT32 ? 4 : 8;
+    static const size_t kSize[9] = {0, 1, 1, 2, 2, 4, 4, 4, 8};
+    if (c->t_dtype < 1 || c->t_dtype > 8) throw std::invalid_argument("unknown timestamp dtype");
+    if ((size_t) c->xyz_offset + 3 * xs > c->point_step || (size_t) c->t_offset + kSize[c->t_dtype] > c->point_step)
+        throw std::invalid_argument("cloud view: a field lies outside the record (point_step)");
+    cticp::ScanView v;
+    v.xyz = static_cast<const char *>(c->data) + c->xyz_offset;
+    v.xyz_stride = c->point_step;
+    v.xyz_dtype = c->xyz_dtype;
+    v.t = static_cast<const char *>(c->data) + c->t_offset;
+    v.t_stride = c->point_step;
+    v.t_dtype = c->t_dtype;
+    v.n = (size_t) c->num_points;
+    return v;
+}
+int cticp_odometry_register_cloud(cticp_odometry *h, const cticp_cloud_view *cloud, uint32_t frame_id,
+                                  const cticp_frame *initial_estimate, cticp_summary *out_summary) {
+    return Guard([&] {
+        if (!h) throw std::invalid_argument("null handle");
+        h->engine->RegisterFrame(ViewOfCloud(cloud), frame_id, initial_estimate, out_summary);
+        return (int) CTICP_OK;
+    });
+}
+int64_t cticp_odometry_stage_cloud(cticp_odometry *h, const cticp_cloud_view *cloud) {
+    int64_t slot = -1;
+    int rc = Guard([&] {
+        slot = h->engine->StageFrame(ViewOfCloud(cloud));
+        return (int) CTICP_OK;
+    });
+    return rc < 0 ? rc : slot;
+}
+int64_t cticp_odometry_write_points(cticp_odometry *h, int which, const cticp_cloud_sink *sink) {
+    int64_t count = 0;
+    int rc = Guard([&] {
+        if (!sink) throw std::invalid_argument("null sink");
+        count = h->engine->WritePoints(which, *sink);
+        return (int) CTICP_OK;
+    });
+    return rc < 0 ? rc : count;
 }
 int64_t cticp_odometry_get_points(cticp_odometry *h, int which, cticp_wpoint *dst, size_t cap) {
     int64_t count = 0;
@@ -362,7 +406,9 @@ int64_t cticp_odometry_stage_frame(cticp_odometry *h, const double *xyz, size_t 
                                    size_t t_stride_bytes, size_t n) {
     int64_t slot = -1;
     int rc = Guard([&] {
-        slot = h->engine->StageFrame(xyz, xyz_stride_bytes, t, t_stride_bytes, n);
+        cticp::ScanView v;
+        v.xyz = xyz; v.xyz_stride = xyz_stride_bytes; v.t = t; v.t_stride = t_stride_bytes; v.n = n;
+        slot = h->engine->StageFrame(v);
         return (int) CTICP_OK;
     });
     return rc < 0 ? rc : slot;

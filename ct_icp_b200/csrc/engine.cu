@@ -176,13 +176,10 @@ void Engine::InitializeMotion(const FrameInfo &info, const cticp_frame *initial_
 
 // InitializeFrame, odometry.cpp:333-382 — host part: pack (x, y, z, alpha) into pinned memory; device part:
 // shuffle / sub_sample_frame / timestamp override / shuffle.
-void Engine::IngestAndSubSample(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
-                                const FrameInfo &info) {
-    IngestImpl(xyz, xyz_stride, t, t_stride, n, info, -1);
-}
+void Engine::IngestAndSubSample(const ScanView &scan, const FrameInfo &info) { IngestImpl(scan, info, -1); }
 
-void Engine::IngestImpl(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
-                        const FrameInfo &info, int64_t staged_slot) {
+void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t staged_slot) {
+    const size_t n = scan.n;
     const int k = info.registered_fid;
     const HostFrame &tr = trajectory_[k];
     const double bts = tr.begin_pose.dest_timestamp, ets = tr.end_pose.dest_timestamp;
@@ -196,7 +193,7 @@ void Engine::IngestImpl(const double *xyz, size_t xyz_stride, const double *t, s
         pipe_->UploadFromDevice(staged_[staged_slot].d_points, n);   // already packed, already in HBM
     } else {
         auto tp = hclock::now();
-        PackScan(xyz, xyz_stride, t, t_stride, n, bts, ets, pipe_->Staging());
+        PackScan(scan, bts, ets, pipe_->Staging());
         const double t_pack = ms_since(tp);
         if (getenv("CTICP_DEBUG_TIMERS")) cudaEventRecord(ev_[4], stream_);
         pipe_->Upload(n);
@@ -268,39 +265,78 @@ void HostPool::ParallelFor(size_t n, const std::function<void(size_t, size_t, in
 
 // (x, y, z, alpha) packing: alpha = GetAlphaTimestamp(t) w.r.t. the pose pair's timestamps (types.h:192-219);
 // the caller has range-checked the timestamps
-void Engine::PackScan(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n, double bts,
-                      double ets, float4 *dst) {
+namespace {
+template <typename T> struct TypeTag { using type = T; };
+// calls fn(TypeTag<xyz scalar>, TypeTag<timestamp scalar>) for the view's dtypes
+template <typename F> void DispatchScanTypes(const ScanView &v, F &&fn) {
+    auto with_t = [&](auto xt) {
+        switch (v.t_dtype) {
+            case CTICP_DTYPE_INT8: fn(xt, TypeTag<int8_t>{}); break;
+            case CTICP_DTYPE_UINT8: fn(xt, TypeTag<uint8_t>{}); break;
+            case CTICP_DTYPE_INT16: fn(xt, TypeTag<int16_t>{}); break;
+            case CTICP_DTYPE_UINT16: fn(xt, TypeTag<uint16_t>{}); break;
+            case CTICP_DTYPE_INT32: fn(xt, TypeTag<int32_t>{}); break;
+            case CTICP_DTYPE_UINT32: fn(xt, TypeTag<uint32_t>{}); break;
+            case CTICP_DTYPE_FLOAT32: fn(xt, TypeTag<float>{}); break;
+            case CTICP_DTYPE_FLOAT64: fn(xt, TypeTag<double>{}); break;
+            default: throw std::invalid_argument("unknown timestamp dtype");
+        }
+    };
+    switch (v.xyz_dtype) {
+        case CTICP_DTYPE_FLOAT32: with_t(TypeTag<float>{}); break;
+        case CTICP_DTYPE_FLOAT64: with_t(TypeTag<double>{}); break;
+        default: throw std::invalid_argument("x/y/z must be FLOAT32 or FLOAT64");
+    }
+}
+template <typename T> inline T LoadUnaligned(const char *p) {   // PointCloud2 records are packed: no alignment promise
+    T v;
+    memcpy(&v, p, sizeof(T));
+    return v;
+}
+}  // namespace
+
+void Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst) {
     const double mn = std::min(bts, ets), mx = std::max(bts, ets);
     const double inv = (mx > mn) ? 1.0 / (mx - mn) : 0.0;
-    const char *px = reinterpret_cast<const char *>(xyz), *pt = reinterpret_cast<const char *>(t);
+    const char *px = static_cast<const char *>(scan.xyz), *pt = static_cast<const char *>(scan.t);
+    const size_t xs = scan.xyz_stride, ts = scan.t_stride;
     const bool spans = mx > mn;
-    pool_->ParallelFor(n, [&](size_t b, size_t e, int) {
-        for (size_t i = b; i < e; ++i) {
-            const double *p = reinterpret_cast<const double *>(px + i * xyz_stride);
-            const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
-            const double a = spans ? (ti - mn) * inv : 1.0;
-            // non-temporal store: the packed scan is consumed by the DMA engine, not by this core — keeping it out
-            // of the CPU caches took the H2D copy from ~12 GB/s (snooped dirty lines) to PCIe speed
-            _mm_stream_ps(reinterpret_cast<float *>(dst + i), _mm_set_ps((float) a, (float) p[2], (float) p[1], (float) p[0]));
-        }
-        _mm_sfence();
+    DispatchScanTypes(scan, [&](auto xt, auto tt) {
+        using XT = typename decltype(xt)::type;
+        using TT = typename decltype(tt)::type;
+        pool_->ParallelFor(scan.n, [&](size_t b, size_t e, int) {
+            for (size_t i = b; i < e; ++i) {
+                const char *p = px + i * xs;
+                const XT x = LoadUnaligned<XT>(p), y = LoadUnaligned<XT>(p + sizeof(XT)), z = LoadUnaligned<XT>(p + 2 * sizeof(XT));
+                const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
+                const double a = spans ? (ti - mn) * inv : 1.0;
+                // non-temporal store: the packed scan is consumed by the DMA engine, not by this core — keeping it
+                // out of the CPU caches took the H2D copy from ~12 GB/s (snooped dirty lines) to PCIe speed
+                _mm_stream_ps(reinterpret_cast<float *>(dst + i), _mm_set_ps((float) a, (float) z, (float) y, (float) x));
+            }
+            _mm_sfence();
+        });
     });
 }
 
-void Engine::MinMaxTimestamps(const double *t, size_t t_stride, size_t n, double *mn_out, double *mx_out) {
-    const char *pt = reinterpret_cast<const char *>(t);
+void Engine::MinMaxTimestamps(const ScanView &scan, double *mn_out, double *mx_out) {
+    const char *pt = static_cast<const char *>(scan.t);
+    const size_t ts = scan.t_stride;
     double mns[64], mxs[64];
     const int parts = pool_->size();
     for (int i = 0; i < parts; ++i) { mns[i] = INFINITY; mxs[i] = -INFINITY; }
-    pool_->ParallelFor(n, [&](size_t b, size_t e, int part) {
-        double mn = INFINITY, mx = -INFINITY;
-        for (size_t i = b; i < e; ++i) {
-            const double ti = *reinterpret_cast<const double *>(pt + i * t_stride);
-            mn = ti < mn ? ti : mn;
-            mx = ti > mx ? ti : mx;
-        }
-        mns[part] = mn;
-        mxs[part] = mx;
+    DispatchScanTypes(scan, [&](auto, auto tt) {
+        using TT = typename decltype(tt)::type;
+        pool_->ParallelFor(scan.n, [&](size_t b, size_t e, int part) {
+            double mn = INFINITY, mx = -INFINITY;
+            for (size_t i = b; i < e; ++i) {
+                const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
+                mn = ti < mn ? ti : mn;
+                mx = ti > mx ? ti : mx;
+            }
+            mns[part] = mn;
+            mxs[part] = mx;
+        });
     });
     double mn = INFINITY, mx = -INFINITY;
     for (int i = 0; i < parts; ++i) { mn = std::min(mn, mns[i]); mx = std::max(mx, mxs[i]); }
@@ -308,15 +344,16 @@ void Engine::MinMaxTimestamps(const double *t, size_t t_stride, size_t n, double
     *mx_out = mx;
 }
 
-int64_t Engine::StageFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n) {
+int64_t Engine::StageFrame(const ScanView &scan) {
     CT_CUDA_CHECK(cudaSetDevice(device_));
-    if (n == 0 || !xyz || !t) throw std::invalid_argument("The registered frame cannot be empty");
+    const size_t n = scan.n;
+    if (n == 0 || !scan.xyz || !scan.t) throw std::invalid_argument("The registered frame cannot be empty");
     if (n > pipe_->MaxPoints()) throw CapacityError("scan has more points than max_points_per_frame");
     StagedScan sc;
     sc.n = n;
-    MinMaxTimestamps(t, t_stride, n, &sc.t_min, &sc.t_max);
+    MinMaxTimestamps(scan, &sc.t_min, &sc.t_max);
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // the pinned staging buffer may still feed a previous copy
-    PackScan(xyz, xyz_stride, t, t_stride, n, sc.t_min, sc.t_max, pipe_->Staging());
+    PackScan(scan, sc.t_min, sc.t_max, pipe_->Staging());
     CT_CUDA_CHECK(cudaMalloc(&sc.d_points, sizeof(float4) * n));
     CT_CUDA_CHECK(cudaMemcpyAsync(sc.d_points, pipe_->Staging(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream_));
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -572,19 +609,21 @@ void Engine::UpdateMap(Summary &s, int registered_fid) {
 }
 
 // RegisterFrame / RegisterFrameWithEstimate (odometry.cpp:199-236) → DoRegister (:386-501)
-void Engine::RegisterFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
-                           uint32_t frame_id, const cticp_frame *initial_estimate, cticp_summary *out) {
-    if (n == 0 || !xyz || !t) throw std::invalid_argument("The registered frame cannot be empty");
-    RegisterCommon(xyz, xyz_stride, t, t_stride, n, frame_id, initial_estimate, -1, out);
+void Engine::RegisterFrame(const ScanView &scan, uint32_t frame_id, const cticp_frame *initial_estimate,
+                           cticp_summary *out) {
+    if (scan.n == 0 || !scan.xyz || !scan.t) throw std::invalid_argument("The registered frame cannot be empty");
+    RegisterCommon(scan, frame_id, initial_estimate, -1, out);
 }
 void Engine::RegisterStaged(int64_t slot, uint32_t frame_id, cticp_summary *out) {
     if (slot < 0 || slot >= (int64_t) staged_.size()) throw std::invalid_argument("unknown staged slot");
-    RegisterCommon(nullptr, 0, nullptr, 0, staged_[slot].n, frame_id, nullptr, slot, out);
+    ScanView none;
+    none.n = staged_[slot].n;
+    RegisterCommon(none, frame_id, nullptr, slot, out);
 }
 
-void Engine::RegisterCommon(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
-                            uint32_t frame_id, const cticp_frame *initial_estimate, int64_t staged_slot,
-                            cticp_summary *out) {
+void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp_frame *initial_estimate,
+                            int64_t staged_slot, cticp_summary *out) {
+    const size_t n = scan.n;
     auto t_start = hclock::now();
     CT_CUDA_CHECK(cudaSetDevice(device_));
     // compute_frame_info, odometry.cpp:186-196
@@ -593,7 +632,7 @@ void Engine::RegisterCommon(const double *xyz, size_t xyz_stride, const double *
         info.begin_timestamp = staged_[staged_slot].t_min;
         info.end_timestamp = staged_[staged_slot].t_max;
     } else {
-        MinMaxTimestamps(t, t_stride, n, &info.begin_timestamp, &info.end_timestamp);
+        MinMaxTimestamps(scan, &info.begin_timestamp, &info.end_timestamp);
     }
     info.registered_fid = registered_frames_++;
     info.frame_id = frame_id;
@@ -612,7 +651,7 @@ void Engine::RegisterCommon(const double *xyz, size_t xyz_stride, const double *
     last_all_world_valid_ = last_kp_world_valid_ = false;
 
     CT_CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
-    IngestImpl(xyz, xyz_stride, t, t_stride, n, info, staged_slot);
+    IngestImpl(scan, info, staged_slot);
     const double t_initialization = ms_since(t_start);
 
     Summary summary;
@@ -727,7 +766,8 @@ cticp_device_timing Engine::LastTiming() {
 }
 
 // RegistrationSummary::{corrected_points, all_corrected_points, keypoints} on demand
-int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
+// the device arrays behind RegistrationSummary::{corrected_points, all_corrected_points, keypoints}
+void Engine::ResolvePoints(int which, const float4 **out_pts, const double **out_world, size_t *out_count) {
     CT_CUDA_CHECK(cudaSetDevice(device_));
     const float4 *d_pts = nullptr;
     const double *d_world = nullptr;
@@ -761,6 +801,17 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
         default:
             throw std::invalid_argument("which");
     }
+    *out_pts = d_pts;
+    *out_world = d_world;
+    *out_count = count;
+}
+
+int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
+    const float4 *d_pts = nullptr;
+    const double *d_world = nullptr;
+    size_t count = 0;
+    ResolvePoints(which, &d_pts, &d_world, &count);
+    const auto &f = last_frame_;
     const size_t m = std::min(cap, count);
     if (m == 0 || !dst) return (int64_t) count;
     std::vector<float4> hp(m);
@@ -778,6 +829,54 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
         o.index_frame = last_info_.frame_id;
         o._pad0 = 0;
     }
+    return (int64_t) count;
+}
+
+// cticp_odometry_write_points: the same vectors written straight into the caller's record layout
+int64_t Engine::WritePoints(int which, const cticp_cloud_sink &sink) {
+    const float4 *d_pts = nullptr;
+    const double *d_world = nullptr;
+    size_t count = 0;
+    ResolvePoints(which, &d_pts, &d_world, &count);
+    const size_t m = std::min((size_t) sink.capacity_points, count);
+    if (m == 0 || !sink.data) return (int64_t) count;
+    const size_t xs = sink.xyz_dtype == CTICP_DTYPE_FLOAT32 ? 4 : 8;
+    if (sink.xyz_dtype != CTICP_DTYPE_FLOAT32 && sink.xyz_dtype != CTICP_DTYPE_FLOAT64)
+        throw std::invalid_argument("sink: x/y/z must be FLOAT32 or FLOAT64");
+    if (sink.t_dtype != 0 && sink.t_dtype != CTICP_DTYPE_FLOAT32 && sink.t_dtype != CTICP_DTYPE_FLOAT64)
+        throw std::invalid_argument("sink: timestamp must be FLOAT32 or FLOAT64");
+    if ((size_t) sink.xyz_offset + 3 * xs > sink.point_step ||
+        (sink.t_dtype && (size_t) sink.t_offset + (sink.t_dtype == CTICP_DTYPE_FLOAT32 ? 4 : 8) > sink.point_step))
+        throw std::invalid_argument("sink: a field lies outside the record (point_step)");
+    std::vector<float4> hp(m);
+    std::vector<double> hw(sink.world ? 3 * m : 0);
+    CT_CUDA_CHECK(cudaMemcpyAsync(hp.data(), d_pts, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream_));
+    if (sink.world)
+        CT_CUDA_CHECK(cudaMemcpyAsync(hw.data(), d_world, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, stream_));
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    const auto &f = last_frame_;
+    const double bts = f.begin_pose.dest_timestamp, ets = f.end_pose.dest_timestamp;
+    const double mn = std::min(bts, ets), mx = std::max(bts, ets);
+    char *base = static_cast<char *>(sink.data);
+    pool_->ParallelFor(m, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            char *rec = base + i * sink.point_step;
+            double p[3];
+            if (sink.world) { p[0] = hw[3 * i]; p[1] = hw[3 * i + 1]; p[2] = hw[3 * i + 2]; }
+            else { p[0] = hp[i].x; p[1] = hp[i].y; p[2] = hp[i].z; }
+            if (sink.xyz_dtype == CTICP_DTYPE_FLOAT32) {
+                const float q[3] = {(float) p[0], (float) p[1], (float) p[2]};
+                memcpy(rec + sink.xyz_offset, q, sizeof(q));
+            } else {
+                memcpy(rec + sink.xyz_offset, p, sizeof(p));
+            }
+            if (sink.t_dtype) {
+                const double t = mn + (double) hp[i].w * (mx - mn);
+                if (sink.t_dtype == CTICP_DTYPE_FLOAT32) { const float tf = (float) t; memcpy(rec + sink.t_offset, &tf, 4); }
+                else memcpy(rec + sink.t_offset, &t, 8);
+            }
+        }
+    });
     return (int64_t) count;
 }
 

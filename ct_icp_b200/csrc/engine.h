@@ -36,6 +36,19 @@ struct HostFrame {   // ct_icp::TrajectoryFrame
     HostPose begin_pose, end_pose;
 };
 
+// A borrowed scan: x,y,z contiguous of one scalar type at `xyz`, one timestamp scalar at `t`, both strided in bytes.
+// What the reference reads through XYZConst<double>() / TimestampsProxy<double>() (odometry.cpp:335-336): any source
+// scalar type, converted with static_cast<double> by the proxy (include/SlamCore/data/view.h:99-120).
+struct ScanView {
+    const void *xyz = nullptr;
+    size_t xyz_stride = 0;
+    int xyz_dtype = CTICP_DTYPE_FLOAT64;   // FLOAT32 / FLOAT64
+    const void *t = nullptr;
+    size_t t_stride = 0;
+    int t_dtype = CTICP_DTYPE_FLOAT64;     // any CTICP_DTYPE_*
+    size_t n = 0;
+};
+
 // Minimal fork-join pool for the two host passes over a scan (timestamp min/max, float4 packing): the only O(N) host
 // work of RegisterFrame. Workers sleep on a condition variable between frames.
 class HostPool {
@@ -63,10 +76,11 @@ public:
     Engine(const cticp_odometry_options &options, int device);
     ~Engine();
 
-    void RegisterFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+    void RegisterFrame(const ScanView &scan,
                        uint32_t frame_id, const cticp_frame *initial_estimate, cticp_summary *out);
     // device-resident input: pack + copy a scan to HBM now, register it later
-    int64_t StageFrame(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n);
+    int64_t StageFrame(const ScanView &scan);
+    int64_t WritePoints(int which, const cticp_cloud_sink &sink);
     void RegisterStaged(int64_t slot, uint32_t frame_id, cticp_summary *out);
     void ClearStaged();
     void TimerStart();
@@ -108,15 +122,16 @@ private:
     };
 
     void InitializeMotion(const FrameInfo &info, const cticp_frame *initial_estimate);
-    void IngestAndSubSample(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+    void ResolvePoints(int which, const float4 **out_pts, const double **out_world, size_t *out_count);
+    void IngestAndSubSample(const ScanView &scan,
                             const FrameInfo &info);
-    void IngestImpl(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+    void IngestImpl(const ScanView &scan,
                     const FrameInfo &info, int64_t staged_slot);
-    void PackScan(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n, double bts,
+    void PackScan(const ScanView &scan, double bts,
                   double ets, float4 *dst);
-    void MinMaxTimestamps(const double *t, size_t t_stride, size_t n, double *mn_out, double *mx_out);
+    void MinMaxTimestamps(const ScanView &scan, double *mn_out, double *mx_out);
     std::unique_ptr<HostPool> pool_;
-    void RegisterCommon(const double *xyz, size_t xyz_stride, const double *t, size_t t_stride, size_t n,
+    void RegisterCommon(const ScanView &scan,
                         uint32_t frame_id, const cticp_frame *initial_estimate, int64_t staged_slot,
                         cticp_summary *out);
     struct StagedScan {

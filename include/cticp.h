@@ -44,6 +44,10 @@ typedef enum cticp_status {
 
 /* ---- enums mirroring the reference (same numeric order) ------------------------------------------------ */
 /* include/ct_icp/ct_icp.h:35-39 */
+/* scalar types of interleaved point records = sensor_msgs/PointField datatype codes
+ * (ros/roscore/src/pc2_conversion.cxx:6-27, slam::PROPERTY_TYPE) */
+enum { CTICP_DTYPE_INT8 = 1, CTICP_DTYPE_UINT8 = 2, CTICP_DTYPE_INT16 = 3, CTICP_DTYPE_UINT16 = 4,
+       CTICP_DTYPE_INT32 = 5, CTICP_DTYPE_UINT32 = 6, CTICP_DTYPE_FLOAT32 = 7, CTICP_DTYPE_FLOAT64 = 8 };
 enum { CTICP_SOLVER_GN = 0, CTICP_SOLVER_CERES = 1, CTICP_SOLVER_ROBUST = 2 };
 /* include/ct_icp/ct_icp.h:41-47 */
 enum { CTICP_LOSS_STANDARD = 0, CTICP_LOSS_CAUCHY = 1, CTICP_LOSS_HUBER = 2, CTICP_LOSS_TOLERANT = 3,
@@ -302,6 +306,45 @@ int cticp_odometry_register_frame(cticp_odometry *h,
                                   size_t n, uint32_t frame_id,
                                   const cticp_frame *initial_estimate,
                                   cticp_summary *out_summary);
+
+/* An interleaved point buffer described like a sensor_msgs/PointCloud2 (one record every point_step bytes; field
+ * "x" at xyz_offset with y and z following contiguously in the same scalar type — the "vertex" element that
+ * SchemaBuilderFromCloud2 builds, ros/roscore/src/pc2_conversion.cxx:73-80 — and one timestamp scalar at t_offset).
+ * It is the zero-copy input of the ROS node (ROSCloud2ToSlamPointCloudShallow, pc2_conversion.cxx:86-96 →
+ * RegisterFrame(const slam::PointCloud&), src/ct_icp/odometry.cpp:199-214): the engine reads the records in place
+ * and converts each scalar with static_cast<double>, as the reference's proxy views do
+ * (include/SlamCore/data/view.h:99-120). Records need no alignment. */
+typedef struct cticp_cloud_view {
+    const void *data;
+    uint64_t num_points;           /* width * height */
+    uint32_t point_step;
+    uint32_t xyz_offset;
+    int32_t xyz_dtype;             /* CTICP_DTYPE_FLOAT32 or CTICP_DTYPE_FLOAT64 */
+    uint32_t t_offset;
+    int32_t t_dtype;               /* any CTICP_DTYPE_* */
+    int32_t _pad0;
+} cticp_cloud_view;
+
+/* RegisterFrame(const slam::PointCloud&, frame_id) / RegisterFrameWithEstimate on a record buffer. */
+int cticp_odometry_register_cloud(cticp_odometry *h, const cticp_cloud_view *cloud, uint32_t frame_id,
+                                  const cticp_frame *initial_estimate, cticp_summary *out_summary);
+/* cticp_odometry_stage_frame on a record buffer. */
+int64_t cticp_odometry_stage_cloud(cticp_odometry *h, const cticp_cloud_view *cloud);
+
+/* Egress in the caller's record layout (what the ROS node builds from summary.corrected_points / keypoints for its
+ * publishers: pcl::PointCloud<slam::XYZTPoint>, ct_icp_odometry_node.cxx:228-262): writes world (world != 0) or raw
+ * x,y,z and, when t_dtype != 0, the timestamp of min(capacity_points, count) points. Returns the count. */
+typedef struct cticp_cloud_sink {
+    void *data;
+    uint64_t capacity_points;
+    uint32_t point_step;
+    uint32_t xyz_offset;
+    int32_t xyz_dtype;             /* CTICP_DTYPE_FLOAT32 or CTICP_DTYPE_FLOAT64 */
+    uint32_t t_offset;
+    int32_t t_dtype;               /* 0 = no timestamp; else CTICP_DTYPE_FLOAT32 / CTICP_DTYPE_FLOAT64 */
+    int32_t world;
+} cticp_cloud_sink;
+int64_t cticp_odometry_write_points(cticp_odometry *h, int which, const cticp_cloud_sink *sink);
 
 /* RegistrationSummary::{corrected_points, all_corrected_points, keypoints}, include/ct_icp/odometry.h:187-191.
  * Copies min(cap, count) points device->host; returns the count or a negative status. */

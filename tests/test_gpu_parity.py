@@ -269,7 +269,7 @@ def test_timestamp_outside_pose_interval_is_an_error(eng):
     assert e.value.code == abi.ERR_TIMESTAMP
 
 
-def _run_sequence(b, seq, solver="GN", **overrides):
+def _sequence_options(b, solver="GN", **overrides):
     o = b.default_odometry_options()
     o.ct_icp_options.solver = abi.SOLVER[solver]
     o.ct_icp_options.min_number_neighbors = 10
@@ -279,7 +279,11 @@ def _run_sequence(b, seq, solver="GN", **overrides):
     o.debug_print = 0
     for k, v in overrides.items():
         setattr(o, k, v)
-    od = b.odometry(o)
+    return o
+
+
+def _run_sequence(b, seq, solver="GN", **overrides):
+    od = b.odometry(_sequence_options(b, solver, **overrides))
     out = []
     for s in seq:
         sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
@@ -669,3 +673,42 @@ def test_odometry_sequence_hdl64_robust(orc, eng, seq_hdl64):
         worst_t, worst_r = max(worst_t, dt), max(worst_r, dr)
         assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
     print("ROBUST worst per-frame pose difference: %.3e m, %.3e rad" % (worst_t, worst_r))
+
+
+# ---- PointCloud2-like record buffers in and out ------------------------------------------------------
+@pytest.mark.parametrize("xyz_type,t_type", [("float32", "float32"), ("float32", "float64"), ("float64", "uint32")])
+def test_register_cloud_records_match_oracle(orc, eng, seq_small, xyz_type, t_type):
+    """cticp_odometry_register_cloud reads packed records in place (any PointField scalar type for the timestamp,
+    float32/float64 coordinates, unaligned record size) and must behave like RegisterFrame on the converted arrays —
+    the reference's XYZConst<double>() / TimestampsProxy<double>() views (odometry.cpp:335-336)."""
+    rec_dtype = np.dtype({"names": ["intensity", "x", "y", "z", "ring", "t"],
+                          "formats": ["u1", xyz_type, xyz_type, xyz_type, "u2", t_type],
+                          "offsets": [0, 1, 1 + np.dtype(xyz_type).itemsize, 1 + 2 * np.dtype(xyz_type).itemsize,
+                                      1 + 3 * np.dtype(xyz_type).itemsize, 3 + 3 * np.dtype(xyz_type).itemsize],
+                          "itemsize": 3 + 3 * np.dtype(xyz_type).itemsize + np.dtype(t_type).itemsize + 2})
+    odo = orc.odometry(_sequence_options(orc, init_num_frames=4))
+    ode = eng.odometry(_sequence_options(eng, init_num_frames=4))
+    for s in seq_small[:6]:
+        rec = np.zeros(len(s["xyz"]), dtype=rec_dtype)
+        rec["x"], rec["y"], rec["z"] = s["xyz"][:, 0], s["xyz"][:, 1], s["xyz"][:, 2]
+        if t_type == "uint32":      # e.g. microseconds since the start of the sequence
+            rec["t"] = np.round(s["t"] * 1e6).astype(np.uint32)
+        else:
+            rec["t"] = s["t"]
+        xyz64 = np.stack([rec["x"], rec["y"], rec["z"]], axis=1).astype(np.float64)
+        t64 = rec["t"].astype(np.float64)
+        so = odo.RegisterFrame(xyz64, t64, s["frame_idx"])
+        se = ode.RegisterCloud(rec, s["frame_idx"])
+        assert so.success and se.success
+        assert (so.num_keypoints, so.number_of_residuals) == (se.num_keypoints, se.number_of_residuals)
+        dt, dr = frame_diff(so.frame, se.frame)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (dt, dr)
+    # egress into pcl::PointCloud<slam::XYZTPoint>-shaped records (float x, y, z, pad; double timestamp)
+    ref = ode.corrected_points()
+    out_dtype = np.dtype({"names": ["x", "y", "z", "t"], "formats": ["f4", "f4", "f4", "f8"], "offsets": [0, 4, 8, 16],
+                          "itemsize": 32})
+    out = np.zeros(len(ref), dtype=out_dtype)
+    n = ode.write_points(abi.POINTS_CORRECTED, out, world=True)
+    assert n == len(ref)
+    assert np.array_equal(np.stack([out["x"], out["y"], out["z"]], 1), ref["world"].astype(np.float32))
+    assert np.array_equal(out["t"], ref["timestamp"])

@@ -85,9 +85,17 @@ class MapOptions(_Struct):
     ]
 
 
+STRATEGY = {"NEAREST_NEIGHBOR_STRATEGY": 0, "DISTANCE_BASED_STRATEGY": 1}
+
+
 class StrategyOptions(_Struct):
     _fields_ = [("type", C.c_int32), ("max_num_neighbors", C.c_int32), ("min_num_neighbors", C.c_int32),
-                ("_pad0", C.c_int32)]
+                ("_pad0", C.c_int32), ("distance_max", C.c_double), ("radius_min", C.c_double),
+                ("radius_max", C.c_double), ("exponent", C.c_double)]
+
+    def __init__(self, type=0, max_num_neighbors=20, min_num_neighbors=8, _pad0=0, distance_max=60.0, radius_min=0.1,
+                 radius_max=2.0, exponent=1.0):
+        super().__init__(type, max_num_neighbors, min_num_neighbors, _pad0, distance_max, radius_min, radius_max, exponent)
 
 
 class MotionModelOptions(_Struct):

@@ -60,6 +60,8 @@ class Binding:
             "map_create": (C.c_int, [P(abi.MapOptions), C.c_int, P(vp)]),
             "map_destroy": (None, [vp]),
             "map_insert": (C.c_int, [vp, vp, sz, sz]),
+            "map_insert_from": (C.c_int, [vp, vp, sz, sz, vp]),
+            "map_radius_search": (C.c_int, [vp, vp, vp, sz, C.c_int, vp, vp, vp]),
             "map_remove_far": (C.c_int, [vp, P(dbl), dbl]),
             "map_num_points": (i64, [vp, C.c_int]),
             "map_num_voxels": (i64, [vp, C.c_int]),
@@ -198,9 +200,13 @@ class VoxelMap:
         except Exception:
             pass
 
-    def insert(self, xyz):                       # InsertPointCloud, map.h:153-254
+    def insert(self, xyz, origin=None):          # InsertPointCloud, map.h:153-254 (origin = frame_poses.front().tr)
         xyz = _as_f64_rows(xyz, 3)
-        self.b.check(self.b.fn("map_insert")(self.h, xyz.ctypes.data, 24, len(xyz)))
+        if origin is None:
+            self.b.check(self.b.fn("map_insert")(self.h, xyz.ctypes.data, 24, len(xyz)))
+        else:
+            o = (C.c_double * 3)(*[float(v) for v in origin])
+            self.b.check(self.b.fn("map_insert_from")(self.h, xyz.ctypes.data, 24, len(xyz), o))
 
     def remove_far(self, location, distance):    # RemoveElementsFarFromLocation, map.h:305-322
         loc = (C.c_double * 3)(*location)
@@ -227,6 +233,17 @@ class VoxelMap:
         cnt = np.zeros(len(q), dtype=np.int32)
         self.b.check(self.b.fn("map_compute_neighborhoods")(self.h, q.ctypes.data, len(q), max_num_neighbors,
                                                             pts.ctypes.data, cnt.ctypes.data))
+        return pts, cnt
+
+    def radius_search(self, queries, radiuses, max_num_neighbors=20, sensor_location=None):
+        """ComputeNeighborhoods(queries, radiuses, max_num_neighbors, true, sensor_location), map.h:434-447."""
+        q = _as_f64_rows(queries, 3)
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radiuses, dtype=np.float64), (len(q),)))
+        pts = np.zeros((len(q), max_num_neighbors, 3), dtype=np.float64)
+        cnt = np.zeros(len(q), dtype=np.int32)
+        loc = (C.c_double * 3)(*[float(v) for v in sensor_location]) if sensor_location is not None else None
+        self.b.check(self.b.fn("map_radius_search")(self.h, q.ctypes.data, r.ctypes.data, len(q), max_num_neighbors, loc,
+                                                    pts.ctypes.data, cnt.ctypes.data))
         return pts, cnt
 
     def clear(self):

@@ -164,6 +164,10 @@ void cticp_default_odometry_options(cticp_odometry_options *o) {
     o->neighborhood_strategy.type = 0;
     o->neighborhood_strategy.max_num_neighbors = 20;
     o->neighborhood_strategy.min_num_neighbors = 8;
+    o->neighborhood_strategy.distance_max = 60.;   // DistanceBasedStrategy::Options, neighborhood_strategy.h:113-119
+    o->neighborhood_strategy.radius_min = 0.1;
+    o->neighborhood_strategy.radius_max = 2.0;
+    o->neighborhood_strategy.exponent = 1.0;
     o->default_motion_model.model = CTICP_MM_CONSTANT_VELOCITY;
     o->default_motion_model.beta_location_consistency = 0.001;
     o->default_motion_model.beta_constant_velocity = 0.001;
@@ -463,7 +467,7 @@ int cticp_map_create(const cticp_map_options *options, int device, cticp_map **o
         m->device = device;
         m->owned = true;
         CAPI_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-        m->map = new DeviceMap(*options, m->stream);
+        m->map = new DeviceMap(*options, m->stream, options->select_valid_normals_direction != 0);
         m->icp = new IcpSolver(m->stream);
         CAPI_CUDA(cudaStreamSynchronize(m->stream));
         *out = m;
@@ -480,9 +484,12 @@ void cticp_map_destroy(cticp_map *m) {
     delete m;
 }
 int cticp_map_insert(cticp_map *m, const double *xyz, size_t stride_bytes, size_t n) {
+    return cticp_map_insert_from(m, xyz, stride_bytes, n, nullptr);
+}
+int cticp_map_insert_from(cticp_map *m, const double *xyz, size_t stride_bytes, size_t n, const double origin[3]) {
     return Guard([&] {
         CAPI_CUDA(cudaSetDevice(m->device));
-        m->map->InsertHost(xyz, stride_bytes, n);
+        m->map->InsertHost(xyz, stride_bytes, n, origin ? V3{origin[0], origin[1], origin[2]} : V3{0, 0, 0});
         m->map->SyncCounters();
         m->map->MaintainTables();
         return (int) CTICP_OK;
@@ -550,6 +557,30 @@ int cticp_map_compute_neighborhoods(cticp_map *m, const double *queries_xyz, siz
         CAPI_CUDA(cudaMemcpyAsync(out_counts, d_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, m->stream));
         CAPI_CUDA(cudaStreamSynchronize(m->stream));
         cudaFree(d_q); cudaFree(d_out); cudaFree(d_cnt);
+        return (int) CTICP_OK;
+    });
+}
+int cticp_map_radius_search(cticp_map *m, const double *queries_xyz, const double *radiuses, size_t n,
+                            int max_num_neighbors, const double *sensor_location, double *out_points,
+                            int32_t *out_counts) {
+    return Guard([&] {
+        CAPI_CUDA(cudaSetDevice(m->device));
+        if (n == 0) return (int) CTICP_OK;
+        if (!queries_xyz || !radiuses || !out_points || !out_counts) throw std::invalid_argument("null argument");
+        double *d_q, *d_r, *d_out;
+        int *d_cnt;
+        CAPI_CUDA(cudaMalloc(&d_q, sizeof(double) * 3 * n));
+        CAPI_CUDA(cudaMalloc(&d_r, sizeof(double) * n));
+        CAPI_CUDA(cudaMalloc(&d_out, sizeof(double) * 3 * n * max_num_neighbors));
+        CAPI_CUDA(cudaMalloc(&d_cnt, sizeof(int) * n));
+        CAPI_CUDA(cudaMemcpyAsync(d_q, queries_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, m->stream));
+        CAPI_CUDA(cudaMemcpyAsync(d_r, radiuses, sizeof(double) * n, cudaMemcpyHostToDevice, m->stream));
+        CAPI_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 3 * n * max_num_neighbors, m->stream));
+        m->icp->RadiusSearch(*m->map, d_q, d_r, n, max_num_neighbors, sensor_location, d_out, d_cnt);
+        CAPI_CUDA(cudaMemcpyAsync(out_points, d_out, sizeof(double) * 3 * n * max_num_neighbors, cudaMemcpyDeviceToHost, m->stream));
+        CAPI_CUDA(cudaMemcpyAsync(out_counts, d_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, m->stream));
+        CAPI_CUDA(cudaStreamSynchronize(m->stream));
+        cudaFree(d_q); cudaFree(d_r); cudaFree(d_out); cudaFree(d_cnt);
         return (int) CTICP_OK;
     });
 }
@@ -634,7 +665,7 @@ int cticp_icp_register(cticp_map *m, const cticp_icp_options *options, const cti
         DeviceKeypoints D;
         IcpState S;
         UploadRegistrationInputs(m, keypoints, n, frame, previous_frame, motion_options, D, S);
-        cticp_strategy_options st{0, 20, 8, 0};
+        cticp_strategy_options st{0, 20, 8, 0, 60., 0.1, 2.0, 1.0};
         if (strategy) st = *strategy;
         switch (options->solver) {
             case CTICP_SOLVER_GN:

@@ -5,6 +5,7 @@
 //   RemoveElementsFarFromLocation             :305-322           (tests the voxel's FIRST stored point)
 //   NumPoints / GetMapPoints                  :345-376
 #include "device_map.h"
+#include "gather.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -30,6 +31,7 @@ __global__ void k_clear_level(MapLevel L) {
         L.slots[i].count = 0;
         L.slots[i]._pad = 0;
         L.head[i] = kNil;
+        if (L.normals) L.normals[4 * (size_t) i + 3] = 0.0;
     }
 }
 
@@ -82,9 +84,15 @@ constexpr int kInsertWarps = 4;
 constexpr int kMaxCand = 512;
 constexpr int kMaxB = 64;
 
+__device__ __forceinline__ double commit_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 __global__ void __launch_bounds__(kInsertWarps * 32)
 k_insert_commit(MapLevel L, MapCounters *ctr, const double *__restrict__ world, const int *__restrict__ next,
-                const uint32_t *__restrict__ touched) {
+                const uint32_t *__restrict__ touched, const double *__restrict__ frame_origins, int frame_ordinal) {
     __shared__ int s_cand[kInsertWarps][kMaxCand];
     __shared__ int s_sorted[kInsertWarps][kMaxCand];
     __shared__ float4 s_pts[kInsertWarps][kMaxB];
@@ -145,7 +153,7 @@ k_insert_commit(MapLevel L, MapCounters *ctr, const double *__restrict__ world, 
                 const bool reject = __any_sync(0xffffffffu, too_close);
                 if (!reject) {
                     if (lane == 0) {
-                        const float4 v = make_float4((float) lx, (float) ly, (float) lz, 0.f);
+                        const float4 v = make_float4((float) lx, (float) ly, (float) lz, (float) (frame_ordinal + 1));
                         s_pts[w][count] = v;
                         gpts[count] = v;
                     }
@@ -159,6 +167,38 @@ k_insert_commit(MapLevel L, MapCounters *ctr, const double *__restrict__ world, 
             L.slots[slot].count = (uint32_t) count;
             L.head[slot] = kNil;
             if (count > count0) atomicAdd(&ctr->num_points, (unsigned long long) (count - count0));
+        }
+        __syncwarp();
+        // map.h:211-235: a voxel that received a point and holds >= 5 gets the normal of ALL its points (V.col(2) of
+        // their covariance), copied to every point and oriented point by point against the begin position of the frame
+        // that point came from. The sign lives in the sign of the point's w.
+        if (L.normals && count > count0 && count >= 5) {
+            double sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+            for (int j = lane; j < count; j += 32) {
+                const float4 q = s_pts[w][j];
+                const double x = (double) q.x, y = (double) q.y, z = (double) q.z;   // relative to the voxel origin
+                sx += x; sy += y; sz += z;
+                sxx += x * x; sxy += x * y; sxz += x * z; syy += y * y; syz += y * z; szz += z * z;
+            }
+            const double inv = 1.0 / (double) count;
+            const double mx = commit_warp_sum(sx) * inv, my = commit_warp_sum(sy) * inv, mz = commit_warp_sum(sz) * inv;
+            const double cxx = commit_warp_sum(sxx) * inv - mx * mx, cxy = commit_warp_sum(sxy) * inv - mx * my,
+                         cxz = commit_warp_sum(sxz) * inv - mx * mz, cyy = commit_warp_sum(syy) * inv - my * my,
+                         cyz = commit_warp_sum(syz) * inv - my * mz, czz = commit_warp_sum(szz) * inv - mz * mz;
+            const Eig3 e = sym_eig3(cxx, cxy, cxz, cyy, cyz, czz);
+            if (lane == 0) {
+                double *nrm = L.normals + 4 * (size_t) slot;
+                nrm[0] = e.normal.x; nrm[1] = e.normal.y; nrm[2] = e.normal.z; nrm[3] = 1.0;
+            }
+            for (int j = lane; j < count; j += 32) {
+                float4 q = s_pts[w][j];
+                const int f = (int) fabsf(q.w) - 1;
+                const double px = ox + (double) q.x - frame_origins[3 * f], py = oy + (double) q.y - frame_origins[3 * f + 1],
+                             pz = oz + (double) q.z - frame_origins[3 * f + 2];
+                const bool flip = px * e.normal.x + py * e.normal.y + pz * e.normal.z > 0.0;
+                q.w = flip ? -fabsf(q.w) : fabsf(q.w);
+                gpts[j] = q;
+            }
         }
         __syncwarp();
     }
@@ -205,6 +245,8 @@ __global__ void k_rebuild(MapLevel src, MapLevel dst, MapCounters *ctr) {
         const uint32_t count = src.slots[s].count;
         dst.slots[h].count = count;
         for (uint32_t j = 0; j < count; ++j) dst.points[(size_t) h * dst.B + j] = src.points[(size_t) s * src.B + j];
+        if (src.normals && dst.normals)
+            for (int c = 0; c < 4; ++c) dst.normals[4 * (size_t) h + c] = src.normals[4 * (size_t) s + c];
     }
     (void) ctr;
 }
@@ -241,7 +283,8 @@ static uint32_t NextPow2(uint64_t v) {
     return (uint32_t) p;
 }
 
-DeviceMap::DeviceMap(const cticp_map_options &options, cudaStream_t stream) : options_(options), stream_(stream) {
+DeviceMap::DeviceMap(const cticp_map_options &options, cudaStream_t stream, bool with_normals)
+    : options_(options), stream_(stream), with_normals_(with_normals) {
     if (options.num_resolutions < 1 || options.num_resolutions > CTICP_MAX_RESOLUTIONS)
         throw std::invalid_argument("map_options.num_resolutions out of range");
     levels_.resize(options.num_resolutions);
@@ -267,6 +310,7 @@ DeviceMap::~DeviceMap() {
     cudaFree(d_next_);
     cudaFree(d_touched_);
     cudaFree(d_world_tmp_);
+    cudaFree(d_frame_origins_);
     cudaFreeHost(h_counters_);
 }
 
@@ -278,6 +322,8 @@ void DeviceMap::AllocLevel(MapLevel &L, uint32_t cap, const cticp_resolution_par
     CT_CUDA_CHECK(cudaMalloc(&L.slots, sizeof(MapSlot) * (size_t) cap));
     CT_CUDA_CHECK(cudaMalloc(&L.points, sizeof(float4) * (size_t) cap * L.B));
     CT_CUDA_CHECK(cudaMalloc(&L.head, sizeof(int) * (size_t) cap));
+    L.normals = nullptr;
+    if (with_normals_) CT_CUDA_CHECK(cudaMalloc(&L.normals, sizeof(double) * 4 * (size_t) cap));
     k_clear_level<<<592, 256, 0, stream_>>>(L);
     CT_CUDA_CHECK(cudaGetLastError());
 }
@@ -285,6 +331,8 @@ void DeviceMap::FreeLevel(MapLevel &L) {
     cudaFree(L.slots);
     cudaFree(L.points);
     cudaFree(L.head);
+    cudaFree(L.normals);
+    L.normals = nullptr;
     L.slots = nullptr;
     L.points = nullptr;
     L.head = nullptr;
@@ -301,9 +349,30 @@ void DeviceMap::EnsureScratch(size_t n_upper) {
     scratch_n_ = n;
 }
 
-void DeviceMap::InsertDevice(const double *d_world_xyz, const int *d_n, size_t n_upper) {
+void DeviceMap::InsertDevice(const double *d_world_xyz, const int *d_n, size_t n_upper, V3 origin) {
     if (n_upper == 0) return;
     EnsureScratch(n_upper);
+    // frame_id_to_frame[fidx].poses.front() (map.h:158-160): one begin position per inserted frame, never erased
+    if (frame_count_ >= (1u << 24) - 2) throw CapacityError("more than 2^24 frames inserted into one map");
+    if (with_normals_) {
+        if (frame_count_ >= frame_capacity_) {
+            const size_t cap = std::max<size_t>(4096, frame_capacity_ * 2);
+            double *fresh = nullptr;
+            CT_CUDA_CHECK(cudaMalloc(&fresh, sizeof(double) * 3 * cap));
+            if (frame_count_)
+                CT_CUDA_CHECK(cudaMemcpyAsync(fresh, d_frame_origins_, sizeof(double) * 3 * frame_count_,
+                                              cudaMemcpyDeviceToDevice, stream_));
+            CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            cudaFree(d_frame_origins_);
+            d_frame_origins_ = fresh;
+            frame_capacity_ = cap;
+        }
+        // 24 bytes by value through a kernel-free path: cudaMemcpyAsync from pageable memory copies the source before
+        // returning, so the stack variable may go out of scope
+        const double o[3] = {origin.x, origin.y, origin.z};
+        CT_CUDA_CHECK(cudaMemcpyAsync(d_frame_origins_ + 3 * frame_count_, o, sizeof(o), cudaMemcpyHostToDevice, stream_));
+    }
+    const int frame_ordinal = (int) frame_count_++;
     const int threads = 256;
     const int blocks = (int) std::min<size_t>((n_upper + threads - 1) / threads, 148 * 8);
     for (size_t i = 0; i < levels_.size(); ++i) {
@@ -311,14 +380,15 @@ void DeviceMap::InsertDevice(const double *d_world_xyz, const int *d_n, size_t n
         CT_CUDA_CHECK(cudaMemsetAsync(&ctr->num_touched, 0, sizeof(unsigned), stream_));
         k_insert_claim<<<blocks, threads, 0, stream_>>>(levels_[i], ctr, d_world_xyz, d_n, d_next_, d_touched_);
         const int cblocks = (int) std::min<size_t>((n_upper + kInsertWarps - 1) / kInsertWarps, 148 * 8);
-        k_insert_commit<<<cblocks, kInsertWarps * 32, 0, stream_>>>(levels_[i], ctr, d_world_xyz, d_next_, d_touched_);
+        k_insert_commit<<<cblocks, kInsertWarps * 32, 0, stream_>>>(levels_[i], ctr, d_world_xyz, d_next_, d_touched_,
+                                                                     d_frame_origins_, frame_ordinal);
         launches_ += 2;
     }
     CT_CUDA_CHECK(cudaGetLastError());
     dirty_ = true;
 }
 
-void DeviceMap::InsertHost(const double *xyz, size_t stride_bytes, size_t n) {
+void DeviceMap::InsertHost(const double *xyz, size_t stride_bytes, size_t n, V3 origin) {
     if (n == 0) return;
     std::vector<double> packed(3 * n);
     for (size_t i = 0; i < n; ++i) {
@@ -334,7 +404,7 @@ void DeviceMap::InsertHost(const double *xyz, size_t stride_bytes, size_t n) {
     CT_CUDA_CHECK(cudaMemcpyAsync(d_world_tmp_, packed.data(), sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream_));
     int ni = (int) n;
     CT_CUDA_CHECK(cudaMemcpyAsync(d_scalar_, &ni, sizeof(int), cudaMemcpyHostToDevice, stream_));
-    InsertDevice(d_world_tmp_, reinterpret_cast<int *>(d_scalar_), n);
+    InsertDevice(d_world_tmp_, reinterpret_cast<int *>(d_scalar_), n, origin);
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // `packed` / `ni` go out of scope
     CheckOverflow();
 }
@@ -352,6 +422,7 @@ void DeviceMap::Clear() {
     for (auto &L : levels_) k_clear_level<<<592, 256, 0, stream_>>>(L);
     CT_CUDA_CHECK(cudaMemsetAsync(d_counters_, 0, sizeof(MapCounters) * levels_.size(), stream_));
     CT_CUDA_CHECK(cudaGetLastError());
+    frame_count_ = 0;
     dirty_ = true;
 }
 

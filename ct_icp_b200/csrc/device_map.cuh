@@ -29,8 +29,11 @@ struct __align__(16) MapSlot {
 
 struct MapLevel {
     MapSlot *slots;       // [cap]
-    float4 *points;       // [cap * B]  xyz = offset from voxel origin, w = reserved
+    float4 *points;       // [cap * B]  xyz = offset from voxel origin, w = +-(source frame ordinal + 1): the sign says
+                          //            whether this point's copy of the voxel normal is flipped (map.h:222-226)
     int *head;            // [cap] insertion scratch: per-voxel candidate list head (kNil between inserts)
+    double *normals;      // [cap * 4] or nullptr: voxel normal (x, y, z) and 1.0 once computed (PointType::normal /
+                          //            is_normal_computed, map.h:211-235); only kept when a search may filter on it
     uint32_t cap_mask;    // cap - 1 (cap is a power of two)
     int B;                // max_num_points
     double res;           // resolution

@@ -19,15 +19,18 @@ struct CapacityError : std::runtime_error {
 
 class DeviceMap {
 public:
-    DeviceMap(const cticp_map_options &options, cudaStream_t stream);
+    // with_normals: maintain the per-voxel normals that RadiusSearchInPlace's sensor_location filter reads (map.h:482-490)
+    DeviceMap(const cticp_map_options &options, cudaStream_t stream, bool with_normals = false);
     ~DeviceMap();
     DeviceMap(const DeviceMap &) = delete;
     DeviceMap &operator=(const DeviceMap &) = delete;
 
     // InsertPointCloud (map.h:153-254): world points (fp64 xyz triples) already on the device, count on the device
-    void InsertDevice(const double *d_world_xyz, const int *d_n, size_t n_upper);
+    // `origin` = frame_poses.front().tr of the inserted frame (orients the normals, :222-226)
+    void InsertDevice(const double *d_world_xyz, const int *d_n, size_t n_upper, V3 origin = V3{0, 0, 0});
     // same from strided host memory (synchronous; used by the cticp_map_* test entry points)
-    void InsertHost(const double *xyz, size_t stride_bytes, size_t n);
+    void InsertHost(const double *xyz, size_t stride_bytes, size_t n, V3 origin = V3{0, 0, 0});
+    bool HasNormals() const { return with_normals_; }
     // RemoveElementsFarFromLocation (map.h:305-322)
     void RemoveFar(V3 location, double distance);
     void Clear();
@@ -73,6 +76,9 @@ private:
     size_t world_tmp_n_ = 0;
     bool dirty_ = true;
     bool readback_pending_ = false;
+    bool with_normals_ = false;
+    double *d_frame_origins_ = nullptr;   // [3 * frame_capacity_] begin position of every inserted frame
+    size_t frame_capacity_ = 0, frame_count_ = 0;
     int launches_ = 0;
     int rebuilds_ = 0;
 };

@@ -90,7 +90,10 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
         pool_ = std::make_unique<HostPool>(threads);
     }
     CT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    map_ = std::make_unique<DeviceMap>(options_.map_options, stream_);
+    // per-voxel normals are only read by the DistanceBasedStrategy's sensor-side filter (map.h:482-490)
+    const bool with_normals = options_.map_options.select_valid_normals_direction &&
+                              options_.neighborhood_strategy.type == CTICP_STRATEGY_DISTANCE_BASED;
+    map_ = std::make_unique<DeviceMap>(options_.map_options, stream_, with_normals);
     const size_t max_pts = options_.max_points_per_frame ? (size_t) options_.max_points_per_frame : (size_t) 524288;
     pipe_ = std::make_unique<FramePipeline>(max_pts, stream_);
     icp_ = std::make_unique<IcpSolver>(stream_);
@@ -597,7 +600,8 @@ void Engine::UpdateMap(Summary &s, int registered_fid) {
     const V3 location = trajectory_.back().end_pose.pose.t;
     map_->RemoveFar(location, options_.max_distance);
     if (add_points) {
-        map_->InsertDevice(pipe_->d_frame_world(), pipe_->d_count_frame(), pipe_->n());
+        // frame_poses = {begin_pose, end_pose} (odometry.cpp:949): the begin position orients the voxel normals
+        map_->InsertDevice(pipe_->d_frame_world(), pipe_->d_count_frame(), pipe_->n(), s.frame.begin_pose.pose.t);
         tracker_.skipped_frames = 0;
         tracker_.cum_orientation = 0;
         tracker_.cum_distance = 0;

@@ -146,8 +146,13 @@ __device__ __forceinline__ void knn_consume32(KnnStage *stage, int &fill, KnnEnt
     __syncwarp();
 }
 
+//
+// kFilter: RadiusSearchInPlace with a sensor_location (map.h:482-490): a stored point whose (oriented) normal faces away
+// from the sensor, (sensor - query) . normal < 0, is skipped. `to_sensor` = sensor_location - query.
+template <bool kFilter = false>
 __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int *stencil, const QueryCtx &ctx,
-                                               int lane, KnnStage *stage, KnnEntry &best, unsigned &stencil_points) {
+                                               int lane, KnnStage *stage, KnnEntry &best, unsigned &stencil_points,
+                                               V3 to_sensor = V3{0, 0, 0}) {
     const MapLevel &L = G.L;
     const int side = 2 * G.r + 1;
     const int nst = side * side * side;
@@ -165,6 +170,8 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int 
         int slot = 0;
         int cnt = 0;
         double ox = 0, oy = 0, oz = 0;   // my voxel's origin relative to the query (fp64)
+        double sdn = 0;                  // kFilter: to_sensor . voxel normal
+        int has_normal = 0;
         if (s < nst) {
             int dx, dy, dz;
             stencil_lookup(stencil, s, G.r, dx, dy, dz);
@@ -173,6 +180,13 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int 
             if (found >= 0) {
                 slot = found;
                 cnt = (int) c;
+                if (kFilter && L.normals && c > 0) {
+                    const double *nrm = L.normals + 4 * (size_t) found;
+                    if (nrm[3] != 0.0) {
+                        has_normal = 1;
+                        sdn = to_sensor.x * nrm[0] + to_sensor.y * nrm[1] + to_sensor.z * nrm[2];
+                    }
+                }
             }
             ox = (kx + dx) * L.res - q.x;
             oy = (ky + dy) * L.res - q.y;
@@ -227,7 +241,14 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int 
                     const int j = owner[u] >> 8;
                     const double rx = vx + (double) pv[u].x, ry = vy + (double) pv[u].y, rz = vz + (double) pv[u].z;
                     const double d2 = rx * rx + ry * ry + rz * rz;
-                    const bool in = valid && !(d2 > G.radius2);
+                    bool in = valid && !(d2 > G.radius2);
+                    if (kFilter) {
+                        const double vs = __shfl_sync(0xffffffffu, sdn, ol);
+                        const int vh = __shfl_sync(0xffffffffu, has_normal, ol);
+                        // this point's copy of the normal is -n when its w is negative
+                        const double scalar = signbit(pv[u].w) ? -vs : vs;
+                        if (vh && scalar < 0.0) in = false;
+                    }
                     const unsigned m = __ballot_sync(0xffffffffu, in);
                     if (in) {
                         KnnStage e;

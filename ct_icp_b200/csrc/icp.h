@@ -79,6 +79,8 @@ public:
     // neighbor lists for queries (fp64 xyz on device): out_points n*kmax*3 (farthest first), out_counts n
     void Neighborhoods(const DeviceMap &map, const double *d_queries, size_t n, int kmax, double *d_out_points,
                        int *d_out_counts);
+    void RadiusSearch(const DeviceMap &map, const double *d_queries, const double *d_radiuses, size_t n, int kmax,
+                      const double *sensor_location, double *d_out_points, int *d_out_counts);
 
     int launches() const { return launches_; }
     float gather_ms() const { return gather_ms_; }
@@ -107,6 +109,7 @@ private:
     void *d_lm_state_ = nullptr, *d_lm_stats_ = nullptr, *d_lm_blocks_ = nullptr;
     int *d_lm_sel_ = nullptr;
     void *d_lm_classes_ = nullptr;   // solver ROBUST: slam::NEIGHBORHOOD_TYPE per keypoint
+    void *d_lm_strategy_ = nullptr;  // DistanceBasedStrategy parameters + every map level
     size_t lm_capacity_ = 0;
     int launches_ = 0;
     float gather_ms_ = 0.f;

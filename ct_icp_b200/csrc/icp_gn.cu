@@ -492,6 +492,47 @@ k_neighborhoods(GatherConfig G, const double *__restrict__ queries, int n, doubl
     }
 }
 
+// ComputeNeighborhoods(queries, radiuses, max_num_neighbors, true, sensor_location), map.h:434-447: per-query radius →
+// per-query level and stencil; optional normal filter.
+struct RadiusSearchLevels {
+    int num_levels, filter;
+    V3 sensor;
+    MapLevel levels[CTICP_MAX_RESOLUTIONS];
+};
+__global__ void __launch_bounds__(kGatherWarps * 32)
+k_radius_search(const RadiusSearchLevels *__restrict__ R, int kmax, const double *__restrict__ queries,
+                const double *__restrict__ radiuses, int n, double *__restrict__ out_points, int *__restrict__ out_counts) {
+    __shared__ KnnStage s_stage[kGatherWarps][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = blockIdx.x * kGatherWarps + w; i < n; i += gridDim.x * kGatherWarps) {
+        const V3 q{queries[3 * i], queries[3 * i + 1], queries[3 * i + 2]};
+        const double radius = radiuses[i];
+        int it = 0;
+        while (it < R->num_levels && R->levels[it].res <= radius) ++it;
+        GatherConfig G;
+        G.L = R->levels[it > 0 ? it - 1 : 0];
+        G.r = (int) ceil(radius / G.L.res);
+        G.radius2 = radius * radius;
+        G.kmax = kmax;
+        const QueryCtx ctx = make_query(q, G.L.res, lane);
+        KnnEntry best;
+        unsigned spts;
+        int cnt;
+        if (R->filter)
+            cnt = warp_gather_knn<true>(G, nullptr, ctx, lane, s_stage[w], best, spts,
+                                        V3{R->sensor.x - q.x, R->sensor.y - q.y, R->sensor.z - q.z});
+        else
+            cnt = warp_gather_knn<false>(G, nullptr, ctx, lane, s_stage[w], best, spts);
+        if (lane == 0) out_counts[i] = cnt;
+        if (lane < cnt) {
+            const V3 rel = knn_rel_position(G, nullptr, ctx, best);
+            double *o = out_points + ((size_t) i * kmax + (cnt - 1 - lane)) * 3;   // farthest first
+            o[0] = q.x + rel.x; o[1] = q.y + rel.y; o[2] = q.z + rel.z;
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 IcpSolver::IcpSolver(cudaStream_t stream) : stream_(stream) {
     UploadPairTables();
@@ -650,6 +691,25 @@ void IcpSolver::Neighborhoods(const DeviceMap &map, const double *d_queries, siz
     k_neighborhoods<<<blocks, kGatherWarps * 32, 0, stream_>>>(G, d_queries, (int) n, d_out_points, d_out_counts);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
+}
+
+void IcpSolver::RadiusSearch(const DeviceMap &map, const double *d_queries, const double *d_radiuses, size_t n, int kmax,
+                             const double *sensor_location, double *d_out_points, int *d_out_counts) {
+    if (kmax > 32 || kmax < 1) throw std::invalid_argument("max_num_neighbors must be in [1, 32]");
+    RadiusSearchLevels R{};
+    R.num_levels = map.NumLevels();
+    R.filter = (sensor_location && map.Options().select_valid_normals_direction && map.HasNormals()) ? 1 : 0;
+    if (sensor_location) R.sensor = V3{sensor_location[0], sensor_location[1], sensor_location[2]};
+    for (int i = 0; i < R.num_levels; ++i) R.levels[i] = map.Level(i);
+    RadiusSearchLevels *d_R = nullptr;
+    CT_CUDA_CHECK(cudaMalloc(&d_R, sizeof(R)));
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_R, &R, sizeof(R), cudaMemcpyHostToDevice, stream_));
+    const int blocks = GatherBlocks(n, num_sms_);
+    k_radius_search<<<blocks, kGatherWarps * 32, 0, stream_>>>(d_R, kmax, d_queries, d_radiuses, (int) n, d_out_points, d_out_counts);
+    launches_ += 1;
+    CT_CUDA_CHECK(cudaGetLastError());
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    cudaFree(d_R);
 }
 
 }  // namespace cticp

@@ -71,15 +71,26 @@ struct LmState {
     double trace[256][13];   // x_cost, candidate_cost, model_cost_change, relative_decrease, radius, flag
 };
 
+// DistanceBasedStrategy (neighborhood_strategy.h:95-146): the search radius — hence the map level and the stencil — is
+// chosen per keypoint from its range, and the search filters on the per-voxel normals with sensor_location = the
+// current end translation (ct_icp.cpp:571 passes &end_t).
+struct DistanceStrategy {
+    int num_levels, filter;
+    double radius_min, radius_max, exponent;
+    MapLevel levels[CTICP_MAX_RESOLUTIONS];
+};
+
 // ---------------------------------------------------------------------------------------------------------------
+template <bool kDB>
 __global__ void __launch_bounds__(kLmWarps * 32)
-k_lm_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
-            const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned long long *stats) {
+k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
+            const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned long long *stats,
+            const DistanceStrategy *__restrict__ D) {
     __shared__ KnnStage s_stage[kLmWarps][64];
     __shared__ int s_stencil[kMaxStencil];
     if (st->done) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int *stencil = stencil_table_fill(s_stencil, G.r);
+    const int *stencil = kDB ? nullptr : stencil_table_fill(s_stencil, G0.r);
     __syncthreads();
     const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
     const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
@@ -92,10 +103,27 @@ k_lm_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, co
         const double alpha = (double) kraw.w;
         // transform_keypoints(), ct_icp.cpp:516-531
         const V3 p = ct_transform_c(qb, tb, qe, te, alpha, raw, sc);
+        GatherConfig G = G0;
+        if (kDB) {
+            // ComputeRadius (neighborhood_strategy.h:121-126) then SearchParamsFromRadiusSearch (map.h:416-432)
+            const double range = sqrt(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z);
+            const double a = pow(fmin(fabs(range), D->radius_max) / D->radius_max, D->exponent);
+            const double radius = a * D->radius_max + (1 - a) * D->radius_min;
+            int it = 0;
+            while (it < D->num_levels && D->levels[it].res <= radius) ++it;
+            const int idx = it > 0 ? it - 1 : 0;
+            G.L = D->levels[idx];
+            G.r = (int) ceil(radius / G.L.res);
+            G.radius2 = radius * radius;
+        }
         const QueryCtx ctx = make_query(p, G.L.res, lane);
         KnnEntry best;
         unsigned spts = 0;
-        const int n = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
+        int n;
+        if (kDB && D->filter)
+            n = warp_gather_knn<true>(G, stencil, ctx, lane, s_stage[w], best, spts, V3{te.x - p.x, te.y - p.y, te.z - p.z});
+        else
+            n = warp_gather_knn<false>(G, stencil, ctx, lane, s_stage[w], best, spts);
         n_kp += 1;
         n_pts += spts;
         ResidualBlock rb;
@@ -716,6 +744,7 @@ void IcpSolver::FreeLmBuffers() {
     cudaFree(d_lm_blocks_);
     cudaFree(d_lm_sel_);
     cudaFree(d_lm_classes_);
+    cudaFree(d_lm_strategy_);
 }
 
 void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt, const cticp_strategy_options &strategy,
@@ -783,6 +812,25 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
 
     k_lm_begin<<<1, 32, 0, stream_>>>(d_state, lm, stats);
     launches_ += 1;
+    // solver CERES consults the neighborhood strategy (ct_icp.cpp:571); ROBUST does not (:1235)
+    const bool distance_based = !robust && strategy.type == CTICP_STRATEGY_DISTANCE_BASED;
+    if (distance_based) {
+        if (!(strategy.radius_max > 0.0)) throw std::invalid_argument("DISTANCE_BASED_STRATEGY: radius_max must be > 0");
+        DistanceStrategy D{};
+        D.num_levels = map.NumLevels();
+        D.filter = map.Options().select_valid_normals_direction ? 1 : 0;
+        if (D.filter && !map.HasNormals())
+            throw std::invalid_argument("DISTANCE_BASED_STRATEGY with select_valid_normals_direction needs a map that keeps normals");
+        D.radius_min = strategy.radius_min;
+        D.radius_max = strategy.radius_max;
+        D.exponent = strategy.exponent;
+        for (int i = 0; i < D.num_levels; ++i) D.levels[i] = map.Level(i);
+        if (!d_lm_strategy_) CT_CUDA_CHECK(cudaMalloc(&d_lm_strategy_, sizeof(DistanceStrategy)));
+        CT_CUDA_CHECK(cudaMemcpyAsync(d_lm_strategy_, &D, sizeof(D), cudaMemcpyHostToDevice, stream_));
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // D lives on this stack frame
+    } else if (!robust && strategy.type != CTICP_STRATEGY_NEAREST_NEIGHBOR) {
+        throw std::invalid_argument("unknown neighborhood strategy type");
+    }
     auto *classes = static_cast<unsigned char *>(d_lm_classes_);
     if (robust) CT_CUDA_CHECK(cudaMemsetAsync(classes, 0, k_capacity, stream_));   // NEIGHBORHOOD_TYPE::NONE
     for (int it = 0; it < opt.num_iters_icp; ++it) {
@@ -791,8 +839,12 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
         if (robust)
             k_rb_gather<<<gather_blocks, kLmWarps * 32, 0, stream_>>>(G, P, d_keypoints, d_num_keypoints, d_state, blocks_buf,
                                                                      classes, stats);
+        else if (distance_based)
+            k_lm_gather<true><<<gather_blocks, kLmWarps * 32, 0, stream_>>>(G, P, d_keypoints, d_num_keypoints, d_state, blocks_buf,
+                                                                           stats, static_cast<const DistanceStrategy *>(d_lm_strategy_));
         else
-            k_lm_gather<<<gather_blocks, kLmWarps * 32, 0, stream_>>>(G, P, d_keypoints, d_num_keypoints, d_state, blocks_buf, stats);
+            k_lm_gather<false><<<gather_blocks, kLmWarps * 32, 0, stream_>>>(G, P, d_keypoints, d_num_keypoints, d_state, blocks_buf,
+                                                                            stats, nullptr);
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
         ++gather_launches_;
         k_lm_select<<<1, 1024, 0, stream_>>>(P, d_num_keypoints, blocks_buf, d_lm_sel_, d_state, lm, stats);

@@ -124,12 +124,21 @@ typedef struct cticp_map_options {
     uint64_t capacity_voxels;      /* slots per resolution (power of two is taken) */
 } cticp_map_options;
 
-/* ct_icp::INeighborStrategyOptions, include/ct_icp/neighborhood_strategy.h:37-55 */
+/* ct_icp::INeighborStrategyOptions + DefaultNearestNeighborStrategy::Options + DistanceBasedStrategy::Options,
+ * include/ct_icp/neighborhood_strategy.h:37-55, 60-85, 95-146. The strategy is consulted by solver CERES only
+ * (src/ct_icp/ct_icp.cpp:571); GN and ROBUST search with the map's default radius. */
+enum { CTICP_STRATEGY_NEAREST_NEIGHBOR = 0, CTICP_STRATEGY_DISTANCE_BASED = 1 };
 typedef struct cticp_strategy_options {
-    int32_t type;                  /* 0 = NEAREST_NEIGHBOR_STRATEGY (the only built one) */
+    int32_t type;                  /* CTICP_STRATEGY_* */
     int32_t max_num_neighbors;
     int32_t min_num_neighbors;
     int32_t _pad0;
+    /* DISTANCE_BASED_STRATEGY (:113-119): search radius grows with the keypoint's range; the map's per-point
+     * normals reject neighbors whose surface faces away from the sensor (map.h:482-490) */
+    double distance_max;
+    double radius_min;
+    double radius_max;
+    double exponent;
 } cticp_strategy_options;
 
 /* ct_icp::PreviousFrameMotionModel::Options, include/ct_icp/motion_model.h:42-58 */
@@ -407,6 +416,10 @@ int cticp_map_create(const cticp_map_options *options, int device, cticp_map **o
 void cticp_map_destroy(cticp_map *m);
 /* InsertPointCloud (world points, given order), include/ct_icp/map.h:153-254,261-293 */
 int cticp_map_insert(cticp_map *m, const double *xyz, size_t stride_bytes, size_t n);
+/* InsertPointCloud(pointcloud, frame_poses, ...) where the begin pose of the source frame matters: per-voxel normals
+ * are oriented towards `origin` = frame_poses.front().tr (include/ct_icp/map.h:211-235). cticp_map_insert is the same
+ * with origin = (0, 0, 0). */
+int cticp_map_insert_from(cticp_map *m, const double *xyz, size_t stride_bytes, size_t n, const double origin[3]);
 /* RemoveElementsFarFromLocation, include/ct_icp/map.h:305-322 */
 int cticp_map_remove_far(cticp_map *m, const double location[3], double distance);
 /* NumPoints(), include/ct_icp/map.h:345 (resolution 0) ; num points of any resolution with map_idx */
@@ -418,6 +431,13 @@ int64_t cticp_map_export(cticp_map *m, int map_idx, double *dst_xyz, int32_t *ds
  * out_points: n × max_num_neighbors × 3 (farthest first, like RadiusSearchInPlace :508-513), out_counts: n */
 int cticp_map_compute_neighborhoods(cticp_map *m, const double *queries_xyz, size_t n, int max_num_neighbors,
                                     double *out_points, int32_t *out_counts);
+/* ComputeNeighborhoods(queries, radiuses, max_num_neighbors, nearest_neighbors = true, sensor_location),
+ * include/ct_icp/map.h:434-447 → RadiusSearchInPlace :449-514: one radius per query (it selects the resolution and the
+ * stencil, :416-432); when sensor_location != NULL and the map's select_valid_normals_direction is set, stored points
+ * whose oriented normal faces away from the sensor are skipped (:482-490). Output layout as above. */
+int cticp_map_radius_search(cticp_map *m, const double *queries_xyz, const double *radiuses, size_t n,
+                            int max_num_neighbors, const double *sensor_location, double *out_points,
+                            int32_t *out_counts);
 /* ClearMap(), include/ct_icp/map.h:296 */
 int cticp_map_clear(cticp_map *m);
 

@@ -109,7 +109,7 @@ void orc_default_odometry_options(cticp_odometry_options *o) {
     orc_default_adaptive_options(&o->adaptive_options);
     orc_default_icp_options(&o->ct_icp_options);
     orc_default_map_options(&o->map_options);
-    o->neighborhood_strategy = {0, 20, 8, 0};
+    o->neighborhood_strategy = {0, 20, 8, 0, 60., 0.1, 2.0, 1.0};   // neighborhood_strategy.h:47-49,113-119
     o->default_motion_model.model = CTICP_MM_CONSTANT_VELOCITY;
     o->default_motion_model.beta_location_consistency = 0.001;
     o->default_motion_model.beta_constant_velocity = 0.001;
@@ -350,14 +350,17 @@ orc_map *orc_odometry_map(orc_odometry *h) {
     m->impl = h->impl->GetMapPointer();
     return m;
 }
-int orc_map_insert(orc_map *m, const double *xyz, size_t stride, size_t n) {
+int orc_map_insert_from(orc_map *m, const double *xyz, size_t stride, size_t n, const double origin[3]) {
     std::vector<Vec3> pts(n);
     for (size_t i = 0; i < n; ++i) {
         const double *p = StrideAt(xyz, stride, i);
         pts[i] = Vec3(p[0], p[1], p[2]);
     }
-    m->impl->InsertPoints(pts);
+    m->impl->InsertPoints(pts, origin ? Vec3(origin[0], origin[1], origin[2]) : Vec3());
     return CTICP_OK;
+}
+int orc_map_insert(orc_map *m, const double *xyz, size_t stride, size_t n) {
+    return orc_map_insert_from(m, xyz, stride, n, nullptr);
 }
 int orc_map_remove_far(orc_map *m, const double location[3], double distance) {
     m->impl->RemoveElementsFarFromLocation(Vec3(location[0], location[1], location[2]), distance);
@@ -389,6 +392,22 @@ int orc_map_compute_neighborhoods(orc_map *m, const double *q, size_t n, int max
     }
     return CTICP_OK;
 }
+int orc_map_radius_search(orc_map *m, const double *q, const double *radiuses, size_t n, int max_num_neighbors,
+                          const double *sensor_location, double *out_points, int32_t *out_counts) {
+    Vec3 sensor;
+    if (sensor_location) sensor = Vec3(sensor_location[0], sensor_location[1], sensor_location[2]);
+    for (size_t i = 0; i < n; ++i) {
+        Neighborhood nb;
+        m->impl->RadiusSearchInPlace(Vec3(q[3 * i], q[3 * i + 1], q[3 * i + 2]), nb, radiuses[i], max_num_neighbors, nullptr,
+                                     sensor_location ? &sensor : nullptr);
+        out_counts[i] = (int32_t) nb.points.size();
+        for (size_t j = 0; j < nb.points.size(); ++j) {
+            double *o = out_points + (i * max_num_neighbors + j) * 3;
+            o[0] = nb.points[j].x; o[1] = nb.points[j].y; o[2] = nb.points[j].z;
+        }
+    }
+    return CTICP_OK;
+}
 int orc_map_clear(orc_map *m) {
     m->impl->Clear();
     return CTICP_OK;
@@ -412,7 +431,7 @@ int orc_icp_register(orc_map *m, const cticp_icp_options *options, const cticp_s
         for (size_t i = 0; i < n; ++i) kpts[i] = WPointFromC(keypoints[i]);
         TrajectoryFrame f = FrameFromC(*frame);
         MotionModel mm = MakeMotionModel(previous_frame, motion_options);
-        cticp_strategy_options st = strategy ? *strategy : cticp_strategy_options{0, 20, 8, 0};
+        cticp_strategy_options st = strategy ? *strategy : cticp_strategy_options{0, 20, 8, 0, 60., 0.1, 2.0, 1.0};
         ICPSummary s = Register(*m->impl, *options, st, kpts, f, mm.present ? &mm : nullptr);
         for (size_t i = 0; i < n; ++i) keypoints[i] = WPointToC(kpts[i]);
         *frame = FrameToC(f);

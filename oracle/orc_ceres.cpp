@@ -696,8 +696,8 @@ ICPSummary DoRegisterCeres(const VoxelMap &map, const cticp_icp_options &options
             const WPoint3D &pt = kpts[k];
             auto &neighborhood = neighborhoods[k];
             size_t st = 0;
-            // DefaultNearestNeighborStrategy::ComputeNeighborhoodInPlace, neighborhood_strategy.h:77-83
-            map.ComputeNeighborhoodInPlace(pt.world, strategy.max_num_neighbors, neighborhood, &st);
+            // const_strategy->ComputeNeighborhoodInPlace(voxels_map, pt, neighborhoods[k], &end_t), :571
+            StrategyComputeNeighborhoodInPlace(strategy, map, pt.raw, pt.world, neighborhood, &frame.end_pose.pose.tr, &st);
             kp_iters++;
             stencil_sum += st;
             if ((int) neighborhood.points.size() < kMinNumNeighbors) continue;

@@ -212,6 +212,10 @@ class VoxelMap {
 public:
     struct Block {
         std::vector<Vec3> points;
+        // PointType::{normal, is_normal_computed (= is_normal_oriented here), frame_id}, map.h:545-554
+        std::vector<Vec3> normals;
+        std::vector<char> has_normal;
+        std::vector<size_t> frame_ids;
     };
     struct SearchParams {
         double radius = 0.5, voxel_resolution = 0;
@@ -223,16 +227,23 @@ public:
     const cticp_map_options &Options() const { return options_; }
 
     // InsertPointInVoxelMap, map.h:261-293
-    bool InsertPointInVoxelMap(const Vec3 &point, size_t map_index) {
+    bool InsertPointInVoxelMap(const Vec3 &point, size_t map_index, size_t frame_idx = 0, Voxel *out_voxel = nullptr) {
         const auto &rp = options_.resolutions[map_index];
         auto &hm = maps_[map_index];
         Voxel voxel = Voxel::Coordinates(point, rp.resolution);
+        if (out_voxel) *out_voxel = voxel;
+        auto push = [&](Block &blk) {
+            blk.points.push_back(point);
+            blk.normals.push_back(Vec3());
+            blk.has_normal.push_back(0);
+            blk.frame_ids.push_back(frame_idx);
+            hm.num_points++;
+        };
         auto it = hm.map.find(voxel);
         if (it == hm.map.end()) {
             auto &blk = hm.map[voxel];
             blk.points.reserve(rp.max_num_points);
-            blk.points.push_back(point);
-            hm.num_points++;
+            push(blk);
             return true;
         }
         auto &blk = it->second;
@@ -243,18 +254,39 @@ public:
                 if (sq < sq_dist_min) sq_dist_min = sq;
             }
             if (sq_dist_min > rp.min_distance_between_points * rp.min_distance_between_points) {
-                blk.points.push_back(point);
-                hm.num_points++;
+                push(blk);
                 return true;
             }
         }
         return false;
     }
-    // InsertPointCloud, map.h:153-254 (world points, sequential in the given order; per-voxel normals :211-235 are
-    // consumed only by the sensor_location filter which the GN / Default-strategy paths never enable → not kept)
-    void InsertPoints(const std::vector<Vec3> &world_points) {
+    // InsertPointCloud, map.h:153-254: world points, sequential in the given order; then every voxel that received a
+    // point and holds >= 5 gets ONE normal (V.col(2) of its points' covariance) copied to all its points and oriented,
+    // point by point, against the begin position of the frame that point came from (:211-235). `origin` is
+    // frame_poses.front().tr of the inserted frame.
+    void InsertPoints(const std::vector<Vec3> &world_points, const Vec3 &origin = Vec3()) {
+        const size_t fidx = frame_origins_.size();
+        frame_origins_.push_back(origin);
+        std::vector<std::set<Voxel>> touched(maps_.size());
         for (auto &p : world_points)
-            for (size_t m = 0; m < maps_.size(); ++m) InsertPointInVoxelMap(p, m);
+            for (size_t m = 0; m < maps_.size(); ++m) {
+                Voxel v;
+                if (InsertPointInVoxelMap(p, m, fidx, &v)) touched[m].insert(v);
+            }
+        for (size_t m = 0; m < maps_.size(); ++m)
+            for (auto &v : touched[m]) {
+                Block &blk = maps_[m].map[v];
+                if (blk.points.size() < 5) continue;
+                Neighborhood nb;
+                nb.points = blk.points;
+                nb.ComputeNeighborhood();
+                for (size_t i = 0; i < blk.points.size(); ++i) {
+                    Vec3 n = nb.description.normal;
+                    if ((blk.points[i] - frame_origins_[blk.frame_ids[i]]).dot(n) > 0.) n = n * -1.0;
+                    blk.normals[i] = n;
+                    blk.has_normal[i] = 1;
+                }
+            }
     }
     // RemoveElementsFarFromLocation, map.h:305-322 — tests the voxel's FIRST stored point
     void RemoveElementsFarFromLocation(const Vec3 &location, double distance) {
@@ -272,6 +304,7 @@ public:
     void Clear() {
         maps_.clear();
         maps_.resize(options_.num_resolutions);
+        frame_origins_.clear();
     }
     size_t NumPoints(size_t map_idx = 0) const { return maps_[map_idx].num_points; }   // map.h:345
     size_t NumVoxels(size_t map_idx = 0) const { return maps_[map_idx].map.size(); }
@@ -289,9 +322,10 @@ public:
         return params;
     }
 
-    // RadiusSearchInPlace, map.h:449-514 with sensor_location == nullptr (GN :762, Default strategy :77-83)
+    // RadiusSearchInPlace, map.h:449-514. sensor_location == nullptr on the GN / ROBUST / Default-strategy paths
+    // (:762, :1235, neighborhood_strategy.h:77-83); the DistanceBasedStrategy passes the current end translation.
     void RadiusSearchInPlace(const Vec3 &query, Neighborhood &nb, double radius, int max_num_neighbors,
-                             size_t *stencil_points = nullptr) const {
+                             size_t *stencil_points = nullptr, const Vec3 *sensor_location = nullptr) const {
         nb.points.resize(0);
         const SearchParams params = SearchParamsFromRadiusSearch(radius);
         const auto &hm = maps_[params.map_id].map;
@@ -313,6 +347,10 @@ public:
                     if (stencil_points) *stencil_points += blk.points.size();
                     for (size_t i = 0; i < blk.points.size(); ++i) {
                         const Vec3 &nbp = blk.points[i];
+                        if (options_.select_valid_normals_direction && sensor_location && blk.has_normal[i]) {   // :482-490
+                            const double scalar = (*sensor_location - query).dot(blk.normals[i]);
+                            if (scalar < 0.) continue;
+                        }
                         double distance = (nbp - query).norm();
                         if (distance > params.radius) continue;
                         if ((int) pq.size() == max_num_neighbors) {
@@ -355,7 +393,23 @@ private:
     };
     cticp_map_options options_;
     std::vector<HashMap> maps_;
+    std::vector<Vec3> frame_origins_;   // frame_id_to_frame[fidx].poses.front().tr (entries are never erased, :246-252)
 };
+
+// ANeighborhoodStrategy::ComputeNeighborhoodInPlace, neighborhood_strategy.h:77-83 (nearest) / :121-141 (distance based)
+inline bool StrategyComputeNeighborhoodInPlace(const cticp_strategy_options &st, const VoxelMap &map, const Vec3 &raw_point,
+                                               const Vec3 &world_point, Neighborhood &nb, const Vec3 *sensor_location,
+                                               size_t *stencil_points = nullptr) {
+    if (st.type == CTICP_STRATEGY_DISTANCE_BASED) {
+        // ComputeRadius (:121-126): the ratio is taken against radius_max (sic — the documentation says distance_max)
+        const double alpha = std::pow(std::min(std::abs(raw_point.norm()), st.radius_max) / st.radius_max, st.exponent);
+        const double radius = alpha * st.radius_max + (1 - alpha) * st.radius_min;
+        map.RadiusSearchInPlace(world_point, nb, radius, st.max_num_neighbors, stencil_points, sensor_location);
+        return true;
+    }
+    map.ComputeNeighborhoodInPlace(world_point, st.max_num_neighbors, nb, stencil_points);
+    return (int) nb.points.size() >= st.min_num_neighbors;
+}
 
 /* ------------------------------------------------------------------------------------------------------------ */
 inline Pose PoseFromC(const cticp_pose &c) {

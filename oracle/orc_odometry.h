@@ -442,7 +442,7 @@ private:
         if (add_points) {
             std::vector<Vec3> world(s.corrected_points.size());
             for (size_t i = 0; i < world.size(); ++i) world[i] = s.corrected_points[i].world;
-            map_->InsertPoints(world);
+            map_->InsertPoints(world, s.frame.BeginTr());   // frame_poses = {begin_pose, end_pose}, odometry.cpp:949
             tracker_.skipped_frames = 0;
             tracker_.cum_orientation = 0;
             tracker_.cum_distance = 0;

@@ -712,3 +712,80 @@ def test_register_cloud_records_match_oracle(orc, eng, seq_small, xyz_type, t_ty
     assert n == len(ref)
     assert np.array_equal(np.stack([out["x"], out["y"], out["z"]], 1), ref["world"].astype(np.float32))
     assert np.array_equal(out["t"], ref["timestamp"])
+
+
+# ---- DistanceBasedStrategy, per-voxel normals, sensor-side filter ---------------------------------------
+def _three_level_options(b, cap=1 << 16):
+    m = b.default_map_options()
+    m.num_resolutions = 3
+    for i, (res, md) in enumerate(((0.5, 0.05), (1.0, 0.1), (2.0, 0.2))):
+        m.resolutions[i].resolution = res
+        m.resolutions[i].max_num_points = 30
+        m.resolutions[i].min_distance_between_points = md
+    m.capacity_voxels = cap
+    m.select_valid_normals_direction = 1
+    return m
+
+
+def test_radius_search_per_query_radius_and_normal_filter(orc, eng):
+    """ComputeNeighborhoods(queries, radiuses, k, true, sensor_location) (map.h:434-447): the radius picks the level and
+    the stencil per query; with a sensor location, points of voxels whose oriented normal faces away are skipped.
+    Three frames inserted from three origins so that the per-point orientation of a shared voxel normal differs."""
+    seq = get_sequence("hdl64", 3)
+    mo, me = orc.voxel_map(_three_level_options(orc)), eng.voxel_map(_three_level_options(eng))
+    rng = np.random.default_rng(5)
+    for i, s in enumerate(seq):
+        world = s["xyz"][::7] + np.array([0.4 * i, 0.0, 0.0])
+        origin = np.array([0.4 * i, 0.1 * i, 0.0])
+        mo.insert(world, origin); me.insert(world, origin)
+    assert [mo.num_points(l) for l in range(3)] == [me.num_points(l) for l in range(3)]
+    q = seq[2]["xyz"][3::41][:1500]
+    q = q + rng.normal(scale=0.05, size=q.shape)
+    radiuses = rng.uniform(0.15, 2.4, len(q))
+    total_unfiltered = total_filtered = 0
+    for sensor in (None, (0.8, 0.2, 0.0), (30.0, -12.0, 4.0)):
+        po, co = mo.radius_search(q, radiuses, 20, sensor)
+        pe, ce = me.radius_search(q, radiuses, 20, sensor)
+        assert np.array_equal(co, ce), (sensor, int((co != ce).sum()))
+        assert np.abs(po - pe).max() < 1e-6          # fp32 storage quantum
+        if sensor is None:
+            total_unfiltered = int(co.sum())
+        else:
+            total_filtered = int(co.sum())
+            assert total_filtered < total_unfiltered   # the filter removes something
+    assert total_unfiltered > 10000
+
+
+def _distance_based(b):
+    st = abi.StrategyOptions(abi.STRATEGY["DISTANCE_BASED_STRATEGY"], 20, 8)
+    st.radius_min, st.radius_max, st.exponent, st.distance_max = 0.1, 1.2, 1.0, 60.0
+    return st
+
+
+def test_odometry_sequence_distance_based_strategy(orc, eng, seq_hdl64):
+    """driving_config.yaml with `neighborhood_strategy: DISTANCE_BASED_STRATEGY` (config.cpp:155-167) on a
+    two-resolution map: per-keypoint radius → level, normals maintained by the map update, sensor-side filter."""
+    seq = seq_hdl64[:14]
+    results = []
+    for b in (orc, eng):
+        o = driving_config(b)
+        m = b.default_map_options()
+        m.num_resolutions = 2
+        for i, (res, md) in enumerate(((0.6, 0.1), (1.2, 0.2))):
+            m.resolutions[i].resolution = res
+            m.resolutions[i].max_num_points = 30
+            m.resolutions[i].min_distance_between_points = md
+        m.select_valid_normals_direction = 1
+        o.map_options = m
+        o.neighborhood_strategy = _distance_based(b)
+        o.ct_icp_options.min_number_neighbors = 10
+        od = b.odometry(o)
+        results.append([(od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]), od.MapSize()) for s in seq])
+    worst = 0.0
+    for i, ((so, mo), (se, me)) in enumerate(zip(*results)):
+        assert so.success and se.success, i
+        assert (so.num_keypoints, so.number_of_residuals, mo) == (se.num_keypoints, se.number_of_residuals, me), i
+        dt, dr = frame_diff(so.frame, se.frame)
+        worst = max(worst, dt)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
+    print("DISTANCE_BASED_STRATEGY worst per-frame pose difference: %.3e m" % worst)

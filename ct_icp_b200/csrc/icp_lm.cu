@@ -62,7 +62,8 @@ struct LmState {
     double diagonal[12];
     double x_cost, minimum_cost, model_cost_change, radius, decrease_factor, x_norm, gradient_max_norm;
     int reuse_diagonal, iteration, done, step_is_successful, num_invalid, usable;
-    int num_residuals, num_valid;
+    int num_residuals, num_valid;   // this rank's share when the keypoints are sharded
+    int num_residuals_global;       // residual blocks in the problem (all ranks)
     // ICP-loop bookkeeping (ct_icp.cpp:650-672)
     double prev_qb[4], prev_qe[4], prev_tb[3], prev_te[3];
     int outer_iter;
@@ -97,7 +98,10 @@ k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, c
     const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
     const int K = *d_num_keypoints;
     unsigned long long n_kp = 0, n_pts = 0;
-    for (int kp = blockIdx.x * kLmWarps + w; kp < K; kp += gridDim.x * kLmWarps) {
+    // keypoint-sharded mode: this rank assembles the blocks of its contiguous chunk only
+    const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
+    const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+    for (int kp = kp_lo + blockIdx.x * kLmWarps + w; kp < kp_hi; kp += gridDim.x * kLmWarps) {
         const float4 kraw = __ldg(keypoints + kp);
         const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
         const double alpha = (double) kraw.w;
@@ -176,7 +180,10 @@ k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, co
     const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
     const int K = *d_num_keypoints;
     unsigned long long n_kp = 0, n_pts = 0;
-    for (int kp = blockIdx.x * kLmWarps + w; kp < K; kp += gridDim.x * kLmWarps) {
+    // keypoint-sharded mode: this rank assembles the blocks of its contiguous chunk only
+    const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
+    const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+    for (int kp = kp_lo + blockIdx.x * kLmWarps + w; kp < kp_hi; kp += gridDim.x * kLmWarps) {
         const float4 kraw = __ldg(keypoints + kp);
         const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
         const V3 p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, raw, sc);   // TransformKeyPoints, :1373-1393
@@ -253,9 +260,13 @@ k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, co
 }
 
 // GetProblem (ct_icp.cpp:409-424) + seeding of the LM state for this ICP iteration. One CTA.
+// Sharded: launched twice. mode 1 counts this rank's valid blocks into counts[rank] (the vector is then summed over the
+// ranks = all-gather); mode 0 selects with the global rank of each block = (valid blocks of lower ranks) + local rank,
+// so the union over ranks is exactly the first max_num_residuals valid blocks in keypoint order.
 __global__ void __launch_bounds__(1024)
-k_lm_select(LmParams P, const int *__restrict__ d_num_keypoints, const ResidualBlock *__restrict__ blocks,
-            int *__restrict__ sel_idx, IcpState *st, LmState *lm, const unsigned long long *stats) {
+k_lm_select(LmParams P, int mode, const int *__restrict__ d_num_keypoints, const ResidualBlock *__restrict__ blocks,
+            int *__restrict__ sel_idx, IcpState *st, LmState *lm, const unsigned long long *stats,
+            double *__restrict__ counts) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     if (st->done) return;
@@ -264,9 +275,20 @@ k_lm_select(LmParams P, const int *__restrict__ d_num_keypoints, const ResidualB
     if (tid == 0) s_carry = 0;
     __syncthreads();
     const int limit = P.max_num_residuals > 0 ? P.max_num_residuals : 0x7fffffff;
-    for (int base = 0; base < K; base += 1024) {
+    const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
+    const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+    int before = 0, total_valid = -1;   // valid blocks on lower ranks / on all ranks
+    if (P.shard_world > 1 && mode == 0) {
+        total_valid = 0;
+        for (int r = 0; r < P.shard_world; ++r) {
+            const int c = (int) (counts[r] + 0.5);
+            if (r < P.shard_rank) before += c;
+            total_valid += c;
+        }
+    }
+    for (int base = kp_lo; base < kp_hi; base += 1024) {
         const int k = base + tid;
-        const int v = (k < K) ? (blocks[k].valid != 0) : 0;
+        const int v = (k < kp_hi) ? (blocks[k].valid != 0) : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -287,16 +309,24 @@ k_lm_select(LmParams P, const int *__restrict__ d_num_keypoints, const ResidualB
         __syncthreads();
         const int carry = s_carry;
         const int rank = carry + (w > 0 ? s_warp[w - 1] : 0) + incl - v;
-        if (v && rank < limit) sel_idx[rank] = k;
+        if (mode == 0 && v && before + rank < limit) sel_idx[rank] = k;
         __syncthreads();
         if (tid == 1023) s_carry = carry + s_warp[31];
         __syncthreads();
     }
+    if (mode == 1) {
+        if (tid < P.shard_world) counts[tid] = (tid == P.shard_rank) ? (double) s_carry : 0.0;
+        return;
+    }
     if (tid == 0) {
         const int num_valid = s_carry;
-        const int R = num_valid < limit ? num_valid : limit;
+        if (total_valid < 0) total_valid = num_valid;
+        const int R = total_valid < limit ? total_valid : limit;                       // the whole problem
+        int R_local = limit - before;                                                   // this rank's share of it
+        R_local = R_local < 0 ? 0 : (R_local < num_valid ? R_local : num_valid);
         lm->num_valid = num_valid;
-        lm->num_residuals = R;
+        lm->num_residuals = R_local;
+        lm->num_residuals_global = R;
         st->n_used = R;
         st->stat_keypoint_iters = stats[0];
         st->stat_stencil_points = stats[1];
@@ -384,6 +414,15 @@ k_lm_eval(LmParams P, int which, const ResidualBlock *__restrict__ blocks, const
         for (int h = 0; h < kLmWarps * 2; ++h) s += s_acc[h][threadIdx.x];
         partials[(size_t) blockIdx.x * kAcc + threadIdx.x] = s;
     }
+}
+
+// sharded mode: fold this rank's evaluation partials into one accumulator row for the all-reduce
+__global__ void __launch_bounds__(128)
+k_lm_reduce(const double *__restrict__ partials, int nblocks, double *__restrict__ acc) {
+    if (threadIdx.x >= kAcc) return;
+    double s = 0;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t) b * kAcc + threadIdx.x];
+    acc[threadIdx.x] = s;
 }
 
 // ---- the minimizer ------------------------------------------------------------------------------------------
@@ -499,7 +538,7 @@ k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblock
     const double min_relative_decrease = 1e-3, function_tolerance = 1e-6, gradient_tolerance = 1e-10,
                  parameter_tolerance = 1e-8, min_radius = 1e-32, max_radius = 1e16, min_lm_diagonal = 1e-6,
                  max_lm_diagonal = 1e32;
-    const int R = lm->num_residuals;
+    const int R = lm->num_residuals_global;
 
     // unpack the evaluation: U = J^T J, gu = J^T r, cost (+ regularisers at the evaluated point)
     for (int e = lane; e < 78; e += 32) {
@@ -763,9 +802,7 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     // neighbor count: the strategy's for CERES (neighborhood_strategy.h:81), the ICP options' for ROBUST (:1235)
     const int kmax = robust ? opt.max_number_neighbors : strategy.max_num_neighbors;
     if (kmax > 32 || kmax < 1) throw std::invalid_argument("max_num_neighbors must be in [1, 32]");
-    if (nccl_comm) throw UnsupportedError("solver CERES: multi-GPU sharding is built for the GN solver only");
-    (void) shard_rank;
-    (void) shard_world;
+    const bool sharded = nccl_comm != nullptr && shard_world > 1;
     const double sum = std::abs(opt.weight_alpha) + std::abs(opt.weight_neighborhood);
     if (!(sum > 0.0)) throw std::invalid_argument("weight_alpha + weight_neighborhood <= 0");
     EnsureLmBuffers(k_capacity);
@@ -786,8 +823,9 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     P.threshold_translation_norm = opt.threshold_translation_norm;
     P.loss = make_loss(opt.loss_function, opt.ls_sigma, opt.ls_tolerant_min_threshold);
     P.ls_max_num_iters = opt.ls_max_num_iters;
-    P.shard_rank = 0;
-    P.shard_world = 1;
+    P.shard_rank = sharded ? shard_rank : 0;
+    P.shard_world = sharded ? shard_world : 1;
+    if (sharded && shard_world > kAcc) throw std::invalid_argument("sharding: world size above 96");
     P.robust = robust ? 1 : 0;
     P.use_lines = opt.use_lines;
     P.use_barycenter = opt.use_barycenter;
@@ -847,15 +885,30 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
                                                                             stats, nullptr);
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
         ++gather_launches_;
-        k_lm_select<<<1, 1024, 0, stream_>>>(P, d_num_keypoints, blocks_buf, d_lm_sel_, d_state, lm, stats);
-        k_lm_eval<<<eval_blocks, kLmWarps * 32, 0, stream_>>>(P, 0, blocks_buf, d_lm_sel_, d_state, lm, d_partials_);
-        k_lm_step<<<1, 128, 0, stream_>>>(P, 0, d_partials_, eval_blocks, d_state, lm);
-        launches_ += 4;
-        for (int ls = 0; ls < opt.ls_max_num_iters; ++ls) {
-            k_lm_eval<<<eval_blocks, kLmWarps * 32, 0, stream_>>>(P, 1, blocks_buf, d_lm_sel_, d_state, lm, d_partials_);
-            k_lm_step<<<1, 128, 0, stream_>>>(P, 1, d_partials_, eval_blocks, d_state, lm);
+        // One evaluation + minimizer step. Sharded: every rank evaluates its share of the residual blocks, the 96-double
+        // accumulators are summed over the ranks (ncclAllReduce, bit-identical result everywhere) and every rank takes
+        // the same step — the exchange of SURVEY §8e, once per LM evaluation.
+        auto eval_and_step = [&](int phase) {
+            k_lm_eval<<<eval_blocks, kLmWarps * 32, 0, stream_>>>(P, phase, blocks_buf, d_lm_sel_, d_state, lm, d_partials_);
+            if (sharded) {
+                k_lm_reduce<<<1, 128, 0, stream_>>>(d_partials_, eval_blocks, d_acc_);
+                AllReduceAccumulator(nccl_comm);
+                k_lm_step<<<1, 128, 0, stream_>>>(P, phase, d_acc_, 1, d_state, lm);
+                launches_ += 1;
+            } else {
+                k_lm_step<<<1, 128, 0, stream_>>>(P, phase, d_partials_, eval_blocks, d_state, lm);
+            }
             launches_ += 2;
+        };
+        if (sharded) {   // all-gather of the per-rank valid counts (as a sum of one-hot vectors)
+            k_lm_select<<<1, 1024, 0, stream_>>>(P, 1, d_num_keypoints, blocks_buf, d_lm_sel_, d_state, lm, stats, d_acc_);
+            AllReduceAccumulator(nccl_comm);
+            launches_ += 1;
         }
+        k_lm_select<<<1, 1024, 0, stream_>>>(P, 0, d_num_keypoints, blocks_buf, d_lm_sel_, d_state, lm, stats, d_acc_);
+        launches_ += 2;
+        eval_and_step(0);
+        for (int ls = 0; ls < opt.ls_max_num_iters; ++ls) eval_and_step(1);
         k_lm_finish<<<1, 32, 0, stream_>>>(P, d_state, lm, it);
         launches_ += 1;
     }

@@ -29,3 +29,15 @@ def unpack_normal_equations(acc):
     A[iu] = acc[:78]
     A = A + A.T - np.diag(np.diag(A))
     return A, np.array(acc[78:90]), int(round(acc[90]))
+
+
+def prefix_shares(valid_counts, rank, max_num_residuals):
+    """Solvers CERES / ROBUST keep the first `max_num_residuals` valid residual blocks in keypoint order
+    (GetProblem, src/ct_icp/ct_icp.cpp:409-424). With contiguous keypoint shards that prefix is split as computed by
+    k_lm_select: `valid_counts[r]` = valid blocks on rank r (all-gathered as a sum of one-hot vectors);
+    returns (blocks of lower ranks, this rank's share, blocks in the whole problem)."""
+    limit = max_num_residuals if max_num_residuals > 0 else 0x7FFFFFFF
+    before = int(sum(valid_counts[:rank]))
+    total = int(sum(valid_counts))
+    share = min(max(limit - before, 0), int(valid_counts[rank]))
+    return before, share, min(total, limit)

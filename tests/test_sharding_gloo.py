@@ -81,3 +81,39 @@ def test_allreduce_of_shards_equals_unsharded(orc, tmp_path):
     assert n == n_full
     assert np.abs(A - A_full).max() < 1e-9 * np.abs(A_full).max()
     assert np.abs(b - b_full).max() < 1e-9 * max(np.abs(b_full).max(), 1e-6)
+
+
+def _prefix_worker(rank, world, port, out, limit):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    from ct_icp_b200.sharding import prefix_shares
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    valid = np.random.default_rng(11).random(1001) < 0.6            # the same flags on every rank
+    lo, hi = shard_bounds(len(valid), rank, world)
+    one_hot = torch.zeros(world, dtype=torch.float64)
+    one_hot[rank] = float(valid[lo:hi].sum())
+    dist.all_reduce(one_hot, op=dist.ReduceOp.SUM)                   # = all-gather of the per-rank counts
+    before, share, total = prefix_shares(one_hot.numpy(), rank, limit)
+    mine = (lo + np.flatnonzero(valid[lo:hi]))[:share]               # this rank's first `share` valid keypoints
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (mine.tolist(), total))
+    if rank == 0:
+        np.save(out, np.array(sorted(sum((g[0] for g in gathered), [])) + [gathered[0][1]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("limit", [-1, 300, 450, 5000])
+def test_sharded_residual_prefix_is_the_global_prefix(tmp_path, limit):
+    """max_num_residuals is a PREFIX rule (ct_icp.cpp:409-424): the union of the per-rank shares must be exactly the
+    first `limit` valid keypoints, whichever rank they live on (k_lm_select mode 0/1)."""
+    out = str(tmp_path / "sel.npy")
+    mp.spawn(_prefix_worker, args=(2, _free_port(), out, limit), nprocs=2, join=True)
+    got = np.load(out)
+    valid = np.random.default_rng(11).random(1001) < 0.6
+    want = np.flatnonzero(valid)[: (limit if limit > 0 else None)]
+    assert got[-1] == len(want)
+    assert np.array_equal(got[:-1], want)

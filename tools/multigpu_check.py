@@ -1,5 +1,6 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU): keypoint-sharded registration with one NCCL
-all-reduce per Gauss-Newton iteration must reproduce the single-GPU poses and be identical on every rank.
+all-reduce per Gauss-Newton iteration (GN) / per LM evaluation (CERES, ROBUST) must reproduce the single-GPU poses and
+be identical on every rank.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/multigpu_check.py
@@ -26,8 +27,23 @@ frames = int(os.environ.get("CTICP_CHECK_FRAMES", "24"))
 seq = syn.make_sequence(frames, syn.HDL64, seed=1234)
 
 
-def run(sharded):
-    od = eng.odometry(bench.make_options(eng), local_rank)
+def options_for(solver):
+    from ct_icp_b200 import _abi as abi
+    if solver == "GN":
+        bench._WORKLOAD = "kitti64_gn"
+        return bench.make_options(eng)
+    bench._WORKLOAD = "kitti64_ceres"           # driving_config.yaml: 5 x 5 LM iterations, 900-residual prefix
+    o = bench.make_options(eng)
+    if solver == "ROBUST":                      # regression_robust_config_short_drive.yaml
+        c = o.ct_icp_options
+        c.solver = abi.SOLVER["ROBUST"]
+        c.max_num_residuals, c.min_number_neighbors, c.ls_max_num_iters = 1000, 8, 8
+        c.threshold_linearity, c.threshold_planarity, c.outlier_distance, c.use_barycenter = 0.9, 0.8, 0.8, 1
+    return o
+
+
+def run(sharded, solver):
+    od = eng.odometry(options_for(solver), local_rank)
     if sharded:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -46,17 +62,21 @@ def run(sharded):
     return np.array(poses)
 
 
-single = run(False)
-sharded = run(True)
-t = torch.from_numpy(sharded).cuda()
-gathered = [torch.zeros_like(t) for _ in range(world)]
-dist.all_gather(gathered, t)
+ok = True
+for solver in os.environ.get("CTICP_CHECK_SOLVERS", "GN,CERES,ROBUST").split(","):
+    single = run(False, solver)
+    sharded = run(True, solver)
+    t = torch.from_numpy(sharded).cuda()
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    if rank == 0:
+        across = max(float((g - gathered[0]).abs().max()) for g in gathered)
+        vs_single = float(np.abs(sharded - single).max())
+        print("MULTIGPU %s world=%d frames=%d max|sharded - single|=%.3e max|rank_i - rank_0|=%.3e"
+              % (solver, world, frames, vs_single, across))
+        ok = ok and across == 0.0 and vs_single < (1e-7 if solver == "GN" else 1e-6)
 if rank == 0:
-    across = max(float((g - gathered[0]).abs().max()) for g in gathered)
-    vs_single = float(np.abs(sharded - single).max())
-    print("MULTIGPU world=%d frames=%d max|sharded - single|=%.3e max|rank_i - rank_0|=%.3e" % (world, frames, vs_single, across))
-    assert across == 0.0, "ranks diverged"
-    assert vs_single < 1e-7
+    assert ok, "sharded registration diverged"
     print("MULTIGPU OK")
 dist.barrier()
 dist.destroy_process_group()

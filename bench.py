@@ -97,54 +97,92 @@ def make_options(b):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+
+    In-process NVML (pynvml) from a daemon thread every 100 ms; `nvidia-smi -lms` is the fallback. (A separate
+    nvidia-smi process polling every 50 ms was measured to stretch the HOST-timed end-to-end steps — its queries
+    contend with this process's driver calls — so the sampler is kept as light as the recipe allows.)"""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index=0):
-        self.rows = []
-        self.proc = None
         self.gpu_index = gpu_index
+        self.sm, self.smax, self.reasons = [], [], set()
+        self.mode = os.environ.get("CTICP_BENCH_CLOCKS", "nvml")
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.proc = None
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                for name, mask in self.REASONS.items():
+                    if bits & mask:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def _smi_loop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                self.sm.append(float(f[0]))
+                self.smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def start(self):
+        if self.mode == "nvml":
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = self.gpu_index
+                if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                    idx = int(vis.split(",")[self.gpu_index])
+                handle = nv.nvmlDeviceGetHandleByIndex(idx)
+                self.smax.append(float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)))
+                self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.mode = "smi"
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0]))
-                smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.smax) if self.smax else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "sampler": self.mode}
 
 
 def run_oracle(seq, preroll, warmup, steps):
@@ -217,6 +255,8 @@ def main():
         npts = float(np.mean([len(s["xyz"]) for s in seq]))
         v, times, _ = run_oracle(seq, args.preroll, W, K)
         ms = float(np.mean(times))
+        from oracle_lib import oracle as _orc
+        ref_threads = int(make_options(_orc()).ct_icp_options.ls_num_threads)
         line = {
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
             "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -224,10 +264,12 @@ def main():
             "config": {"workload": WORKLOAD, "points_per_scan": npts, "preroll_frames": args.preroll,
                        "note": "CPU restatement (oracle/) of the reference's RegisterFrame; the reference cannot be "
                                "built offline (Eigen/Ceres/glog/yaml-cpp/robin_map absent)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "%d consecutive steady-state frames after %d untimed frames; GN per-keypoint "
-                                       "loop serial on 1 core like src/ct_icp/ct_icp.cpp:753, transforms OpenMP "
-                                       "(%d host cores available)" % (K, args.preroll + W, cores)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref_threads, "kind": "port",
+                             "sample": "%d consecutive steady-state frames after %d untimed frames; threading as in the "
+                                       "reference: GN per-keypoint loop serial (src/ct_icp/ct_icp.cpp:753), point "
+                                       "transforms (and the CERES/ROBUST residual assembly) on ls_num_threads = %d OpenMP "
+                                       "threads (odometry.cpp:469,480; ct_icp.cpp:561); %d host CPUs on this box"
+                                       % (K, args.preroll + W, ref_threads, cores)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -249,6 +291,8 @@ def main():
     npts = float(np.mean([len(s["xyz"]) for s in seq]))
     n_timed_begin = args.preroll + W
 
+    shard_modes = []
+
     def make_odometry():
         od = eng.odometry(make_options(eng), device)
         if world > 1:
@@ -260,6 +304,7 @@ def main():
                 uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
             dist.broadcast(uid, 0)
             od.enable_sharding(bytes(uid.cpu().numpy().tobytes()), rank, world)
+            shard_modes.append(od.sharding_mode())
         return od
 
     def barrier():
@@ -359,10 +404,13 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, times, _ = run_oracle(seq, args.preroll, W, K)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": "the same %d timed frames (after %d untimed), CPU oracle restating the reference's GN "
-                                  "path: per-keypoint loop serial on 1 core like src/ct_icp/ct_icp.cpp:753 "
-                                  "(%d host cores on this box)" % (K, n_timed_begin, cores),
+        from oracle_lib import oracle as _orc
+        ref_threads = int(make_options(_orc()).ct_icp_options.ls_num_threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": ref_threads, "kind": "port",
+                        "sample": "the same %d timed frames (after %d untimed), CPU oracle restating the reference's "
+                                  "RegisterFrame with the reference's threading: GN per-keypoint loop serial "
+                                  "(src/ct_icp/ct_icp.cpp:753), point transforms on ls_num_threads = %d OpenMP threads "
+                                  "(odometry.cpp:469,480); %d host CPUs on this box" % (K, n_timed_begin, ref_threads, cores),
                         "ms_per_step": float(np.mean(times))}
 
     if rank == 0:
@@ -373,9 +421,12 @@ def main():
             "config": {"workload": WORKLOAD, "points_per_scan": npts, "frame_points": f_sum / K,
                        "keypoints": kp_sum / K, "icp_iters_per_step": iters_sum / K, "preroll_frames": args.preroll,
                        "l2": "flushed between steps (256 MiB memset, untimed)",
-                       "parallelism": "single GPU" if world == 1 else "keypoints sharded x%d, NCCL all-reduce of JTJ/JTr per iteration" % world,
+                       "parallelism": "single GPU" if world == 1 else "keypoints sharded x%d, JTJ/JTr summed over ranks once per iteration: %s" % (
+                           world, "inside the persistent GN kernel over NVLink peer mailboxes (one launch per frame)"
+                           if shard_modes and min(shard_modes) == 2 else "ncclAllReduce (peer mapping unavailable)"),
                        "storage": "fp32 voxel-local map points / keypoints, fp64 arithmetic"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_total / K, "h2d_bytes_per_step": h2d / K,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_total / K, "ms_per_step_median": float(np.median(e2e_ms)),
+                    "ms_per_step_max": float(np.max(e2e_ms)), "h2d_bytes_per_step": h2d / K,
                     "d2h_bytes_per_step": d2h / K, "timing": "wall clock per step incl. host packing and the map-update tail"},
             "gpu_launches": launches,
             "clocks": clock_info,

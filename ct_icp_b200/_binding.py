@@ -93,6 +93,7 @@ class Binding:
             "odometry_flush_l2": (C.c_int, [vp, sz]),
             "odometry_set_gather_timing": (C.c_int, [vp, C.c_int]),
             "odometry_enable_sharding": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+            "odometry_sharding_mode": (C.c_int, [vp]),
             # oracle only (KAT taps)
             "odometry_last_counters": (None, [vp, P(u64), P(u64)]),
             "neighborhood_describe": (C.c_int, [vp, sz, vp, P(dbl), P(dbl), P(dbl), vp]),
@@ -430,3 +431,7 @@ class Odometry:
     def enable_sharding(self, unique_id_bytes, rank, world):
         buf = (C.c_char * 128).from_buffer_copy(unique_id_bytes)
         self.b.check(self.b.fn("odometry_enable_sharding")(self.h, buf, rank, world))
+
+    def sharding_mode(self):
+        """0 = single GPU, 1 = NCCL all-reduce per exchange, 2 = in-kernel exchange over NVLink peer mailboxes."""
+        return self.b.fn("odometry_sharding_mode")(self.h)

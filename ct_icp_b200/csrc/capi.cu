@@ -457,6 +457,7 @@ int cticp_odometry_enable_sharding(cticp_odometry *h, const void *unique_id_128_
         return (int) CTICP_OK;
     });
 }
+int cticp_odometry_sharding_mode(cticp_odometry *h) { return h->engine->ShardingMode(); }
 
 /* ---- Map ----------------------------------------------------------------------------------------------------- */
 int cticp_map_create(const cticp_map_options *options, int device, cticp_map **out) {

@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -135,6 +136,8 @@ void Engine::Reset() {   // odometry.cpp:956-965
     last_num_keypoints_ = 0;   // grid-size hint: keeps a reset run bit-identical to a fresh one
     last_all_world_valid_ = last_kp_world_valid_ = false;
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    tail_event_valid_ = false;
+    staging_in_flight_ = false;
 }
 
 int64_t Engine::MapSize() {
@@ -179,8 +182,6 @@ void Engine::InitializeMotion(const FrameInfo &info, const cticp_frame *initial_
 
 // InitializeFrame, odometry.cpp:333-382 — host part: pack (x, y, z, alpha) into pinned memory; device part:
 // shuffle / sub_sample_frame / timestamp override / shuffle.
-void Engine::IngestAndSubSample(const ScanView &scan, const FrameInfo &info) { IngestImpl(scan, info, -1); }
-
 void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t staged_slot) {
     const size_t n = scan.n;
     const int k = info.registered_fid;
@@ -188,21 +189,15 @@ void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t sta
     const double bts = tr.begin_pose.dest_timestamp, ets = tr.end_pose.dest_timestamp;
     // TPose::InterpolatePose CHECK (types.h:456): begin <= t <= end for every timestamp that gets interpolated
     const double t_lo = (k <= 1) ? info.end_timestamp : info.begin_timestamp, t_hi = info.end_timestamp;
-    if (!(bts <= t_lo && t_hi <= ets))
+    if (!(bts <= t_lo && t_hi <= ets)) {
+        cudaStreamSynchronize(stream_);   // the scan's H2D copy may be in flight: leave the staging buffer quiescent
+        staging_in_flight_ = false;
         throw TimestampError("The timestamp cannot be interpolated between the two poses");
+    }
     if (n > pipe_->MaxPoints()) throw CapacityError("scan has more points than max_points_per_frame");
 
-    if (staged_slot >= 0) {
-        pipe_->UploadFromDevice(staged_[staged_slot].d_points, n);   // already packed, already in HBM
-    } else {
-        auto tp = hclock::now();
-        PackScan(scan, bts, ets, pipe_->Staging());
-        const double t_pack = ms_since(tp);
-        if (getenv("CTICP_DEBUG_TIMERS")) cudaEventRecord(ev_[4], stream_);
-        pipe_->Upload(n);
-        if (getenv("CTICP_DEBUG_TIMERS")) cudaEventRecord(ev_[5], stream_);
-        if (getenv("CTICP_DEBUG_TIMERS")) fprintf(stderr, "[cticp] host pack %.3f ms, upload enqueue %.3f ms\n", t_pack, ms_since(tp) - t_pack);
-    }
+    // host buffers were packed and their H2D copy enqueued by PackAndUpload (RegisterCommon) before the pose pair existed
+    if (staged_slot >= 0) pipe_->UploadFromDevice(staged_[staged_slot].d_points, n);   // already packed, already in HBM
     timing_.h2d_bytes += pipe_->h2d_bytes();
     const double sample_size = k < options_.init_num_frames ? options_.init_voxel_size : options_.voxel_size;
     // frames 0 and 1: every timestamp := end_timestamp (odometry.cpp:355-359)
@@ -228,42 +223,43 @@ HostPool::~HostPool() {
 void HostPool::Worker(int id) {
     uint64_t seen = 0;
     while (true) {
-        const std::function<void(size_t, size_t, int)> *fn;
-        size_t n;
+        const std::function<void(int, int)> *fn;
         {
             std::unique_lock<std::mutex> lk(mu_);
             cv_start_.wait(lk, [&] { return generation_ != seen; });
             seen = generation_;
             if (stop_) return;
             fn = fn_;
-            n = n_;
         }
-        const int parts = size();
-        const size_t b = n * id / parts, e = n * (id + 1) / parts;
-        if (e > b) (*fn)(b, e, id);
+        (*fn)(id, size());
         {
             std::lock_guard<std::mutex> lk(mu_);
             if (--pending_ == 0) cv_done_.notify_one();
         }
     }
 }
-void HostPool::ParallelFor(size_t n, const std::function<void(size_t, size_t, int)> &fn) {
-    const int parts = size();
-    if (parts == 1 || n < 16384) {
-        fn(0, n, 0);
+void HostPool::ParallelRegion(size_t n, const std::function<void(int, int)> &fn) {
+    const int parts = PartsFor(n);
+    if (parts == 1) {
+        fn(0, 1);
         return;
     }
     {
         std::lock_guard<std::mutex> lk(mu_);
         fn_ = &fn;
-        n_ = n;
         pending_ = parts - 1;
         ++generation_;
     }
     cv_start_.notify_all();
-    fn(0, n / parts, 0);
+    fn(0, parts);
     std::unique_lock<std::mutex> lk(mu_);
     cv_done_.wait(lk, [&] { return pending_ == 0; });
+}
+void HostPool::ParallelFor(size_t n, const std::function<void(size_t, size_t, int)> &fn) {
+    ParallelRegion(n, [&](int part, int parts) {
+        const size_t b = n * (size_t) part / (size_t) parts, e = n * (size_t) (part + 1) / (size_t) parts;
+        if (e > b) fn(b, e, part);
+    });
 }
 
 // (x, y, z, alpha) packing: alpha = GetAlphaTimestamp(t) w.r.t. the pose pair's timestamps (types.h:192-219);
@@ -320,6 +316,100 @@ void Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst)
             _mm_sfence();
         });
     });
+}
+
+// RegisterFrame's O(N) host work as ONE parallel region (one wake-up of the team instead of two):
+//   1. every part reduces the timestamps of its slice to (min, max);
+//   2. team barrier; the pose-pair timestamps are the scan's (min, max) (compute_frame_info, odometry.cpp:186-196)
+//      unless the caller supplied an initial estimate (pose_timestamps = its {begin, end} dest_timestamp);
+//   3. the scan is packed in kRounds rounds; in round r part p packs piece r * parts + p, so a finished round is one
+//      contiguous range — part 0 enqueues its H2D copy at once and the copy engine works while later rounds are packed.
+void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, double *mn_out, double *mx_out) {
+    constexpr int kRounds = 4;
+    const size_t n = scan.n;
+    const int parts = pool_->PartsFor(n);
+    const int rounds = parts == 1 ? 1 : kRounds;
+    const size_t pieces = (size_t) rounds * (size_t) parts;
+    const char *px = static_cast<const char *>(scan.xyz), *pt = static_cast<const char *>(scan.t);
+    const size_t xs = scan.xyz_stride, ts = scan.t_stride;
+    float4 *dst = pipe_->Staging();
+    double mns[64], mxs[64];
+    std::atomic<int> arrived{0};
+    std::atomic<int> round_done[kRounds];
+    for (auto &r : round_done) r.store(0, std::memory_order_relaxed);
+    std::atomic<bool> failed{false};
+    const bool debug = getenv("CTICP_DEBUG_TIMERS") != nullptr;
+    // piece boundaries on multiples of 4 points (= one 64-byte line of the staging buffer per 4 NT stores)
+    auto piece_begin = [&](size_t piece) { return piece >= pieces ? n : (n * piece / pieces) & ~size_t(3); };
+    pipe_->UploadBegin(n);
+    if (debug) cudaEventRecord(ev_[4], stream_);
+
+    DispatchScanTypes(scan, [&](auto xt, auto tt) {
+        using XT = typename decltype(xt)::type;
+        using TT = typename decltype(tt)::type;
+        pool_->ParallelRegion(n, [&](int part, int nparts) {
+            // 1. min / max of my slice
+            {
+                const size_t b = n * (size_t) part / (size_t) nparts, e = n * (size_t) (part + 1) / (size_t) nparts;
+                double mn = INFINITY, mx = -INFINITY;
+                for (size_t i = b; i < e; ++i) {
+                    const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
+                    mn = ti < mn ? ti : mn;
+                    mx = ti > mx ? ti : mx;
+                }
+                mns[part] = mn;
+                mxs[part] = mx;
+            }
+            // 2. team barrier (all parts are running: a short spin, yielding if the machine is oversubscribed)
+            arrived.fetch_add(1, std::memory_order_acq_rel);
+            for (int spins = 0; arrived.load(std::memory_order_acquire) < nparts; ++spins) {
+                if (spins < 4096) _mm_pause();
+                else std::this_thread::yield();
+            }
+            double smn = INFINITY, smx = -INFINITY;
+            for (int i = 0; i < nparts; ++i) { smn = std::min(smn, mns[i]); smx = std::max(smx, mxs[i]); }
+            if (part == 0) { *mn_out = smn; *mx_out = smx; }
+            const double bts = pose_timestamps ? pose_timestamps[0] : smn, ets = pose_timestamps ? pose_timestamps[1] : smx;
+            const double mn = std::min(bts, ets), mx = std::max(bts, ets);
+            const bool spans = mx > mn;
+            const double inv = spans ? 1.0 / (mx - mn) : 0.0;
+            // 3. packing in rounds; alpha = GetAlphaTimestamp(t) (types.h:192-219; the caller range-checks)
+            int issued = 0;
+            auto issue_ready = [&](bool wait_all) {   // part 0 only
+                while (issued < rounds) {
+                    if (round_done[issued].load(std::memory_order_acquire) < nparts) {
+                        if (!wait_all) return;
+                        _mm_pause();
+                        continue;
+                    }
+                    try {
+                        pipe_->UploadRange(piece_begin((size_t) issued * nparts), piece_begin((size_t) (issued + 1) * nparts));
+                    } catch (...) {
+                        failed.store(true);
+                    }
+                    ++issued;
+                }
+            };
+            for (int r = 0; r < rounds; ++r) {
+                const size_t piece = (size_t) r * nparts + part;
+                const size_t b = piece_begin(piece), e = piece_begin(piece + 1);
+                for (size_t i = b; i < e; ++i) {
+                    const char *p = px + i * xs;
+                    const XT x = LoadUnaligned<XT>(p), y = LoadUnaligned<XT>(p + sizeof(XT)), z = LoadUnaligned<XT>(p + 2 * sizeof(XT));
+                    const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
+                    const double a = spans ? (ti - mn) * inv : 1.0;
+                    // non-temporal store: the packed scan is consumed by the DMA engine, not by this core
+                    _mm_stream_ps(reinterpret_cast<float *>(dst + i), _mm_set_ps((float) a, (float) z, (float) y, (float) x));
+                }
+                _mm_sfence();
+                round_done[r].fetch_add(1, std::memory_order_acq_rel);
+                if (part == 0) issue_ready(false);
+            }
+            if (part == 0) issue_ready(true);
+        });
+    });
+    if (debug) cudaEventRecord(ev_[5], stream_);
+    if (failed.load()) throw CudaError("cudaMemcpyAsync (scan upload)");
 }
 
 void Engine::MinMaxTimestamps(const ScanView &scan, double *mn_out, double *mx_out) {
@@ -447,6 +537,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     CT_CUDA_CHECK(cudaMemcpyAsync(h_state_, d_state_, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
     pipe_->QueueCountsReadback();
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    staging_in_flight_ = false;
     icp_->CollectGatherTiming();
     timing_.h2d_bytes += sizeof(IcpState);
     timing_.d2h_bytes += sizeof(IcpState) + sizeof(int) * 4;
@@ -470,6 +561,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     rs.frame.begin_pose.pose.t = V3{S.tb[0], S.tb[1], S.tb[2]};
     rs.frame.end_pose.pose.t = V3{S.te[0], S.te[1], S.te[2]};
     if (S.failed == 2) throw std::runtime_error("Error During Optimization");   // ct_icp.cpp:639-642
+    if (S.failed == 3) throw std::runtime_error("multi-GPU exchange timed out: a peer rank never delivered its accumulator");
     if (!rs.success) {
         char buf[160];
         snprintf(buf, sizeof(buf), "[CT_ICP]Error : not enough keypoints selected in ct-icp ! Number_of_residuals : %d",
@@ -630,13 +722,33 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     const size_t n = scan.n;
     auto t_start = hclock::now();
     CT_CUDA_CHECK(cudaSetDevice(device_));
+    if (n > pipe_->MaxPoints()) throw CapacityError("scan has more points than max_points_per_frame");
+    memset(&timing_, 0, sizeof(timing_));
+    icp_->reset_timing();
+    const int launches0 = map_->launches() + pipe_->launches() + icp_->launches();
+    last_all_world_valid_ = last_kp_world_valid_ = false;
+
     // compute_frame_info, odometry.cpp:186-196
     FrameInfo info;
+    double t_pack = 0;
     if (staged_slot >= 0) {
         info.begin_timestamp = staged_[staged_slot].t_min;
         info.end_timestamp = staged_[staged_slot].t_max;
     } else {
-        MinMaxTimestamps(scan, &info.begin_timestamp, &info.end_timestamp);
+        // Host buffers: timestamp min/max, packing and the H2D copy, pipelined (PackAndUpload). The copy is enqueued
+        // behind the previous frame's map update, which may still be running: the stream keeps the order, and the
+        // pinned staging buffer is free (its previous copy completed before that frame's ICP state was read back).
+        if (staging_in_flight_) CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // only after a call that threw midway
+        staging_in_flight_ = true;
+        CT_CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
+        double pose_ts[2];
+        if (initial_estimate) {
+            pose_ts[0] = initial_estimate->begin_pose.dest_timestamp;
+            pose_ts[1] = initial_estimate->end_pose.dest_timestamp;
+        }
+        PackAndUpload(scan, initial_estimate ? pose_ts : nullptr, &info.begin_timestamp, &info.end_timestamp);
+        t_pack = ms_since(t_start);
+        if (getenv("CTICP_DEBUG_TIMERS")) fprintf(stderr, "[cticp] host min/max + pack + upload enqueue %.3f ms\n", t_pack);
     }
     info.registered_fid = registered_frames_++;
     info.frame_id = frame_id;
@@ -644,17 +756,15 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     InitializeMotion(info, initial_estimate);
     const double t_init_motion = ms_since(t_start);
 
-    // the previous frame's map update has been enqueued; its counters tell whether the tables need maintenance
-    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    // the previous frame's map update: its counters tell whether the tables need maintenance. Waits on that frame's
+    // last event, NOT on the stream — this frame's H2D copy is already in flight behind it.
+    if (tail_event_valid_) CT_CUDA_CHECK(cudaEventSynchronize(ev_[3]));
+    else CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // first frame, after Reset(), or after a call that threw
+    tail_event_valid_ = false;
     map_->NotifyStreamSynchronized();
     map_->MaintainTables();
 
-    memset(&timing_, 0, sizeof(timing_));
-    icp_->reset_timing();
-    const int launches0 = map_->launches() + pipe_->launches() + icp_->launches();
-    last_all_world_valid_ = last_kp_world_valid_ = false;
-
-    CT_CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
+    if (staged_slot >= 0) CT_CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
     IngestImpl(scan, info, staged_slot);
     const double t_initialization = ms_since(t_start);
 
@@ -707,7 +817,11 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
         UpdateMap(summary, k);
     }
     CT_CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
-    if (!ran_icp) CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // frame 0: counts for the summary
+    tail_event_valid_ = true;
+    if (!ran_icp) {   // frame 0: counts for the summary
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        staging_in_flight_ = false;
+    }
 
     timing_.kernel_launches = map_->launches() + pipe_->launches() + icp_->launches() - launches0;
     if (out) {

@@ -49,14 +49,19 @@ struct ScanView {
     size_t n = 0;
 };
 
-// Minimal fork-join pool for the two host passes over a scan (timestamp min/max, float4 packing): the only O(N) host
+// Minimal fork-join pool for the host passes over a scan (timestamp min/max, float4 packing): the only O(N) host
 // work of RegisterFrame. Workers sleep on a condition variable between frames.
 class HostPool {
 public:
     explicit HostPool(int threads);
     ~HostPool();
     int size() const { return (int) workers_.size() + 1; }
-    // fn(begin, end, part) over [0, n) split into size() contiguous parts; the caller runs part 0
+    // number of parts a pass over n items is split into (1 below the threading threshold)
+    int PartsFor(size_t n) const { return (size() == 1 || n < 16384) ? 1 : size(); }
+    // fn(part, parts) on every thread of the team at once (parts = PartsFor(n)); the caller runs part 0. All parts run
+    // concurrently, so fn may synchronise its parts (TeamBarrier)
+    void ParallelRegion(size_t n, const std::function<void(int, int)> &fn);
+    // fn(begin, end, part) over [0, n) split into PartsFor(n) contiguous parts
     void ParallelFor(size_t n, const std::function<void(size_t, size_t, int)> &fn);
 
 private:
@@ -64,8 +69,7 @@ private:
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_start_, cv_done_;
-    const std::function<void(size_t, size_t, int)> *fn_ = nullptr;
-    size_t n_ = 0;
+    const std::function<void(int, int)> *fn_ = nullptr;
     uint64_t generation_ = 0;
     int pending_ = 0;
     bool stop_ = false;
@@ -98,6 +102,7 @@ public:
     void SetTimeGather(bool on) { icp_->set_time_gather(on); }
     void EnableSharding(const void *unique_id, int rank, int world);
     void DestroySharding();
+    int ShardingMode() const { return shard_world_ <= 1 ? 0 : (icp_ && icp_->peers_ready() ? 2 : 1); }
 
 private:
     struct FrameInfo {
@@ -123,12 +128,13 @@ private:
 
     void InitializeMotion(const FrameInfo &info, const cticp_frame *initial_estimate);
     void ResolvePoints(int which, const float4 **out_pts, const double **out_world, size_t *out_count);
-    void IngestAndSubSample(const ScanView &scan,
-                            const FrameInfo &info);
     void IngestImpl(const ScanView &scan,
                     const FrameInfo &info, int64_t staged_slot);
     void PackScan(const ScanView &scan, double bts,
                   double ets, float4 *dst);
+    // one parallel region: timestamp min/max → team barrier → (x, y, z, alpha) packing in rounds, the H2D copy of a
+    // round enqueued as soon as the round is complete (the copy engine runs while the later rounds are still packed)
+    void PackAndUpload(const ScanView &scan, const double *pose_timestamps, double *mn_out, double *mx_out);
     void MinMaxTimestamps(const ScanView &scan, double *mn_out, double *mx_out);
     std::unique_ptr<HostPool> pool_;
     void RegisterCommon(const ScanView &scan,
@@ -187,9 +193,16 @@ private:
     // timing
     cticp_device_timing timing_{};
     cudaEvent_t ev_[6];
+    bool tail_event_valid_ = false;    // ev_[3] (end of the last frame's map update) has been recorded and not yet waited on
+    bool staging_in_flight_ = false;   // the pinned staging buffer may still feed an H2D copy
     // multi-GPU
     void *nccl_comm_ = nullptr;
     int shard_rank_ = 0, shard_world_ = 1;
+    // NVLink peer mailboxes of the in-kernel exchange (peer_exchange.cuh, nccl_shard.cu)
+    bool ConnectPeers();
+    void DisconnectPeers();
+    void *d_mailbox_ = nullptr;
+    std::vector<void *> peer_mapped_;
 };
 
 // conversions shared with capi.cu

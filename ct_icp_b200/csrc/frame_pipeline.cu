@@ -304,6 +304,18 @@ void FramePipeline::Upload(size_t n) {
     h2d_bytes_ = sizeof(float4) * n + sizeof(int);
 }
 
+void FramePipeline::UploadBegin(size_t n) {
+    if (n > max_points_) throw CapacityError("scan has more points than max_points_per_frame");
+    n_ = n;
+    h_counts_[0] = (int) n;
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_counts_, h_counts_, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    h2d_bytes_ = sizeof(float4) * n + sizeof(int);
+}
+void FramePipeline::UploadRange(size_t begin, size_t end) {
+    if (end <= begin) return;
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_raw_ + begin, h_stage_ + begin, sizeof(float4) * (end - begin), cudaMemcpyHostToDevice, stream_));
+}
+
 void FramePipeline::UploadFromDevice(const float4 *d_src, size_t n) {
     if (n > max_points_) throw CapacityError("scan has more points than max_points_per_frame");
     n_ = n;

@@ -21,6 +21,10 @@ public:
     float4 *Staging() { return h_stage_; }
     size_t MaxPoints() const { return max_points_; }
     void Upload(size_t n);
+    // the same copy in pieces, so that it can start while the tail of the scan is still being packed:
+    // UploadBegin(n), then UploadRange over a partition of [0, n) in any order
+    void UploadBegin(size_t n);
+    void UploadRange(size_t begin, size_t end);
     void UploadFromDevice(const float4 *d_src, size_t n);   // scan already packed and resident in HBM
 
     // Odometry::InitializeFrame: shuffle → sub_sample_frame → (frames 0,1: timestamp := end) → shuffle

@@ -43,6 +43,14 @@ inline void icp_state_refresh_slerp(IcpState &S) {
     S.slerp_negate = c.negate;
 }
 
+// Host-side description of the peer mailboxes (mirrors PeerLinks of peer_exchange.cuh without device code)
+constexpr int kMaxPeerRanks = 8;
+struct PeerLinksHost {
+    int world = 1, rank = 0;
+    unsigned long long *inbox[kMaxPeerRanks] = {};
+    unsigned int *seq = nullptr;
+};
+
 struct GnParams {
     int r;                      // stencil radius (voxels)
     int level;                  // map level searched
@@ -89,8 +97,15 @@ public:
     void set_time_gather(bool on) { time_gather_ = on; }
     void set_persistent(bool on) { use_persistent_ = on; }
     void CollectGatherTiming();   // after a stream sync: accumulates the event pairs recorded since the last call
-    // multi-GPU: partials[0..kAcc) ← all-reduce over ranks of Σ_blocks partials (nccl_shard.cu)
-    void AllReduceAccumulator(void *nccl_comm);
+    // multi-GPU: d_acc_[0..kAcc) ← Σ over ranks of d_acc_, in place: over the NVLink peer mailboxes when they are
+    // connected (k_peer_allreduce, peer_exchange.cuh), else ncclAllReduce (nccl_shard.cu). d_state receives the
+    // failure flag if a peer never answers.
+    void AllReduceAccumulator(void *nccl_comm, IcpState *d_state);
+    // peer mailboxes (nccl_shard.cu sets them up); world == 1 disconnects
+    void SetPeerLinks(const PeerLinksHost &links);
+    void NcclAllReduceAccumulator(void *nccl_comm);   // nccl_shard.cu
+    double *acc_buffer() const { return d_acc_; }
+    bool peers_ready() const { return peers_ready_; }
 
 private:
     void EnsurePartials(int blocks);
@@ -119,8 +134,10 @@ private:
     cudaEvent_t ev_begin_[kMaxEvents], ev_end_[kMaxEvents];
     int ev_used_ = 0;
     int num_sms_ = 148;
-    int max_coresident_ = 0;
+    int max_coresident_[2] = {0, 0};   // k_gn_persistent<false / true>
     bool use_persistent_ = true;
+    PeerLinksHost links_host_;
+    bool peers_ready_ = false;
 };
 
 }  // namespace cticp

@@ -12,6 +12,7 @@
 
 #include "gather.cuh"
 #include "icp.h"
+#include "peer_exchange.cuh"
 #include "small_solve.cuh"
 
 namespace cticp {
@@ -299,9 +300,14 @@ __device__ __forceinline__ void load_state_volatile(const IcpState *st, Q4 &qb, 
     sc = SlerpConsts{__ldcg(&st->slerp_theta), __ldcg(&st->slerp_inv_sin), __ldcg(&st->slerp_linear), __ldcg(&st->slerp_negate)};
 }
 
+//
+// kPeers (multi-GPU, keypoints sharded): between its reduction and its solve the solver CTA exchanges the accumulator
+// with the other ranks' solver CTAs through NVLink peer memory (peer_exchange.cuh) — the all-reduce of SURVEY §8e
+// happens INSIDE the loop, so the sharded loop is still one launch and costs one NVLink round trip per iteration.
+template <bool kPeers>
 __global__ void __launch_bounds__(kGatherWarps * 32)
 k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
-                IcpState *st, double *__restrict__ partials, int num_iters) {
+                IcpState *st, double *__restrict__ partials, int num_iters, PeerLinks links) {
     // Measured alternatives (config 2, 5 iterations, ICP ms): this design 0.180; arrive-counter / epoch-word hand-off
     // instead of grid.sync() 0.383; ONE barrier per iteration with every CTA redundantly reducing + solving 0.343 —
     // although its empty loop is 2.4x cheaper (0.029 vs 0.070): when every SM alternates between the gather code and
@@ -314,10 +320,13 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
     __shared__ int s_stencil[kMaxStencil];
     __shared__ SolveScratch s_solve;
     __shared__ IcpState s_dummy;
+    __shared__ int s_peer_ok;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const GatherConfig &G = cfg.G;
     const GnParams &P = cfg.P;
     const bool solver_cta = blockIdx.x == 0;
+    unsigned int peer_seq = 0;   // sequence number of the last exchange (solver CTA only)
+    if (kPeers && solver_cta) peer_seq = *links.seq;
     const int gather_ctas = gridDim.x - 1;
     const int *stencil = stencil_table_fill(s_stencil, G.r);
     __syncthreads();
@@ -443,9 +452,21 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 s_acc[0][threadIdx.x] = s;
             }
             __syncthreads();
+            bool peers_ok = true;
+            if (kPeers) {
+                // Σ over ranks, in rank order (bit-identical on every rank); the stencil staging area of this CTA is
+                // unused by the solver CTA and serves as scratch
+                static_assert(sizeof(KnnStage) * 64 * kGatherWarps >= sizeof(unsigned int) * kMaxPeers * kPeerWords, "scratch");
+                peers_ok = peer_allreduce(links, ++peer_seq, s_acc[0], reinterpret_cast<unsigned int *>(&s_stage[0][0]), &s_peer_ok);
+            }
             CT_STAMP(if (threadIdx.x == 0) st->dbg_t[2] = global_timer_ns();)
             if (w == 0) {
-                if (P.debug_flags & 1) {
+                if (!peers_ok) {
+                    if (lane == 0) {   // a peer never answered: give up instead of hanging the device
+                        st->failed = 3;
+                        st->done = 1;
+                    }
+                } else if (P.debug_flags & 1) {
                     if (lane == 0) st->iter += 1;
                 } else
                     warp_gn_solve(s_acc[0], s_solve, st, P, 0, nullptr, lane);
@@ -454,6 +475,26 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             __threadfence();
         }
         grid.sync();
+    }
+    if (kPeers && solver_cta && threadIdx.x == 0) *links.seq = peer_seq;
+}
+
+// Stand-alone exchange for the launch-per-step paths (solvers CERES / ROBUST: one per LM evaluation; GN with
+// CTICP_PERSISTENT=0): acc ← Σ over ranks of acc, in place, one CTA.
+__global__ void __launch_bounds__(256) k_peer_allreduce(PeerLinks links, double *__restrict__ acc, IcpState *st) {
+    __shared__ double s_acc[kAcc];
+    __shared__ unsigned int s_half[kMaxPeers * kPeerWords];
+    __shared__ int s_ok;
+    if (threadIdx.x < kAcc) s_acc[threadIdx.x] = acc[threadIdx.x];
+    const unsigned int seq = *links.seq + 1;
+    const bool ok = peer_allreduce(links, seq, s_acc, s_half, &s_ok);
+    if (threadIdx.x < kAcc) acc[threadIdx.x] = s_acc[threadIdx.x];
+    if (threadIdx.x == 0) {
+        *links.seq = seq;
+        if (!ok && st) {
+            st->failed = 3;
+            st->done = 1;
+        }
     }
 }
 
@@ -534,6 +575,28 @@ k_radius_search(const RadiusSearchLevels *__restrict__ R, int kmax, const double
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+static_assert(kMaxPeerRanks == kMaxPeers, "host / device peer tables");
+static PeerLinks MakeLinks(const PeerLinksHost &h) {
+    PeerLinks L;
+    L.world = h.world;
+    L.rank = h.rank;
+    for (int i = 0; i < kMaxPeers; ++i) L.inbox[i] = h.inbox[i];
+    L.seq = h.seq;
+    return L;
+}
+void IcpSolver::SetPeerLinks(const PeerLinksHost &links) {
+    links_host_ = links;
+    peers_ready_ = links.world > 1 && links.seq != nullptr;
+}
+void IcpSolver::AllReduceAccumulator(void *nccl_comm, IcpState *d_state) {
+    if (peers_ready_) {
+        k_peer_allreduce<<<1, 256, 0, stream_>>>(MakeLinks(links_host_), d_acc_, d_state);
+        launches_ += 1;
+        return;
+    }
+    NcclAllReduceAccumulator(nccl_comm);
+}
+
 IcpSolver::IcpSolver(cudaStream_t stream) : stream_(stream) {
     UploadPairTables();
     if (const char *e = getenv("CTICP_PERSISTENT")) use_persistent_ = atoi(e) != 0;
@@ -615,23 +678,27 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
     cfg.G.kmax = cfg.P.kmax;
     const int blocks = GatherBlocks((k_upper + shard_world - 1) / shard_world + 16, num_sms_);
     EnsurePartials(blocks + 1);
-    if (!nccl_comm && use_persistent_) {
+    const bool peers = nccl_comm && shard_world > 1 && peers_ready_;
+    if (use_persistent_ && (!nccl_comm || peers)) {
         // one cooperative launch for the whole loop; the grid must be co-resident (grid-wide barriers)
-        if (max_coresident_ == 0) {
+        void *kernel = peers ? (void *) k_gn_persistent<true> : (void *) k_gn_persistent<false>;
+        int &coresident = max_coresident_[peers ? 1 : 0];
+        if (coresident == 0) {
             int per_sm = 0;
-            CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_persistent, kGatherWarps * 32, 0));
-            max_coresident_ = std::max(1, per_sm * num_sms_);
+            CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGatherWarps * 32, 0));
+            coresident = std::max(1, per_sm * num_sms_);
         }
-        int grid = std::min(blocks + 1, max_coresident_);
+        int grid = std::min(blocks + 1, coresident);
         grid = std::max(grid, 2);
         const float4 *kp = d_keypoints;
         const int *nk = d_num_keypoints;
         double *parts = d_partials_;
         int iters = num_iters;
-        void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters};
+        PeerLinks links = peers ? MakeLinks(links_host_) : PeerLinks{};
+        void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters, &links};
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
-        CT_CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_gn_persistent, dim3(grid), dim3(kGatherWarps * 32), args, 0, stream_));
+        CT_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kGatherWarps * 32), args, 0, stream_));
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
         gather_launches_ += 1;
         launches_ += 1;
@@ -646,7 +713,7 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         ++gather_launches_;
         launches_ += 1;
         if (nccl_comm) {
-            AllReduceAccumulator(nccl_comm);   // nccl_shard.cu: in-place sum of d_acc_ over ranks
+            AllReduceAccumulator(nccl_comm, d_state);   // in-place sum of d_acc_ over ranks (peer mailboxes, else NCCL)
             k_gn_solve_acc<<<1, 32, 0, stream_>>>(d_acc_, d_state, cfg.P);
             launches_ += 1;
         }

@@ -892,7 +892,7 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
             k_lm_eval<<<eval_blocks, kLmWarps * 32, 0, stream_>>>(P, phase, blocks_buf, d_lm_sel_, d_state, lm, d_partials_);
             if (sharded) {
                 k_lm_reduce<<<1, 128, 0, stream_>>>(d_partials_, eval_blocks, d_acc_);
-                AllReduceAccumulator(nccl_comm);
+                AllReduceAccumulator(nccl_comm, d_state);
                 k_lm_step<<<1, 128, 0, stream_>>>(P, phase, d_acc_, 1, d_state, lm);
                 launches_ += 1;
             } else {
@@ -902,7 +902,7 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
         };
         if (sharded) {   // all-gather of the per-rank valid counts (as a sum of one-hot vectors)
             k_lm_select<<<1, 1024, 0, stream_>>>(P, 1, d_num_keypoints, blocks_buf, d_lm_sel_, d_state, lm, stats, d_acc_);
-            AllReduceAccumulator(nccl_comm);
+            AllReduceAccumulator(nccl_comm, d_state);
             launches_ += 1;
         }
         k_lm_select<<<1, 1024, 0, stream_>>>(P, 0, d_num_keypoints, blocks_buf, d_lm_sel_, d_state, lm, stats, d_acc_);

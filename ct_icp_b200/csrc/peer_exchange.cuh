@@ -1,0 +1,88 @@
+// peer_exchange.cuh — the multi-GPU exchange of SURVEY §8e done by the ICP kernels themselves over NVLink peer memory.
+//
+// The path has exactly one exchange per Gauss-Newton iteration / LM evaluation: the sum over ranks of a 96-double
+// accumulator (JTJ upper triangle, JTr, counters: 768 bytes). That is latency, not bandwidth: a library collective
+// costs a kernel launch (and, inside the persistent GN kernel, would force the loop back to one launch per iteration).
+// Instead every rank owns a MAILBOX in its HBM that all peers map (CUDA IPC between processes, peer access inside one
+// process), and the exchanging CTA
+//   1. stores its accumulator into its slot of EVERY rank's mailbox — 192 eight-byte words, each carrying 32 payload
+//      bits and the 32-bit sequence number of this exchange (the "LL" idea: an aligned 8-byte store is delivered
+//      atomically over NVLink, so a word whose flag matches is complete and no fence / separate flag is needed),
+//   2. polls its OWN mailbox until the words of all ranks carry this exchange's sequence number,
+//   3. sums the contributions in RANK ORDER — every rank adds the same numbers in the same order, so the result is
+//      bit-identical everywhere and all ranks keep taking the same solver decisions (no broadcast).
+// Slots are double-buffered by the parity of the sequence number: a rank can only be one exchange ahead of a peer
+// (exchange n+1 needs that peer's contribution to n+1, sent after it finished reading n), so parity n is free again
+// when exchange n+2 writes it. The sequence counter lives in device memory, advances by one per exchange and is the
+// same number on every rank because all ranks run the same number of exchanges (same decisions, see 3.).
+// A poll that does not complete within kPeerTimeoutCycles gives up (returns false) so a dead peer can never hang the GPU.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "icp.h"
+
+namespace cticp {
+
+constexpr int kMaxPeers = 8;                         // one NVSwitch domain
+constexpr int kPeerWords = 2 * kAcc;                 // 8-byte words per contribution (32 payload bits each)
+constexpr size_t kMailboxWords = (size_t) 2 * kMaxPeers * kPeerWords;   // [parity][source rank][word]
+constexpr long long kPeerTimeoutCycles = 6000000000LL;   // ~3 s at 1.9 GHz: ranks are host-launched, allow jitter
+
+struct PeerLinks {
+    int world = 1, rank = 0;
+    unsigned long long *inbox[kMaxPeers] = {};   // inbox[p] = rank p's mailbox as mapped into THIS process (inbox[rank]: own)
+    unsigned int *seq = nullptr;                 // device counter: exchanges completed so far
+};
+
+__device__ __forceinline__ void peer_store_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long peer_load_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// In-place sum over ranks of acc[0..kAcc) (shared memory of the calling CTA). Called by ALL threads of a CTA with at
+// least kPeerWords threads; s_half: world * kPeerWords unsigned ints of shared scratch; s_ok: one shared int.
+// `seq` = sequence number of this exchange (uniform, never 0). Returns false on time-out (uniform).
+__device__ __forceinline__ bool peer_allreduce(const PeerLinks &L, unsigned int seq, double *acc, unsigned int *s_half,
+                                               int *s_ok) {
+    const int tid = threadIdx.x;
+    const size_t slot = (size_t) (seq & 1u) * kMaxPeers * kPeerWords;
+    if (tid == 0) *s_ok = 1;
+    __syncthreads();   // acc complete, s_ok initialised
+    if (tid < kPeerWords) {
+        const unsigned int half = reinterpret_cast<const unsigned int *>(acc)[tid];
+        const unsigned long long word = ((unsigned long long) seq << 32) | (unsigned long long) half;
+        for (int p = 0; p < L.world; ++p)
+            peer_store_u64(L.inbox[p] + slot + (size_t) L.rank * kPeerWords + tid, word);
+        const unsigned long long *mine = L.inbox[L.rank] + slot;
+        const long long t0 = clock64();
+        for (int r = 0; r < L.world; ++r) {
+            unsigned long long w = peer_load_u64(mine + (size_t) r * kPeerWords + tid);
+            while ((unsigned int) (w >> 32) != seq) {
+                if (clock64() - t0 > kPeerTimeoutCycles) {
+                    *s_ok = 0;
+                    break;
+                }
+                w = peer_load_u64(mine + (size_t) r * kPeerWords + tid);
+            }
+            s_half[r * kPeerWords + tid] = (unsigned int) w;
+        }
+    }
+    __syncthreads();
+    const bool ok = *s_ok != 0;
+    if (ok && tid < kAcc) {
+        double s = 0;
+        for (int r = 0; r < L.world; ++r) {   // rank order: the same sum on every rank
+            const unsigned int lo = s_half[r * kPeerWords + 2 * tid], hi = s_half[r * kPeerWords + 2 * tid + 1];
+            s += __hiloint2double((int) hi, (int) lo);
+        }
+        acc[tid] = s;
+    }
+    __syncthreads();
+    return ok;
+}
+
+}  // namespace cticp

@@ -370,10 +370,14 @@ int cticp_odometry_reset(cticp_odometry *h);
 /* ct_icp::Odometry::GetMapPointer(), src/ct_icp/odometry.cpp:991-993 (borrowed; owned by the odometry) */
 cticp_map *cticp_odometry_map(cticp_odometry *h);
 
-/* multi-GPU (new): keypoints sharded rank/world, one NCCL all-reduce of JTJ/JTr per iteration.
- * unique_id is the 128-byte ncclUniqueId produced by cticp_nccl_unique_id on rank 0 and broadcast by the caller. */
+/* multi-GPU (new): keypoints sharded rank/world, one exchange (sum over ranks) of JTJ/JTr per GN
+ * iteration / LM evaluation. unique_id is the 128-byte ncclUniqueId produced by cticp_nccl_unique_id on rank 0 and
+ * broadcast by the caller; NCCL bootstraps NVLink peer mailboxes (CUDA IPC) through which the ICP kernels exchange
+ * the accumulators themselves, and stays as the fallback (ncclAllReduce per exchange) where peers cannot be mapped. */
 int cticp_nccl_unique_id(void *out_128_bytes);
 int cticp_odometry_enable_sharding(cticp_odometry *h, const void *unique_id_128_bytes, int rank, int world);
+/* 0 = not sharded, 1 = exchange through ncclAllReduce, 2 = in-kernel exchange over peer mailboxes */
+int cticp_odometry_sharding_mode(cticp_odometry *h);
 
 /* device timing of the last register_frame (CUDA events on the handle's stream), milliseconds */
 typedef struct cticp_device_timing {

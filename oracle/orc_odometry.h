@@ -368,7 +368,9 @@ private:
         summary.all_corrected_points.resize(xyz.size());
         const Pose &bp = summary.frame.begin_pose;
         const Pose &ep = summary.frame.end_pose;
-#pragma omp parallel for
+        // odometry.cpp:469,480: num_threads(options_.ct_icp_options.ls_num_threads) — NOT the machine's core count
+        const int transform_threads = std::max(1, options_.ct_icp_options.ls_num_threads);
+#pragma omp parallel for num_threads(transform_threads)
         for (long i = 0; i < (long) summary.all_corrected_points.size(); ++i) {
             auto &p = summary.all_corrected_points[i];
             p.raw = xyz[i];
@@ -376,7 +378,7 @@ private:
             p.index_frame = info.frame_id;
             p.world = bp.ContinuousTransform(p.raw, ep, p.timestamp);
         }
-#pragma omp parallel for
+#pragma omp parallel for num_threads(transform_threads)
         for (long i = 0; i < (long) summary.corrected_points.size(); ++i) {
             auto &p = summary.corrected_points[i];
             p.world = bp.ContinuousTransform(p.raw, ep, p.timestamp);

@@ -1,6 +1,8 @@
-"""Multi-GPU parity check (run under torchrun, one rank per GPU): keypoint-sharded registration with one NCCL
-all-reduce per Gauss-Newton iteration (GN) / per LM evaluation (CERES, ROBUST) must reproduce the single-GPU poses and
-be identical on every rank.
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): keypoint-sharded registration with one exchange
+(sum over ranks of JTJ/JTr) per Gauss-Newton iteration (GN) / per LM evaluation (CERES, ROBUST) must reproduce the
+single-GPU poses and be identical on every rank. The exchange runs inside the ICP kernels over NVLink peer mailboxes
+(sharding_mode 2); CTICP_P2P=0 forces the ncclAllReduce fallback (mode 1). Also prints the mean steady-state
+RegisterFrame latency (wall clock, max over ranks) of the single and the sharded run.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/multigpu_check.py
@@ -8,6 +10,7 @@ be identical on every rank.
 import ctypes
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -52,28 +55,39 @@ def run(sharded, solver):
             uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         od.enable_sharding(uid.cpu().numpy().tobytes(), rank, world)
-    poses = []
-    for s in seq:
+    mode = od.sharding_mode()
+    poses, ms = [], []
+    for i, s in enumerate(seq):
+        if sharded:
+            dist.barrier()          # ranks enter the frame together, like a driver feeding all GPUs the same scan
+        od.last_timing()
+        t0 = time.perf_counter()
         sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        od.last_timing()
+        if i >= 21:
+            ms.append((time.perf_counter() - t0) * 1e3)
         assert sm.success, sm.error_message
         poses.append(list(sm.frame.begin_pose.quat) + list(sm.frame.begin_pose.tr) + list(sm.frame.end_pose.quat) +
                      list(sm.frame.end_pose.tr))
     od.close()
-    return np.array(poses)
+    return np.array(poses), mode, (float(np.mean(ms)) if ms else float("nan"))
 
 
 ok = True
 for solver in os.environ.get("CTICP_CHECK_SOLVERS", "GN,CERES,ROBUST").split(","):
-    single = run(False, solver)
-    sharded = run(True, solver)
+    single, _, ms_single = run(False, solver)
+    sharded, mode, ms_sharded = run(True, solver)
+    lat = torch.tensor([ms_single, ms_sharded], dtype=torch.float64, device="cuda")
+    dist.all_reduce(lat, op=dist.ReduceOp.MAX)
     t = torch.from_numpy(sharded).cuda()
     gathered = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(gathered, t)
     if rank == 0:
         across = max(float((g - gathered[0]).abs().max()) for g in gathered)
         vs_single = float(np.abs(sharded - single).max())
-        print("MULTIGPU %s world=%d frames=%d max|sharded - single|=%.3e max|rank_i - rank_0|=%.3e"
-              % (solver, world, frames, vs_single, across))
+        print("MULTIGPU %s world=%d frames=%d sharding_mode=%d max|sharded - single|=%.3e max|rank_i - rank_0|=%.3e "
+              "latency ms/frame: single %.3f sharded %.3f"
+              % (solver, world, frames, mode, vs_single, across, float(lat[0]), float(lat[1])))
         ok = ok and across == 0.0 and vs_single < (1e-7 if solver == "GN" else 1e-6)
 if rank == 0:
     assert ok, "sharded registration diverged"

@@ -99,9 +99,8 @@ def make_options(b):
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
 
-    In-process NVML (pynvml) from a daemon thread every 100 ms; `nvidia-smi -lms` is the fallback. (A separate
-    nvidia-smi process polling every 50 ms was measured to stretch the HOST-timed end-to-end steps — its queries
-    contend with this process's driver calls — so the sampler is kept as light as the recipe allows.)"""
+    In-process NVML (pynvml) from a daemon thread every 100 ms — two cheap queries per sample, no child process next
+    to the HOST-timed end-to-end steps; `nvidia-smi -lms 200` is the fallback (CTICP_BENCH_CLOCKS=smi forces it)."""
 
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 

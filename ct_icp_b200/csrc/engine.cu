@@ -85,9 +85,12 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
     next_robust_level_ = options_.robust_minimal_level;
 
     {
-        int threads = 8;
+        // host team of the O(N) passes: a quarter of the machine, 4..16 threads (measured on the 128-CPU B200 host:
+        // packing 130k points takes 0.25 ms on 2 threads, 0.085 on 8, 0.073 on 16)
+        const int hw = std::max(1, (int) std::thread::hardware_concurrency());
+        int threads = std::max(4, std::min(16, hw / 4));
         if (const char *e = getenv("CTICP_HOST_THREADS")) threads = atoi(e);
-        threads = std::max(1, std::min(threads, std::min(64, (int) std::thread::hardware_concurrency())));
+        threads = std::max(1, std::min(threads, std::min(64, hw)));
         pool_ = std::make_unique<HostPool>(threads);
     }
     CT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));

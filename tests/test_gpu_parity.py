@@ -333,6 +333,71 @@ def test_odometry_sequence_hdl64_gn(orc, eng, seq_hdl64):
     assert len(ka) == len(kb) and np.abs(ka["world"] - kb["world"]).max() < 1e-4
 
 
+def _estimate_from(prev_frame, t_begin, t_end, frame_idx):
+    """RegisterFrameWithEstimate input (odometry.cpp:236-248): a pose pair at the previous end pose whose timestamps
+    bracket the scan a little wider than its own min / max (alpha is taken against the POSE timestamps)."""
+    est = abi.Frame()
+    for dst, ts in ((est.begin_pose, t_begin), (est.end_pose, t_end)):
+        for i in range(4):
+            dst.quat[i] = prev_frame.end_pose.quat[i]
+        for i in range(3):
+            dst.tr[i] = prev_frame.end_pose.tr[i]
+        dst.ref_timestamp, dst.dest_timestamp = 0.0, ts
+        dst.ref_frame_id, dst.dest_frame_id = 0, frame_idx
+    return est
+
+
+def _run_with_estimates(b, seq):
+    od = b.odometry(_sequence_options(b, "GN", init_num_frames=4))
+    out, prev = [], None
+    for i, s in enumerate(seq):
+        # frames 0 and 1 collapse every timestamp onto the end pose (odometry.cpp:355-359): with a wider pose interval
+        # the begin pose would be all but unobservable there, so the estimates start at frame 2
+        if i < 2:
+            sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        else:
+            est = _estimate_from(prev.frame, float(s["t"].min()) - 1e-3, float(s["t"].max()) + 2e-3, s["frame_idx"])
+            sm = od.RegisterFrameWithEstimate(s["xyz"], s["t"], est, s["frame_idx"])
+        prev = sm
+        out.append((sm, od.MapSize()))
+    return od, out
+
+
+def test_odometry_register_frame_with_estimate(orc, eng, seq_small):
+    """RegisterFrameWithEstimate (odometry.cpp:236-248): the caller's pose pair replaces InitializeMotion and its
+    timestamps — not the scan's min / max — define the per-point alpha."""
+    _, ro = _run_with_estimates(orc, seq_small)
+    _, re_ = _run_with_estimates(eng, seq_small)
+    for i, ((so, mo), (se, me)) in enumerate(zip(ro, re_)):
+        assert so.success == se.success, i
+        assert so.num_corrected_points == se.num_corrected_points, i
+        assert so.num_keypoints == se.num_keypoints, i
+        assert mo == me, i
+        dt, dr = frame_diff(so.frame, se.frame)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
+        assert se.frame.begin_pose.dest_timestamp == so.frame.begin_pose.dest_timestamp
+
+
+def test_estimate_not_covering_the_scan_is_an_error_and_recoverable(eng, seq_small):
+    """A pose pair that does not bracket the scan's timestamps is CTICP_ERR_TIMESTAMP (the reference CHECK-aborts,
+    types.h:456); the scan's upload is already in flight when that is detected, and the handle must stay usable."""
+    from ct_icp_b200 import CticpError
+    od = eng.odometry(_sequence_options(eng, "GN", init_num_frames=4))
+    sms = [od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]) for s in seq_small[:3]]
+    s = seq_small[3]
+    bad = _estimate_from(sms[-1].frame, float(s["t"].min()) + 0.01, float(s["t"].max()) + 0.01, s["frame_idx"])
+    with pytest.raises(CticpError) as e:
+        od.RegisterFrameWithEstimate(s["xyz"], s["t"], bad, s["frame_idx"])
+    assert e.value.code == abi.ERR_TIMESTAMP
+    od.Reset()
+    ref = eng.odometry(_sequence_options(eng, "GN", init_num_frames=4))
+    for s in seq_small[:4]:
+        a = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        b = ref.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        assert a.success and b.success
+        assert frame_diff(a.frame, b.frame) == (0.0, 0.0)
+
+
 def test_odometry_reset(eng, seq_small):
     od, r1 = _run_sequence(eng, seq_small[:4], init_num_frames=2)
     p1 = [list(s.frame.end_pose.tr) for s, _ in r1]

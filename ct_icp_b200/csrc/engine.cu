@@ -218,7 +218,7 @@ HostPool::~HostPool() {
     {
         std::lock_guard<std::mutex> lk(mu_);
         stop_ = true;
-        ++generation_;
+        generation_.fetch_add(1, std::memory_order_release);
     }
     cv_start_.notify_all();
     for (auto &w : workers_) w.join();
@@ -226,19 +226,26 @@ HostPool::~HostPool() {
 void HostPool::Worker(int id) {
     uint64_t seen = 0;
     while (true) {
-        const std::function<void(int, int)> *fn;
-        {
+        // poll for the next job for ~1 ms, then sleep
+        bool have = false;
+        const auto t0 = hclock::now();
+        for (int spins = 0;; ++spins) {
+            if (generation_.load(std::memory_order_acquire) != seen) {
+                have = true;
+                break;
+            }
+            _mm_pause();
+            if ((spins & 255) == 255 && ms_since(t0) > 1.0) break;
+        }
+        if (!have) {
             std::unique_lock<std::mutex> lk(mu_);
-            cv_start_.wait(lk, [&] { return generation_ != seen; });
-            seen = generation_;
-            if (stop_) return;
-            fn = fn_;
+            cv_start_.wait(lk, [&] { return generation_.load(std::memory_order_acquire) != seen; });
         }
+        seen = generation_.load(std::memory_order_acquire);
+        if (stop_) return;   // written before the generation bump that released us
+        const std::function<void(int, int)> *fn = fn_;
         (*fn)(id, size());
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--pending_ == 0) cv_done_.notify_one();
-        }
+        pending_.fetch_sub(1, std::memory_order_acq_rel);
     }
 }
 void HostPool::ParallelRegion(size_t n, const std::function<void(int, int)> &fn) {
@@ -248,15 +255,17 @@ void HostPool::ParallelRegion(size_t n, const std::function<void(int, int)> &fn)
         return;
     }
     {
-        std::lock_guard<std::mutex> lk(mu_);
+        std::lock_guard<std::mutex> lk(mu_);   // orders the bump against a worker about to sleep on cv_start_
         fn_ = &fn;
-        pending_ = parts - 1;
-        ++generation_;
+        pending_.store(parts - 1, std::memory_order_relaxed);
+        generation_.fetch_add(1, std::memory_order_release);
     }
     cv_start_.notify_all();
     fn(0, parts);
-    std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    for (int spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins) {
+        if (spins < (1 << 16)) _mm_pause();
+        else std::this_thread::yield();
+    }
 }
 void HostPool::ParallelFor(size_t n, const std::function<void(size_t, size_t, int)> &fn) {
     ParallelRegion(n, [&](int part, int parts) {

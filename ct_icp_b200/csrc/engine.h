@@ -5,6 +5,7 @@
 // RobustRegistration :780-852, UpdateMap :855-953) while every O(N)/O(K·S) stage runs on the device.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -50,7 +51,10 @@ struct ScanView {
 };
 
 // Minimal fork-join pool for the host passes over a scan (timestamp min/max, float4 packing): the only O(N) host
-// work of RegisterFrame. Workers sleep on a condition variable between frames.
+// work of RegisterFrame. After a job the workers keep polling for the next one for ~1 ms before they go to sleep on a
+// condition variable (what OpenMP runtimes do by default, cf. GOMP_SPINCOUNT): when frames arrive back to back the
+// team starts within a microsecond instead of a futex wake-up per worker (~50 us for 15 workers); at sensor rate
+// (10-20 Hz) the polling is a ~1 % duty cycle. The caller polls for completion as well (the job is ~50 us long).
 class HostPool {
 public:
     explicit HostPool(int threads);
@@ -68,10 +72,10 @@ private:
     void Worker(int id);
     std::vector<std::thread> workers_;
     std::mutex mu_;
-    std::condition_variable cv_start_, cv_done_;
+    std::condition_variable cv_start_;
     const std::function<void(int, int)> *fn_ = nullptr;
-    uint64_t generation_ = 0;
-    int pending_ = 0;
+    std::atomic<uint64_t> generation_{0};
+    std::atomic<int> pending_{0};
     bool stop_ = false;
 };
 

@@ -575,22 +575,13 @@ k_radius_search(const RadiusSearchLevels *__restrict__ R, int kmax, const double
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-static_assert(kMaxPeerRanks == kMaxPeers, "host / device peer tables");
-static PeerLinks MakeLinks(const PeerLinksHost &h) {
-    PeerLinks L;
-    L.world = h.world;
-    L.rank = h.rank;
-    for (int i = 0; i < kMaxPeers; ++i) L.inbox[i] = h.inbox[i];
-    L.seq = h.seq;
-    return L;
-}
 void IcpSolver::SetPeerLinks(const PeerLinksHost &links) {
     links_host_ = links;
     peers_ready_ = links.world > 1 && links.seq != nullptr;
 }
 void IcpSolver::AllReduceAccumulator(void *nccl_comm, IcpState *d_state) {
     if (peers_ready_) {
-        k_peer_allreduce<<<1, 256, 0, stream_>>>(MakeLinks(links_host_), d_acc_, d_state);
+        k_peer_allreduce<<<1, 256, 0, stream_>>>(PeerLinksOf(links_host_), d_acc_, d_state);
         launches_ += 1;
         return;
     }
@@ -694,7 +685,7 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         const int *nk = d_num_keypoints;
         double *parts = d_partials_;
         int iters = num_iters;
-        PeerLinks links = peers ? MakeLinks(links_host_) : PeerLinks{};
+        PeerLinks links = peers ? PeerLinksOf(links_host_) : PeerLinks{};
         void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters, &links};
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);

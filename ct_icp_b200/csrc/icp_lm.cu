@@ -21,6 +21,7 @@
 #include "gather.cuh"
 #include "icp.h"
 #include "lm_functor.cuh"
+#include "peer_exchange.cuh"
 #include "small_solve.cuh"
 
 namespace cticp {
@@ -513,8 +514,14 @@ __device__ double norm14(const double *v) {
 // phase 0: the accumulator holds the evaluation at lm->x (start of ceres::Solve: IterationZero).
 // phase 1: the accumulator holds the evaluation at lm->cand.
 // One warp; the 12x12 solves are warp-collective, the scalar logic runs on lane 0.
+// kPeers (multi-GPU): the evaluation is the sum over ranks — the exchange (peer_exchange.cuh) happens here, between
+// the reduction of this rank's partials and the minimizer step, so a sharded LM evaluation costs the same two launches
+// as a single-GPU one. The early return below is taken by all ranks together (done flags derive from identical sums),
+// so the ranks' exchange counters stay in step.
+template <bool kPeers>
 __global__ void __launch_bounds__(128)
-k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblocks, IcpState *st, LmState *lm) {
+k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblocks, IcpState *st, LmState *lm,
+          PeerLinks links) {
     __shared__ LmScratch S;
     __shared__ double s_part[4][kAcc];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -533,6 +540,20 @@ k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblock
         __syncthreads();
         if (threadIdx.x < kAcc) S.acc[threadIdx.x] = s_part[0][threadIdx.x] + s_part[1][threadIdx.x] + s_part[2][threadIdx.x] + s_part[3][threadIdx.x];
         __syncthreads();
+    }
+    if (kPeers) {
+        __shared__ unsigned int s_half[kMaxPeers * kPeerWords];
+        __shared__ int s_peer_ok;
+        const unsigned int seq = *links.seq + 1;
+        const bool ok = peer_allreduce(links, seq, S.acc, s_half, &s_peer_ok);   // Σ over ranks, in rank order
+        if (threadIdx.x == 0) {
+            *links.seq = seq;
+            if (!ok) {   // a peer never answered: give up instead of hanging the device
+                st->failed = 3;
+                st->done = 1;
+            }
+        }
+        if (!ok) return;
     }
     if (w != 0) return;
     const double min_relative_decrease = 1e-3, function_tolerance = 1e-6, gradient_tolerance = 1e-10,
@@ -890,13 +911,15 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
         // the same step — the exchange of SURVEY §8e, once per LM evaluation.
         auto eval_and_step = [&](int phase) {
             k_lm_eval<<<eval_blocks, kLmWarps * 32, 0, stream_>>>(P, phase, blocks_buf, d_lm_sel_, d_state, lm, d_partials_);
-            if (sharded) {
+            if (sharded && peers_ready_) {   // exchange inside the step kernel (NVLink peer mailboxes)
+                k_lm_step<true><<<1, 128, 0, stream_>>>(P, phase, d_partials_, eval_blocks, d_state, lm, PeerLinksOf(links_host_));
+            } else if (sharded) {            // fallback: library collective between two kernels
                 k_lm_reduce<<<1, 128, 0, stream_>>>(d_partials_, eval_blocks, d_acc_);
                 AllReduceAccumulator(nccl_comm, d_state);
-                k_lm_step<<<1, 128, 0, stream_>>>(P, phase, d_acc_, 1, d_state, lm);
+                k_lm_step<false><<<1, 128, 0, stream_>>>(P, phase, d_acc_, 1, d_state, lm, PeerLinks{});
                 launches_ += 1;
             } else {
-                k_lm_step<<<1, 128, 0, stream_>>>(P, phase, d_partials_, eval_blocks, d_state, lm);
+                k_lm_step<false><<<1, 128, 0, stream_>>>(P, phase, d_partials_, eval_blocks, d_state, lm, PeerLinks{});
             }
             launches_ += 2;
         };

@@ -34,6 +34,16 @@ struct PeerLinks {
     unsigned int *seq = nullptr;                 // device counter: exchanges completed so far
 };
 
+static_assert(kMaxPeerRanks == kMaxPeers, "host / device peer tables");
+inline PeerLinks PeerLinksOf(const PeerLinksHost &h) {   // the host-side description (icp.h) as a kernel argument
+    PeerLinks L;
+    L.world = h.world;
+    L.rank = h.rank;
+    for (int i = 0; i < kMaxPeers; ++i) L.inbox[i] = h.inbox[i];
+    L.seq = h.seq;
+    return L;
+}
+
 __device__ __forceinline__ void peer_store_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -43,43 +53,47 @@ __device__ __forceinline__ unsigned long long peer_load_u64(const unsigned long 
     return v;
 }
 
-// In-place sum over ranks of acc[0..kAcc) (shared memory of the calling CTA). Called by ALL threads of a CTA with at
-// least kPeerWords threads; s_half: world * kPeerWords unsigned ints of shared scratch; s_ok: one shared int.
+// In-place sum over ranks of acc[0..kAcc) (shared memory of the calling CTA). Called by ALL threads of a CTA (any
+// size that is a multiple of 32); s_half: world * kPeerWords unsigned ints of shared scratch; s_ok: one shared int.
 // `seq` = sequence number of this exchange (uniform, never 0). Returns false on time-out (uniform).
 __device__ __forceinline__ bool peer_allreduce(const PeerLinks &L, unsigned int seq, double *acc, unsigned int *s_half,
                                                int *s_ok) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
     const size_t slot = (size_t) (seq & 1u) * kMaxPeers * kPeerWords;
     if (tid == 0) *s_ok = 1;
     __syncthreads();   // acc complete, s_ok initialised
-    if (tid < kPeerWords) {
-        const unsigned int half = reinterpret_cast<const unsigned int *>(acc)[tid];
+    for (int wd = tid; wd < kPeerWords; wd += nthreads) {
+        const unsigned int half = reinterpret_cast<const unsigned int *>(acc)[wd];
         const unsigned long long word = ((unsigned long long) seq << 32) | (unsigned long long) half;
         for (int p = 0; p < L.world; ++p)
-            peer_store_u64(L.inbox[p] + slot + (size_t) L.rank * kPeerWords + tid, word);
-        const unsigned long long *mine = L.inbox[L.rank] + slot;
-        const long long t0 = clock64();
+            peer_store_u64(L.inbox[p] + slot + (size_t) L.rank * kPeerWords + wd, word);
+    }
+    const unsigned long long *mine = L.inbox[L.rank] + slot;
+    const long long t0 = clock64();
+    for (int wd = tid; wd < kPeerWords; wd += nthreads) {
         for (int r = 0; r < L.world; ++r) {
-            unsigned long long w = peer_load_u64(mine + (size_t) r * kPeerWords + tid);
+            unsigned long long w = peer_load_u64(mine + (size_t) r * kPeerWords + wd);
             while ((unsigned int) (w >> 32) != seq) {
                 if (clock64() - t0 > kPeerTimeoutCycles) {
                     *s_ok = 0;
                     break;
                 }
-                w = peer_load_u64(mine + (size_t) r * kPeerWords + tid);
+                w = peer_load_u64(mine + (size_t) r * kPeerWords + wd);
             }
-            s_half[r * kPeerWords + tid] = (unsigned int) w;
+            s_half[r * kPeerWords + wd] = (unsigned int) w;
         }
     }
     __syncthreads();
     const bool ok = *s_ok != 0;
-    if (ok && tid < kAcc) {
-        double s = 0;
-        for (int r = 0; r < L.world; ++r) {   // rank order: the same sum on every rank
-            const unsigned int lo = s_half[r * kPeerWords + 2 * tid], hi = s_half[r * kPeerWords + 2 * tid + 1];
-            s += __hiloint2double((int) hi, (int) lo);
+    if (ok) {
+        for (int e = tid; e < kAcc; e += nthreads) {
+            double s = 0;
+            for (int r = 0; r < L.world; ++r) {   // rank order: the same sum on every rank
+                const unsigned int lo = s_half[r * kPeerWords + 2 * e], hi = s_half[r * kPeerWords + 2 * e + 1];
+                s += __hiloint2double((int) hi, (int) lo);
+            }
+            acc[e] = s;
         }
-        acc[tid] = s;
     }
     __syncthreads();
     return ok;

@@ -333,6 +333,8 @@ def main():
     step_ms, launches, kp_sum, f_sum, iters_sum = [], 0, 0, 0, 0
     for i in range(n_timed_begin, n_timed_begin + K):
         od.flush_l2(256 << 20)
+        if dist is not None:
+            barrier()                     # all ranks receive the scan at the same time (untimed)
         od.timer_start()
         sm = od.RegisterStaged(slots[i], seq[i]["frame_idx"])
         ms = od.timer_stop()
@@ -385,7 +387,9 @@ def main():
     for i in range(n_timed_begin, n_timed_begin + K):
         od.flush_l2(256 << 20)
         torch.cuda.synchronize(device)
-        od.last_timing()                  # drains the engine's stream (flush included)
+        od.last_timing()                  # the previous frame's tail has completed
+        if dist is not None:
+            barrier()                     # all ranks receive the scan at the same time (untimed)
         t0 = time.perf_counter()
         sm = od.RegisterFrame(seq[i]["xyz"], seq[i]["t"], seq[i]["frame_idx"])
         t = od.last_timing()              # waits for the map-update tail of this frame
@@ -417,7 +421,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_scan": npts, "frame_points": f_sum / K,
+            "config": {"workload": WORKLOAD.replace("1xB200", "%dxB200" % world), "points_per_scan": npts, "frame_points": f_sum / K,
                        "keypoints": kp_sum / K, "icp_iters_per_step": iters_sum / K, "preroll_frames": args.preroll,
                        "l2": "flushed between steps (256 MiB memset, untimed)",
                        "parallelism": "single GPU" if world == 1 else "keypoints sharded x%d, JTJ/JTr summed over ranks once per iteration: %s" % (

@@ -1,0 +1,79 @@
+"""Turns the ncu outputs of a gpurun call into the small JSON summaries committed under profiles/.
+
+    python tools/summarize_ncu.py launches <launches.csv> <out.json>      # per-launch times of the LAST frame + shares
+    python tools/summarize_ncu.py full <raw.csv> <out.json> [kernel ...]  # selected metrics of a --set full capture
+                                                                          # (raw.csv = `ncu -i x.ncu-rep --page raw --csv`)
+"""
+import csv
+import json
+import sys
+
+FRAME_FIRST_KERNEL = "k_grid_claim"      # first launch of a RegisterFrame step with device-resident input
+KEEP = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.sum", "smsp__inst_executed.sum",
+    "sm__inst_issued.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "launch__registers_per_thread",
+    "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
+    "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
+    "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct",
+    "smsp__warp_issue_stalled_membar_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct",
+    "smsp__average_warp_latency_issue_stalled_no_instruction.pct", "sm__icc_requests.sum", "sm__icc_requests_lookup_miss.sum",
+]
+
+
+def rows_of(path):
+    with open(path, newline="") as f:
+        lines = [l for l in f if l.startswith('"')]
+    return list(csv.DictReader(lines))
+
+
+def launches(src, dst):
+    rows = [r for r in rows_of(src) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    seq = [(r["Kernel Name"].split("(")[0], float(r["Metric Value"]) / 1e3, r["Grid Size"], r["Block Size"]) for r in rows]
+    # the last frame = from the last but one... find the last occurrence of the first-of-frame kernel that is followed
+    # by a complete frame (the frame sub-sampling launches k_grid_claim twice: frame grid, then keypoint grid)
+    starts = [i for i, s in enumerate(seq) if s[0] == FRAME_FIRST_KERNEL and (i == 0 or seq[i - 1][0] != "k_grid_emit")]
+    begin = starts[-1]
+    frame = seq[begin:]
+    total = sum(s[1] for s in frame)
+    out = {"frame": "last frame of the capture (steady state)", "sum_us": total,
+           "launches": [{"kernel": k, "us": us, "share": us / total, "grid": g, "block": b} for k, us, g, b in frame]}
+    by_kernel = {}
+    for k, us, _, _ in frame:
+        by_kernel[k] = by_kernel.get(k, 0.0) + us
+    out["share_by_kernel"] = {k: v / total for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out["share_by_kernel"], indent=1), "sum_us", total, "launches", len(frame))
+
+
+def full(src, dst, kernels):
+    rows = rows_of(src)
+    out = {}
+    # the raw page is wide: one row per launch, one column per metric (first data row holds the units)
+    units = rows[0] if rows and rows[0].get("ID", "") == "" else {}
+    for r in rows:
+        name = r.get("Kernel Name", "")
+        if not name:
+            continue
+        short = name.split("(")[0].split("<")[0]
+        if kernels and not any(k in short for k in kernels):
+            continue
+        m = {}
+        for key in KEEP:
+            if key in r and r[key] != "":
+                m[key] = {"value": r[key], "unit": units.get(key, "")}
+        out.setdefault(short, []).append({"grid": r.get("Grid Size"), "block": r.get("Block Size"), "metrics": m})
+    json.dump(out, open(dst, "w"), indent=1)
+    for k, v in out.items():
+        print(k, len(v), "launch(es)", {a: b["value"] for a, b in v[0]["metrics"].items()
+                                       if a in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum")})
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3])
+    else:
+        full(sys.argv[2], sys.argv[3], sys.argv[4:])

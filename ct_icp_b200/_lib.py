@@ -9,7 +9,8 @@ import os
 from ._binding import Binding
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcticp_b200.so")
+# CTICP_ENGINE_LIB: an experiment build of the same engine (csrc/Makefile BUILD= OUT= EXTRA=), for A/B measurements
+LIB_PATH = os.environ.get("CTICP_ENGINE_LIB") or os.path.join(_PKG, "libcticp_b200.so")
 _engine = None
 
 

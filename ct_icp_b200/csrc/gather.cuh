@@ -32,7 +32,10 @@ struct __align__(16) KnnStage {
 constexpr double kKnnInf = 1e300;
 
 __device__ __forceinline__ bool knn_less(const KnnEntry &a, const KnnEntry &b) {
-    return a.d2 < b.d2 || (a.d2 == b.d2 && a.seq < b.seq);
+    // predicate logic only (| and &, not || and &&): the short-circuit form compiled to a divergent branch with a
+    // reconvergence barrier in every step of the compare-exchange network (measured: GN loop 201 -> 186 us per frame)
+    const bool lt = a.d2 < b.d2, eq = a.d2 == b.d2, sl = a.seq < b.seq;
+    return lt | (eq & sl);
 }
 __device__ __forceinline__ KnnEntry knn_shfl_xor(const KnnEntry &e, int mask) {
     KnnEntry o;
@@ -134,6 +137,8 @@ __device__ __forceinline__ QueryCtx make_query(const V3 &q, double res, int lane
 // of them is consumed, so a keypoint pays ~one L2/HBM round trip for all its map points instead of one per voxel.
 constexpr int kPrefetch = 4;
 
+// (Outlining this function — one copy of the sort / merge network instead of one per unrolled call site, kernel 19.5k
+// instead of 23.1k instructions — was measured slower: GN loop 190.9 vs 186.0 us per frame.)
 __device__ __forceinline__ void knn_consume32(KnnStage *stage, int &fill, KnnEntry &best, int lane) {
     const KnnStage t = stage[lane];
     KnnEntry c{t.d2, t.seq, t.addr};
@@ -164,6 +169,13 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int 
     int fill = 0;
     unsigned pts_total = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
+#ifdef CTICP_PRUNE
+    // Opt-in (build with -DCTICP_PRUNE): distance of the kmax-th best so far — a later candidate at or beyond it can
+    // never enter the result (candidates arrive in scan order, so on a tie the earlier-scanned point, already kept,
+    // wins, map.h:495). Parity-clean (all GPU tests pass) but neutral on config 2 (GN loop 190.9 vs 192.7 us: a
+    // keypoint there has ~35 in-radius candidates, i.e. one or two merges either way); kept for denser maps.
+    double prune_d2 = kKnnInf;
+#endif
 
     for (int base = 0; base < nst; base += 32) {
         const int s = base + lane;
@@ -242,6 +254,9 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int 
                     const double rx = vx + (double) pv[u].x, ry = vy + (double) pv[u].y, rz = vz + (double) pv[u].z;
                     const double d2 = rx * rx + ry * ry + rz * rz;
                     bool in = valid && !(d2 > G.radius2);
+#ifdef CTICP_PRUNE
+                    in = in && d2 < prune_d2;
+#endif
                     if (kFilter) {
                         const double vs = __shfl_sync(0xffffffffu, sdn, ol);
                         const int vh = __shfl_sync(0xffffffffu, has_normal, ol);
@@ -259,7 +274,12 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int 
                     }
                     fill += __popc(m);
                     __syncwarp();
-                    if (fill >= 32) knn_consume32(stage, fill, best, lane);
+                    if (fill >= 32) {
+                        knn_consume32(stage, fill, best, lane);
+#ifdef CTICP_PRUNE
+                        prune_d2 = __shfl_sync(0xffffffffu, best.d2, G.kmax - 1);
+#endif
+                    }
                 }
             }
         }

@@ -1,0 +1,19 @@
+"""cticp::HostPool (the host team of RegisterFrame's min/max + packing pass): built with plain g++ against the engine
+library and run on CPU — coverage of ParallelFor, concurrency of ParallelRegion, poll → sleep → wake transitions."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "host_pool_test")
+
+
+def test_host_pool():
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cuda_inc = "/usr/local/cuda/include"
+    cmd = [cxx, "-std=c++17", "-O1", "-Wall", "-I", cuda_inc, "-I", os.path.join(ROOT, "ct_icp_b200", "csrc"),
+           os.path.join(ROOT, "tests", "cpp", "host_pool_test.cpp"), "-L", os.path.join(ROOT, "ct_icp_b200"),
+           "-lcticp_b200", "-Wl,-rpath," + os.path.join(ROOT, "ct_icp_b200"), "-lpthread", "-o", EXE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "HOST POOL OK" in r.stdout, r.stdout + r.stderr

@@ -3,6 +3,7 @@
     python tools/summarize_ncu.py launches <launches.csv> <out.json>      # per-launch times of the LAST frame + shares
     python tools/summarize_ncu.py full <raw.csv> <out.json> [kernel ...]  # selected metrics of a --set full capture
                                                                           # (raw.csv = `ncu -i x.ncu-rep --page raw --csv`)
+    python tools/summarize_ncu.py source <src.csv> <out.json>             # stall samples (`--page source --csv`)
 """
 import csv
 import json
@@ -72,8 +73,36 @@ def full(src, dst, kernels):
                                        if a in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum")})
 
 
+def source(src, dst, top=12):
+    """`ncu -i x.ncu-rep --page source --csv` → warp-stall samples per reason and the instructions that collect them."""
+    rows = list(csv.reader(open(src, newline="")))
+    hdr = next(r for r in rows if "Address" in r and "Source" in r)
+    data = rows[rows.index(hdr) + 1:]
+    col = {h: i for i, h in enumerate(hdr)}
+    reasons = [h for h in hdr if h.startswith("stall_") and "(Not Issued)" not in h]
+    total = sum(int(r[col["# Samples"]]) for r in data)
+    by_reason = {h: sum(int(r[col[h]] or 0) for r in data) for h in reasons}
+    by_reason = {k: v for k, v in sorted(by_reason.items(), key=lambda kv: -kv[1]) if v}
+    hot = sorted(data, key=lambda r: -int(r[col["# Samples"]]))[:top]
+    out = {"kernel": rows[0][1] if rows and len(rows[0]) > 1 else "", "samples": total,
+           "samples_by_stall_reason": by_reason,
+           "share_by_stall_reason": {k: v / total for k, v in by_reason.items()},
+           "instructions_executed": sum(int(r[col["Instructions Executed"]] or 0) for r in data),
+           "sass_instructions": len(data),
+           "hottest_instructions": [
+               {"sass": r[col["Source"]].strip(), "offset": r[col["Address"]][-5:], "samples": int(r[col["# Samples"]]),
+                "share": int(r[col["# Samples"]]) / total, "executed": int(r[col["Instructions Executed"]] or 0),
+                "top_reason": max(reasons, key=lambda h: int(r[col[h]] or 0))} for r in hot]}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out["share_by_stall_reason"], indent=1))
+    for h in out["hottest_instructions"]:
+        print("%5d %5.1f%% %-18s %s" % (h["samples"], 100 * h["share"], h["top_reason"], h["sass"][:70]))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "source":
+        source(sys.argv[2], sys.argv[3])
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4:])

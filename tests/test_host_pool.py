@@ -17,3 +17,15 @@ def test_host_pool():
     assert r.returncode == 0, r.stderr
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "HOST POOL OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_peer_exchange_protocol_model():
+    """Design check of the multi-GPU exchange (csrc/peer_exchange.cuh): LL words + two parity slots per source rank are
+    race-free for any interleaving and give every rank the same rank-ordered sum (host model, threads = ranks)."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = os.path.join(ROOT, "tests", "cpp", "peer_protocol_model")
+    r = subprocess.run([cxx, "-std=c++17", "-O1", "-Wall", os.path.join(ROOT, "tests", "cpp", "peer_protocol_model.cpp"),
+                        "-lpthread", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "PEER PROTOCOL OK" in r.stdout, r.stdout + r.stderr

@@ -84,6 +84,34 @@ struct PeerBlob {   // what every rank tells every other rank (all-gathered thro
     int device;
     int ok;
 };
+// Mailboxes are never cudaFree'd while the process lives: a peer may still hold an IPC mapping of one when its owner
+// tears its engine down (ranks destroy their handles at their own pace, and freeing exported memory before every
+// importer closed it is undefined behaviour). A retired mailbox goes back to this per-device pool and is re-zeroed
+// when the next engine of this process adopts it; the exchange protocol is symmetric, so once an owner has finished
+// its last exchange no peer writes to its mailbox any more.
+struct MailboxPool {
+    std::mutex mu;
+    std::vector<std::pair<int, void *>> free_list;   // (device, mailbox)
+    void *Take(int device) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].first == device) {
+                void *p = free_list[i].second;
+                free_list.erase(free_list.begin() + (long) i);
+                return p;
+            }
+        return nullptr;
+    }
+    void Give(int device, void *p) {
+        std::lock_guard<std::mutex> lk(mu);
+        free_list.emplace_back(device, p);
+    }
+};
+MailboxPool &Pool() {
+    static MailboxPool pool;
+    return pool;
+}
+
 unsigned long long HostTag() {
     char name[256] = {0};
     gethostname(name, sizeof(name) - 1);
@@ -103,7 +131,8 @@ bool Engine::ConnectPeers() {
     if (world > kMaxPeerRanks || !api.AllGather) my_ok = 0;
 
     // own mailbox (+ the exchange counter behind it), zeroed before anybody can learn its address
-    if (cudaMalloc(&d_mailbox_, kMailboxBytes + 256) != cudaSuccess) {
+    d_mailbox_ = Pool().Take(device_);
+    if (!d_mailbox_ && cudaMalloc(&d_mailbox_, kMailboxBytes + 256) != cudaSuccess) {
         cudaGetLastError();
         d_mailbox_ = nullptr;
         my_ok = 0;
@@ -210,7 +239,7 @@ void Engine::DisconnectPeers() {
     if (icp_) icp_->SetPeerLinks(PeerLinksHost{});
     for (void *m : peer_mapped_) cudaIpcCloseMemHandle(m);
     peer_mapped_.clear();
-    if (d_mailbox_) cudaFree(d_mailbox_);
+    if (d_mailbox_) Pool().Give(device_, d_mailbox_);   // not freed: see MailboxPool
     d_mailbox_ = nullptr;
     cudaGetLastError();
 }

@@ -502,8 +502,11 @@ def test_odometry_sequence_hdl64_ceres(orc, eng, seq_hdl64):
     print("CERES worst per-frame pose difference: %.3e m, %.3e rad" % (worst_t, worst_r))
 
 
-def test_multigpu_sharded_registration_matches_single_gpu():
-    """Keypoints sharded over 2 GPUs with one NCCL all-reduce per GN iteration (needs >= 2 devices; skipped otherwise)."""
+@pytest.mark.parametrize("p2p,mode", [("1", 2), ("0", 1)])
+def test_multigpu_sharded_registration_matches_single_gpu(p2p, mode):
+    """Keypoints sharded over 2 GPUs, JTJ/JTr summed over the ranks once per GN iteration / LM evaluation: inside the ICP
+    kernels over NVLink peer mailboxes (sharding_mode 2) and through the ncclAllReduce fallback (CTICP_P2P=0, mode 1).
+    Needs >= 2 devices; skipped otherwise."""
     import os
     import subprocess
     import sys
@@ -511,12 +514,13 @@ def test_multigpu_sharded_registration_matches_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CTICP_CHECK_FRAMES="8")
+    env = dict(os.environ, CTICP_CHECK_FRAMES="8", CTICP_P2P=p2p)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
                         os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, env=env,
                        timeout=600)
     assert "MULTIGPU OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "sharding_mode=%d" % mode in r.stdout, r.stdout[-2000:]
 
 
 # ---- BASELINE.json configs[3] and configs[4] ------------------------------------------------------------------------

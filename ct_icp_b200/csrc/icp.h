@@ -33,6 +33,12 @@ struct IcpState {
     int slerp_linear, slerp_negate;
     unsigned long long stat_keypoint_iters, stat_stencil_points;
     unsigned long long dbg_t[4];   // %globaltimer stamps of the last iteration: CTA0 start, last-CTA elected, reduced, solved
+#ifdef CTICP_HANDOFF
+    // experiment build: point-to-point hand-off between the gather CTAs and the solver CTA of k_gn_persistent instead
+    // of two grid-wide barriers per iteration (zeroed with the rest of the state before every launch)
+    unsigned int handoff_arrive;   // gather CTAs that delivered their partial row (monotonic over the iterations)
+    unsigned int handoff_epoch;    // iterations whose pose update the solver CTA has published
+#endif
 };
 
 inline void icp_state_refresh_slerp(IcpState &S) {

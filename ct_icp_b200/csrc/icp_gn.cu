@@ -311,6 +311,20 @@ __device__ __forceinline__ void load_state_volatile(const IcpState *st, Q4 &qb, 
 // kPeers (multi-GPU, keypoints sharded): between its reduction and its solve the solver CTA exchanges the accumulator
 // with the other ranks' solver CTAs through NVLink peer memory (peer_exchange.cuh) — the all-reduce of SURVEY §8e
 // happens INSIDE the loop, so the sharded loop is still one launch and costs one NVLink round trip per iteration.
+#ifdef CTICP_HANDOFF
+// Experiment (-DCTICP_HANDOFF, to be measured): the two grid-wide barriers of an iteration become two one-directional
+// hand-offs — gather CTAs → solver CTA through an arrive counter (only the solver polls it), solver CTA → gather CTAs
+// through an epoch word (one thread per gather CTA polls it, the rest of the CTA waits at a hardware barrier).
+__device__ __forceinline__ unsigned int handoff_load(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void handoff_store(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#endif
+
 template <bool kPeers>
 __global__ void __launch_bounds__(kGatherWarps * 32)
 k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
@@ -356,6 +370,13 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
     }
 
     for (int it = 0; it < num_iters; ++it) {
+#ifdef CTICP_HANDOFF
+        if (!solver_cta && it > 0) {   // wait until the solver CTA has published the pose of iteration it - 1
+            if (threadIdx.x == 0)
+                while (handoff_load(&st->handoff_epoch) < (unsigned int) it) {}
+            __syncthreads();
+        }
+#endif
         if (__ldcg(&st->done)) break;   // uniform: written before the previous grid barrier
         if (!solver_cta) {
             double acc0 = 0, acc1 = 0, acc2 = 0;
@@ -435,18 +456,56 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 __stcg(&partials[(size_t) (blockIdx.x - 1) * kAcc + threadIdx.x], s);
             }
         }
+#ifdef CTICP_HANDOFF
+        if (!solver_cta) {   // deliver: row written → fence → count this CTA in
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&st->handoff_arrive, 1u);
+        } else {             // collect: all gather CTAs of this iteration have delivered
+            if (threadIdx.x == 0)
+                while (handoff_load(&st->handoff_arrive) < (unsigned int) gather_ctas * (unsigned int) (it + 1)) {}
+            __syncthreads();
+        }
+#else
         grid.sync();
+#endif
         if (solver_cta) {
             CT_STAMP(if (threadIdx.x == 0) st->dbg_t[1] = global_timer_ns();)
-            // deterministic reduction: warp g sums the rows b = g (mod 4) of three columns per lane, then the four
-            // partial sums are combined in fixed order
+            // deterministic reduction: warp g sums the rows b = g (mod kGatherWarps) of three columns per lane, then
+            // the per-warp sums are combined in fixed order
             double a0 = 0, a1 = 0, a2 = 0;
+#ifdef CTICP_REDUCE_MLP
+            // Experiment (-DCTICP_REDUCE_MLP, to be measured): all of a warp's rows are requested before the first is
+            // added (one L2 round trip instead of one per four rows); the additions keep their order
+            constexpr int kRowsInFlight = 8;
+            for (int b0 = w; b0 < gather_ctas; b0 += kGatherWarps * kRowsInFlight) {
+                double v0[kRowsInFlight], v1[kRowsInFlight], v2[kRowsInFlight];
+#pragma unroll
+                for (int u = 0; u < kRowsInFlight; ++u) {
+                    const int b = b0 + u * kGatherWarps;
+                    if (b < gather_ctas) {
+                        const double *row = partials + (size_t) b * kAcc;
+                        v0[u] = __ldcg(row + lane);
+                        v1[u] = __ldcg(row + lane + 32);
+                        v2[u] = __ldcg(row + lane + 64);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kRowsInFlight; ++u)
+                    if (b0 + u * kGatherWarps < gather_ctas) {
+                        a0 += v0[u];
+                        a1 += v1[u];
+                        a2 += v2[u];
+                    }
+            }
+#else
             for (int b = w; b < gather_ctas; b += kGatherWarps) {
                 const double *row = partials + (size_t) b * kAcc;
                 a0 += __ldcg(row + lane);
                 a1 += __ldcg(row + lane + 32);
                 a2 += __ldcg(row + lane + 64);
             }
+#endif
             s_acc[w][lane] = a0;
             s_acc[w][lane + 32] = a1;
             s_acc[w][lane + 64] = a2;
@@ -481,7 +540,14 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             }
             __threadfence();
         }
+#ifdef CTICP_HANDOFF
+        if (solver_cta) {   // publish: the pose update (fenced above by every thread of this CTA) is visible → epoch
+            __syncthreads();
+            if (threadIdx.x == 0) handoff_store(&st->handoff_epoch, (unsigned int) (it + 1));
+        }
+#else
         grid.sync();
+#endif
     }
     if (kPeers && solver_cta && threadIdx.x == 0) *links.seq = peer_seq;
 }

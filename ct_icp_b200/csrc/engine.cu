@@ -85,13 +85,7 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
     next_robust_level_ = options_.robust_minimal_level;
 
     {
-        // host team of the O(N) passes: a quarter of the machine, 4..16 threads (measured on the 128-CPU B200 host:
-        // packing 130k points takes 0.25 ms on 2 threads, 0.085 on 8, 0.073 on 16)
-        const int hw = std::max(1, (int) std::thread::hardware_concurrency());
-        int threads = std::max(4, std::min(16, hw / 4));
-        if (const char *e = getenv("CTICP_HOST_THREADS")) threads = atoi(e);
-        threads = std::max(1, std::min(threads, std::min(64, hw)));
-        pool_ = std::make_unique<HostPool>(threads);
+        pool_ = std::make_unique<HostPool>(HostTeamSize(1));
     }
     CT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     // per-voxel normals are only read by the DistanceBasedStrategy's sensor-side filter (map.h:482-490)
@@ -210,6 +204,16 @@ void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t sta
                           override_alpha, alpha_value);
 }
 
+// Host team of the O(N) passes: a quarter of the machine shared by the ranks of this node, 2..16 threads (measured on
+// the 128-CPU B200 host: packing 130k points takes 0.25 ms on 2 threads, 0.085 on 8, 0.073 on 16).
+int Engine::HostTeamSize(int ranks_on_node) {
+    const int hw = std::max(1, (int) std::thread::hardware_concurrency());
+    int threads = std::max(2, std::min(16, hw / (4 * std::max(1, ranks_on_node))));
+    if (ranks_on_node <= 1) threads = std::max(4, threads);
+    if (const char *e = getenv("CTICP_HOST_THREADS")) threads = atoi(e);
+    return std::max(1, std::min(threads, std::min(64, hw)));
+}
+
 // ---- host fork-join pool -------------------------------------------------------------------------------------
 HostPool::HostPool(int threads) {
     for (int i = 1; i < threads; ++i) workers_.emplace_back([this, i] { Worker(i); });
@@ -226,7 +230,9 @@ HostPool::~HostPool() {
 void HostPool::Worker(int id) {
     uint64_t seen = 0;
     while (true) {
-        // poll for the next job for ~1 ms, then sleep
+        // poll for the next job for ~1 ms, then sleep. The first ~2k polls only pause (back-to-back frames find the
+        // team awake); after that every poll also yields, so an oversubscribed host (several ranks per node, each
+        // with its own team) is never held up by pollers
         bool have = false;
         const auto t0 = hclock::now();
         for (int spins = 0;; ++spins) {
@@ -235,6 +241,7 @@ void HostPool::Worker(int id) {
                 break;
             }
             _mm_pause();
+            if (spins >= 2048) std::this_thread::yield();
             if ((spins & 255) == 255 && ms_since(t0) > 1.0) break;
         }
         if (!have) {

@@ -141,6 +141,7 @@ private:
     void PackAndUpload(const ScanView &scan, const double *pose_timestamps, double *mn_out, double *mx_out);
     void MinMaxTimestamps(const ScanView &scan, double *mn_out, double *mx_out);
     std::unique_ptr<HostPool> pool_;
+    static int HostTeamSize(int ranks_on_node);
     void RegisterCommon(const ScanView &scan,
                         uint32_t frame_id, const cticp_frame *initial_estimate, int64_t staged_slot,
                         cticp_summary *out);

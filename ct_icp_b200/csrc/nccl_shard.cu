@@ -255,6 +255,8 @@ void Engine::EnableSharding(const void *unique_id, int rank, int world) {
     }
     shard_rank_ = rank;
     shard_world_ = world;
+    // every rank of the node runs its own host team: share the machine between them (one node assumed)
+    if (HostTeamSize(world) != pool_->size()) pool_ = std::make_unique<HostPool>(HostTeamSize(world));
     if (world == 1) return;
     ncclUniqueId id;
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");

@@ -92,6 +92,27 @@ def test_ct_point_to_plane_residual_zero_on_plane(orc, seed):
         assert abs(r_error) >= 1e-3
 
 
+# ---- test/unit/ct_icp/test_cost_functions.cxx:9-30 (FunctorPointToPlane on ONE pose) -----------------------------
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("alpha", [0.0, 0.37, 1.0])
+def test_point_to_plane_functor_single_pose(orc, seed, alpha):
+    """The reference's single-pose functor is what the CT functor evaluates when begin == end (any alpha): zero for a
+    point in the plane through `reference`, clearly non-zero off the plane."""
+    rng = np.random.default_rng(40 + seed)
+    normal = np.array([0.0, 0.0, 1.0])
+    reference = rng.uniform(-1, 1, 3)
+    world_point = rng.uniform(-1, 1, 3)
+    world_in_plane = rng.uniform(-1, 1, 3)
+    world_in_plane[2] = reference[2]
+    q, t = _q(rng), rng.uniform(-1, 1, 3)
+    qinv, tinv = se3_inverse(orc, q, t)
+    raw = se3_apply(orc, qinv, tinv, world_point)
+    raw_in_plane = se3_apply(orc, qinv, tinv, world_in_plane)
+    assert abs(ct_residual(orc, alpha, reference, raw_in_plane, normal, 1.0, q, t, q, t)) <= 1e-12
+    if abs(world_point[2] - reference[2]) > 1e-2:
+        assert abs(ct_residual(orc, alpha, reference, raw, normal, 1.0, q, t, q, t)) >= 1e-3
+
+
 # ---- the autodiff restatement: tangent-space Jacobian vs central differences through Plus -----------------------
 def _quat_plus(q, d):
     n = np.linalg.norm(d)

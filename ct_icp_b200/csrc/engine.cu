@@ -773,7 +773,6 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     info.frame_id = frame_id;
     const int k = info.registered_fid;
     InitializeMotion(info, initial_estimate);
-    const double t_init_motion = ms_since(t_start);
 
     // the previous frame's map update: its counters tell whether the tables need maintenance. Waits on that frame's
     // last event, NOT on the stream — this frame's H2D copy is already in flight behind it.
@@ -849,7 +848,7 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
         out->num_corrected_points = (uint64_t) pipe_->h_counts()[1];
         out->num_keypoints = ran_icp ? (uint64_t) pipe_->h_counts()[2] : 0;
         out->odometry_total = ms_since(t_start);
-        out->odometry_initialization = t_initialization + 0 * t_init_motion;
+        out->odometry_initialization = t_initialization;
         out->odometry_try_register = summary.t_try_register;
         out->odometry_duration_sampling = summary.t_sampling;
         out->odometry_map_update = ms_since(t_before_map);

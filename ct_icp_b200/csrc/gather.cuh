@@ -135,7 +135,12 @@ __device__ __forceinline__ QueryCtx make_query(const V3 &q, double res, int lane
 // counts over the lanes); chunk c gives lane l the candidate with flat index 32 c + l, found by a 5-step binary
 // search over the prefix sums with shuffles. The loads of up to kPrefetch chunks are issued back to back before any
 // of them is consumed, so a keypoint pays ~one L2/HBM round trip for all its map points instead of one per voxel.
-constexpr int kPrefetch = 4;
+// (Bench map, K = 1237: a stencil holds 147 points on average, median 153, p99 301 — with 4 chunks = 128 points per
+// batch most keypoints need two batches; -DCTICP_PREFETCH=6 / 8 are experiment builds, tools/ab_variants.sh.)
+#ifndef CTICP_PREFETCH
+#define CTICP_PREFETCH 4
+#endif
+constexpr int kPrefetch = CTICP_PREFETCH;
 
 // (Outlining this function — one copy of the sort / merge network instead of one per unrolled call site, kernel 19.5k
 // instead of 23.1k instructions — was measured slower: GN loop 190.9 vs 186.0 us per frame.)

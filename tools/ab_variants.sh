@@ -9,11 +9,12 @@
 #   reducemlp   -DCTICP_REDUCE_MLP                    all partial rows of a warp in flight before the first add
 #   handoffmlp  -DCTICP_HANDOFF -DCTICP_REDUCE_MLP
 #   prune       -DCTICP_PRUNE                         drop candidates beyond the current k-th distance
+#   prefetch6/8 -DCTICP_PREFETCH=6 / 8                6 / 8 chunks (192 / 256 stencil points) in flight per load batch
 #   warps8      -DCTICP_GATHER_WARPS=8                the previous CTA shape (control)
 set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 VARIANTS=("handoff:-DCTICP_HANDOFF" "reducemlp:-DCTICP_REDUCE_MLP" "handoffmlp:-DCTICP_HANDOFF -DCTICP_REDUCE_MLP"
-          "prune:-DCTICP_PRUNE" "warps8:-DCTICP_GATHER_WARPS=8")
+          "prune:-DCTICP_PRUNE" "prefetch6:-DCTICP_PREFETCH=6" "prefetch8:-DCTICP_PREFETCH=8" "warps8:-DCTICP_GATHER_WARPS=8")
 case "${1:-}" in
 build)
     for v in "${VARIANTS[@]}"; do

@@ -323,6 +323,13 @@ __device__ __forceinline__ unsigned int handoff_load(const unsigned int *p) {
 __device__ __forceinline__ void handoff_store(unsigned int *p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// bounded poll (one thread per CTA): false after ~1 s, so a protocol error ends the kernel instead of hanging the GPU
+__device__ __forceinline__ bool handoff_wait(const unsigned int *p, unsigned int target) {
+    const long long t0 = clock64();
+    while (handoff_load(p) < target)
+        if (clock64() - t0 > 2000000000LL) return false;
+    return true;
+}
 #endif
 
 template <bool kPeers>
@@ -372,9 +379,9 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
     for (int it = 0; it < num_iters; ++it) {
 #ifdef CTICP_HANDOFF
         if (!solver_cta && it > 0) {   // wait until the solver CTA has published the pose of iteration it - 1
-            if (threadIdx.x == 0)
-                while (handoff_load(&st->handoff_epoch) < (unsigned int) it) {}
+            if (threadIdx.x == 0) s_peer_ok = handoff_wait(&st->handoff_epoch, (unsigned int) it);
             __syncthreads();
+            if (!s_peer_ok) break;   // timed out (the solver CTA flags the failure)
         }
 #endif
         if (__ldcg(&st->done)) break;   // uniform: written before the previous grid barrier
@@ -462,9 +469,15 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             __syncthreads();
             if (threadIdx.x == 0) atomicAdd(&st->handoff_arrive, 1u);
         } else {             // collect: all gather CTAs of this iteration have delivered
-            if (threadIdx.x == 0)
-                while (handoff_load(&st->handoff_arrive) < (unsigned int) gather_ctas * (unsigned int) (it + 1)) {}
+            if (threadIdx.x == 0) {
+                s_peer_ok = handoff_wait(&st->handoff_arrive, (unsigned int) gather_ctas * (unsigned int) (it + 1));
+                if (!s_peer_ok) {
+                    st->failed = 3;
+                    st->done = 1;
+                }
+            }
             __syncthreads();
+            if (!s_peer_ok) break;
         }
 #else
         grid.sync();

@@ -92,6 +92,7 @@ class Binding:
             "odometry_timer_stop": (C.c_int, [vp, P(dbl)]),
             "odometry_flush_l2": (C.c_int, [vp, sz]),
             "odometry_set_gather_timing": (C.c_int, [vp, C.c_int]),
+            "odometry_set_summary_points": (C.c_int, [vp, C.c_int]),
             "odometry_enable_sharding": (C.c_int, [vp, vp, C.c_int, C.c_int]),
             "odometry_sharding_mode": (C.c_int, [vp]),
             # oracle only (KAT taps)
@@ -105,6 +106,14 @@ class Binding:
             "se3_apply": (None, [vp, vp, vp, vp]),
             "ct_point_to_plane_residual": (dbl, [dbl, vp, vp, vp, dbl, vp, vp, vp, vp, vp]),
             "ct_residual": (dbl, [C.c_int, dbl, vp, vp, vp, vp, dbl, vp, vp, vp, vp, vp]),
+            "loss_evaluate": (None, [P(abi.IcpOptions), dbl, vp]),
+            "corrector": (None, [dbl, vp, P(dbl), P(dbl)]),
+            "quat_plus": (None, [vp, vp, vp]),
+            "lm_solve_plane_blocks": (None, [P(abi.IcpOptions), C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+            "quat_from_matrix": (None, [vp, vp]),
+            "quat_to_matrix": (None, [vp, vp]),
+            "symmetric_svd3": (None, [vp, vp, vp]),
+            "ldlt_solve12": (None, [vp, vp, vp]),
         }
         for name, (res, args) in sigs.items():
             if self.has(name):
@@ -385,6 +394,14 @@ class Odometry:
 
     def set_gather_timing(self, on):
         self.b.check(self.b.fn("odometry_set_gather_timing")(self.h, 1 if on else 0))
+
+    def set_summary_points(self, mask):
+        """bit POINTS_* set: every RegisterFrame produces that vector of the RegistrationSummary eagerly."""
+        self.b.check(self.b.fn("odometry_set_summary_points")(self.h, int(mask)))
+
+    def points_into(self, which, buf):
+        """one of the summary's point vectors into a caller-owned record array (abi.wpoint_dtype()); returns the count"""
+        return self.b.check(self.b.fn("odometry_get_points")(self.h, which, buf.ctypes.data, len(buf)))
 
     def points(self, which):
         cap = 1 << 16

@@ -376,6 +376,12 @@ int64_t cticp_odometry_get_points(cticp_odometry *h, int which, cticp_wpoint *ds
     });
     return rc < 0 ? rc : count;
 }
+int cticp_odometry_set_summary_points(cticp_odometry *h, int mask) {
+    return Guard([&] {
+        h->engine->SetSummaryPoints(mask);
+        return (int) CTICP_OK;
+    });
+}
 int64_t cticp_odometry_trajectory(cticp_odometry *h, cticp_frame *dst, size_t cap) {
     const auto &tr = h->engine->Trajectory();
     const size_t m = std::min(cap, tr.size());

@@ -117,6 +117,13 @@ Engine::~Engine() {
     for (auto &e : timer_ev_) cudaEventDestroy(e);
     for (auto &sc : staged_) cudaFree(sc.d_points);
     cudaFree(d_flush_);
+    for (int i = 0; i < 3; ++i) {
+        cudaFreeHost(h_world_[i]);
+        cudaFreeHost(h_src_[i]);
+    }
+    if (ev_egress_main_) cudaEventDestroy(ev_egress_main_);
+    if (ev_egress_done_) cudaEventDestroy(ev_egress_done_);
+    if (egress_stream_) cudaStreamDestroy(egress_stream_);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -133,8 +140,73 @@ void Engine::Reset() {   // odometry.cpp:956-965
     last_num_keypoints_ = 0;   // grid-size hint: keeps a reset run bit-identical to a fresh one
     last_all_world_valid_ = last_kp_world_valid_ = false;
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (egress_stream_) CT_CUDA_CHECK(cudaStreamSynchronize(egress_stream_));
+    egress_pending_ = false;
+    egress_valid_[0] = egress_valid_[1] = egress_valid_[2] = false;
     tail_event_valid_ = false;
     staging_in_flight_ = false;
+}
+
+void Engine::SetSummaryPoints(int mask) {
+    CT_CUDA_CHECK(cudaSetDevice(device_));
+    summary_points_mask_ = mask & 7;
+    if (summary_points_mask_) AllocEgress();
+}
+void Engine::AllocEgress() {
+    if (!egress_stream_) {
+        CT_CUDA_CHECK(cudaStreamCreateWithFlags(&egress_stream_, cudaStreamNonBlocking));
+        CT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_egress_main_, cudaEventDisableTiming));
+        CT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_egress_done_, cudaEventDisableTiming));
+    }
+    const size_t cap = pipe_->MaxPoints();
+    for (int i = 0; i < 3; ++i) {
+        if (!(summary_points_mask_ & (1 << i))) continue;
+        if (!h_world_[i]) CT_CUDA_CHECK(cudaMallocHost(&h_world_[i], sizeof(double) * 3 * cap));
+        if (i != CTICP_POINTS_ALL_CORRECTED && !h_src_[i]) CT_CUDA_CHECK(cudaMallocHost(&h_src_[i], sizeof(uint32_t) * cap));
+    }
+    if (summary_points_mask_ & (1 << CTICP_POINTS_ALL_CORRECTED)) pipe_->EnsureAllWorld();
+}
+
+// World coordinates of the summary's three vectors → pinned host memory, on the egress stream: the transforms of all N
+// points and of the keypoints run next to the map update of the main stream, the copies use the D2H engine. Called after
+// the main stream has been synchronised on the pose read-back (so everything the egress kernels read is complete) and
+// after TransformFrame was enqueued on the main stream (ev_egress_main_ orders the copy of d_frame_world behind it).
+void Engine::EnqueueEgress(const HostFrame &f, bool ran_icp) {
+    const Q4 qb = f.begin_pose.pose.q, qe = f.end_pose.pose.q;
+    const V3 tb = f.begin_pose.pose.t, te = f.end_pose.pose.t;
+    const size_t n_all = pipe_->n(), n_frame = (size_t) pipe_->h_counts()[1];
+    const size_t n_kp = ran_icp ? (size_t) pipe_->h_counts()[2] : 0;
+    cudaStream_t es = egress_stream_;
+    if (summary_points_mask_ & (1 << CTICP_POINTS_ALL_CORRECTED)) {
+        pipe_->TransformAll(qb, tb, qe, te, es);
+        CT_CUDA_CHECK(cudaMemcpyAsync(h_world_[1], pipe_->d_all_world(), sizeof(double) * 3 * n_all, cudaMemcpyDeviceToHost, es));
+        last_all_world_valid_ = true;
+        egress_valid_[1] = true;
+        egress_count_[1] = n_all;
+        timing_.d2h_bytes += sizeof(double) * 3 * n_all;
+    }
+    if ((summary_points_mask_ & (1 << CTICP_POINTS_KEYPOINTS))) {
+        if (n_kp) {
+            pipe_->TransformInto(pipe_->d_keypoints(), pipe_->d_count_keypoints(), qb, tb, qe, te, d_kp_world_, es);
+            CT_CUDA_CHECK(cudaMemcpyAsync(h_world_[2], d_kp_world_, sizeof(double) * 3 * n_kp, cudaMemcpyDeviceToHost, es));
+            CT_CUDA_CHECK(cudaMemcpyAsync(h_src_[2], pipe_->d_keypoints_src(), sizeof(uint32_t) * n_kp, cudaMemcpyDeviceToHost, es));
+            last_kp_world_valid_ = true;
+        }
+        egress_valid_[2] = true;
+        egress_count_[2] = n_kp;
+        timing_.d2h_bytes += (sizeof(double) * 3 + sizeof(uint32_t)) * n_kp;
+    }
+    if (summary_points_mask_ & (1 << CTICP_POINTS_CORRECTED)) {
+        CT_CUDA_CHECK(cudaEventRecord(ev_egress_main_, stream_));          // d_frame_world is written by the main stream
+        CT_CUDA_CHECK(cudaStreamWaitEvent(es, ev_egress_main_, 0));
+        CT_CUDA_CHECK(cudaMemcpyAsync(h_world_[0], pipe_->d_frame_world(), sizeof(double) * 3 * n_frame, cudaMemcpyDeviceToHost, es));
+        CT_CUDA_CHECK(cudaMemcpyAsync(h_src_[0], pipe_->d_frame_src(), sizeof(uint32_t) * n_frame, cudaMemcpyDeviceToHost, es));
+        egress_valid_[0] = true;
+        egress_count_[0] = n_frame;
+        timing_.d2h_bytes += (sizeof(double) * 3 + sizeof(uint32_t)) * n_frame;
+    }
+    CT_CUDA_CHECK(cudaEventRecord(ev_egress_done_, es));
+    egress_pending_ = true;
 }
 
 int64_t Engine::MapSize() {
@@ -746,6 +818,12 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     icp_->reset_timing();
     const int launches0 = map_->launches() + pipe_->launches() + icp_->launches();
     last_all_world_valid_ = last_kp_world_valid_ = false;
+    egress_valid_[0] = egress_valid_[1] = egress_valid_[2] = false;
+    if (egress_pending_) {   // the previous frame's egress still reads d_raw / d_frame_world / the keypoints
+        CT_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_egress_done_, 0));
+        egress_pending_ = false;
+    }
+    scan_in_staging_ = staged_slot < 0;
 
     // compute_frame_info, odometry.cpp:186-196
     FrameInfo info;
@@ -831,6 +909,13 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     if (!early_return) {
         const auto &f = summary.frame;
         pipe_->TransformFrame(f.begin_pose.pose.q, f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t);
+        if (summary_points_mask_) {
+            if (!ran_icp) {   // frame 0: no pose read-back has synchronised the stream yet; the egress reads N and F
+                CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+                staging_in_flight_ = false;
+            }
+            EnqueueEgress(f, ran_icp);
+        }
         ComputeSummaryMetrics(summary, k);
         UpdateMap(summary, k);
     }
@@ -943,6 +1028,37 @@ void Engine::ResolvePoints(int which, const float4 **out_pts, const double **out
 }
 
 int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
+    if (which >= 0 && which < 3 && egress_valid_[which] && scan_in_staging_) {
+        // eager path: the world coordinates (and source indices) are already on their way to pinned host memory; the raw
+        // coordinates and the alpha timestamps are still in the pinned staging buffer the scan was packed into
+        CT_CUDA_CHECK(cudaSetDevice(device_));
+        const size_t count = egress_count_[which];
+        const size_t m = std::min(cap, count);
+        if (m == 0 || !dst) return (int64_t) count;
+        CT_CUDA_CHECK(cudaEventSynchronize(ev_egress_done_));
+        const auto &f = last_frame_;
+        const double bts = f.begin_pose.dest_timestamp, ets = f.end_pose.dest_timestamp;
+        const double mn = std::min(bts, ets), mx = std::max(bts, ets);
+        const float4 *stage = pipe_->Staging();
+        const double *w = h_world_[which];
+        const uint32_t *src = which == CTICP_POINTS_ALL_CORRECTED ? nullptr : h_src_[which];
+        // frames 0 and 1: the sub-sampled frame (and its keypoints) carry timestamp := end_timestamp (odometry.cpp:355-359)
+        const bool override_t = src && last_info_.registered_fid <= 1;
+        const double t_override = mn + (double) (float) AlphaTimestamp(last_info_.end_timestamp, bts, ets) * (mx - mn);
+        const uint32_t frame_id = last_info_.frame_id;
+        pool_->ParallelFor(m, [&](size_t b, size_t e, int) {
+            for (size_t i = b; i < e; ++i) {
+                const float4 p = stage[src ? src[i] : i];
+                cticp_wpoint &o = dst[i];
+                o.raw[0] = p.x; o.raw[1] = p.y; o.raw[2] = p.z;
+                o.timestamp = override_t ? t_override : mn + (double) p.w * (mx - mn);
+                o.world[0] = w[3 * i]; o.world[1] = w[3 * i + 1]; o.world[2] = w[3 * i + 2];
+                o.index_frame = frame_id;
+                o._pad0 = 0;
+            }
+        });
+        return (int64_t) count;
+    }
     const float4 *d_pts = nullptr;
     const double *d_world = nullptr;
     size_t count = 0;

@@ -95,6 +95,9 @@ public:
     double TimerStop();
     void FlushL2(size_t bytes);
     int64_t GetPoints(int which, cticp_wpoint *dst, size_t cap);
+    // RegistrationSummary's point vectors (odometry.cpp:462-486,597) produced EAGERLY by every RegisterFrame: bit
+    // `which` of the mask (CTICP_POINTS_*) selects a vector. 0 (default): computed on demand by GetPoints / WritePoints.
+    void SetSummaryPoints(int mask);
     const std::vector<HostFrame> &Trajectory() const { return trajectory_; }
     int64_t MapSize();
     void Reset();
@@ -195,6 +198,19 @@ private:
     FrameInfo last_info_;
     bool last_all_world_valid_ = false, last_kp_world_valid_ = false;
     double *d_kp_world_ = nullptr;
+    // eager egress of the summary vectors: world coordinates (+ source indices) to pinned host memory on a second
+    // stream, overlapped with the map update; GetPoints assembles the 64-byte records on the host team
+    void EnqueueEgress(const HostFrame &f, bool ran_icp);
+    void AllocEgress();
+    int summary_points_mask_ = 0;
+    cudaStream_t egress_stream_ = nullptr;
+    cudaEvent_t ev_egress_main_ = nullptr, ev_egress_done_ = nullptr;
+    bool egress_pending_ = false;           // ev_egress_done_ recorded, next frame's upload must wait for it
+    bool egress_valid_[3] = {false, false, false};
+    size_t egress_count_[3] = {0, 0, 0};
+    double *h_world_[3] = {nullptr, nullptr, nullptr};   // pinned: corrected / all corrected / keypoints, xyz triples
+    uint32_t *h_src_[3] = {nullptr, nullptr, nullptr};   // pinned: index into the scan (corrected, keypoints)
+    bool scan_in_staging_ = false;          // the pinned staging buffer holds the last registered scan
     // timing
     cticp_device_timing timing_{};
     cudaEvent_t ev_[6];

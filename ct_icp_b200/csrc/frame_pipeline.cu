@@ -246,11 +246,12 @@ __global__ void k_clamp_count(int *d_n, int max_n) {
 }
 // world = ContinuousTransform(raw, begin, end, alpha) for every point (odometry.cpp:463-486)
 __global__ void k_transform_points(const float4 *__restrict__ pts, const int *__restrict__ d_n, Q4 qb, V3 tb, Q4 qe,
-                                   V3 te, double *__restrict__ world) {
+                                   V3 te, SlerpConsts sc, double *__restrict__ world) {
     const int n = *d_n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pts[i];
-        const V3 w = ct_transform(qb, tb, qe, te, (double) p.w, V3{(double) p.x, (double) p.y, (double) p.z});
+        // acos / 1/sin(theta) of the pose pair are hoisted (sc): two sin per point instead of acos + three sin
+        const V3 w = ct_transform_c(qb, tb, qe, te, (double) p.w, V3{(double) p.x, (double) p.y, (double) p.z}, sc);
         world[3 * i] = w.x; world[3 * i + 1] = w.y; world[3 * i + 2] = w.z;
     }
 }
@@ -419,21 +420,24 @@ void FramePipeline::QueueCountsReadback() {
 }
 
 void FramePipeline::TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te) {
-    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_counts_ + 1, qb, tb, qe, te, d_frame_world_);
+    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_counts_ + 1, qb, tb, qe, te, slerp_consts(qb, qe), d_frame_world_);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
 }
 
-void FramePipeline::TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te) {
+void FramePipeline::EnsureAllWorld() {
     if (!d_all_world_) CT_CUDA_CHECK(cudaMalloc(&d_all_world_, sizeof(double) * 3 * max_points_));
-    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(d_raw_, d_counts_ + 0, qb, tb, qe, te, d_all_world_);
+}
+void FramePipeline::TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te, cudaStream_t stream) {
+    EnsureAllWorld();
+    k_transform_points<<<Blocks(n_), 256, 0, stream ? stream : stream_>>>(d_raw_, d_counts_ + 0, qb, tb, qe, te, slerp_consts(qb, qe), d_all_world_);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
 }
 
 void FramePipeline::TransformInto(const float4 *pts, const int *d_n, const Q4 &qb, const V3 &tb, const Q4 &qe,
-                                  const V3 &te, double *d_world) {
-    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(pts, d_n, qb, tb, qe, te, d_world);
+                                  const V3 &te, double *d_world, cudaStream_t stream) {
+    k_transform_points<<<Blocks(n_), 256, 0, stream ? stream : stream_>>>(pts, d_n, qb, tb, qe, te, slerp_consts(qb, qe), d_world);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
 }

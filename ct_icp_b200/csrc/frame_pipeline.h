@@ -38,9 +38,11 @@ public:
                         size_t n_upper, float4 *out, uint32_t *out_src, int *d_n_out);
     // world points of the sub-sampled frame / of every input point with the final pose pair
     void TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
-    void TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
+    // (stream: nullptr = the pipeline's own; the egress of the summary vectors runs on a second stream)
+    void TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te, cudaStream_t stream = nullptr);
     void TransformInto(const float4 *pts, const int *d_n, const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te,
-                       double *d_world);
+                       double *d_world, cudaStream_t stream = nullptr);
+    void EnsureAllWorld();
 
     void QueueCountsReadback();   // h_counts()[0..2] = N, F, K after the next stream sync
     const int *h_counts() const { return h_counts_; }

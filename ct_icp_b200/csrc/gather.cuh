@@ -341,7 +341,7 @@ struct Eig3Full {
     V3 line, normal;        // eigenvectors of sv0 / sv2 (V.col(0), V.col(2))
 };
 
-__device__ __forceinline__ Eig3Full sym_eig3_full(double a00, double a01, double a02, double a11, double a12, double a22) {
+static __device__ __noinline__ Eig3Full sym_eig3_full(double a00, double a01, double a02, double a11, double a12, double a22) {
     double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
 #pragma unroll 1
     for (int sweep = 0; sweep < 12; ++sweep) {

@@ -1,0 +1,315 @@
+// gather_select.cuh — the ICP kernels' neighbor gather: one warp per query, k-nearest SELECTION without a sort.
+//
+// Replaces MultipleResolutionVoxelMap::RadiusSearchInPlace (include/ct_icp/map.h:449-514) + the sums of
+// TNeighborhood::ComputeNeighborhood (include/SlamCore/experimental/neighborhood.h:226-257) for the callers that only
+// need WHICH k neighbors are kept, their first and second moments, and the reference's points[0] (the farthest kept,
+// map.h:508-513) — i.e. the GN / CERES / ROBUST residual assembly (src/ct_icp/ct_icp.cpp:561-604, 753-857, 1229-1289).
+// (gather.cuh's warp_gather_knn keeps the SORTED variant for the ComputeNeighborhoods API entry points.)
+//
+// Round-1's kernel kept the k nearest in a register-resident sorted list with a bitonic sort/merge network over
+// shuffles: ~50 dependent compare-exchange steps (4 shuffles each) per keypoint, half of its ~2.9k warp instructions.
+// The order of the kept neighbors is never used by the residual assembly, so this version SELECTS instead:
+//   1. the stencil's points are read as one flattened list (prefix sum of the voxel counts; up to kSelPrefetch chunks of
+//      32 float4 loads in flight), distances in fp64, in-radius candidates compacted IN SCAN ORDER into shared memory;
+//   2. a 32-bucket histogram of d2 (bucket = floor(32 d2 / radius^2): monotone in d2, uniform for points on a surface
+//      through the query) gives, by one prefix sum over the lanes, the bucket x* that holds the k-th smallest; every
+//      candidate of a lower bucket is kept, and only the handful of candidates INSIDE x* are ranked exactly by
+//      (d2, scan order) — the reference's strict `<` replacement (map.h:495) keeps the earlier-scanned point on a tie;
+//   3. the kept candidates' first / second moments are accumulated per lane and reduced over the warp.
+// The result is the exact set the reference keeps. A stencil with more in-radius candidates than the staging area holds
+// is compacted to its k best (same selection) and pruned with the k-th distance from then on.
+#pragma once
+#include "gather.cuh"
+
+namespace cticp {
+
+constexpr int kSelCap = 192;       // staged in-radius candidates per warp (compaction when a batch might not fit)
+constexpr int kSelBuckets = 32;    // one histogram bucket per lane
+#ifndef CTICP_SEL_PREFETCH
+#define CTICP_SEL_PREFETCH 4
+#endif
+constexpr int kSelPrefetch = CTICP_SEL_PREFETCH;
+
+struct __align__(16) SelScratch {   // per-warp shared memory (6.5 KB)
+    double d2[kSelCap];             // SoA: lane i touches word i — no bank conflicts
+    double rx[kSelCap], ry[kSelCap], rz[kSelCap];   // candidate position relative to the query (fp64)
+    unsigned int hist[kSelBuckets];
+    unsigned char eidx[kSelCap];    // staged positions of the boundary bucket's candidates
+    unsigned char eflag[kSelCap];   // per staged position (boundary bucket only): 0 dropped, 1 kept, 2 kept & farthest
+    double far[4];                  // rel xyz, d2 of the farthest kept candidate (= reference points[0])
+};
+static_assert(kSelCap <= 256, "eidx is a byte");
+static_assert(kSelCap >= 32 * kSelPrefetch + 32, "a batch must fit next to the k kept candidates");
+
+struct NeighborSums {
+    int n;                                             // neighbors kept (min(kmax, in-radius candidates))
+    double sx, sy, sz, sxx, sxy, sxz, syy, syz, szz;   // Σ rel, Σ rel rel^T over the kept neighbors (query-centred)
+    double fx, fy, fz, fd2;                            // farthest kept neighbor: rel position, squared distance
+};
+
+__device__ __forceinline__ int sel_bucket(double d2, double scale) {
+    const int b = (int) (d2 * scale);
+    return b < kSelBuckets - 1 ? b : kSelBuckets - 1;
+}
+
+struct SelPlan {
+    int k_eff;   // neighbors to keep
+    int xstar;   // boundary bucket: lower buckets are kept whole
+};
+
+// Steps 2 of the header comment on the M staged candidates: fills S.eflag for the candidates of the boundary bucket.
+__device__ __forceinline__ SelPlan sel_plan(SelScratch &S, int M, int kmax, double scale, int lane) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    S.hist[lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < M; i += 32) atomicAdd(&S.hist[sel_bucket(S.d2[i], scale)], 1u);
+    __syncwarp();
+    const int h = (int) S.hist[lane];
+    int cum = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, cum, o);
+        if (lane >= o) cum += y;
+    }
+    SelPlan P;
+    P.k_eff = M < kmax ? M : kmax;
+    const unsigned ge = __ballot_sync(0xffffffffu, cum >= P.k_eff);   // non-zero: cum[31] = M >= k_eff
+    P.xstar = __ffs(ge) - 1;
+    const int c_less = __shfl_sync(0xffffffffu, cum - h, P.xstar);    // candidates in lower buckets
+    const int m = P.k_eff - c_less;                                   // to keep from the boundary bucket (>= 1)
+    // the boundary bucket's candidates, in scan order
+    int ne = 0;
+    for (int base = 0; base < M; base += 32) {
+        const int i = base + lane;
+        const bool is_e = i < M && sel_bucket(S.d2[i], scale) == P.xstar;
+        const unsigned mask = __ballot_sync(0xffffffffu, is_e);
+        if (is_e) S.eidx[ne + __popc(mask & lt_mask)] = (unsigned char) i;
+        ne += __popc(mask);
+    }
+    __syncwarp();
+    // exact rank inside the bucket by (d2, scan order): kept if rank < m, rank m-1 is the farthest kept
+    for (int t0 = 0; t0 < ne; t0 += 32) {
+        const int t = t0 + lane;
+        const int i = t < ne ? (int) S.eidx[t] : 0;
+        const double di = S.d2[i];
+        int rank = 0;
+        for (int u = 0; u < ne; ++u) {
+            const int j = (int) S.eidx[u];
+            const double dj = S.d2[j];
+            rank += (int) ((dj < di) | ((dj == di) & (j < i)));
+        }
+        if (t < ne) S.eflag[i] = (unsigned char) (rank < m ? (rank == m - 1 ? 2 : 1) : 0);
+    }
+    __syncwarp();
+    return P;
+}
+
+// Staging area full: keep only the k best (in scan order, at the front of the staging area); returns the new fill and
+// the prune threshold (the k-th distance: a later candidate at or beyond it can never be kept, map.h:495).
+__device__ __forceinline__ int sel_compact(SelScratch &S, int M, int kmax, double scale, int lane, double &prune_d2) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const SelPlan P = sel_plan(S, M, kmax, scale, lane);
+    int out = 0;
+    for (int base = 0; base < M; base += 32) {
+        const int i = base + lane;
+        double d = 0, x = 0, y = 0, z = 0;
+        bool kept = false;
+        if (i < M) {
+            d = S.d2[i]; x = S.rx[i]; y = S.ry[i]; z = S.rz[i];
+            const int b = sel_bucket(d, scale);
+            const int flag = b == P.xstar ? (int) S.eflag[i] : 0;
+            kept = b < P.xstar || flag != 0;
+            if (flag == 2) S.far[3] = d;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, kept);
+        __syncwarp();   // every lane has read its entry before any lane overwrites one
+        if (kept) {
+            const int o = out + __popc(mask & lt_mask);   // o <= i: never clobbers an unread entry of a later round
+            S.d2[o] = d; S.rx[o] = x; S.ry[o] = y; S.rz[o] = z;
+        }
+        out += __popc(mask);
+        __syncwarp();
+    }
+    if (out >= kmax) prune_d2 = S.far[3];
+    return out;
+}
+
+// One query, one warp. `origin_*`: all lanes pass the same query (world position q, its voxel kx ky kz).
+// need: callers ignore neighborhoods with fewer than `need` neighbors — the moments are then skipped (out.n is set).
+// kFilter: RadiusSearchInPlace with a sensor_location (map.h:482-490), `to_sensor` = sensor_location - query.
+template <bool kFilter>
+__device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double bucket_scale, const int *stencil,
+                                                 const V3 &q, int kx, int ky, int kz, int need, int lane,
+                                                 SelScratch &S, NeighborSums &out, unsigned &stencil_points,
+                                                 V3 to_sensor = V3{0, 0, 0}) {
+    const MapLevel &L = G.L;
+    const int side = 2 * G.r + 1;
+    const int nst = side * side * side;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int fill = 0;
+    unsigned pts_total = 0;
+    double prune_d2 = kKnnInf;
+
+    for (int base = 0; base < nst; base += 32) {
+        const int s = base + lane;
+        int slot = 0, cnt = 0;
+        double ox = 0, oy = 0, oz = 0;   // my voxel's origin relative to the query (fp64)
+        double sdn = 0;                  // kFilter: to_sensor . voxel normal
+        int has_normal = 0;
+        if (s < nst) {
+            int dx, dy, dz;
+            stencil_lookup(stencil, s, G.r, dx, dy, dz);
+            uint32_t c = 0;
+            const int found = map_find(L, pack_voxel(kx + dx, ky + dy, kz + dz), &c);
+            if (found >= 0) {
+                slot = found;
+                cnt = (int) c;
+                if (kFilter && L.normals && c > 0) {
+                    const double *nrm = L.normals + 4 * (size_t) found;
+                    if (nrm[3] != 0.0) {
+                        has_normal = 1;
+                        sdn = to_sensor.x * nrm[0] + to_sensor.y * nrm[1] + to_sensor.z * nrm[2];
+                    }
+                }
+            }
+            ox = (kx + dx) * L.res - q.x;
+            oy = (ky + dy) * L.res - q.y;
+            oz = (kz + dz) * L.res - q.z;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - cnt;
+        pts_total += (unsigned) total;
+
+        for (int c0 = 0; c0 < total; c0 += 32 * kSelPrefetch) {
+            // room for a whole batch (checked once per batch: one copy of the compaction code, off the common path)
+            if (fill + 32 * kSelPrefetch > kSelCap) fill = sel_compact(S, fill, G.kmax, bucket_scale, lane, prune_d2);
+            float4 pv[kSelPrefetch];
+            int owner[kSelPrefetch];
+            // phase 1: locate and issue every load of this batch
+#pragma unroll
+            for (int u = 0; u < kSelPrefetch; ++u) {
+                const int f = c0 + 32 * u + lane;   // flat candidate index
+                owner[u] = -1;
+                pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + 32 * u < total) {           // warp-uniform
+                    int lo = 0;                      // owner = last lane whose exclusive prefix is <= f
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int probe = lo + step;
+                        const int ex = __shfl_sync(0xffffffffu, excl, probe & 31);
+                        if (probe < 32 && ex <= f) lo = probe;
+                    }
+                    const int o_excl = __shfl_sync(0xffffffffu, excl, lo);
+                    const int o_slot = __shfl_sync(0xffffffffu, slot, lo);
+                    if (f < total) {
+                        owner[u] = lo;
+                        pv[u] = __ldg(L.points + (size_t) o_slot * L.B + (f - o_excl));
+                    }
+                }
+            }
+            // phase 2: distances, radius test, compaction (in scan order) into the staging area
+#pragma unroll
+            for (int u = 0; u < kSelPrefetch; ++u) {
+                if (c0 + 32 * u < total) {           // warp-uniform
+                    const int ol = owner[u] < 0 ? 0 : owner[u];
+                    const double vx = __shfl_sync(0xffffffffu, ox, ol), vy = __shfl_sync(0xffffffffu, oy, ol),
+                                 vz = __shfl_sync(0xffffffffu, oz, ol);
+                    const double rx = vx + (double) pv[u].x, ry = vy + (double) pv[u].y, rz = vz + (double) pv[u].z;
+                    const double d2 = rx * rx + ry * ry + rz * rz;
+                    bool in = owner[u] >= 0 && !(d2 > G.radius2) && d2 < prune_d2;
+                    if (kFilter) {
+                        const double vs = __shfl_sync(0xffffffffu, sdn, ol);
+                        const int vh = __shfl_sync(0xffffffffu, has_normal, ol);
+                        // this point's copy of the normal is -n when its w is negative
+                        const double scalar = signbit(pv[u].w) ? -vs : vs;
+                        if (vh && scalar < 0.0) in = false;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int o = fill + __popc(m & lt_mask);
+                        S.d2[o] = d2; S.rx[o] = rx; S.ry[o] = ry; S.rz[o] = rz;
+                    }
+                    fill += __popc(m);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    stencil_points = pts_total;
+    out.n = fill < G.kmax ? fill : G.kmax;
+    if (out.n < need || fill == 0) return;
+
+    const SelPlan P = sel_plan(S, fill, G.kmax, bucket_scale, lane);
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int base = 0; base < fill; base += 32) {
+        const int i = base + lane;
+        if (i < fill) {
+            const double d = S.d2[i];
+            const int b = sel_bucket(d, bucket_scale);
+            const int flag = b == P.xstar ? (int) S.eflag[i] : 0;
+            if (b < P.xstar || flag != 0) {
+                const double x = S.rx[i], y = S.ry[i], z = S.rz[i];
+                a[0] += x; a[1] += y; a[2] += z;
+                a[3] += x * x; a[4] += x * y; a[5] += x * z;
+                a[6] += y * y; a[7] += y * z; a[8] += z * z;
+                if (flag == 2) { S.far[0] = x; S.far[1] = y; S.far[2] = z; S.far[3] = d; }
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 9; ++v) a[v] = warp_sum(a[v]);
+    __syncwarp();
+    out.sx = a[0]; out.sy = a[1]; out.sz = a[2];
+    out.sxx = a[3]; out.sxy = a[4]; out.sxz = a[5];
+    out.syy = a[6]; out.syz = a[7]; out.szz = a[8];
+    out.fx = S.far[0]; out.fy = S.far[1]; out.fz = S.far[2]; out.fd2 = S.far[3];
+    __syncwarp();   // S.far is read before the next query's selection rewrites it
+}
+
+// TNeighborhood::ComputeNeighborhood + ComputeNeighborhoodInfo (neighborhood.h:226-257, 286-316) from the moments: one
+// THREAD per neighborhood (the epilogue of a tile of queries runs lane-per-query).
+__device__ __forceinline__ NeighborhoodDesc describe_from_sums(const NeighborSums &s) {
+    const double inv = 1.0 / (double) s.n;
+    const double mx = s.sx * inv, my = s.sy * inv, mz = s.sz * inv;
+    const Eig3 e = sym_eig3_fast(s.sxx * inv - mx * mx, s.sxy * inv - mx * my, s.sxz * inv - mx * mz,
+                                 s.syy * inv - my * my, s.syz * inv - my * mz, s.szz * inv - mz * mz);
+    NeighborhoodDesc d;
+    d.normal = e.normal;
+    d.a2D = (sqrt(e.sv1) - sqrt(e.sv2)) / sqrt(e.sv0);
+    d.far_rel = V3{s.fx, s.fy, s.fz};
+    d.far_d2 = s.fd2;
+    return d;
+}
+__device__ __forceinline__ NeighborhoodDescFull describe_full_from_sums(const NeighborSums &s) {
+    const double inv = 1.0 / (double) s.n;
+    const double mx = s.sx * inv, my = s.sy * inv, mz = s.sz * inv;
+    NeighborhoodDescFull d;
+    d.cov[0] = s.sxx * inv - mx * mx;
+    d.cov[1] = s.sxy * inv - mx * my;
+    d.cov[2] = s.sxz * inv - mx * mz;
+    d.cov[3] = s.syy * inv - my * my;
+    d.cov[4] = s.syz * inv - my * mz;
+    d.cov[5] = s.szz * inv - mz * mz;
+    const Eig3Full e = sym_eig3_full(d.cov[0], d.cov[1], d.cov[2], d.cov[3], d.cov[4], d.cov[5]);
+    d.normal = e.normal;
+    d.line = e.line;
+    d.linearity = (e.sv0 - e.sv1) / e.sv0;
+    d.planarity = (e.sv1 - e.sv2) / e.sv0;
+    d.mean_rel = V3{mx, my, mz};
+    d.far_rel = V3{s.fx, s.fy, s.fz};
+    return d;
+}
+
+// lane `src`'s copy of the sums to every lane's registers is not needed: the tile loops keep the result of query j in
+// lane j only (all lanes hold the same totals after the warp reductions).
+__device__ __forceinline__ void sums_keep_if(bool mine, NeighborSums &dst, const NeighborSums &src) {
+    if (mine) dst = src;
+}
+
+}  // namespace cticp

@@ -33,12 +33,6 @@ struct IcpState {
     int slerp_linear, slerp_negate;
     unsigned long long stat_keypoint_iters, stat_stencil_points;
     unsigned long long dbg_t[4];   // %globaltimer stamps of the last iteration: CTA0 start, last-CTA elected, reduced, solved
-#ifdef CTICP_HANDOFF
-    // experiment build: point-to-point hand-off between the gather CTAs and the solver CTA of k_gn_persistent instead
-    // of two grid-wide barriers per iteration (zeroed with the rest of the state before every launch)
-    unsigned int handoff_arrive;   // gather CTAs that delivered their partial row (monotonic over the iterations)
-    unsigned int handoff_epoch;    // iterations whose pose update the solver CTA has published
-#endif
 };
 
 inline void icp_state_refresh_slerp(IcpState &S) {
@@ -66,6 +60,7 @@ struct GnParams {
     double threshold_norm;      // threshold_orientation_norm (GN stop criterion on ‖x‖, ct_icp.cpp:978)
     int shard_rank, shard_world;   // keypoint sharding (multi-GPU); 0/1 when single
     int debug_flags;               // profiling only (env CTICP_DEBUG_FLAGS): 1 = skip the solve, 2 = skip the gather work
+    double bucket_scale;           // 32 / radius^2: d2 → histogram bucket of the k-nearest selection (gather_select.cuh)
 };
 
 class IcpSolver {
@@ -141,6 +136,7 @@ private:
     int ev_used_ = 0;
     int num_sms_ = 148;
     int max_coresident_[2] = {0, 0};   // k_gn_persistent<false / true>
+    int kp_per_cta_ = 8;               // keypoints per gather CTA below which the persistent grid is not widened further
     bool use_persistent_ = true;
     PeerLinksHost links_host_;
     bool peers_ready_ = false;

@@ -10,7 +10,7 @@
 
 #include <cooperative_groups.h>
 
-#include "gather.cuh"
+#include "gather_select.cuh"
 #include "icp.h"
 #include "peer_exchange.cuh"
 #include "small_solve.cuh"
@@ -60,7 +60,7 @@ __device__ __forceinline__ M3 euler_from_sincos(double sa, double ca, double sb,
 
 // One warp: accumulator (96 doubles in `acc`) → normal equations → GN step → pose update (ct_icp.cpp:860-980).
 // mode 0: full step. mode 1: only emit the linear system into sys_out (debug tap).
-__device__ void warp_gn_solve(const double *acc, SolveScratch &S, IcpState *st, const GnParams &P, int mode,
+__device__ __noinline__ void warp_gn_solve(const double *acc, SolveScratch &S, IcpState *st, const GnParams &P, int mode,
                               double *sys_out, int lane) {
     const int n_used = (int) (acc[kAccUsed] + 0.5);
     if (lane == 0) {
@@ -140,403 +140,357 @@ __device__ void warp_gn_solve(const double *acc, SolveScratch &S, IcpState *st, 
     }
 }
 
-// mode 0: gather + (last CTA) reduce + solve + pose update          [single GPU: ONE launch per ICP iteration]
+// ---- the gather half of an iteration: tiles of keypoints per warp --------------------------------------------------
+// A warp owns a TILE of W consecutive keypoints (W = ceil(K / warps in the grid), at most 32: one keypoint per warp
+// while the grid has spare warps — the loop is then bound by the latency of one keypoint —, several when K exceeds the
+// grid, where throughput counts). Per tile:
+//   A  lane j < W : keypoint j's world position from the pose pair (slerp: two sin, one rsqrt) and its voxel (three
+//                   fp64 divisions)                                                  [once per keypoint, not per lane]
+//   B  all lanes  : for j = 0..W-1 the warp-cooperative gather + selection of gather_select.cuh; lane j keeps the moments
+//   C  lane j < W : covariance → closed-form eigen → normal, a2D, residual, 12-vector Jacobian row
+//   D  all lanes  : the rows of the tile (through shared memory) into the 90 accumulators, three per lane.
+// Round 1 ran A and C redundantly on all 32 lanes of the warp for every keypoint (~1.5k of its ~2.9k warp instructions
+// per keypoint-iteration); here they cost 1/W of that.
+struct GnPose {
+    Q4 qb, qe;
+    V3 tb, te;
+    SlerpConsts sc;
+};
+struct GnWarpAcc {
+    double a0 = 0, a1 = 0, a2 = 0;   // entries lane, lane+32, lane+64 of [A upper | b]
+    double sum_sq = 0;               // per-lane partial counters from here on
+    unsigned n_stencil = 0;
+    int n_used = 0, n_kp = 0, n_valid = 0;
+};
+
+constexpr int kTileMax = 16;   // keypoints per warp tile (phases A / C cost 1/W per keypoint: 16 is deep in the flat part)
+
+// Per-warp shared memory of a tile: the gather's staging area, the moments of each keypoint of the tile (phase B hands
+// them to phase C through here instead of through 27 registers that would stay live across the gather), and the tile's
+// Jacobian rows.
+struct __align__(16) TileScratch {
+    SelScratch sel;
+    double sums[kTileMax][14];   // NeighborSums of keypoint j: n, stencil points, s*, f*
+    double rows[kTileMax][13];   // u[0..11], -scalar
+};
+
+__device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const int *stencil,
+                                                const float4 *__restrict__ keypoints, int lo, int hi, int warp_global,
+                                                int warps_total, const GnPose &pose, TileScratch &T, int lane,
+                                                GnWarpAcc &A) {
+    const GatherConfig &G = cfg.G;
+    const GnParams &P = cfg.P;
+    const int span = hi - lo;
+    if (span <= 0) return;
+    int W = (span + warps_total - 1) / warps_total;
+    W = W < kTileMax ? W : kTileMax;
+    const int need = P.kmin > 5 ? P.kmin : 5;   // ct_icp.cpp:769 ; neighborhood.h:227
+    const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+    const int pi0 = c_pair_i[i0], pj0 = c_pair_j[i0], pi1 = c_pair_i[i1], pj1 = c_pair_j[i1];
+    const int pi2 = i2 < kAccUsed ? c_pair_i[i2] : 0, pj2 = i2 < kAccUsed ? c_pair_j[i2] : 0;
+
+    for (int t0 = lo + warp_global * W; t0 < hi; t0 += warps_total * W) {
+        const int wt = (hi - t0) < W ? (hi - t0) : W;
+        // ---- A: world_kpts[i] = InterpolatePose(begin, end, t_i) * raw_i  (ct_icp.cpp:964-966, types.h:361-366)
+        V3 p{0, 0, 0};
+        int kx = 0, ky = 0, kz = 0;
+        if (lane < wt) {
+            const float4 kraw = __ldg(keypoints + t0 + lane);   // raw xyz (sensor frame) + alpha timestamp
+            p = ct_transform_c(pose.qb, pose.tb, pose.qe, pose.te, (double) kraw.w,
+                               V3{(double) kraw.x, (double) kraw.y, (double) kraw.z}, pose.sc);
+            kx = voxel_coord(p.x, G.L.res);
+            ky = voxel_coord(p.y, G.L.res);
+            kz = voxel_coord(p.z, G.L.res);
+        }
+        // ---- B
+        for (int j = 0; j < wt; ++j) {
+            const V3 q{__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j)};
+            const int qx = __shfl_sync(0xffffffffu, kx, j), qy = __shfl_sync(0xffffffffu, ky, j),
+                      qz = __shfl_sync(0xffffffffu, kz, j);
+            NeighborSums s;
+            unsigned spts = 0;
+            warp_gather_sums<false>(G, P.bucket_scale, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts);
+            if (lane == 0) {
+                double *o = T.sums[j];
+                o[0] = (double) s.n; o[1] = (double) spts;
+                if (s.n >= need) {
+                    o[2] = s.sx; o[3] = s.sy; o[4] = s.sz;
+                    o[5] = s.sxx; o[6] = s.sxy; o[7] = s.sxz; o[8] = s.syy; o[9] = s.syz; o[10] = s.szz;
+                    o[11] = s.fx; o[12] = s.fy; o[13] = s.fz;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- C (ct_icp.cpp:769-850)
+        bool used = false;
+        if (lane < wt) {
+            const double *o = T.sums[lane];
+            NeighborSums mine;
+            mine.n = (int) o[0];
+            A.n_kp += 1;
+            A.n_stencil += (unsigned) o[1];
+            if (mine.n >= need) {
+                A.n_valid += 1;
+                mine.sx = o[2]; mine.sy = o[3]; mine.sz = o[4];
+                mine.sxx = o[5]; mine.sxy = o[6]; mine.sxz = o[7]; mine.syy = o[8]; mine.syz = o[9]; mine.szz = o[10];
+                mine.fx = o[11]; mine.fy = o[12]; mine.fz = o[13]; mine.fd2 = 0;
+                const NeighborhoodDesc nd = describe_from_sums(mine);
+                V3 normal = nd.normal;
+                // orient towards the sensor position at frame begin (:782-784)
+                if (dot(normal, pose.tb - p) < 0) normal = -1.0 * normal;
+                const double weight = nd.a2D * nd.a2D;                       // :787-788
+                // p - closest_point, closest_point = points[0] = farthest kept (:791)
+                const V3 diff{-nd.far_rel.x, -nd.far_rel.y, -nd.far_rel.z};
+                const double dist_to_plane = dot(normal, diff);
+                if (fabs(dist_to_plane) < P.max_dist_to_plane) {              // :803
+                    const V3 nw = weight * normal;
+                    const double scalar = dot(nw, diff);
+                    const float4 kraw = __ldg(keypoints + t0 + lane);
+                    const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+                    const V3 ob = qrot(pose.qb, raw), oe = qrot(pose.qe, raw);   // :813-816
+                    const double a = (double) kraw.w, am = 1.0 - a;
+                    const V3 cb = cross(ob, nw), ce = cross(oe, nw);
+                    double *u = T.rows[lane];
+                    u[0] = am * cb.x; u[1] = am * cb.y; u[2] = am * cb.z;
+                    u[3] = am * nw.x; u[4] = am * nw.y; u[5] = am * nw.z;
+                    u[6] = a * ce.x;  u[7] = a * ce.y;  u[8] = a * ce.z;
+                    u[9] = a * nw.x;  u[10] = a * nw.y; u[11] = a * nw.z;
+                    u[12] = -scalar;   // b -= u * scalar (:849)
+                    used = true;
+                    A.n_used += 1;
+                    A.sum_sq += scalar * scalar;
+                }
+            }
+        }
+        // ---- D: A += u u^T, b -= u scalar, in keypoint order (deterministic)
+        unsigned mask = __ballot_sync(0xffffffffu, used);
+        __syncwarp();
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const double *u = T.rows[j];
+            A.a0 += u[pi0] * u[pj0];
+            A.a1 += u[pi1] * u[pj1];
+            if (i2 < kAccUsed) A.a2 += u[pi2] * u[pj2];
+        }
+        __syncwarp();   // the rows are consumed before the next tile rewrites them
+    }
+}
+
+// per-warp accumulators → one row of `kAcc` doubles per warp in shared memory (counters reduced over the lanes)
+__device__ __forceinline__ void gn_store_warp_row(double *row, const GnWarpAcc &A, int lane) {
+    row[lane] = A.a0;
+    row[lane + 32] = A.a1;
+    if (lane + 64 < kAccUsed) row[lane + 64] = A.a2;
+    const double sum_sq = warp_sum(A.sum_sq);
+    const unsigned n_stencil = __reduce_add_sync(0xffffffffu, A.n_stencil);
+    const int n_used = __reduce_add_sync(0xffffffffu, A.n_used), n_kp = __reduce_add_sync(0xffffffffu, A.n_kp),
+              n_valid = __reduce_add_sync(0xffffffffu, A.n_valid);
+    if (lane == 0) {
+        row[kAccUsed] = (double) n_used;
+        row[kAccSumSq] = sum_sq;
+        row[kAccStencil] = (double) n_stencil;
+        row[kAccKeypoints] = (double) n_kp;
+        row[kAccValidNb] = (double) n_valid;
+        row[95] = 0;
+    }
+}
+
+// shared memory of the GN kernels (dynamic: the staging areas alone are 70 KB)
+struct GnShared {
+    TileScratch tile[kGatherWarps];
+    GnPose pose;
+    double acc[kGatherWarps][kAcc];
+    int stencil[kMaxStencil];
+    SolveScratch solve;
+    IcpState dummy;
+    int flag;
+};
+
+// deterministic reduction of `rows` partial rows by one CTA: warp g sums the rows b = g (mod kGatherWarps), three
+// columns per lane, all of a warp's loads in flight before the first add; then the per-warp sums in fixed order.
+// Result in sh.acc[0][0..kAcc). Called by all threads.
+__device__ __forceinline__ void gn_reduce_rows(GnShared &sh, const double *__restrict__ partials, int rows, int lane, int w) {
+    constexpr int kInFlight = 10;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int b0 = w; b0 < rows; b0 += kGatherWarps * kInFlight) {
+        double v0[kInFlight], v1[kInFlight], v2[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const int b = b0 + u * kGatherWarps;
+            v0[u] = v1[u] = v2[u] = 0.0;
+            if (b < rows) {
+                const double *row = partials + (size_t) b * kAcc;
+                v0[u] = __ldcg(row + lane);
+                v1[u] = __ldcg(row + lane + 32);
+                v2[u] = __ldcg(row + lane + 64);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+            if (b0 + u * kGatherWarps < rows) {
+                a0 += v0[u];
+                a1 += v1[u];
+                a2 += v2[u];
+            }
+    }
+    __syncthreads();
+    sh.acc[w][lane] = a0;
+    sh.acc[w][lane + 32] = a1;
+    sh.acc[w][lane + 64] = a2;
+    __syncthreads();
+    double sum = 0;
+    if (threadIdx.x < kAcc) {
+#pragma unroll
+        for (int ww = 0; ww < kGatherWarps; ++ww) sum += sh.acc[ww][threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x < kAcc) sh.acc[0][threadIdx.x] = sum;
+    __syncthreads();
+}
+
+__device__ __forceinline__ GnPose load_pose(const IcpState *st) {
+    GnPose p;
+    p.qb = Q4{__ldcg(&st->qb[0]), __ldcg(&st->qb[1]), __ldcg(&st->qb[2]), __ldcg(&st->qb[3])};
+    p.qe = Q4{__ldcg(&st->qe[0]), __ldcg(&st->qe[1]), __ldcg(&st->qe[2]), __ldcg(&st->qe[3])};
+    p.tb = V3{__ldcg(&st->tb[0]), __ldcg(&st->tb[1]), __ldcg(&st->tb[2])};
+    p.te = V3{__ldcg(&st->te[0]), __ldcg(&st->te[1]), __ldcg(&st->te[2])};
+    p.sc = SlerpConsts{__ldcg(&st->slerp_theta), __ldcg(&st->slerp_inv_sin), __ldcg(&st->slerp_linear), __ldcg(&st->slerp_negate)};
+    return p;
+}
+
+extern __shared__ __align__(16) unsigned char gn_smem_raw[];
+
+// mode 0: gather + (last CTA) reduce + solve + pose update          [one launch per ICP iteration]
 // mode 1: gather + (last CTA) reduce + emit linear system to sys_out [debug tap]
-// mode 2: gather + (last CTA) reduce into acc_out                    [multi-GPU: all-reduce then k_gn_solve_acc]
-__global__ void __launch_bounds__(kGatherWarps * 32)
+// mode 2: gather + (last CTA) reduce into acc_out                    [multi-GPU over NCCL: all-reduce then k_gn_solve_acc]
+__global__ void __launch_bounds__(kGatherWarps * 32, 1)
 k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
              IcpState *st, double *__restrict__ partials, unsigned int *ticket, int mode, double *acc_out,
              double *sys_out) {
-    __shared__ KnnStage s_stage[kGatherWarps][64];
-    __shared__ double s_u[kGatherWarps][16];
-    __shared__ double s_acc[kGatherWarps][kAcc];
-    __shared__ int s_stencil[kMaxStencil];
-    __shared__ SolveScratch s_solve;
-    __shared__ int s_last;
+    GnShared &sh = *reinterpret_cast<GnShared *>(gn_smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const GatherConfig &G = cfg.G;
     const GnParams &P = cfg.P;
-
-    double acc0 = 0, acc1 = 0, acc2 = 0;              // entries lane, lane+32, lane+64 of [A upper | b]
-    double n_used = 0, sum_sq = 0, n_stencil = 0, n_kp = 0, n_valid = 0;
     const bool active = (mode == 1) || !st->done;
     CT_STAMP(if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg_t[0] = global_timer_ns();)
 
+    GnWarpAcc A;
     if (active) {
-        const int *stencil = stencil_table_fill(s_stencil, G.r);
+        const int *stencil = stencil_table_fill(sh.stencil, cfg.G.r);
+        if (threadIdx.x == 0) sh.pose = load_pose(st);
         __syncthreads();
-        const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
-        const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
-        const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
+        const GnPose &pose = sh.pose;
         const int K = *d_num_keypoints;
         const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
         const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-        const int warps_total = gridDim.x * kGatherWarps;
-        const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
-        const int pi0 = c_pair_i[i0], pj0 = c_pair_j[i0], pi1 = c_pair_i[i1], pj1 = c_pair_j[i1];
-        const int pi2 = i2 < kAccUsed ? c_pair_i[i2] : 0, pj2 = i2 < kAccUsed ? c_pair_j[i2] : 0;
-
-        for (int kp = lo + blockIdx.x * kGatherWarps + w; kp < hi; kp += warps_total) {
-            const float4 kraw = __ldg(keypoints + kp);   // raw xyz (sensor frame) + alpha timestamp
-            const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
-            const double alpha = (double) kraw.w;
-            // world_kpts[i] = InterpolatePose(begin, end, t_i) * raw_i  (ct_icp.cpp:964-966, types.h:361-366)
-            const V3 p = ct_transform_c(qb, tb, qe, te, alpha, raw, sc);
-            const QueryCtx ctx = make_query(p, G.L.res, lane);
-
-            KnnEntry best;
-            unsigned spts = 0;
-            const int n = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
-            n_kp += 1;
-            n_stencil += (double) spts;
-            if (n < P.kmin || n < 5) continue;   // ct_icp.cpp:769 ; neighborhood.h:227
-            n_valid += 1;
-
-            const NeighborhoodDesc nd = warp_describe(G, stencil, ctx, best, n, lane);
-            V3 normal = nd.normal;
-            // orient towards the sensor position at frame begin (ct_icp.cpp:782-784)
-            if (dot(normal, tb - p) < 0) normal = -1.0 * normal;
-            const double weight = nd.a2D * nd.a2D;                     // :787-788
-            // p - closest_point, closest_point = points[0] = farthest kept (:791)
-            const V3 diff{-nd.far_rel.x, -nd.far_rel.y, -nd.far_rel.z};
-            const double dist_to_plane = dot(normal, diff);
-            if (!(fabs(dist_to_plane) < P.max_dist_to_plane)) continue;   // :803
-            const V3 nw = weight * normal;
-            const double scalar = dot(nw, diff);
-
-            if (lane == 0) {
-                const V3 ob = qrot(qb, raw), oe = qrot(qe, raw);         // :813-816
-                const double am = 1.0 - alpha, a = alpha;
-                const V3 cb = cross(ob, nw), ce = cross(oe, nw);
-                double *u = s_u[w];
-                u[0] = am * cb.x; u[1] = am * cb.y; u[2] = am * cb.z;
-                u[3] = am * nw.x; u[4] = am * nw.y; u[5] = am * nw.z;
-                u[6] = a * ce.x;  u[7] = a * ce.y;  u[8] = a * ce.z;
-                u[9] = a * nw.x;  u[10] = a * nw.y; u[11] = a * nw.z;
-                u[12] = -scalar;   // b -= u * scalar (:849)
-            }
-            __syncwarp();
-            {
-                const double *u = s_u[w];
-                acc0 += u[pi0] * u[pj0];
-                acc1 += u[pi1] * u[pj1];
-                if (i2 < kAccUsed) acc2 += u[pi2] * u[pj2];
-            }
-            __syncwarp();
-            n_used += 1;
-            sum_sq += scalar * scalar;
-        }
+        gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gridDim.x + blockIdx.x, gridDim.x * kGatherWarps, pose,
+                        sh.tile[w], lane, A);
     }
-
     // block reduction (fixed order → run-to-run deterministic)
-    s_acc[w][lane] = acc0;
-    s_acc[w][lane + 32] = acc1;
-    s_acc[w][lane + 64] = acc2;
-    if (lane == 0) {
-        s_acc[w][kAccUsed] = n_used;
-        s_acc[w][kAccSumSq] = sum_sq;
-        s_acc[w][kAccStencil] = n_stencil;
-        s_acc[w][kAccKeypoints] = n_kp;
-        s_acc[w][kAccValidNb] = n_valid;
-        s_acc[w][95] = 0;
-    }
+    gn_store_warp_row(sh.acc[w], A, lane);
     __syncthreads();
     if (threadIdx.x < kAcc) {
         double s = 0;
 #pragma unroll
-        for (int ww = 0; ww < kGatherWarps; ++ww) s += s_acc[ww][threadIdx.x];
+        for (int ww = 0; ww < kGatherWarps; ++ww) s += sh.acc[ww][threadIdx.x];
         partials[(size_t) blockIdx.x * kAcc + threadIdx.x] = s;
     }
     // ---- last CTA to finish reduces the partials (fixed order) and takes the Gauss-Newton step -----------------
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) sh.flag = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (!s_last) return;
+    if (!sh.flag) return;
     __threadfence();
     if (threadIdx.x == 0) {
         *ticket = 0;
         CT_STAMP(st->dbg_t[1] = global_timer_ns();)
     }
     if (!active) return;
-    double *acc = &s_acc[0][0];
-    {
-        // deterministic reduction: warp g sums rows b = g (mod 4) of three columns per lane; fixed-order combine
-        double a0 = 0, a1 = 0, a2 = 0;
-        const int nb = gridDim.x;
-        for (int b = w; b < nb; b += kGatherWarps) {
-            const double *row = partials + (size_t) b * kAcc;
-            a0 += __ldcg(row + lane);
-            a1 += __ldcg(row + lane + 32);
-            a2 += __ldcg(row + lane + 64);
-        }
-        __syncthreads();
-        s_acc[w][lane] = a0;
-        s_acc[w][lane + 32] = a1;
-        s_acc[w][lane + 64] = a2;
-        __syncthreads();
-        double sum = 0;
-        if (threadIdx.x < kAcc) {
-#pragma unroll
-            for (int ww = 0; ww < kGatherWarps; ++ww) sum += s_acc[ww][threadIdx.x];
-        }
-        __syncthreads();
-        if (threadIdx.x < kAcc) {
-            acc[threadIdx.x] = sum;
-            if (mode == 2) acc_out[threadIdx.x] = sum;
-        }
-    }
-    __syncthreads();
+    gn_reduce_rows(sh, partials, (int) gridDim.x, lane, w);
+    if (mode == 2 && threadIdx.x < kAcc) acc_out[threadIdx.x] = sh.acc[0][threadIdx.x];
     CT_STAMP(if (threadIdx.x == 0) st->dbg_t[2] = global_timer_ns();)
     if (mode == 2 || w != 0) return;
-    warp_gn_solve(acc, s_solve, st, P, mode, sys_out, lane);
+    warp_gn_solve(sh.acc[0], sh.solve, st, P, mode, sys_out, lane);
     CT_STAMP(if (lane == 0) st->dbg_t[3] = global_timer_ns();)
 }
 
 // ---- persistent variant: the WHOLE Gauss-Newton loop in one cooperative launch --------------------------------
 // CTA 0 is the solver CTA (deterministic reduction of the partials + 12x12 solve + pose update, by the same warp on
-// the same SM every iteration, so its instructions stay in that SM's instruction cache: executed cold, the ~1.5k
-// instructions of the serial tail cost ~45 us per iteration, warm ~8 us); CTAs 1..G gather. Two grid-wide barriers
-// per iteration replace two kernel launches. While the gather CTAs work on iteration 0, the solver warp runs the
-// solve once on a dummy system to pull its code into the instruction cache.
-__device__ __forceinline__ void load_state_volatile(const IcpState *st, Q4 &qb, V3 &tb, Q4 &qe, V3 &te, SlerpConsts &sc) {
-    qb = Q4{__ldcg(&st->qb[0]), __ldcg(&st->qb[1]), __ldcg(&st->qb[2]), __ldcg(&st->qb[3])};
-    qe = Q4{__ldcg(&st->qe[0]), __ldcg(&st->qe[1]), __ldcg(&st->qe[2]), __ldcg(&st->qe[3])};
-    tb = V3{__ldcg(&st->tb[0]), __ldcg(&st->tb[1]), __ldcg(&st->tb[2])};
-    te = V3{__ldcg(&st->te[0]), __ldcg(&st->te[1]), __ldcg(&st->te[2])};
-    sc = SlerpConsts{__ldcg(&st->slerp_theta), __ldcg(&st->slerp_inv_sin), __ldcg(&st->slerp_linear), __ldcg(&st->slerp_negate)};
-}
-
+// the same SM every iteration, so its instructions stay in that SM's instruction cache: executed cold, the serial tail
+// costs tens of microseconds per iteration, warm a few); CTAs 1..G gather. Two grid-wide barriers per iteration replace
+// two kernel launches. While the gather CTAs work on iteration 0, the solver warp runs the solve once on a dummy system
+// to pull its code into the instruction cache.
 //
 // kPeers (multi-GPU, keypoints sharded): between its reduction and its solve the solver CTA exchanges the accumulator
 // with the other ranks' solver CTAs through NVLink peer memory (peer_exchange.cuh) — the all-reduce of SURVEY §8e
 // happens INSIDE the loop, so the sharded loop is still one launch and costs one NVLink round trip per iteration.
-#ifdef CTICP_HANDOFF
-// Experiment (-DCTICP_HANDOFF, to be measured): the two grid-wide barriers of an iteration become two one-directional
-// hand-offs — gather CTAs → solver CTA through an arrive counter (only the solver polls it), solver CTA → gather CTAs
-// through an epoch word (one thread per gather CTA polls it, the rest of the CTA waits at a hardware barrier).
-__device__ __forceinline__ unsigned int handoff_load(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void handoff_store(unsigned int *p, unsigned int v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// bounded poll (one thread per CTA): false after ~1 s, so a protocol error ends the kernel instead of hanging the GPU
-__device__ __forceinline__ bool handoff_wait(const unsigned int *p, unsigned int target) {
-    const long long t0 = clock64();
-    while (handoff_load(p) < target)
-        if (clock64() - t0 > 2000000000LL) return false;
-    return true;
-}
-#endif
-
 template <bool kPeers>
-__global__ void __launch_bounds__(kGatherWarps * 32)
+__global__ void __launch_bounds__(kGatherWarps * 32, 1)
 k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
                 IcpState *st, double *__restrict__ partials, int num_iters, PeerLinks links) {
-    // Measured alternatives (config 2, 5 iterations, ICP ms): this design 0.180; arrive-counter / epoch-word hand-off
-    // instead of grid.sync() 0.383; ONE barrier per iteration with every CTA redundantly reducing + solving 0.343 —
-    // although its empty loop is 2.4x cheaper (0.029 vs 0.070): when every SM alternates between the gather code and
-    // the solve code each iteration, the instruction working set no longer fits the SM's instruction cache, while a
-    // dedicated solver CTA keeps the ~1.5k-instruction serial tail hot on one SM (6.6 us vs ~40 us per iteration).
     cg::grid_group grid = cg::this_grid();
-    __shared__ KnnStage s_stage[kGatherWarps][64];
-    __shared__ double s_u[kGatherWarps][16];
-    __shared__ double s_acc[kGatherWarps][kAcc];
-    __shared__ int s_stencil[kMaxStencil];
-    __shared__ SolveScratch s_solve;
-    __shared__ IcpState s_dummy;
-    __shared__ int s_peer_ok;
+    GnShared &sh = *reinterpret_cast<GnShared *>(gn_smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const GatherConfig &G = cfg.G;
     const GnParams &P = cfg.P;
     const bool solver_cta = blockIdx.x == 0;
     unsigned int peer_seq = 0;   // sequence number of the last exchange (solver CTA only)
     if (kPeers && solver_cta) peer_seq = *links.seq;
     const int gather_ctas = gridDim.x - 1;
-    const int *stencil = stencil_table_fill(s_stencil, G.r);
+    const int *stencil = stencil_table_fill(sh.stencil, cfg.G.r);
     __syncthreads();
 
     if (solver_cta && w == 0 && !(P.debug_flags & 4)) {
         // instruction-cache warm-up of the serial tail on a dummy well-posed system (results discarded)
         CT_STAMP(if (lane == 0) st->dbg_t[0] = global_timer_ns();)
-        for (int i = lane; i < kAcc; i += 32) s_acc[1][i] = 0.0;
+        for (int i = lane; i < kAcc; i += 32) sh.acc[1][i] = 0.0;
         __syncwarp();
         for (int e = lane; e < 78; e += 32)
-            if (c_pair_i[e] == c_pair_j[e]) s_acc[1][e] = 200.0 * (1.0 + c_pair_i[e]);
-        if (lane < 12) s_acc[1][78 + lane] = 1e-3 * (lane + 1);
+            if (c_pair_i[e] == c_pair_j[e]) sh.acc[1][e] = 200.0 * (1.0 + c_pair_i[e]);
+        if (lane < 12) sh.acc[1][78 + lane] = 1e-3 * (lane + 1);
         if (lane == 0) {
-            s_acc[1][kAccUsed] = 200.0;
-            s_dummy = *st;
+            sh.acc[1][kAccUsed] = 200.0;
+            sh.dummy = *st;
         }
         __syncwarp();
-        warp_gn_solve(s_acc[1], s_solve, &s_dummy, P, 0, nullptr, lane);
+        warp_gn_solve(sh.acc[1], sh.solve, &sh.dummy, P, 0, nullptr, lane);
         __syncwarp();
     }
 
     for (int it = 0; it < num_iters; ++it) {
-#ifdef CTICP_HANDOFF
-        if (!solver_cta && it > 0) {   // wait until the solver CTA has published the pose of iteration it - 1
-            if (threadIdx.x == 0) s_peer_ok = handoff_wait(&st->handoff_epoch, (unsigned int) it);
-            __syncthreads();
-            if (!s_peer_ok) break;   // timed out (the solver CTA flags the failure)
-        }
-#endif
         if (__ldcg(&st->done)) break;   // uniform: written before the previous grid barrier
         if (!solver_cta) {
-            double acc0 = 0, acc1 = 0, acc2 = 0;
-            double n_used = 0, sum_sq = 0, n_stencil = 0, n_kp = 0, n_valid = 0;
-            Q4 qb, qe;
-            V3 tb, te;
-            SlerpConsts sc;
-            load_state_volatile(st, qb, tb, qe, te, sc);
-            const int K = *d_num_keypoints;
-            const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
-            const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-            const int warps_total = gather_ctas * kGatherWarps;
-            const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
-            const int pi0 = c_pair_i[i0], pj0 = c_pair_j[i0], pi1 = c_pair_i[i1], pj1 = c_pair_j[i1];
-            const int pi2 = i2 < kAccUsed ? c_pair_i[i2] : 0, pj2 = i2 < kAccUsed ? c_pair_j[i2] : 0;
-            for (int kp = lo + (blockIdx.x - 1) * kGatherWarps + w; kp < hi; kp += warps_total) {
-                if (P.debug_flags & 2) break;
-                const float4 kraw = __ldg(keypoints + kp);
-                const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
-                const double alpha = (double) kraw.w;
-                const V3 p = ct_transform_c(qb, tb, qe, te, alpha, raw, sc);
-                const QueryCtx ctx = make_query(p, G.L.res, lane);
-                KnnEntry best;
-                unsigned spts = 0;
-                const int n = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
-                n_kp += 1;
-                n_stencil += (double) spts;
-                if (n < P.kmin || n < 5) continue;
-                n_valid += 1;
-                const NeighborhoodDesc nd = warp_describe(G, stencil, ctx, best, n, lane);
-                V3 normal = nd.normal;
-                if (dot(normal, tb - p) < 0) normal = -1.0 * normal;
-                const double weight = nd.a2D * nd.a2D;
-                const V3 diff{-nd.far_rel.x, -nd.far_rel.y, -nd.far_rel.z};
-                const double dist_to_plane = dot(normal, diff);
-                if (!(fabs(dist_to_plane) < P.max_dist_to_plane)) continue;
-                const V3 nw = weight * normal;
-                const double scalar = dot(nw, diff);
-                if (lane == 0) {
-                    const V3 ob = qrot(qb, raw), oe = qrot(qe, raw);
-                    const double am = 1.0 - alpha, a = alpha;
-                    const V3 cb = cross(ob, nw), ce = cross(oe, nw);
-                    double *u = s_u[w];
-                    u[0] = am * cb.x; u[1] = am * cb.y; u[2] = am * cb.z;
-                    u[3] = am * nw.x; u[4] = am * nw.y; u[5] = am * nw.z;
-                    u[6] = a * ce.x;  u[7] = a * ce.y;  u[8] = a * ce.z;
-                    u[9] = a * nw.x;  u[10] = a * nw.y; u[11] = a * nw.z;
-                    u[12] = -scalar;
-                }
-                __syncwarp();
-                {
-                    const double *u = s_u[w];
-                    acc0 += u[pi0] * u[pj0];
-                    acc1 += u[pi1] * u[pj1];
-                    if (i2 < kAccUsed) acc2 += u[pi2] * u[pj2];
-                }
-                __syncwarp();
-                n_used += 1;
-                sum_sq += scalar * scalar;
+            GnWarpAcc A;
+            if (threadIdx.x == 0) sh.pose = load_pose(st);   // phases A / C read the pose from shared memory: 34
+            __syncthreads();                                  // registers less to keep live across the gather
+            if (!(P.debug_flags & 2)) {
+                const GnPose &pose = sh.pose;
+                const int K = *d_num_keypoints;
+                const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
+                const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+                // warp index interleaved over the CTAs: a keypoint set smaller than the grid spreads over all SMs
+                gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gather_ctas + (blockIdx.x - 1),
+                                gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A);
             }
-            s_acc[w][lane] = acc0;
-            s_acc[w][lane + 32] = acc1;
-            s_acc[w][lane + 64] = acc2;
-            if (lane == 0) {
-                s_acc[w][kAccUsed] = n_used;
-                s_acc[w][kAccSumSq] = sum_sq;
-                s_acc[w][kAccStencil] = n_stencil;
-                s_acc[w][kAccKeypoints] = n_kp;
-                s_acc[w][kAccValidNb] = n_valid;
-                s_acc[w][95] = 0;
-            }
+            gn_store_warp_row(sh.acc[w], A, lane);
             __syncthreads();
             if (threadIdx.x < kAcc) {
                 double s = 0;
 #pragma unroll
-                for (int ww = 0; ww < kGatherWarps; ++ww) s += s_acc[ww][threadIdx.x];
+                for (int ww = 0; ww < kGatherWarps; ++ww) s += sh.acc[ww][threadIdx.x];
                 __stcg(&partials[(size_t) (blockIdx.x - 1) * kAcc + threadIdx.x], s);
             }
         }
-#ifdef CTICP_HANDOFF
-        if (!solver_cta) {   // deliver: row written → fence → count this CTA in
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) atomicAdd(&st->handoff_arrive, 1u);
-        } else {             // collect: all gather CTAs of this iteration have delivered
-            if (threadIdx.x == 0) {
-                s_peer_ok = handoff_wait(&st->handoff_arrive, (unsigned int) gather_ctas * (unsigned int) (it + 1));
-                if (!s_peer_ok) {
-                    st->failed = 3;
-                    st->done = 1;
-                }
-            }
-            __syncthreads();
-            if (!s_peer_ok) break;
-        }
-#else
         grid.sync();
-#endif
         if (solver_cta) {
             CT_STAMP(if (threadIdx.x == 0) st->dbg_t[1] = global_timer_ns();)
-            // deterministic reduction: warp g sums the rows b = g (mod kGatherWarps) of three columns per lane, then
-            // the per-warp sums are combined in fixed order
-            double a0 = 0, a1 = 0, a2 = 0;
-#ifdef CTICP_REDUCE_MLP
-            // Experiment (-DCTICP_REDUCE_MLP, to be measured): all of a warp's rows are requested before the first is
-            // added (one L2 round trip instead of one per four rows); the additions keep their order
-            constexpr int kRowsInFlight = 8;
-            for (int b0 = w; b0 < gather_ctas; b0 += kGatherWarps * kRowsInFlight) {
-                double v0[kRowsInFlight], v1[kRowsInFlight], v2[kRowsInFlight];
-#pragma unroll
-                for (int u = 0; u < kRowsInFlight; ++u) {
-                    const int b = b0 + u * kGatherWarps;
-                    if (b < gather_ctas) {
-                        const double *row = partials + (size_t) b * kAcc;
-                        v0[u] = __ldcg(row + lane);
-                        v1[u] = __ldcg(row + lane + 32);
-                        v2[u] = __ldcg(row + lane + 64);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kRowsInFlight; ++u)
-                    if (b0 + u * kGatherWarps < gather_ctas) {
-                        a0 += v0[u];
-                        a1 += v1[u];
-                        a2 += v2[u];
-                    }
-            }
-#else
-            for (int b = w; b < gather_ctas; b += kGatherWarps) {
-                const double *row = partials + (size_t) b * kAcc;
-                a0 += __ldcg(row + lane);
-                a1 += __ldcg(row + lane + 32);
-                a2 += __ldcg(row + lane + 64);
-            }
-#endif
-            s_acc[w][lane] = a0;
-            s_acc[w][lane + 32] = a1;
-            s_acc[w][lane + 64] = a2;
-            __syncthreads();
-            if (threadIdx.x < kAcc) {
-                double s = 0;
-#pragma unroll
-                for (int ww = 0; ww < kGatherWarps; ++ww) s += s_acc[ww][threadIdx.x];
-                s_u[0][0] = 0;   // (keeps s_u referenced in the solver CTA)
-                s_acc[0][threadIdx.x] = s;
-            }
-            __syncthreads();
+            gn_reduce_rows(sh, partials, gather_ctas, lane, w);
             bool peers_ok = true;
             if (kPeers) {
-                // Σ over ranks, in rank order (bit-identical on every rank); the stencil staging area of this CTA is
-                // unused by the solver CTA and serves as scratch
-                static_assert(sizeof(KnnStage) * 64 * kGatherWarps >= sizeof(unsigned int) * kMaxPeers * kPeerWords, "scratch");
-                peers_ok = peer_allreduce(links, ++peer_seq, s_acc[0], reinterpret_cast<unsigned int *>(&s_stage[0][0]), &s_peer_ok);
+                // Σ over ranks, in rank order (bit-identical on every rank); the staging areas are unused by the solver
+                // CTA and serve as scratch
+                static_assert(sizeof(TileScratch) * kGatherWarps >= sizeof(unsigned int) * kMaxPeers * kPeerWords, "scratch");
+                peers_ok = peer_allreduce(links, ++peer_seq, sh.acc[0], reinterpret_cast<unsigned int *>(&sh.tile[0]), &sh.flag);
             }
             CT_STAMP(if (threadIdx.x == 0) st->dbg_t[2] = global_timer_ns();)
             if (w == 0) {
@@ -548,19 +502,12 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 } else if (P.debug_flags & 1) {
                     if (lane == 0) st->iter += 1;
                 } else
-                    warp_gn_solve(s_acc[0], s_solve, st, P, 0, nullptr, lane);
+                    warp_gn_solve(sh.acc[0], sh.solve, st, P, 0, nullptr, lane);
                 CT_STAMP(if (lane == 0) st->dbg_t[3] = global_timer_ns();)
             }
             __threadfence();
         }
-#ifdef CTICP_HANDOFF
-        if (solver_cta) {   // publish: the pose update (fenced above by every thread of this CTA) is visible → epoch
-            __syncthreads();
-            if (threadIdx.x == 0) handoff_store(&st->handoff_epoch, (unsigned int) (it + 1));
-        }
-#else
         grid.sync();
-#endif
     }
     if (kPeers && solver_cta && threadIdx.x == 0) *links.seq = peer_seq;
 }
@@ -675,10 +622,13 @@ void IcpSolver::AllReduceAccumulator(void *nccl_comm, IcpState *d_state) {
 }
 
 IcpSolver::IcpSolver(cudaStream_t stream) : stream_(stream) {
-    UploadPairTables();
     if (const char *e = getenv("CTICP_PERSISTENT")) use_persistent_ = atoi(e) != 0;
+    if (const char *e = getenv("CTICP_GN_KP_PER_CTA")) kp_per_cta_ = std::max(1, std::min(atoi(e), 32 * kGatherWarps));
     int dev = 0;
     cudaGetDevice(&dev);
+    CT_CUDA_CHECK(cudaFuncSetAttribute(k_gn_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(GnShared)));
+    CT_CUDA_CHECK(cudaFuncSetAttribute(k_gn_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(GnShared)));
+    CT_CUDA_CHECK(cudaFuncSetAttribute(k_gn_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(GnShared)));
     cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev);
     CT_CUDA_CHECK(cudaMalloc(&d_sys_, sizeof(double) * 160));
     CT_CUDA_CHECK(cudaMalloc(&d_acc_, sizeof(double) * kAcc));
@@ -721,15 +671,17 @@ GnParams IcpSolver::MakeParams(const DeviceMap &map, const cticp_icp_options &op
     P.shard_world = 1;
     P.debug_flags = 0;
     if (const char *e = getenv("CTICP_DEBUG_FLAGS")) P.debug_flags = atoi(e);
+    P.bucket_scale = (double) kSelBuckets / (P.radius * P.radius);
     return P;
 }
-static int GatherBlocks(size_t k_hint, int num_sms) {
-    // one warp per keypoint, kGatherWarps warps per CTA, at most 8 CTAs per SM; beyond that warps loop.
-    // k_hint is an ESTIMATE of the keypoint count (the exact count lives on the device): too small only makes
-    // warps iterate, too large only adds idle CTAs whose zero partials the last CTA has to sum.
-    size_t want = (k_hint + kGatherWarps - 1) / kGatherWarps;
-    size_t cap = (size_t) num_sms * 8;
-    return (int) std::max<size_t>(1, std::min(want, cap));
+static int GatherBlocks(size_t k_hint, int num_sms, int kp_per_cta) {
+    // One CTA (kGatherWarps warps, 128 registers per thread) per SM. A keypoint set smaller than the machine is spread
+    // thin — `kp_per_cta` keypoints per CTA, so each keypoint's warp has an SM sub-partition nearly to itself: the loop
+    // is latency-bound there — until every SM has a CTA; beyond that the tiles widen (gn_gather_tiles).
+    // k_hint is an ESTIMATE of the keypoint count (the exact count lives on the device): too small only widens the
+    // tiles, too large only adds idle CTAs whose zero partials have to be summed.
+    size_t want = (k_hint + kp_per_cta - 1) / kp_per_cta;
+    return (int) std::max<size_t>(1, std::min(want, (size_t) num_sms));
 }
 
 void IcpSolver::CollectGatherTiming() {
@@ -753,7 +705,7 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
     cfg.G.r = cfg.P.r;
     cfg.G.radius2 = cfg.P.radius * cfg.P.radius;
     cfg.G.kmax = cfg.P.kmax;
-    const int blocks = GatherBlocks((k_upper + shard_world - 1) / shard_world + 16, num_sms_);
+    const int blocks = GatherBlocks((k_upper + shard_world - 1) / shard_world + 16, num_sms_, kp_per_cta_);
     EnsurePartials(blocks + 1);
     const bool peers = nccl_comm && shard_world > 1 && peers_ready_;
     if (use_persistent_ && (!nccl_comm || peers)) {
@@ -762,7 +714,7 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         int &coresident = max_coresident_[peers ? 1 : 0];
         if (coresident == 0) {
             int per_sm = 0;
-            CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGatherWarps * 32, 0));
+            CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGatherWarps * 32, sizeof(GnShared)));
             coresident = std::max(1, per_sm * num_sms_);
         }
         int grid = std::min(blocks + 1, coresident);
@@ -775,7 +727,7 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters, &links};
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
-        CT_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kGatherWarps * 32), args, 0, stream_));
+        CT_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kGatherWarps * 32), args, sizeof(GnShared), stream_));
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
         gather_launches_ += 1;
         launches_ += 1;
@@ -784,8 +736,8 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
     for (int it = 0; it < num_iters; ++it) {
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
-        k_gn_iterate<<<blocks, kGatherWarps * 32, 0, stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state, d_partials_,
-                                                               d_ticket_, nccl_comm ? 2 : 0, d_acc_, nullptr);
+        k_gn_iterate<<<blocks, kGatherWarps * 32, sizeof(GnShared), stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state,
+                                                                              d_partials_, d_ticket_, nccl_comm ? 2 : 0, d_acc_, nullptr);
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
         ++gather_launches_;
         launches_ += 1;
@@ -807,11 +759,11 @@ void IcpSolver::NormalEquations(const DeviceMap &map, const cticp_icp_options &o
     cfg.G.r = cfg.P.r;
     cfg.G.radius2 = cfg.P.radius * cfg.P.radius;
     cfg.G.kmax = cfg.P.kmax;
-    const int blocks = GatherBlocks(k_upper, num_sms_);
+    const int blocks = GatherBlocks(k_upper, num_sms_, kp_per_cta_);
     EnsurePartials(blocks);
     CT_CUDA_CHECK(cudaMemsetAsync(d_sys_, 0, sizeof(double) * 160, stream_));
-    k_gn_iterate<<<blocks, kGatherWarps * 32, 0, stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state, d_partials_,
-                                                           d_ticket_, 1, d_acc_, d_sys_);
+    k_gn_iterate<<<blocks, kGatherWarps * 32, sizeof(GnShared), stream_>>>(cfg, d_keypoints, d_num_keypoints, d_state,
+                                                                          d_partials_, d_ticket_, 1, d_acc_, d_sys_);
     launches_ += 1;
     double h[160];
     CT_CUDA_CHECK(cudaMemcpyAsync(h, d_sys_, sizeof(h), cudaMemcpyDeviceToHost, stream_));
@@ -831,7 +783,7 @@ void IcpSolver::Neighborhoods(const DeviceMap &map, const double *d_queries, siz
     G.r = r;
     G.radius2 = map.Options().default_radius * map.Options().default_radius;
     G.kmax = kmax;
-    const int blocks = GatherBlocks(n, num_sms_);
+    const int blocks = (int) std::max<size_t>(1, std::min((n + kGatherWarps - 1) / kGatherWarps, (size_t) num_sms_ * 2));
     k_neighborhoods<<<blocks, kGatherWarps * 32, 0, stream_>>>(G, d_queries, (int) n, d_out_points, d_out_counts);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
@@ -848,7 +800,7 @@ void IcpSolver::RadiusSearch(const DeviceMap &map, const double *d_queries, cons
     RadiusSearchLevels *d_R = nullptr;
     CT_CUDA_CHECK(cudaMalloc(&d_R, sizeof(R)));
     CT_CUDA_CHECK(cudaMemcpyAsync(d_R, &R, sizeof(R), cudaMemcpyHostToDevice, stream_));
-    const int blocks = GatherBlocks(n, num_sms_);
+    const int blocks = (int) std::max<size_t>(1, std::min((n + kGatherWarps - 1) / kGatherWarps, (size_t) num_sms_ * 2));
     k_radius_search<<<blocks, kGatherWarps * 32, 0, stream_>>>(d_R, kmax, d_queries, d_radiuses, (int) n, d_out_points, d_out_counts);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());

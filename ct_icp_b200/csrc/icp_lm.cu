@@ -18,7 +18,7 @@
 #include <cstdlib>
 
 #include "engine.h"
-#include "gather.cuh"
+#include "gather_select.cuh"
 #include "icp.h"
 #include "lm_functor.cuh"
 #include "peer_exchange.cuh"
@@ -43,6 +43,7 @@ struct LmParams {
     double radius;
     double lambda_weight, lambda_neighborhood, power_planarity, max_dist_to_plane;
     int max_num_residuals, min_number_neighbors, num_iters_icp;
+    double bucket_scale;   // 32 / radius^2 (gather_select.cuh)
     double threshold_orientation_norm, threshold_translation_norm;
     // least squares
     LossParams loss;
@@ -83,17 +84,43 @@ struct DistanceStrategy {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// Residual assembly, tiled like the GN gather (icp_gn.cu gn_gather_tiles): a warp owns W consecutive keypoints;
+// lane j does keypoint j's scalar work (transform, per-keypoint radius, covariance → eigen → weight with its pow / exp,
+// the 144-byte residual block) and the whole warp does the gather + k-nearest selection of each keypoint in turn.
+constexpr int kLmTileMax = 16;
+struct __align__(16) LmTile {
+    SelScratch sel;
+    double sums[kLmTileMax][14];   // n, stencil points, Σ rel (3), Σ rel rel^T (6), farthest kept (3)
+};
+__device__ __forceinline__ void lm_store_sums(double *o, const NeighborSums &s, unsigned spts, int need) {
+    o[0] = (double) s.n; o[1] = (double) spts;
+    if (s.n >= need) {
+        o[2] = s.sx; o[3] = s.sy; o[4] = s.sz;
+        o[5] = s.sxx; o[6] = s.sxy; o[7] = s.sxz; o[8] = s.syy; o[9] = s.syz; o[10] = s.szz;
+        o[11] = s.fx; o[12] = s.fy; o[13] = s.fz;
+    }
+}
+__device__ __forceinline__ NeighborSums lm_load_sums(const double *o) {
+    NeighborSums s;
+    s.n = (int) o[0];
+    s.sx = o[2]; s.sy = o[3]; s.sz = o[4];
+    s.sxx = o[5]; s.sxy = o[6]; s.sxz = o[7]; s.syy = o[8]; s.syz = o[9]; s.szz = o[10];
+    s.fx = o[11]; s.fy = o[12]; s.fz = o[13]; s.fd2 = 0;
+    return s;
+}
+
 template <bool kDB>
 __global__ void __launch_bounds__(kLmWarps * 32)
 k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
             const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned long long *stats,
             const DistanceStrategy *__restrict__ D) {
-    __shared__ KnnStage s_stage[kLmWarps][64];
+    __shared__ LmTile s_tile[kLmWarps];
     __shared__ int s_stencil[kMaxStencil];
     if (st->done) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int *stencil = kDB ? nullptr : stencil_table_fill(s_stencil, G0.r);
     __syncthreads();
+    LmTile &T = s_tile[w];
     const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
     const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
     const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
@@ -102,57 +129,98 @@ k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, c
     // keypoint-sharded mode: this rank assembles the blocks of its contiguous chunk only
     const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
     const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-    for (int kp = kp_lo + blockIdx.x * kLmWarps + w; kp < kp_hi; kp += gridDim.x * kLmWarps) {
-        const float4 kraw = __ldg(keypoints + kp);
-        const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
-        const double alpha = (double) kraw.w;
-        // transform_keypoints(), ct_icp.cpp:516-531
-        const V3 p = ct_transform_c(qb, tb, qe, te, alpha, raw, sc);
-        GatherConfig G = G0;
-        if (kDB) {
-            // ComputeRadius (neighborhood_strategy.h:121-126) then SearchParamsFromRadiusSearch (map.h:416-432)
-            const double range = sqrt(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z);
-            const double a = pow(fmin(fabs(range), D->radius_max) / D->radius_max, D->exponent);
-            const double radius = a * D->radius_max + (1 - a) * D->radius_min;
-            int it = 0;
-            while (it < D->num_levels && D->levels[it].res <= radius) ++it;
-            const int idx = it > 0 ? it - 1 : 0;
-            G.L = D->levels[idx];
-            G.r = (int) ceil(radius / G.L.res);
-            G.radius2 = radius * radius;
+    const int warps_total = gridDim.x * kLmWarps;
+    int W = (kp_hi - kp_lo + warps_total - 1) / warps_total;
+    W = W < kLmTileMax ? (W < 1 ? 1 : W) : kLmTileMax;
+    const int need = P.kmin > 5 ? P.kmin : 5;   // :574 ; neighborhood.h:227
+    for (int t0 = kp_lo + (w * (int) gridDim.x + (int) blockIdx.x) * W; t0 < kp_hi; t0 += warps_total * W) {
+        const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
+        // ---- lane j: transform_keypoints() (ct_icp.cpp:516-531) and, for the distance-based strategy, this
+        // keypoint's radius → map level + stencil (neighborhood_strategy.h:121-126, map.h:416-432)
+        float4 kraw = make_float4(0.f, 0.f, 0.f, 0.f);
+        V3 p{0, 0, 0};
+        int kx = 0, ky = 0, kz = 0, lvl = 0, rr = G0.r;
+        double radius2 = G0.radius2, scale = P.bucket_scale;
+        if (lane < wt) {
+            kraw = __ldg(keypoints + t0 + lane);
+            const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+            p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, raw, sc);
+            double res = G0.L.res;
+            if (kDB) {
+                const double range = sqrt(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z);
+                const double a = pow(fmin(fabs(range), D->radius_max) / D->radius_max, D->exponent);
+                const double radius = a * D->radius_max + (1 - a) * D->radius_min;
+                int it = 0;
+                while (it < D->num_levels && D->levels[it].res <= radius) ++it;
+                lvl = it > 0 ? it - 1 : 0;
+                res = D->levels[lvl].res;
+                rr = (int) ceil(radius / res);
+                radius2 = radius * radius;
+                scale = (double) kSelBuckets / radius2;
+            }
+            kx = voxel_coord(p.x, res);
+            ky = voxel_coord(p.y, res);
+            kz = voxel_coord(p.z, res);
         }
-        const QueryCtx ctx = make_query(p, G.L.res, lane);
-        KnnEntry best;
-        unsigned spts = 0;
-        int n;
-        if (kDB && D->filter)
-            n = warp_gather_knn<true>(G, stencil, ctx, lane, s_stage[w], best, spts, V3{te.x - p.x, te.y - p.y, te.z - p.z});
-        else
-            n = warp_gather_knn<false>(G, stencil, ctx, lane, s_stage[w], best, spts);
-        n_kp += 1;
-        n_pts += spts;
-        ResidualBlock rb;
-        rb.valid = 0;
-        if (n >= P.kmin && n >= 5) {   // :574 ; neighborhood.h:227
-            const NeighborhoodDesc nd = warp_describe(G, stencil, ctx, best, n, lane);
-            // (the normal flip test at :578 is a no-op: BeginTr - BeginTr)
-            double weight = pow(nd.a2D, P.power_planarity);
-            const double far_dist = sqrt(nd.far_rel.x * nd.far_rel.x + nd.far_rel.y * nd.far_rel.y + nd.far_rel.z * nd.far_rel.z);
-            weight = P.lambda_weight * weight +
-                     P.lambda_neighborhood * exp(-far_dist / (P.max_dist_to_plane * P.min_number_neighbors));   // :582-587
-            rb.ref[0] = p.x + nd.far_rel.x; rb.ref[1] = p.y + nd.far_rel.y; rb.ref[2] = p.z + nd.far_rel.z;   // points[0]
-            rb.normal[0] = nd.normal.x; rb.normal[1] = nd.normal.y; rb.normal[2] = nd.normal.z;
-            rb.weight = weight;
-            rb.alpha = alpha;
-            rb.raw[0] = kraw.x; rb.raw[1] = kraw.y; rb.raw[2] = kraw.z;
-            rb.valid = 1;
-            rb.kind = kResPlane;
-        }
-        if (lane == 0) {
-            if (rb.valid) blocks[kp] = rb;
-            else blocks[kp].valid = 0;
+        // ---- all lanes: gather + selection, keypoint by keypoint
+        for (int j = 0; j < wt; ++j) {
+            const V3 q{__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j)};
+            const int qx = __shfl_sync(0xffffffffu, kx, j), qy = __shfl_sync(0xffffffffu, ky, j),
+                      qz = __shfl_sync(0xffffffffu, kz, j);
+            GatherConfig G = G0;
+            double sc_j = P.bucket_scale;
+            if (kDB) {
+                G.L = D->levels[__shfl_sync(0xffffffffu, lvl, j)];
+                G.r = __shfl_sync(0xffffffffu, rr, j);
+                G.radius2 = __shfl_sync(0xffffffffu, radius2, j);
+                sc_j = __shfl_sync(0xffffffffu, scale, j);
+            }
+            NeighborSums s;
+            unsigned spts = 0;
+            if (kDB && D->filter)
+                warp_gather_sums<true>(G, sc_j, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts,
+                                       V3{te.x - q.x, te.y - q.y, te.z - q.z});
+            else
+                warp_gather_sums<false>(G, sc_j, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts);
+            if (lane == 0) lm_store_sums(T.sums[j], s, spts, need);
         }
         __syncwarp();
+        // ---- lane j: the residual block (:574-604)
+        if (lane < wt) {
+            const int kp = t0 + lane;
+            const NeighborSums mine = lm_load_sums(T.sums[lane]);
+            n_kp += 1;
+            n_pts += (unsigned long long) T.sums[lane][1];
+            if (mine.n >= need) {
+                const NeighborhoodDesc nd = describe_from_sums(mine);
+                // (the normal flip test at :578 is a no-op: BeginTr - BeginTr)
+                double weight = pow(nd.a2D, P.power_planarity);
+                const double far_dist = sqrt(nd.far_rel.x * nd.far_rel.x + nd.far_rel.y * nd.far_rel.y + nd.far_rel.z * nd.far_rel.z);
+                weight = P.lambda_weight * weight +
+                         P.lambda_neighborhood * exp(-far_dist / (P.max_dist_to_plane * P.min_number_neighbors));   // :582-587
+                ResidualBlock rb;
+                rb.ref[0] = p.x + nd.far_rel.x; rb.ref[1] = p.y + nd.far_rel.y; rb.ref[2] = p.z + nd.far_rel.z;   // points[0]
+                rb.normal[0] = nd.normal.x; rb.normal[1] = nd.normal.y; rb.normal[2] = nd.normal.z;
+                rb.weight = weight;
+                rb.alpha = (double) kraw.w;
+                rb.raw[0] = kraw.x; rb.raw[1] = kraw.y; rb.raw[2] = kraw.z;
+                rb.valid = 1;
+                for (int i = 0; i < 6; ++i) rb.info[i] = 0.0;
+                rb.kind = kResPlane;
+                rb._pad = 0;
+                blocks[kp] = rb;
+            } else {
+                blocks[kp].valid = 0;
+            }
+        }
+        __syncwarp();
+    }
+    n_kp = __reduce_add_sync(0xffffffffu, (unsigned) n_kp);
+    {
+        unsigned long long t = n_pts;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        n_pts = t;
     }
     if (lane == 0 && n_kp) {
         atomicAdd(&stats[0], n_kp);
@@ -169,13 +237,14 @@ __global__ void __launch_bounds__(kLmWarps * 32)
 k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
             const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned char *__restrict__ classes,
             unsigned long long *stats) {
-    __shared__ KnnStage s_stage[kLmWarps][64];
+    __shared__ LmTile s_tile[kLmWarps];
     __shared__ int s_stencil[kMaxStencil];
     if (st->done) return;
     enum { NONE = 0, LINEAR = 1, PLANAR = 2, VOLUMIC = 3 };
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int *stencil = stencil_table_fill(s_stencil, G.r);
     __syncthreads();
+    LmTile &T = s_tile[w];
     const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
     const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
     const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
@@ -184,44 +253,65 @@ k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, co
     // keypoint-sharded mode: this rank assembles the blocks of its contiguous chunk only
     const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
     const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-    for (int kp = kp_lo + blockIdx.x * kLmWarps + w; kp < kp_hi; kp += gridDim.x * kLmWarps) {
-        const float4 kraw = __ldg(keypoints + kp);
-        const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
-        const V3 p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, raw, sc);   // TransformKeyPoints, :1373-1393
-        const QueryCtx ctx = make_query(p, G.L.res, lane);
-        KnnEntry best;
-        unsigned spts = 0;
-        const int n = warp_gather_knn(G, stencil, ctx, lane, s_stage[w], best, spts);
-        n_kp += 1;
-        n_pts += spts;
-        int valid = 0;
-        if (n >= P.kmin) {   // :1238 (kmin >= 5 is enforced by the host, so the neighborhood is always describable)
-            const NeighborhoodDescFull nd = warp_describe_full(G, stencil, ctx, best, n, lane);
-            int cls = classes[kp];
-            if (nd.planarity > P.threshold_planarity) cls = PLANAR;
-            else if (nd.linearity > P.threshold_linearity) cls = LINEAR;
-            if (!P.use_lines && cls == LINEAR) cls = P.threshold_planarity < nd.planarity ? PLANAR : VOLUMIC;   // :1243-1248
-            double weight;
-            if (cls == LINEAR) weight = pow(fabs(nd.linearity), P.power_planarity);
-            else if (cls == PLANAR) weight = pow(fabs(nd.planarity), P.power_planarity);
-            else weight = P.weight_neighborhood;
-            const V3 d = P.use_barycenter ? nd.mean_rel : nd.far_rel;   // point - world_point
-            double distance;
-            int kind = kResDistribution;
-            if (cls == LINEAR) {
-                V3 u = nd.line;
-                const double z = dot(u, u);
-                if (z > 0) u = (1.0 / sqrt(z)) * u;
-                const V3 c = cross(d, u);
-                distance = sqrt(dot(c, c));
-                kind = kResLine;
-            } else if (cls == PLANAR) {
-                distance = fabs(dot(d, nd.normal));
-                kind = kResPlane;
-            } else {
-                distance = sqrt(dot(d, d));
-            }
-            if (lane == 0) {
+    const int warps_total = gridDim.x * kLmWarps;
+    int W = (kp_hi - kp_lo + warps_total - 1) / warps_total;
+    W = W < kLmTileMax ? (W < 1 ? 1 : W) : kLmTileMax;
+    const int need = P.kmin;   // :1238 (kmin >= 5 is enforced by the host, so the neighborhood is always describable)
+    for (int t0 = kp_lo + (w * (int) gridDim.x + (int) blockIdx.x) * W; t0 < kp_hi; t0 += warps_total * W) {
+        const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
+        float4 kraw = make_float4(0.f, 0.f, 0.f, 0.f);
+        V3 p{0, 0, 0};
+        int kx = 0, ky = 0, kz = 0;
+        if (lane < wt) {
+            kraw = __ldg(keypoints + t0 + lane);
+            p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, V3{(double) kraw.x, (double) kraw.y, (double) kraw.z},
+                               sc);   // TransformKeyPoints, :1373-1393
+            kx = voxel_coord(p.x, G.L.res);
+            ky = voxel_coord(p.y, G.L.res);
+            kz = voxel_coord(p.z, G.L.res);
+        }
+        for (int j = 0; j < wt; ++j) {
+            const V3 q{__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j)};
+            const int qx = __shfl_sync(0xffffffffu, kx, j), qy = __shfl_sync(0xffffffffu, ky, j),
+                      qz = __shfl_sync(0xffffffffu, kz, j);
+            NeighborSums s;
+            unsigned spts = 0;
+            warp_gather_sums<false>(G, P.bucket_scale, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts);
+            if (lane == 0) lm_store_sums(T.sums[j], s, spts, need);
+        }
+        __syncwarp();
+        if (lane < wt) {
+            const int kp = t0 + lane;
+            const NeighborSums mine = lm_load_sums(T.sums[lane]);
+            n_kp += 1;
+            n_pts += (unsigned long long) T.sums[lane][1];
+            int valid = 0;
+            if (mine.n >= need) {
+                const NeighborhoodDescFull nd = describe_full_from_sums(mine);
+                int cls = classes[kp];
+                if (nd.planarity > P.threshold_planarity) cls = PLANAR;
+                else if (nd.linearity > P.threshold_linearity) cls = LINEAR;
+                if (!P.use_lines && cls == LINEAR) cls = P.threshold_planarity < nd.planarity ? PLANAR : VOLUMIC;   // :1243-1248
+                double weight;
+                if (cls == LINEAR) weight = pow(fabs(nd.linearity), P.power_planarity);
+                else if (cls == PLANAR) weight = pow(fabs(nd.planarity), P.power_planarity);
+                else weight = P.weight_neighborhood;
+                const V3 d = P.use_barycenter ? nd.mean_rel : nd.far_rel;   // point - world_point
+                double distance;
+                int kind = kResDistribution;
+                if (cls == LINEAR) {
+                    V3 u = nd.line;
+                    const double z = dot(u, u);
+                    if (z > 0) u = (1.0 / sqrt(z)) * u;
+                    const V3 c = cross(d, u);
+                    distance = sqrt(dot(c, c));
+                    kind = kResLine;
+                } else if (cls == PLANAR) {
+                    distance = fabs(dot(d, nd.normal));
+                    kind = kResPlane;
+                } else {
+                    distance = sqrt(dot(d, d));
+                }
                 classes[kp] = (unsigned char) cls;
                 if (distance < P.outlier_distance) {
                     ResidualBlock rb;
@@ -250,9 +340,16 @@ k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, co
                     valid = 1;
                 }
             }
+            if (!valid) blocks[kp].valid = 0;
         }
-        if (lane == 0 && !valid) blocks[kp].valid = 0;
         __syncwarp();
+    }
+    n_kp = __reduce_add_sync(0xffffffffu, (unsigned) n_kp);
+    {
+        unsigned long long t = n_pts;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        n_pts = t;
     }
     if (lane == 0 && n_kp) {
         atomicAdd(&stats[0], n_kp);
@@ -785,8 +882,7 @@ void IcpSolver::EnsureLmBuffers(size_t k_upper) {
     if (!d_lm_state_) {
         CT_CUDA_CHECK(cudaMalloc(&d_lm_state_, sizeof(LmState)));
         CT_CUDA_CHECK(cudaMalloc(&d_lm_stats_, sizeof(unsigned long long) * 2));
-        UploadPairTables();
-    }
+        }
     if (k_upper > lm_capacity_) {
         CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
         cudaFree(d_lm_blocks_);
@@ -831,6 +927,7 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     LmParams P{};
     map.SearchParams(map.Options().default_radius, &P.level, &P.r);
     P.radius = map.Options().default_radius;
+    P.bucket_scale = (double) kSelBuckets / (P.radius * P.radius);
     P.kmax = kmax;
     P.kmin = opt.min_number_neighbors;            // ct_icp.cpp:574
     P.lambda_weight = std::abs(opt.weight_alpha) / sum;

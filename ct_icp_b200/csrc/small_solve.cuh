@@ -1,6 +1,6 @@
 // small_solve.cuh — pieces shared by the GN and LM solver kernels: the (i,j) pair table of the packed 12x12 upper
 // triangle and the warp-resident 12x12 SPD solve. Each translation unit that includes this header owns a copy of the
-// __constant__ tables and must call UploadPairTables() once (host) before launching kernels that read them.
+// __constant__ tables (statically initialised, see below).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -8,29 +8,17 @@
 
 namespace cticp {
 
-// (i,j) of the idx-th entry of the row-major upper triangle of a 12x12 matrix; entries 78..89 pair (i, 12)
-static __constant__ unsigned char c_pair_i[kAccUsed];
-static __constant__ unsigned char c_pair_j[kAccUsed];
-
-static inline void UploadPairTables() {
-    static bool done = false;
-    if (done) return;
-    unsigned char pi[kAccUsed], pj[kAccUsed];
-    int idx = 0;
-    for (int i = 0; i < 12; ++i)
-        for (int j = i; j < 12; ++j) {
-            pi[idx] = (unsigned char) i;
-            pj[idx] = (unsigned char) j;
-            ++idx;
-        }
-    for (int i = 0; i < 12; ++i) {   // entry 78+i = Σ u[i] * u[12]
-        pi[78 + i] = (unsigned char) i;
-        pj[78 + i] = 12;
-    }
-    cudaMemcpyToSymbol(c_pair_i, pi, sizeof(pi));
-    cudaMemcpyToSymbol(c_pair_j, pj, sizeof(pj));
-    done = true;
-}
+// (i,j) of the idx-th entry of the row-major upper triangle of a 12x12 matrix; entries 78..89 pair (i, 12).
+// Statically initialised: __constant__ memory is per device and per module load, so every device that runs these kernels
+// gets the tables with the module — no upload call that could be skipped for a second GPU in the same process.
+static __constant__ unsigned char c_pair_i[kAccUsed] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2,
+    2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 6, 6, 6,
+    6, 6, 6, 7, 7, 7, 7, 7, 8, 8, 8, 8, 9, 9, 9, 10, 10, 11, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+static __constant__ unsigned char c_pair_j[kAccUsed] = {
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 2, 3, 4, 5, 6, 7, 8,
+    9, 10, 11, 3, 4, 5, 6, 7, 8, 9, 10, 11, 4, 5, 6, 7, 8, 9, 10, 11, 5, 6, 7, 8, 9, 10, 11, 6, 7, 8,
+    9, 10, 11, 7, 8, 9, 10, 11, 8, 9, 10, 11, 9, 10, 11, 10, 11, 11, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12};
 
 // ---- 12x12 SPD solve by one warp ---------------------------------------------------------------------------
 struct SolveScratch {

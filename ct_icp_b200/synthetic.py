@@ -23,11 +23,16 @@ class SensorModel:
     min_range: float
     max_range: float
     height: float        # sensor height above ground
+    elev_table_deg: tuple = None   # explicit ring elevations (top to bottom); None = uniform between max and min
 
 
 HDL64 = SensorModel("HDL-64", 64, 2.0, -24.8, 2083, 0.1, 3.0, 100.0, 1.73)       # KITTI-shape, config 2/3
 HDL32 = SensorModel("HDL-32", 32, 10.67, -30.67, 2170, 0.1, 1.0, 100.0, 1.0)     # NCLT-shape, config 4
 DENSE128 = SensorModel("DENSE-128", 128, 15.0, -25.0, 2400, 0.1, 2.0, 120.0, 1.8)  # config 5
+# the real HDL-64E: two laser blocks, 32 rings at 1/3 degree over +2 .. -8.33 and 32 rings at 1/2 degree below (the uniform
+# HDL64 model above puts only 24 rings in the upper block, i.e. a quarter fewer far returns)
+HDL64E = SensorModel("HDL-64E", 64, 2.0, -24.33, 2083, 0.1, 3.0, 100.0, 1.73,
+                     tuple(np.concatenate([np.linspace(2.0, -8.33, 32), np.linspace(-8.83, -24.33, 32)]).tolist()))
 SMALL16 = SensorModel("SMALL-16", 16, 15.0, -15.0, 900, 0.1, 1.0, 60.0, 1.5)      # ~10k pts, config 1 stand-in
 
 
@@ -62,10 +67,20 @@ class UrbanScene:
     """Ground plane z=0, axis-aligned boxes along a street (buildings, cars, fences = solid; bushes and tree
     crowns = porous, returning at a random depth), vertical cylinders (poles / trunks)."""
 
-    def __init__(self, seed=1234, length=2000.0):
+    def __init__(self, seed=1234, length=2000.0, profile="street"):
+        """profile "street": a narrow street canyon (the round-1 scene: ~6.7k occupied 0.5 m voxels per HDL-64 sweep);
+        "suburb": open lots, set-back buildings in two rows, parked cars, dense vegetation — the sweep then fills the
+        25-40k 0.5 m voxels / 3-6k 1.5 m keypoint voxels SURVEY.md §8 quotes for real KITTI sweeps."""
         rng = np.random.default_rng(seed)
         boxes = []   # x0,y0,z0,x1,y1,z1,mean_free_path
         cyl = []     # cx,cy,radius,height
+        self.profile = profile
+        if profile == "suburb":
+            self._build_suburb(rng, length, boxes, cyl)
+            self._finish(boxes, cyl, seed)
+            return
+        if profile != "street":
+            raise ValueError("unknown scene profile %r" % profile)
         x = -120.0
         while x < length:
             for side in (-1.0, 1.0):
@@ -107,10 +122,74 @@ class UrbanScene:
                 cyl.append([xp + rng.uniform(-2, 2), side * rng.uniform(7.0, 8.5), rng.uniform(0.12, 0.35),
                             rng.uniform(4.0, 9.0)])
             xp += rng.uniform(10.0, 20.0)
+        self._finish(boxes, cyl, seed)
+
+    def _finish(self, boxes, cyl, seed):
         b = np.asarray(boxes, dtype=np.float64)
         self.boxes = np.ascontiguousarray(b[np.argsort(b[:, 0], kind="stable")])
         self.cyl = np.ascontiguousarray(np.asarray(cyl, dtype=np.float64))
         self.seed = seed
+
+    @staticmethod
+    def _build_suburb(rng, length, boxes, cyl):
+        """Tuned (tools/scene_stats.py) for the number of occupied 0.5 m voxels per HDL-64E sweep: what counts is how far
+        the upper beams travel before they hit something — dense clutter next to the road occludes everything behind it
+        and LOWERS the count — so: two rows of set-back buildings, parked cars, vegetation spread over the lots, lawns as
+        low porous slabs (rough ground)."""
+        x = -150.0
+        while x < length:   # two rows of buildings per side
+            for side in (-1.0, 1.0):
+                for (s0, s1, prob) in ((25.0, 40.0, 0.9), (55.0, 85.0, 0.9)):
+                    if rng.random() < prob:
+                        w = rng.uniform(10.0, 26.0)
+                        d = rng.uniform(8.0, 18.0)
+                        h = rng.uniform(4.0, 14.0)
+                        setback = rng.uniform(s0, s1)
+                        y0 = side * setback if side > 0 else side * setback - d
+                        boxes.append([x + rng.uniform(-3, 3), y0, 0.0, x + w, y0 + d, h, 0.0])
+            x += rng.uniform(14.0, 24.0)
+        xc = -120.0
+        while xc < length:   # parked cars, both sides
+            for side in (-1.0, 1.0):
+                if rng.random() < 0.7:
+                    y0 = side * rng.uniform(4.5, 6.5)
+                    boxes.append([xc, y0 - 0.9, 0.0, xc + rng.uniform(3.8, 4.8), y0 + 0.9, rng.uniform(1.4, 1.9), 0.0])
+            xc += rng.uniform(6.0, 12.0)
+        xv = -140.0
+        while xv < length:   # vegetation / clutter scattered over the lots
+            side = rng.choice([-1.0, 1.0])
+            kind = rng.random()
+            y = side * rng.uniform(8.0, 70.0)
+            if kind < 0.30:      # bush (porous)
+                sx, sy, sz = rng.uniform(1.0, 3.0, size=3)
+                boxes.append([xv, y, 0.0, xv + sx, y + sy, sz, 1.0])
+            elif kind < 0.62:    # tree: porous crown + trunk
+                sx, sy = rng.uniform(3.0, 8.0, size=2)
+                z0 = rng.uniform(1.8, 3.0)
+                boxes.append([xv, y, z0, xv + sx, y + sy, z0 + rng.uniform(2.5, 7.0), 2.0])
+                cyl.append([xv + sx / 2, y + sy / 2, rng.uniform(0.15, 0.45), z0 + 0.1])
+            elif kind < 0.80:    # hedge / tall grass strip (porous, low)
+                boxes.append([xv, y, 0.0, xv + rng.uniform(2.0, 10.0), y + rng.uniform(0.6, 3.0), rng.uniform(0.4, 1.4), 0.6])
+            elif kind < 0.90:    # fence along the street
+                boxes.append([xv, y, 0.0, xv + rng.uniform(3.0, 12.0), y + 0.2, rng.uniform(0.8, 2.0), 0.0])
+            else:                # wall segment across the street direction
+                boxes.append([xv, y, 0.0, xv + 0.2, y + rng.uniform(3.0, 12.0), rng.uniform(0.8, 2.2), 0.0])
+            xv += rng.uniform(0.3, 0.7)
+        xg = -140.0
+        while xg < length:   # lawns / verges: low porous slabs (returns scatter over 0..h above the plane)
+            for side in (-1.0, 1.0):
+                if rng.random() < 0.8:
+                    w, d = rng.uniform(8.0, 22.0, size=2)
+                    y0 = side * rng.uniform(3.8, 40.0)
+                    y0 = y0 if side > 0 else y0 - d
+                    boxes.append([xg, y0, 0.0, xg + w, y0 + d, rng.uniform(0.25, 0.7), rng.uniform(1.5, 5.0)])
+            xg += rng.uniform(6.0, 14.0)
+        xp = -140.0
+        while xp < length:   # poles / sign posts
+            for side in (-1.0, 1.0):
+                cyl.append([xp + rng.uniform(-2, 2), side * rng.uniform(7.0, 8.5), rng.uniform(0.08, 0.3),
+                            rng.uniform(3.0, 9.0)])
+            xp += rng.uniform(8.0, 16.0)
 
     def raycast(self, o, d, max_range, ray_seed=0):
         """o, d: (n,3) origins / unit directions in the world. Returns range (n,), inf where nothing is hit."""
@@ -176,7 +255,8 @@ def generate_scan(scene, traj, sensor, frame_idx, seed=1234, noise_sigma=0.02, r
     rng = np.random.default_rng(seed + 7919 * frame_idx)
     t0 = frame_idx * sensor.period
     az_idx = np.arange(sensor.n_azimuth)
-    elev = np.deg2rad(np.linspace(sensor.elev_max_deg, sensor.elev_min_deg, sensor.n_rings))
+    elev = np.deg2rad(np.asarray(sensor.elev_table_deg) if sensor.elev_table_deg is not None
+                      else np.linspace(sensor.elev_max_deg, sensor.elev_min_deg, sensor.n_rings))
     az = -2.0 * np.pi * az_idx / sensor.n_azimuth        # clockwise spin like a Velodyne
     frac = (az_idx + 0.5) / sensor.n_azimuth
     AZ, EL = np.meshgrid(az, elev, indexing="xy")          # (rings, az)

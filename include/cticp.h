@@ -358,6 +358,11 @@ int64_t cticp_odometry_write_points(cticp_odometry *h, int which, const cticp_cl
 /* RegistrationSummary::{corrected_points, all_corrected_points, keypoints}, include/ct_icp/odometry.h:187-191.
  * Copies min(cap, count) points device->host; returns the count or a negative status. */
 int64_t cticp_odometry_get_points(cticp_odometry *h, int which, cticp_wpoint *dst, size_t cap);
+/* RegistrationSummary returns its three point vectors BY VALUE from every RegisterFrame (src/ct_icp/odometry.cpp:462-486,
+ * 597). mask: bit CTICP_POINTS_* set = that vector is produced eagerly by every following cticp_odometry_register_* call
+ * (world coordinates transformed and copied to pinned host memory on a second stream, next to the map update), so the
+ * cticp_odometry_get_points that follows only assembles the 64-byte records. 0 (default) = on demand. */
+int cticp_odometry_set_summary_points(cticp_odometry *h, int mask);
 
 /* ct_icp::Odometry::Trajectory(), src/ct_icp/odometry.cpp:687-689 */
 int64_t cticp_odometry_trajectory(cticp_odometry *h, cticp_frame *dst, size_t cap);

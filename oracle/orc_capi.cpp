@@ -590,3 +590,55 @@ extern "C" double orc_ct_point_to_plane_residual(double alpha, const double ref[
                                                  double *local_jac12) {
     return orc::CTResidualForTest(alpha, ref, raw, normal, weight, qb, tb, qe, te, local_jac12);
 }
+
+/* ---- taps for tests/test_math_pins.py: the out-of-tree arithmetic one function at a time ---- */
+namespace orc {
+void LossEvaluateForTest(const cticp_icp_options &o, double s, double rho[3]);
+void CorrectorForTest(double s, const double rho[3], double *residual_scale, double *jacobian_scale);
+void QuatPlusForTest(const double q[4], const double delta[3], double out[4]);
+void SolveLMForTest(const cticp_icp_options &o, int n, const double *alpha, const double *ref, const double *raw,
+                    const double *normal, const double *weight, double *x, double out[5]);
+}
+extern "C" void orc_loss_evaluate(const cticp_icp_options *o, double s, double rho[3]) { orc::LossEvaluateForTest(*o, s, rho); }
+extern "C" void orc_corrector(double s, const double rho[3], double *residual_scale, double *jacobian_scale) {
+    orc::CorrectorForTest(s, rho, residual_scale, jacobian_scale);
+}
+extern "C" void orc_quat_plus(const double q[4], const double delta[3], double out[4]) { orc::QuatPlusForTest(q, delta, out); }
+extern "C" void orc_lm_solve_plane_blocks(const cticp_icp_options *o, int n, const double *alpha, const double *ref,
+                                          const double *raw, const double *normal, const double *weight, double *x14,
+                                          double out5[5]) {
+    orc::SolveLMForTest(*o, n, alpha, ref, raw, normal, weight, x14, out5);
+}
+// Eigen Quaternion(Matrix3) (ct_icp.cpp:950-954), row-major 3x3 in
+extern "C" void orc_quat_from_matrix(const double R[9], double q[4]) {
+    orc::Mat3 m;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) m(i, j) = R[3 * i + j];
+    const orc::Quat r = orc::Quat::fromRotationMatrix(m);
+    q[0] = r.x; q[1] = r.y; q[2] = r.z; q[3] = r.w;
+}
+extern "C" void orc_quat_to_matrix(const double q[4], double R[9]) {
+    const orc::Mat3 m = orc::Quat(q[0], q[1], q[2], q[3]).toRotationMatrix();
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = m(i, j);
+}
+// JacobiSVD<Matrix3d>(C, ComputeFullV) stand-in (neighborhood.h:293): singular values descending, V row-major
+extern "C" void orc_symmetric_svd3(const double C9[9], double sv[3], double V9[9]) {
+    orc::Mat3 c, v;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c(i, j) = C9[3 * i + j];
+    orc::SymmetricSVD3(c, sv, v);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V9[3 * i + j] = v(i, j);
+}
+// Matrix<12,12>.ldlt().solve(b) stand-in (ct_icp.cpp:914)
+extern "C" void orc_ldlt_solve12(const double A144[144], const double b12[12], double x12[12]) {
+    double A[12][12];
+    std::array<double, 12> b;
+    for (int i = 0; i < 12; ++i) {
+        b[i] = b12[i];
+        for (int j = 0; j < 12; ++j) A[i][j] = A144[12 * i + j];
+    }
+    const std::array<double, 12> x = orc::LDLTSolve<12>(A, b);
+    for (int i = 0; i < 12; ++i) x12[i] = x[i];
+}

@@ -575,6 +575,34 @@ double CTResidualForTest(double alpha, const double ref[3], const double raw[3],
                                  local_jac12);
 }
 
+// KAT taps for tests/test_math_pins.py (checked there against numpy / scipy and an independent Python transcription of
+// ceres::Solve): the loss functions, the Corrector, the quaternion Plus, and SolveLM on explicit point-to-plane blocks.
+void LossEvaluateForTest(const cticp_icp_options &o, double s, double rho[3]) { Loss(o).Evaluate(s, rho); }
+void CorrectorForTest(double s, const double rho[3], double *residual_scale, double *jacobian_scale) {
+    Corrector1D(s, rho, *residual_scale, *jacobian_scale);
+}
+void QuatPlusForTest(const double q[4], const double delta[3], double out[4]) { QuatPlus(q, delta, out); }
+// x: 14 parameters in program order qb(4) qe(4) tb(3) te(3), optimised in place; out = {initial cost, final cost,
+// successful steps, unsuccessful steps, usable}
+void SolveLMForTest(const cticp_icp_options &o, int n, const double *alpha, const double *ref, const double *raw,
+                    const double *normal, const double *weight, double *x, double out[5]) {
+    Problem problem(o);
+    problem.num_threads = 1;
+    for (int i = 0; i < n; ++i) {
+        ResidualBlock rb;
+        rb.kind = CTICP_DIST_POINT_TO_PLANE;
+        rb.alpha = alpha[i];
+        rb.reference = Vec3(ref[3 * i], ref[3 * i + 1], ref[3 * i + 2]);
+        rb.raw = Vec3(raw[3 * i], raw[3 * i + 1], raw[3 * i + 2]);
+        rb.normal = Vec3(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+        rb.weight = weight[i];
+        problem.blocks.push_back(rb);
+    }
+    const SolveSummary sum = SolveLM(problem, x, o.ls_max_num_iters);
+    out[0] = sum.initial_cost; out[1] = sum.final_cost; out[2] = sum.num_successful; out[3] = sum.num_unsuccessful;
+    out[4] = sum.usable ? 1.0 : 0.0;
+}
+
 // One ICP iteration's tail shared by solvers CERES and ROBUST: GetProblem (ct_icp.cpp:409-424), the motion model's
 // regularisers, ceres::Solve, the stop criterion (:613-672 / :1291-1336). Returns 0 = continue, 1 = converged,
 // 2 = not enough residuals (`failed` filled).

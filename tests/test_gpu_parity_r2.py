@@ -1,0 +1,180 @@
+"""GPU parity tests, second batch: the holes round 1 left open.
+
+* scans whose coordinates / timestamps are genuinely fp64 (not float32-representable);
+* a trajectory 5 km away from the origin (fp32 voxel-local storage, fp64 arithmetic);
+* BASELINE.json configs[0]'s map (legacy resolution 0.2 m → stencil radius 4 = 729 voxels);
+* the bench scene (suburb, HDL-64E ring table);
+* the summary's point vectors produced eagerly (cticp_odometry_set_summary_points) against the on-demand path and the oracle;
+* an engine on a second device of the same process (__constant__ tables are per device).
+"""
+import numpy as np
+import pytest
+
+from conftest import frame_diff, get_sequence
+from ct_icp_b200 import _abi as abi
+from test_gpu_parity import POSE_TOL_M, POSE_TOL_RAD, _estimate_from, _run_sequence, _sequence_options
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(ro, re_, exact_counts=True):
+    worst_t = worst_r = 0.0
+    for i, ((so, mo), (se, me)) in enumerate(zip(ro, re_)):
+        assert so.success and se.success, (i, so.error_message, se.error_message)
+        if exact_counts:
+            assert so.num_corrected_points == se.num_corrected_points, i
+            assert so.num_keypoints == se.num_keypoints, i
+            assert so.number_of_residuals == se.number_of_residuals, i
+            assert mo == me, i
+        dt, dr = frame_diff(so.frame, se.frame)
+        worst_t, worst_r = max(worst_t, dt), max(worst_r, dr)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)
+    return worst_t, worst_r
+
+
+def test_fp64_scan_coordinates_and_timestamps(orc, eng):
+    """The reference reads XYZConst<double>() / TimestampsProxy<double>() (odometry.cpp:335-336): nothing says the scan is
+    float32-representable. The engine keeps (x, y, z, alpha) as fp32 on the device (include/cticp.h, "ingest precision"):
+    a coordinate moves by <= 4e-6 m at 60 m range, which can move a point across a voxel boundary of the samplers (the
+    sample SETS may differ in a handful of points), never the pose beyond the 1e-4 bound."""
+    rng = np.random.default_rng(99)
+    seq = []
+    for s in get_sequence("small16", 8):
+        xyz = s["xyz"] + rng.uniform(-3e-6, 3e-6, size=s["xyz"].shape)        # not representable in fp32
+        t = s["t"] + rng.uniform(0.0, 1e-9, size=s["t"].shape)
+        assert np.any(xyz.astype(np.float32).astype(np.float64) != xyz)
+        seq.append(dict(s, xyz=xyz, t=t))
+    _, ro = _run_sequence(orc, seq, init_num_frames=4)
+    _, re_ = _run_sequence(eng, seq, init_num_frames=4)
+    wt, wr = _compare(ro, re_, exact_counts=False)
+    for (so, _), (se, _) in zip(ro, re_):
+        # sample sizes: the same up to the few points that sit within 4e-6 m of a voxel face
+        assert abs(int(so.num_corrected_points) - int(se.num_corrected_points)) <= max(3, so.num_corrected_points // 1000)
+        assert abs(int(so.num_keypoints) - int(se.num_keypoints)) <= max(3, so.num_keypoints // 200)
+    print("fp64 scans: worst per-frame pose difference %.3e m, %.3e rad" % (wt, wr))
+
+
+def _run_offset(b, seq, offset, yaw):
+    """Every frame registered with an estimate: frame 0 at `offset`/`yaw`, the others at the previous end pose."""
+    od = b.odometry(_sequence_options(b, "GN", init_num_frames=4))
+    out, prev = [], None
+    for i, s in enumerate(seq):
+        t0, t1 = float(s["t"].min()), float(s["t"].max())
+        if i == 0:
+            est = abi.Frame()
+            for dst, ts in ((est.begin_pose, t0), (est.end_pose, t1)):
+                dst.quat[0], dst.quat[1], dst.quat[2], dst.quat[3] = 0.0, 0.0, np.sin(yaw / 2), np.cos(yaw / 2)
+                dst.tr[0], dst.tr[1], dst.tr[2] = offset
+                dst.ref_timestamp, dst.dest_timestamp = 0.0, ts
+                dst.ref_frame_id, dst.dest_frame_id = 0, s["frame_idx"]
+        else:
+            est = _estimate_from(prev.frame, t0, t1, s["frame_idx"])
+        sm = od.RegisterFrameWithEstimate(s["xyz"], s["t"], est, s["frame_idx"])
+        prev = sm
+        out.append((sm, od.MapSize()))
+    return od, out
+
+
+def test_trajectory_five_kilometres_from_the_origin(orc, eng):
+    """World coordinates of 5-7 km: map points are stored as fp32 offsets from their voxel origin, everything else is
+    fp64 — the pose difference to the oracle must not grow with the distance from the origin (SURVEY §7 hard parts)."""
+    seq = get_sequence("small16", 8)
+    offset, yaw = (5123.4567, -3987.6543, 211.125), 0.7
+    odo, ro = _run_offset(orc, seq, offset, yaw)
+    ode, re_ = _run_offset(eng, seq, offset, yaw)
+    wt, wr = _compare(ro, re_)
+    assert np.linalg.norm(np.array(re_[-1][0].frame.end_pose.tr) - np.array(offset)) < 50.0   # it stayed out there
+    assert np.array_equal(odo.GetMapPointer().export(0)[1], ode.GetMapPointer().export(0)[1])
+    xo, xe = odo.GetMapPointer().export(0)[0], ode.GetMapPointer().export(0)[0]
+    assert np.abs(xo - xe).max() < 2e-7 + 1e-4      # stored map points: pose tolerance + fp32 voxel-local quantum
+    print("5 km offset: worst per-frame pose difference %.3e m, %.3e rad" % (wt, wr))
+
+
+def test_config0_legacy_map_stencil_radius_4(orc, eng):
+    """BASELINE.json configs[0] (config/synthetic_ct_icp_config.yaml as the reference actually loads it): no
+    map_options → legacy resolution 0.2 m, 20 points per voxel, min distance 0.05, search radius 0.8 → r = 4, a 729-voxel
+    stencil; CT_ICP_GN, 5 iterations, ~10k-point scans."""
+    seq = get_sequence("small16", 8)
+
+    def run(b):
+        o = _sequence_options(b, "GN", init_num_frames=4)
+        o.map_options = b.legacy_map_options(0.2, 20, 0.05)
+        o.ct_icp_options.num_iters_icp = 5
+        od = b.odometry(o)
+        out = []
+        for s in seq:
+            sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+            out.append((sm, od.MapSize()))
+        return od, out
+
+    odo, ro = run(orc)
+    ode, re_ = run(eng)
+    wt, wr = _compare(ro, re_)
+    assert np.array_equal(odo.GetMapPointer().export(0)[1], ode.GetMapPointer().export(0)[1])
+    print("configs[0] (729-voxel stencil): worst per-frame pose difference %.3e m, %.3e rad" % (wt, wr))
+
+
+def test_bench_scene_suburb_hdl64e_gn(orc, eng):
+    """The bench workload (bench.py: suburb scene, HDL-64E ring table, configs[1] options) through the start-up regime
+    into the steady state."""
+    from ct_icp_b200 import synthetic as syn
+    seq = syn.make_sequence(24, syn.HDL64E, seed=1234, scene=syn.UrbanScene(1234, profile="suburb"))
+
+    def opts(b):
+        o = _sequence_options(b, "GN")
+        o.ct_icp_options.num_iters_icp = 5
+        o.voxel_size, o.sample_voxel_size, o.max_distance = 0.5, 1.5, 100.0
+        return o
+
+    def run(b):
+        od = b.odometry(opts(b))
+        return od, [(od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]), od.MapSize()) for s in seq]
+
+    odo, ro = run(orc)
+    ode, re_ = run(eng)
+    wt, wr = _compare(ro, re_)
+    gt = np.linalg.inv(seq[0]["gt_end"]) @ seq[-1]["gt_end"]
+    est = np.array(re_[-1][0].frame.end_pose.tr)
+    assert np.linalg.norm(est - gt[:3, 3]) < 0.5, (est, gt[:3, 3])   # and it tracks the ground truth
+    print("suburb / HDL-64E: F %d K %d, worst per-frame pose difference %.3e m, %.3e rad"
+          % (re_[-1][0].num_corrected_points, re_[-1][0].num_keypoints, wt, wr))
+
+
+def test_eager_summary_points_match_on_demand_and_oracle(orc, eng, seq_small):
+    """cticp_odometry_set_summary_points(7): the three vectors of RegistrationSummary (odometry.cpp:462-486,597) produced
+    by every RegisterFrame on the egress stream == the vectors computed on demand == the oracle's."""
+    oo = orc.odometry(_sequence_options(orc, "GN", init_num_frames=4))
+    lazy = eng.odometry(_sequence_options(eng, "GN", init_num_frames=4))
+    eager = eng.odometry(_sequence_options(eng, "GN", init_num_frames=4))
+    eager.set_summary_points(7)
+    for s in seq_small:
+        so = oo.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        sl = lazy.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        se = eager.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+        assert frame_diff(sl.frame, se.frame) == (0.0, 0.0)
+        for which in (abi.POINTS_CORRECTED, abi.POINTS_ALL_CORRECTED, abi.POINTS_KEYPOINTS):
+            a, b, c = oo.points(which), lazy.points(which), eager.points(which)
+            assert len(a) == len(b) == len(c), which
+            if len(a) == 0:
+                continue
+            assert np.array_equal(b["raw"], c["raw"]) and np.array_equal(b["world"], c["world"]), which
+            assert np.array_equal(b["timestamp"], c["timestamp"]) and np.array_equal(b["index_frame"], c["index_frame"])
+            assert np.abs(a["world"] - c["world"]).max() < POSE_TOL_M, which
+            assert np.abs(a["raw"] - c["raw"]).max() == 0.0, which
+            assert np.abs(a["timestamp"] - c["timestamp"]).max() < 1e-7, which
+        assert so.num_keypoints == se.num_keypoints
+
+
+def test_engine_on_a_second_device_of_the_same_process(eng, seq_small):
+    """One process, two GPUs (the C ABI takes a device index): the tables the ICP kernels read from __constant__ memory
+    exist per device. Needs 2 visible GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 visible GPUs")
+    res = []
+    for device in (0, 1):
+        od = eng.odometry(_sequence_options(eng, "GN", init_num_frames=4), device)
+        res.append([od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]) for s in seq_small])
+    for a, b in zip(*res):
+        assert a.success and b.success
+        assert frame_diff(a.frame, b.frame) == (0.0, 0.0)

@@ -30,6 +30,9 @@ SAMPLING = {"NONE": 0, "GRID": 1, "ADAPTIVE": 2}
 MOTION_MODEL = {"CONSTANT_VELOCITY": 0, "SMALL_VELOCITY": 1}
 
 POINTS_CORRECTED, POINTS_ALL_CORRECTED, POINTS_KEYPOINTS = 0, 1, 2
+EVENT_BEFORE_ITERATION, EVENT_ITERATION_COMPLETED, EVENT_FINISHED_REGISTRATION = 0, 1, 2
+EVENT_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p)   # cticp_event_fn
+ERR_CALLBACK = -9
 
 
 class _Struct(C.Structure):
@@ -169,6 +172,10 @@ class Pose(_Struct):
 
 class Frame(_Struct):
     _fields_ = [("begin_pose", Pose), ("end_pose", Pose)]
+
+
+class MotionPrior(_Struct):   # cticp_motion_prior: the AMotionModel* argument of RegisterFrame (a PreviousFrameMotionModel)
+    _fields_ = [("options", MotionModelOptions), ("previous_frame", Frame)]
 
 
 class WPoint(_Struct):

@@ -93,6 +93,9 @@ class Binding:
             "odometry_flush_l2": (C.c_int, [vp, sz]),
             "odometry_set_gather_timing": (C.c_int, [vp, C.c_int]),
             "odometry_set_summary_points": (C.c_int, [vp, C.c_int]),
+            "odometry_register_frame_ex": (C.c_int, [vp, vp, sz, vp, sz, sz, u32, P(abi.Frame), P(abi.MotionPrior), P(abi.Summary)]),
+            "odometry_set_callback": (C.c_int, [vp, abi.EVENT_FN, vp]),
+            "odometry_reset_options": (C.c_int, [vp, P(abi.OdometryOptions)]),
             "odometry_enable_sharding": (C.c_int, [vp, vp, C.c_int, C.c_int]),
             "odometry_sharding_mode": (C.c_int, [vp]),
             # oracle only (KAT taps)
@@ -324,8 +327,31 @@ class Odometry:
             frame_id, C.byref(initial_estimate) if initial_estimate is not None else None, C.byref(summary)))
         return summary
 
-    def RegisterFrame(self, xyz, timestamps, frame_id):
+    def RegisterFrame(self, xyz, timestamps, frame_id, motion_model=None):
+        """motion_model: an abi.MotionPrior — the AMotionModel* of the reference's overloads (odometry.h:231-248)"""
+        if motion_model is not None:
+            return self._register_ex(xyz, timestamps, frame_id, None, motion_model)
         return self._register(xyz, timestamps, frame_id, None)
+
+    def _register_ex(self, xyz, timestamps, frame_id, initial_estimate, motion_model):
+        xyz = np.ascontiguousarray(np.asarray(xyz)[:, :3], dtype=np.float64)
+        timestamps = np.ascontiguousarray(timestamps, dtype=np.float64).reshape(-1)
+        summary = abi.Summary()
+        self.b.check(self.b.fn("odometry_register_frame_ex")(
+            self.h, xyz.ctypes.data, xyz.strides[0], timestamps.ctypes.data, timestamps.strides[0], len(xyz), frame_id,
+            C.byref(initial_estimate) if initial_estimate is not None else None,
+            C.byref(motion_model) if motion_model is not None else None, C.byref(summary)))
+        return summary
+
+    def RegisterCallback(self, fn):
+        """fn(event) -> bool, called at BEFORE_ITERATION / ITERATION_COMPLETED / FINISHED_REGISTRATION
+        (Odometry::RegisterCallback, odometry.h:260); None removes it."""
+        self._callback = abi.EVENT_FN(lambda event, user: 1 if fn(event) else 0) if fn else abi.EVENT_FN()
+        self.b.check(self.b.fn("odometry_set_callback")(self.h, self._callback, None))
+
+    def ResetWithOptions(self, options):        # Odometry::Reset(const OdometryOptions&), odometry.h:269
+        self.options = options.copy()
+        self.b.check(self.b.fn("odometry_reset_options")(self.h, C.byref(self.options)))
 
     def RegisterFrameWithEstimate(self, xyz, timestamps, initial_estimate, frame_id):
         return self._register(xyz, timestamps, frame_id, initial_estimate)

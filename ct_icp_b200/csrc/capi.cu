@@ -27,6 +27,8 @@ int Guard(F &&f) {
         return Fail(CTICP_ERR_UNSUPPORTED, e.what());
     } catch (const CapacityError &e) {
         return Fail(CTICP_ERR_CAPACITY, e.what());
+    } catch (const cticp::CallbackError &e) {
+        return Fail(CTICP_ERR_CALLBACK, e.what());
     } catch (const CudaError &e) {
         return Fail(CTICP_ERR_CUDA, e.what());
     } catch (const std::invalid_argument &e) {
@@ -323,6 +325,38 @@ int cticp_odometry_register_frame(cticp_odometry *h, const double *xyz, size_t x
         cticp::ScanView v;
         v.xyz = xyz; v.xyz_stride = xyz_stride_bytes; v.t = t; v.t_stride = t_stride_bytes; v.n = n;
         h->engine->RegisterFrame(v, frame_id, initial_estimate, out_summary);
+        return (int) CTICP_OK;
+    });
+}
+int cticp_odometry_register_frame_ex(cticp_odometry *h, const double *xyz, size_t xyz_stride_bytes, const double *t,
+                                     size_t t_stride_bytes, size_t n, uint32_t frame_id,
+                                     const cticp_frame *initial_estimate, const cticp_motion_prior *motion_model,
+                                     cticp_summary *out_summary) {
+    return Guard([&] {
+        if (!h) throw std::invalid_argument("null handle");
+        cticp::ScanView v;
+        v.xyz = xyz; v.xyz_stride = xyz_stride_bytes; v.t = t; v.t_stride = t_stride_bytes; v.n = n;
+        h->engine->RegisterFrame(v, frame_id, initial_estimate, out_summary, motion_model);
+        return (int) CTICP_OK;
+    });
+}
+int cticp_odometry_set_callback(cticp_odometry *h, cticp_event_fn fn, void *user) {
+    return Guard([&] {
+        if (!h) throw std::invalid_argument("null handle");
+        h->engine->SetCallback(fn, user);
+        return (int) CTICP_OK;
+    });
+}
+int cticp_odometry_reset_options(cticp_odometry *h, const cticp_odometry_options *options) {
+    return Guard([&] {
+        if (!h || !options) throw std::invalid_argument("null argument");
+        const int device = h->engine->Device();
+        Engine *fresh = new Engine(*options, device);   // throws before the old engine is touched
+        delete h->engine;
+        h->engine = fresh;
+        h->map_view.map = &h->engine->Map();
+        h->map_view.icp = &h->engine->Solver();
+        h->map_view.stream = h->engine->Stream();
         return (int) CTICP_OK;
     });
 }

@@ -582,6 +582,12 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
                            (!at_startup && options_.max_num_keypoints > 0) ? options_.max_num_keypoints : -1,
                            options_.shuffle_seed, ShuffleCounter(k, 2 + attempt_idx), &options_.adaptive_options);
     rs.t_sampling = ms_since(t0);
+    if (callback_) {   // odometry.cpp:568: the keypoint count is needed on the host for the hook's GetPoints
+        pipe_->QueueCountsReadback();
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        staging_in_flight_ = false;
+        FireEvent(CTICP_EVENT_BEFORE_ITERATION, rs, info);
+    }
     if (at_startup) {
         options.threshold_voxel_occupancy = 1;
         options.num_iters_icp = std::max(options.num_iters_icp, 15);
@@ -659,6 +665,24 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
                  S.n_used);
         rs.error_message = buf;
     }
+    // ICPSummary durations (ct_icp.cpp:664-666,690-694), milliseconds on the device: the ICP kernels between the two
+    // events; the neighborhood / solve split of an iteration from the solver CTA's cycle stamps where the loop is one
+    // persistent launch (solver GN), else the whole iteration is reported as neighborhood time
+    {
+        float icp_ms = 0.f;
+        if (cudaEventElapsedTime(&icp_ms, ev_[1], ev_[2]) != cudaSuccess) {
+            cudaGetLastError();
+            icp_ms = 0.f;
+        }
+        const int iters = std::max(1, (int) S.iter);
+        rs.icp.duration_total = icp_ms;
+        rs.icp.duration_init = 0.0;
+        rs.icp.avg_duration_iter = icp_ms / iters;
+        const double share = (S.cycles_total > 0) ? std::min(1.0, (double) S.cycles_solve / (double) S.cycles_total) : 0.0;
+        rs.icp.avg_duration_solve = rs.icp.avg_duration_iter * share;
+        rs.icp.avg_duration_neighborhood = rs.icp.avg_duration_iter - rs.icp.avg_duration_solve;
+    }
+    FireEvent(CTICP_EVENT_ITERATION_COMPLETED, rs, info);   // odometry.cpp:600
 }
 
 // AssessRegistration, odometry.cpp:604-684
@@ -797,9 +821,20 @@ void Engine::UpdateMap(Summary &s, int registered_fid) {
 
 // RegisterFrame / RegisterFrameWithEstimate (odometry.cpp:199-236) → DoRegister (:386-501)
 void Engine::RegisterFrame(const ScanView &scan, uint32_t frame_id, const cticp_frame *initial_estimate,
-                           cticp_summary *out) {
+                           cticp_summary *out, const cticp_motion_prior *motion_model) {
     if (scan.n == 0 || !scan.xyz || !scan.t) throw std::invalid_argument("The registered frame cannot be empty");
-    RegisterCommon(scan, frame_id, initial_estimate, -1, out);
+    RegisterCommon(scan, frame_id, initial_estimate, -1, out, motion_model);
+}
+
+// IterateOverCallbacks, odometry.cpp:742-750. The hook may fetch the frame / the keypoints (GetPoints) under the pose pair
+// of this moment.
+void Engine::FireEvent(int event, const Summary &rs, const FrameInfo &info) {
+    if (!callback_) return;
+    last_frame_ = rs.frame;
+    last_info_ = info;
+    frame_world_valid_ = last_all_world_valid_ = last_kp_world_valid_ = false;
+    egress_valid_[0] = egress_valid_[1] = egress_valid_[2] = false;
+    if (!callback_(event, callback_user_)) throw CallbackError("Callback returned false");
 }
 void Engine::RegisterStaged(int64_t slot, uint32_t frame_id, cticp_summary *out) {
     if (slot < 0 || slot >= (int64_t) staged_.size()) throw std::invalid_argument("unknown staged slot");
@@ -809,7 +844,7 @@ void Engine::RegisterStaged(int64_t slot, uint32_t frame_id, cticp_summary *out)
 }
 
 void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp_frame *initial_estimate,
-                            int64_t staged_slot, cticp_summary *out) {
+                            int64_t staged_slot, cticp_summary *out, const cticp_motion_prior *motion_model) {
     const size_t n = scan.n;
     auto t_start = hclock::now();
     CT_CUDA_CHECK(cudaSetDevice(device_));
@@ -817,7 +852,7 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     memset(&timing_, 0, sizeof(timing_));
     icp_->reset_timing();
     const int launches0 = map_->launches() + pipe_->launches() + icp_->launches();
-    last_all_world_valid_ = last_kp_world_valid_ = false;
+    last_all_world_valid_ = last_kp_world_valid_ = frame_world_valid_ = false;
     egress_valid_[0] = egress_valid_[1] = egress_valid_[2] = false;
     if (egress_pending_) {   // the previous frame's egress still reads d_raw / d_frame_world / the keypoints
         CT_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_egress_done_, 0));
@@ -871,7 +906,13 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     bool ran_icp = false;
     if (k > 0) {
         const MotionModel *mm = nullptr;
-        if (options_.with_default_motion_model) {   // odometry.cpp:412-417
+        MotionModel caller_model;
+        if (motion_model) {   // the caller's AMotionModel* (a PreviousFrameMotionModel in its current state)
+            caller_model.present = true;
+            caller_model.options = motion_model->options;
+            caller_model.previous_frame = FrameFromC(motion_model->previous_frame);
+            mm = &caller_model;
+        } else if (options_.with_default_motion_model) {   // odometry.cpp:412-417
             default_motion_model_.present = true;
             default_motion_model_.options = options_.default_motion_model;
             default_motion_model_.previous_frame = trajectory_[k - 1];
@@ -909,6 +950,7 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     if (!early_return) {
         const auto &f = summary.frame;
         pipe_->TransformFrame(f.begin_pose.pose.q, f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t);
+        frame_world_valid_ = true;
         if (summary_points_mask_) {
             if (!ran_icp) {   // frame 0: no pose read-back has synchronised the stream yet; the egress reads N and F
                 CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -918,6 +960,13 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
         }
         ComputeSummaryMetrics(summary, k);
         UpdateMap(summary, k);
+        if (callback_) {   // odometry.cpp:491
+            const bool fw = frame_world_valid_, aw = last_all_world_valid_, kw = last_kp_world_valid_;
+            const bool e0 = egress_valid_[0], e1 = egress_valid_[1], e2 = egress_valid_[2];
+            FireEvent(CTICP_EVENT_FINISHED_REGISTRATION, summary, info);
+            frame_world_valid_ = fw; last_all_world_valid_ = aw; last_kp_world_valid_ = kw;   // same pose pair: still valid
+            egress_valid_[0] = e0; egress_valid_[1] = e1; egress_valid_[2] = e2;
+        }
     }
     CT_CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
     tail_event_valid_ = true;
@@ -996,6 +1045,10 @@ void Engine::ResolvePoints(int which, const float4 **out_pts, const double **out
     const auto &f = last_frame_;
     switch (which) {
         case CTICP_POINTS_CORRECTED:
+            if (!frame_world_valid_) {
+                pipe_->TransformFrame(f.begin_pose.pose.q, f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t);
+                frame_world_valid_ = true;
+            }
             d_pts = pipe_->d_frame();
             d_world = pipe_->d_frame_world();
             count = (size_t) pipe_->h_counts()[1];

@@ -55,6 +55,10 @@ struct ScanView {
 // condition variable (what OpenMP runtimes do by default, cf. GOMP_SPINCOUNT): when frames arrive back to back the
 // team starts within a microsecond instead of a futex wake-up per worker (~50 us for 15 workers); at sensor rate
 // (10-20 Hz) the polling is a ~1 % duty cycle. The caller polls for completion as well (the job is ~50 us long).
+struct CallbackError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
 class HostPool {
 public:
     explicit HostPool(int threads);
@@ -84,8 +88,10 @@ public:
     Engine(const cticp_odometry_options &options, int device);
     ~Engine();
 
-    void RegisterFrame(const ScanView &scan,
-                       uint32_t frame_id, const cticp_frame *initial_estimate, cticp_summary *out);
+    void RegisterFrame(const ScanView &scan, uint32_t frame_id, const cticp_frame *initial_estimate, cticp_summary *out,
+                       const cticp_motion_prior *motion_model = nullptr);
+    void SetCallback(cticp_event_fn fn, void *user) { callback_ = fn; callback_user_ = user; }
+    const cticp_odometry_options &Options() const { return options_; }
     // device-resident input: pack + copy a scan to HBM now, register it later
     int64_t StageFrame(const ScanView &scan);
     int64_t WritePoints(int which, const cticp_cloud_sink &sink);
@@ -145,9 +151,12 @@ private:
     void MinMaxTimestamps(const ScanView &scan, double *mn_out, double *mx_out);
     std::unique_ptr<HostPool> pool_;
     static int HostTeamSize(int ranks_on_node);
-    void RegisterCommon(const ScanView &scan,
-                        uint32_t frame_id, const cticp_frame *initial_estimate, int64_t staged_slot,
-                        cticp_summary *out);
+    void RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp_frame *initial_estimate,
+                        int64_t staged_slot, cticp_summary *out, const cticp_motion_prior *motion_model = nullptr);
+    void FireEvent(int event, const Summary &rs, const FrameInfo &info);
+    cticp_event_fn callback_ = nullptr;
+    void *callback_user_ = nullptr;
+    bool frame_world_valid_ = false;   // d_frame_world holds the sub-sampled frame under last_frame_
     struct StagedScan {
         float4 *d_points = nullptr;
         size_t n = 0;

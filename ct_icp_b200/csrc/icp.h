@@ -32,7 +32,10 @@ struct IcpState {
     double slerp_theta, slerp_inv_sin;
     int slerp_linear, slerp_negate;
     unsigned long long stat_keypoint_iters, stat_stencil_points;
-    unsigned long long dbg_t[4];   // %globaltimer stamps of the last iteration: CTA0 start, last-CTA elected, reduced, solved
+    unsigned long long dbg_t[4];   // SM cycle stamps of the last iteration (CTICP_DEBUG_TIMERS builds)
+    // SM cycles of the solver CTA over the persistent GN loop: whole loop, and the reduce + solve part of it (the rest is
+    // the neighborhood / residual assembly it waits for) — the split behind ICPSummary::avg_duration_neighborhood / _solve
+    unsigned long long cycles_total, cycles_solve;
 };
 
 inline void icp_state_refresh_slerp(IcpState &S) {

@@ -457,6 +457,8 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
         __syncwarp();
     }
 
+    long long t_loop = 0, t_solve = 0;
+    if (solver_cta && threadIdx.x == 0) t_loop = clock64();
     for (int it = 0; it < num_iters; ++it) {
         if (__ldcg(&st->done)) break;   // uniform: written before the previous grid barrier
         if (!solver_cta) {
@@ -484,6 +486,7 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
         grid.sync();
         if (solver_cta) {
             CT_STAMP(if (threadIdx.x == 0) st->dbg_t[1] = global_timer_ns();)
+            const long long t_begin = threadIdx.x == 0 ? clock64() : 0;
             gn_reduce_rows(sh, partials, gather_ctas, lane, w);
             bool peers_ok = true;
             if (kPeers) {
@@ -504,10 +507,15 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 } else
                     warp_gn_solve(sh.acc[0], sh.solve, st, P, 0, nullptr, lane);
                 CT_STAMP(if (lane == 0) st->dbg_t[3] = global_timer_ns();)
+                if (lane == 0) t_solve += clock64() - t_begin;
             }
             __threadfence();
         }
         grid.sync();
+    }
+    if (solver_cta && threadIdx.x == 0) {
+        st->cycles_total = (unsigned long long) (clock64() - t_loop);
+        st->cycles_solve = (unsigned long long) t_solve;
     }
     if (kPeers && solver_cta && threadIdx.x == 0) *links.seq = peer_seq;
 }

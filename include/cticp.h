@@ -39,7 +39,8 @@ typedef enum cticp_status {
     CTICP_ERR_TIMESTAMP = -5,     /* reference: CHECK in TPose::InterpolatePose, include/SlamCore/types.h:456 */
     CTICP_ERR_UNSUPPORTED = -6,   /* option combination outside the built hot path */
     CTICP_ERR_NCCL = -7,
-    CTICP_ERR_INTERNAL = -8
+    CTICP_ERR_INTERNAL = -8,
+    CTICP_ERR_CALLBACK = -9       /* a registered callback returned 0 (reference: CHECK, src/ct_icp/odometry.cpp:748) */
 } cticp_status;
 
 /* ---- enums mirroring the reference (same numeric order) ------------------------------------------------ */
@@ -316,6 +317,29 @@ int cticp_odometry_register_frame(cticp_odometry *h,
                                   const cticp_frame *initial_estimate,
                                   cticp_summary *out_summary);
 
+/* The AMotionModel* argument of the RegisterFrame overloads (include/ct_icp/odometry.h:231-248). The reference's only
+ * concrete model is PreviousFrameMotionModel (include/ct_icp/motion_model.h:35-78): its options and the previous frame it
+ * was updated with. NULL = the reference's nullptr (the odometry's own default model when with_default_motion_model). */
+typedef struct cticp_motion_prior {
+    cticp_motion_model_options options;
+    cticp_frame previous_frame;
+} cticp_motion_prior;
+int cticp_odometry_register_frame_ex(cticp_odometry *h,
+                                     const double *xyz, size_t xyz_stride_bytes,
+                                     const double *t, size_t t_stride_bytes,
+                                     size_t n, uint32_t frame_id,
+                                     const cticp_frame *initial_estimate,      /* nullable */
+                                     const cticp_motion_prior *motion_model,   /* nullable */
+                                     cticp_summary *out_summary);
+
+/* ct_icp::Odometry::RegisterCallback (include/ct_icp/odometry.h:260, src/ct_icp/odometry.cpp:737-750): ONE hook per
+ * handle, called on the registering thread at the reference's three events; inside it the caller may use
+ * cticp_odometry_get_points (frame / keypoints with the pose pair of that moment). Returning 0 aborts the
+ * registration with CTICP_ERR_CALLBACK. fn == NULL removes the hook. */
+enum { CTICP_EVENT_BEFORE_ITERATION = 0, CTICP_EVENT_ITERATION_COMPLETED = 1, CTICP_EVENT_FINISHED_REGISTRATION = 2 };
+typedef int (*cticp_event_fn)(int event, void *user);
+int cticp_odometry_set_callback(cticp_odometry *h, cticp_event_fn fn, void *user);
+
 /* An interleaved point buffer described like a sensor_msgs/PointCloud2 (one record every point_step bytes; field
  * "x" at xyz_offset with y and z following contiguously in the same scalar type — the "vertex" element that
  * SchemaBuilderFromCloud2 builds, ros/roscore/src/pc2_conversion.cxx:73-80 — and one timestamp scalar at t_offset).
@@ -372,6 +396,8 @@ int64_t cticp_odometry_map_size(cticp_odometry *h);
 int64_t cticp_odometry_map_points(cticp_odometry *h, double *dst_xyz, size_t cap_points);
 /* ct_icp::Odometry::Reset(), src/ct_icp/odometry.cpp:956-965 */
 int cticp_odometry_reset(cticp_odometry *h);
+/* ct_icp::Odometry::Reset(const OdometryOptions&), include/ct_icp/odometry.h:269: same handle, new options (new map) */
+int cticp_odometry_reset_options(cticp_odometry *h, const cticp_odometry_options *options);
 /* ct_icp::Odometry::GetMapPointer(), src/ct_icp/odometry.cpp:991-993 (borrowed; owned by the odometry) */
 cticp_map *cticp_odometry_map(cticp_odometry *h);
 

@@ -8,6 +8,7 @@
 #include <random>
 
 #include "ct_icp_b200/odometry.hpp"
+#include "slam_pointcloud_stub.h"
 
 namespace {
 const double kScale = 30., kPlaneLoc = 4. + kScale;
@@ -94,6 +95,78 @@ int main(int argc, char **argv) {
             err = std::sqrt((t[0] - g.tx) * (t[0] - g.tx) + (t[1] - g.ty) * (t[1] - g.ty) + (t[2] - g.tz) * (t[2] - g.tz));
             std::printf("frame %d: keypoints %zu residuals %d end_tr (%.3f %.3f %.3f) gt (%.3f %.3f %.3f) err %.4f\n", i,
                         result.keypoints.size(), result.number_of_residuals, t[0], t[1], t[2], g.tx, g.ty, g.tz, err);
+        }
+        // ---- the rest of the boundary (include/ct_icp/odometry.h:226-272): a second odometry on the same frames through the
+        // slam::PointCloud overload (what odometry_runner.cpp:194 and the ROS node call), with a caller-owned motion model,
+        // callbacks at the three events and Reset(options) — it must reproduce the first trajectory
+        {
+            struct Counter : ct_icp::Odometry::OdometryCallback {
+                int runs = 0;
+                size_t frame_points = 0, keypoints = 0;
+                bool Run(const ct_icp::Odometry &, const std::vector<slam::WPoint3D> &current_frame,
+                         const std::vector<slam::WPoint3D> *kp, const ct_icp::Odometry::RegistrationSummary *) override {
+                    ++runs;
+                    frame_points = current_frame.size();
+                    if (kp) keypoints = kp->size();
+                    return true;
+                }
+            } before, completed, finished;
+            auto options2 = options;
+            options2.voxel_size = 2.0;                      // wrong on purpose: Reset(options) below restores the real ones
+            ct_icp::Odometry second(&options2);             // the pointer constructor (:228)
+            second.Reset(options);
+            second.RegisterCallback(ct_icp::Odometry::OdometryCallback::BEFORE_ITERATION, before);
+            second.RegisterCallback(ct_icp::Odometry::OdometryCallback::ITERATION_COMPLETED, completed);
+            second.RegisterCallback(ct_icp::Odometry::OdometryCallback::FINISHED_REGISTRATION, finished);
+            ct_icp::PreviousFrameMotionModel model;         // same options as the default model: same result expected
+            model.GetOptions() = ct_icp::PreviousFrameMotionModel::Options();
+            static_cast<cticp_motion_model_options &>(model.GetOptions()) = options.default_motion_model;
+            std::mt19937_64 rng2(42);
+            const auto first_trajectory = odometry.Trajectory();
+            for (int i = 0; i < kFrames; ++i) {
+                const auto frame = generate_frame(i, 5000, rng2);
+                slam::PointCloud cloud;
+                for (const auto &p : frame) cloud.push_back(p.raw_point.point[0], p.raw_point.point[1], p.raw_point.point[2], p.raw_point.timestamp);
+                const auto result = second.RegisterFrame(cloud, (slam::frame_id_t) i, &model);
+                if (!result.success) {
+                    std::printf("PointCloud overload failed at frame %d: %s\n", i, result.error_message.c_str());
+                    return 1;
+                }
+                model.UpdateState(result.frame, i);
+                const auto &a = result.frame.end_pose.pose.tr, &b = first_trajectory[i].end_pose.pose.tr;
+                const double d = (a - b).norm();
+                if (d > 1e-9) {
+                    std::printf("PointCloud overload / caller motion model: frame %d differs by %.3e m\n", i, d);
+                    return 1;
+                }
+                if (result.logged_values.count("odometry_total_duration(ms)") == 0 || result.logged_values.count("icp_total_duration") == 0 ||
+                    (i > 0 && !(result.icp_summary.duration_total > 0.0))) {
+                    std::printf("logged_values / icp_summary durations missing\n");
+                    return 1;
+                }
+            }
+            // frame 0 has no ICP: BEFORE / COMPLETED run on kFrames - 1 frames, FINISHED on all
+            if (before.runs != kFrames - 1 || completed.runs != kFrames - 1 || finished.runs != kFrames || before.keypoints == 0 ||
+                finished.frame_points == 0) {
+                std::printf("callbacks: before %d completed %d finished %d\n", before.runs, completed.runs, finished.runs);
+                return 1;
+            }
+            if (second.Map().NumPoints() != odometry.MapConst().NumPoints()) return 1;
+            struct Veto : ct_icp::Odometry::OdometryCallback {
+                bool Run(const ct_icp::Odometry &, const std::vector<slam::WPoint3D> &, const std::vector<slam::WPoint3D> *,
+                         const ct_icp::Odometry::RegistrationSummary *) override { return false; }
+            } veto;
+            second.RegisterCallback(ct_icp::Odometry::OdometryCallback::BEFORE_ITERATION, veto);
+            bool threw = false;
+            try {
+                second.RegisterFrame(generate_frame(kFrames, 5000, rng2));
+            } catch (const ct_icp::CticpFailure &e) {
+                threw = e.code == CTICP_ERR_CALLBACK;   // the reference CHECK-aborts here (odometry.cpp:748)
+            }
+            if (!threw) {
+                std::printf("a callback returning false must abort the registration\n");
+                return 1;
+            }
         }
         auto trajectory = odometry.Trajectory();
         if ((int) trajectory.size() != kFrames || odometry.MapSize() == 0 || odometry.GetMapPointer()->NumPoints() != odometry.MapSize())

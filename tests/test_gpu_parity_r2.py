@@ -178,3 +178,57 @@ def test_engine_on_a_second_device_of_the_same_process(eng, seq_small):
     for a, b in zip(*res):
         assert a.success and b.success
         assert frame_diff(a.frame, b.frame) == (0.0, 0.0)
+
+
+def test_caller_motion_model_callbacks_and_reset_with_options(eng, seq_small):
+    """The rest of ct_icp::Odometry's surface through the C ABI (include/ct_icp/odometry.h:231-272):
+    * RegisterFrame(..., AMotionModel*) with a PreviousFrameMotionModel in the state of the default one == the default;
+    * RegisterCallback: the three events per registered frame, a callback returning false aborts (CHECK at odometry.cpp:748);
+    * Reset(options): same handle, new options."""
+    opts = _sequence_options(eng, "GN", init_num_frames=4)
+    ref = eng.odometry(opts)
+    base = [ref.RegisterFrame(s["xyz"], s["t"], s["frame_idx"]) for s in seq_small]
+
+    wrong = _sequence_options(eng, "GN", init_num_frames=4)
+    wrong.voxel_size = 2.0
+    od = eng.odometry(wrong)
+    od.RegisterFrame(seq_small[0]["xyz"], seq_small[0]["t"], 0)
+    od.ResetWithOptions(opts)
+    events = []
+    od.RegisterCallback(lambda e: (events.append((e, len(od.keypoints()), len(od.corrected_points()))) or True))
+    prev = None
+    for i, s in enumerate(seq_small):
+        prior = None
+        if prev is not None:
+            prior = abi.MotionPrior()
+            prior.options = opts.default_motion_model
+            prior.previous_frame = prev.frame
+        sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"], motion_model=prior)
+        assert frame_diff(sm.frame, base[i].frame) == (0.0, 0.0), i
+        assert sm.num_keypoints == base[i].num_keypoints
+        if i > 0:
+            assert sm.icp_summary.duration_total > 0.0 and sm.icp_summary.avg_duration_iter > 0.0
+            assert 0.0 <= sm.icp_summary.avg_duration_solve <= sm.icp_summary.avg_duration_iter
+        prev = sm
+    kinds = [e for e, _, _ in events]
+    n = len(seq_small)
+    assert kinds.count(abi.EVENT_BEFORE_ITERATION) == n - 1 and kinds.count(abi.EVENT_ITERATION_COMPLETED) == n - 1
+    assert kinds.count(abi.EVENT_FINISHED_REGISTRATION) == n
+    assert all(k > 0 and f > 0 for e, k, f in events if e == abi.EVENT_BEFORE_ITERATION)
+    # a different model changes the result (the prior is really used)
+    strong = abi.MotionPrior()
+    strong.options = opts.default_motion_model
+    strong.options.beta_constant_velocity = 10.0
+    strong.previous_frame = prev.frame
+    od2 = eng.odometry(opts)
+    for s in seq_small[:-1]:
+        od2.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+    last = seq_small[-1]
+    sm2 = od2.RegisterFrame(last["xyz"], last["t"], last["frame_idx"], motion_model=strong)
+    assert frame_diff(sm2.frame, base[-1].frame)[0] > 1e-9
+    # veto
+    from ct_icp_b200._binding import CticpError
+    od.RegisterCallback(lambda e: e != abi.EVENT_BEFORE_ITERATION)
+    with pytest.raises(CticpError) as err:
+        od.RegisterFrame(last["xyz"], last["t"] + 1.0, 99)
+    assert err.value.code == abi.ERR_CALLBACK

@@ -395,6 +395,8 @@ void DeviceMap::InsertHost(const double *xyz, size_t stride_bytes, size_t n, V3 
         const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(xyz) + stride_bytes * i);
         packed[3 * i] = p[0]; packed[3 * i + 1] = p[1]; packed[3 * i + 2] = p[2];
     }
+    SyncCounters();
+    EnsureRoomFor(n);
     if (n > world_tmp_n_) {
         CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
         cudaFree(d_world_tmp_);
@@ -454,25 +456,51 @@ void DeviceMap::CheckOverflow() {
 }
 
 // Purge tombstones / grow. Called by the odometry between frames with counters it already read back.
+void DeviceMap::RebuildLevel(size_t i, uint64_t new_cap) {
+    MapLevel fresh{};
+    cticp_resolution_param rp = options_.resolutions[i];
+    AllocLevel(fresh, (uint32_t) new_cap, rp);
+    k_rebuild<<<592, 256, 0, stream_>>>(levels_[i], fresh, d_counters_ + i);
+    CT_CUDA_CHECK(cudaMemsetAsync(&(d_counters_ + i)->num_tombs, 0, sizeof(unsigned), stream_));
+    CT_CUDA_CHECK(cudaMemsetAsync(&(d_counters_ + i)->overflow, 0, sizeof(unsigned), stream_));
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    FreeLevel(levels_[i]);
+    levels_[i] = fresh;
+    h_counters_[i].num_tombs = 0;
+    h_counters_[i].overflow = 0;
+    ++rebuilds_;
+}
+
 void DeviceMap::MaintainTables() {
     const MapCounters *c = h_counters_;
     for (size_t i = 0; i < levels_.size(); ++i) {
         const uint64_t cap = (uint64_t) levels_[i].cap_mask + 1;
         const uint64_t used = (uint64_t) c[i].num_voxels + c[i].num_tombs;
-        if (c[i].overflow) throw CapacityError("voxel table of map level " + std::to_string(i) + " is full");
+        if (c[i].overflow) {
+            // A probe sequence wrapped during the last insert: the points of that voxel were dropped (EnsureRoomFor makes
+            // this unreachable for callers that announce their insert size). Recover — double the table, clear the flag —
+            // and report the loss ONCE; the handle stays usable.
+            RebuildLevel(i, cap * 2);
+            throw CapacityError("voxel table of map level " + std::to_string(i) + " was full: points of the last insert were "
+                                "dropped; the table has been doubled");
+        }
         const bool grow = (uint64_t) c[i].num_voxels * 2 > cap;          // live load factor > 0.5
         const bool purge = used * 10 > cap * 7 || c[i].num_tombs * 4ull > cap;   // probe chains getting long
         if (!grow && !purge) continue;
-        MapLevel fresh{};
-        cticp_resolution_param rp = options_.resolutions[i];
-        AllocLevel(fresh, (uint32_t) (grow ? cap * 2 : cap), rp);
-        k_rebuild<<<592, 256, 0, stream_>>>(levels_[i], fresh, d_counters_ + i);
-        CT_CUDA_CHECK(cudaMemsetAsync(&(d_counters_ + i)->num_tombs, 0, sizeof(unsigned), stream_));
-        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-        FreeLevel(levels_[i]);
-        levels_[i] = fresh;
-        h_counters_[i].num_tombs = 0;
-        ++rebuilds_;
+        RebuildLevel(i, grow ? cap * 2 : cap);
+    }
+}
+
+// Before an insert of up to n_new points (every one of them may open a new voxel): make sure no probe sequence can wrap.
+// Uses the host copy of the counters (the previous frame's read-back), so it costs nothing unless a table must grow.
+void DeviceMap::EnsureRoomFor(size_t n_new) {
+    const MapCounters *c = h_counters_;
+    for (size_t i = 0; i < levels_.size(); ++i) {
+        uint64_t cap = (uint64_t) levels_[i].cap_mask + 1;
+        const uint64_t live = (uint64_t) c[i].num_voxels + n_new, used = live + c[i].num_tombs;
+        if (used * 10 <= cap * 8) continue;
+        while (live * 2 > cap) cap *= 2;   // load <= 0.5 after the insert; tombstones vanish in the rebuild
+        RebuildLevel(i, cap);
     }
 }
 

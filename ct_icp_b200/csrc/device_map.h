@@ -44,6 +44,8 @@ public:
     void CheckOverflow();
     // tombstone purge / growth, driven by HostCounters(); call between frames
     void MaintainTables();
+    // room for an insert of up to n_new points (grows / purges a table now if a probe sequence could wrap)
+    void EnsureRoomFor(size_t n_new);
 
     // SearchParamsFromRadiusSearch (map.h:416-432)
     void SearchParams(double radius, int *level, int *voxel_neighborhood) const;
@@ -60,6 +62,7 @@ public:
 
 private:
     void AllocLevel(MapLevel &L, uint32_t cap, const cticp_resolution_param &rp);
+    void RebuildLevel(size_t i, uint64_t new_cap);
     void FreeLevel(MapLevel &L);
     void EnsureScratch(size_t n_upper);
 

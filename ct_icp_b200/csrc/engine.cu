@@ -659,7 +659,9 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     rs.frame.end_pose.pose.t = V3{S.te[0], S.te[1], S.te[2]};
     if (S.failed == 2) throw std::runtime_error("Error During Optimization");   // ct_icp.cpp:639-642
     if (S.failed == 3) throw std::runtime_error("multi-GPU exchange timed out: a peer rank never delivered its accumulator");
-    if (!rs.success) {
+    if (S.failed == 4) {
+        rs.error_message = "[CT_ICP]Error : the normal equations are singular (degenerate geometry and no regulariser)";
+    } else if (!rs.success) {
         char buf[160];
         snprintf(buf, sizeof(buf), "[CT_ICP]Error : not enough keypoints selected in ct-icp ! Number_of_residuals : %d",
                  S.n_used);
@@ -807,6 +809,7 @@ void Engine::UpdateMap(Summary &s, int registered_fid) {
     const V3 location = trajectory_.back().end_pose.pose.t;
     map_->RemoveFar(location, options_.max_distance);
     if (add_points) {
+        map_->EnsureRoomFor((size_t) std::max(0, pipe_->h_counts()[1]));   // F is known since the pose read-back
         // frame_poses = {begin_pose, end_pose} (odometry.cpp:949): the begin position orients the voxel normals
         map_->InsertDevice(pipe_->d_frame_world(), pipe_->d_count_frame(), pipe_->n(), s.frame.begin_pose.pose.t);
         tracker_.skipped_frames = 0;

@@ -52,6 +52,7 @@ struct PeerLinksHost {
     int world = 1, rank = 0;
     unsigned long long *inbox[kMaxPeerRanks] = {};
     unsigned int *seq = nullptr;
+    long long timeout_cycles = 0;   // 0 = the default of peer_exchange.cuh
 };
 
 struct GnParams {
@@ -107,6 +108,10 @@ public:
     void AllReduceAccumulator(void *nccl_comm, IcpState *d_state);
     // peer mailboxes (nccl_shard.cu sets them up); world == 1 disconnects
     void SetPeerLinks(const PeerLinksHost &links);
+    // loads the modules of the sharded kernels now (lazy loading would otherwise hit the first sharded frame of one rank
+    // while its peers already wait in the exchange)
+    void PreloadShardedKernels();
+    void PreloadLmKernels();   // icp_lm.cu
     void NcclAllReduceAccumulator(void *nccl_comm);   // nccl_shard.cu
     double *acc_buffer() const { return d_acc_; }
     bool peers_ready() const { return peers_ready_; }

@@ -106,6 +106,18 @@ __device__ __noinline__ void warp_gn_solve(const double *acc, SolveScratch &S, I
     if (mode == 1) return;
 
     warp_ldlt_solve12(S, lane);   // :914
+    {
+        // A rank-deficient system (all keypoints on one plane and no regulariser, …) gives a non-finite step where Eigen's
+        // pivoted LDL^T would still return something bounded: report the failure instead of propagating NaN poses
+        const bool finite = lane >= 12 || isfinite(S.x[lane]);
+        if (!__all_sync(0xffffffffu, finite)) {
+            if (lane == 0) {
+                st->failed = 4;
+                st->done = 1;
+            }
+            return;
+        }
+    }
 
     if (lane < 6) {   // angles x[0..2] (begin) and x[6..8] (end): sin / cos evaluated by six lanes at once
         const double ang = S.x[lane < 3 ? lane : lane + 3];
@@ -619,6 +631,16 @@ k_radius_search(const RadiusSearchLevels *__restrict__ R, int kmax, const double
 void IcpSolver::SetPeerLinks(const PeerLinksHost &links) {
     links_host_ = links;
     peers_ready_ = links.world > 1 && links.seq != nullptr;
+}
+void IcpSolver::PreloadShardedKernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_gn_persistent<true>);
+    cudaFuncGetAttributes(&a, k_gn_persistent<false>);
+    cudaFuncGetAttributes(&a, k_gn_iterate);
+    cudaFuncGetAttributes(&a, k_peer_allreduce);
+    cudaFuncGetAttributes(&a, k_gn_solve_acc);
+    PreloadLmKernels();
+    cudaGetLastError();
 }
 void IcpSolver::AllReduceAccumulator(void *nccl_comm, IcpState *d_state) {
     if (peers_ready_) {

@@ -894,6 +894,16 @@ void IcpSolver::EnsureLmBuffers(size_t k_upper) {
         lm_capacity_ = k_upper;
     }
 }
+void IcpSolver::PreloadLmKernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_lm_step<true>);
+    cudaFuncGetAttributes(&a, k_lm_step<false>);
+    cudaFuncGetAttributes(&a, k_lm_eval);
+    cudaFuncGetAttributes(&a, k_lm_gather<false>);
+    cudaFuncGetAttributes(&a, k_lm_gather<true>);
+    cudaFuncGetAttributes(&a, k_rb_gather);
+    cudaFuncGetAttributes(&a, k_lm_select);
+}
 void IcpSolver::FreeLmBuffers() {
     cudaFree(d_lm_state_);
     cudaFree(d_lm_stats_);

@@ -229,7 +229,26 @@ bool Engine::ConnectPeers() {
         DisconnectPeers();
         return false;
     }
+    {   // exchange time-out (see peer_exchange.cuh): CTICP_PEER_TIMEOUT_MS, default 30 s, in SM cycles
+        double ms = 30000.0;
+        if (const char *e = getenv("CTICP_PEER_TIMEOUT_MS")) ms = std::max(1.0, atof(e));
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_);
+        links.timeout_cycles = (long long) (ms * (double) std::max(khz, 1000000));
+    }
     icp_->SetPeerLinks(links);
+    // every rank loads the sharded kernels' modules NOW, then the ranks meet once more: the first exchange finds all peers
+    // warm instead of one of them inside a lazy module load
+    icp_->PreloadShardedKernels();
+    {
+        int *d_flag = nullptr;
+        if (cudaMalloc(&d_flag, sizeof(int)) == cudaSuccess) {
+            cudaMemsetAsync(d_flag, 0, sizeof(int), stream_);
+            Check(api.AllReduce(d_flag, d_flag, 1, ncclInt, ncclMin, comm, stream_), "ncclAllReduce (peer rendezvous)");
+            cudaStreamSynchronize(stream_);
+            cudaFree(d_flag);
+        }
+    }
     if (getenv("CTICP_DEBUG_P2P"))
         fprintf(stderr, "[cticp] rank %d/%d: peer mailboxes connected (%zu IPC mappings)\n", rank, world, peer_mapped_.size());
     return true;

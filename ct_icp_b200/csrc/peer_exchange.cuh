@@ -15,7 +15,7 @@
 // (exchange n+1 needs that peer's contribution to n+1, sent after it finished reading n), so parity n is free again
 // when exchange n+2 writes it. The sequence counter lives in device memory, advances by one per exchange and is the
 // same number on every rank because all ranks run the same number of exchanges (same decisions, see 3.).
-// A poll that does not complete within kPeerTimeoutCycles gives up (returns false) so a dead peer can never hang the GPU.
+// A poll that does not complete within PeerLinks::timeout_cycles gives up (returns false) so a dead peer can never hang the GPU.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -26,12 +26,17 @@ namespace cticp {
 constexpr int kMaxPeers = 8;                         // one NVSwitch domain
 constexpr int kPeerWords = 2 * kAcc;                 // 8-byte words per contribution (32 payload bits each)
 constexpr size_t kMailboxWords = (size_t) 2 * kMaxPeers * kPeerWords;   // [parity][source rank][word]
-constexpr long long kPeerTimeoutCycles = 6000000000LL;   // ~3 s at 1.9 GHz: ranks are host-launched, allow jitter
+// Bound on the skew between ranks at an exchange, in SM cycles (PeerLinks::timeout_cycles, set by the host from
+// CTICP_PEER_TIMEOUT_MS x the SM clock; default 30 s). The ranks are launched independently by their hosts: anything that
+// delays one of them (a late scan, a page fault, the OS) delays the exchange, and the waiting rank must not give up on a
+// healthy peer — the bound only has to be finite so that a DEAD peer cannot hang the GPU.
+constexpr long long kPeerTimeoutCyclesDefault = 60000000000LL;
 
 struct PeerLinks {
     int world = 1, rank = 0;
     unsigned long long *inbox[kMaxPeers] = {};   // inbox[p] = rank p's mailbox as mapped into THIS process (inbox[rank]: own)
     unsigned int *seq = nullptr;                 // device counter: exchanges completed so far
+    long long timeout_cycles = kPeerTimeoutCyclesDefault;
 };
 
 static_assert(kMaxPeerRanks == kMaxPeers, "host / device peer tables");
@@ -41,6 +46,7 @@ inline PeerLinks PeerLinksOf(const PeerLinksHost &h) {   // the host-side descri
     L.rank = h.rank;
     for (int i = 0; i < kMaxPeers; ++i) L.inbox[i] = h.inbox[i];
     L.seq = h.seq;
+    if (h.timeout_cycles > 0) L.timeout_cycles = h.timeout_cycles;
     return L;
 }
 
@@ -74,7 +80,7 @@ __device__ __forceinline__ bool peer_allreduce(const PeerLinks &L, unsigned int 
         for (int r = 0; r < L.world; ++r) {
             unsigned long long w = peer_load_u64(mine + (size_t) r * kPeerWords + wd);
             while ((unsigned int) (w >> 32) != seq) {
-                if (clock64() - t0 > kPeerTimeoutCycles) {
+                if (clock64() - t0 > L.timeout_cycles) {
                     *s_ok = 0;
                     break;
                 }

@@ -119,6 +119,8 @@ public:
 private:
     void EnsurePartials(int blocks);
     void EnsureLmBuffers(size_t k_upper);
+    void DebugLmTrace(void *d_lm);
+    int lm_coresident_[6] = {0, 0, 0, 0, 0, 0};   // k_lm_persistent<mode, peers>
     void FreeLmBuffers();
     GnParams MakeParams(const DeviceMap &map, const cticp_icp_options &opt) const;
 

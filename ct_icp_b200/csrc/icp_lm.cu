@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "engine.h"
 #include "gather_select.cuh"
 #include "icp.h"
@@ -109,31 +111,26 @@ __device__ __forceinline__ NeighborSums lm_load_sums(const double *o) {
     return s;
 }
 
+// One warp's share of the residual assembly of solver CERES (ct_icp.cpp:561-604). warp_global / warps_total: this warp's
+// index among all gathering warps of the launch (interleaved over the CTAs by the callers).
 template <bool kDB>
-__global__ void __launch_bounds__(kLmWarps * 32)
-k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
-            const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned long long *stats,
-            const DistanceStrategy *__restrict__ D) {
-    __shared__ LmTile s_tile[kLmWarps];
-    __shared__ int s_stencil[kMaxStencil];
-    if (st->done) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int *stencil = kDB ? nullptr : stencil_table_fill(s_stencil, G0.r);
-    __syncthreads();
-    LmTile &T = s_tile[w];
-    const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
-    const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
-    const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
-    const int K = *d_num_keypoints;
+__device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmParams &P, const int *stencil,
+                                                const float4 *__restrict__ keypoints, int K, const IcpState *st,
+                                                ResidualBlock *__restrict__ blocks, unsigned long long *stats,
+                                                const DistanceStrategy *__restrict__ D, LmTile &T, int warp_global,
+                                                int warps_total, int lane) {
+    const Q4 qb{__ldcg(&st->qb[0]), __ldcg(&st->qb[1]), __ldcg(&st->qb[2]), __ldcg(&st->qb[3])},
+        qe{__ldcg(&st->qe[0]), __ldcg(&st->qe[1]), __ldcg(&st->qe[2]), __ldcg(&st->qe[3])};
+    const V3 tb{__ldcg(&st->tb[0]), __ldcg(&st->tb[1]), __ldcg(&st->tb[2])}, te{__ldcg(&st->te[0]), __ldcg(&st->te[1]), __ldcg(&st->te[2])};
+    const SlerpConsts sc{__ldcg(&st->slerp_theta), __ldcg(&st->slerp_inv_sin), __ldcg(&st->slerp_linear), __ldcg(&st->slerp_negate)};
     unsigned long long n_kp = 0, n_pts = 0;
     // keypoint-sharded mode: this rank assembles the blocks of its contiguous chunk only
     const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
     const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-    const int warps_total = gridDim.x * kLmWarps;
     int W = (kp_hi - kp_lo + warps_total - 1) / warps_total;
     W = W < kLmTileMax ? (W < 1 ? 1 : W) : kLmTileMax;
     const int need = P.kmin > 5 ? P.kmin : 5;   // :574 ; neighborhood.h:227
-    for (int t0 = kp_lo + (w * (int) gridDim.x + (int) blockIdx.x) * W; t0 < kp_hi; t0 += warps_total * W) {
+    for (int t0 = kp_lo + warp_global * W; t0 < kp_hi; t0 += warps_total * W) {
         const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
         // ---- lane j: transform_keypoints() (ct_icp.cpp:516-531) and, for the distance-based strategy, this
         // keypoint's radius → map level + stencil (neighborhood_strategy.h:121-126, map.h:416-432)
@@ -228,36 +225,44 @@ k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, c
     }
 }
 
+template <bool kDB>
+__global__ void __launch_bounds__(kLmWarps * 32)
+k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
+            const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned long long *stats,
+            const DistanceStrategy *__restrict__ D) {
+    __shared__ LmTile s_tile[kLmWarps];
+    __shared__ int s_stencil[kMaxStencil];
+    if (st->done) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int *stencil = kDB ? nullptr : stencil_table_fill(s_stencil, G0.r);
+    __syncthreads();
+    lm_gather_tiles<kDB>(G0, P, stencil, keypoints, *d_num_keypoints, st, blocks, stats, D, s_tile[w],
+                         w * (int) gridDim.x + (int) blockIdx.x, (int) gridDim.x * kLmWarps, lane);
+}
+
 // Solver ROBUST's per-keypoint assembly (ct_icp.cpp:1229-1289): same gather, the neighborhood is classified planar /
 // linear / other and yields a point-to-plane / point-to-line / point-to-distribution block. `classes` holds
 // slam::NEIGHBORHOOD_TYPE per keypoint ACROSS the ICP iterations: the reference keeps its `neighborhoods` vector alive
 // (:1214) and ClassifyNeighborhood (neighborhood.h:268-282) leaves the previous class in place when neither threshold
 // is passed.
-__global__ void __launch_bounds__(kLmWarps * 32)
-k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
-            const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned char *__restrict__ classes,
-            unsigned long long *stats) {
-    __shared__ LmTile s_tile[kLmWarps];
-    __shared__ int s_stencil[kMaxStencil];
-    if (st->done) return;
+__device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmParams &P, const int *stencil,
+                                                const float4 *__restrict__ keypoints, int K, const IcpState *st,
+                                                ResidualBlock *__restrict__ blocks, unsigned char *__restrict__ classes,
+                                                unsigned long long *stats, LmTile &T, int warp_global, int warps_total,
+                                                int lane) {
     enum { NONE = 0, LINEAR = 1, PLANAR = 2, VOLUMIC = 3 };
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int *stencil = stencil_table_fill(s_stencil, G.r);
-    __syncthreads();
-    LmTile &T = s_tile[w];
-    const Q4 qb{st->qb[0], st->qb[1], st->qb[2], st->qb[3]}, qe{st->qe[0], st->qe[1], st->qe[2], st->qe[3]};
-    const V3 tb{st->tb[0], st->tb[1], st->tb[2]}, te{st->te[0], st->te[1], st->te[2]};
-    const SlerpConsts sc{st->slerp_theta, st->slerp_inv_sin, st->slerp_linear, st->slerp_negate};
-    const int K = *d_num_keypoints;
+    const Q4 qb{__ldcg(&st->qb[0]), __ldcg(&st->qb[1]), __ldcg(&st->qb[2]), __ldcg(&st->qb[3])},
+        qe{__ldcg(&st->qe[0]), __ldcg(&st->qe[1]), __ldcg(&st->qe[2]), __ldcg(&st->qe[3])};
+    const V3 tb{__ldcg(&st->tb[0]), __ldcg(&st->tb[1]), __ldcg(&st->tb[2])}, te{__ldcg(&st->te[0]), __ldcg(&st->te[1]), __ldcg(&st->te[2])};
+    const SlerpConsts sc{__ldcg(&st->slerp_theta), __ldcg(&st->slerp_inv_sin), __ldcg(&st->slerp_linear), __ldcg(&st->slerp_negate)};
     unsigned long long n_kp = 0, n_pts = 0;
     // keypoint-sharded mode: this rank assembles the blocks of its contiguous chunk only
     const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
     const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-    const int warps_total = gridDim.x * kLmWarps;
     int W = (kp_hi - kp_lo + warps_total - 1) / warps_total;
     W = W < kLmTileMax ? (W < 1 ? 1 : W) : kLmTileMax;
     const int need = P.kmin;   // :1238 (kmin >= 5 is enforced by the host, so the neighborhood is always describable)
-    for (int t0 = kp_lo + (w * (int) gridDim.x + (int) blockIdx.x) * W; t0 < kp_hi; t0 += warps_total * W) {
+    for (int t0 = kp_lo + warp_global * W; t0 < kp_hi; t0 += warps_total * W) {
         const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
         float4 kraw = make_float4(0.f, 0.f, 0.f, 0.f);
         V3 p{0, 0, 0};
@@ -357,20 +362,38 @@ k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, co
     }
 }
 
+__global__ void __launch_bounds__(kLmWarps * 32)
+k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
+            const IcpState *__restrict__ st, ResidualBlock *__restrict__ blocks, unsigned char *__restrict__ classes,
+            unsigned long long *stats) {
+    __shared__ LmTile s_tile[kLmWarps];
+    __shared__ int s_stencil[kMaxStencil];
+    if (st->done) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int *stencil = stencil_table_fill(s_stencil, G.r);
+    __syncthreads();
+    rb_gather_tiles(G, P, stencil, keypoints, *d_num_keypoints, st, blocks, classes, stats, s_tile[w],
+                    w * (int) gridDim.x + (int) blockIdx.x, (int) gridDim.x * kLmWarps, lane);
+}
+
 // GetProblem (ct_icp.cpp:409-424) + seeding of the LM state for this ICP iteration. One CTA.
 // Sharded: launched twice. mode 1 counts this rank's valid blocks into counts[rank] (the vector is then summed over the
 // ranks = all-gather); mode 0 selects with the global rank of each block = (valid blocks of lower ranks) + local rank,
 // so the union over ranks is exactly the first max_num_residuals valid blocks in keypoint order.
-__global__ void __launch_bounds__(1024)
-k_lm_select(LmParams P, int mode, const int *__restrict__ d_num_keypoints, const ResidualBlock *__restrict__ blocks,
-            int *__restrict__ sel_idx, IcpState *st, LmState *lm, const unsigned long long *stats,
-            double *__restrict__ counts) {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    if (st->done) return;
-    const int K = *d_num_keypoints;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+struct LmSelectScratch {
+    int warp[32];
+    int carry;
+};
+// Called by ALL threads of one CTA (any multiple of 32 up to 1024 threads).
+__device__ __forceinline__ void lm_select_device(const LmParams &P, int mode, int K, const ResidualBlock *__restrict__ blocks,
+                                                 int *__restrict__ sel_idx, IcpState *st, LmState *lm,
+                                                 const unsigned long long *stats, double *__restrict__ counts,
+                                                 LmSelectScratch &sc) {
+    int *s_warp = sc.warp;
+    int &s_carry = sc.carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nthreads = blockDim.x;
     if (tid == 0) s_carry = 0;
+    if (tid < 32) s_warp[tid] = 0;
     __syncthreads();
     const int limit = P.max_num_residuals > 0 ? P.max_num_residuals : 0x7fffffff;
     const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
@@ -384,7 +407,7 @@ k_lm_select(LmParams P, int mode, const int *__restrict__ d_num_keypoints, const
             total_valid += c;
         }
     }
-    for (int base = kp_lo; base < kp_hi; base += 1024) {
+    for (int base = kp_lo; base < kp_hi; base += nthreads) {
         const int k = base + tid;
         const int v = (k < kp_hi) ? (blocks[k].valid != 0) : 0;
         int incl = v;
@@ -396,7 +419,7 @@ k_lm_select(LmParams P, int mode, const int *__restrict__ d_num_keypoints, const
         if (lane == 31) s_warp[w] = incl;
         __syncthreads();
         if (w == 0) {
-            int ws = s_warp[lane];
+            int ws = lane < (nthreads >> 5) ? s_warp[lane] : 0;   // (entries beyond the CTA's warps hold last round's totals)
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int y = __shfl_up_sync(0xffffffffu, ws, o);
@@ -409,7 +432,7 @@ k_lm_select(LmParams P, int mode, const int *__restrict__ d_num_keypoints, const
         const int rank = carry + (w > 0 ? s_warp[w - 1] : 0) + incl - v;
         if (mode == 0 && v && before + rank < limit) sel_idx[rank] = k;
         __syncthreads();
-        if (tid == 1023) s_carry = carry + s_warp[31];
+        if (tid == nthreads - 1) s_carry = carry + s_warp[31];
         __syncthreads();
     }
     if (mode == 1) {
@@ -448,28 +471,37 @@ k_lm_select(LmParams P, int mode, const int *__restrict__ d_num_keypoints, const
         lm->step_is_successful = 1;
     }
 }
+__global__ void __launch_bounds__(1024)
+k_lm_select(LmParams P, int mode, const int *__restrict__ d_num_keypoints, const ResidualBlock *__restrict__ blocks,
+            int *__restrict__ sel_idx, IcpState *st, LmState *lm, const unsigned long long *stats,
+            double *__restrict__ counts) {
+    __shared__ LmSelectScratch sc;
+    if (st->done) return;
+    lm_select_device(P, mode, *d_num_keypoints, blocks, sel_idx, st, lm, stats, counts, sc);
+}
 
-// residual evaluation at lm->x (which = 0) or lm->cand (which = 1): half a warp per residual block
-__global__ void __launch_bounds__(kLmWarps * 32)
-k_lm_eval(LmParams P, int which, const ResidualBlock *__restrict__ blocks, const int *__restrict__ sel_idx,
-          const IcpState *__restrict__ st, const LmState *__restrict__ lm, double *__restrict__ partials) {
-    __shared__ double s_u[kLmWarps * 2][16];
-    __shared__ double s_acc[kLmWarps * 2][kAcc];
+// `half_index` / `halves_total`: this half-warp's index among all evaluating half-warps of the launch. s_u / s_acc: this
+// CTA's scratch, one row per half-warp (hw = local half-warp index). Writes the CTA's sum to `row_out` (kAcc doubles).
+// Called by ALL threads of the CTA.
+template <int kHalves>
+__device__ __noinline__ void lm_eval_device(const LmParams &P, int which, const ResidualBlock *__restrict__ blocks,
+                                               const int *__restrict__ sel_idx, const IcpState *st, const LmState *lm,
+                                               double (*s_u)[16], double (*s_acc)[kAcc], int half_index, int halves_total,
+                                               double *__restrict__ row_out) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int hl = lane & 15, half = lane >> 4, hw = w * 2 + half;
     const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
     double acc[6] = {0, 0, 0, 0, 0, 0};   // entries hl + 16 m of [JTJ upper | JTr]
     double cost = 0;
-    const bool active = !st->done && !lm->done;
+    const bool active = !__ldcg(&st->done) && !__ldcg(&lm->done);
     if (active) {
         const double *x = which ? lm->cand : lm->x;
         double qb[4], qe[4], tb[3], te[3];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) { qb[d] = x[d]; qe[d] = x[4 + d]; }
+        for (int d = 0; d < 4; ++d) { qb[d] = __ldcg(x + d); qe[d] = __ldcg(x + 4 + d); }
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { tb[d] = x[8 + d]; te[d] = x[11 + d]; }
-        const int R = lm->num_residuals;
-        const int halves_total = gridDim.x * kLmWarps * 2;
+        for (int d = 0; d < 3; ++d) { tb[d] = __ldcg(x + 8 + d); te[d] = __ldcg(x + 11 + d); }
+        const int R = __ldcg(&lm->num_residuals);
         int pi[6], pj[6];
 #pragma unroll
         for (int m = 0; m < 6; ++m) {
@@ -477,8 +509,8 @@ k_lm_eval(LmParams P, int which, const ResidualBlock *__restrict__ blocks, const
             pi[m] = e < kAccUsed ? c_pair_i[e] : 0;
             pj[m] = e < kAccUsed ? c_pair_j[e] : 0;
         }
-        for (int r = blockIdx.x * kLmWarps * 2 + hw; r < R; r += halves_total) {
-            const ResidualBlock rb = blocks[sel_idx[r]];
+        for (int r = half_index; r < R; r += halves_total) {
+            const ResidualBlock rb = blocks[__ldcg(sel_idx + r)];
             const Dual res = P.robust ? ct_residual<true>(rb, qb, qe, tb, te, hl) : ct_residual<false>(rb, qb, qe, tb, te, hl);
             const double s = res.a * res.a;
             double rs = 1.0, js = 1.0;
@@ -509,9 +541,20 @@ k_lm_eval(LmParams P, int which, const ResidualBlock *__restrict__ blocks, const
     if (threadIdx.x < kAcc) {
         double s = 0;
 #pragma unroll
-        for (int h = 0; h < kLmWarps * 2; ++h) s += s_acc[h][threadIdx.x];
-        partials[(size_t) blockIdx.x * kAcc + threadIdx.x] = s;
+        for (int h = 0; h < kHalves; ++h) s += s_acc[h][threadIdx.x];
+        __stcg(row_out + threadIdx.x, s);
     }
+}
+
+// residual evaluation at lm->x (which = 0) or lm->cand (which = 1): half a warp per residual block
+__global__ void __launch_bounds__(kLmWarps * 32)
+k_lm_eval(LmParams P, int which, const ResidualBlock *__restrict__ blocks, const int *__restrict__ sel_idx,
+          const IcpState *__restrict__ st, const LmState *__restrict__ lm, double *__restrict__ partials) {
+    __shared__ double s_u[kLmWarps * 2][16];
+    __shared__ double s_acc[kLmWarps * 2][kAcc];
+    const int hw = (threadIdx.x >> 5) * 2 + ((threadIdx.x & 31) >> 4);
+    lm_eval_device<kLmWarps * 2>(P, which, blocks, sel_idx, st, lm, s_u, s_acc, blockIdx.x * kLmWarps * 2 + hw,
+                                 gridDim.x * kLmWarps * 2, partials + (size_t) blockIdx.x * kAcc);
 }
 
 // sharded mode: fold this rank's evaluation partials into one accumulator row for the all-reduce
@@ -615,44 +658,9 @@ __device__ double norm14(const double *v) {
 // the reduction of this rank's partials and the minimizer step, so a sharded LM evaluation costs the same two launches
 // as a single-GPU one. The early return below is taken by all ranks together (done flags derive from identical sums),
 // so the ranks' exchange counters stay in step.
-template <bool kPeers>
-__global__ void __launch_bounds__(128)
-k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblocks, IcpState *st, LmState *lm,
-          PeerLinks links) {
-    __shared__ LmScratch S;
-    __shared__ double s_part[4][kAcc];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (st->done || lm->done) return;
-    {   // deterministic reduction of the evaluation partials
-        double a0 = 0, a1 = 0, a2 = 0;
-        for (int b = w; b < nblocks; b += 4) {
-            const double *row = partials + (size_t) b * kAcc;
-            a0 += row[lane];
-            a1 += row[lane + 32];
-            a2 += row[lane + 64];
-        }
-        s_part[w][lane] = a0;
-        s_part[w][lane + 32] = a1;
-        s_part[w][lane + 64] = a2;
-        __syncthreads();
-        if (threadIdx.x < kAcc) S.acc[threadIdx.x] = s_part[0][threadIdx.x] + s_part[1][threadIdx.x] + s_part[2][threadIdx.x] + s_part[3][threadIdx.x];
-        __syncthreads();
-    }
-    if (kPeers) {
-        __shared__ unsigned int s_half[kMaxPeers * kPeerWords];
-        __shared__ int s_peer_ok;
-        const unsigned int seq = *links.seq + 1;
-        const bool ok = peer_allreduce(links, seq, S.acc, s_half, &s_peer_ok);   // Σ over ranks, in rank order
-        if (threadIdx.x == 0) {
-            *links.seq = seq;
-            if (!ok) {   // a peer never answered: give up instead of hanging the device
-                st->failed = 3;
-                st->done = 1;
-            }
-        }
-        if (!ok) return;
-    }
-    if (w != 0) return;
+// The minimizer step on the evaluation held in S.acc (already reduced over this rank's CTAs and, when sharded, over the
+// ranks). ONE WARP; the 12x12 solves are warp-collective, the scalar logic runs on lane 0.
+__device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmScratch &S, IcpState *st, LmState *lm, int lane) {
     const double min_relative_decrease = 1e-3, function_tolerance = 1e-6, gradient_tolerance = 1e-10,
                  parameter_tolerance = 1e-8, min_radius = 1e-32, max_radius = 1e16, min_lm_diagonal = 1e-6,
                  max_lm_diagonal = 1e32;
@@ -828,9 +836,50 @@ k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblock
     }
 }
 
+template <bool kPeers>
+__global__ void __launch_bounds__(128)
+k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblocks, IcpState *st, LmState *lm,
+          PeerLinks links) {
+    __shared__ LmScratch S;
+    __shared__ double s_part[4][kAcc];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (st->done || lm->done) return;
+    {   // deterministic reduction of the evaluation partials
+        double a0 = 0, a1 = 0, a2 = 0;
+        for (int b = w; b < nblocks; b += 4) {
+            const double *row = partials + (size_t) b * kAcc;
+            a0 += row[lane];
+            a1 += row[lane + 32];
+            a2 += row[lane + 64];
+        }
+        s_part[w][lane] = a0;
+        s_part[w][lane + 32] = a1;
+        s_part[w][lane + 64] = a2;
+        __syncthreads();
+        if (threadIdx.x < kAcc) S.acc[threadIdx.x] = s_part[0][threadIdx.x] + s_part[1][threadIdx.x] + s_part[2][threadIdx.x] + s_part[3][threadIdx.x];
+        __syncthreads();
+    }
+    if (kPeers) {
+        __shared__ unsigned int s_half[kMaxPeers * kPeerWords];
+        __shared__ int s_peer_ok;
+        const unsigned int seq = *links.seq + 1;
+        const bool ok = peer_allreduce(links, seq, S.acc, s_half, &s_peer_ok);   // Σ over ranks, in rank order
+        if (threadIdx.x == 0) {
+            *links.seq = seq;
+            if (!ok) {   // a peer never answered: give up instead of hanging the device
+                st->failed = 3;
+                st->done = 1;
+            }
+        }
+        if (!ok) return;
+    }
+    if (w != 0) return;
+    lm_step_device(P, phase, S, st, lm, lane);
+}
+
 // end of one ICP iteration (ct_icp.cpp:636-672): write the pose pair back and test the stop criterion
-__global__ void k_lm_finish(LmParams P, IcpState *st, LmState *lm, int outer_index) {
-    if (threadIdx.x != 0 || st->done) return;
+// one thread
+__device__ __forceinline__ void lm_finish_device(const LmParams &P, IcpState *st, LmState *lm, int outer_index) {
     if (!lm->usable) {   // reference: throw std::runtime_error("Error During Optimization") (:639-642)
         st->failed = 2;
         st->done = 1;
@@ -866,8 +915,13 @@ __global__ void k_lm_finish(LmParams P, IcpState *st, LmState *lm, int outer_ind
     }
 }
 
-__global__ void k_lm_begin(IcpState *st, LmState *lm, unsigned long long *stats) {
-    if (threadIdx.x != 0) return;
+__global__ void k_lm_finish(LmParams P, IcpState *st, LmState *lm, int outer_index) {
+    if (threadIdx.x != 0 || st->done) return;
+    lm_finish_device(P, st, lm, outer_index);
+}
+
+// one thread
+__device__ __forceinline__ void lm_begin_device(IcpState *st, LmState *lm, unsigned long long *stats) {
     for (int d = 0; d < 4; ++d) { lm->prev_qb[d] = st->qb[d]; lm->prev_qe[d] = st->qe[d]; }
     for (int d = 0; d < 3; ++d) { lm->prev_tb[d] = st->tb[d]; lm->prev_te[d] = st->te[d]; }
     lm->done = 0;
@@ -875,6 +929,195 @@ __global__ void k_lm_begin(IcpState *st, LmState *lm, unsigned long long *stats)
     lm->trace_n = 0;
     stats[0] = 0;
     stats[1] = 0;
+}
+__global__ void k_lm_begin(IcpState *st, LmState *lm, unsigned long long *stats) {
+    if (threadIdx.x != 0) return;
+    lm_begin_device(st, lm, stats);
+}
+
+// ---- persistent variant: the WHOLE CERES / ROBUST registration of a frame in one cooperative launch -------------------
+// The reference's DoRegisterCeres / DoRegisterRobust loop (ct_icp.cpp:549-672, 1229-1336) — per ICP iteration: residual
+// assembly, GetProblem, ceres::Solve (one evaluation + up to ls_max_num_iters candidate evaluations, each followed by a
+// trust-region step), stop test — used to be ~15 launches per ICP iteration. Here CTA 0 is the SOLVER CTA: it runs
+// GetProblem and the minimizer with the whole LM state in its shared memory (the serial trust-region logic no longer pays
+// global-memory latency on every access) and publishes the candidate point; CTAs 1..G assemble the residual blocks
+// (gather + selection, tiled) and evaluate the residuals / Jacobians (half a warp per block). Grid-wide barriers separate
+// the phases: 2 per ICP iteration + 2 per evaluation. Sharded (kPeers): the per-rank valid counts and every evaluation's
+// accumulator are exchanged by the solver CTA over the NVLink peer mailboxes, inside the loop.
+// kMode: 0 = CERES with the nearest-neighbor strategy, 1 = CERES with the distance-based strategy, 2 = ROBUST.
+constexpr int kLmPWarps = 16;
+struct LmSolverShared {
+    LmScratch S;
+    double part[kLmPWarps][kAcc];
+    LmSelectScratch sel;
+    unsigned int half[kMaxPeers * kPeerWords];
+    LmState lm;
+};
+struct LmEvalShared {
+    double u[kLmPWarps * 2][16];
+    double acc[kLmPWarps * 2][kAcc];
+};
+struct __align__(16) LmPShared {
+    union {
+        LmTile tile[kLmPWarps];   // workers, assembly phase
+        LmEvalShared eval;        // workers, evaluation phase
+        LmSolverShared solver;    // CTA 0
+    };
+    int stencil[kMaxStencil];
+    int flag;
+};
+extern __shared__ __align__(16) unsigned char lm_smem_raw[];
+
+// what the worker CTAs read of the LM state: the point to evaluate, the problem size, the stop flag
+__device__ __forceinline__ void lm_publish(LmState *dst, const LmState *src, int tid) {
+    if (tid < 14) {
+        __stcg(&dst->x[tid], src->x[tid]);
+        __stcg(&dst->cand[tid], src->cand[tid]);
+    }
+    if (tid == 0) {
+        __stcg(&dst->num_residuals, src->num_residuals);
+        __stcg(&dst->done, src->done);
+    }
+}
+
+template <int kMode, bool kPeers>
+__global__ void __launch_bounds__(kLmPWarps * 32, 1)
+k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
+                IcpState *st, LmState *lm_g, ResidualBlock *__restrict__ blocks, int *__restrict__ sel_idx,
+                unsigned char *__restrict__ classes, unsigned long long *stats, const DistanceStrategy *__restrict__ D,
+                double *__restrict__ partials, PeerLinks links) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    LmPShared &sh = *reinterpret_cast<LmPShared *>(lm_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool solver = blockIdx.x == 0;
+    const int workers = (int) gridDim.x - 1, wi = (int) blockIdx.x - 1;
+    const int *stencil = kMode == 1 ? nullptr : stencil_table_fill(sh.stencil, G0.r);
+    LmState *lm = &sh.solver.lm;   // the solver CTA's working copy (shared memory); lm_g is what the workers see
+    unsigned int peer_seq = 0;
+    if (solver) {
+        if (kPeers) peer_seq = *links.seq;
+        if (tid == 0) lm_begin_device(st, lm, stats);
+        __syncthreads();
+        lm_publish(lm_g, lm, tid);
+        __threadfence();
+    }
+    grid.sync();
+    const int K = *d_num_keypoints;
+
+    for (int it = 0; it < P.num_iters_icp; ++it) {
+        if (__ldcg(&st->done)) break;   // uniform: written before a grid barrier
+        // ---- residual assembly (workers)
+        if (!solver) {
+            const int wg = w * workers + wi, warps_total = workers * kLmPWarps;
+            if (kMode == 2)
+                rb_gather_tiles(G0, P, stencil, keypoints, K, st, blocks, classes, stats, sh.tile[w], wg, warps_total, lane);
+            else if (kMode == 1)
+                lm_gather_tiles<true>(G0, P, stencil, keypoints, K, st, blocks, stats, D, sh.tile[w], wg, warps_total, lane);
+            else
+                lm_gather_tiles<false>(G0, P, stencil, keypoints, K, st, blocks, stats, D, sh.tile[w], wg, warps_total, lane);
+        }
+        grid.sync();
+        // ---- GetProblem (solver): the first max_num_residuals valid blocks in keypoint order, seeds the minimizer
+        if (solver) {
+            double *counts = sh.solver.part[0];
+            if (kPeers) {   // all-gather of the per-rank valid counts (as a sum of one-hot vectors)
+                if (tid < kAcc) counts[tid] = 0.0;
+                __syncthreads();
+                lm_select_device(P, 1, K, blocks, sel_idx, st, lm, stats, counts, sh.solver.sel);
+                const bool ok = peer_allreduce(links, ++peer_seq, counts, sh.solver.half, &sh.flag);
+                if (!ok && tid == 0) {
+                    st->failed = 3;
+                    st->done = 1;
+                }
+                __syncthreads();
+            }
+            if (!__ldcg(&st->done)) lm_select_device(P, 0, K, blocks, sel_idx, st, lm, stats, counts, sh.solver.sel);
+            __syncthreads();
+            lm_publish(lm_g, lm, tid);
+            __threadfence();
+        }
+        grid.sync();
+        // ---- ceres::Solve: evaluation 0 at x, then one evaluation per candidate
+        for (int ev = 0; ev <= P.ls_max_num_iters; ++ev) {
+            if (__ldcg(&st->done) || __ldcg(&lm_g->done)) break;   // uniform
+            const int phase = ev > 0 ? 1 : 0;
+            if (!solver) {
+                const int hw = w * 2 + (lane >> 4);
+                lm_eval_device<kLmPWarps * 2>(P, phase, blocks, sel_idx, st, lm_g, sh.eval.u, sh.eval.acc,
+                                              hw * workers + wi, workers * kLmPWarps * 2, partials + (size_t) wi * kAcc);
+            }
+            grid.sync();
+            if (solver) {
+                // deterministic reduction of the workers' rows: warp g sums the rows b = g (mod warps), all its loads in
+                // flight before the first add; then the per-warp sums in fixed order
+                {
+                    constexpr int kInFlight = 10;
+                    double a0 = 0, a1 = 0, a2 = 0;
+                    for (int b0 = w; b0 < workers; b0 += kLmPWarps * kInFlight) {
+                        double v0[kInFlight], v1[kInFlight], v2[kInFlight];
+#pragma unroll
+                        for (int u = 0; u < kInFlight; ++u) {
+                            const int b = b0 + u * kLmPWarps;
+                            v0[u] = v1[u] = v2[u] = 0.0;
+                            if (b < workers) {
+                                const double *row = partials + (size_t) b * kAcc;
+                                v0[u] = __ldcg(row + lane);
+                                v1[u] = __ldcg(row + lane + 32);
+                                v2[u] = __ldcg(row + lane + 64);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kInFlight; ++u)
+                            if (b0 + u * kLmPWarps < workers) {
+                                a0 += v0[u];
+                                a1 += v1[u];
+                                a2 += v2[u];
+                            }
+                    }
+                    sh.solver.part[w][lane] = a0;
+                    sh.solver.part[w][lane + 32] = a1;
+                    sh.solver.part[w][lane + 64] = a2;
+                    __syncthreads();
+                    if (tid < kAcc) {
+                        double sum = 0;
+#pragma unroll
+                        for (int ww = 0; ww < kLmPWarps; ++ww) sum += sh.solver.part[ww][tid];
+                        sh.solver.S.acc[tid] = sum;
+                    }
+                    __syncthreads();
+                }
+                bool ok = true;
+                if (kPeers) ok = peer_allreduce(links, ++peer_seq, sh.solver.S.acc, sh.solver.half, &sh.flag);
+                if (w == 0) {
+                    if (!ok) {
+                        if (lane == 0) {   // a peer never answered: give up instead of hanging the device
+                            st->failed = 3;
+                            st->done = 1;
+                        }
+                    } else {
+                        lm_step_device(P, phase, sh.solver.S, st, lm, lane);
+                        __syncwarp();
+                        // the solve has terminated: pose write-back + stop test of the ICP loop (ct_icp.cpp:636-672)
+                        if (lane == 0 && lm->done && !st->done) lm_finish_device(P, st, lm, it);
+                    }
+                }
+                __syncthreads();
+                lm_publish(lm_g, lm, tid);
+                __threadfence();
+            }
+            grid.sync();
+        }
+    }
+    if (solver) {
+        if (kPeers && tid == 0) *links.seq = peer_seq;
+        // the whole state (incl. the debug trace) for the host
+        __syncthreads();
+        const int words = (int) (sizeof(LmState) / sizeof(int));
+        const int *src = reinterpret_cast<const int *>(lm);
+        int *dst = reinterpret_cast<int *>(lm_g);
+        for (int i = tid; i < words; i += blockDim.x) dst[i] = src[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -976,8 +1219,6 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     const int eval_blocks = (int) std::max<size_t>(1, std::min<size_t>((r_hint + kLmWarps * 2 - 1) / (kLmWarps * 2), (size_t) num_sms_ * 4));
     EnsurePartials(eval_blocks);
 
-    k_lm_begin<<<1, 32, 0, stream_>>>(d_state, lm, stats);
-    launches_ += 1;
     // solver CERES consults the neighborhood strategy (ct_icp.cpp:571); ROBUST does not (:1235)
     const bool distance_based = !robust && strategy.type == CTICP_STRATEGY_DISTANCE_BASED;
     if (distance_based) {
@@ -999,6 +1240,50 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     }
     auto *classes = static_cast<unsigned char *>(d_lm_classes_);
     if (robust) CT_CUDA_CHECK(cudaMemsetAsync(classes, 0, k_capacity, stream_));   // NEIGHBORHOOD_TYPE::NONE
+
+    if (use_persistent_ && (!sharded || peers_ready_)) {
+        // one cooperative launch for the whole registration (k_lm_persistent); the grid must be co-resident
+        const int mode = robust ? 2 : (distance_based ? 1 : 0);
+        const bool peers = sharded;
+        void *kernel = nullptr;
+        switch (mode * 2 + (peers ? 1 : 0)) {
+            case 0: kernel = (void *) k_lm_persistent<0, false>; break;
+            case 1: kernel = (void *) k_lm_persistent<0, true>; break;
+            case 2: kernel = (void *) k_lm_persistent<1, false>; break;
+            case 3: kernel = (void *) k_lm_persistent<1, true>; break;
+            case 4: kernel = (void *) k_lm_persistent<2, false>; break;
+            default: kernel = (void *) k_lm_persistent<2, true>; break;
+        }
+        int &coresident = lm_coresident_[mode * 2 + (peers ? 1 : 0)];
+        if (coresident == 0) {
+            CT_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LmPShared)));
+            int per_sm = 0;
+            CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kLmPWarps * 32, sizeof(LmPShared)));
+            coresident = std::max(1, per_sm * num_sms_);
+        }
+        const size_t k_share = (k_hint + (size_t) P.shard_world - 1) / (size_t) P.shard_world + 16;
+        int grid = (int) std::min<size_t>((size_t) coresident, 1 + std::max<size_t>(1, (k_share + kp_per_cta_ - 1) / kp_per_cta_));
+        grid = std::max(grid, 2);
+        EnsurePartials(grid);
+        const float4 *kp = d_keypoints;
+        const int *nk = d_num_keypoints;
+        int *sel = d_lm_sel_;
+        const DistanceStrategy *dstrat = static_cast<const DistanceStrategy *>(d_lm_strategy_);
+        double *parts = d_partials_;
+        PeerLinks links = peers ? PeerLinksOf(links_host_) : PeerLinks{};
+        void *args[] = {&G, &P, &kp, &nk, &d_state, &lm, &blocks_buf, &sel, &classes, &stats, &dstrat, &parts, &links};
+        const bool timed = time_gather_ && ev_used_ < kMaxEvents;
+        if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
+        CT_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kLmPWarps * 32), args, sizeof(LmPShared), stream_));
+        if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
+        gather_launches_ += 1;
+        launches_ += 1;
+        DebugLmTrace(lm);
+        return;
+    }
+
+    k_lm_begin<<<1, 32, 0, stream_>>>(d_state, lm, stats);
+    launches_ += 1;
     for (int it = 0; it < opt.num_iters_icp; ++it) {
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
@@ -1043,14 +1328,17 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
         launches_ += 1;
     }
     CT_CUDA_CHECK(cudaGetLastError());
-    if (getenv("CTICP_DEBUG_LM")) {
-        static LmState h;
-        CT_CUDA_CHECK(cudaMemcpyAsync(&h, lm, sizeof(LmState), cudaMemcpyDeviceToHost, stream_));
-        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-        for (int i = 0; i < h.trace_n; ++i)
-            fprintf(stderr, "[eng-lm] x_cost %.12g cand %.12g x %.12g %.12g %.12g %.12g | %.12g %.12g %.12g %s\n", h.trace[i][0], h.trace[i][1],
-                    h.trace[i][6], h.trace[i][7], h.trace[i][8], h.trace[i][9], h.trace[i][10], h.trace[i][11], h.trace[i][12], h.trace[i][5] > 0.5 ? "ACCEPT" : "reject");
-    }
+    DebugLmTrace(lm);
+}
+
+void IcpSolver::DebugLmTrace(void *d_lm) {
+    if (!getenv("CTICP_DEBUG_LM")) return;
+    static LmState h;
+    CT_CUDA_CHECK(cudaMemcpyAsync(&h, d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, stream_));
+    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (int i = 0; i < h.trace_n; ++i)
+        fprintf(stderr, "[eng-lm] x_cost %.12g cand %.12g x %.12g %.12g %.12g %.12g | %.12g %.12g %.12g %s\n", h.trace[i][0], h.trace[i][1],
+                h.trace[i][6], h.trace[i][7], h.trace[i][8], h.trace[i][9], h.trace[i][10], h.trace[i][11], h.trace[i][12], h.trace[i][5] > 0.5 ? "ACCEPT" : "reject");
 }
 
 }  // namespace cticp

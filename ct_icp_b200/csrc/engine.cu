@@ -276,11 +276,13 @@ void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t sta
                           override_alpha, alpha_value);
 }
 
-// Host team of the O(N) passes: a quarter of the machine shared by the ranks of this node, 2..16 threads (measured on
+// Host team of the O(N) passes: half of the machine shared by the ranks of this node, 2..16 threads (measured on
 // the 128-CPU B200 host: packing 130k points takes 0.25 ms on 2 threads, 0.085 on 8, 0.073 on 16).
 int Engine::HostTeamSize(int ranks_on_node) {
     const int hw = std::max(1, (int) std::thread::hardware_concurrency());
-    int threads = std::max(2, std::min(16, hw / (4 * std::max(1, ranks_on_node))));
+    // half of the machine divided between the ranks (round 1 gave each rank hw / (4 ranks): 4 threads at 8 ranks on the
+    // 128-CPU host, and the replicated packing — not the exchange — made the 8-GPU end-to-end time grow)
+    int threads = std::max(2, std::min(16, hw / (2 * std::max(1, ranks_on_node))));
     if (ranks_on_node <= 1) threads = std::max(4, threads);
     if (const char *e = getenv("CTICP_HOST_THREADS")) threads = atoi(e);
     return std::max(1, std::min(threads, std::min(64, hw)));

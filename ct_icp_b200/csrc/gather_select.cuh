@@ -23,7 +23,19 @@
 
 namespace cticp {
 
-constexpr int kSelCap = 192;       // staged in-radius candidates per warp (compaction when a batch might not fit)
+#ifdef CTICP_SEL_BULK
+// Variant (-DCTICP_SEL_BULK, A/B of the north star's "shared-memory/TMA staging of each voxel's neighbor list"): every
+// occupied voxel of the stencil is one contiguous run of <= B float4 — its owner lane issues ONE cp.async.bulk (the TMA
+// engine's 1-D bulk copy, UBLKCP) into the warp's staging area at its prefix offset, one mbarrier per warp collects the
+// bytes, and the distance pass reads the points from shared memory instead of issuing per-lane global loads.
+constexpr int kSelCap = 128;       // staged in-radius candidates per warp (compaction checked per 32-point chunk)
+constexpr int kBulkCap = 256;      // points the staging area holds; a 32-cell stencil slice beyond it uses the load path
+#else
+#ifndef CTICP_SEL_CAP
+#define CTICP_SEL_CAP 192
+#endif
+constexpr int kSelCap = CTICP_SEL_CAP;   // staged in-radius candidates per warp (compaction when a batch might not fit)
+#endif
 constexpr int kSelBuckets = 32;    // one histogram bucket per lane
 #ifndef CTICP_SEL_PREFETCH
 #define CTICP_SEL_PREFETCH 4
@@ -37,9 +49,45 @@ struct __align__(16) SelScratch {   // per-warp shared memory (6.5 KB)
     unsigned char eidx[kSelCap];    // staged positions of the boundary bucket's candidates
     unsigned char eflag[kSelCap];   // per staged position (boundary bucket only): 0 dropped, 1 kept, 2 kept & farthest
     double far[4];                  // rel xyz, d2 of the farthest kept candidate (= reference points[0])
+#ifdef CTICP_SEL_BULK
+    float4 pts[kBulkCap];           // the stencil slice's points, bulk-copied
+#endif
 };
 static_assert(kSelCap <= 256, "eidx is a byte");
+#ifndef CTICP_SEL_BULK
 static_assert(kSelCap >= 32 * kSelPrefetch + 32, "a batch must fit next to the k kept candidates");
+#endif
+
+#ifdef CTICP_SEL_BULK
+__device__ __forceinline__ unsigned sel_smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+// The warp's mbarrier (8 bytes of shared memory OUTSIDE any area that is reused between phases) and its phase parity.
+struct SelBulk {
+    unsigned long long *mbar;
+    unsigned phase;
+};
+// once per kernel and warp, before the first query (all lanes call; lane 0 initialises)
+__device__ __forceinline__ void sel_bulk_init(SelBulk &B, unsigned long long *mbar, int lane) {
+    B.mbar = mbar;
+    B.phase = 0;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sel_smem_addr(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+// bounded wait (a protocol error must end the kernel, not hang the GPU): false after ~0.5 s
+__device__ __forceinline__ bool sel_bulk_wait(const SelBulk &B, unsigned parity) {
+    const unsigned bar = sel_smem_addr(B.mbar);
+    const long long t0 = clock64();
+    unsigned done = 0;
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return true;
+        if (clock64() - t0 > 1000000000LL) return false;
+    }
+}
+#endif
 
 struct NeighborSums {
     int n;                                             // neighbors kept (min(kmax, in-radius candidates))
@@ -141,7 +189,10 @@ template <bool kFilter>
 __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double bucket_scale, const int *stencil,
                                                  const V3 &q, int kx, int ky, int kz, int need, int lane,
                                                  SelScratch &S, NeighborSums &out, unsigned &stencil_points,
-                                                 V3 to_sensor = V3{0, 0, 0}) {
+                                                 V3 to_sensor = V3{0, 0, 0}, void *bulk_ptr = nullptr) {
+#ifdef CTICP_SEL_BULK
+    SelBulk *bulk = static_cast<SelBulk *>(bulk_ptr);   // nullptr: this caller uses the load path
+#endif
     const MapLevel &L = G.L;
     const int side = 2 * G.r + 1;
     const int nst = side * side * side;
@@ -186,6 +237,91 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
         const int excl = incl - cnt;
         pts_total += (unsigned) total;
 
+#ifdef CTICP_SEL_BULK
+        bool staged = false;
+        if (bulk && total > 0 && total <= kBulkCap) {
+            // one bulk copy per occupied voxel into the staging area at its prefix offset; the mbarrier counts the bytes
+            const unsigned bar = sel_smem_addr(bulk->mbar);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned) total * 16u) : "memory");
+            __syncwarp();
+            if (cnt > 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sel_smem_addr(&S.pts[excl])), "l"(L.points + (size_t) slot * L.B), "r"((unsigned) cnt * 16u), "r"(bar)
+                             : "memory");
+            const unsigned parity = bulk->phase & 1u;
+            staged = sel_bulk_wait(*bulk, parity);
+            bulk->phase = parity ^ 1u;   // (per-lane copy of the same value)
+            __syncwarp();
+        }
+        if (staged) {
+            for (int c0 = 0; c0 < total; c0 += 32) {
+                if (fill + 32 > kSelCap) fill = sel_compact(S, fill, G.kmax, bucket_scale, lane, prune_d2);
+                const int f = c0 + lane;
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int probe = lo + step;
+                    const int ex = __shfl_sync(0xffffffffu, excl, probe & 31);
+                    if (probe < 32 && ex <= f) lo = probe;
+                }
+                const bool valid = f < total;
+                const float4 p4 = valid ? S.pts[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const double vx = __shfl_sync(0xffffffffu, ox, lo), vy = __shfl_sync(0xffffffffu, oy, lo),
+                             vz = __shfl_sync(0xffffffffu, oz, lo);
+                const double rx = vx + (double) p4.x, ry = vy + (double) p4.y, rz = vz + (double) p4.z;
+                const double d2 = rx * rx + ry * ry + rz * rz;
+                bool in = valid && !(d2 > G.radius2) && d2 < prune_d2;
+                if (kFilter) {
+                    const double vs = __shfl_sync(0xffffffffu, sdn, lo);
+                    const int vh = __shfl_sync(0xffffffffu, has_normal, lo);
+                    const double scalar = signbit(p4.w) ? -vs : vs;
+                    if (vh && scalar < 0.0) in = false;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const int o = fill + __popc(m & lt_mask);
+                    S.d2[o] = d2; S.rx[o] = rx; S.ry[o] = ry; S.rz[o] = rz;
+                }
+                fill += __popc(m);
+            }
+            __syncwarp();   // the staging area is read before the next slice's copies overwrite it
+            continue;
+        }
+        // slices beyond the staging area (or a timed-out copy: never expected) take the load path below
+        for (int c0 = 0; c0 < total; c0 += 32) {
+            if (fill + 32 > kSelCap) fill = sel_compact(S, fill, G.kmax, bucket_scale, lane, prune_d2);
+            const int f = c0 + lane;
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int probe = lo + step;
+                const int ex = __shfl_sync(0xffffffffu, excl, probe & 31);
+                if (probe < 32 && ex <= f) lo = probe;
+            }
+            const int o_excl = __shfl_sync(0xffffffffu, excl, lo);
+            const int o_slot = __shfl_sync(0xffffffffu, slot, lo);
+            const bool valid = f < total;
+            const float4 p4 = valid ? __ldg(L.points + (size_t) o_slot * L.B + (f - o_excl)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const double vx = __shfl_sync(0xffffffffu, ox, lo), vy = __shfl_sync(0xffffffffu, oy, lo),
+                         vz = __shfl_sync(0xffffffffu, oz, lo);
+            const double rx = vx + (double) p4.x, ry = vy + (double) p4.y, rz = vz + (double) p4.z;
+            const double d2 = rx * rx + ry * ry + rz * rz;
+            bool in = valid && !(d2 > G.radius2) && d2 < prune_d2;
+            if (kFilter) {
+                const double vs = __shfl_sync(0xffffffffu, sdn, lo);
+                const int vh = __shfl_sync(0xffffffffu, has_normal, lo);
+                const double scalar = signbit(p4.w) ? -vs : vs;
+                if (vh && scalar < 0.0) in = false;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const int o = fill + __popc(m & lt_mask);
+                S.d2[o] = d2; S.rx[o] = rx; S.ry[o] = ry; S.rz[o] = rz;
+            }
+            fill += __popc(m);
+        }
+#else
         for (int c0 = 0; c0 < total; c0 += 32 * kSelPrefetch) {
             // room for a whole batch (checked once per batch: one copy of the compaction code, off the common path)
             if (fill + 32 * kSelPrefetch > kSelCap) fill = sel_compact(S, fill, G.kmax, bucket_scale, lane, prune_d2);
@@ -239,6 +375,7 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
                 }
             }
         }
+    #endif
     }
     __syncwarp();
     stencil_points = pts_total;

@@ -189,7 +189,7 @@ struct __align__(16) TileScratch {
 __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const int *stencil,
                                                 const float4 *__restrict__ keypoints, int lo, int hi, int warp_global,
                                                 int warps_total, const GnPose &pose, TileScratch &T, int lane,
-                                                GnWarpAcc &A) {
+                                                GnWarpAcc &A, void *bulk = nullptr) {
     const GatherConfig &G = cfg.G;
     const GnParams &P = cfg.P;
     const int span = hi - lo;
@@ -221,7 +221,7 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
                       qz = __shfl_sync(0xffffffffu, kz, j);
             NeighborSums s;
             unsigned spts = 0;
-            warp_gather_sums<false>(G, P.bucket_scale, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts);
+            warp_gather_sums<false>(G, P.bucket_scale, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts, V3{0, 0, 0}, bulk);
             if (lane == 0) {
                 double *o = T.sums[j];
                 o[0] = (double) s.n; o[1] = (double) spts;
@@ -316,7 +316,9 @@ struct GnShared {
     int stencil[kMaxStencil];
     SolveScratch solve;
     IcpState dummy;
+    IcpState state;   // persistent kernel, solver CTA: the registration state lives here; `st` (global) is its published copy
     int flag;
+    unsigned long long mbar[kGatherWarps];   // -DCTICP_SEL_BULK: one mbarrier per warp for the bulk copies
 };
 
 // deterministic reduction of `rows` partial rows by one CTA: warp g sums the rows b = g (mod kGatherWarps), three
@@ -387,6 +389,12 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
     CT_STAMP(if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg_t[0] = global_timer_ns();)
 
     GnWarpAcc A;
+    void *bulk_ptr = nullptr;
+#ifdef CTICP_SEL_BULK
+    SelBulk bulk;
+    sel_bulk_init(bulk, &sh.mbar[w], lane);
+    bulk_ptr = &bulk;
+#endif
     if (active) {
         const int *stencil = stencil_table_fill(sh.stencil, cfg.G.r);
         if (threadIdx.x == 0) sh.pose = load_pose(st);
@@ -396,7 +404,7 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
         const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
         const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
         gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gridDim.x + blockIdx.x, gridDim.x * kGatherWarps, pose,
-                        sh.tile[w], lane, A);
+                        sh.tile[w], lane, A, bulk_ptr);
     }
     // block reduction (fixed order → run-to-run deterministic)
     gn_store_warp_row(sh.acc[w], A, lane);
@@ -452,6 +460,12 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
     const int *stencil = stencil_table_fill(sh.stencil, cfg.G.r);
     __syncthreads();
 
+    if (solver_cta) {   // working copy of the state in shared memory: the serial tail never waits for global memory
+        const int *src = reinterpret_cast<const int *>(st);
+        int *dst = reinterpret_cast<int *>(&sh.state);
+        for (int i = threadIdx.x; i < (int) (sizeof(IcpState) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
     if (solver_cta && w == 0 && !(P.debug_flags & 4)) {
         // instruction-cache warm-up of the serial tail on a dummy well-posed system (results discarded)
         CT_STAMP(if (lane == 0) st->dbg_t[0] = global_timer_ns();)
@@ -462,13 +476,19 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
         if (lane < 12) sh.acc[1][78 + lane] = 1e-3 * (lane + 1);
         if (lane == 0) {
             sh.acc[1][kAccUsed] = 200.0;
-            sh.dummy = *st;
+            sh.dummy = sh.state;
         }
         __syncwarp();
         warp_gn_solve(sh.acc[1], sh.solve, &sh.dummy, P, 0, nullptr, lane);
         __syncwarp();
     }
 
+    void *bulk_ptr = nullptr;
+#ifdef CTICP_SEL_BULK
+    SelBulk bulk;
+    sel_bulk_init(bulk, &sh.mbar[w], lane);
+    bulk_ptr = &bulk;
+#endif
     long long t_loop = 0, t_solve = 0;
     if (solver_cta && threadIdx.x == 0) t_loop = clock64();
     for (int it = 0; it < num_iters; ++it) {
@@ -484,7 +504,7 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
                 // warp index interleaved over the CTAs: a keypoint set smaller than the grid spreads over all SMs
                 gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gather_ctas + (blockIdx.x - 1),
-                                gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A);
+                                gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A, bulk_ptr);
             }
             gn_store_warp_row(sh.acc[w], A, lane);
             __syncthreads();
@@ -509,25 +529,32 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             }
             CT_STAMP(if (threadIdx.x == 0) st->dbg_t[2] = global_timer_ns();)
             if (w == 0) {
+                IcpState *ws = &sh.state;
                 if (!peers_ok) {
                     if (lane == 0) {   // a peer never answered: give up instead of hanging the device
-                        st->failed = 3;
-                        st->done = 1;
+                        ws->failed = 3;
+                        ws->done = 1;
                     }
                 } else if (P.debug_flags & 1) {
-                    if (lane == 0) st->iter += 1;
+                    if (lane == 0) ws->iter += 1;
                 } else
-                    warp_gn_solve(sh.acc[0], sh.solve, st, P, 0, nullptr, lane);
+                    warp_gn_solve(sh.acc[0], sh.solve, ws, P, 0, nullptr, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    t_solve += clock64() - t_begin;
+                    ws->cycles_total = (unsigned long long) (clock64() - t_loop);
+                    ws->cycles_solve = (unsigned long long) t_solve;
+                }
+                __syncwarp();
+                // publish: the gather CTAs read the pose pair / done flag of the next iteration from global memory
+                const int *src = reinterpret_cast<const int *>(ws);
+                int *dst = reinterpret_cast<int *>(st);
+                for (int i = lane; i < (int) (sizeof(IcpState) / sizeof(int)); i += 32) __stcg(dst + i, src[i]);
                 CT_STAMP(if (lane == 0) st->dbg_t[3] = global_timer_ns();)
-                if (lane == 0) t_solve += clock64() - t_begin;
             }
             __threadfence();
         }
         grid.sync();
-    }
-    if (solver_cta && threadIdx.x == 0) {
-        st->cycles_total = (unsigned long long) (clock64() - t_loop);
-        st->cycles_solve = (unsigned long long) t_solve;
     }
     if (kPeers && solver_cta && threadIdx.x == 0) *links.seq = peer_seq;
 }

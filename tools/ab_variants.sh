@@ -2,19 +2,17 @@
 # A/B of experiment builds of the engine (compile-time variants of the kernels) against the default build.
 #
 #   tools/ab_variants.sh build            # here (no GPU needed): nvcc cross-compiles ct_icp_b200/libcticp_b200_<name>.so
-#   tools/ab_variants.sh run [outdir]     # on the GPU box (inside ONE gpurun call): full GPU test-suite + bench per build
+#   tools/ab_variants.sh run [outdir]     # on the GPU box (inside ONE gpurun call): GN parity tests + bench per build
 #
-# Variants (name:flags). Every variant must pass the whole `pytest -m gpu` suite before its bench line counts.
-#   handoff     -DCTICP_HANDOFF                       point-to-point hand-off instead of two grid barriers per GN iteration
-#   reducemlp   -DCTICP_REDUCE_MLP                    all partial rows of a warp in flight before the first add
-#   handoffmlp  -DCTICP_HANDOFF -DCTICP_REDUCE_MLP
-#   prune       -DCTICP_PRUNE                         drop candidates beyond the current k-th distance
-#   prefetch6/8 -DCTICP_PREFETCH=6 / 8                6 / 8 chunks (192 / 256 stencil points) in flight per load batch
-#   warps8      -DCTICP_GATHER_WARPS=8                the previous CTA shape (control)
+# Variants (name:flags). A variant's bench line only counts if its parity tests pass.
+#   bulk        -DCTICP_SEL_BULK            the stencil's point runs staged in shared memory by cp.async.bulk + mbarrier
+#                                           (UBLKCP / SYNCS: the north star's "TMA staging") instead of per-lane loads
+#   prefetch2/8 -DCTICP_SEL_PREFETCH=2 / 8  2 / 8 chunks of 32 point loads in flight per batch (default 4)
+#   warps8      -DCTICP_GATHER_WARPS=8      8 warps per gather CTA (two CTAs per SM) instead of 16
 set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
-VARIANTS=("handoff:-DCTICP_HANDOFF" "reducemlp:-DCTICP_REDUCE_MLP" "handoffmlp:-DCTICP_HANDOFF -DCTICP_REDUCE_MLP"
-          "prune:-DCTICP_PRUNE" "prefetch6:-DCTICP_PREFETCH=6" "prefetch8:-DCTICP_PREFETCH=8" "warps8:-DCTICP_GATHER_WARPS=8")
+VARIANTS=("bulk:-DCTICP_SEL_BULK" "prefetch2:-DCTICP_SEL_PREFETCH=2" "prefetch8:-DCTICP_SEL_PREFETCH=8 -DCTICP_SEL_CAP=224"
+          "warps8:-DCTICP_GATHER_WARPS=8")
 case "${1:-}" in
 build)
     for v in "${VARIANTS[@]}"; do
@@ -26,27 +24,32 @@ build)
 run)
     out="${2:-$ROOT/gpurun_out/ab}"; mkdir -p "$out"
     cd "$ROOT"
-    python bench.py --no-cpu-baseline > "$out/bench_default.json" 2> /dev/null
+    timeout 600 python bench.py --no-cpu-baseline --no-extras > "$out/bench_default.json" 2> "$out/bench_default.err"
     for v in "${VARIANTS[@]}"; do
         name="${v%%:*}"
         lib="$ROOT/ct_icp_b200/libcticp_b200_$name.so"
         [ -f "$lib" ] || continue
-        CTICP_ENGINE_LIB="$lib" python -m pytest tests -m gpu -q -n 6 > "$out/pytest_$name.log" 2>&1
+        CTICP_ENGINE_LIB="$lib" timeout 900 python -m pytest tests -m gpu -q -n 6 -k "gn or neighborhoods or small or suburb" \
+            > "$out/pytest_$name.log" 2>&1
         echo "rc=$?" >> "$out/pytest_$name.log"
-        CTICP_ENGINE_LIB="$lib" python bench.py --no-cpu-baseline > "$out/bench_$name.json" 2> /dev/null
+        CTICP_ENGINE_LIB="$lib" timeout 600 python bench.py --no-cpu-baseline --no-extras > "$out/bench_$name.json" 2> "$out/bench_$name.err"
     done
     python - "$out" <<'PY'
 import glob, json, os, sys
+rows = []
 for f in sorted(glob.glob(os.path.join(sys.argv[1], "bench_*.json"))):
+    name = os.path.basename(f)[6:-5]
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
-        name = os.path.basename(f)[6:-5]
         log = os.path.join(sys.argv[1], "pytest_%s.log" % name)
-        tests = open(log).read().strip().splitlines()[-2:] if os.path.exists(log) else ["(default build)"]
-        print("%-12s step %.4f ms  GN loop %.1f us  e2e %.4f ms  | %s" % (
-            name, d["ms_per_step"], d["roofline"]["us_per_launch"], d["e2e"]["ms_per_step"], " ".join(tests)))
+        tests = " ".join(open(log).read().strip().splitlines()[-2:]) if os.path.exists(log) else "(default build)"
+        rows.append({"variant": name, "ms_per_step": d["ms_per_step"], "gn_loop_us": d["roofline"]["us_per_launch"],
+                     "e2e_ms": d["e2e"]["ms_per_step"], "tests": tests})
+        print("%-12s step %.4f ms  GN loop %.1f us  e2e %.4f ms  | %s" % (name, d["ms_per_step"], d["roofline"]["us_per_launch"],
+                                                                        d["e2e"]["ms_per_step"], tests))
     except Exception as e:
         print(f, "unreadable:", e)
+json.dump(rows, open(os.path.join(sys.argv[1], "summary.json"), "w"), indent=1)
 PY
     ;;
 *) echo "usage: $0 build | run [outdir]"; exit 2 ;;

@@ -13,10 +13,15 @@ from ct_icp_b200 import synthetic as syn  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=26)
-ap.add_argument("--sensor", default="hdl64")
+ap.add_argument("--sensor", default="hdl64e", help="hdl64e (the bench workload: suburb scene) | hdl64 (street scene) | dense128")
+ap.add_argument("--workload", default="kitti64_gn", choices=sorted(bench.WORKLOADS))
 args = ap.parse_args()
 eng = ct_icp_b200.engine()
-seq = syn.make_sequence(args.frames, {"hdl64": syn.HDL64, "dense128": syn.DENSE128}[args.sensor], seed=1234)
+bench._WORKLOAD = args.workload
+if args.sensor == "hdl64e":
+    seq = bench.make_scans(args.frames, "HDL64E")
+else:
+    seq = syn.make_sequence(args.frames, {"hdl64": syn.HDL64, "dense128": syn.DENSE128}[args.sensor], seed=1234)
 od = eng.odometry(bench.make_options(eng))
 slots = [od.stage_frame(s["xyz"], s["t"]) for s in seq]
 for i, s in enumerate(seq):

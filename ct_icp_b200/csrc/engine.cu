@@ -83,6 +83,7 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
     if (options_.sampling == CTICP_SAMPLING_ADAPTIVE && options_.adaptive_options.num_points_per_voxel != 1)
         throw UnsupportedError("sampling ADAPTIVE: only num_points_per_voxel == 1 is built");
     next_robust_level_ = options_.robust_minimal_level;
+    if (const char *e = getenv("CTICP_FUSED_SAMPLING")) fused_sampling_ = atoi(e) != 0;
 
     {
         pool_ = std::make_unique<HostPool>(HostTeamSize(1));
@@ -272,6 +273,18 @@ void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t sta
     // frames 0 and 1: every timestamp := end_timestamp (odometry.cpp:355-359)
     const bool override_alpha = (k <= 1);
     const float alpha_value = (float) AlphaTimestamp(info.end_timestamp, bts, ets);
+    // The keypoint sampling of the first registration attempt is known already (TryRegister: GRID sampling of the frame,
+    // no truncation): both selections then run in ONE cooperative launch instead of six kernels and four memsets
+    keypoints_sampled_ = false;
+    const bool at_startup = k < options_.init_num_frames;
+    if (fused_sampling_ && k > 0 && !options_.robust_registration && options_.sampling == CTICP_SAMPLING_GRID &&
+        (at_startup || options_.max_num_keypoints <= 0)) {
+        const double kp_size = at_startup ? options_.init_sample_voxel_size : options_.sample_voxel_size;
+        pipe_->SampleFused(sample_size, kp_size, options_.shuffle_seed, ShuffleCounter(k, 0), ShuffleCounter(k, 1),
+                           override_alpha, alpha_value);
+        keypoints_sampled_ = true;
+        return;
+    }
     pipe_->SubSampleFrame(sample_size, options_.shuffle_seed, ShuffleCounter(k, 0), ShuffleCounter(k, 1),
                           override_alpha, alpha_value);
 }
@@ -580,9 +593,11 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     const int k = info.registered_fid;
     const bool at_startup = k < options_.init_num_frames;
     auto t0 = hclock::now();
-    pipe_->SampleKeypoints(options_.sampling, sample_voxel_size,
-                           (!at_startup && options_.max_num_keypoints > 0) ? options_.max_num_keypoints : -1,
-                           options_.shuffle_seed, ShuffleCounter(k, 2 + attempt_idx), &options_.adaptive_options);
+    if (!(keypoints_sampled_ && attempt_idx == 0))   // (else: sampled together with the frame, IngestImpl)
+        pipe_->SampleKeypoints(options_.sampling, sample_voxel_size,
+                               (!at_startup && options_.max_num_keypoints > 0) ? options_.max_num_keypoints : -1,
+                               options_.shuffle_seed, ShuffleCounter(k, 2 + attempt_idx), &options_.adaptive_options);
+    keypoints_sampled_ = false;
     rs.t_sampling = ms_since(t0);
     if (callback_) {   // odometry.cpp:568: the keypoint count is needed on the host for the hook's GetPoints
         pipe_->QueueCountsReadback();

@@ -156,7 +156,9 @@ private:
     void FireEvent(int event, const Summary &rs, const FrameInfo &info);
     cticp_event_fn callback_ = nullptr;
     void *callback_user_ = nullptr;
-    bool frame_world_valid_ = false;   // d_frame_world holds the sub-sampled frame under last_frame_
+    bool frame_world_valid_ = false;
+    bool fused_sampling_ = true;       // CTICP_FUSED_SAMPLING=0: the two grid selections as separate launches
+    bool keypoints_sampled_ = false;   // the keypoints of the coming first attempt were sampled with the frame   // d_frame_world holds the sub-sampled frame under last_frame_
     struct StagedScan {
         float4 *d_points = nullptr;
         size_t n = 0;

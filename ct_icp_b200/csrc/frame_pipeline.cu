@@ -10,6 +10,8 @@
 // and the second shuffle is one scatter through a second permutation — no sort anywhere.
 #include "frame_pipeline.h"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -37,10 +39,9 @@ __device__ __forceinline__ unsigned long long short_voxel_key(const float4 &p, d
 }
 
 // claim: every point bids (priority, index) for its voxel
-__global__ void k_grid_claim(const float4 *__restrict__ pts, const int *__restrict__ d_n, double voxel_size,
-                             int use_perm, uint64_t seed, uint64_t counter, unsigned long long *keys,
-                             unsigned long long *vals, uint32_t cap_mask, int *__restrict__ slot_of) {
-    const int n = *d_n;
+__device__ __forceinline__ void grid_claim_dev(const float4 *__restrict__ pts, int n, double voxel_size, int use_perm,
+                                               uint64_t seed, uint64_t counter, unsigned long long *keys,
+                                               unsigned long long *vals, uint32_t cap_mask, int *__restrict__ slot_of) {
     const Perm perm = perm_make(seed, counter, (uint32_t) max(n, 1));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned long long key = short_voxel_key(pts[i], voxel_size);
@@ -56,12 +57,15 @@ __global__ void k_grid_claim(const float4 *__restrict__ pts, const int *__restri
         slot_of[i] = (int) h;
     }
 }
+__global__ void k_grid_claim(const float4 *__restrict__ pts, const int *__restrict__ d_n, double voxel_size,
+                             int use_perm, uint64_t seed, uint64_t counter, unsigned long long *keys,
+                             unsigned long long *vals, uint32_t cap_mask, int *__restrict__ slot_of) {
+    grid_claim_dev(pts, *d_n, voxel_size, use_perm, seed, counter, keys, vals, cap_mask, slot_of);
+}
 // mark: winners raise a flag at their position in the permuted order
-__global__ void k_grid_mark(const int *__restrict__ d_n, int use_perm, uint64_t seed, uint64_t counter,
-                            const unsigned long long *__restrict__ vals, const int *__restrict__ slot_of,
-                            uint32_t *__restrict__ flags, uint32_t *__restrict__ src,
-                            uint32_t *__restrict__ tile_count) {
-    const int n = *d_n;
+__device__ __forceinline__ void grid_mark_dev(int n, int use_perm, uint64_t seed, uint64_t counter,
+                                              const unsigned long long *vals, const int *slot_of, uint32_t *__restrict__ flags,
+                                              uint32_t *__restrict__ src, uint32_t *__restrict__ tile_count) {
     const Perm perm = perm_make(seed, counter, (uint32_t) max(n, 1));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t prio = use_perm ? perm_apply(perm, (uint32_t) i) : (uint32_t) i;
@@ -73,20 +77,31 @@ __global__ void k_grid_mark(const int *__restrict__ d_n, int use_perm, uint64_t 
         }
     }
 }
+__global__ void k_grid_mark(const int *__restrict__ d_n, int use_perm, uint64_t seed, uint64_t counter,
+                            const unsigned long long *__restrict__ vals, const int *__restrict__ slot_of,
+                            uint32_t *__restrict__ flags, uint32_t *__restrict__ src,
+                            uint32_t *__restrict__ tile_count) {
+    grid_mark_dev(*d_n, use_perm, seed, counter, vals, slot_of, flags, src, tile_count);
+}
 // emit: compact the winners in permuted order and (optionally) scatter them through a second permutation (the
 // second shuffle). One CTA per tile of 1024 positions: the exclusive prefix of a position is
 //   Σ tile_count[tiles before] (every CTA re-adds those <= 512 counters) + a CTA-local scan of the tile's flags,
 // which replaces a serial single-CTA scan over all positions (64 us for 130k points) by a fully parallel pass.
-__global__ void __launch_bounds__(kTileThreads)
-k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_index, const int *__restrict__ d_n,
-            const uint32_t *__restrict__ flags, const uint32_t *__restrict__ src,
-            const uint32_t *__restrict__ tile_count, int use_perm2, uint64_t seed, uint64_t counter2,
-            int override_alpha, float alpha_value, float4 *__restrict__ out, uint32_t *__restrict__ out_src_index,
-            int *__restrict__ d_total) {
-    __shared__ uint32_t s_red[2][kTileThreads / 32];
-    __shared__ uint32_t s_warp[kTileThreads / 32];
-    __shared__ uint32_t s_before, s_total;
-    const int n = *d_n;
+struct EmitScratch {
+    uint32_t red[2][kTileThreads / 32];
+    uint32_t warp[kTileThreads / 32];
+    uint32_t before, total;
+};
+// all threads of a CTA of kTileThreads threads; returns the number of winners (identical in every CTA)
+__device__ __forceinline__ uint32_t grid_emit_dev(const float4 *pts, const uint32_t *in_src_index, int n,
+                                                  const uint32_t *flags, const uint32_t *src, const uint32_t *tile_count,
+                                                  int use_perm2, uint64_t seed, uint64_t counter2, int override_alpha,
+                                                  float alpha_value, float4 *__restrict__ out,
+                                                  uint32_t *__restrict__ out_src_index, int *__restrict__ d_total,
+                                                  EmitScratch &sc) {
+    uint32_t (&s_red)[2][kTileThreads / 32] = sc.red;
+    uint32_t (&s_warp)[kTileThreads / 32] = sc.warp;
+    uint32_t &s_before = sc.before, &s_total = sc.total;
     const int num_tiles = (n + kTile - 1) >> kTileShift;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     // grand total (domain of the second permutation) — identical in every CTA
@@ -153,6 +168,66 @@ k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_
             excl += v[k];
         }
     }
+    return total;
+}
+__global__ void __launch_bounds__(kTileThreads)
+k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_index, const int *__restrict__ d_n,
+            const uint32_t *__restrict__ flags, const uint32_t *__restrict__ src,
+            const uint32_t *__restrict__ tile_count, int use_perm2, uint64_t seed, uint64_t counter2,
+            int override_alpha, float alpha_value, float4 *__restrict__ out, uint32_t *__restrict__ out_src_index,
+            int *__restrict__ d_total) {
+    __shared__ EmitScratch sc;
+    grid_emit_dev(pts, in_src_index, *d_n, flags, src, tile_count, use_perm2, seed, counter2, override_alpha, alpha_value, out,
+                  out_src_index, d_total, sc);
+}
+
+// ---- both grid selections of a frame (sub_sample_frame N -> F, grid_sampling F -> K) in ONE cooperative launch: seven
+// phases separated by grid barriers instead of six kernels + four memsets. (Each of those kernels lasts 4-11 us for work
+// worth about one: launch ramp, tail, and the dependency on its predecessor; 46 us of a 310 us step in round 1.)
+struct FusedSampleArgs {
+    const float4 *raw;
+    int *counts;                       // [0] = N in, [1] = F out, [2] = K out
+    double voxel1, voxel2;
+    uint64_t seed, c1, c2;
+    int override_alpha;
+    float alpha_value;
+    unsigned long long *grid;          // keys | vals, 2 * cap1 words
+    uint32_t cap1;
+    int *slot_of;
+    uint32_t *tile1, *flags1, *src1;   // selection 1 (tile counters and flags adjacent)
+    uint32_t *tile2, *flags2, *src2;   // selection 2
+    float4 *frame, *keypoints;
+    uint32_t *frame_src, *kp_src;
+};
+__global__ void __launch_bounds__(kTileThreads)
+k_sample_fused(FusedSampleArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ EmitScratch sc;
+    const size_t gtid = (size_t) blockIdx.x * blockDim.x + threadIdx.x, gsize = (size_t) gridDim.x * blockDim.x;
+    const int n = a.counts[0];
+    // phase 0: clear the hash grid and the flag / tile-counter arrays of selection 1
+    for (size_t i = gtid; i < 2 * (size_t) a.cap1; i += gsize) a.grid[i] = kGridEmpty;
+    for (size_t i = gtid; i < kMaxTiles + (size_t) n; i += gsize) a.tile1[i] = 0u;   // flags1 = tile1 + kMaxTiles
+    grid.sync();
+    grid_claim_dev(a.raw, n, a.voxel1, 1, a.seed, a.c1, a.grid, a.grid + a.cap1, a.cap1 - 1, a.slot_of);
+    grid.sync();
+    grid_mark_dev(n, 1, a.seed, a.c1, a.grid + a.cap1, a.slot_of, a.flags1, a.src1, a.tile1);
+    grid.sync();
+    const uint32_t F = grid_emit_dev(a.raw, nullptr, n, a.flags1, a.src1, a.tile1, 1, a.seed, a.c2, a.override_alpha,
+                                     a.alpha_value, a.frame, a.frame_src, a.counts + 1, sc);
+    // selection 2 works on F points: a smaller grid (the first one is not read any more), its own flags
+    uint32_t cap2 = 1024;
+    while (cap2 < 2 * F) cap2 <<= 1;
+    for (size_t i = gtid; i < 2 * (size_t) cap2; i += gsize) a.grid[i] = kGridEmpty;
+    for (size_t i = gtid; i < kMaxTiles + (size_t) F; i += gsize) a.tile2[i] = 0u;
+    grid.sync();
+    grid_claim_dev(a.frame, (int) F, a.voxel2, 0, 0, 0, a.grid, a.grid + cap2, cap2 - 1, a.slot_of);
+    grid.sync();
+    grid_mark_dev((int) F, 0, 0, 0, a.grid + cap2, a.slot_of, a.flags2, a.src2, a.tile2);
+    grid.sync();
+    grid_emit_dev(a.frame, a.frame_src, (int) F, a.flags2, a.src2, a.tile2, 0, 0, 0, 0, 0.f, a.keypoints, a.kp_src,
+                  a.counts + 2, sc);
 }
 // ---- adaptive (distance-banded) grid sampling: AdaptiveSamplePointsInGrid, include/ct_icp/algorithm/sampling.h:55-110
 struct AdaptiveBands {
@@ -292,6 +367,7 @@ FramePipeline::~FramePipeline() {
     cudaFree(d_frame_src_); cudaFree(d_kp_src_); cudaFree(d_tmp_src_);
     cudaFree(d_grid_); cudaFree(d_slot_of_); cudaFree(d_tile_count_); cudaFree(d_src_);
     cudaFree(d_counts_); cudaFree(d_frame_world_); cudaFree(d_all_world_); cudaFree(d_adaptive_);
+    cudaFree(d_tile2_); cudaFree(d_src2_);
 }
 
 int FramePipeline::Blocks(size_t n) const { return (int) std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 148 * 8)); }
@@ -383,6 +459,40 @@ void FramePipeline::AdaptiveSelect(const cticp_adaptive_options &o, const float4
         launches_ += 1;
     }
     CT_CUDA_CHECK(cudaGetLastError());
+}
+
+// SubSampleFrame + SampleKeypoints(GRID) of one frame in a single cooperative launch (k_sample_fused). The keypoint
+// sampling's parameters must be known when the frame arrives: true for the first registration attempt of a frame.
+void FramePipeline::SampleFused(double voxel_size, double sample_voxel_size, uint64_t seed, uint64_t counter1,
+                                uint64_t counter2, bool override_alpha, float alpha_value) {
+    if (!d_tile2_) {
+        CT_CUDA_CHECK(cudaMalloc(&d_tile2_, sizeof(uint32_t) * (kMaxTiles + max_points_)));
+        CT_CUDA_CHECK(cudaMalloc(&d_src2_, sizeof(uint32_t) * max_points_));
+        int per_sm = 0;
+        CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_fused, kTileThreads, 0));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        fused_grid_ = std::max(1, std::min(per_sm, 4) * sms);
+    }
+    FusedSampleArgs a;
+    a.raw = d_raw_;
+    a.counts = d_counts_;
+    a.voxel1 = voxel_size;
+    a.voxel2 = sample_voxel_size;
+    a.seed = seed; a.c1 = counter1; a.c2 = counter2;
+    a.override_alpha = override_alpha ? 1 : 0;
+    a.alpha_value = alpha_value;
+    a.grid = d_grid_;
+    a.cap1 = std::max<uint32_t>(NextPow2(2 * n_), 1024);
+    a.slot_of = d_slot_of_;
+    a.tile1 = d_tile_count_; a.flags1 = d_flags_; a.src1 = d_src_;
+    a.tile2 = d_tile2_; a.flags2 = d_tile2_ + kMaxTiles; a.src2 = d_src2_;
+    a.frame = d_frame_; a.keypoints = d_keypoints_;
+    a.frame_src = d_frame_src_; a.kp_src = d_kp_src_;
+    void *args[] = {&a};
+    CT_CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_sample_fused, dim3(fused_grid_), dim3(kTileThreads), args, 0, stream_));
+    launches_ += 1;
 }
 
 void FramePipeline::SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2,

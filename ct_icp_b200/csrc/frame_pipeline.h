@@ -30,6 +30,9 @@ public:
     // Odometry::InitializeFrame: shuffle → sub_sample_frame → (frames 0,1: timestamp := end) → shuffle
     void SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2, bool override_alpha,
                         float alpha_value);
+    // both of the above (GRID sampling, no truncation) in one cooperative launch
+    void SampleFused(double voxel_size, double sample_voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2,
+                     bool override_alpha, float alpha_value);
     // TryRegister: grid_sampling | NONE, then the optional max_num_keypoints shuffle-truncate
     void SampleKeypoints(int sampling, double sample_voxel_size, int max_num_keypoints, uint64_t seed, uint64_t counter,
                          const cticp_adaptive_options *adaptive = nullptr);
@@ -85,6 +88,8 @@ private:
     uint32_t *d_tile_count_ = nullptr, *d_flags_ = nullptr, *d_src_ = nullptr;   // flags live right after the tile counters
     int *d_counts_ = nullptr;
     double *d_frame_world_ = nullptr, *d_all_world_ = nullptr;
+    uint32_t *d_tile2_ = nullptr, *d_src2_ = nullptr;   // second selection of the fused sampler
+    int fused_grid_ = 0;
     uint32_t *d_adaptive_ = nullptr;   // tile counters + flags + src of the band-major position space
     size_t adaptive_capacity_ = 0;
     int launches_ = 0;

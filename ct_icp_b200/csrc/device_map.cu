@@ -5,6 +5,8 @@
 //   RemoveElementsFarFromLocation             :305-322           (tests the voxel's FIRST stored point)
 //   NumPoints / GetMapPoints                  :345-376
 #include "device_map.h"
+
+#include <cooperative_groups.h>
 #include "gather.cuh"
 
 #include <algorithm>
@@ -37,9 +39,8 @@ __global__ void k_clear_level(MapLevel L) {
 
 // Phase 1 of InsertPointCloud: find-or-create the voxel of every point and thread the point onto the voxel's
 // candidate list. One thread per point; the list order is arbitrary (phase 2 re-orders by point index).
-__global__ void k_insert_claim(MapLevel L, MapCounters *ctr, const double *__restrict__ world, const int *d_n,
-                               int *__restrict__ next, uint32_t *__restrict__ touched) {
-    const int n = *d_n;
+__device__ __forceinline__ void insert_claim_dev(const MapLevel &L, MapCounters *ctr, const double *world, int n,
+                                                 int *__restrict__ next, uint32_t *__restrict__ touched) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double px = world[3 * i], py = world[3 * i + 1], pz = world[3 * i + 2];
         if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
@@ -76,6 +77,10 @@ __global__ void k_insert_claim(MapLevel L, MapCounters *ctr, const double *__res
         if (old == kNil) touched[atomicAdd(&ctr->num_touched, 1u)] = (uint32_t) slot;
     }
 }
+__global__ void k_insert_claim(MapLevel L, MapCounters *ctr, const double *__restrict__ world, const int *d_n,
+                               int *__restrict__ next, uint32_t *__restrict__ touched) {
+    insert_claim_dev(L, ctr, world, *d_n, next, touched);
+}
 
 // Phase 2: one warp per touched voxel applies the reference's sequential rule to that voxel's candidates in
 // ascending point index: accept while count < B and every stored point is farther than min_dist (map.h:276-291);
@@ -90,14 +95,19 @@ __device__ __forceinline__ double commit_warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kInsertWarps * 32)
-k_insert_commit(MapLevel L, MapCounters *ctr, const double *__restrict__ world, const int *__restrict__ next,
-                const uint32_t *__restrict__ touched, const double *__restrict__ frame_origins, int frame_ordinal) {
-    __shared__ int s_cand[kInsertWarps][kMaxCand];
-    __shared__ int s_sorted[kInsertWarps][kMaxCand];
-    __shared__ float4 s_pts[kInsertWarps][kMaxB];
+struct CommitScratch {
+    int cand[kInsertWarps][kMaxCand];
+    int sorted[kInsertWarps][kMaxCand];
+    float4 pts[kInsertWarps][kMaxB];
+};
+__device__ __forceinline__ void insert_commit_dev(const MapLevel &L, MapCounters *ctr, const double *world,
+                                                  const int *next, const uint32_t *touched, const double *frame_origins,
+                                                  int frame_ordinal, CommitScratch &sc) {
+    int (&s_cand)[kInsertWarps][kMaxCand] = sc.cand;
+    int (&s_sorted)[kInsertWarps][kMaxCand] = sc.sorted;
+    float4 (&s_pts)[kInsertWarps][kMaxB] = sc.pts;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned n_touched = ctr->num_touched;
+    const unsigned n_touched = *reinterpret_cast<volatile unsigned *>(&ctr->num_touched);
     const int warps_total = gridDim.x * kInsertWarps;
     for (unsigned t = blockIdx.x * kInsertWarps + w; t < n_touched; t += warps_total) {
         const uint32_t slot = touched[t];
@@ -204,9 +214,16 @@ k_insert_commit(MapLevel L, MapCounters *ctr, const double *__restrict__ world, 
     }
 }
 
+__global__ void __launch_bounds__(kInsertWarps * 32)
+k_insert_commit(MapLevel L, MapCounters *ctr, const double *__restrict__ world, const int *__restrict__ next,
+                const uint32_t *__restrict__ touched, const double *__restrict__ frame_origins, int frame_ordinal) {
+    __shared__ CommitScratch sc;
+    insert_commit_dev(L, ctr, world, next, touched, frame_origins, frame_ordinal, sc);
+}
+
 // RemoveElementsFarFromLocation (map.h:305-322): a voxel goes when its FIRST stored point is farther than
 // `distance` from `location` (or when it is empty). Tombstones keep probe chains intact; Rebuild() purges them.
-__global__ void k_remove_far(MapLevel L, MapCounters *ctr, V3 loc, double distance) {
+__device__ __forceinline__ void remove_far_dev(const MapLevel &L, MapCounters *ctr, V3 loc, double distance) {
     const uint32_t cap = L.cap_mask + 1;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
         const unsigned long long key = L.slots[s].key;
@@ -228,6 +245,54 @@ __global__ void k_remove_far(MapLevel L, MapCounters *ctr, V3 loc, double distan
             atomicSub(&ctr->num_voxels, 1u);
             atomicAdd(&ctr->num_points, (unsigned long long) (-(long long) count));
         }
+    }
+}
+
+__global__ void k_remove_far(MapLevel L, MapCounters *ctr, V3 loc, double distance) { remove_far_dev(L, ctr, loc, distance); }
+
+// ---- the whole map update of a frame (odometry.cpp:855-953: transform of the sub-sampled frame with the final pose pair,
+// RemoveElementsFarFromLocation, InsertPointCloud on every resolution) in ONE cooperative launch: phases separated by
+// grid barriers instead of 2 + 2 x levels kernels and their memsets (29 us of a 310 us step in round 1, most of it the
+// fixed cost of five short dependent launches).
+struct FusedUpdateArgs {
+    MapLevel levels[CTICP_MAX_RESOLUTIONS];
+    int num_levels;
+    MapCounters *counters;
+    const float4 *frame;        // sub-sampled frame (raw xyz, alpha)
+    const int *d_n;
+    double *world;              // out: its world points under the pose pair
+    Q4 qb, qe;
+    V3 tb, te;
+    SlerpConsts sc;
+    V3 location;                // eviction centre (the end position) and radius
+    double max_distance;
+    int do_remove, do_insert;
+    int *next;
+    uint32_t *touched;
+    const double *frame_origins;
+    int frame_ordinal;
+};
+__global__ void __launch_bounds__(kInsertWarps * 32)
+k_map_update_fused(FusedUpdateArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ CommitScratch sc;
+    const int n = *a.d_n;
+    // phase 1: world points of the frame; eviction on every level; reset the per-level touched counters
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = a.frame[i];
+        const V3 w = ct_transform_c(a.qb, a.tb, a.qe, a.te, (double) p.w, V3{(double) p.x, (double) p.y, (double) p.z}, a.sc);
+        a.world[3 * i] = w.x; a.world[3 * i + 1] = w.y; a.world[3 * i + 2] = w.z;
+    }
+    if (a.do_remove)
+        for (int l = 0; l < a.num_levels; ++l) remove_far_dev(a.levels[l], a.counters + l, a.location, a.max_distance);
+    if (blockIdx.x == 0 && threadIdx.x < a.num_levels) a.counters[threadIdx.x].num_touched = 0;
+    if (!a.do_insert) return;   // uniform
+    for (int l = 0; l < a.num_levels; ++l) {
+        grid.sync();
+        insert_claim_dev(a.levels[l], a.counters + l, a.world, n, a.next, a.touched);
+        grid.sync();
+        insert_commit_dev(a.levels[l], a.counters + l, a.world, a.next, a.touched, a.frame_origins, a.frame_ordinal, sc);
     }
 }
 
@@ -385,6 +450,62 @@ void DeviceMap::InsertDevice(const double *d_world_xyz, const int *d_n, size_t n
         launches_ += 2;
     }
     CT_CUDA_CHECK(cudaGetLastError());
+    dirty_ = true;
+}
+
+void DeviceMap::UpdateFused(const float4 *d_frame, const int *d_n, size_t n_upper, double *d_world, const Q4 &qb,
+                            const V3 &tb, const Q4 &qe, const V3 &te, bool do_remove, V3 location, double max_distance,
+                            bool do_insert, V3 origin) {
+    if (n_upper == 0) return;
+    EnsureScratch(n_upper);
+    int frame_ordinal = 0;
+    if (do_insert) {
+        if (frame_count_ >= (1u << 24) - 2) throw CapacityError("more than 2^24 frames inserted into one map");
+        if (with_normals_) {
+            if (frame_count_ >= frame_capacity_) {
+                const size_t cap = std::max<size_t>(4096, frame_capacity_ * 2);
+                double *fresh = nullptr;
+                CT_CUDA_CHECK(cudaMalloc(&fresh, sizeof(double) * 3 * cap));
+                if (frame_count_)
+                    CT_CUDA_CHECK(cudaMemcpyAsync(fresh, d_frame_origins_, sizeof(double) * 3 * frame_count_,
+                                                  cudaMemcpyDeviceToDevice, stream_));
+                CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+                cudaFree(d_frame_origins_);
+                d_frame_origins_ = fresh;
+                frame_capacity_ = cap;
+            }
+            const double o[3] = {origin.x, origin.y, origin.z};
+            CT_CUDA_CHECK(cudaMemcpyAsync(d_frame_origins_ + 3 * frame_count_, o, sizeof(o), cudaMemcpyHostToDevice, stream_));
+        }
+        frame_ordinal = (int) frame_count_++;
+    }
+    if (fused_grid_ == 0) {
+        int per_sm = 0, dev = 0, sms = 148;
+        CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_update_fused, kInsertWarps * 32, 0));
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        fused_grid_ = std::max(1, std::min(per_sm, 4) * sms);
+    }
+    FusedUpdateArgs a{};
+    a.num_levels = (int) levels_.size();
+    for (int l = 0; l < a.num_levels; ++l) a.levels[l] = levels_[l];
+    a.counters = d_counters_;
+    a.frame = d_frame;
+    a.d_n = d_n;
+    a.world = d_world;
+    a.qb = qb; a.qe = qe; a.tb = tb; a.te = te;
+    a.sc = slerp_consts(qb, qe);
+    a.location = location;
+    a.max_distance = max_distance;
+    a.do_remove = do_remove ? 1 : 0;
+    a.do_insert = do_insert ? 1 : 0;
+    a.next = d_next_;
+    a.touched = d_touched_;
+    a.frame_origins = d_frame_origins_;
+    a.frame_ordinal = frame_ordinal;
+    void *args[] = {&a};
+    CT_CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_map_update_fused, dim3(fused_grid_), dim3(kInsertWarps * 32), args, 0, stream_));
+    launches_ += 1;
     dirty_ = true;
 }
 

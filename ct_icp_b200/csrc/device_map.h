@@ -33,6 +33,9 @@ public:
     bool HasNormals() const { return with_normals_; }
     // RemoveElementsFarFromLocation (map.h:305-322)
     void RemoveFar(V3 location, double distance);
+    // one cooperative launch: world points of the sub-sampled frame under the pose pair (→ d_world), RemoveFar, InsertDevice
+    void UpdateFused(const float4 *d_frame, const int *d_n, size_t n_upper, double *d_world, const Q4 &qb, const V3 &tb,
+                     const Q4 &qe, const V3 &te, bool do_remove, V3 location, double max_distance, bool do_insert, V3 origin);
     void Clear();
 
     // counters (synchronises the stream when stale)
@@ -84,6 +87,7 @@ private:
     size_t frame_capacity_ = 0, frame_count_ = 0;
     int launches_ = 0;
     int rebuilds_ = 0;
+    int fused_grid_ = 0;
 };
 
 }  // namespace cticp

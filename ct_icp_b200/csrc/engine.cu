@@ -84,6 +84,7 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
         throw UnsupportedError("sampling ADAPTIVE: only num_points_per_voxel == 1 is built");
     next_robust_level_ = options_.robust_minimal_level;
     if (const char *e = getenv("CTICP_FUSED_SAMPLING")) fused_sampling_ = atoi(e) != 0;
+    if (const char *e = getenv("CTICP_FUSED_MAP_UPDATE")) fused_map_update_ = atoi(e) != 0;
 
     {
         pool_ = std::make_unique<HostPool>(HostTeamSize(1));
@@ -824,11 +825,20 @@ void Engine::UpdateMap(Summary &s, int registered_fid) {
     if (options_.always_insert) add_points = true;
 
     const V3 location = trajectory_.back().end_pose.pose.t;
-    map_->RemoveFar(location, options_.max_distance);
-    if (add_points) {
-        map_->EnsureRoomFor((size_t) std::max(0, pipe_->h_counts()[1]));   // F is known since the pose read-back
+    if (add_points) map_->EnsureRoomFor((size_t) std::max(0, pipe_->h_counts()[1]));   // F is known since the pose read-back
+    if (fused_map_update_) {
+        // transform of the sub-sampled frame + eviction + insertion on every resolution: one cooperative launch
+        const auto &f = s.frame;
+        map_->UpdateFused(pipe_->d_frame(), pipe_->d_count_frame(), pipe_->n(), pipe_->d_frame_world_mut(), f.begin_pose.pose.q,
+                          f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t, true, location, options_.max_distance,
+                          add_points, f.begin_pose.pose.t);
+        frame_world_valid_ = true;
+    } else {
+        map_->RemoveFar(location, options_.max_distance);
         // frame_poses = {begin_pose, end_pose} (odometry.cpp:949): the begin position orients the voxel normals
-        map_->InsertDevice(pipe_->d_frame_world(), pipe_->d_count_frame(), pipe_->n(), s.frame.begin_pose.pose.t);
+        if (add_points) map_->InsertDevice(pipe_->d_frame_world(), pipe_->d_count_frame(), pipe_->n(), s.frame.begin_pose.pose.t);
+    }
+    if (add_points) {
         tracker_.skipped_frames = 0;
         tracker_.cum_orientation = 0;
         tracker_.cum_distance = 0;
@@ -969,17 +979,19 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     auto t_before_map = hclock::now();
     if (!early_return) {
         const auto &f = summary.frame;
-        pipe_->TransformFrame(f.begin_pose.pose.q, f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t);
-        frame_world_valid_ = true;
-        if (summary_points_mask_) {
-            if (!ran_icp) {   // frame 0: no pose read-back has synchronised the stream yet; the egress reads N and F
-                CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-                staging_in_flight_ = false;
-            }
-            EnqueueEgress(f, ran_icp);
+        if (!ran_icp) {   // frame 0: no pose read-back has synchronised the stream yet; F sizes the map tables / the egress
+            pipe_->QueueCountsReadback();
+            CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+            staging_in_flight_ = false;
+        }
+        if (!fused_map_update_) {
+            pipe_->TransformFrame(f.begin_pose.pose.q, f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t);
+            frame_world_valid_ = true;
+            if (summary_points_mask_) EnqueueEgress(f, ran_icp);
         }
         ComputeSummaryMetrics(summary, k);
         UpdateMap(summary, k);
+        if (fused_map_update_ && summary_points_mask_) EnqueueEgress(f, ran_icp);   // (the fused update wrote d_frame_world)
         if (callback_) {   // odometry.cpp:491
             const bool fw = frame_world_valid_, aw = last_all_world_valid_, kw = last_kp_world_valid_;
             const bool e0 = egress_valid_[0], e1 = egress_valid_[1], e2 = egress_valid_[2];

@@ -157,6 +157,7 @@ private:
     cticp_event_fn callback_ = nullptr;
     void *callback_user_ = nullptr;
     bool frame_world_valid_ = false;
+    bool fused_map_update_ = true;     // CTICP_FUSED_MAP_UPDATE=0: transform / evict / insert as separate launches
     bool fused_sampling_ = true;       // CTICP_FUSED_SAMPLING=0: the two grid selections as separate launches
     bool keypoints_sampled_ = false;   // the keypoints of the coming first attempt were sampled with the frame   // d_frame_world holds the sub-sampled frame under last_frame_
     struct StagedScan {

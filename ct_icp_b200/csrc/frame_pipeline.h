@@ -70,6 +70,7 @@ public:
                     int use_perm1, uint64_t seed, uint64_t c1, int use_perm2, uint64_t c2, int override_alpha,
                     float alpha_value, float4 *out, uint32_t *out_src, int *d_n_out);
     float4 *d_raw_mut() { return d_raw_; }
+    double *d_frame_world_mut() { return d_frame_world_; }
     float4 *d_frame_mut() { return d_frame_; }
     uint32_t *d_frame_src_mut() { return d_frame_src_; }
 

@@ -12,6 +12,8 @@
 #include <emmintrin.h>
 #include <xmmintrin.h>
 
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges are no-ops unless a profiler injects the NVTX library
+
 namespace cticp {
 
 #define CT_CUDA_CHECK(expr)                                                                              \
@@ -21,6 +23,13 @@ namespace cticp {
             throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
                             std::to_string(__LINE__));                                                   \
     } while (0)
+
+// NVTX range of one stage of RegisterFrame (ingest / sample / icp / map_update / egress): timelines of ncu / nsys-less tools
+// attribute the launches to the stage that enqueued them
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 using hclock = std::chrono::steady_clock;
 static double ms_since(hclock::time_point t0) {
@@ -174,6 +183,7 @@ void Engine::AllocEgress() {
 // the main stream has been synchronised on the pose read-back (so everything the egress kernels read is complete) and
 // after TransformFrame was enqueued on the main stream (ev_egress_main_ orders the copy of d_frame_world behind it).
 void Engine::EnqueueEgress(const HostFrame &f, bool ran_icp) {
+    NvtxRange range("cticp.egress");
     const Q4 qb = f.begin_pose.pose.q, qe = f.end_pose.pose.q;
     const V3 tb = f.begin_pose.pose.t, te = f.end_pose.pose.t;
     const size_t n_all = pipe_->n(), n_frame = (size_t) pipe_->h_counts()[1];
@@ -254,6 +264,7 @@ void Engine::InitializeMotion(const FrameInfo &info, const cticp_frame *initial_
 // InitializeFrame, odometry.cpp:333-382 — host part: pack (x, y, z, alpha) into pinned memory; device part:
 // shuffle / sub_sample_frame / timestamp override / shuffle.
 void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t staged_slot) {
+    NvtxRange range("cticp.ingest.subsample");
     const size_t n = scan.n;
     const int k = info.registered_fid;
     const HostFrame &tr = trajectory_[k];
@@ -432,6 +443,7 @@ void Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst)
 //   3. the scan is packed in kRounds rounds; in round r part p packs piece r * parts + p, so a finished round is one
 //      contiguous range — part 0 enqueues its H2D copy at once and the copy engine works while later rounds are packed.
 void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, double *mn_out, double *mx_out) {
+    NvtxRange range("cticp.ingest.pack_upload");
     constexpr int kRounds = 4;
     const size_t n = scan.n;
     const int parts = pool_->PartsFor(n);
@@ -591,6 +603,7 @@ void Engine::FlushL2(size_t bytes) {
 // TryRegister, odometry.cpp:525-601
 void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summary &rs, double sample_voxel_size,
                          const MotionModel *mm, int attempt_idx) {
+    NvtxRange range("cticp.icp");
     const int k = info.registered_fid;
     const bool at_startup = k < options_.init_num_frames;
     auto t0 = hclock::now();
@@ -794,6 +807,7 @@ void Engine::ComputeSummaryMetrics(Summary &s, int k) {
 
 // UpdateMap, odometry.cpp:855-953
 void Engine::UpdateMap(Summary &s, int registered_fid) {
+    NvtxRange range("cticp.map_update");
     bool add_points = true;
     if (options_.robust_registration) {
         suspect_registration_error_ = s.number_of_attempts >= options_.robust_num_attempts;

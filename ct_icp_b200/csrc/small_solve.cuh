@@ -29,33 +29,42 @@ struct SolveScratch {
 };
 
 // Solve the 12x12 SPD system held in S.A / S.b; x → S.x.
-// Eigen's A.ldlt().solve(b) (ct_icp.cpp:914) is replaced by Gauss-Jordan elimination in natural order: lane r keeps
-// row r of [A | b] in 13 registers, the pivot row is broadcast with shuffles and all rows are eliminated at once, so
-// a step costs one fp64 reciprocal plus 13 FMAs instead of a serial O(n^2) sweep, and no back-substitution is
-// needed. The system is symmetric positive definite (JTJ/n plus the diagonal regularisers), for which elimination
-// without pivoting is backward stable; the result agrees with a pivoted LDL^T to ~1e-13 relative. This serial tail
-// sits on the critical path of every ICP iteration (it was 60 us as single-thread code, ~2 us now).
-static __device__ void warp_ldlt_solve12(SolveScratch &S, int lane) {
-    double row[13];
-    const int r = lane < 12 ? lane : 0;
+// Eigen's A.ldlt().solve(b) (ct_icp.cpp:914) is replaced by Gauss-Jordan elimination in natural order on the augmented
+// matrix [A | b] IN SHARED MEMORY: at pivot p the 12 x 13 entries are updated by all 32 lanes at once (five entries per
+// lane: entry (r, c) becomes A[p][c] / A[p][p] on the pivot row and A[r][c] - (A[r][p] / A[p][p]) A[p][c] elsewhere), so a
+// pivot step is one reciprocal, ~15 shared loads, 10 FMAs and 5 stores per lane, and no back-substitution is needed.
+// (Round 1 kept row r in 13 registers of lane r and broadcast the pivot row with 13 fp64 shuffles per step: ~3.5k
+// instructions on one warp per solve — the serial tail of every ICP iteration; this form is ~0.5k.)
+// The system is symmetric positive definite (JTJ/n plus the diagonal regularisers), for which elimination without pivoting
+// is backward stable; the result agrees with a pivoted LDL^T to ~1e-13 relative.
+static __device__ __forceinline__ void warp_ldlt_solve12(SolveScratch &S, int lane) {
+    if (lane < 12) S.A[lane][12] = S.b[lane];   // augmented column
+    int er[5], ec[5];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) row[j] = S.A[r][j];
-    row[12] = S.b[r];
-#pragma unroll
-    for (int p = 0; p < 12; ++p) {
-        const double pd = __shfl_sync(0xffffffffu, row[p], p);
-        const double inv = (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0;   // pseudo-inverse like Eigen's D
-        const double f = row[p] * inv;
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            const double pj = __shfl_sync(0xffffffffu, row[j], p);
-            if (lane == p)
-                row[j] = pj * inv;
-            else
-                row[j] -= f * pj;
-        }
+    for (int k = 0; k < 5; ++k) {
+        const int e = lane + 32 * k;            // 156 entries: rows of 13
+        er[k] = e < 156 ? e / 13 : 0;
+        ec[k] = e < 156 ? e % 13 : 0;
     }
-    if (lane < 12) S.x[lane] = row[12];
+    __syncwarp();
+#pragma unroll 1
+    for (int p = 0; p < 12; ++p) {
+        const double pd = S.A[p][p];
+        const double inv = (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0;   // pseudo-inverse like Eigen's D
+        double nv[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double arc = S.A[er[k]][ec[k]], arp = S.A[er[k]][p], apc = S.A[p][ec[k]];
+            const double f = arp * inv;
+            nv[k] = er[k] == p ? apc * inv : arc - f * apc;
+        }
+        __syncwarp();   // every lane has read the old matrix
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (lane + 32 * k < 156) S.A[er[k]][ec[k]] = nv[k];
+        __syncwarp();
+    }
+    if (lane < 12) S.x[lane] = S.A[lane][12];
     __syncwarp();
 }
 

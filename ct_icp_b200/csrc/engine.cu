@@ -81,13 +81,24 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
 
     // Odometry::Odometry, odometry.cpp:697-734: motion_compensation overrides the ICP parametrisation
     switch (options_.motion_compensation) {
-        case CTICP_MC_CONTINUOUS:
+        case CTICP_MC_NONE:
+        case CTICP_MC_CONSTANT_VELOCITY:   // ElasticICP does not compensate the motion
+            options_.ct_icp_options.point_to_plane_with_distortion = 0;
+            options_.ct_icp_options.distance = CTICP_DIST_POINT_TO_PLANE;
+            options_.ct_icp_options.parametrization = CTICP_PARAM_SIMPLE;
+            break;
+        case CTICP_MC_ITERATIVE:           // … compensates the motion at each ICP iteration
+            options_.ct_icp_options.point_to_plane_with_distortion = 1;
+            options_.ct_icp_options.distance = CTICP_DIST_POINT_TO_PLANE;
+            options_.ct_icp_options.parametrization = CTICP_PARAM_SIMPLE;
+            break;
+        case CTICP_MC_CONTINUOUS:          // … compensates continuously the motion
             options_.ct_icp_options.point_to_plane_with_distortion = 1;
             options_.ct_icp_options.parametrization = CTICP_PARAM_CONTINUOUS_TIME;
             options_.ct_icp_options.distance = CTICP_DIST_POINT_TO_PLANE;
             break;
         default:
-            throw UnsupportedError("motion_compensation other than CONTINUOUS is outside the built hot path (SURVEY §8)");
+            throw std::invalid_argument("unknown motion_compensation");
     }
     if (options_.sampling == CTICP_SAMPLING_ADAPTIVE && options_.adaptive_options.num_points_per_voxel != 1)
         throw UnsupportedError("sampling ADAPTIVE: only num_points_per_voxel == 1 is built");
@@ -252,8 +263,12 @@ void Engine::InitializeMotion(const FrameInfo &info, const cticp_frame *initial_
         return;
     }
     if (cv) {
-        // CONTINUOUS: extrapolate the begin pose from the previous begin poses (:311-317)
-        T[k].begin_pose.pose = se3_mul(se3_mul(T[k - 1].begin_pose.pose, se3_inverse(T[k - 2].begin_pose.pose)), T[k - 1].begin_pose.pose);
+        // CONTINUOUS: extrapolate the begin pose from the previous begin poses (:311-317); otherwise the new begin pose and
+        // the previous end pose are made consistent (:318-321)
+        if (options_.motion_compensation == CTICP_MC_CONTINUOUS)
+            T[k].begin_pose.pose = se3_mul(se3_mul(T[k - 1].begin_pose.pose, se3_inverse(T[k - 2].begin_pose.pose)), T[k - 1].begin_pose.pose);
+        else
+            T[k].begin_pose.pose = T[k - 1].end_pose.pose;
         T[k].end_pose.pose = se3_mul(se3_mul(T[k - 1].end_pose.pose, se3_inverse(T[k - 2].end_pose.pose)), T[k - 1].end_pose.pose);
     } else {
         T[k].begin_pose.pose = T[k - 1].end_pose.pose;
@@ -289,7 +304,10 @@ void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t sta
     // no truncation): both selections then run in ONE cooperative launch instead of six kernels and four memsets
     keypoints_sampled_ = false;
     const bool at_startup = k < options_.init_num_frames;
-    if (fused_sampling_ && k > 0 && !options_.robust_registration && options_.sampling == CTICP_SAMPLING_GRID &&
+    // motion compensation CONSTANT_VELOCITY moves the raw points of the sub-sampled frame into the end pose's frame before
+    // anything samples from it (DistortFrame, odometry.cpp:161-168,364-369)
+    const bool distort = k > 1 && options_.motion_compensation == CTICP_MC_CONSTANT_VELOCITY;
+    if (fused_sampling_ && !distort && k > 0 && !options_.robust_registration && options_.sampling == CTICP_SAMPLING_GRID &&
         (at_startup || options_.max_num_keypoints <= 0)) {
         const double kp_size = at_startup ? options_.init_sample_voxel_size : options_.sample_voxel_size;
         pipe_->SampleFused(sample_size, kp_size, options_.shuffle_seed, ShuffleCounter(k, 0), ShuffleCounter(k, 1),
@@ -299,6 +317,8 @@ void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t sta
     }
     pipe_->SubSampleFrame(sample_size, options_.shuffle_seed, ShuffleCounter(k, 0), ShuffleCounter(k, 1),
                           override_alpha, alpha_value);
+    if (distort)
+        pipe_->DistortFrame(tr.begin_pose.pose.q, tr.begin_pose.pose.t, tr.end_pose.pose.q, tr.end_pose.pose.t);
 }
 
 // Host team of the O(N) passes: half of the machine shared by the ranks of this node, 2..16 threads (measured on

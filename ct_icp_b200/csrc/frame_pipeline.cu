@@ -331,6 +331,21 @@ __global__ void k_transform_points(const float4 *__restrict__ pts, const int *__
     }
 }
 
+// DistortFrame (odometry.cpp:161-168): raw <- end^-1 * (Interpolate(begin, end, t) * raw), in place (alpha kept)
+__global__ void k_distort_frame(float4 *__restrict__ pts, const int *__restrict__ d_n, Q4 qb, V3 tb, Q4 qe, V3 te,
+                                SlerpConsts sc) {
+    const int n = *d_n;
+    const Q4 qi = qinverse(qe);
+    const V3 ti = (-1.0) * qrot(qnormalized(qi), te);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pts[i];
+        const V3 w = ct_transform_c(qb, tb, qe, te, (double) p.w, V3{(double) p.x, (double) p.y, (double) p.z}, sc);
+        const V3 r = qrot(qnormalized(qi), w) + ti;
+        p.x = (float) r.x; p.y = (float) r.y; p.z = (float) r.z;
+        pts[i] = p;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 static uint32_t NextPow2(uint64_t v) {
     uint64_t p = 1;
@@ -527,6 +542,12 @@ void FramePipeline::SampleKeypoints(int sampling, double sample_voxel_size, int 
 
 void FramePipeline::QueueCountsReadback() {
     CT_CUDA_CHECK(cudaMemcpyAsync(h_counts_, d_counts_, sizeof(int) * 4, cudaMemcpyDeviceToHost, stream_));
+}
+
+void FramePipeline::DistortFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te) {
+    k_distort_frame<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_counts_ + 1, qb, tb, qe, te, slerp_consts(qb, qe));
+    launches_ += 1;
+    CT_CUDA_CHECK(cudaGetLastError());
 }
 
 void FramePipeline::TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te) {

@@ -39,6 +39,8 @@ public:
     // AdaptiveSamplePointsInGrid (include/ct_icp/algorithm/sampling.h:55-110)
     void AdaptiveSelect(const cticp_adaptive_options &o, const float4 *in, const uint32_t *in_src, const int *d_n_in,
                         size_t n_upper, float4 *out, uint32_t *out_src, int *d_n_out);
+    // DistortFrame (odometry.cpp:161-168) on the sub-sampled frame, in place
+    void DistortFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
     // world points of the sub-sampled frame / of every input point with the final pose pair
     void TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
     // (stream: nullptr = the pipeline's own; the egress of the summary vectors runs on a second stream)

@@ -65,6 +65,9 @@ struct GnParams {
     int shard_rank, shard_world;   // keypoint sharding (multi-GPU); 0/1 when single
     int debug_flags;               // profiling only (env CTICP_DEBUG_FLAGS): 1 = skip the solve, 2 = skip the gather work
     double bucket_scale;           // 32 / radius^2: d2 → histogram bucket of the k-nearest selection (gather_select.cuh)
+    int rigid_first;               // motion compensation NONE / CONSTANT_VELOCITY: the keypoints enter the first iteration
+                                   // transformed by the END pose alone (TransformPoint, odometry.cpp:171-184), afterwards GN
+                                   // interpolates like always (ct_icp.cpp:964-966)
 };
 
 class IcpSolver {

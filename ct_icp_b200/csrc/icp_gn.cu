@@ -189,7 +189,7 @@ struct __align__(16) TileScratch {
 __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const int *stencil,
                                                 const float4 *__restrict__ keypoints, int lo, int hi, int warp_global,
                                                 int warps_total, const GnPose &pose, TileScratch &T, int lane,
-                                                GnWarpAcc &A, void *bulk = nullptr) {
+                                                GnWarpAcc &A, void *bulk = nullptr, bool rigid = false) {
     const GatherConfig &G = cfg.G;
     const GnParams &P = cfg.P;
     const int span = hi - lo;
@@ -208,8 +208,9 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
         int kx = 0, ky = 0, kz = 0;
         if (lane < wt) {
             const float4 kraw = __ldg(keypoints + t0 + lane);   // raw xyz (sensor frame) + alpha timestamp
-            p = ct_transform_c(pose.qb, pose.tb, pose.qe, pose.te, (double) kraw.w,
-                               V3{(double) kraw.x, (double) kraw.y, (double) kraw.z}, pose.sc);
+            const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+            p = rigid ? qrot(qnormalized(pose.qe), raw) + pose.te
+                      : ct_transform_c(pose.qb, pose.tb, pose.qe, pose.te, (double) kraw.w, raw, pose.sc);
             kx = voxel_coord(p.x, G.L.res);
             ky = voxel_coord(p.y, G.L.res);
             kz = voxel_coord(p.z, G.L.res);
@@ -404,7 +405,7 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
         const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
         const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
         gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gridDim.x + blockIdx.x, gridDim.x * kGatherWarps, pose,
-                        sh.tile[w], lane, A, bulk_ptr);
+                        sh.tile[w], lane, A, bulk_ptr, P.rigid_first && __ldcg(&st->iter) == 0);
     }
     // block reduction (fixed order → run-to-run deterministic)
     gn_store_warp_row(sh.acc[w], A, lane);
@@ -504,7 +505,7 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
                 // warp index interleaved over the CTAs: a keypoint set smaller than the grid spreads over all SMs
                 gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gather_ctas + (blockIdx.x - 1),
-                                gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A, bulk_ptr);
+                                gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A, bulk_ptr, P.rigid_first && it == 0);
             }
             gn_store_warp_row(sh.acc[w], A, lane);
             __syncthreads();
@@ -729,6 +730,7 @@ GnParams IcpSolver::MakeParams(const DeviceMap &map, const cticp_icp_options &op
     P.debug_flags = 0;
     if (const char *e = getenv("CTICP_DEBUG_FLAGS")) P.debug_flags = atoi(e);
     P.bucket_scale = (double) kSelBuckets / (P.radius * P.radius);
+    P.rigid_first = (opt.parametrization == CTICP_PARAM_SIMPLE && !opt.point_to_plane_with_distortion) ? 1 : 0;
     return P;
 }
 static int GatherBlocks(size_t k_hint, int num_sms, int kp_per_cta) {

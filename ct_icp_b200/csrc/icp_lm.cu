@@ -51,6 +51,9 @@ struct LmParams {
     LossParams loss;
     int ls_max_num_iters;
     int shard_rank, shard_world;
+    // POSE_PARAMETRIZATION SIMPLE (motion compensation NONE / CONSTANT_VELOCITY / ITERATIVE, odometry.cpp:704-724): only the
+    // end pose is optimised; `distortion` = point_to_plane_with_distortion (ITERATIVE)
+    int simple, distortion;
     // solver ROBUST (ct_icp.cpp:1180-1370)
     int robust, use_lines, use_barycenter;
     double threshold_linearity, threshold_planarity, outlier_distance, weight_neighborhood;
@@ -141,7 +144,11 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
         if (lane < wt) {
             kraw = __ldg(keypoints + t0 + lane);
             const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
-            p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, raw, sc);
+            // transform_keypoints (:516-531): interpolated pose unless SIMPLE without distortion (then the end pose)
+            if (P.simple && !P.distortion)
+                p = qrot(qnormalized(qe), raw) + te;
+            else
+                p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, raw, sc);
             double res = G0.L.res;
             if (kDB) {
                 const double range = sqrt(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z);
@@ -200,11 +207,17 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
                 rb.normal[0] = nd.normal.x; rb.normal[1] = nd.normal.y; rb.normal[2] = nd.normal.z;
                 rb.weight = weight;
                 rb.alpha = (double) kraw.w;
-                rb.raw[0] = kraw.x; rb.raw[1] = kraw.y; rb.raw[2] = kraw.z;
+                V3 rawc{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+                if (P.simple && P.distortion) {
+                    // ICPOptimizationBuilder::DistortFrame (:198-215): the raw point in the frame of the END pose
+                    const V3 w = ct_transform_c(qb, tb, qe, te, (double) kraw.w, rawc, sc);
+                    const Q4 qi = qinverse(qe);
+                    rawc = qrot(qi, w) + (-1.0) * qrot(qi, te);
+                }
+                rb.raw[0] = rawc.x; rb.raw[1] = rawc.y; rb.raw[2] = rawc.z;
                 rb.valid = 1;
                 for (int i = 0; i < 6; ++i) rb.info[i] = 0.0;
-                rb.kind = kResPlane;
-                rb._pad = 0;
+                rb.kind = kResPlane | (P.simple ? kResSimple : 0);
                 blocks[kp] = rb;
             } else {
                 blocks[kp].valid = 0;
@@ -328,7 +341,6 @@ __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmPara
                     rb.raw[0] = kraw.x; rb.raw[1] = kraw.y; rb.raw[2] = kraw.z;
                     rb.valid = 1;
                     rb.kind = kind;
-                    rb._pad = 0;
                     if (kind == kResDistribution) {
                         // (covariance + 0.05 I).inverse(), cost_functions.h:147-158 (Eigen's cofactor inverse)
                         const double m00 = nd.cov[0] + 0.05, m01 = nd.cov[1], m02 = nd.cov[2], m11 = nd.cov[3] + 0.05,
@@ -645,9 +657,11 @@ __device__ void lm_plus(const double *x, const double *delta, double *out) {
     for (int k = 0; k < 3; ++k) out[8 + k] = x[8 + k] + delta[6 + k];
     for (int k = 0; k < 3; ++k) out[11 + k] = x[11 + k] + delta[9 + k];
 }
-__device__ double norm14(const double *v) {
+// norm over the problem's parameter blocks: all 14 numbers, or end_quat + end_t with parametrization SIMPLE
+__device__ double norm14(const double *v, int simple = 0) {
     double s = 0;
-    for (int i = 0; i < 14; ++i) s += v[i] * v[i];
+    for (int i = 0; i < 14; ++i)
+        if (!simple || (i >= 4 && i < 8) || i >= 11) s += v[i] * v[i];
     return sqrt(s);
 }
 
@@ -676,7 +690,8 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
     __syncwarp();
     if (lane == 0) {
         S.cost = S.acc[kAccCost];
-        add_regularisers(st, R, phase == 0 ? lm->x : lm->cand, S.U, S.gu, S.cost);
+        if (!P.simple)   // AddConstraintsToCeresProblem only with CONTINUOUS_TIME (ct_icp.cpp:613)
+            add_regularisers(st, R, phase == 0 ? lm->x : lm->cand, S.U, S.gu, S.cost);
         S.flag = 0;
     }
     __syncwarp();
@@ -704,7 +719,7 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
     if (phase == 0) {
         adopt(true);
         if (lane == 0) {
-            lm->x_norm = norm14(lm->x);
+            lm->x_norm = norm14(lm->x, P.simple);
             lm->step_is_successful = 1;
         }
         __syncwarp();
@@ -753,7 +768,7 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
             __syncwarp();
             adopt(false);
             if (lane == 0) {
-                lm->x_norm = norm14(lm->x);
+                lm->x_norm = norm14(lm->x, P.simple);
                 lm->step_is_successful = 1;
             }
             __syncwarp();
@@ -1160,8 +1175,6 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
                              const float4 *d_keypoints, const int *d_num_keypoints, size_t k_hint, size_t k_capacity,
                              IcpState *d_state, int shard_rank, int shard_world, void *nccl_comm) {
     const bool robust = opt.solver == CTICP_SOLVER_ROBUST;
-    if (opt.parametrization != CTICP_PARAM_CONTINUOUS_TIME)
-        throw UnsupportedError("solvers CERES / ROBUST: only the CONTINUOUS_TIME parametrization is built (SURVEY §8)");
     if (!robust && opt.distance != CTICP_DIST_POINT_TO_PLANE)
         throw UnsupportedError("solver CERES: only POINT_TO_PLANE is built (SURVEY §8)");
     if (!robust && opt.num_closest_neighbors != 1)
@@ -1198,6 +1211,9 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     P.shard_world = sharded ? shard_world : 1;
     if (sharded && shard_world > kAcc) throw std::invalid_argument("sharding: world size above 96");
     P.robust = robust ? 1 : 0;
+    // solver ROBUST ignores the parametrization (DoRegisterRobust is CONTINUOUS_TIME only, ct_icp.cpp:1180-1370)
+    P.simple = (!robust && opt.parametrization == CTICP_PARAM_SIMPLE) ? 1 : 0;
+    P.distortion = opt.point_to_plane_with_distortion ? 1 : 0;
     P.use_lines = opt.use_lines;
     P.use_barycenter = opt.use_barycenter;
     P.threshold_linearity = opt.threshold_linearity;

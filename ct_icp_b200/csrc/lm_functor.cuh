@@ -84,17 +84,17 @@ CT_HD Q4 quat_plus(Q4 q, double dx, double dy, double dz) {
 }
 
 enum { kResPlane = 0, kResLine = 1, kResDistribution = 2 };
+constexpr int kResSimple = 16;   // flag in ResidualBlock::kind: POSE_PARAMETRIZATION SIMPLE — the inner functor on the END pose alone
 
 struct ResidualBlock {   // CTFunctor<FunctorT> state for one keypoint
     double ref[3];       // world_reference_ (the neighbor / barycenter the residual is anchored on)
     double normal[3];    // reference_normal_ (plane) or direction_ (line, not normalised)
     double weight;
     double alpha;
-    float raw[3];        // raw_point_ (sensor frame)
-    int valid;
+    double raw[3];       // raw_point_ (sensor frame; with parametrization SIMPLE + distortion: moved into the end pose's frame)
     double info[6];      // FunctorPointToDistribution::neighborhood_information_ (xx xy xz yy yz zz); solver ROBUST only
-    int kind;            // kResPlane / kResLine / kResDistribution (solver CERES: always plane)
-    int _pad;
+    int valid;
+    int kind;            // kResPlane / kResLine / kResDistribution (solver CERES: always plane) [| kResSimple]
 };
 
 // Residual and its derivative along tangent direction `dir` (0..11; >= 12 → value only).
@@ -110,14 +110,24 @@ __device__ __forceinline__ Dual ct_residual(const ResidualBlock &rb, const doubl
     const DQuat Qb{{qb[0], sb[0]}, {qb[1], sb[1]}, {qb[2], sb[2]}, {qb[3], sb[3]}};
     const DQuat Qe{{qe[0], se[0]}, {qe[1], se[1]}, {qe[2], se[2]}, {qe[3], se[3]}};
     const double alpha = rb.alpha, alpha_m = 1.0 - rb.alpha;
-    DQuat qi = dq_slerp(dq_normalized(Qb), dq_normalized(Qe), alpha);   // cost_functions.h:208-209
-    qi = dq_normalized(qi);                                              // :210
-    const Dual tx = alpha_m * mkd(tb[0], stb[0]) + alpha * mkd(te[0], ste[0]);
-    const Dual ty = alpha_m * mkd(tb[1], stb[1]) + alpha * mkd(te[1], ste[1]);
-    const Dual tz = alpha_m * mkd(tb[2], stb[2]) + alpha * mkd(te[2], ste[2]);
+    DQuat qi;
+    Dual tx, ty, tz;
+    if (rb.kind & kResSimple) {
+        // parametrization SIMPLE (ct_icp.cpp:314-321, 352-358): FunctorPointToPlane on the end pose's blocks; the tangent
+        // directions of the begin pose see a constant (derivative 0)
+        qi = Qe;
+        tx = mkd(te[0], ste[0]); ty = mkd(te[1], ste[1]); tz = mkd(te[2], ste[2]);
+    } else {
+        qi = dq_slerp(dq_normalized(Qb), dq_normalized(Qe), alpha);   // cost_functions.h:208-209
+        qi = dq_normalized(qi);                                        // :210
+        tx = alpha_m * mkd(tb[0], stb[0]) + alpha * mkd(te[0], ste[0]);
+        ty = alpha_m * mkd(tb[1], stb[1]) + alpha * mkd(te[1], ste[1]);
+        tz = alpha_m * mkd(tb[2], stb[2]) + alpha * mkd(te[2], ste[2]);
+    }
     // FunctorPointToPlane / FunctorPointToDistribution: quat.normalized() (cost_functions.h:47-51, 163-167);
     // FunctorPointToLine rotates with the quaternion as is (:121-125)
-    const DQuat q = (kRobust && rb.kind == kResLine) ? qi : dq_normalized(qi);
+    const int kind = rb.kind & 15;
+    const DQuat q = (kRobust && kind == kResLine) ? qi : dq_normalized(qi);
     const Dual vx = mkd(rb.raw[0]), vy = mkd(rb.raw[1]), vz = mkd(rb.raw[2]);
     // Eigen _transformVector: uv = 2 (q.vec x v); v + w uv + q.vec x uv
     Dual uvx = q.y * vz - q.z * vy, uvy = q.z * vx - q.x * vz, uvz = q.x * vy - q.y * vx;
@@ -125,7 +135,7 @@ __device__ __forceinline__ Dual ct_residual(const ResidualBlock &rb, const doubl
     const Dual px = vx + q.w * uvx + (q.y * uvz - q.z * uvy) + tx;
     const Dual py = vy + q.w * uvy + (q.z * uvx - q.x * uvz) + ty;
     const Dual pz = vz + q.w * uvz + (q.x * uvy - q.y * uvx) + tz;
-    if (kRobust && rb.kind == kResLine) {   // cost_functions.h:127-129
+    if (kRobust && kind == kResLine) {   // cost_functions.h:127-129
         double ux = rb.normal[0], uy = rb.normal[1], uz = rb.normal[2];
         const double z = ux * ux + uy * uy + uz * uz;
         if (z > 0) { const double inv = 1.0 / sqrt(z); ux *= inv; uy *= inv; uz *= inv; }
@@ -133,7 +143,7 @@ __device__ __forceinline__ Dual ct_residual(const ResidualBlock &rb, const doubl
         const Dual cx = uy * dz - uz * dy, cy = uz * dx - ux * dz, cz = ux * dy - uy * dx;
         return rb.weight * dsqrt(cx * cx + cy * cy + cz * cz);
     }
-    if (kRobust && rb.kind == kResDistribution) {   // cost_functions.h:169-171 : w * diff^T M diff
+    if (kRobust && kind == kResDistribution) {   // cost_functions.h:169-171 : w * diff^T M diff
         const Dual dx = px - mkd(rb.ref[0]), dy = py - mkd(rb.ref[1]), dz = pz - mkd(rb.ref[2]);
         const Dual r0 = rb.info[0] * dx + rb.info[1] * dy + rb.info[2] * dz;
         const Dual r1 = rb.info[1] * dx + rb.info[3] * dy + rb.info[4] * dz;

@@ -95,6 +95,7 @@ struct ResidualBlock {   // CTFunctor<FunctorT> state, cost_functions.h:186-222
     double weight;
     int kind = CTICP_DIST_POINT_TO_PLANE;   // inner functor: POINT_TO_PLANE / POINT_TO_LINE / POINT_TO_DISTRIBUTION
     Mat3 information;                       // FunctorPointToDistribution::neighborhood_information_
+    bool simple = false;                    // POSE_PARAMETRIZATION SIMPLE: the inner functor on (end_quat, end_t) alone
 };
 
 // Eigen::Matrix3d::inverse() (compute_inverse_size3: cofactors, det from the first column)
@@ -121,10 +122,13 @@ inline double EvalCTResidual(const ResidualBlock &rb, const double *qb, const do
     Jet Te[3] = {Jet::Var(te[0], 11), Jet::Var(te[1], 12), Jet::Var(te[2], 13)};
 
     Jet alpha_m(1.0 - rb.alpha), alpha(rb.alpha);
-    JQuat qi = Qb.normalized().slerp(alpha, Qe.normalized());   // cost_functions.h:208-209
-    qi = qi.normalized();                                         // :210 quat_inter.normalize()
-    Jet tr[3];
-    for (int k = 0; k < 3; ++k) tr[k] = alpha_m * Tb[k] + alpha * Te[k];
+    JQuat qi = Qe;
+    Jet tr[3] = {Te[0], Te[1], Te[2]};
+    if (!rb.simple) {   // CTFunctor; with parametrization SIMPLE the functor sees the end pose's blocks directly
+        qi = Qb.normalized().slerp(alpha, Qe.normalized());   // cost_functions.h:208-209
+        qi = qi.normalized();                                   // :210 quat_inter.normalize()
+        for (int k = 0; k < 3; ++k) tr[k] = alpha_m * Tb[k] + alpha * Te[k];
+    }
 
     // FunctorPointToPlane / FunctorPointToDistribution: quat.normalized() * raw + t (cost_functions.h:47-51,163-167);
     // FunctorPointToLine: quat * raw + t (:121-125)
@@ -267,6 +271,7 @@ struct Problem {
     Vec3 prev_end_tr, prev_velocity;
     Quat prev_orientation;
     int num_threads = 1;
+    bool simple = false;   // parametrization SIMPLE: only end_quat / end_t are parameter blocks (ct_icp.cpp:234-237)
     explicit Problem(const cticp_icp_options &o) : loss(o) {}
 
     int NumRegResiduals() const { return (has_location ? 3 : 0) + (has_orientation ? 1 : 0) + (has_cv ? 3 : 0) + (has_small ? 3 : 0); }
@@ -383,7 +388,11 @@ SolveSummary SolveLM(const Problem &problem, double *parameters, int max_num_ite
     SolveSummary summary;
     double x[14], candidate_x[14];
     for (int i = 0; i < 14; ++i) x[i] = parameters[i];
-    auto norm14 = [](const double *v) { double s = 0; for (int i = 0; i < 14; ++i) s += v[i] * v[i]; return std::sqrt(s); };
+    // (parametrization SIMPLE: the problem's parameter vector is end_quat + end_t only; the begin blocks stay in x with
+    //  all-zero Jacobian columns, which decouple in the damped normal equations and get a zero step)
+    const bool simple = problem.simple;
+    auto is_active = [simple](int i) { return !simple || (i >= 4 && i < 8) || i >= 11; };
+    auto norm14 = [&](const double *v) { double s = 0; for (int i = 0; i < 14; ++i) if (is_active(i)) s += v[i] * v[i]; return std::sqrt(s); };
     double x_norm = norm14(x);
     double x_cost = 0, minimum_cost = std::numeric_limits<double>::max();
     std::vector<double> residuals, jacobian;
@@ -612,6 +621,7 @@ static int AssembleAndSolve(const cticp_icp_options &options, const std::vector<
                             ICPSummary &failed) {
     Problem problem(options);   // GetProblem, :409-424 : first max_num_residuals non-null functors
     problem.num_threads = num_threads;
+    problem.simple = options.parametrization == CTICP_PARAM_SIMPLE;
     number_of_residuals = 0;
     for (size_t i = 0; i < all_blocks.size(); ++i) {
         if (!has_block[i]) continue;
@@ -682,12 +692,13 @@ static int AssembleAndSolve(const cticp_icp_options &options, const std::vector<
     return (diff_rot < options.threshold_orientation_norm && diff_trans < options.threshold_translation_norm) ? 1 : 0;
 }
 
-// DoRegisterCeres, src/ct_icp/ct_icp.cpp:460-706 (CONTINUOUS_TIME + POINT_TO_PLANE)
+// DoRegisterCeres, src/ct_icp/ct_icp.cpp:460-706 (POINT_TO_PLANE; parametrizations CONTINUOUS_TIME and SIMPLE)
 ICPSummary DoRegisterCeres(const VoxelMap &map, const cticp_icp_options &options,
                            const cticp_strategy_options &strategy, std::vector<WPoint3D> &kpts,
                            TrajectoryFrame &frame, const MotionModel *motion_model) {
-    if (options.parametrization != CTICP_PARAM_CONTINUOUS_TIME || options.distance != CTICP_DIST_POINT_TO_PLANE)
-        throw std::runtime_error("oracle: only CONTINUOUS_TIME + POINT_TO_PLANE is restated for the CERES solver");
+    if (options.distance != CTICP_DIST_POINT_TO_PLANE)
+        throw std::runtime_error("oracle: only POINT_TO_PLANE is restated for the CERES solver");
+    const bool simple = options.parametrization == CTICP_PARAM_SIMPLE;
     ICPSummary icp_summary;
     const size_t num_points = kpts.size();
     frame.begin_pose.pose.quat.normalize();
@@ -698,8 +709,24 @@ ICPSummary DoRegisterCeres(const VoxelMap &map, const cticp_icp_options &options
     SE3 previous_begin_pose = frame.begin_pose.pose, previous_end_pose = frame.end_pose.pose;
     int number_of_residuals = 0;
 
+    // ICPOptimizationBuilder::corrected_raw_points_ (= the raw points) and DistortFrame (:198-215): with parametrization
+    // SIMPLE every raw point is moved into the coordinate frame of the END pose of the acquisition
+    std::vector<Vec3> corrected_raw(num_points);
+    for (size_t i = 0; i < num_points; ++i) corrected_raw[i] = kpts[i].raw;
+    auto distort_frame = [&]() {
+        if (!simple) return;
+        const SE3 end_pose_I = frame.end_pose.Inverse().pose;
+        for (size_t i = 0; i < num_points; ++i)
+            corrected_raw[i] = end_pose_I * (frame.begin_pose.InterpolatePose(frame.end_pose, kpts[i].timestamp) * kpts[i].raw);
+    };
+    if (options.point_to_plane_with_distortion) distort_frame();   // :512-514
     auto transform_keypoints = [&]() {   // :516-531
-        for (auto &kp : kpts) kp.world = frame.begin_pose.InterpolatePose(frame.end_pose, kp.timestamp) * kp.raw;
+        for (auto &kp : kpts) {
+            if (options.point_to_plane_with_distortion || !simple)
+                kp.world = frame.begin_pose.InterpolatePose(frame.end_pose, kp.timestamp) * kp.raw;
+            else
+                kp.world = frame.end_pose.pose * kp.raw;
+        }
     };
     double lambda_weight = std::abs(options.weight_alpha);
     double lambda_neighborhood = std::abs(options.weight_neighborhood);
@@ -740,7 +767,8 @@ ICPSummary DoRegisterCeres(const VoxelMap &map, const cticp_icp_options &options
                 ResidualBlock rb;
                 rb.alpha = alpha;
                 rb.reference = neighborhood.points[i];
-                rb.raw = pt.raw;
+                rb.raw = corrected_raw[k];   // SetResidualBlock reads corrected_raw_points_ (:381)
+                rb.simple = simple;
                 rb.normal = neighborhood.description.normal;
                 rb.weight = weight;
                 all_blocks[ncn * k + i] = rb;
@@ -758,6 +786,7 @@ ICPSummary DoRegisterCeres(const VoxelMap &map, const cticp_icp_options &options
             failed.stencil_points = icp_summary.stencil_points;
             return failed;
         }
+        if (options.point_to_plane_with_distortion) distort_frame();   // :657-659 (before the stop test's break)
         if (status == 1) break;
     }
     transform_keypoints();

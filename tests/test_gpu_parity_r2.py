@@ -232,3 +232,25 @@ def test_caller_motion_model_callbacks_and_reset_with_options(eng, seq_small):
     with pytest.raises(CticpError) as err:
         od.RegisterFrame(last["xyz"], last["t"] + 1.0, 99)
     assert err.value.code == abi.ERR_CALLBACK
+
+
+@pytest.mark.parametrize("mode", ["NONE", "CONSTANT_VELOCITY", "ITERATIVE"])
+@pytest.mark.parametrize("solver", ["CERES", "GN"])
+def test_motion_compensation_modes(orc, eng, seq_small, mode, solver):
+    """MOTION_COMPENSATION NONE / CONSTANT_VELOCITY / ITERATIVE (odometry.cpp:161-184,311-321,364-369,704-724): the pose
+    parametrization becomes SIMPLE — solver CERES optimises the end pose alone (ct_icp.cpp:234-237,314-321) on raw points
+    that ITERATIVE re-distorts into the end pose's frame every ICP iteration (:198-215,512-514,657-659); CONSTANT_VELOCITY
+    distorts the sub-sampled frame once (DistortFrame); GN enters with the end-pose transform of TransformPoint. The
+    distorted raw points of CONSTANT_VELOCITY are stored as fp32 on the device (<= 4e-6 m), hence the sample-size slack."""
+    mc = {"NONE": 0, "CONSTANT_VELOCITY": 1, "ITERATIVE": 2}[mode]
+    odo, ro = _run_sequence(orc, seq_small, solver, init_num_frames=4, motion_compensation=mc)
+    ode, re_ = _run_sequence(eng, seq_small, solver, init_num_frames=4, motion_compensation=mc)
+    exact = mode != "CONSTANT_VELOCITY"
+    wt, wr = _compare(ro, re_, exact_counts=exact)
+    if not exact:
+        for (so, _), (se, _) in zip(ro, re_):
+            assert abs(int(so.num_keypoints) - int(se.num_keypoints)) <= max(3, so.num_keypoints // 200)
+    # and the mode matters: the trajectory differs from the CONTINUOUS one
+    _, rc = _run_sequence(eng, seq_small, solver, init_num_frames=4)
+    assert frame_diff(rc[-1][0].frame, re_[-1][0].frame)[0] > 1e-6
+    print("motion compensation %s / %s: worst per-frame pose difference %.3e m, %.3e rad" % (mode, solver, wt, wr))

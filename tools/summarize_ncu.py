@@ -9,7 +9,8 @@ import csv
 import json
 import sys
 
-FRAME_FIRST_KERNEL = "k_grid_claim"      # first launch of a RegisterFrame step with device-resident input
+# first launch of a RegisterFrame step with device-resident input: round 2's fused sampler, else round 1's first grid pass
+FRAME_FIRST_KERNELS = ("k_sample_fused", "k_grid_claim")
 KEEP = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -36,7 +37,8 @@ def launches(src, dst):
     seq = [(r["Kernel Name"].split("(")[0], float(r["Metric Value"]) / 1e3, r["Grid Size"], r["Block Size"]) for r in rows]
     # the last frame = from the last but one... find the last occurrence of the first-of-frame kernel that is followed
     # by a complete frame (the frame sub-sampling launches k_grid_claim twice: frame grid, then keypoint grid)
-    starts = [i for i, s in enumerate(seq) if s[0] == FRAME_FIRST_KERNEL and (i == 0 or seq[i - 1][0] != "k_grid_emit")]
+    first = next(k for k in FRAME_FIRST_KERNELS if any(s[0] == k for s in seq))
+    starts = [i for i, s in enumerate(seq) if s[0] == first and (i == 0 or seq[i - 1][0] != "k_grid_emit")]
     begin = starts[-1]
     frame = seq[begin:]
     total = sum(s[1] for s in frame)

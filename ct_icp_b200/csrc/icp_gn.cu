@@ -733,14 +733,14 @@ GnParams IcpSolver::MakeParams(const DeviceMap &map, const cticp_icp_options &op
     P.rigid_first = (opt.parametrization == CTICP_PARAM_SIMPLE && !opt.point_to_plane_with_distortion) ? 1 : 0;
     return P;
 }
-static int GatherBlocks(size_t k_hint, int num_sms, int kp_per_cta) {
+static int GatherBlocks(size_t k_hint, int max_blocks, int kp_per_cta) {
     // One CTA (kGatherWarps warps, 128 registers per thread) per SM. A keypoint set smaller than the machine is spread
     // thin — `kp_per_cta` keypoints per CTA, so each keypoint's warp has an SM sub-partition nearly to itself: the loop
     // is latency-bound there — until every SM has a CTA; beyond that the tiles widen (gn_gather_tiles).
     // k_hint is an ESTIMATE of the keypoint count (the exact count lives on the device): too small only widens the
     // tiles, too large only adds idle CTAs whose zero partials have to be summed.
     size_t want = (k_hint + kp_per_cta - 1) / kp_per_cta;
-    return (int) std::max<size_t>(1, std::min(want, (size_t) num_sms));
+    return (int) std::max<size_t>(1, std::min(want, (size_t) max_blocks));
 }
 
 void IcpSolver::CollectGatherTiming() {
@@ -764,9 +764,8 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
     cfg.G.r = cfg.P.r;
     cfg.G.radius2 = cfg.P.radius * cfg.P.radius;
     cfg.G.kmax = cfg.P.kmax;
-    const int blocks = GatherBlocks((k_upper + shard_world - 1) / shard_world + 16, num_sms_, kp_per_cta_);
-    EnsurePartials(blocks + 1);
     const bool peers = nccl_comm && shard_world > 1 && peers_ready_;
+    const size_t k_share = (k_upper + shard_world - 1) / shard_world + 16;
     if (use_persistent_ && (!nccl_comm || peers)) {
         // one cooperative launch for the whole loop; the grid must be co-resident (grid-wide barriers)
         void *kernel = peers ? (void *) k_gn_persistent<true> : (void *) k_gn_persistent<false>;
@@ -776,6 +775,8 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
             CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGatherWarps * 32, sizeof(GnShared)));
             coresident = std::max(1, per_sm * num_sms_);
         }
+        const int blocks = GatherBlocks(k_share, std::max(1, coresident - 1), kp_per_cta_);
+        EnsurePartials(blocks + 1);
         int grid = std::min(blocks + 1, coresident);
         grid = std::max(grid, 2);
         const float4 *kp = d_keypoints;
@@ -792,6 +793,8 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         launches_ += 1;
         return;
     }
+    const int blocks = GatherBlocks(k_share, num_sms_, kp_per_cta_);
+    EnsurePartials(blocks + 1);
     for (int it = 0; it < num_iters; ++it) {
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);

@@ -7,11 +7,11 @@
 # Variants (name:flags). A variant's bench line only counts if its parity tests pass.
 #   bulk        -DCTICP_SEL_BULK            the stencil's point runs staged in shared memory by cp.async.bulk + mbarrier
 #                                           (UBLKCP / SYNCS: the north star's "TMA staging") instead of per-lane loads
-#   prefetch2/8 -DCTICP_SEL_PREFETCH=2 / 8  2 / 8 chunks of 32 point loads in flight per batch (default 4)
+#   prefetch2/6 -DCTICP_SEL_PREFETCH=2 / 6  2 / 6 chunks of 32 point loads in flight per batch (default 4)
 #   warps8      -DCTICP_GATHER_WARPS=8      8 warps per gather CTA (two CTAs per SM) instead of 16
 set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
-VARIANTS=("bulk:-DCTICP_SEL_BULK" "prefetch2:-DCTICP_SEL_PREFETCH=2" "prefetch8:-DCTICP_SEL_PREFETCH=8 -DCTICP_SEL_CAP=224"
+VARIANTS=("bulk:-DCTICP_SEL_BULK" "prefetch2:-DCTICP_SEL_PREFETCH=2" "prefetch6:-DCTICP_SEL_PREFETCH=6 -DCTICP_SEL_CAP=224"
           "warps8:-DCTICP_GATHER_WARPS=8")
 case "${1:-}" in
 build)

@@ -1,11 +1,17 @@
 #!/bin/bash
-# One GPU-box visit: the whole GPU test-suite (all failures reported), a bisection over the round-2 switches if anything
-# fails, then the bench lines. Logs under gpurun_out/.   usage (on the box): bash tools/gpu_check.sh <tag> [pytest|bench|all]
+# One GPU-box visit, in priority order (each step under its own timeout; logs under gpurun_out/):
+#   1. the whole GPU test-suite (all failures reported) + a bisection over the round-2 switches if anything fails
+#   2. the bench line (and one without the fused kernels if the tests failed)
+#   3. the profiling evidence (launch list + one --set full capture of the dominant kernel)         [all only]
+#   4. the A/B of the experiment builds (tools/ab_variants.sh)                                      [all only]
+#   5. compute-sanitizer memcheck / racecheck / synccheck                                           [all only]
+#   6. the bench line with the extra workloads and the CPU baselines                                [all only]
+# usage (on the box): bash tools/gpu_check.sh <tag> [pytest|bench|quick|all]
 TAG=${1:-x}; WHAT=${2:-all}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/${TAG}_gpu.txt 2>&1
 RC=0
-if [ "$WHAT" = "all" ] || [ "$WHAT" = "pytest" ]; then
+if [ "$WHAT" != "bench" ]; then
   timeout 1500 python -m pytest tests -m gpu -q -n 6 --tb=short -p no:cacheprovider > gpurun_out/${TAG}_pytest.log 2>&1
   RC=$?
   echo "rc=$RC" >> gpurun_out/${TAG}_pytest.log
@@ -21,11 +27,20 @@ if [ "$WHAT" = "all" ] || [ "$WHAT" = "pytest" ]; then
     done
   fi
 fi
-if [ "$WHAT" = "all" ] || [ "$WHAT" = "bench" ]; then
-  timeout 900 python bench.py --no-extras > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+if [ "$WHAT" != "pytest" ]; then
+  timeout 900 python bench.py --no-extras --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
   echo "bench rc=$?"; tail -5 gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench.json
   if [ $RC -ne 0 ]; then
     CTICP_FUSED_SAMPLING=0 CTICP_FUSED_MAP_UPDATE=0 timeout 900 python bench.py --no-extras --no-cpu-baseline > gpurun_out/${TAG}_bench_nofuse.json 2> gpurun_out/${TAG}_bench_nofuse.err
     echo "bench (no fused kernels) rc=$?"; tail -3 gpurun_out/${TAG}_bench_nofuse.err; cat gpurun_out/${TAG}_bench_nofuse.json
   fi
+fi
+if [ "$WHAT" = "all" ]; then
+  echo "---- profile"; bash tools/gpu_profile.sh ${TAG} kitti64_gn 2>&1 | tail -12
+  echo "---- A/B"; timeout 2400 bash tools/ab_variants.sh run gpurun_out/${TAG}_ab 2>&1 | tail -12
+  echo "---- sanitizer"; timeout 2400 bash tools/gpu_sanitize.sh ${TAG} 2>&1 | tail -12
+  echo "---- full bench"; timeout 1500 python bench.py > gpurun_out/${TAG}_bench_full.json 2> gpurun_out/${TAG}_bench_full.err
+  echo "full bench rc=$?"; tail -3 gpurun_out/${TAG}_bench_full.err; cat gpurun_out/${TAG}_bench_full.json
+  echo "---- reference arm"; timeout 900 python bench.py --impl reference --steps 20 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
+  cat gpurun_out/${TAG}_bench_reference.json | cut -c1-600
 fi

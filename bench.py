@@ -409,7 +409,7 @@ def run_native(eng, D, seq, preroll, W, K, n_roof, with_dropin=True, parity_fram
             sm = od.RegisterFrame(seq[i]["xyz"], seq[i]["t"], seq[i]["frame_idx"])
             assert sm.success, sm.error_message
             if dropin:
-                for w in range(3):
+                for w in (1, 2, 0):
                     od.points_into(w, bufs[w])
         od.last_timing()
         D.barrier()
@@ -422,8 +422,10 @@ def run_native(eng, D, seq, preroll, W, K, n_roof, with_dropin=True, parity_fram
                 D.barrier()                   # all ranks receive the scan at the same time (untimed)
             t0 = time.perf_counter()
             sm = od.RegisterFrame(seq[i]["xyz"], seq[i]["t"], seq[i]["frame_idx"])
-            if dropin:
-                counts = [od.points_into(w, bufs[w]) for w in range(3)]
+            if dropin:   # all_corrected_points first: it comes back in pieces, assembled while the rest is still copying
+                counts = [0, 0, 0]
+                for w in (1, 2, 0):
+                    counts[w] = od.points_into(w, bufs[w])
             t = od.last_timing()              # waits for the map-update tail of this frame
             ms_list.append((time.perf_counter() - t0) * 1e3)
             assert sm.success, sm.error_message

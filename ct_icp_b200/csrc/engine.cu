@@ -145,6 +145,8 @@ Engine::~Engine() {
     }
     if (ev_egress_main_) cudaEventDestroy(ev_egress_main_);
     if (ev_egress_done_) cudaEventDestroy(ev_egress_done_);
+    for (auto &e : ev_egress_chunk_)
+        if (e) cudaEventDestroy(e);
     if (egress_stream_) cudaStreamDestroy(egress_stream_);
     if (stream_) cudaStreamDestroy(stream_);
 }
@@ -179,6 +181,7 @@ void Engine::AllocEgress() {
         CT_CUDA_CHECK(cudaStreamCreateWithFlags(&egress_stream_, cudaStreamNonBlocking));
         CT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_egress_main_, cudaEventDisableTiming));
         CT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_egress_done_, cudaEventDisableTiming));
+        for (auto &e : ev_egress_chunk_) CT_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     const size_t cap = pipe_->MaxPoints();
     for (int i = 0; i < 3; ++i) {
@@ -202,7 +205,13 @@ void Engine::EnqueueEgress(const HostFrame &f, bool ran_icp) {
     cudaStream_t es = egress_stream_;
     if (summary_points_mask_ & (1 << CTICP_POINTS_ALL_CORRECTED)) {
         pipe_->TransformAll(qb, tb, qe, te, es);
-        CT_CUDA_CHECK(cudaMemcpyAsync(h_world_[1], pipe_->d_all_world(), sizeof(double) * 3 * n_all, cudaMemcpyDeviceToHost, es));
+        for (int c = 0; c < kEgressChunks; ++c) {
+            const size_t b = n_all * (size_t) c / kEgressChunks, e = n_all * (size_t) (c + 1) / kEgressChunks;
+            if (e > b)
+                CT_CUDA_CHECK(cudaMemcpyAsync(h_world_[1] + 3 * b, pipe_->d_all_world() + 3 * b, sizeof(double) * 3 * (e - b),
+                                              cudaMemcpyDeviceToHost, es));
+            CT_CUDA_CHECK(cudaEventRecord(ev_egress_chunk_[c], es));
+        }
         last_all_world_valid_ = true;
         egress_valid_[1] = true;
         egress_count_[1] = n_all;
@@ -1154,7 +1163,8 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
         const size_t count = egress_count_[which];
         const size_t m = std::min(cap, count);
         if (m == 0 || !dst) return (int64_t) count;
-        CT_CUDA_CHECK(cudaEventSynchronize(ev_egress_done_));
+        const bool chunked = which == CTICP_POINTS_ALL_CORRECTED;   // copied first and in pieces (EnqueueEgress)
+        if (!chunked) CT_CUDA_CHECK(cudaEventSynchronize(ev_egress_done_));
         const auto &f = last_frame_;
         const double bts = f.begin_pose.dest_timestamp, ets = f.end_pose.dest_timestamp;
         const double mn = std::min(bts, ets), mx = std::max(bts, ets);
@@ -1165,8 +1175,14 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
         const bool override_t = src && last_info_.registered_fid <= 1;
         const double t_override = mn + (double) (float) AlphaTimestamp(last_info_.end_timestamp, bts, ets) * (mx - mn);
         const uint32_t frame_id = last_info_.frame_id;
-        pool_->ParallelFor(m, [&](size_t b, size_t e, int) {
-            for (size_t i = b; i < e; ++i) {
+        const int pieces = chunked ? kEgressChunks : 1;
+        for (int c = 0; c < pieces; ++c) {
+        const size_t pb = chunked ? count * (size_t) c / kEgressChunks : 0;
+        const size_t pe = std::min(m, chunked ? count * (size_t) (c + 1) / kEgressChunks : m);
+        if (chunked) CT_CUDA_CHECK(cudaEventSynchronize(ev_egress_chunk_[c]));
+        if (pe <= pb) continue;
+        pool_->ParallelFor(pe - pb, [&](size_t b0, size_t e0, int) {
+            for (size_t i = pb + b0; i < pb + e0; ++i) {
                 const float4 p = stage[src ? src[i] : i];
                 cticp_wpoint &o = dst[i];
                 o.raw[0] = p.x; o.raw[1] = p.y; o.raw[2] = p.z;
@@ -1176,6 +1192,7 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
                 o._pad0 = 0;
             }
         });
+        }
         return (int64_t) count;
     }
     const float4 *d_pts = nullptr;

@@ -217,6 +217,8 @@ private:
     int summary_points_mask_ = 0;
     cudaStream_t egress_stream_ = nullptr;
     cudaEvent_t ev_egress_main_ = nullptr, ev_egress_done_ = nullptr;
+    static constexpr int kEgressChunks = 4;            // the N world points go back in pieces: the host assembles the
+    cudaEvent_t ev_egress_chunk_[kEgressChunks] = {};  // records of piece i while piece i + 1 is still on the bus
     bool egress_pending_ = false;           // ev_egress_done_ recorded, next frame's upload must wait for it
     bool egress_valid_[3] = {false, false, false};
     size_t egress_count_[3] = {0, 0, 0};

@@ -407,9 +407,10 @@ private:
         r.icp_summary.avg_duration_iter = s.icp_summary.avg_duration_iter;
         r.icp_summary.avg_duration_neighborhood = s.icp_summary.avg_duration_neighborhood;
         r.icp_summary.avg_duration_solve = s.icp_summary.avg_duration_solve;
-        if (copy_back.corrected_points) Fetch(CTICP_POINTS_CORRECTED, s.num_corrected_points, r.corrected_points);
+        // (all_corrected_points first: the engine sends it back first and in pieces, assembled while the rest is copying)
         if (copy_back.all_corrected_points) Fetch(CTICP_POINTS_ALL_CORRECTED, s.num_all_corrected_points, r.all_corrected_points);
         if (copy_back.keypoints) Fetch(CTICP_POINTS_KEYPOINTS, s.num_keypoints, r.keypoints);
+        if (copy_back.corrected_points) Fetch(CTICP_POINTS_CORRECTED, s.num_corrected_points, r.corrected_points);
         // keys the ROS monitor consumes verbatim (ct_icp_odometry_node.cxx:279-287; odometry.cpp:495-513)
         r.logged_values["odometry_total"] = s.odometry_total;                              // :210
         r.logged_values["odometry_initialization"] = s.odometry_initialization;           // :211

@@ -4,6 +4,8 @@
     python tools/summarize_ncu.py full <raw.csv> <out.json> [kernel ...]  # selected metrics of a --set full capture
                                                                           # (raw.csv = `ncu -i x.ncu-rep --page raw --csv`)
     python tools/summarize_ncu.py source <src.csv> <out.json>             # stall samples (`--page source --csv`)
+    python tools/summarize_ncu.py digest <raw.csv> <src.csv> <out.json> <kernel> [keypoint_iterations]
+                                                                          # the one-file summary bench.py reads `traffic` from
 """
 import csv
 import json
@@ -101,8 +103,46 @@ def source(src, dst, top=12):
         print("%5d %5.1f%% %-18s %s" % (h["samples"], 100 * h["share"], h["top_reason"], h["sass"][:70]))
 
 
+def digest(raw, src, dst, kernel, kp_iters=None):
+    """One JSON per capture: duration, DRAM bytes per launch (= `traffic` of the bench line), instructions (and per
+    keypoint-iteration when given), occupancy / issue / cache metrics, stall shares."""
+    import os
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    full(raw, os.path.join(tmp, "full.json"), [kernel])
+    f = json.load(open(os.path.join(tmp, "full.json")))
+    name = next(iter(f))
+    m = f[name][0]["metrics"]
+
+    def val(key):
+        try:
+            return float(str(m[key]["value"]).replace(",", ""))
+        except Exception:
+            return None
+    out = {"kernel": name, "grid": f[name][0]["grid"], "block": f[name][0]["block"],
+           "duration_us": (val("gpu__time_duration.sum") or 0) / 1e3,
+           "dram_bytes_per_launch": (val("dram__bytes_read.sum") or 0) + (val("dram__bytes_write.sum") or 0),
+           "metrics": {k: v["value"] + (" " + v["unit"] if v["unit"] else "") for k, v in m.items()}}
+    insts = val("smsp__inst_executed.sum") or val("sm__inst_executed.sum")
+    if insts:
+        out["warp_instructions"] = insts
+        if kp_iters:
+            out["keypoint_iterations"] = kp_iters
+            out["warp_instructions_per_keypoint_iteration"] = insts / kp_iters
+    if src and os.path.exists(src):
+        source(src, os.path.join(tmp, "src.json"))
+        sj = json.load(open(os.path.join(tmp, "src.json")))
+        out["stall_share"] = sj["share_by_stall_reason"]
+        out["sass_instructions"] = sj["sass_instructions"]
+        out["hottest_instructions"] = sj["hottest_instructions"][:8]
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps({k: v for k, v in out.items() if k not in ("metrics", "hottest_instructions")}, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "digest":
+        digest(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], float(sys.argv[6]) if len(sys.argv) > 6 else None)
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     elif sys.argv[1] == "source":
         source(sys.argv[2], sys.argv[3])

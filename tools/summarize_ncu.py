@@ -114,13 +114,16 @@ def digest(raw, src, dst, kernel, kp_iters=None):
     name = next(iter(f))
     m = f[name][0]["metrics"]
 
-    def val(key):
+    SCALE = {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6,
+             "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def val(key):   # value in us / bytes / plain number (ncu prints scaled units in the raw page)
         try:
-            return float(str(m[key]["value"]).replace(",", ""))
+            return float(str(m[key]["value"]).replace(",", "")) * SCALE.get(m[key]["unit"], 1.0)
         except Exception:
             return None
     out = {"kernel": name, "grid": f[name][0]["grid"], "block": f[name][0]["block"],
-           "duration_us": (val("gpu__time_duration.sum") or 0) / 1e3,
+           "duration_us": val("gpu__time_duration.sum") or 0,
            "dram_bytes_per_launch": (val("dram__bytes_read.sum") or 0) + (val("dram__bytes_write.sum") or 0),
            "metrics": {k: v["value"] + (" " + v["unit"] if v["unit"] else "") for k, v in m.items()}}
     insts = val("smsp__inst_executed.sum") or val("sm__inst_executed.sum")

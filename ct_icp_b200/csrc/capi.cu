@@ -645,10 +645,14 @@ double AlphaOf(double t, double bts, double ets) {
 }
 struct DeviceKeypoints {
     float4 *d_kp = nullptr;
+    float4 *d_lo = nullptr;   // residual plane (se3.cuh load_raw); has_lo: some coordinate is not float32-representable
+    bool has_lo = false;
     int *d_n = nullptr;
     IcpState *d_state = nullptr;
+    const float4 *lo() const { return has_lo ? d_lo : nullptr; }
     ~DeviceKeypoints() {
         cudaFree(d_kp);
+        cudaFree(d_lo);
         cudaFree(d_n);
         cudaFree(d_state);
     }
@@ -657,14 +661,19 @@ void UploadRegistrationInputs(cticp_map *m, const cticp_wpoint *keypoints, size_
                               const cticp_frame *previous_frame, const cticp_motion_model_options *mo,
                               DeviceKeypoints &D, IcpState &S) {
     const double bts = frame->begin_pose.dest_timestamp, ets = frame->end_pose.dest_timestamp;
-    std::vector<float4> kp(n);
+    std::vector<float4> kp(n), lo(n);
     for (size_t i = 0; i < n; ++i) {
         const double t = keypoints[i].timestamp;
         if (!(bts <= t && t <= ets)) throw TimestampError("The timestamp cannot be interpolated between the two poses");
-        kp[i] = make_float4((float) keypoints[i].raw[0], (float) keypoints[i].raw[1], (float) keypoints[i].raw[2],
-                            (float) AlphaOf(t, bts, ets));
+        const double v[4] = {keypoints[i].raw[0], keypoints[i].raw[1], keypoints[i].raw[2], AlphaOf(t, bts, ets)};
+        kp[i] = make_float4((float) v[0], (float) v[1], (float) v[2], (float) v[3]);
+        lo[i] = make_float4((float) (v[0] - (double) kp[i].x), (float) (v[1] - (double) kp[i].y),
+                            (float) (v[2] - (double) kp[i].z), (float) (v[3] - (double) kp[i].w));
+        if (lo[i].x != 0.f || lo[i].y != 0.f || lo[i].z != 0.f || lo[i].w != 0.f) D.has_lo = true;
     }
     CAPI_CUDA(cudaMalloc(&D.d_kp, sizeof(float4) * std::max<size_t>(n, 1)));
+    CAPI_CUDA(cudaMalloc(&D.d_lo, sizeof(float4) * std::max<size_t>(n, 1)));
+    CAPI_CUDA(cudaMemcpyAsync(D.d_lo, lo.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, m->stream));
     CAPI_CUDA(cudaMalloc(&D.d_n, sizeof(int)));
     CAPI_CUDA(cudaMalloc(&D.d_state, sizeof(IcpState)));
     const int ni = (int) n;
@@ -708,6 +717,7 @@ int cticp_icp_register(cticp_map *m, const cticp_icp_options *options, const cti
         UploadRegistrationInputs(m, keypoints, n, frame, previous_frame, motion_options, D, S);
         cticp_strategy_options st{0, 20, 8, 0, 60., 0.1, 2.0, 1.0};
         if (strategy) st = *strategy;
+        m->icp->set_keypoints_lo(D.lo());
         switch (options->solver) {
             case CTICP_SOLVER_GN:
                 m->icp->EnqueueGaussNewton(*m->map, *options, D.d_kp, D.d_n, n, options->num_iters_icp, D.d_state);
@@ -734,9 +744,8 @@ int cticp_icp_register(cticp_map *m, const cticp_icp_options *options, const cti
         const V3 tb{S.tb[0], S.tb[1], S.tb[2]}, te{S.te[0], S.te[1], S.te[2]};
         const double bts = frame->begin_pose.dest_timestamp, ets = frame->end_pose.dest_timestamp;
         for (size_t i = 0; i < n; ++i) {
-            const V3 w = ct_transform(qb, tb, qe, te, (double) (float) AlphaOf(keypoints[i].timestamp, bts, ets),
-                                      V3{(double) (float) keypoints[i].raw[0], (double) (float) keypoints[i].raw[1],
-                                         (double) (float) keypoints[i].raw[2]});
+            const V3 w = ct_transform(qb, tb, qe, te, AlphaOf(keypoints[i].timestamp, bts, ets),
+                                      V3{keypoints[i].raw[0], keypoints[i].raw[1], keypoints[i].raw[2]});
             keypoints[i].world[0] = w.x; keypoints[i].world[1] = w.y; keypoints[i].world[2] = w.z;
         }
         if (out_summary) {
@@ -762,6 +771,7 @@ int cticp_icp_gn_normal_equations(cticp_map *m, const cticp_icp_options *options
         IcpState S;
         UploadRegistrationInputs(m, keypoints, n, frame, previous_frame, motion_options, D, S);
         int n_used = 0;
+        m->icp->set_keypoints_lo(D.lo());
         m->icp->NormalEquations(*m->map, *options, D.d_kp, D.d_n, n, D.d_state, out_A144, out_b12, &n_used);
         *out_num_used = n_used;
         return (int) CTICP_OK;
@@ -779,14 +789,17 @@ int64_t cticp_grid_sample_indices(int device, const double *xyz, size_t stride_b
         CAPI_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         {
             FramePipeline pipe(n, stream);
-            float4 *stage = pipe.Staging();
+            float4 *stage = pipe.Staging(), *stage_lo = pipe.StagingLo();
             for (size_t i = 0; i < n; ++i) {
                 const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(xyz) + stride_bytes * i);
                 stage[i] = make_float4((float) p[0], (float) p[1], (float) p[2], 0.f);
+                stage_lo[i] = make_float4((float) (p[0] - (double) stage[i].x), (float) (p[1] - (double) stage[i].y),
+                                          (float) (p[2] - (double) stage[i].z), 0.f);
             }
             pipe.Upload(n);
-            pipe.GridSelect(pipe.d_raw(), nullptr, pipe.d_count_n(), n, voxel_size, 0, 0, 0, 0, 0, 0, 0.f,
-                            pipe.d_frame_mut(), pipe.d_frame_src_mut(), pipe.d_count_frame());
+            pipe.UploadLo(n);
+            pipe.GridSelect(pipe.d_raw(), pipe.d_raw_lo(), nullptr, pipe.d_count_n(), n, voxel_size, 0, 0, 0, 0, 0, 0, 0.f,
+                            pipe.d_frame_mut(), pipe.d_frame_lo_mut(), pipe.d_frame_src_mut(), pipe.d_count_frame());
             pipe.QueueCountsReadback();
             CAPI_CUDA(cudaStreamSynchronize(stream));
             total = pipe.h_counts()[1];
@@ -808,14 +821,17 @@ int64_t cticp_adaptive_sample_indices(int device, const cticp_adaptive_options *
         CAPI_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         {
             FramePipeline pipe(n, stream);
-            float4 *stage = pipe.Staging();
+            float4 *stage = pipe.Staging(), *stage_lo = pipe.StagingLo();
             for (size_t i = 0; i < n; ++i) {
                 const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(xyz) + stride_bytes * i);
                 stage[i] = make_float4((float) p[0], (float) p[1], (float) p[2], 0.f);
+                stage_lo[i] = make_float4((float) (p[0] - (double) stage[i].x), (float) (p[1] - (double) stage[i].y),
+                                          (float) (p[2] - (double) stage[i].z), 0.f);
             }
             pipe.Upload(n);
-            pipe.AdaptiveSelect(*options, pipe.d_raw(), nullptr, pipe.d_count_n(), n, pipe.d_frame_mut(),
-                                pipe.d_frame_src_mut(), pipe.d_count_frame());
+            pipe.UploadLo(n);
+            pipe.AdaptiveSelect(*options, pipe.d_raw(), pipe.d_raw_lo(), nullptr, pipe.d_count_n(), n, pipe.d_frame_mut(),
+                                pipe.d_frame_lo_mut(), pipe.d_frame_src_mut(), pipe.d_count_frame());
             pipe.QueueCountsReadback();
             CAPI_CUDA(cudaStreamSynchronize(stream));
             total = pipe.h_counts()[1];

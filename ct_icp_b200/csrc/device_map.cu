@@ -259,6 +259,7 @@ struct FusedUpdateArgs {
     int num_levels;
     MapCounters *counters;
     const float4 *frame;        // sub-sampled frame (raw xyz, alpha)
+    const float4 *frame_lo;     // its residual plane (nullptr: float32-representable, see load_raw)
     const int *d_n;
     double *world;              // out: its world points under the pose pair
     Q4 qb, qe;
@@ -280,8 +281,8 @@ k_map_update_fused(FusedUpdateArgs a) {
     const int n = *a.d_n;
     // phase 1: world points of the frame; eviction on every level; reset the per-level touched counters
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = a.frame[i];
-        const V3 w = ct_transform_c(a.qb, a.tb, a.qe, a.te, (double) p.w, V3{(double) p.x, (double) p.y, (double) p.z}, a.sc);
+        const RawPoint p = load_raw(a.frame, a.frame_lo, i);
+        const V3 w = ct_transform_c(a.qb, a.tb, a.qe, a.te, p.alpha, V3{p.x, p.y, p.z}, a.sc);
         a.world[3 * i] = w.x; a.world[3 * i + 1] = w.y; a.world[3 * i + 2] = w.z;
     }
     if (a.do_remove)
@@ -453,7 +454,7 @@ void DeviceMap::InsertDevice(const double *d_world_xyz, const int *d_n, size_t n
     dirty_ = true;
 }
 
-void DeviceMap::UpdateFused(const float4 *d_frame, const int *d_n, size_t n_upper, double *d_world, const Q4 &qb,
+void DeviceMap::UpdateFused(const float4 *d_frame, const float4 *d_frame_lo, const int *d_n, size_t n_upper, double *d_world, const Q4 &qb,
                             const V3 &tb, const Q4 &qe, const V3 &te, bool do_remove, V3 location, double max_distance,
                             bool do_insert, V3 origin) {
     if (n_upper == 0) return;
@@ -491,6 +492,7 @@ void DeviceMap::UpdateFused(const float4 *d_frame, const int *d_n, size_t n_uppe
     for (int l = 0; l < a.num_levels; ++l) a.levels[l] = levels_[l];
     a.counters = d_counters_;
     a.frame = d_frame;
+    a.frame_lo = d_frame_lo;
     a.d_n = d_n;
     a.world = d_world;
     a.qb = qb; a.qe = qe; a.tb = tb; a.te = te;

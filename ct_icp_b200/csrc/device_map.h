@@ -34,7 +34,7 @@ public:
     // RemoveElementsFarFromLocation (map.h:305-322)
     void RemoveFar(V3 location, double distance);
     // one cooperative launch: world points of the sub-sampled frame under the pose pair (→ d_world), RemoveFar, InsertDevice
-    void UpdateFused(const float4 *d_frame, const int *d_n, size_t n_upper, double *d_world, const Q4 &qb, const V3 &tb,
+    void UpdateFused(const float4 *d_frame, const float4 *d_frame_lo, const int *d_n, size_t n_upper, double *d_world, const Q4 &qb, const V3 &tb,
                      const Q4 &qe, const V3 &te, bool do_remove, V3 location, double max_distance, bool do_insert, V3 origin);
     void Clear();
 

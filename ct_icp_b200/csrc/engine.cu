@@ -137,7 +137,7 @@ Engine::~Engine() {
     cudaFree(d_kp_world_);
     for (auto &e : ev_) cudaEventDestroy(e);
     for (auto &e : timer_ev_) cudaEventDestroy(e);
-    for (auto &sc : staged_) cudaFree(sc.d_points);
+    for (auto &sc : staged_) { cudaFree(sc.d_points); cudaFree(sc.d_lo); }
     cudaFree(d_flush_);
     for (int i = 0; i < 3; ++i) {
         cudaFreeHost(h_world_[i]);
@@ -219,7 +219,8 @@ void Engine::EnqueueEgress(const HostFrame &f, bool ran_icp) {
     }
     if ((summary_points_mask_ & (1 << CTICP_POINTS_KEYPOINTS))) {
         if (n_kp) {
-            pipe_->TransformInto(pipe_->d_keypoints(), pipe_->d_count_keypoints(), qb, tb, qe, te, d_kp_world_, es);
+            pipe_->TransformInto(pipe_->d_keypoints(), pipe_->d_keypoints_lo(), pipe_->d_count_keypoints(), qb, tb, qe, te,
+                                 d_kp_world_, es);
             CT_CUDA_CHECK(cudaMemcpyAsync(h_world_[2], d_kp_world_, sizeof(double) * 3 * n_kp, cudaMemcpyDeviceToHost, es));
             CT_CUDA_CHECK(cudaMemcpyAsync(h_src_[2], pipe_->d_keypoints_src(), sizeof(uint32_t) * n_kp, cudaMemcpyDeviceToHost, es));
             last_kp_world_valid_ = true;
@@ -303,7 +304,7 @@ void Engine::IngestImpl(const ScanView &scan, const FrameInfo &info, int64_t sta
     if (n > pipe_->MaxPoints()) throw CapacityError("scan has more points than max_points_per_frame");
 
     // host buffers were packed and their H2D copy enqueued by PackAndUpload (RegisterCommon) before the pose pair existed
-    if (staged_slot >= 0) pipe_->UploadFromDevice(staged_[staged_slot].d_points, n);   // already packed, already in HBM
+    if (staged_slot >= 0) pipe_->UploadFromDevice(staged_[staged_slot].d_points, staged_[staged_slot].d_lo, n);   // already packed, already in HBM
     timing_.h2d_bytes += pipe_->h2d_bytes();
     const double sample_size = k < options_.init_num_frames ? options_.init_voxel_size : options_.voxel_size;
     // frames 0 and 1: every timestamp := end_timestamp (odometry.cpp:355-359)
@@ -441,7 +442,26 @@ template <typename T> inline T LoadUnaligned(const char *p) {   // PointCloud2 r
 }
 }  // namespace
 
-void Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst) {
+namespace {
+// one packed point: hi = float32(x, y, z, alpha) with a non-temporal store (the packed scan is consumed by the DMA engine,
+// not by this core — keeping it out of the CPU caches took the H2D copy from ~12 GB/s, snooped dirty lines, to PCIe
+// speed); for float64 sources also the residual plane lo = value - hi, and whether any coordinate needs it
+template <typename XT>
+inline void PackPoint(XT x, XT y, XT z, double a, float4 *dst, float4 *dst_lo, bool *any_lo) {
+    const float fx = (float) x, fy = (float) y, fz = (float) z, fa = (float) a;
+    _mm_stream_ps(reinterpret_cast<float *>(dst), _mm_set_ps(fa, fz, fy, fx));
+    if constexpr (std::is_same<XT, double>::value) {
+        const float lx = (float) (x - (double) fx), ly = (float) (y - (double) fy), lz = (float) (z - (double) fz);
+        _mm_stream_ps(reinterpret_cast<float *>(dst_lo), _mm_set_ps((float) (a - (double) fa), lz, ly, lx));
+        if (lx != 0.f || ly != 0.f || lz != 0.f) *any_lo = true;
+    }
+}
+}  // namespace
+
+// returns whether the scan needs its residual plane (float64 coordinates that are not float32-representable); dst_lo is
+// written iff the coordinates are float64
+bool Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst, float4 *dst_lo) {
+    std::atomic<bool> needs_lo{false};
     const double mn = std::min(bts, ets), mx = std::max(bts, ets);
     const double inv = (mx > mn) ? 1.0 / (mx - mn) : 0.0;
     const char *px = static_cast<const char *>(scan.xyz), *pt = static_cast<const char *>(scan.t);
@@ -451,18 +471,19 @@ void Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst)
         using XT = typename decltype(xt)::type;
         using TT = typename decltype(tt)::type;
         pool_->ParallelFor(scan.n, [&](size_t b, size_t e, int) {
+            bool any = false;
             for (size_t i = b; i < e; ++i) {
                 const char *p = px + i * xs;
                 const XT x = LoadUnaligned<XT>(p), y = LoadUnaligned<XT>(p + sizeof(XT)), z = LoadUnaligned<XT>(p + 2 * sizeof(XT));
                 const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
                 const double a = spans ? (ti - mn) * inv : 1.0;
-                // non-temporal store: the packed scan is consumed by the DMA engine, not by this core — keeping it
-                // out of the CPU caches took the H2D copy from ~12 GB/s (snooped dirty lines) to PCIe speed
-                _mm_stream_ps(reinterpret_cast<float *>(dst + i), _mm_set_ps((float) a, (float) z, (float) y, (float) x));
+                PackPoint<XT>(x, y, z, a, dst + i, dst_lo + i, &any);
             }
             _mm_sfence();
+            if (any) needs_lo.store(true, std::memory_order_relaxed);
         });
     });
+    return needs_lo.load();
 }
 
 // RegisterFrame's O(N) host work as ONE parallel region (one wake-up of the team instead of two):
@@ -481,6 +502,8 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
     const char *px = static_cast<const char *>(scan.xyz), *pt = static_cast<const char *>(scan.t);
     const size_t xs = scan.xyz_stride, ts = scan.t_stride;
     float4 *dst = pipe_->Staging();
+    float4 *dst_lo = scan.xyz_dtype == CTICP_DTYPE_FLOAT64 ? pipe_->StagingLo() : nullptr;   // residual plane (PackPoint)
+    std::atomic<bool> needs_lo{false};
     double mns[64], mxs[64];
     std::atomic<int> arrived{0};
     std::atomic<int> round_done[kRounds];
@@ -538,6 +561,7 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
                     ++issued;
                 }
             };
+            bool any = false;
             for (int r = 0; r < rounds; ++r) {
                 const size_t piece = (size_t) r * nparts + part;
                 const size_t b = piece_begin(piece), e = piece_begin(piece + 1);
@@ -546,16 +570,18 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
                     const XT x = LoadUnaligned<XT>(p), y = LoadUnaligned<XT>(p + sizeof(XT)), z = LoadUnaligned<XT>(p + 2 * sizeof(XT));
                     const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
                     const double a = spans ? (ti - mn) * inv : 1.0;
-                    // non-temporal store: the packed scan is consumed by the DMA engine, not by this core
-                    _mm_stream_ps(reinterpret_cast<float *>(dst + i), _mm_set_ps((float) a, (float) z, (float) y, (float) x));
+                    PackPoint<XT>(x, y, z, a, dst + i, dst_lo + i, &any);
                 }
                 _mm_sfence();
+                if (any) needs_lo.store(true, std::memory_order_relaxed);
                 round_done[r].fetch_add(1, std::memory_order_acq_rel);
                 if (part == 0) issue_ready(false);
             }
             if (part == 0) issue_ready(true);
         });
     });
+    // float64 coordinates that float32 cannot hold: the residual plane follows (one more copy; float32 scans never get here)
+    if (needs_lo.load()) pipe_->UploadLo(n);
     if (debug) cudaEventRecord(ev_[5], stream_);
     if (failed.load()) throw CudaError("cudaMemcpyAsync (scan upload)");
 }
@@ -594,9 +620,14 @@ int64_t Engine::StageFrame(const ScanView &scan) {
     sc.n = n;
     MinMaxTimestamps(scan, &sc.t_min, &sc.t_max);
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // the pinned staging buffer may still feed a previous copy
-    PackScan(scan, sc.t_min, sc.t_max, pipe_->Staging());
+    float4 *stage_lo = scan.xyz_dtype == CTICP_DTYPE_FLOAT64 ? pipe_->StagingLo() : nullptr;
+    const bool needs_lo = PackScan(scan, sc.t_min, sc.t_max, pipe_->Staging(), stage_lo);
     CT_CUDA_CHECK(cudaMalloc(&sc.d_points, sizeof(float4) * n));
     CT_CUDA_CHECK(cudaMemcpyAsync(sc.d_points, pipe_->Staging(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream_));
+    if (needs_lo) {
+        CT_CUDA_CHECK(cudaMalloc(&sc.d_lo, sizeof(float4) * n));
+        CT_CUDA_CHECK(cudaMemcpyAsync(sc.d_lo, stage_lo, sizeof(float4) * n, cudaMemcpyHostToDevice, stream_));
+    }
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
     staged_.push_back(sc);
     return (int64_t) staged_.size() - 1;
@@ -604,7 +635,7 @@ int64_t Engine::StageFrame(const ScanView &scan) {
 void Engine::ClearStaged() {
     CT_CUDA_CHECK(cudaSetDevice(device_));
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    for (auto &sc : staged_) cudaFree(sc.d_points);
+    for (auto &sc : staged_) { cudaFree(sc.d_points); cudaFree(sc.d_lo); }
     staged_.clear();
 }
 void Engine::TimerStart() {
@@ -676,6 +707,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     icp_state_refresh_slerp(S);
     CT_CUDA_CHECK(cudaMemcpyAsync(d_state_, h_state_, sizeof(IcpState), cudaMemcpyHostToDevice, stream_));
     CT_CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
+    icp_->set_keypoints_lo(pipe_->d_keypoints_lo());
     switch (options.solver) {
         case CTICP_SOLVER_GN:
             icp_->EnqueueGaussNewton(*map_, options, pipe_->d_keypoints(), pipe_->d_count_keypoints(), KeypointHint(),
@@ -872,7 +904,7 @@ void Engine::UpdateMap(Summary &s, int registered_fid) {
     if (fused_map_update_) {
         // transform of the sub-sampled frame + eviction + insertion on every resolution: one cooperative launch
         const auto &f = s.frame;
-        map_->UpdateFused(pipe_->d_frame(), pipe_->d_count_frame(), pipe_->n(), pipe_->d_frame_world_mut(), f.begin_pose.pose.q,
+        map_->UpdateFused(pipe_->d_frame(), pipe_->d_frame_lo(), pipe_->d_count_frame(), pipe_->n(), pipe_->d_frame_world_mut(), f.begin_pose.pose.q,
                           f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t, true, location, options_.max_distance,
                           add_points, f.begin_pose.pose.t);
         frame_world_valid_ = true;
@@ -1112,9 +1144,10 @@ cticp_device_timing Engine::LastTiming() {
 
 // RegistrationSummary::{corrected_points, all_corrected_points, keypoints} on demand
 // the device arrays behind RegistrationSummary::{corrected_points, all_corrected_points, keypoints}
-void Engine::ResolvePoints(int which, const float4 **out_pts, const double **out_world, size_t *out_count) {
+void Engine::ResolvePoints(int which, const float4 **out_pts, const float4 **out_lo, const double **out_world,
+                           size_t *out_count) {
     CT_CUDA_CHECK(cudaSetDevice(device_));
-    const float4 *d_pts = nullptr;
+    const float4 *d_pts = nullptr, *d_lo = nullptr;
     const double *d_world = nullptr;
     size_t count = 0;
     const auto &f = last_frame_;
@@ -1125,6 +1158,7 @@ void Engine::ResolvePoints(int which, const float4 **out_pts, const double **out
                 frame_world_valid_ = true;
             }
             d_pts = pipe_->d_frame();
+            d_lo = pipe_->d_frame_lo();
             d_world = pipe_->d_frame_world();
             count = (size_t) pipe_->h_counts()[1];
             break;
@@ -1134,29 +1168,34 @@ void Engine::ResolvePoints(int which, const float4 **out_pts, const double **out
                 last_all_world_valid_ = true;
             }
             d_pts = pipe_->d_raw();
+            d_lo = pipe_->d_raw_lo();
             d_world = pipe_->d_all_world();
             count = pipe_->n();
             break;
         case CTICP_POINTS_KEYPOINTS:
             count = last_info_.registered_fid > 0 ? (size_t) pipe_->h_counts()[2] : 0;
             if (count && !last_kp_world_valid_) {
-                pipe_->TransformInto(pipe_->d_keypoints(), pipe_->d_count_keypoints(), f.begin_pose.pose.q,
+                pipe_->TransformInto(pipe_->d_keypoints(), pipe_->d_keypoints_lo(), pipe_->d_count_keypoints(), f.begin_pose.pose.q,
                                      f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t, d_kp_world_);
                 last_kp_world_valid_ = true;
             }
             d_pts = pipe_->d_keypoints();
+            d_lo = pipe_->d_keypoints_lo();
             d_world = d_kp_world_;
             break;
         default:
             throw std::invalid_argument("which");
     }
     *out_pts = d_pts;
+    *out_lo = d_lo;
     *out_world = d_world;
     *out_count = count;
 }
 
 int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
-    if (which >= 0 && which < 3 && egress_valid_[which] && scan_in_staging_) {
+    // (a frame distorted on the device — motion compensation CONSTANT_VELOCITY — is no longer what the staging buffer holds)
+    if (which >= 0 && which < 3 && egress_valid_[which] && scan_in_staging_ &&
+        !(pipe_->frame_distorted() && which != CTICP_POINTS_ALL_CORRECTED)) {
         // eager path: the world coordinates (and source indices) are already on their way to pinned host memory; the raw
         // coordinates and the alpha timestamps are still in the pinned staging buffer the scan was packed into
         CT_CUDA_CHECK(cudaSetDevice(device_));
@@ -1169,6 +1208,7 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
         const double bts = f.begin_pose.dest_timestamp, ets = f.end_pose.dest_timestamp;
         const double mn = std::min(bts, ets), mx = std::max(bts, ets);
         const float4 *stage = pipe_->Staging();
+        const float4 *stage_lo = pipe_->StagingLoIfAny();
         const double *w = h_world_[which];
         const uint32_t *src = which == CTICP_POINTS_ALL_CORRECTED ? nullptr : h_src_[which];
         // frames 0 and 1: the sub-sampled frame (and its keypoints) carry timestamp := end_timestamp (odometry.cpp:355-359)
@@ -1183,10 +1223,17 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
         if (pe <= pb) continue;
         pool_->ParallelFor(pe - pb, [&](size_t b0, size_t e0, int) {
             for (size_t i = pb + b0; i < pb + e0; ++i) {
-                const float4 p = stage[src ? src[i] : i];
+                const size_t si = src ? src[i] : i;
+                const float4 p = stage[si];
                 cticp_wpoint &o = dst[i];
                 o.raw[0] = p.x; o.raw[1] = p.y; o.raw[2] = p.z;
-                o.timestamp = override_t ? t_override : mn + (double) p.w * (mx - mn);
+                double alpha = (double) p.w;
+                if (stage_lo) {
+                    const float4 l = stage_lo[si];
+                    o.raw[0] += (double) l.x; o.raw[1] += (double) l.y; o.raw[2] += (double) l.z;
+                    alpha += (double) l.w;
+                }
+                o.timestamp = override_t ? t_override : mn + alpha * (mx - mn);
                 o.world[0] = w[3 * i]; o.world[1] = w[3 * i + 1]; o.world[2] = w[3 * i + 2];
                 o.index_frame = frame_id;
                 o._pad0 = 0;
@@ -1195,16 +1242,17 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
         }
         return (int64_t) count;
     }
-    const float4 *d_pts = nullptr;
+    const float4 *d_pts = nullptr, *d_lo = nullptr;
     const double *d_world = nullptr;
     size_t count = 0;
-    ResolvePoints(which, &d_pts, &d_world, &count);
+    ResolvePoints(which, &d_pts, &d_lo, &d_world, &count);
     const auto &f = last_frame_;
     const size_t m = std::min(cap, count);
     if (m == 0 || !dst) return (int64_t) count;
-    std::vector<float4> hp(m);
+    std::vector<float4> hp(m), hl(d_lo ? m : 0);
     std::vector<double> hw(3 * m);
     CT_CUDA_CHECK(cudaMemcpyAsync(hp.data(), d_pts, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream_));
+    if (d_lo) CT_CUDA_CHECK(cudaMemcpyAsync(hl.data(), d_lo, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream_));
     CT_CUDA_CHECK(cudaMemcpyAsync(hw.data(), d_world, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, stream_));
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
     const double bts = f.begin_pose.dest_timestamp, ets = f.end_pose.dest_timestamp;
@@ -1212,7 +1260,12 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
     for (size_t i = 0; i < m; ++i) {
         cticp_wpoint &o = dst[i];
         o.raw[0] = hp[i].x; o.raw[1] = hp[i].y; o.raw[2] = hp[i].z;
-        o.timestamp = mn + (double) hp[i].w * (mx - mn);
+        double alpha = (double) hp[i].w;
+        if (d_lo) {
+            o.raw[0] += (double) hl[i].x; o.raw[1] += (double) hl[i].y; o.raw[2] += (double) hl[i].z;
+            alpha += (double) hl[i].w;
+        }
+        o.timestamp = mn + alpha * (mx - mn);
         o.world[0] = hw[3 * i]; o.world[1] = hw[3 * i + 1]; o.world[2] = hw[3 * i + 2];
         o.index_frame = last_info_.frame_id;
         o._pad0 = 0;
@@ -1222,10 +1275,10 @@ int64_t Engine::GetPoints(int which, cticp_wpoint *dst, size_t cap) {
 
 // cticp_odometry_write_points: the same vectors written straight into the caller's record layout
 int64_t Engine::WritePoints(int which, const cticp_cloud_sink &sink) {
-    const float4 *d_pts = nullptr;
+    const float4 *d_pts = nullptr, *d_lo = nullptr;
     const double *d_world = nullptr;
     size_t count = 0;
-    ResolvePoints(which, &d_pts, &d_world, &count);
+    ResolvePoints(which, &d_pts, &d_lo, &d_world, &count);
     const size_t m = std::min((size_t) sink.capacity_points, count);
     if (m == 0 || !sink.data) return (int64_t) count;
     const size_t xs = sink.xyz_dtype == CTICP_DTYPE_FLOAT32 ? 4 : 8;
@@ -1236,9 +1289,10 @@ int64_t Engine::WritePoints(int which, const cticp_cloud_sink &sink) {
     if ((size_t) sink.xyz_offset + 3 * xs > sink.point_step ||
         (sink.t_dtype && (size_t) sink.t_offset + (sink.t_dtype == CTICP_DTYPE_FLOAT32 ? 4 : 8) > sink.point_step))
         throw std::invalid_argument("sink: a field lies outside the record (point_step)");
-    std::vector<float4> hp(m);
+    std::vector<float4> hp(m), hl(d_lo ? m : 0);
     std::vector<double> hw(sink.world ? 3 * m : 0);
     CT_CUDA_CHECK(cudaMemcpyAsync(hp.data(), d_pts, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream_));
+    if (d_lo) CT_CUDA_CHECK(cudaMemcpyAsync(hl.data(), d_lo, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream_));
     if (sink.world)
         CT_CUDA_CHECK(cudaMemcpyAsync(hw.data(), d_world, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, stream_));
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -1251,7 +1305,10 @@ int64_t Engine::WritePoints(int which, const cticp_cloud_sink &sink) {
             char *rec = base + i * sink.point_step;
             double p[3];
             if (sink.world) { p[0] = hw[3 * i]; p[1] = hw[3 * i + 1]; p[2] = hw[3 * i + 2]; }
-            else { p[0] = hp[i].x; p[1] = hp[i].y; p[2] = hp[i].z; }
+            else {
+                p[0] = hp[i].x; p[1] = hp[i].y; p[2] = hp[i].z;
+                if (d_lo) { p[0] += (double) hl[i].x; p[1] += (double) hl[i].y; p[2] += (double) hl[i].z; }
+            }
             if (sink.xyz_dtype == CTICP_DTYPE_FLOAT32) {
                 const float q[3] = {(float) p[0], (float) p[1], (float) p[2]};
                 memcpy(rec + sink.xyz_offset, q, sizeof(q));
@@ -1259,7 +1316,7 @@ int64_t Engine::WritePoints(int which, const cticp_cloud_sink &sink) {
                 memcpy(rec + sink.xyz_offset, p, sizeof(p));
             }
             if (sink.t_dtype) {
-                const double t = mn + (double) hp[i].w * (mx - mn);
+                const double t = mn + ((double) hp[i].w + (d_lo ? (double) hl[i].w : 0.0)) * (mx - mn);
                 if (sink.t_dtype == CTICP_DTYPE_FLOAT32) { const float tf = (float) t; memcpy(rec + sink.t_offset, &tf, 4); }
                 else memcpy(rec + sink.t_offset, &t, 8);
             }

@@ -140,11 +140,10 @@ private:
     };
 
     void InitializeMotion(const FrameInfo &info, const cticp_frame *initial_estimate);
-    void ResolvePoints(int which, const float4 **out_pts, const double **out_world, size_t *out_count);
+    void ResolvePoints(int which, const float4 **out_pts, const float4 **out_lo, const double **out_world, size_t *out_count);
     void IngestImpl(const ScanView &scan,
                     const FrameInfo &info, int64_t staged_slot);
-    void PackScan(const ScanView &scan, double bts,
-                  double ets, float4 *dst);
+    bool PackScan(const ScanView &scan, double bts, double ets, float4 *dst, float4 *dst_lo);
     // one parallel region: timestamp min/max → team barrier → (x, y, z, alpha) packing in rounds, the H2D copy of a
     // round enqueued as soon as the round is complete (the copy engine runs while the later rounds are still packed)
     void PackAndUpload(const ScanView &scan, const double *pose_timestamps, double *mn_out, double *mx_out);
@@ -162,6 +161,7 @@ private:
     bool keypoints_sampled_ = false;   // the keypoints of the coming first attempt were sampled with the frame   // d_frame_world holds the sub-sampled frame under last_frame_
     struct StagedScan {
         float4 *d_points = nullptr;
+        float4 *d_lo = nullptr;   // residual plane, float64 scans only (se3.cuh load_raw)
         size_t n = 0;
         double t_min = 0, t_max = 0;
     };

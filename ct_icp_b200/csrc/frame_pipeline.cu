@@ -30,21 +30,21 @@ constexpr size_t kMaxTiles = 4096;   // up to 4M points per scan
 constexpr int kTileShift = 10, kTile = 1 << kTileShift, kTileThreads = kTile / 4;   // 1024 positions per CTA
 
 // voxel key of sub_sample_frame: static_cast<short>(raw / size) per axis (ct_icp.cpp:70-72)
-__device__ __forceinline__ unsigned long long short_voxel_key(const float4 &p, double voxel_size) {
-    const short x = (short) (int) ((double) p.x / voxel_size);
-    const short y = (short) (int) ((double) p.y / voxel_size);
-    const short z = (short) (int) ((double) p.z / voxel_size);
+__device__ __forceinline__ unsigned long long short_voxel_key(const RawPoint &p, double voxel_size) {
+    const short x = (short) (int) (p.x / voxel_size);
+    const short y = (short) (int) (p.y / voxel_size);
+    const short z = (short) (int) (p.z / voxel_size);
     return ((unsigned long long) (unsigned short) x << 32) | ((unsigned long long) (unsigned short) y << 16) |
            (unsigned long long) (unsigned short) z;
 }
 
 // claim: every point bids (priority, index) for its voxel
-__device__ __forceinline__ void grid_claim_dev(const float4 *__restrict__ pts, int n, double voxel_size, int use_perm,
+__device__ __forceinline__ void grid_claim_dev(const float4 *pts, const float4 *lo, int n, double voxel_size, int use_perm,
                                                uint64_t seed, uint64_t counter, unsigned long long *keys,
                                                unsigned long long *vals, uint32_t cap_mask, int *__restrict__ slot_of) {
     const Perm perm = perm_make(seed, counter, (uint32_t) max(n, 1));
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long key = short_voxel_key(pts[i], voxel_size);
+        const unsigned long long key = short_voxel_key(load_raw(pts, lo, i), voxel_size);
         const uint32_t prio = use_perm ? perm_apply(perm, (uint32_t) i) : (uint32_t) i;
         uint32_t h = hash_key(key) & cap_mask;
         while (true) {
@@ -57,10 +57,10 @@ __device__ __forceinline__ void grid_claim_dev(const float4 *__restrict__ pts, i
         slot_of[i] = (int) h;
     }
 }
-__global__ void k_grid_claim(const float4 *__restrict__ pts, const int *__restrict__ d_n, double voxel_size,
-                             int use_perm, uint64_t seed, uint64_t counter, unsigned long long *keys,
+__global__ void k_grid_claim(const float4 *__restrict__ pts, const float4 *__restrict__ lo, const int *__restrict__ d_n,
+                             double voxel_size, int use_perm, uint64_t seed, uint64_t counter, unsigned long long *keys,
                              unsigned long long *vals, uint32_t cap_mask, int *__restrict__ slot_of) {
-    grid_claim_dev(pts, *d_n, voxel_size, use_perm, seed, counter, keys, vals, cap_mask, slot_of);
+    grid_claim_dev(pts, lo, *d_n, voxel_size, use_perm, seed, counter, keys, vals, cap_mask, slot_of);
 }
 // mark: winners raise a flag at their position in the permuted order
 __device__ __forceinline__ void grid_mark_dev(int n, int use_perm, uint64_t seed, uint64_t counter,
@@ -93,10 +93,10 @@ struct EmitScratch {
     uint32_t before, total;
 };
 // all threads of a CTA of kTileThreads threads; returns the number of winners (identical in every CTA)
-__device__ __forceinline__ uint32_t grid_emit_dev(const float4 *pts, const uint32_t *in_src_index, int n,
+__device__ __forceinline__ uint32_t grid_emit_dev(const float4 *pts, const float4 *lo, const uint32_t *in_src_index, int n,
                                                   const uint32_t *flags, const uint32_t *src, const uint32_t *tile_count,
                                                   int use_perm2, uint64_t seed, uint64_t counter2, int override_alpha,
-                                                  float alpha_value, float4 *__restrict__ out,
+                                                  float alpha_value, float4 *__restrict__ out, float4 *__restrict__ out_lo,
                                                   uint32_t *__restrict__ out_src_index, int *__restrict__ d_total,
                                                   EmitScratch &sc) {
     uint32_t (&s_red)[2][kTileThreads / 32] = sc.red;
@@ -163,6 +163,11 @@ __device__ __forceinline__ uint32_t grid_emit_dev(const float4 *pts, const uint3
                 float4 val = pts[i];
                 if (override_alpha) val.w = alpha_value;
                 out[dst] = val;
+                if (out_lo) {
+                    float4 l = lo ? lo[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (override_alpha) l.w = 0.f;
+                    out_lo[dst] = l;
+                }
                 out_src_index[dst] = in_src_index ? in_src_index[i] : i;
             }
             excl += v[k];
@@ -171,14 +176,14 @@ __device__ __forceinline__ uint32_t grid_emit_dev(const float4 *pts, const uint3
     return total;
 }
 __global__ void __launch_bounds__(kTileThreads)
-k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_index, const int *__restrict__ d_n,
-            const uint32_t *__restrict__ flags, const uint32_t *__restrict__ src,
+k_grid_emit(const float4 *__restrict__ pts, const float4 *__restrict__ lo, const uint32_t *__restrict__ in_src_index,
+            const int *__restrict__ d_n, const uint32_t *__restrict__ flags, const uint32_t *__restrict__ src,
             const uint32_t *__restrict__ tile_count, int use_perm2, uint64_t seed, uint64_t counter2,
-            int override_alpha, float alpha_value, float4 *__restrict__ out, uint32_t *__restrict__ out_src_index,
-            int *__restrict__ d_total) {
+            int override_alpha, float alpha_value, float4 *__restrict__ out, float4 *__restrict__ out_lo,
+            uint32_t *__restrict__ out_src_index, int *__restrict__ d_total) {
     __shared__ EmitScratch sc;
-    grid_emit_dev(pts, in_src_index, *d_n, flags, src, tile_count, use_perm2, seed, counter2, override_alpha, alpha_value, out,
-                  out_src_index, d_total, sc);
+    grid_emit_dev(pts, lo, in_src_index, *d_n, flags, src, tile_count, use_perm2, seed, counter2, override_alpha, alpha_value,
+                  out, out_lo, out_src_index, d_total, sc);
 }
 
 // ---- both grid selections of a frame (sub_sample_frame N -> F, grid_sampling F -> K) in ONE cooperative launch: seven
@@ -186,6 +191,8 @@ k_grid_emit(const float4 *__restrict__ pts, const uint32_t *__restrict__ in_src_
 // worth about one: launch ramp, tail, and the dependency on its predecessor; 46 us of a 310 us step in round 1.)
 struct FusedSampleArgs {
     const float4 *raw;
+    const float4 *raw_lo;              // residual plane of the scan (nullptr: float32-representable)
+    float4 *frame_lo, *kp_lo;          // residual planes of the two selections (written iff raw_lo)
     int *counts;                       // [0] = N in, [1] = F out, [2] = K out
     double voxel1, voxel2;
     uint64_t seed, c1, c2;
@@ -210,24 +217,25 @@ k_sample_fused(FusedSampleArgs a) {
     for (size_t i = gtid; i < 2 * (size_t) a.cap1; i += gsize) a.grid[i] = kGridEmpty;
     for (size_t i = gtid; i < kMaxTiles + (size_t) n; i += gsize) a.tile1[i] = 0u;   // flags1 = tile1 + kMaxTiles
     grid.sync();
-    grid_claim_dev(a.raw, n, a.voxel1, 1, a.seed, a.c1, a.grid, a.grid + a.cap1, a.cap1 - 1, a.slot_of);
+    grid_claim_dev(a.raw, a.raw_lo, n, a.voxel1, 1, a.seed, a.c1, a.grid, a.grid + a.cap1, a.cap1 - 1, a.slot_of);
     grid.sync();
     grid_mark_dev(n, 1, a.seed, a.c1, a.grid + a.cap1, a.slot_of, a.flags1, a.src1, a.tile1);
     grid.sync();
-    const uint32_t F = grid_emit_dev(a.raw, nullptr, n, a.flags1, a.src1, a.tile1, 1, a.seed, a.c2, a.override_alpha,
-                                     a.alpha_value, a.frame, a.frame_src, a.counts + 1, sc);
+    float4 *frame_lo = a.raw_lo ? a.frame_lo : nullptr, *kp_lo = a.raw_lo ? a.kp_lo : nullptr;
+    const uint32_t F = grid_emit_dev(a.raw, a.raw_lo, nullptr, n, a.flags1, a.src1, a.tile1, 1, a.seed, a.c2, a.override_alpha,
+                                     a.alpha_value, a.frame, frame_lo, a.frame_src, a.counts + 1, sc);
     // selection 2 works on F points: a smaller grid (the first one is not read any more), its own flags
     uint32_t cap2 = 1024;
     while (cap2 < 2 * F) cap2 <<= 1;
     for (size_t i = gtid; i < 2 * (size_t) cap2; i += gsize) a.grid[i] = kGridEmpty;
     for (size_t i = gtid; i < kMaxTiles + (size_t) F; i += gsize) a.tile2[i] = 0u;
     grid.sync();
-    grid_claim_dev(a.frame, (int) F, a.voxel2, 0, 0, 0, a.grid, a.grid + cap2, cap2 - 1, a.slot_of);
+    grid_claim_dev(a.frame, frame_lo, (int) F, a.voxel2, 0, 0, 0, a.grid, a.grid + cap2, cap2 - 1, a.slot_of);
     grid.sync();
     grid_mark_dev((int) F, 0, 0, 0, a.grid + cap2, a.slot_of, a.flags2, a.src2, a.tile2);
     grid.sync();
-    grid_emit_dev(a.frame, a.frame_src, (int) F, a.flags2, a.src2, a.tile2, 0, 0, 0, 0, 0.f, a.keypoints, a.kp_src,
-                  a.counts + 2, sc);
+    grid_emit_dev(a.frame, frame_lo, a.frame_src, (int) F, a.flags2, a.src2, a.tile2, 0, 0, 0, 0, 0.f, a.keypoints, kp_lo,
+                  a.kp_src, a.counts + 2, sc);
 }
 // ---- adaptive (distance-banded) grid sampling: AdaptiveSamplePointsInGrid, include/ct_icp/algorithm/sampling.h:55-110
 struct AdaptiveBands {
@@ -235,7 +243,7 @@ struct AdaptiveBands {
     double distance[CTICP_MAX_ADAPTIVE_BANDS];
     double voxel_size[CTICP_MAX_ADAPTIVE_BANDS];
 };
-__device__ __forceinline__ int adaptive_band(const AdaptiveBands &B, const float4 &p, unsigned long long *key_out) {
+__device__ __forceinline__ int adaptive_band(const AdaptiveBands &B, const RawPoint &p, unsigned long long *key_out) {
     const double x = p.x, y = p.y, z = p.z;
     const double dist = sqrt(x * x + y * y + z * z);
     int lw = 0;   // std::lower_bound with comp(elem, v) = elem.first < v (:69-74)
@@ -250,14 +258,14 @@ __device__ __forceinline__ int adaptive_band(const AdaptiveBands &B, const float
                ((unsigned long long) (unsigned) ((vy + bias) & 0xFFFFF) << 20) | (unsigned long long) (unsigned) ((vz + bias) & 0xFFFFF);
     return band;
 }
-__global__ void k_adaptive_claim(const float4 *__restrict__ pts, const int *__restrict__ d_n, AdaptiveBands B,
+__global__ void k_adaptive_claim(const float4 *__restrict__ pts, const float4 *__restrict__ lo, const int *__restrict__ d_n, AdaptiveBands B,
                                  unsigned long long *keys, unsigned long long *vals, uint32_t cap_mask,
                                  int *__restrict__ slot_of, int *__restrict__ d_positions) {
     const int n = *d_n;
     if (blockIdx.x == 0 && threadIdx.x == 0) *d_positions = n * B.num_bands;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         unsigned long long key;
-        const int band = adaptive_band(B, pts[i], &key);
+        const int band = adaptive_band(B, load_raw(pts, lo, i), &key);
         if (band < 0) {
             slot_of[i] = -1;
             continue;
@@ -273,7 +281,7 @@ __global__ void k_adaptive_claim(const float4 *__restrict__ pts, const int *__re
         slot_of[i] = (int) h;
     }
 }
-__global__ void k_adaptive_mark(const float4 *__restrict__ pts, const int *__restrict__ d_n, AdaptiveBands B,
+__global__ void k_adaptive_mark(const float4 *__restrict__ pts, const float4 *__restrict__ lo, const int *__restrict__ d_n, AdaptiveBands B,
                                 const unsigned long long *__restrict__ vals, const int *__restrict__ slot_of,
                                 uint32_t *__restrict__ flags, uint32_t *__restrict__ src,
                                 uint32_t *__restrict__ tile_count) {
@@ -282,7 +290,7 @@ __global__ void k_adaptive_mark(const float4 *__restrict__ pts, const int *__res
         const int slot = slot_of[i];
         if (slot < 0 || vals[slot] != (unsigned long long) (unsigned) i) continue;
         unsigned long long key;
-        const int band = adaptive_band(B, pts[i], &key);
+        const int band = adaptive_band(B, load_raw(pts, lo, i), &key);
         const uint32_t pos = (uint32_t) band * (uint32_t) n + (uint32_t) i;   // band-major, then first appearance
         flags[pos] = 1u;
         src[pos] = (uint32_t) i;
@@ -291,20 +299,21 @@ __global__ void k_adaptive_mark(const float4 *__restrict__ pts, const int *__res
 }
 
 // keypoints = frame (sampling NONE, odometry.cpp:546)
-__global__ void k_copy_points(const float4 *__restrict__ in, const uint32_t *__restrict__ in_src,
-                              const int *__restrict__ d_n, float4 *__restrict__ out, uint32_t *__restrict__ out_src,
-                              int *__restrict__ d_n_out) {
+__global__ void k_copy_points(const float4 *__restrict__ in, const float4 *__restrict__ in_lo, const uint32_t *__restrict__ in_src,
+                              const int *__restrict__ d_n, float4 *__restrict__ out, float4 *__restrict__ out_lo,
+                              uint32_t *__restrict__ out_src, int *__restrict__ d_n_out) {
     const int n = *d_n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         out[i] = in[i];
+        if (in_lo) out_lo[i] = in_lo[i];
         out_src[i] = in_src[i];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *d_n_out = n;
 }
 // max_num_keypoints: shuffle + resize (odometry.cpp:549-552) when *d_n > max_n
-__global__ void k_truncate_shuffle(const float4 *__restrict__ in, const uint32_t *__restrict__ in_src,
+__global__ void k_truncate_shuffle(const float4 *__restrict__ in, const float4 *__restrict__ in_lo, const uint32_t *__restrict__ in_src,
                                    const int *__restrict__ d_n, int max_n, uint64_t seed, uint64_t counter,
-                                   float4 *__restrict__ out, uint32_t *__restrict__ out_src) {
+                                   float4 *__restrict__ out, float4 *__restrict__ out_lo, uint32_t *__restrict__ out_src) {
     const int n = *d_n;
     const bool active = n > max_n;
     const Perm perm = perm_make(seed, counter, (uint32_t) max(n, 1));
@@ -312,6 +321,7 @@ __global__ void k_truncate_shuffle(const float4 *__restrict__ in, const uint32_t
         const uint32_t d = active ? perm_apply(perm, (uint32_t) i) : (uint32_t) i;
         if (!active || (int) d < max_n) {
             out[d] = in[i];
+            if (in_lo) out_lo[d] = in_lo[i];
             out_src[d] = in_src[i];
         }
     }
@@ -320,29 +330,28 @@ __global__ void k_clamp_count(int *d_n, int max_n) {
     if (*d_n > max_n) *d_n = max_n;
 }
 // world = ContinuousTransform(raw, begin, end, alpha) for every point (odometry.cpp:463-486)
-__global__ void k_transform_points(const float4 *__restrict__ pts, const int *__restrict__ d_n, Q4 qb, V3 tb, Q4 qe,
-                                   V3 te, SlerpConsts sc, double *__restrict__ world) {
+__global__ void k_transform_points(const float4 *__restrict__ pts, const float4 *__restrict__ lo, const int *__restrict__ d_n,
+                                   Q4 qb, V3 tb, Q4 qe, V3 te, SlerpConsts sc, double *__restrict__ world) {
     const int n = *d_n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = pts[i];
+        const RawPoint p = load_raw(pts, lo, i);
         // acos / 1/sin(theta) of the pose pair are hoisted (sc): two sin per point instead of acos + three sin
-        const V3 w = ct_transform_c(qb, tb, qe, te, (double) p.w, V3{(double) p.x, (double) p.y, (double) p.z}, sc);
+        const V3 w = ct_transform_c(qb, tb, qe, te, p.alpha, V3{p.x, p.y, p.z}, sc);
         world[3 * i] = w.x; world[3 * i + 1] = w.y; world[3 * i + 2] = w.z;
     }
 }
 
 // DistortFrame (odometry.cpp:161-168): raw <- end^-1 * (Interpolate(begin, end, t) * raw), in place (alpha kept)
-__global__ void k_distort_frame(float4 *__restrict__ pts, const int *__restrict__ d_n, Q4 qb, V3 tb, Q4 qe, V3 te,
-                                SlerpConsts sc) {
+__global__ void k_distort_frame(float4 *__restrict__ pts, float4 *__restrict__ lo, int lo_valid,
+                                const int *__restrict__ d_n, Q4 qb, V3 tb, Q4 qe, V3 te, SlerpConsts sc) {
     const int n = *d_n;
     const Q4 qi = qinverse(qe);
     const V3 ti = (-1.0) * qrot(qnormalized(qi), te);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 p = pts[i];
-        const V3 w = ct_transform_c(qb, tb, qe, te, (double) p.w, V3{(double) p.x, (double) p.y, (double) p.z}, sc);
+        const RawPoint p = load_raw(pts, lo_valid ? lo : nullptr, i);
+        const V3 w = ct_transform_c(qb, tb, qe, te, p.alpha, V3{p.x, p.y, p.z}, sc);
         const V3 r = qrot(qnormalized(qi), w) + ti;
-        p.x = (float) r.x; p.y = (float) r.y; p.z = (float) r.z;
-        pts[i] = p;
+        store_raw(pts, lo, i, r.x, r.y, r.z, p.alpha);   // the distorted point is not float32-representable: hi + lo
     }
 }
 
@@ -379,6 +388,8 @@ FramePipeline::FramePipeline(size_t max_points, cudaStream_t stream) : stream_(s
 FramePipeline::~FramePipeline() {
     cudaFreeHost(h_stage_); cudaFreeHost(h_counts_);
     cudaFree(d_raw_); cudaFree(d_frame_); cudaFree(d_keypoints_); cudaFree(d_tmp_points_);
+    cudaFreeHost(h_stage_lo_);
+    cudaFree(d_raw_lo_); cudaFree(d_frame_lo_); cudaFree(d_kp_lo_); cudaFree(d_tmp_lo_);
     cudaFree(d_frame_src_); cudaFree(d_kp_src_); cudaFree(d_tmp_src_);
     cudaFree(d_grid_); cudaFree(d_slot_of_); cudaFree(d_tile_count_); cudaFree(d_src_);
     cudaFree(d_counts_); cudaFree(d_frame_world_); cudaFree(d_all_world_); cudaFree(d_adaptive_);
@@ -387,8 +398,25 @@ FramePipeline::~FramePipeline() {
 
 int FramePipeline::Blocks(size_t n) const { return (int) std::max<size_t>(1, std::min<size_t>((n + 255) / 256, 148 * 8)); }
 
+void FramePipeline::EnsureLo() {
+    if (d_raw_lo_) return;
+    CT_CUDA_CHECK(cudaMallocHost(&h_stage_lo_, sizeof(float4) * max_points_));
+    CT_CUDA_CHECK(cudaMalloc(&d_raw_lo_, sizeof(float4) * max_points_));
+    CT_CUDA_CHECK(cudaMalloc(&d_frame_lo_, sizeof(float4) * max_points_));
+    CT_CUDA_CHECK(cudaMalloc(&d_kp_lo_, sizeof(float4) * max_points_));
+    CT_CUDA_CHECK(cudaMalloc(&d_tmp_lo_, sizeof(float4) * max_points_));
+}
+
+void FramePipeline::UploadLo(size_t n) {
+    EnsureLo();
+    CT_CUDA_CHECK(cudaMemcpyAsync(d_raw_lo_, h_stage_lo_, sizeof(float4) * n, cudaMemcpyHostToDevice, stream_));
+    raw_lo_ = true;
+    h2d_bytes_ += sizeof(float4) * n;
+}
+
 void FramePipeline::Upload(size_t n) {
     if (n > max_points_) throw CapacityError("scan has more points than max_points_per_frame");
+    raw_lo_ = frame_lo_ = distorted_ = false;
     n_ = n;
     h_counts_[0] = (int) n;
     CT_CUDA_CHECK(cudaMemcpyAsync(d_raw_, h_stage_, sizeof(float4) * n, cudaMemcpyHostToDevice, stream_));
@@ -398,6 +426,7 @@ void FramePipeline::Upload(size_t n) {
 
 void FramePipeline::UploadBegin(size_t n) {
     if (n > max_points_) throw CapacityError("scan has more points than max_points_per_frame");
+    raw_lo_ = frame_lo_ = distorted_ = false;
     n_ = n;
     h_counts_[0] = (int) n;
     CT_CUDA_CHECK(cudaMemcpyAsync(d_counts_, h_counts_, sizeof(int), cudaMemcpyHostToDevice, stream_));
@@ -408,19 +437,26 @@ void FramePipeline::UploadRange(size_t begin, size_t end) {
     CT_CUDA_CHECK(cudaMemcpyAsync(d_raw_ + begin, h_stage_ + begin, sizeof(float4) * (end - begin), cudaMemcpyHostToDevice, stream_));
 }
 
-void FramePipeline::UploadFromDevice(const float4 *d_src, size_t n) {
+void FramePipeline::UploadFromDevice(const float4 *d_src, const float4 *d_src_lo, size_t n) {
     if (n > max_points_) throw CapacityError("scan has more points than max_points_per_frame");
+    raw_lo_ = frame_lo_ = distorted_ = false;
     n_ = n;
     h_counts_[0] = (int) n;
     CT_CUDA_CHECK(cudaMemcpyAsync(d_raw_, d_src, sizeof(float4) * n, cudaMemcpyDeviceToDevice, stream_));
+    if (d_src_lo) {
+        EnsureLo();
+        CT_CUDA_CHECK(cudaMemcpyAsync(d_raw_lo_, d_src_lo, sizeof(float4) * n, cudaMemcpyDeviceToDevice, stream_));
+        raw_lo_ = true;
+    }
     CT_CUDA_CHECK(cudaMemcpyAsync(d_counts_, h_counts_, sizeof(int), cudaMemcpyHostToDevice, stream_));
     h2d_bytes_ = sizeof(int);
 }
 
-void FramePipeline::GridSelect(const float4 *in, const uint32_t *in_src, const int *d_n_in, size_t n_upper,
-                               double voxel_size, int use_perm1, uint64_t seed, uint64_t c1, int use_perm2,
-                               uint64_t c2, int override_alpha, float alpha_value, float4 *out, uint32_t *out_src,
-                               int *d_n_out) {
+void FramePipeline::GridSelect(const float4 *in, const float4 *in_lo, const uint32_t *in_src, const int *d_n_in,
+                               size_t n_upper, double voxel_size, int use_perm1, uint64_t seed, uint64_t c1,
+                               int use_perm2, uint64_t c2, int override_alpha, float alpha_value, float4 *out,
+                               float4 *out_lo, uint32_t *out_src, int *d_n_out) {
+    if (!in_lo) out_lo = nullptr;
     // scratch hash grid: only the prefix that can be touched is cleared; keys and vals are adjacent → one memset
     const uint32_t cap = std::max<uint32_t>(NextPow2(2 * n_upper), 1024);
     unsigned long long *keys = d_grid_, *vals = d_grid_ + cap;
@@ -429,17 +465,19 @@ void FramePipeline::GridSelect(const float4 *in, const uint32_t *in_src, const i
     const size_t num_tiles = (n_upper + kTile - 1) / kTile;
     CT_CUDA_CHECK(cudaMemsetAsync(d_tile_count_, 0, sizeof(uint32_t) * (kMaxTiles + n_upper), stream_));
     const int blocks = Blocks(n_upper);
-    k_grid_claim<<<blocks, 256, 0, stream_>>>(in, d_n_in, voxel_size, use_perm1, seed, c1, keys, vals, cap - 1, d_slot_of_);
+    k_grid_claim<<<blocks, 256, 0, stream_>>>(in, in_lo, d_n_in, voxel_size, use_perm1, seed, c1, keys, vals, cap - 1, d_slot_of_);
     k_grid_mark<<<blocks, 256, 0, stream_>>>(d_n_in, use_perm1, seed, c1, vals, d_slot_of_, d_flags_, d_src_, d_tile_count_);
     k_grid_emit<<<(int) std::max<size_t>(1, num_tiles), kTileThreads, 0, stream_>>>(
-        in, in_src, d_n_in, d_flags_, d_src_, d_tile_count_, use_perm2, seed, c2, override_alpha, alpha_value, out,
-        out_src, d_n_out);
+        in, in_lo, in_src, d_n_in, d_flags_, d_src_, d_tile_count_, use_perm2, seed, c2, override_alpha, alpha_value, out,
+        out_lo, out_src, d_n_out);
     launches_ += 3;
     CT_CUDA_CHECK(cudaGetLastError());
 }
 
-void FramePipeline::AdaptiveSelect(const cticp_adaptive_options &o, const float4 *in, const uint32_t *in_src,
-                                   const int *d_n_in, size_t n_upper, float4 *out, uint32_t *out_src, int *d_n_out) {
+void FramePipeline::AdaptiveSelect(const cticp_adaptive_options &o, const float4 *in, const float4 *in_lo,
+                                   const uint32_t *in_src, const int *d_n_in, size_t n_upper, float4 *out,
+                                   float4 *out_lo, uint32_t *out_src, int *d_n_out) {
+    if (!in_lo) out_lo = nullptr;
     if (o.num_points_per_voxel != 1) throw std::invalid_argument("adaptive sampling: only num_points_per_voxel == 1 is built");
     if (o.num_bands < 2 || o.num_bands > CTICP_MAX_ADAPTIVE_BANDS) throw std::invalid_argument("adaptive sampling: num_bands");
     AdaptiveBands B;
@@ -463,11 +501,11 @@ void FramePipeline::AdaptiveSelect(const cticp_adaptive_options &o, const float4
     CT_CUDA_CHECK(cudaMemsetAsync(tile_count, 0, sizeof(uint32_t) * (kMaxTiles + positions), stream_));
     const int blocks = Blocks(n_upper);
     int *d_positions = d_counts_ + 3;
-    k_adaptive_claim<<<blocks, 256, 0, stream_>>>(in, d_n_in, B, keys, vals, cap - 1, d_slot_of_, d_positions);
-    k_adaptive_mark<<<blocks, 256, 0, stream_>>>(in, d_n_in, B, vals, d_slot_of_, flags, src, tile_count);
+    k_adaptive_claim<<<blocks, 256, 0, stream_>>>(in, in_lo, d_n_in, B, keys, vals, cap - 1, d_slot_of_, d_positions);
+    k_adaptive_mark<<<blocks, 256, 0, stream_>>>(in, in_lo, d_n_in, B, vals, d_slot_of_, flags, src, tile_count);
     const size_t num_tiles = (positions + kTile - 1) / kTile;
     k_grid_emit<<<(int) std::min<size_t>(std::max<size_t>(1, num_tiles), 1184), kTileThreads, 0, stream_>>>(
-        in, in_src, d_positions, flags, src, tile_count, 0, 0, 0, 0, 0.f, out, out_src, d_n_out);
+        in, in_lo, in_src, d_positions, flags, src, tile_count, 0, 0, 0, 0, 0.f, out, out_lo, out_src, d_n_out);
     launches_ += 3;
     if (o.max_num_points > 0) {   // `indices.size() > kMaxNumPoints` lets max + 1 through (:96-105)
         k_clamp_count<<<1, 1, 0, stream_>>>(d_n_out, o.max_num_points + 1);
@@ -492,6 +530,9 @@ void FramePipeline::SampleFused(double voxel_size, double sample_voxel_size, uin
     }
     FusedSampleArgs a;
     a.raw = d_raw_;
+    a.raw_lo = d_raw_lo();
+    a.frame_lo = d_frame_lo_; a.kp_lo = d_kp_lo_;
+    frame_lo_ = raw_lo_;
     a.counts = d_counts_;
     a.voxel1 = voxel_size;
     a.voxel2 = sample_voxel_size;
@@ -512,28 +553,32 @@ void FramePipeline::SampleFused(double voxel_size, double sample_voxel_size, uin
 
 void FramePipeline::SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2,
                                    bool override_alpha, float alpha_value) {
-    GridSelect(d_raw_, nullptr, d_counts_ + 0, n_, voxel_size, 1, seed, counter1, 1, counter2, override_alpha ? 1 : 0,
-               alpha_value, d_frame_, d_frame_src_, d_counts_ + 1);
+    GridSelect(d_raw_, d_raw_lo(), nullptr, d_counts_ + 0, n_, voxel_size, 1, seed, counter1, 1, counter2,
+               override_alpha ? 1 : 0, alpha_value, d_frame_, d_frame_lo_, d_frame_src_, d_counts_ + 1);
+    frame_lo_ = raw_lo_;
 }
 
 void FramePipeline::SampleKeypoints(int sampling, double sample_voxel_size, int max_num_keypoints, uint64_t seed,
                                     uint64_t counter, const cticp_adaptive_options *adaptive) {
     if (sampling == CTICP_SAMPLING_ADAPTIVE) {
         if (!adaptive) throw std::invalid_argument("adaptive options missing");
-        AdaptiveSelect(*adaptive, d_frame_, d_frame_src_, d_counts_ + 1, n_, d_keypoints_, d_kp_src_, d_counts_ + 2);
+        AdaptiveSelect(*adaptive, d_frame_, d_frame_lo(), d_frame_src_, d_counts_ + 1, n_, d_keypoints_, d_kp_lo_, d_kp_src_,
+                       d_counts_ + 2);
     } else if (sampling == CTICP_SAMPLING_GRID) {
-        GridSelect(d_frame_, d_frame_src_, d_counts_ + 1, n_, sample_voxel_size, 0, 0, 0, 0, 0, 0, 0.f, d_keypoints_,
-                   d_kp_src_, d_counts_ + 2);
+        GridSelect(d_frame_, d_frame_lo(), d_frame_src_, d_counts_ + 1, n_, sample_voxel_size, 0, 0, 0, 0, 0, 0, 0.f,
+                   d_keypoints_, d_kp_lo_, d_kp_src_, d_counts_ + 2);
     } else {
-        k_copy_points<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_frame_src_, d_counts_ + 1, d_keypoints_, d_kp_src_,
-                                                       d_counts_ + 2);
+        k_copy_points<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_frame_lo(), d_frame_src_, d_counts_ + 1, d_keypoints_,
+                                                       d_kp_lo_, d_kp_src_, d_counts_ + 2);
         launches_ += 1;
     }
     if (max_num_keypoints > 0) {
-        k_truncate_shuffle<<<Blocks(n_), 256, 0, stream_>>>(d_keypoints_, d_kp_src_, d_counts_ + 2, max_num_keypoints,
-                                                            seed, counter, d_tmp_points_, d_tmp_src_);
+        k_truncate_shuffle<<<Blocks(n_), 256, 0, stream_>>>(d_keypoints_, d_keypoints_lo(), d_kp_src_, d_counts_ + 2,
+                                                            max_num_keypoints, seed, counter, d_tmp_points_, d_tmp_lo_,
+                                                            d_tmp_src_);
         k_clamp_count<<<1, 1, 0, stream_>>>(d_counts_ + 2, max_num_keypoints);
         std::swap(d_keypoints_, d_tmp_points_);
+        std::swap(d_kp_lo_, d_tmp_lo_);
         std::swap(d_kp_src_, d_tmp_src_);
         launches_ += 2;
     }
@@ -545,13 +590,16 @@ void FramePipeline::QueueCountsReadback() {
 }
 
 void FramePipeline::DistortFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te) {
-    k_distort_frame<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_counts_ + 1, qb, tb, qe, te, slerp_consts(qb, qe));
+    EnsureLo();
+    k_distort_frame<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_frame_lo_, frame_lo_ ? 1 : 0, d_counts_ + 1, qb, tb, qe, te,
+                                                     slerp_consts(qb, qe));
+    frame_lo_ = distorted_ = true;
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
 }
 
 void FramePipeline::TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te) {
-    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_counts_ + 1, qb, tb, qe, te, slerp_consts(qb, qe), d_frame_world_);
+    k_transform_points<<<Blocks(n_), 256, 0, stream_>>>(d_frame_, d_frame_lo(), d_counts_ + 1, qb, tb, qe, te, slerp_consts(qb, qe), d_frame_world_);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
 }
@@ -561,14 +609,14 @@ void FramePipeline::EnsureAllWorld() {
 }
 void FramePipeline::TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te, cudaStream_t stream) {
     EnsureAllWorld();
-    k_transform_points<<<Blocks(n_), 256, 0, stream ? stream : stream_>>>(d_raw_, d_counts_ + 0, qb, tb, qe, te, slerp_consts(qb, qe), d_all_world_);
+    k_transform_points<<<Blocks(n_), 256, 0, stream ? stream : stream_>>>(d_raw_, d_raw_lo(), d_counts_ + 0, qb, tb, qe, te, slerp_consts(qb, qe), d_all_world_);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
 }
 
-void FramePipeline::TransformInto(const float4 *pts, const int *d_n, const Q4 &qb, const V3 &tb, const Q4 &qe,
-                                  const V3 &te, double *d_world, cudaStream_t stream) {
-    k_transform_points<<<Blocks(n_), 256, 0, stream ? stream : stream_>>>(pts, d_n, qb, tb, qe, te, slerp_consts(qb, qe), d_world);
+void FramePipeline::TransformInto(const float4 *pts, const float4 *lo, const int *d_n, const Q4 &qb, const V3 &tb,
+                                  const Q4 &qe, const V3 &te, double *d_world, cudaStream_t stream) {
+    k_transform_points<<<Blocks(n_), 256, 0, stream ? stream : stream_>>>(pts, lo, d_n, qb, tb, qe, te, slerp_consts(qb, qe), d_world);
     launches_ += 1;
     CT_CUDA_CHECK(cudaGetLastError());
 }

@@ -19,13 +19,26 @@ public:
 
     // pinned staging buffer the host packs (x, y, z, alpha) into, then Upload(n) enqueues the H2D copy
     float4 *Staging() { return h_stage_; }
+    // residual planes (value - (double)(float)value, see load_raw in se3.cuh) — allocated on first use: float32 scans,
+    // what LiDAR drivers emit, never need them. raw_lo: the scan as uploaded; frame_lo: the sub-sampled frame and the
+    // keypoints drawn from it (also set by DistortFrame, whose output is not float32-representable).
+    void EnsureLo();
+    float4 *StagingLo() { EnsureLo(); return h_stage_lo_; }
+    const float4 *StagingLoIfAny() const { return raw_lo_ ? h_stage_lo_ : nullptr; }
+    void UploadLo(size_t n);                                  // after Upload*/UploadBegin of the same scan
+    bool raw_has_lo() const { return raw_lo_; }
+    bool frame_has_lo() const { return frame_lo_; }
+    bool frame_distorted() const { return distorted_; }
+    const float4 *d_raw_lo() const { return raw_lo_ ? d_raw_lo_ : nullptr; }
+    const float4 *d_frame_lo() const { return frame_lo_ ? d_frame_lo_ : nullptr; }
+    const float4 *d_keypoints_lo() const { return frame_lo_ ? d_kp_lo_ : nullptr; }
     size_t MaxPoints() const { return max_points_; }
     void Upload(size_t n);
     // the same copy in pieces, so that it can start while the tail of the scan is still being packed:
     // UploadBegin(n), then UploadRange over a partition of [0, n) in any order
     void UploadBegin(size_t n);
     void UploadRange(size_t begin, size_t end);
-    void UploadFromDevice(const float4 *d_src, size_t n);   // scan already packed and resident in HBM
+    void UploadFromDevice(const float4 *d_src, const float4 *d_src_lo, size_t n);   // scan already packed and resident in HBM
 
     // Odometry::InitializeFrame: shuffle → sub_sample_frame → (frames 0,1: timestamp := end) → shuffle
     void SubSampleFrame(double voxel_size, uint64_t seed, uint64_t counter1, uint64_t counter2, bool override_alpha,
@@ -37,16 +50,16 @@ public:
     void SampleKeypoints(int sampling, double sample_voxel_size, int max_num_keypoints, uint64_t seed, uint64_t counter,
                          const cticp_adaptive_options *adaptive = nullptr);
     // AdaptiveSamplePointsInGrid (include/ct_icp/algorithm/sampling.h:55-110)
-    void AdaptiveSelect(const cticp_adaptive_options &o, const float4 *in, const uint32_t *in_src, const int *d_n_in,
-                        size_t n_upper, float4 *out, uint32_t *out_src, int *d_n_out);
+    void AdaptiveSelect(const cticp_adaptive_options &o, const float4 *in, const float4 *in_lo, const uint32_t *in_src,
+                        const int *d_n_in, size_t n_upper, float4 *out, float4 *out_lo, uint32_t *out_src, int *d_n_out);
     // DistortFrame (odometry.cpp:161-168) on the sub-sampled frame, in place
     void DistortFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
     // world points of the sub-sampled frame / of every input point with the final pose pair
     void TransformFrame(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te);
     // (stream: nullptr = the pipeline's own; the egress of the summary vectors runs on a second stream)
     void TransformAll(const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te, cudaStream_t stream = nullptr);
-    void TransformInto(const float4 *pts, const int *d_n, const Q4 &qb, const V3 &tb, const Q4 &qe, const V3 &te,
-                       double *d_world, cudaStream_t stream = nullptr);
+    void TransformInto(const float4 *pts, const float4 *lo, const int *d_n, const Q4 &qb, const V3 &tb, const Q4 &qe,
+                       const V3 &te, double *d_world, cudaStream_t stream = nullptr);
     void EnsureAllWorld();
 
     void QueueCountsReadback();   // h_counts()[0..2] = N, F, K after the next stream sync
@@ -68,9 +81,10 @@ public:
     int launches() const { return launches_; }
 
     // generic "first-seen per voxel" selection (also behind cticp_grid_sample_indices)
-    void GridSelect(const float4 *in, const uint32_t *in_src, const int *d_n_in, size_t n_upper, double voxel_size,
-                    int use_perm1, uint64_t seed, uint64_t c1, int use_perm2, uint64_t c2, int override_alpha,
-                    float alpha_value, float4 *out, uint32_t *out_src, int *d_n_out);
+    void GridSelect(const float4 *in, const float4 *in_lo, const uint32_t *in_src, const int *d_n_in, size_t n_upper,
+                    double voxel_size, int use_perm1, uint64_t seed, uint64_t c1, int use_perm2, uint64_t c2,
+                    int override_alpha, float alpha_value, float4 *out, float4 *out_lo, uint32_t *out_src, int *d_n_out);
+    float4 *d_frame_lo_mut() { EnsureLo(); return d_frame_lo_; }
     float4 *d_raw_mut() { return d_raw_; }
     double *d_frame_world_mut() { return d_frame_world_; }
     float4 *d_frame_mut() { return d_frame_; }
@@ -85,6 +99,8 @@ private:
     float4 *h_stage_ = nullptr;
     int *h_counts_ = nullptr;
     float4 *d_raw_ = nullptr, *d_frame_ = nullptr, *d_keypoints_ = nullptr, *d_tmp_points_ = nullptr;
+    float4 *h_stage_lo_ = nullptr, *d_raw_lo_ = nullptr, *d_frame_lo_ = nullptr, *d_kp_lo_ = nullptr, *d_tmp_lo_ = nullptr;
+    bool raw_lo_ = false, frame_lo_ = false, distorted_ = false;
     uint32_t *d_frame_src_ = nullptr, *d_kp_src_ = nullptr, *d_tmp_src_ = nullptr;
     unsigned long long *d_grid_ = nullptr;
     int *d_slot_of_ = nullptr;

@@ -65,6 +65,7 @@ struct GnParams {
     int shard_rank, shard_world;   // keypoint sharding (multi-GPU); 0/1 when single
     int debug_flags;               // profiling only (env CTICP_DEBUG_FLAGS): 1 = skip the solve, 2 = skip the gather work
     double bucket_scale;           // 32 / radius^2: d2 → histogram bucket of the k-nearest selection (gather_select.cuh)
+    const float4 *kp_lo;           // residual plane of the keypoints (nullptr: float32-representable; load_raw, se3.cuh)
     int rigid_first;               // motion compensation NONE / CONSTANT_VELOCITY: the keypoints enter the first iteration
                                    // transformed by the END pose alone (TransformPoint, odometry.cpp:171-184), afterwards GN
                                    // interpolates like always (ct_icp.cpp:964-966)
@@ -98,6 +99,8 @@ public:
     void RadiusSearch(const DeviceMap &map, const double *d_queries, const double *d_radiuses, size_t n, int kmax,
                       const double *sensor_location, double *d_out_points, int *d_out_counts);
 
+    // residual plane of the keypoint array the next Enqueue*/NormalEquations calls are given (nullptr: none; se3.cuh load_raw)
+    void set_keypoints_lo(const float4 *d_lo) { kp_lo_ = d_lo; }
     int launches() const { return launches_; }
     float gather_ms() const { return gather_ms_; }
     void reset_timing() { gather_ms_ = 0.f; gather_launches_ = 0; }
@@ -128,6 +131,7 @@ private:
     GnParams MakeParams(const DeviceMap &map, const cticp_icp_options &opt) const;
 
     cudaStream_t stream_;
+    const float4 *kp_lo_ = nullptr;
     double *d_partials_ = nullptr;
     int partial_blocks_ = 0;
     double *d_sys_ = nullptr;      // 12*12 + 12 + 4 debug output of the solve kernel

@@ -207,10 +207,10 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
         V3 p{0, 0, 0};
         int kx = 0, ky = 0, kz = 0;
         if (lane < wt) {
-            const float4 kraw = __ldg(keypoints + t0 + lane);   // raw xyz (sensor frame) + alpha timestamp
-            const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+            const RawPoint kraw = load_raw(keypoints, P.kp_lo, t0 + lane);   // raw xyz (sensor frame) + alpha timestamp
+            const V3 raw{kraw.x, kraw.y, kraw.z};
             p = rigid ? qrot(qnormalized(pose.qe), raw) + pose.te
-                      : ct_transform_c(pose.qb, pose.tb, pose.qe, pose.te, (double) kraw.w, raw, pose.sc);
+                      : ct_transform_c(pose.qb, pose.tb, pose.qe, pose.te, kraw.alpha, raw, pose.sc);
             kx = voxel_coord(p.x, G.L.res);
             ky = voxel_coord(p.y, G.L.res);
             kz = voxel_coord(p.z, G.L.res);
@@ -258,10 +258,10 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
                 if (fabs(dist_to_plane) < P.max_dist_to_plane) {              // :803
                     const V3 nw = weight * normal;
                     const double scalar = dot(nw, diff);
-                    const float4 kraw = __ldg(keypoints + t0 + lane);
-                    const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+                    const RawPoint kraw = load_raw(keypoints, P.kp_lo, t0 + lane);
+                    const V3 raw{kraw.x, kraw.y, kraw.z};
                     const V3 ob = qrot(pose.qb, raw), oe = qrot(pose.qe, raw);   // :813-816
-                    const double a = (double) kraw.w, am = 1.0 - a;
+                    const double a = kraw.alpha, am = 1.0 - a;
                     const V3 cb = cross(ob, nw), ce = cross(oe, nw);
                     double *u = T.rows[lane];
                     u[0] = am * cb.x; u[1] = am * cb.y; u[2] = am * cb.z;
@@ -730,6 +730,7 @@ GnParams IcpSolver::MakeParams(const DeviceMap &map, const cticp_icp_options &op
     P.debug_flags = 0;
     if (const char *e = getenv("CTICP_DEBUG_FLAGS")) P.debug_flags = atoi(e);
     P.bucket_scale = (double) kSelBuckets / (P.radius * P.radius);
+    P.kp_lo = kp_lo_;
     P.rigid_first = (opt.parametrization == CTICP_PARAM_SIMPLE && !opt.point_to_plane_with_distortion) ? 1 : 0;
     return P;
 }

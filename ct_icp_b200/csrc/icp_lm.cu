@@ -54,6 +54,7 @@ struct LmParams {
     // POSE_PARAMETRIZATION SIMPLE (motion compensation NONE / CONSTANT_VELOCITY / ITERATIVE, odometry.cpp:704-724): only the
     // end pose is optimised; `distortion` = point_to_plane_with_distortion (ITERATIVE)
     int simple, distortion;
+    const float4 *kp_lo;   // residual plane of the keypoints (nullptr: float32-representable; load_raw, se3.cuh)
     // solver ROBUST (ct_icp.cpp:1180-1370)
     int robust, use_lines, use_barycenter;
     double threshold_linearity, threshold_planarity, outlier_distance, weight_neighborhood;
@@ -137,18 +138,17 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
         const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
         // ---- lane j: transform_keypoints() (ct_icp.cpp:516-531) and, for the distance-based strategy, this
         // keypoint's radius → map level + stencil (neighborhood_strategy.h:121-126, map.h:416-432)
-        float4 kraw = make_float4(0.f, 0.f, 0.f, 0.f);
         V3 p{0, 0, 0};
         int kx = 0, ky = 0, kz = 0, lvl = 0, rr = G0.r;
         double radius2 = G0.radius2, scale = P.bucket_scale;
         if (lane < wt) {
-            kraw = __ldg(keypoints + t0 + lane);
-            const V3 raw{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+            const RawPoint kraw = load_raw(keypoints, P.kp_lo, t0 + lane);
+            const V3 raw{kraw.x, kraw.y, kraw.z};
             // transform_keypoints (:516-531): interpolated pose unless SIMPLE without distortion (then the end pose)
             if (P.simple && !P.distortion)
                 p = qrot(qnormalized(qe), raw) + te;
             else
-                p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, raw, sc);
+                p = ct_transform_c(qb, tb, qe, te, kraw.alpha, raw, sc);
             double res = G0.L.res;
             if (kDB) {
                 const double range = sqrt(raw.x * raw.x + raw.y * raw.y + raw.z * raw.z);
@@ -206,11 +206,12 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
                 rb.ref[0] = p.x + nd.far_rel.x; rb.ref[1] = p.y + nd.far_rel.y; rb.ref[2] = p.z + nd.far_rel.z;   // points[0]
                 rb.normal[0] = nd.normal.x; rb.normal[1] = nd.normal.y; rb.normal[2] = nd.normal.z;
                 rb.weight = weight;
-                rb.alpha = (double) kraw.w;
-                V3 rawc{(double) kraw.x, (double) kraw.y, (double) kraw.z};
+                const RawPoint kraw = load_raw(keypoints, P.kp_lo, t0 + lane);
+                rb.alpha = kraw.alpha;
+                V3 rawc{kraw.x, kraw.y, kraw.z};
                 if (P.simple && P.distortion) {
                     // ICPOptimizationBuilder::DistortFrame (:198-215): the raw point in the frame of the END pose
-                    const V3 w = ct_transform_c(qb, tb, qe, te, (double) kraw.w, rawc, sc);
+                    const V3 w = ct_transform_c(qb, tb, qe, te, kraw.alpha, rawc, sc);
                     const Q4 qi = qinverse(qe);
                     rawc = qrot(qi, w) + (-1.0) * qrot(qi, te);
                 }
@@ -277,13 +278,11 @@ __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmPara
     const int need = P.kmin;   // :1238 (kmin >= 5 is enforced by the host, so the neighborhood is always describable)
     for (int t0 = kp_lo + warp_global * W; t0 < kp_hi; t0 += warps_total * W) {
         const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
-        float4 kraw = make_float4(0.f, 0.f, 0.f, 0.f);
         V3 p{0, 0, 0};
         int kx = 0, ky = 0, kz = 0;
         if (lane < wt) {
-            kraw = __ldg(keypoints + t0 + lane);
-            p = ct_transform_c(qb, tb, qe, te, (double) kraw.w, V3{(double) kraw.x, (double) kraw.y, (double) kraw.z},
-                               sc);   // TransformKeyPoints, :1373-1393
+            const RawPoint kraw = load_raw(keypoints, P.kp_lo, t0 + lane);
+            p = ct_transform_c(qb, tb, qe, te, kraw.alpha, V3{kraw.x, kraw.y, kraw.z}, sc);   // TransformKeyPoints, :1373-1393
             kx = voxel_coord(p.x, G.L.res);
             ky = voxel_coord(p.y, G.L.res);
             kz = voxel_coord(p.z, G.L.res);
@@ -337,7 +336,8 @@ __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmPara
                     const V3 dir = kind == kResLine ? nd.line : nd.normal;
                     rb.normal[0] = dir.x; rb.normal[1] = dir.y; rb.normal[2] = dir.z;
                     rb.weight = weight;
-                    rb.alpha = (double) kraw.w;
+                    const RawPoint kraw = load_raw(keypoints, P.kp_lo, t0 + lane);
+                    rb.alpha = kraw.alpha;
                     rb.raw[0] = kraw.x; rb.raw[1] = kraw.y; rb.raw[2] = kraw.z;
                     rb.valid = 1;
                     rb.kind = kind;
@@ -1194,6 +1194,7 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     map.SearchParams(map.Options().default_radius, &P.level, &P.r);
     P.radius = map.Options().default_radius;
     P.bucket_scale = (double) kSelBuckets / (P.radius * P.radius);
+    P.kp_lo = kp_lo_;
     P.kmax = kmax;
     P.kmin = opt.min_number_neighbors;            // ct_icp.cpp:574
     P.lambda_weight = std::abs(opt.weight_alpha) / sum;

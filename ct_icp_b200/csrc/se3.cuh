@@ -188,6 +188,30 @@ CT_HD V3 ct_transform_c(Q4 qb, V3 tb, Q4 qe, V3 te, double alpha, V3 raw, const 
     V3 t = (1.0 - alpha) * tb + alpha * te;
     return qrot(q, raw) + t;
 }
+#ifdef __CUDACC__
+// A scan point lives on the device as fp32 (x, y, z, alpha) — what LiDAR drivers emit — plus an OPTIONAL residual plane
+// `lo` = value - (double)(float)value (also fp32): hi + lo reproduces an fp64 input to ~2^-48 relative, i.e. exactly as far
+// as voxel assignment and the 1e-4 m tolerance are concerned. lo == nullptr: the scan is float32-representable.
+struct RawPoint {
+    double x, y, z, alpha;
+};
+__device__ __forceinline__ RawPoint load_raw(const float4 *hi, const float4 *lo, size_t i) {
+    const float4 h = hi[i];
+    RawPoint r{(double) h.x, (double) h.y, (double) h.z, (double) h.w};
+    if (lo) {
+        const float4 l = lo[i];
+        r.x += (double) l.x; r.y += (double) l.y; r.z += (double) l.z; r.alpha += (double) l.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void store_raw(float4 *hi, float4 *lo, size_t i, double x, double y, double z, double alpha) {
+    const float4 h = make_float4((float) x, (float) y, (float) z, (float) alpha);
+    hi[i] = h;
+    if (lo) lo[i] = make_float4((float) (x - (double) h.x), (float) (y - (double) h.y), (float) (z - (double) h.z),
+                                (float) (alpha - (double) h.w));
+}
+#endif
+
 // slam::AngularDistance (types.h:141-156), degrees; returns NaN when the CHECK would fire
 CT_HD double angular_distance_deg(Q4 a, Q4 b) {
     M3 Ra = qtoR(a), Rb = qtoR(b);

@@ -20,14 +20,15 @@
  *     fp32 — what LiDAR drivers emit (KITTI .bin, PointCloud2 FLOAT32) — and all
  *     geometry is evaluated in fp64 from there. The reference reads the scan
  *     through double-converting views (src/ct_icp/odometry.cpp:335-336), so for
- *     FLOAT32 sources the two agree exactly. A genuinely fp64 coordinate moves
- *     by at most half an fp32 ulp (<= 4e-6 m at 60 m range) and alpha by <= 6e-8
- *     (<= 1e-6 m at 15 m/s): three orders below the 1e-4 m pose tolerance, but a
- *     point that sits within that distance of a voxel face of the samplers may
- *     fall into the neighbouring voxel, so sample SETS can differ in a few
- *     points (tests/test_gpu_parity_r2.py::test_fp64_scan_coordinates_and_timestamps
- *     bounds both). The timestamps returned in cticp_wpoint records are rebuilt
- *     from alpha (error <= 6e-8 of the sweep duration).
+ *     FLOAT32 sources the two agree exactly. FLOAT64 coordinates that fp32
+ *     cannot hold travel with a second fp32 plane of residuals (value - fp32(value);
+ *     hi + lo reproduces the double to ~2^-48 relative), uploaded only for such
+ *     scans: the samplers then see the same voxel for every point as the
+ *     reference does and the sample sets are identical
+ *     (tests/test_gpu_parity_r2.py::test_fp64_scan_coordinates_and_timestamps).
+ *     With FLOAT32 coordinates and wider timestamps alpha is rounded to fp32
+ *     (<= 6e-8 of the sweep: <= 1e-6 m at 15 m/s); the timestamps returned in
+ *     cticp_wpoint records are rebuilt from alpha.
  *   - multi-GPU (cticp_odometry_enable_sharding): ONE driving thread per rank —
  *     every exchange is a device-side rendezvous that needs all ranks' kernels in
  *     flight at once, so one host thread driving two handles in turn deadlocks

@@ -34,9 +34,9 @@ def _compare(ro, re_, exact_counts=True):
 
 def test_fp64_scan_coordinates_and_timestamps(orc, eng):
     """The reference reads XYZConst<double>() / TimestampsProxy<double>() (odometry.cpp:335-336): nothing says the scan is
-    float32-representable. The engine keeps (x, y, z, alpha) as fp32 on the device (include/cticp.h, "ingest precision"):
-    a coordinate moves by <= 4e-6 m at 60 m range, which can move a point across a voxel boundary of the samplers (the
-    sample SETS may differ in a handful of points), never the pose beyond the 1e-4 bound."""
+    float32-representable. Coordinates that fp32 cannot hold travel as fp32 hi + fp32 lo planes (include/cticp.h, "ingest
+    precision"; se3.cuh load_raw): every point falls into the same sampler voxel as in the reference, so the sample sets —
+    and with them every count — are identical, and the returned raw points are the caller's doubles."""
     rng = np.random.default_rng(99)
     seq = []
     for s in get_sequence("small16", 8):
@@ -45,12 +45,14 @@ def test_fp64_scan_coordinates_and_timestamps(orc, eng):
         assert np.any(xyz.astype(np.float32).astype(np.float64) != xyz)
         seq.append(dict(s, xyz=xyz, t=t))
     _, ro = _run_sequence(orc, seq, init_num_frames=4)
-    _, re_ = _run_sequence(eng, seq, init_num_frames=4)
-    wt, wr = _compare(ro, re_, exact_counts=False)
-    for (so, _), (se, _) in zip(ro, re_):
-        # sample sizes: the same up to the few points that sit within 4e-6 m of a voxel face
-        assert abs(int(so.num_corrected_points) - int(se.num_corrected_points)) <= max(3, so.num_corrected_points // 1000)
-        assert abs(int(so.num_keypoints) - int(se.num_keypoints)) <= max(3, so.num_keypoints // 200)
+    od, re_ = _run_sequence(eng, seq, init_num_frames=4)
+    wt, wr = _compare(ro, re_, exact_counts=True)
+    # the records handed back carry the caller's coordinates (hi + lo), not their fp32 rounding
+    allp = od.all_corrected_points()
+    assert len(allp) == len(seq[-1]["xyz"])
+    assert np.abs(allp["raw"] - seq[-1]["xyz"]).max() < 1e-12
+    kp_e = od.keypoints()
+    assert np.abs(kp_e["raw"].astype(np.float32).astype(np.float64) - kp_e["raw"]).max() > 0   # not rounded to fp32
     print("fp64 scans: worst per-frame pose difference %.3e m, %.3e rad" % (wt, wr))
 
 

@@ -359,10 +359,13 @@ def run_native(eng, D, seq, preroll, W, K, n_roof, with_dropin=True, parity_fram
     if n_roof:
         od.set_gather_timing(True)
         g_ms, g_launch, g_kp, g_pts = 0.0, 0, 0, 0
+        solve_share = []
         for i in range(first + K, first + K + n_roof):
             od.flush_l2(256 << 20)
             sm = od.RegisterStaged(slots[i], seq[i]["frame_idx"])
             t = od.last_timing()
+            if sm.icp_summary.avg_duration_iter > 0:   # clock64 stamps of the solver CTA (k_gn_persistent)
+                solve_share.append(sm.icp_summary.avg_duration_solve / sm.icp_summary.avg_duration_iter)
             g_ms += t.gather_ms
             g_launch += t.gather_launches
             g_kp += t.gather_keypoint_iterations
@@ -378,7 +381,8 @@ def run_native(eng, D, seq, preroll, W, K, n_roof, with_dropin=True, parity_fram
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / g_launch,
                         "us_per_launch": g_ms / g_launch * 1e3, "keypoint_iterations_per_launch": g_kp / g_launch,
                         "us_per_1k_keypoint_iterations": (g_ms * 1e3) / max(g_kp, 1) * 1e3,
-                        "mean_stencil_points": g_pts / max(g_kp, 1), "launches_timed": g_launch}
+                        "mean_stencil_points": g_pts / max(g_kp, 1), "launches_timed": g_launch,
+                        "serial_reduce_and_solve_share": float(np.mean(solve_share)) if solve_share else None}
     out["roofline"] = roofline
     od.clear_staged()
     od.close()

@@ -63,6 +63,16 @@ CT_HD uint32_t hash_key(unsigned long long k) {
 }
 // slam::Voxel::Coordinates (src/SlamCore/types.cxx:13-20): C int() truncation toward zero
 CT_HD int voxel_coord(double p, double res) { return int(p / res); }
+// the same integer from p * (1 / res): the product is within 2 ulp of the quotient, so the truncation can only differ when
+// the quotient is within ~1e-15 relative of an integer — those (and only those) take the division. Three fp64 divisions
+// (~30 dependent instructions each) leave the serial lane-per-keypoint phase of the gathers.
+CT_HD int voxel_coord_rcp(double p, double res, double inv_res) {
+    const double q = p * inv_res;
+    const int k = int(q);
+    const double f = fabs(q - (double) k);
+    const double guard = 1e-12 * (1.0 + fabs(q));
+    return (f < guard || f > 1.0 - guard) ? int(p / res) : k;
+}
 
 #ifdef __CUDACC__
 // Lookup: returns slot index or -1. Linear probing, stops at the first empty slot; tombstones are skipped.

@@ -197,6 +197,7 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
     int W = (span + warps_total - 1) / warps_total;
     W = W < kTileMax ? W : kTileMax;
     const int need = P.kmin > 5 ? P.kmin : 5;   // ct_icp.cpp:769 ; neighborhood.h:227
+    const double inv_res = 1.0 / G.L.res;
     const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
     const int pi0 = c_pair_i[i0], pj0 = c_pair_j[i0], pi1 = c_pair_i[i1], pj1 = c_pair_j[i1];
     const int pi2 = i2 < kAccUsed ? c_pair_i[i2] : 0, pj2 = i2 < kAccUsed ? c_pair_j[i2] : 0;
@@ -211,9 +212,9 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
             const V3 raw{kraw.x, kraw.y, kraw.z};
             p = rigid ? qrot(qnormalized(pose.qe), raw) + pose.te
                       : ct_transform_c(pose.qb, pose.tb, pose.qe, pose.te, kraw.alpha, raw, pose.sc);
-            kx = voxel_coord(p.x, G.L.res);
-            ky = voxel_coord(p.y, G.L.res);
-            kz = voxel_coord(p.z, G.L.res);
+            kx = voxel_coord_rcp(p.x, G.L.res, inv_res);
+            ky = voxel_coord_rcp(p.y, G.L.res, inv_res);
+            kz = voxel_coord_rcp(p.z, G.L.res, inv_res);
         }
         // ---- B
         for (int j = 0; j < wt; ++j) {
@@ -319,6 +320,7 @@ struct GnShared {
     IcpState dummy;
     IcpState state;   // persistent kernel, solver CTA: the registration state lives here; `st` (global) is its published copy
     int flag;
+    int done;         // gather CTAs: the published `done` flag, fetched together with the pose (one memory round trip)
     unsigned long long mbar[kGatherWarps];   // -DCTICP_SEL_BULK: one mbarrier per warp for the bulk copies
 };
 
@@ -493,16 +495,26 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
     long long t_loop = 0, t_solve = 0;
     if (solver_cta && threadIdx.x == 0) t_loop = clock64();
     for (int it = 0; it < num_iters; ++it) {
-        if (__ldcg(&st->done)) break;   // uniform: written before the previous grid barrier
-        if (!solver_cta) {
+        // `done` is uniform over the grid: published before the previous grid barrier (the solver CTA reads its own copy)
+        if (solver_cta) {
+            if (sh.state.done) break;
+        } else {
             GnWarpAcc A;
-            if (threadIdx.x == 0) sh.pose = load_pose(st);   // phases A / C read the pose from shared memory: 34
-            __syncthreads();                                  // registers less to keep live across the gather
+            if (threadIdx.x == 0) {   // phases A / C read the pose from shared memory: 34 registers less to keep live
+                const int done = __ldcg(&st->done);   // issued with the pose loads: one round trip, not two
+                sh.pose = load_pose(st);
+                sh.done = done;
+            }
+            __syncthreads();
+            if (sh.done) break;
             if (!(P.debug_flags & 2)) {
                 const GnPose &pose = sh.pose;
                 const int K = *d_num_keypoints;
-                const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
-                const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+                int lo = 0, hi = K;
+                if (P.shard_world > 1) {   // (64-bit divisions: only when the keypoints are sharded)
+                    lo = (int) ((long long) K * P.shard_rank / P.shard_world);
+                    hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+                }
                 // warp index interleaved over the CTAs: a keypoint set smaller than the grid spreads over all SMs
                 gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gather_ctas + (blockIdx.x - 1),
                                 gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A, bulk_ptr, P.rigid_first && it == 0);

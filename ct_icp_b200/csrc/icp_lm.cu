@@ -276,6 +276,7 @@ __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmPara
     int W = (kp_hi - kp_lo + warps_total - 1) / warps_total;
     W = W < kLmTileMax ? (W < 1 ? 1 : W) : kLmTileMax;
     const int need = P.kmin;   // :1238 (kmin >= 5 is enforced by the host, so the neighborhood is always describable)
+    const double inv_res = 1.0 / G.L.res;
     for (int t0 = kp_lo + warp_global * W; t0 < kp_hi; t0 += warps_total * W) {
         const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
         V3 p{0, 0, 0};
@@ -283,9 +284,9 @@ __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmPara
         if (lane < wt) {
             const RawPoint kraw = load_raw(keypoints, P.kp_lo, t0 + lane);
             p = ct_transform_c(qb, tb, qe, te, kraw.alpha, V3{kraw.x, kraw.y, kraw.z}, sc);   // TransformKeyPoints, :1373-1393
-            kx = voxel_coord(p.x, G.L.res);
-            ky = voxel_coord(p.y, G.L.res);
-            kz = voxel_coord(p.z, G.L.res);
+            kx = voxel_coord_rcp(p.x, G.L.res, inv_res);
+            ky = voxel_coord_rcp(p.y, G.L.res, inv_res);
+            kz = voxel_coord_rcp(p.z, G.L.res, inv_res);
         }
         for (int j = 0; j < wt; ++j) {
             const V3 q{__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j)};

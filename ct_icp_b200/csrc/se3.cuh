@@ -88,11 +88,28 @@ CT_HD SlerpConsts slerp_consts(Q4 a, Q4 b) {
     c.inv_sin = c.linear ? 0.0 : 1.0 / sqrt((1.0 - ad) * (1.0 + ad));
     return c;
 }
+// sin(x) for |x| <= 0.5 by its Taylor series up to x^17 (next term 0.5^19 / 19! = 1.6e-23: below half an ulp): ten
+// dependent FMAs instead of libm's argument reduction. The slerp angle of one sweep is a few degrees at most.
+CT_HD double sin_upto_half(double x) {
+    const double x2 = x * x;
+    double p = 2.8114572543455206e-15;          //  1/17!
+    p = p * x2 - 7.647163731819816e-13;         // -1/15!
+    p = p * x2 + 1.6059043836821613e-10;        //  1/13!
+    p = p * x2 - 2.505210838544172e-8;          // -1/11!
+    p = p * x2 + 2.7557319223985893e-6;         //  1/9!
+    p = p * x2 - 1.984126984126984e-4;          // -1/7!
+    p = p * x2 + 8.333333333333333e-3;          //  1/5!
+    p = p * x2 - 0.16666666666666666;           // -1/3!
+    return x + x * (x2 * p);
+}
 CT_HD Q4 qslerp_c(Q4 a, Q4 b, double t, const SlerpConsts &c) {
     double s0, s1;
     if (c.linear) {
         s0 = 1.0 - t;
         s1 = t;
+    } else if (c.theta <= 0.5) {   // t in [0, 1] for every point of the sweep
+        s0 = sin_upto_half((1.0 - t) * c.theta) * c.inv_sin;
+        s1 = sin_upto_half(t * c.theta) * c.inv_sin;
     } else {
         s0 = sin((1.0 - t) * c.theta) * c.inv_sin;
         s1 = sin(t * c.theta) * c.inv_sin;

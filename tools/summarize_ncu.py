@@ -142,8 +142,46 @@ def digest(raw, src, dst, kernel, kp_iters=None):
     print(json.dumps({k: v for k, v in out.items() if k not in ("metrics", "hottest_instructions")}, indent=1))
 
 
+def lines(src, dst, top=40):
+    """`ncu -i X.ncu-rep --page source --csv --print-source cuda,sass` → where the issue slots and the non-barrier stall
+    samples of the kernel go, per source file and per source line (inlined code is attributed to its own file)."""
+    import collections
+    agg = collections.defaultdict(lambda: [0, 0, 0])   # (file, line) → non-barrier samples, instructions, barrier samples
+    cur, idx = None, None
+    for r in csv.reader(open(src)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+        elif r[0] == "Line No":
+            idx = {n: i for i, n in enumerate(r)}
+        elif idx and r[0] not in ("", "Function Name") and len(r) > 3 and r[2] == "-":
+            a = agg[(cur, int(r[0]))]
+            bar = int(r[idx["stall_barrier"]] or 0)
+            a[0] += int(r[idx["# Samples"]] or 0) - bar
+            a[1] += int(r[idx["Instructions Executed"]] or 0)
+            a[2] += bar
+    ts, ti, tb = (sum(a[k] for a in agg.values()) for k in range(3))
+    files = collections.defaultdict(lambda: [0, 0])
+    for (f, _), a in agg.items():
+        files[f][0] += a[0]
+        files[f][1] += a[1]
+    out = {"non_barrier_samples": ts, "barrier_samples": tb, "warp_instructions": ti,
+           "by_file": [{"file": f, "sample_share": round(a[0] / max(ts, 1), 4), "instruction_share": round(a[1] / max(ti, 1), 4)}
+                       for f, a in sorted(files.items(), key=lambda x: -x[1][0])],
+           "by_line": [{"file": f, "line": l, "sample_share": round(a[0] / max(ts, 1), 4),
+                        "instruction_share": round(a[1] / max(ti, 1), 4), "instructions": a[1]}
+                       for (f, l), a in sorted(agg.items(), key=lambda x: -x[1][0])[:top]]}
+    json.dump(out, open(dst, "w"), indent=1)
+    print("non-barrier samples %d, barrier %d; top files:" % (ts, tb))
+    for e in out["by_file"][:8]:
+        print("  %-24s samples %5.1f%%  instructions %5.1f%%" % (e["file"], 100 * e["sample_share"], 100 * e["instruction_share"]))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "digest":
+    if sys.argv[1] == "lines":
+        lines(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "digest":
         digest(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], float(sys.argv[6]) if len(sys.argv) > 6 else None)
     elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])

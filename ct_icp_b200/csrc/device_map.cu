@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <stdexcept>
 #include <vector>
@@ -485,7 +486,9 @@ void DeviceMap::UpdateFused(const float4 *d_frame, const float4 *d_frame_lo, con
         CT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_update_fused, kInsertWarps * 32, 0));
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        fused_grid_ = std::max(1, std::min(per_sm, 4) * sms);
+        int want = 4;   // CTAs per SM: more hide the latency of the probes, fewer make the grid barriers cheaper (A/B knob)
+        if (const char *e = getenv("CTICP_UPDATE_CTAS_PER_SM")) want = std::max(1, atoi(e));
+        fused_grid_ = std::max(1, std::min(per_sm, want) * sms);
     }
     FusedUpdateArgs a{};
     a.num_levels = (int) levels_.size();

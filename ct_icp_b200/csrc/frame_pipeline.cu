@@ -11,6 +11,7 @@
 #include "frame_pipeline.h"
 
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include <algorithm>
 #include <cstring>
@@ -526,7 +527,9 @@ void FramePipeline::SampleFused(double voxel_size, double sample_voxel_size, uin
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        fused_grid_ = std::max(1, std::min(per_sm, 4) * sms);
+        int want = 4;   // CTAs per SM: more hide the latency of the probes, fewer make the grid barriers cheaper (A/B knob)
+        if (const char *e = getenv("CTICP_SAMPLE_CTAS_PER_SM")) want = std::max(1, atoi(e));
+        fused_grid_ = std::max(1, std::min(per_sm, want) * sms);
     }
     FusedSampleArgs a;
     a.raw = d_raw_;

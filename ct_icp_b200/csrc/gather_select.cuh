@@ -19,7 +19,17 @@
 // The result is the exact set the reference keeps. A stencil with more in-radius candidates than the staging area holds
 // is compacted to its k best (same selection) and pruned with the k-th distance from then on.
 #pragma once
+#include <cstddef>
+
 #include "gather.cuh"
+
+// -DCTICP_SEL_V1: the first cut of this file's load path, kept for A/B (tools/ab_variants.sh): owner lane of a flat candidate
+// index by a binary search over shuffles, histogram counted in a separate pass, moments reduced by nine butterfly sums.
+// The default path below replaces the three: owner by a start-bit mask (one popc per chunk), buckets recorded and counted
+// when a candidate is staged, moments reduced through shared memory (~300 warp instructions less per query).
+#if defined(CTICP_SEL_BULK) && !defined(CTICP_SEL_V1)
+#define CTICP_SEL_V1 1
+#endif
 
 namespace cticp {
 
@@ -49,6 +59,14 @@ struct __align__(16) SelScratch {   // per-warp shared memory (6.5 KB)
     unsigned char eidx[kSelCap];    // staged positions of the boundary bucket's candidates
     unsigned char eflag[kSelCap];   // per staged position (boundary bucket only): 0 dropped, 1 kept, 2 kept & farthest
     double far[4];                  // rel xyz, d2 of the farthest kept candidate (= reference points[0])
+#ifndef CTICP_SEL_V1
+    unsigned char bkt[kSelCap];     // histogram bucket of each staged candidate (S.hist counts the staged ones at all times)
+    double mom[9];                  // reduced moments
+    // the occupied voxels of the current stencil slice, in scan order: first flat index, slot, origin relative to the query
+    int own_excl[32], own_slot[32];
+    double own_ox[32], own_oy[32], own_oz[32];
+    unsigned int starts[64];        // bit f set: a voxel's run starts at flat index f (32 cells x <= 64 points per voxel)
+#endif
 #ifdef CTICP_SEL_BULK
     float4 pts[kBulkCap];           // the stencil slice's points, bulk-copied
 #endif
@@ -108,9 +126,11 @@ struct SelPlan {
 // Steps 2 of the header comment on the M staged candidates: fills S.eflag for the candidates of the boundary bucket.
 __device__ __forceinline__ SelPlan sel_plan(SelScratch &S, int M, int kmax, double scale, int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
+#ifdef CTICP_SEL_V1
     S.hist[lane] = 0;
     __syncwarp();
     for (int i = lane; i < M; i += 32) atomicAdd(&S.hist[sel_bucket(S.d2[i], scale)], 1u);
+#endif
     __syncwarp();
     const int h = (int) S.hist[lane];
     int cum = h;
@@ -129,7 +149,11 @@ __device__ __forceinline__ SelPlan sel_plan(SelScratch &S, int M, int kmax, doub
     int ne = 0;
     for (int base = 0; base < M; base += 32) {
         const int i = base + lane;
+#ifdef CTICP_SEL_V1
         const bool is_e = i < M && sel_bucket(S.d2[i], scale) == P.xstar;
+#else
+        const bool is_e = i < M && (int) S.bkt[i] == P.xstar;
+#endif
         const unsigned mask = __ballot_sync(0xffffffffu, is_e);
         if (is_e) S.eidx[ne + __popc(mask & lt_mask)] = (unsigned char) i;
         ne += __popc(mask);
@@ -157,14 +181,23 @@ __device__ __forceinline__ SelPlan sel_plan(SelScratch &S, int M, int kmax, doub
 __device__ __forceinline__ int sel_compact(SelScratch &S, int M, int kmax, double scale, int lane, double &prune_d2) {
     const unsigned lt_mask = (1u << lane) - 1u;
     const SelPlan P = sel_plan(S, M, kmax, scale, lane);
+#ifndef CTICP_SEL_V1
+    S.hist[lane] = 0;   // (sel_plan has read it) recounted below for the candidates that stay
+    __syncwarp();
+#endif
     int out = 0;
     for (int base = 0; base < M; base += 32) {
         const int i = base + lane;
         double d = 0, x = 0, y = 0, z = 0;
         bool kept = false;
+        int b = 0;
         if (i < M) {
             d = S.d2[i]; x = S.rx[i]; y = S.ry[i]; z = S.rz[i];
-            const int b = sel_bucket(d, scale);
+#ifdef CTICP_SEL_V1
+            b = sel_bucket(d, scale);
+#else
+            b = (int) S.bkt[i];
+#endif
             const int flag = b == P.xstar ? (int) S.eflag[i] : 0;
             kept = b < P.xstar || flag != 0;
             if (flag == 2) S.far[3] = d;
@@ -174,6 +207,10 @@ __device__ __forceinline__ int sel_compact(SelScratch &S, int M, int kmax, doubl
         if (kept) {
             const int o = out + __popc(mask & lt_mask);   // o <= i: never clobbers an unread entry of a later round
             S.d2[o] = d; S.rx[o] = x; S.ry[o] = y; S.rz[o] = z;
+#ifndef CTICP_SEL_V1
+            S.bkt[o] = (unsigned char) b;
+            atomicAdd(&S.hist[b], 1u);
+#endif
         }
         out += __popc(mask);
         __syncwarp();
@@ -200,6 +237,9 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
     int fill = 0;
     unsigned pts_total = 0;
     double prune_d2 = kKnnInf;
+#ifndef CTICP_SEL_V1
+    S.hist[lane] = 0;   // counts the staged candidates per bucket as they arrive (visible after the slice's first __syncwarp)
+#endif
 
     for (int base = 0; base < nst; base += 32) {
         const int s = base + lane;
@@ -321,6 +361,74 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
             }
             fill += __popc(m);
         }
+#elif !defined(CTICP_SEL_V1)
+        // the slice's occupied voxels in scan order (rank = position among them) and the start bits of their runs: the
+        // owner of flat index f is voxel number popc(start bits up to f) - 1 — one LDS + popc per chunk instead of a
+        // binary search over shuffles
+        const unsigned occ = __ballot_sync(0xffffffffu, cnt > 0);
+        S.starts[lane] = 0u;
+        S.starts[lane + 32] = 0u;
+        __syncwarp();
+        if (cnt > 0) {
+            const int rk = __popc(occ & lt_mask);
+            S.own_excl[rk] = excl; S.own_slot[rk] = slot;
+            S.own_ox[rk] = ox; S.own_oy[rk] = oy; S.own_oz[rk] = oz;
+            atomicOr(&S.starts[excl >> 5], 1u << (excl & 31));
+        }
+        __syncwarp();
+        int started = 0;   // runs that start before the current batch (warp-uniform)
+        for (int c0 = 0; c0 < total; c0 += 32 * kSelPrefetch) {
+            // room for a whole batch (checked once per batch: one copy of the compaction code, off the common path)
+            if (fill + 32 * kSelPrefetch > kSelCap) fill = sel_compact(S, fill, G.kmax, bucket_scale, lane, prune_d2);
+            float4 pv[kSelPrefetch];
+            int owner[kSelPrefetch];   // rank of the owning voxel, -1: no candidate
+            // phase 1: locate and issue every load of this batch
+#pragma unroll
+            for (int u = 0; u < kSelPrefetch; ++u) {
+                const int f = c0 + 32 * u + lane;   // flat candidate index
+                owner[u] = -1;
+                pv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + 32 * u < total) {           // warp-uniform
+                    const unsigned word = S.starts[(c0 >> 5) + u];
+                    const int rk = started + __popc(word & (0xffffffffu >> (31 - lane))) - 1;
+                    started += __popc(word);
+                    if (f < total) {
+                        owner[u] = rk;
+                        pv[u] = __ldg(L.points + (size_t) S.own_slot[rk] * L.B + (f - S.own_excl[rk]));
+                    }
+                }
+            }
+            // phase 2: distances, radius test, compaction (in scan order) into the staging area
+#pragma unroll
+            for (int u = 0; u < kSelPrefetch; ++u) {
+                if (c0 + 32 * u < total) {           // warp-uniform
+                    const int ol = owner[u] < 0 ? 0 : owner[u];
+                    const double rx = S.own_ox[ol] + (double) pv[u].x, ry = S.own_oy[ol] + (double) pv[u].y,
+                                 rz = S.own_oz[ol] + (double) pv[u].z;
+                    const double d2 = rx * rx + ry * ry + rz * rz;
+                    bool in = owner[u] >= 0 && !(d2 > G.radius2) && d2 < prune_d2;
+                    if (kFilter) {
+                        // (the filter's per-voxel terms stay with the voxel's lane: found again through the scan order)
+                        const int vl = __fns(occ, 0, ol + 1);
+                        const double vs = __shfl_sync(0xffffffffu, sdn, vl & 31);
+                        const int vh = __shfl_sync(0xffffffffu, has_normal, vl & 31);
+                        // this point's copy of the normal is -n when its w is negative
+                        const double scalar = signbit(pv[u].w) ? -vs : vs;
+                        if (vh && scalar < 0.0) in = false;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int o = fill + __popc(m & lt_mask);
+                        const int b = sel_bucket(d2, bucket_scale);
+                        S.d2[o] = d2; S.rx[o] = rx; S.ry[o] = ry; S.rz[o] = rz;
+                        S.bkt[o] = (unsigned char) b;
+                        atomicAdd(&S.hist[b], 1u);
+                    }
+                    fill += __popc(m);
+                }
+            }
+        }
+        __syncwarp();   // the owner tables are read before the next slice rewrites them
 #else
         for (int c0 = 0; c0 < total; c0 += 32 * kSelPrefetch) {
             // room for a whole batch (checked once per batch: one copy of the compaction code, off the common path)
@@ -388,7 +496,11 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
         const int i = base + lane;
         if (i < fill) {
             const double d = S.d2[i];
+#ifdef CTICP_SEL_V1
             const int b = sel_bucket(d, bucket_scale);
+#else
+            const int b = (int) S.bkt[i];
+#endif
             const int flag = b == P.xstar ? (int) S.eflag[i] : 0;
             if (b < P.xstar || flag != 0) {
                 const double x = S.rx[i], y = S.ry[i], z = S.rz[i];
@@ -399,9 +511,36 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
             }
         }
     }
+#ifdef CTICP_SEL_V1
 #pragma unroll
     for (int v = 0; v < 9; ++v) a[v] = warp_sum(a[v]);
     __syncwarp();
+#else
+    // Σ over the lanes through shared memory: the staging arrays are free now (rows of 33 words, conflict-free both ways;
+    // d2 and rx are adjacent: 9 x 33 = 297 <= 2 kSelCap); lane 3v + part sums a third of row v, three partials per moment
+    // meet by two shuffles — 9 stores + 11 loads per lane instead of 45 double shuffles. Fixed order: deterministic.
+    {
+        static_assert(offsetof(SelScratch, rx) == offsetof(SelScratch, d2) + sizeof(double) * kSelCap && 2 * kSelCap >= 9 * 33,
+                      "reduction scratch");
+        __syncwarp();   // every lane is done reading the staged candidates
+        double *red = S.d2;
+#pragma unroll
+        for (int v = 0; v < 9; ++v) red[v * 33 + lane] = a[v];
+        __syncwarp();
+        const int v = lane / 3, part = lane - 3 * v;   // lanes 27..31: v = 9, idle
+        double t = 0;
+        if (v < 9) {
+            const double *row = red + v * 33 + part * 11;
+            const int cntp = part < 2 ? 11 : 10;
+            for (int e = 0; e < cntp; ++e) t += row[e];
+        }
+        const double t1 = __shfl_down_sync(0xffffffffu, t, 1), t2 = __shfl_down_sync(0xffffffffu, t, 2);
+        if (v < 9 && part == 0) S.mom[v] = (t + t1) + t2;
+        __syncwarp();
+#pragma unroll
+        for (int v2 = 0; v2 < 9; ++v2) a[v2] = S.mom[v2];
+    }
+#endif
     out.sx = a[0]; out.sy = a[1]; out.sz = a[2];
     out.sxx = a[3]; out.sxy = a[4]; out.sxz = a[5];
     out.syy = a[6]; out.syz = a[7]; out.szz = a[8];

@@ -376,6 +376,7 @@ __device__ __forceinline__ GnPose load_pose(const IcpState *st) {
     return p;
 }
 
+static_assert(sizeof(GnShared) <= 227 * 1024, "k_gn_persistent: dynamic shared memory of one CTA (sm_100: 227 KB)");
 extern __shared__ __align__(16) unsigned char gn_smem_raw[];
 
 // mode 0: gather + (last CTA) reduce + solve + pose update          [one launch per ICP iteration]

@@ -982,6 +982,7 @@ struct __align__(16) LmPShared {
     int stencil[kMaxStencil];
     int flag;
 };
+static_assert(sizeof(LmPShared) <= 227 * 1024, "k_lm_persistent: dynamic shared memory of one CTA (sm_100: 227 KB)");
 extern __shared__ __align__(16) unsigned char lm_smem_raw[];
 
 // what the worker CTAs read of the LM state: the point to evaluate, the problem size, the stop flag

@@ -7,6 +7,8 @@ when the staging area fills up. This model restates those steps one-to-one (same
 capacity / batch size, same prune rule) and checks them against a plain stable sort on adversarial inputs: ties,
 everything in one bucket, more candidates than the staging area, fewer than k.
 """
+import random
+
 import numpy as np
 import pytest
 
@@ -104,3 +106,43 @@ def test_bucket_is_monotone():
     d = np.sort(rng.uniform(0, 1, 10000))
     b = bucket(d, K_BUCKETS / 1.0)
     assert np.all(np.diff(b) >= 0)
+
+
+def test_owner_lookup_by_start_bits():
+    """warp_gather_sums (gather_select.cuh, default path): the stencil slice's points form one flat list (prefix sum of the
+    voxel counts); the voxel that owns flat index f is found as popc(start bits up to f) - 1 among the OCCUPIED voxels in
+    scan order, the start-bit words consumed batch by batch with a running count. Model of that index arithmetic."""
+    rng = random.Random(5)
+    for _ in range(500):
+        B = rng.choice([1, 5, 20, 24, 64])
+        cnt = [rng.choice([0, 0, rng.randint(1, B)]) for _ in range(32)]
+        excl = [sum(cnt[:i]) for i in range(32)]
+        total = sum(cnt)
+        occupied = [i for i in range(32) if cnt[i] > 0]
+        own_excl, own_cnt = [excl[i] for i in occupied], [cnt[i] for i in occupied]
+        starts = [0] * 64
+        for e in own_excl:
+            starts[e >> 5] |= 1 << (e & 31)
+        for prefetch in (2, 4, 6):
+            started, c0 = 0, 0
+            while c0 < total:
+                for u in range(prefetch):
+                    if c0 + 32 * u < total:
+                        word = starts[(c0 >> 5) + u]
+                        for lane in range(32):
+                            f = c0 + 32 * u + lane
+                            rk = started + bin(word & (0xFFFFFFFF >> (31 - lane))).count("1") - 1
+                            if f < total:
+                                assert own_excl[rk] <= f < own_excl[rk] + own_cnt[rk]
+                        started += bin(word).count("1")
+                c0 += 32 * prefetch
+
+
+def test_moment_reduction_partition():
+    """the nine moment sums leave the lanes through shared memory: lane 3v + part adds entries [11 part, 11 part + 11 or 10)
+    of row v — the three parts tile the 32 lanes exactly"""
+    covered = []
+    for part in range(3):
+        covered += list(range(part * 11, part * 11 + (11 if part < 2 else 10)))
+    assert covered == list(range(32))
+    assert [lane // 3 for lane in range(27)] == [v for v in range(9) for _ in range(3)]

@@ -9,9 +9,11 @@
 #                                           (UBLKCP / SYNCS: the north star's "TMA staging") instead of per-lane loads
 #   prefetch2/6 -DCTICP_SEL_PREFETCH=2 / 6  2 / 6 chunks of 32 point loads in flight per batch (default 4)
 #   warps8      -DCTICP_GATHER_WARPS=8      8 warps per gather CTA (two CTAs per SM) instead of 16
+#   selv1       -DCTICP_SEL_V1              the selection's first cut (owner by binary search over shuffles, separate histogram
+#                                           pass, butterfly sums): what the default path of gather_select.cuh replaced
 set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
-VARIANTS=("bulk:-DCTICP_SEL_BULK" "prefetch2:-DCTICP_SEL_PREFETCH=2" "prefetch6:-DCTICP_SEL_PREFETCH=6 -DCTICP_SEL_CAP=224"
+VARIANTS=("selv1:-DCTICP_SEL_V1" "bulk:-DCTICP_SEL_BULK" "prefetch2:-DCTICP_SEL_PREFETCH=2" "prefetch6:-DCTICP_SEL_PREFETCH=6 -DCTICP_SEL_CAP=224"
           "warps8:-DCTICP_GATHER_WARPS=8")
 case "${1:-}" in
 build)

@@ -732,8 +732,10 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     timing_.d2h_bytes += sizeof(IcpState) + sizeof(int) * 4;
 
     if (getenv("CTICP_DEBUG_TIMERS"))
-        fprintf(stderr, "[cticp] last iteration (SM cycles, needs -DCTICP_DEBUG_TIMERS): reduce %lld, solve %lld\n",
-                (long long) (S.dbg_t[2] - S.dbg_t[1]), (long long) (S.dbg_t[3] - S.dbg_t[2]));
+        fprintf(stderr, "[cticp] GN loop, solver CTA (SM cycles over %d iterations, needs a -DCTICP_DEBUG_TIMERS build): loop %llu, "
+                "reduce+solve %llu = reduce %llu + rest %llu (12x12 solve %llu, pose update %llu)\n", (int) S.iter,
+                (unsigned long long) S.cycles_total, (unsigned long long) S.cycles_solve, (unsigned long long) S.dbg_t[0],
+                (unsigned long long) S.dbg_t[1], (unsigned long long) S.dbg_t[2], (unsigned long long) S.dbg_t[3]);
     rs.sample_size = pipe_->h_counts()[2];
     last_num_keypoints_ = (size_t) std::max(0, pipe_->h_counts()[2]);
     rs.icp.success = !S.failed;

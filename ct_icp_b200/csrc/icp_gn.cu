@@ -105,7 +105,10 @@ __device__ __noinline__ void warp_gn_solve(const double *acc, SolveScratch &S, I
     }
     if (mode == 1) return;
 
+    CT_STAMP(const long long t_ldlt = clock64();)
     warp_ldlt_solve12(S, lane);   // :914
+    CT_STAMP(if (lane == 0) st->dbg_t[2] += (unsigned long long) (clock64() - t_ldlt);)
+    CT_STAMP(const long long t_pose = clock64();)
     {
         // A rank-deficient system (all keypoints on one plane and no regulariser, …) gives a non-finite step where Eigen's
         // pivoted LDL^T would still return something bounded: report the failure instead of propagating NaN poses
@@ -149,6 +152,7 @@ __device__ __noinline__ void warp_gn_solve(const double *acc, SolveScratch &S, I
         st->slerp_inv_sin = sc.inv_sin;
         st->slerp_linear = sc.linear;
         st->slerp_negate = sc.negate;
+        CT_STAMP(st->dbg_t[3] += (unsigned long long) (clock64() - t_pose);)
     }
 }
 
@@ -390,7 +394,6 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const GnParams &P = cfg.P;
     const bool active = (mode == 1) || !st->done;
-    CT_STAMP(if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg_t[0] = global_timer_ns();)
 
     GnWarpAcc A;
     void *bulk_ptr = nullptr;
@@ -428,15 +431,12 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
     __threadfence();
     if (threadIdx.x == 0) {
         *ticket = 0;
-        CT_STAMP(st->dbg_t[1] = global_timer_ns();)
     }
     if (!active) return;
     gn_reduce_rows(sh, partials, (int) gridDim.x, lane, w);
     if (mode == 2 && threadIdx.x < kAcc) acc_out[threadIdx.x] = sh.acc[0][threadIdx.x];
-    CT_STAMP(if (threadIdx.x == 0) st->dbg_t[2] = global_timer_ns();)
     if (mode == 2 || w != 0) return;
     warp_gn_solve(sh.acc[0], sh.solve, st, P, mode, sys_out, lane);
-    CT_STAMP(if (lane == 0) st->dbg_t[3] = global_timer_ns();)
 }
 
 // ---- persistent variant: the WHOLE Gauss-Newton loop in one cooperative launch --------------------------------
@@ -470,9 +470,9 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
         for (int i = threadIdx.x; i < (int) (sizeof(IcpState) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
+    CT_STAMP(if (solver_cta && threadIdx.x < 4) sh.state.dbg_t[threadIdx.x] = 0; __syncthreads();)
     if (solver_cta && w == 0 && !(P.debug_flags & 4)) {
         // instruction-cache warm-up of the serial tail on a dummy well-posed system (results discarded)
-        CT_STAMP(if (lane == 0) st->dbg_t[0] = global_timer_ns();)
         for (int i = lane; i < kAcc; i += 32) sh.acc[1][i] = 0.0;
         __syncwarp();
         for (int e = lane; e < 78; e += 32)
@@ -531,9 +531,12 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
         }
         grid.sync();
         if (solver_cta) {
-            CT_STAMP(if (threadIdx.x == 0) st->dbg_t[1] = global_timer_ns();)
             const long long t_begin = threadIdx.x == 0 ? clock64() : 0;
             gn_reduce_rows(sh, partials, gather_ctas, lane, w);
+            // -DCTICP_DEBUG_TIMERS: SM cycles summed over the iterations — dbg_t[0] reduction of the partial rows,
+            // [1] everything from there to the published state, [2] the 12x12 solve, [3] the pose update
+            CT_STAMP(if (threadIdx.x == 0) sh.state.dbg_t[0] += (unsigned long long) (clock64() - t_begin);)
+            CT_STAMP(const long long t_rest = clock64();)
             bool peers_ok = true;
             if (kPeers) {
                 // Σ over ranks, in rank order (bit-identical on every rank); the staging areas are unused by the solver
@@ -541,7 +544,6 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 static_assert(sizeof(TileScratch) * kGatherWarps >= sizeof(unsigned int) * kMaxPeers * kPeerWords, "scratch");
                 peers_ok = peer_allreduce(links, ++peer_seq, sh.acc[0], reinterpret_cast<unsigned int *>(&sh.tile[0]), &sh.flag);
             }
-            CT_STAMP(if (threadIdx.x == 0) st->dbg_t[2] = global_timer_ns();)
             if (w == 0) {
                 IcpState *ws = &sh.state;
                 if (!peers_ok) {
@@ -564,7 +566,10 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 const int *src = reinterpret_cast<const int *>(ws);
                 int *dst = reinterpret_cast<int *>(st);
                 for (int i = lane; i < (int) (sizeof(IcpState) / sizeof(int)); i += 32) __stcg(dst + i, src[i]);
-                CT_STAMP(if (lane == 0) st->dbg_t[3] = global_timer_ns();)
+                CT_STAMP(if (lane == 0) {
+                    ws->dbg_t[1] += (unsigned long long) (clock64() - t_rest);
+                    __stcg(&st->dbg_t[1], ws->dbg_t[1]);
+                })
             }
             __threadfence();
         }

@@ -9,12 +9,13 @@
 #                                           (UBLKCP / SYNCS: the north star's "TMA staging") instead of per-lane loads
 #   prefetch2/6 -DCTICP_SEL_PREFETCH=2 / 6  2 / 6 chunks of 32 point loads in flight per batch (default 4)
 #   warps8      -DCTICP_GATHER_WARPS=8      8 warps per gather CTA (two CTAs per SM) instead of 16
+#   timers      -DCTICP_DEBUG_TIMERS        clock64 stamps in the solver CTA of k_gn_persistent (built here, not benchmarked)
 #   selv1       -DCTICP_SEL_V1              the selection's first cut (owner by binary search over shuffles, separate histogram
 #                                           pass, butterfly sums): what the default path of gather_select.cuh replaced
 set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 VARIANTS=("selv1:-DCTICP_SEL_V1" "bulk:-DCTICP_SEL_BULK" "prefetch2:-DCTICP_SEL_PREFETCH=2" "prefetch6:-DCTICP_SEL_PREFETCH=6 -DCTICP_SEL_CAP=224"
-          "warps8:-DCTICP_GATHER_WARPS=8")
+          "warps8:-DCTICP_GATHER_WARPS=8" "timers:-DCTICP_DEBUG_TIMERS")
 case "${1:-}" in
 build)
     for v in "${VARIANTS[@]}"; do
@@ -31,6 +32,7 @@ run)
         name="${v%%:*}"
         lib="$ROOT/ct_icp_b200/libcticp_b200_$name.so"
         [ -f "$lib" ] || continue
+        [ "$name" = "timers" ] && continue   # instrumented build (tools/gpu_check.sh prints its stamps), not a candidate
         CTICP_ENGINE_LIB="$lib" timeout 900 python -m pytest tests -m gpu -q -n 6 -k "gn or neighborhoods or small or suburb" \
             > "$out/pytest_$name.log" 2>&1
         echo "rc=$?" >> "$out/pytest_$name.log"

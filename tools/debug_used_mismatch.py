@@ -16,7 +16,7 @@ from ct_icp_b200 import synthetic as syn  # noqa: E402
 from oracle_lib import oracle  # noqa: E402
 from test_gpu_parity import _sequence_options  # noqa: E402
 
-frames = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 eng, orc = ct_icp_b200.engine(), oracle()
 seq = syn.make_sequence(frames + 1, syn.HDL64E, seed=1234, scene=syn.UrbanScene(1234, profile="suburb"))
 
@@ -28,31 +28,35 @@ def opts(b):
     return o
 
 
-ods = {}
-for name, b in (("orc", orc), ("eng", eng)):
-    od = b.odometry(opts(b))
-    for s in seq[:frames]:
-        sm = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
-    ods[name] = (od, sm)
-    print(name, "frame", frames - 1, "residuals", sm.number_of_residuals, "keypoints", sm.num_keypoints, "map", od.MapSize())
-frame = ods["orc"][1].frame                      # pose pair of the last registered frame ~ where the next scan is
-s = seq[frames]
-kp = np.zeros(len(s["xyz"][::30]), dtype=abi.wpoint_dtype())
-kp["raw"] = s["xyz"][::30]
-t0, t1 = s["t"].min(), s["t"].max()
-kp["timestamp"] = s["t"][::30]
-fr = abi.Frame()
-for dst, src, ts in ((fr.begin_pose, frame.end_pose, t0), (fr.end_pose, frame.end_pose, t1)):
-    for i in range(4):
-        dst.quat[i] = src.quat[i]
-    for i in range(3):
-        dst.tr[i] = src.tr[i]
-    dst.dest_timestamp = ts
-from scipy.spatial.transform import Rotation  # noqa: E402
-R = Rotation.from_quat(list(frame.end_pose.quat)).as_matrix()
-T = np.array(list(frame.end_pose.tr))
-kp["world"] = kp["raw"] @ R.T + T               # the reference's GN enters with the caller's world points
-maps = {k: v[0].GetMapPointer() for k, v in ods.items()}
+# pass 1: both arms over the sequence; the first frame whose residual count differs
+first_bad, sums = None, {}
+ods = {name: b.odometry(opts(b)) for name, b in (("orc", orc), ("eng", eng))}
+for k, s in enumerate(seq[:frames]):
+    for name, od in ods.items():
+        sums[name] = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+    so, se = sums["orc"], sums["eng"]
+    print("frame %2d  residuals orc %d eng %d | iters orc %d eng %d | keypoints %d %d" % (
+        k, so.number_of_residuals, se.number_of_residuals, so.icp_summary.num_iters, se.icp_summary.num_iters,
+        so.num_keypoints, se.num_keypoints))
+    if so.number_of_residuals != se.number_of_residuals:
+        first_bad = k
+        break
+if first_bad is None:
+    print("no mismatch in %d frames" % frames)
+    sys.exit(0)
+kps = {name: od.keypoints() for name, od in ods.items()}
+print("keypoint records identical (raw, timestamp):", np.array_equal(kps["orc"]["raw"], kps["eng"]["raw"]),
+      np.array_equal(kps["orc"]["timestamp"], kps["eng"]["timestamp"]))
+final = {name: sums[name].frame for name in ods}
+
+# pass 2: fresh arms up to the frame before → the maps the bad frame was registered against
+ods2 = {name: b.odometry(opts(b)) for name, b in (("orc", orc), ("eng", eng))}
+for s in seq[:first_bad]:
+    for od in ods2.values():
+        od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
+maps = {k: v.GetMapPointer() for k, v in ods2.items()}
+kp = kps["orc"].copy()
+fr = final["orc"]
 used = {}
 for name, m in maps.items():
     u = np.zeros(len(kp), dtype=np.int32)
@@ -62,11 +66,11 @@ for name, m in maps.items():
         _, _, n = m.gn_normal_equations(io, one, fr)
         u[i] = n
     used[name] = u
-    print(name, "used", int(u.sum()), "of", len(kp))
+    print(name, "used", int(u.sum()), "of", len(kp), "(single linearisation at the oracle's final pose pair)")
 bad = np.flatnonzero(used["orc"] != used["eng"])
 print("mismatching keypoints:", len(bad))
 for i in bad[:12]:
-    q = R @ kp["raw"][i] + T
+    q = kp["world"][i]
     no, co = maps["orc"].compute_neighborhoods(q[None, :], 20)
     ne, ce = maps["eng"].compute_neighborhoods(q[None, :], 20)
     same = co[0] == ce[0] and np.abs(no[0, :co[0]] - ne[0, :ce[0]]).max() < 1e-6

@@ -19,9 +19,9 @@ if [ "$WHAT" != "bench" ]; then
   if [ $RC -ne 0 ]; then
     # which switch breaks it? a fast subset under each fallback
     SUB="sequence_small or gn_register or gn_normal or ceres_register_matches_oracle or robust_register or neighborhoods"
-    for cfg in "CTICP_FUSED_SAMPLING=0" "CTICP_FUSED_MAP_UPDATE=0" "CTICP_PERSISTENT=0" \
+    for cfg in "CTICP_ENGINE_LIB=$PWD/ct_icp_b200/libcticp_b200_selv1.so" "CTICP_FUSED_SAMPLING=0" "CTICP_FUSED_MAP_UPDATE=0" "CTICP_PERSISTENT=0" \
                "CTICP_FUSED_SAMPLING=0 CTICP_FUSED_MAP_UPDATE=0" "CTICP_FUSED_SAMPLING=0 CTICP_FUSED_MAP_UPDATE=0 CTICP_PERSISTENT=0"; do
-      name=$(echo "$cfg" | tr ' =' '__')
+      name=$(echo "$cfg" | tr ' =/' '___' | sed 's/.*libcticp_b200_//')
       env $cfg timeout 600 python -m pytest tests -m gpu -q -n 6 --tb=line -p no:cacheprovider -k "$SUB" > gpurun_out/${TAG}_bisect_${name}.log 2>&1
       echo "== $cfg: $(tail -1 gpurun_out/${TAG}_bisect_${name}.log)"
     done
@@ -34,6 +34,28 @@ if [ "$WHAT" != "pytest" ]; then
     CTICP_FUSED_SAMPLING=0 CTICP_FUSED_MAP_UPDATE=0 timeout 900 python bench.py --no-extras --no-cpu-baseline > gpurun_out/${TAG}_bench_nofuse.json 2> gpurun_out/${TAG}_bench_nofuse.err
     echo "bench (no fused kernels) rc=$?"; tail -3 gpurun_out/${TAG}_bench_nofuse.err; cat gpurun_out/${TAG}_bench_nofuse.json
   fi
+fi
+if [ "$WHAT" = "all" ] || [ "$WHAT" = "knobs" ]; then
+  # run-time knobs, one bench line each (step / GN loop / e2e): CTAs per SM of the two fused kernels (grid-barrier cost vs
+  # latency hiding), keypoints per gather CTA, and the loop without its solve (CTICP_DEBUG_FLAGS=1: timing only)
+  echo "---- knobs"
+  for cfg in "CTICP_SAMPLE_CTAS_PER_SM=1" "CTICP_SAMPLE_CTAS_PER_SM=2" "CTICP_UPDATE_CTAS_PER_SM=1" "CTICP_UPDATE_CTAS_PER_SM=2" \
+             "CTICP_GN_KP_PER_CTA=16" "CTICP_DEBUG_FLAGS=1"; do
+    name=$(echo "$cfg" | tr ' =' '__')
+    env $cfg timeout 600 python bench.py --no-extras --no-cpu-baseline > gpurun_out/${TAG}_knob_${name}.json 2> gpurun_out/${TAG}_knob_${name}.err
+    python - "$cfg" gpurun_out/${TAG}_knob_${name}.json <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    print("%-32s step %.4f ms  GN loop %6.1f us  e2e %.4f ms  solve share %s" % (sys.argv[1], d["ms_per_step"],
+          d["roofline"]["us_per_launch"], d["e2e"]["ms_per_step"], d["roofline"].get("serial_reduce_and_solve_share")))
+except Exception as e:
+    print(sys.argv[1], "unreadable:", e)
+PY
+  done
+  # where the solver CTA's serial part goes (instrumented build; SM cycles per frame on stderr)
+  CTICP_ENGINE_LIB=$PWD/ct_icp_b200/libcticp_b200_timers.so CTICP_DEBUG_TIMERS=1 timeout 300 python tools/profile_step.py --frames 30 \
+      2>&1 | grep "GN loop, solver CTA" | tail -4 | tee gpurun_out/${TAG}_solver_cta_stamps.log
 fi
 if [ "$WHAT" = "all" ]; then
   echo "---- profile"; bash tools/gpu_profile.sh ${TAG} kitti64_gn 2>&1 | tail -12

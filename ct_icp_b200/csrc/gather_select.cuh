@@ -517,10 +517,12 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
     __syncwarp();
 #else
     // Σ over the lanes through shared memory: the staging arrays are free now (rows of 33 words, conflict-free both ways;
-    // d2 and rx are adjacent: 9 x 33 = 297 <= 2 kSelCap); lane 3v + part sums a third of row v, three partials per moment
+    // d2 .. rz are adjacent: 9 x 33 = 297 <= 4 kSelCap); lane 3v + part sums a third of row v, three partials per moment
     // meet by two shuffles — 9 stores + 11 loads per lane instead of 45 double shuffles. Fixed order: deterministic.
     {
-        static_assert(offsetof(SelScratch, rx) == offsetof(SelScratch, d2) + sizeof(double) * kSelCap && 2 * kSelCap >= 9 * 33,
+        static_assert(offsetof(SelScratch, rx) == offsetof(SelScratch, d2) + sizeof(double) * kSelCap &&
+                          offsetof(SelScratch, rz) == offsetof(SelScratch, d2) + 3 * sizeof(double) * kSelCap &&
+                          4 * kSelCap >= 9 * 33,
                       "reduction scratch");
         __syncwarp();   // every lane is done reading the staged candidates
         double *red = S.d2;

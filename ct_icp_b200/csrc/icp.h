@@ -55,6 +55,15 @@ struct PeerLinksHost {
     long long timeout_cycles = 0;   // 0 = the default of peer_exchange.cuh
 };
 
+// -DCTICP_DEBUG_TIMERS builds (tools/ab_variants.sh "timers"): clock64 stamps of the solver CTAs, printed by the host when
+// the environment has CTICP_DEBUG_TIMERS. (%globaltimer proved far too slow to read: it tripled the kernel time; only
+// differences taken on the same SM are meaningful.)
+#ifdef CTICP_DEBUG_TIMERS
+#define CT_STAMP(expr) expr
+#else
+#define CT_STAMP(expr)
+#endif
+
 struct GnParams {
     int r;                      // stencil radius (voxels)
     int level;                  // map level searched

@@ -36,14 +36,6 @@ namespace cg = cooperative_groups;
 constexpr int kGatherWarps = CTICP_GATHER_WARPS;
 
 
-#ifdef CTICP_DEBUG_TIMERS
-// SM-local cycle counter (%globaltimer proved far too slow to read: it tripled the kernel time). Only differences
-// taken on the same SM are meaningful: dbg_t[1..3] are all stamped by the solver CTA.
-__device__ __forceinline__ unsigned long long global_timer_ns() { return (unsigned long long) clock64(); }
-#define CT_STAMP(expr) expr
-#else
-#define CT_STAMP(expr)
-#endif
 
 struct GatherLaunch {
     GatherConfig G;
@@ -124,8 +116,10 @@ __device__ __noinline__ void warp_gn_solve(const double *acc, SolveScratch &S, I
 
     if (lane < 6) {   // angles x[0..2] (begin) and x[6..8] (end): sin / cos evaluated by six lanes at once
         const double ang = S.x[lane < 3 ? lane : lane + 3];
-        S.sn[lane] = sin(ang);
-        S.cs[lane] = cos(ang);
+        // a GN step's angles are a fraction of a degree: polynomials (se3.cuh) instead of libm's argument reduction
+        const bool small = fabs(ang) <= 0.5;
+        S.sn[lane] = small ? sin_upto_half(ang) : sin(ang);
+        S.cs[lane] = small ? cos_upto_half(ang) : cos(ang);
     }
     __syncwarp();
     if (lane < 2) {   // lane 0: begin pose, lane 1: end pose (:916-962)

@@ -76,6 +76,10 @@ struct LmState {
     double prev_qb[4], prev_qe[4], prev_tb[3], prev_te[3];
     int outer_iter;
     // debug trace (CTICP_DEBUG_LM): one record per evaluated candidate
+    // -DCTICP_DEBUG_TIMERS: SM cycles of the solver CTA per launch — [0] whole loop, [1] waiting for the residual assembly,
+    // [2] GetProblem (selection), [3] waiting for an evaluation, [4] reduction of the partial rows, [5] minimizer step,
+    // [6] the barriers behind a publish, [7] evaluations
+    unsigned long long dbg_cycles[8];
     int trace_n;
     double trace[256][13];   // x_cost, candidate_cost, model_cost_change, relative_decrease, radius, flag
 };
@@ -585,6 +589,7 @@ struct LmScratch {
     double U[12][12], gu[12];
     double cost;
     double step[12], delta[12];
+    double hs[12];   // rows of H step (model cost change), one per lane
     SolveScratch solve;
     int flag;
 };
@@ -808,20 +813,23 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
         if (lane < 12) S.solve.A[lane][lane] += lm->diagonal[lane] / lm->radius;
         __syncwarp();
         warp_ldlt_solve12(S.solve, lane);   // (J'J + D^2) y = J'r
+        if (lane < 12) S.step[lane] = -S.solve.x[lane];
+        __syncwarp();
+        if (lane < 12) {   // row `lane` of H step, the twelve rows at once (same order of operations as a serial loop)
+            double hs = 0;
+            for (int b = 0; b < 12; ++b) hs += lm->U[lane][b] * lm->scaling[lane] * lm->scaling[b] * S.step[b];
+            S.hs[lane] = hs;
+        }
+        __syncwarp();
         if (lane == 0) {
             lm->reuse_diagonal = 1;
             bool finite = true;
-            for (int j = 0; j < 12; ++j) {
-                S.step[j] = -S.solve.x[j];
-                finite = finite && isfinite(S.step[j]);
-            }
+            for (int j = 0; j < 12; ++j) finite = finite && isfinite(S.step[j]);
             // model_cost_change = -(J step)'(f + J step / 2) = -step'g - step'H step / 2   (scaled quantities)
             double sg = 0, shs = 0;
             for (int a = 0; a < 12; ++a) {
                 sg += S.step[a] * lm->gu[a] * lm->scaling[a];
-                double hs = 0;
-                for (int b = 0; b < 12; ++b) hs += lm->U[a][b] * lm->scaling[a] * lm->scaling[b] * S.step[b];
-                shs += S.step[a] * hs;
+                shs += S.step[a] * S.hs[a];
             }
             const double mcc = -sg - 0.5 * shs;
             lm->model_cost_change = mcc;
@@ -1021,6 +1029,9 @@ k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoint
     }
     grid.sync();
     const int K = *d_num_keypoints;
+    CT_STAMP(long long t_mark = clock64(); const long long t_loop = t_mark;)
+    CT_STAMP(if (solver && tid < 8) lm->dbg_cycles[tid] = 0;)
+#define LM_STAMP(slot) CT_STAMP(if (solver && tid == 0) { const long long now = clock64(); lm->dbg_cycles[slot] += (unsigned long long) (now - t_mark); t_mark = now; })
 
     for (int it = 0; it < P.num_iters_icp; ++it) {
         if (__ldcg(&st->done)) break;   // uniform: written before a grid barrier
@@ -1035,6 +1046,7 @@ k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoint
                 lm_gather_tiles<false>(G0, P, stencil, keypoints, K, st, blocks, stats, D, sh.tile[w], wg, warps_total, lane);
         }
         grid.sync();
+        LM_STAMP(1)
         // ---- GetProblem (solver): the first max_num_residuals valid blocks in keypoint order, seeds the minimizer
         if (solver) {
             double *counts = sh.solver.part[0];
@@ -1054,7 +1066,9 @@ k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoint
             lm_publish(lm_g, lm, tid);
             __threadfence();
         }
+        LM_STAMP(2)
         grid.sync();
+        LM_STAMP(6)
         // ---- ceres::Solve: evaluation 0 at x, then one evaluation per candidate
         for (int ev = 0; ev <= P.ls_max_num_iters; ++ev) {
             if (__ldcg(&st->done) || __ldcg(&lm_g->done)) break;   // uniform
@@ -1065,6 +1079,8 @@ k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoint
                                               hw * workers + wi, workers * kLmPWarps * 2, partials + (size_t) wi * kAcc);
             }
             grid.sync();
+            LM_STAMP(3)
+            CT_STAMP(if (solver && tid == 0) lm->dbg_cycles[7] += 1;)
             if (solver) {
                 // deterministic reduction of the workers' rows: warp g sums the rows b = g (mod warps), all its loads in
                 // flight before the first add; then the per-warp sums in fixed order
@@ -1104,6 +1120,7 @@ k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoint
                     }
                     __syncthreads();
                 }
+                LM_STAMP(4)
                 bool ok = true;
                 if (kPeers) ok = peer_allreduce(links, ++peer_seq, sh.solver.S.acc, sh.solver.half, &sh.flag);
                 if (w == 0) {
@@ -1123,9 +1140,13 @@ k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoint
                 lm_publish(lm_g, lm, tid);
                 __threadfence();
             }
+            LM_STAMP(5)
             grid.sync();
+            LM_STAMP(6)
         }
     }
+    CT_STAMP(if (solver && tid == 0) lm->dbg_cycles[0] = (unsigned long long) (clock64() - t_loop);)
+#undef LM_STAMP
     if (solver) {
         if (kPeers && tid == 0) *links.seq = peer_seq;
         // the whole state (incl. the debug trace) for the host
@@ -1351,10 +1372,18 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
 }
 
 void IcpSolver::DebugLmTrace(void *d_lm) {
-    if (!getenv("CTICP_DEBUG_LM")) return;
+    const bool timers = getenv("CTICP_DEBUG_TIMERS") != nullptr;
+    if (!getenv("CTICP_DEBUG_LM") && !timers) return;
     static LmState h;
     CT_CUDA_CHECK(cudaMemcpyAsync(&h, d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, stream_));
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (timers) {
+        const unsigned long long *c = h.dbg_cycles;
+        fprintf(stderr, "[cticp] LM loop, solver CTA (SM cycles, needs a -DCTICP_DEBUG_TIMERS build): loop %llu = assembly wait %llu + "
+                "selection %llu + evaluation wait %llu + reduce %llu + minimizer step %llu + barriers %llu; %llu evaluations\n",
+                c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+        if (!getenv("CTICP_DEBUG_LM")) return;
+    }
     for (int i = 0; i < h.trace_n; ++i)
         fprintf(stderr, "[eng-lm] x_cost %.12g cand %.12g x %.12g %.12g %.12g %.12g | %.12g %.12g %.12g %s\n", h.trace[i][0], h.trace[i][1],
                 h.trace[i][6], h.trace[i][7], h.trace[i][8], h.trace[i][9], h.trace[i][10], h.trace[i][11], h.trace[i][12], h.trace[i][5] > 0.5 ? "ACCEPT" : "reject");

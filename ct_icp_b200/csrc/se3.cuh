@@ -102,6 +102,20 @@ CT_HD double sin_upto_half(double x) {
     p = p * x2 - 0.16666666666666666;           // -1/3!
     return x + x * (x2 * p);
 }
+// cos(x) for |x| <= 0.5, Taylor up to x^18 (next term 0.5^20 / 20! = 3.9e-25)
+CT_HD double cos_upto_half(double x) {
+    const double x2 = x * x;
+    double p = 1.5619206968586226e-16;          //  1/18!
+    p = p * x2 - 4.779477332387385e-14;         // -1/16!
+    p = p * x2 + 1.1470745597729725e-11;        //  1/14!
+    p = p * x2 - 2.08767569878681e-9;           // -1/12!
+    p = p * x2 + 2.755731922398589e-7;          //  1/10!
+    p = p * x2 - 2.48015873015873e-5;           // -1/8!
+    p = p * x2 + 1.388888888888889e-3;          //  1/6!
+    p = p * x2 - 4.1666666666666664e-2;         // -1/4!
+    p = p * x2 + 0.5;                           //  1/2!
+    return 1.0 - x2 * p;
+}
 CT_HD Q4 qslerp_c(Q4 a, Q4 b, double t, const SlerpConsts &c) {
     double s0, s1;
     if (c.linear) {

@@ -47,10 +47,18 @@ static __device__ __forceinline__ void warp_ldlt_solve12(SolveScratch &S, int la
         ec[k] = e < 156 ? e % 13 : 0;
     }
     __syncwarp();
+    // The reciprocal of pivot p + 1 is started during step p: every lane predicts the entry (p+1, p+1) with the very
+    // expression its owner uses below, so the division's latency overlaps the store / barrier / load of the update instead
+    // of heading every step's dependency chain.
+    auto guarded_rcp = [](double pd) { return (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0; };   // pseudo-inverse like Eigen's D
+    double inv = guarded_rcp(S.A[0][0]);
 #pragma unroll 1
     for (int p = 0; p < 12; ++p) {
-        const double pd = S.A[p][p];
-        const double inv = (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0;   // pseudo-inverse like Eigen's D
+        double next_inv = 0.0;
+        if (p < 11) {
+            const double f = S.A[p + 1][p] * inv;
+            next_inv = guarded_rcp(S.A[p + 1][p + 1] - f * S.A[p][p + 1]);
+        }
         double nv[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -63,6 +71,7 @@ static __device__ __forceinline__ void warp_ldlt_solve12(SolveScratch &S, int la
         for (int k = 0; k < 5; ++k)
             if (lane + 32 * k < 156) S.A[er[k]][ec[k]] = nv[k];
         __syncwarp();
+        inv = next_inv;
     }
     if (lane < 12) S.x[lane] = S.A[lane][12];
     __syncwarp();

@@ -9,13 +9,16 @@
 #                                           (UBLKCP / SYNCS: the north star's "TMA staging") instead of per-lane loads
 #   prefetch2/6 -DCTICP_SEL_PREFETCH=2 / 6  2 / 6 chunks of 32 point loads in flight per batch (default 4)
 #   warps8      -DCTICP_GATHER_WARPS=8      8 warps per gather CTA (two CTAs per SM) instead of 16
+#   warps20/24  -DCTICP_GATHER_WARPS=20/24  20 / 24 warps per gather CTA (96 / 80 registers per thread, smaller staging areas):
+#                                           2940 / 3528 warps in the grid instead of 2352 — one keypoint per warp up to that K
 #   timers      -DCTICP_DEBUG_TIMERS        clock64 stamps in the solver CTA of k_gn_persistent (built here, not benchmarked)
 #   selv1       -DCTICP_SEL_V1              the selection's first cut (owner by binary search over shuffles, separate histogram
 #                                           pass, butterfly sums): what the default path of gather_select.cuh replaced
 set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 VARIANTS=("selv1:-DCTICP_SEL_V1" "bulk:-DCTICP_SEL_BULK" "prefetch2:-DCTICP_SEL_PREFETCH=2" "prefetch6:-DCTICP_SEL_PREFETCH=6 -DCTICP_SEL_CAP=224"
-          "warps8:-DCTICP_GATHER_WARPS=8" "timers:-DCTICP_DEBUG_TIMERS")
+          "warps8:-DCTICP_GATHER_WARPS=8" "warps20:-DCTICP_GATHER_WARPS=20 -DCTICP_SEL_CAP=128 -DCTICP_SEL_PREFETCH=2"
+          "warps24:-DCTICP_GATHER_WARPS=24 -DCTICP_SEL_CAP=96 -DCTICP_SEL_PREFETCH=2" "timers:-DCTICP_DEBUG_TIMERS")
 case "${1:-}" in
 build)
     for v in "${VARIANTS[@]}"; do

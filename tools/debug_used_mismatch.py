@@ -80,3 +80,26 @@ for i in bad[:12]:
     print("kp %d used orc %d eng %d | neighbors %d / %d same=%s | sv %s | |n.(p - p0)| %.6f" % (
         i, used["orc"][i], used["eng"][i], co[0], ce[0], same, np.array2string(sv[1], precision=6),
         abs(normal @ (q - pts[0]))))
+
+# pass 3: the bad frame's registration replayed through the L3 entry point with 1, 2, … iterations, on both arms, from
+# the estimate RegisterFrame started from — where do the two iterations part?
+o = opts(eng)
+k = first_bad
+traj = ods2["orc"].Trajectory()
+prev = traj[-1] if traj else None
+init = {name: sums[name].initial_frame for name in ods}
+print("initial estimates (end tr):", list(init["orc"].end_pose.tr)[:3], list(init["eng"].end_pose.tr)[:3])
+for n_it in range(1, 17):
+    res = {}
+    for name, b in (("orc", orc), ("eng", eng)):
+        ob = opts(b)
+        io = ob.ct_icp_options
+        io.num_iters_icp = n_it
+        kq = kps["orc"].copy()
+        fr0 = init["orc"].copy()
+        mm = ob.default_motion_model if ob.with_default_motion_model and prev is not None else None
+        sm3 = maps[name].icp_register(io, kq, fr0, prev if mm is not None else None, mm)
+        res[name] = (sm3.num_residuals_used, sm3.num_iters, np.array(list(fr0.end_pose.tr)), np.array(list(fr0.begin_pose.tr)))
+    print("iters %2d: n_used orc %d eng %d | iters run %d %d | end tr diff %.3e begin tr diff %.3e" % (
+        n_it, res["orc"][0], res["eng"][0], res["orc"][1], res["eng"][1],
+        np.linalg.norm(res["orc"][2] - res["eng"][2]), np.linalg.norm(res["orc"][3] - res["eng"][3])))

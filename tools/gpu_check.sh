@@ -56,6 +56,8 @@ PY
   # where the solver CTA's serial part goes (instrumented build; SM cycles per frame on stderr)
   CTICP_ENGINE_LIB=$PWD/ct_icp_b200/libcticp_b200_timers.so CTICP_DEBUG_TIMERS=1 timeout 300 python tools/profile_step.py --frames 30 \
       2>&1 | grep "GN loop, solver CTA" | tail -4 | tee gpurun_out/${TAG}_solver_cta_stamps.log
+  CTICP_ENGINE_LIB=$PWD/ct_icp_b200/libcticp_b200_timers.so CTICP_DEBUG_TIMERS=1 timeout 300 python tools/profile_step.py --frames 30 \
+      --workload kitti64_ceres 2>&1 | grep "LM loop, solver CTA" | tail -6 | tee -a gpurun_out/${TAG}_solver_cta_stamps.log
 fi
 if [ "$WHAT" = "all" ]; then
   echo "---- profile"; bash tools/gpu_profile.sh ${TAG} kitti64_gn 2>&1 | tail -12

@@ -42,6 +42,7 @@ __global__ void k_clear_level(MapLevel L) {
 // candidate list. One thread per point; the list order is arbitrary (phase 2 re-orders by point index).
 __device__ __forceinline__ void insert_claim_dev(const MapLevel &L, MapCounters *ctr, const double *world, int n,
                                                  int *__restrict__ next, uint32_t *__restrict__ touched) {
+    const double inv_res = 1.0 / L.res;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double px = world[3 * i], py = world[3 * i + 1], pz = world[3 * i + 2];
         if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
@@ -49,7 +50,7 @@ __device__ __forceinline__ void insert_claim_dev(const MapLevel &L, MapCounters 
             continue;
         }
         const unsigned long long key =
-            pack_voxel(voxel_coord(px, L.res), voxel_coord(py, L.res), voxel_coord(pz, L.res));
+            pack_voxel(voxel_coord_rcp(px, L.res, inv_res), voxel_coord_rcp(py, L.res, inv_res), voxel_coord_rcp(pz, L.res, inv_res));
         uint32_t h = hash_key(key) & L.cap_mask;
         int slot = -1;
         for (uint32_t probe = 0; probe <= L.cap_mask; ++probe) {

@@ -68,8 +68,13 @@ CT_HD int voxel_coord(double p, double res) { return int(p / res); }
 // (~30 dependent instructions each) leave the serial lane-per-keypoint phase of the gathers.
 CT_HD int voxel_coord_rcp(double p, double res, double inv_res) {
     const double q = p * inv_res;
+#ifdef __CUDA_ARCH__
+    const int k = f64_trunc(q);                       // (conversions off the XU pipe, se3.cuh)
+    const double f = fabs(q - i32_to_f64(k));
+#else
     const int k = int(q);
     const double f = fabs(q - (double) k);
+#endif
     const double guard = 1e-12 * (1.0 + fabs(q));
     return (f < guard || f > 1.0 - guard) ? int(p / res) : k;
 }

@@ -32,9 +32,11 @@ constexpr int kTileShift = 10, kTile = 1 << kTileShift, kTileThreads = kTile / 4
 
 // voxel key of sub_sample_frame: static_cast<short>(raw / size) per axis (ct_icp.cpp:70-72)
 __device__ __forceinline__ unsigned long long short_voxel_key(const RawPoint &p, double voxel_size) {
-    const short x = (short) (int) (p.x / voxel_size);
-    const short y = (short) (int) (p.y / voxel_size);
-    const short z = (short) (int) (p.z / voxel_size);
+    // int(p / size) from the reciprocal (division only next to an integer quotient: voxel_coord_rcp, device_map.cuh)
+    const double inv = 1.0 / voxel_size;
+    const short x = (short) voxel_coord_rcp(p.x, voxel_size, inv);
+    const short y = (short) voxel_coord_rcp(p.y, voxel_size, inv);
+    const short z = (short) voxel_coord_rcp(p.z, voxel_size, inv);
     return ((unsigned long long) (unsigned short) x << 32) | ((unsigned long long) (unsigned short) y << 16) |
            (unsigned long long) (unsigned short) z;
 }

@@ -256,7 +256,7 @@ __device__ __forceinline__ int warp_gather_knn(const GatherConfig &G, const int 
                     const int vslot = __shfl_sync(0xffffffffu, slot, ol);
                     const bool valid = owner[u] >= 0;
                     const int j = owner[u] >> 8;
-                    const double rx = vx + (double) pv[u].x, ry = vy + (double) pv[u].y, rz = vz + (double) pv[u].z;
+                    const double rx = vx + f32_to_f64(pv[u].x), ry = vy + f32_to_f64(pv[u].y), rz = vz + f32_to_f64(pv[u].z);
                     const double d2 = rx * rx + ry * ry + rz * rz;
                     bool in = valid && !(d2 > G.radius2);
 #ifdef CTICP_PRUNE
@@ -370,6 +370,28 @@ __device__ __forceinline__ Eig3 sym_eig3(double a00, double a01, double a02, dou
 // 3x3 Symmetric Matrices"). One acos + two cos instead of ~15 dependent Jacobi rotations: the dependent fp64 chain
 // of the per-keypoint epilogue shrinks ~5x. The result is verified ((A - e0 I) n ~ 0); the rare failure (two
 // coincident eigenvalues, where the normal is ill-defined anyway) falls back to the Jacobi solver.
+// cos and sin on [0, pi/3] by their Taylor series (x^26 / x^25: truncation < 1e-26, measured error 1.1e-16 = libm's): the
+// trigonometric eigenvalue formula needs cos(t) and cos(t + 2 pi / 3) = -cos(t)/2 - sin(t) sqrt(3)/2. libm's cos costs an
+// argument reduction with two conversions on the XU pipe per call (se3.cuh).
+__device__ __forceinline__ void cos_sin_upto_third_pi(double x, double &c, double &s) {
+    const double x2 = x * x;
+    double pc = -2.4795962632247976e-27, ps = 6.446950284384474e-26;
+    pc = pc * x2 + 1.6117375710961184e-24;  ps = ps * x2 - 3.868170170630684e-23;
+    pc = pc * x2 - 8.896791392450574e-22;   ps = ps * x2 + 1.9572941063391263e-20;
+    pc = pc * x2 + 4.110317623312165e-19;   ps = ps * x2 - 8.22063524662433e-18;
+    pc = pc * x2 - 1.5619206968586225e-16;  ps = ps * x2 + 2.8114572543455206e-15;
+    pc = pc * x2 + 4.779477332387385e-14;   ps = ps * x2 - 7.647163731819816e-13;
+    pc = pc * x2 - 1.1470745597729725e-11;  ps = ps * x2 + 1.6059043836821613e-10;
+    pc = pc * x2 + 2.08767569878681e-09;    ps = ps * x2 - 2.505210838544172e-08;
+    pc = pc * x2 - 2.755731922398589e-07;   ps = ps * x2 + 2.7557319223985893e-06;
+    pc = pc * x2 + 2.48015873015873e-05;    ps = ps * x2 - 0.0001984126984126984;
+    pc = pc * x2 - 0.001388888888888889;    ps = ps * x2 + 0.008333333333333333;
+    pc = pc * x2 + 0.041666666666666664;    ps = ps * x2 - 0.16666666666666666;
+    pc = pc * x2 - 0.5;                     ps = ps * x2 + 1.0;
+    c = pc * x2 + 1.0;
+    s = x * ps;
+}
+
 __device__ __forceinline__ Eig3 sym_eig3_fast(double a00, double a01, double a02, double a11, double a12, double a22) {
     const double mx = fmax(fmax(fmax(fabs(a00), fabs(a01)), fmax(fabs(a02), fabs(a11))), fmax(fabs(a12), fabs(a22)));
     if (!(mx > 0.0)) return sym_eig3(a00, a01, a02, a11, a12, a22);
@@ -384,8 +406,10 @@ __device__ __forceinline__ Eig3 sym_eig3_fast(double a00, double a01, double a02
     const double det = (b00 * c00 - s01 * c01 + s02 * c02) / (p * p * p);
     const double half_det = fmin(fmax(det * 0.5, -1.0), 1.0);
     const double angle = acos(half_det) * (1.0 / 3.0);
-    const double beta2 = 2.0 * cos(angle);
-    const double beta0 = 2.0 * cos(angle + 2.0943951023931953);   // + 2 pi / 3
+    double ca, sa;   // angle in [0, pi/3]
+    cos_sin_upto_third_pi(angle, ca, sa);
+    const double beta2 = 2.0 * ca;
+    const double beta0 = -ca - 1.7320508075688772 * sa;   // 2 cos(angle + 2 pi / 3)
     const double beta1 = -(beta0 + beta2);
     const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;   // e0 <= e1 <= e2
     // rows of (A - e0 I)
@@ -397,7 +421,7 @@ __device__ __forceinline__ Eig3 sym_eig3_fast(double a00, double a01, double a02
     if (d02 > dm) { n = x02; dm = d02; }
     if (d12 > dm) { n = x12; dm = d12; }
     if (!(dm > 0.0)) return sym_eig3(a00, a01, a02, a11, a12, a22);
-    const double ninv = 1.0 / sqrt(dm);
+    const double ninv = rsqrt(dm);
     n = ninv * n;
     // verification in scaled units (|A| ~ 1)
     const double rx = dot(r0, n), ry = dot(r1, n), rz = dot(r2, n);

@@ -114,7 +114,7 @@ struct NeighborSums {
 };
 
 __device__ __forceinline__ int sel_bucket(double d2, double scale) {
-    const int b = (int) (d2 * scale);
+    const int b = f64_floor_nonneg(d2 * scale);   // (= (int) (d2 * scale) for d2 >= 0, off the XU pipe: se3.cuh)
     return b < kSelBuckets - 1 ? b : kSelBuckets - 1;
 }
 
@@ -263,9 +263,9 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
                     }
                 }
             }
-            ox = (kx + dx) * L.res - q.x;
-            oy = (ky + dy) * L.res - q.y;
-            oz = (kz + dz) * L.res - q.z;
+            ox = i32_to_f64(kx + dx) * L.res - q.x;
+            oy = i32_to_f64(ky + dy) * L.res - q.y;
+            oz = i32_to_f64(kz + dz) * L.res - q.z;
         }
         int incl = cnt;
 #pragma unroll
@@ -309,7 +309,7 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
                 const float4 p4 = valid ? S.pts[f] : make_float4(0.f, 0.f, 0.f, 0.f);
                 const double vx = __shfl_sync(0xffffffffu, ox, lo), vy = __shfl_sync(0xffffffffu, oy, lo),
                              vz = __shfl_sync(0xffffffffu, oz, lo);
-                const double rx = vx + (double) p4.x, ry = vy + (double) p4.y, rz = vz + (double) p4.z;
+                const double rx = vx + f32_to_f64(p4.x), ry = vy + f32_to_f64(p4.y), rz = vz + f32_to_f64(p4.z);
                 const double d2 = rx * rx + ry * ry + rz * rz;
                 bool in = valid && !(d2 > G.radius2) && d2 < prune_d2;
                 if (kFilter) {
@@ -345,7 +345,7 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
             const float4 p4 = valid ? __ldg(L.points + (size_t) o_slot * L.B + (f - o_excl)) : make_float4(0.f, 0.f, 0.f, 0.f);
             const double vx = __shfl_sync(0xffffffffu, ox, lo), vy = __shfl_sync(0xffffffffu, oy, lo),
                          vz = __shfl_sync(0xffffffffu, oz, lo);
-            const double rx = vx + (double) p4.x, ry = vy + (double) p4.y, rz = vz + (double) p4.z;
+            const double rx = vx + f32_to_f64(p4.x), ry = vy + f32_to_f64(p4.y), rz = vz + f32_to_f64(p4.z);
             const double d2 = rx * rx + ry * ry + rz * rz;
             bool in = valid && !(d2 > G.radius2) && d2 < prune_d2;
             if (kFilter) {
@@ -403,8 +403,8 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
             for (int u = 0; u < kSelPrefetch; ++u) {
                 if (c0 + 32 * u < total) {           // warp-uniform
                     const int ol = owner[u] < 0 ? 0 : owner[u];
-                    const double rx = S.own_ox[ol] + (double) pv[u].x, ry = S.own_oy[ol] + (double) pv[u].y,
-                                 rz = S.own_oz[ol] + (double) pv[u].z;
+                    const double rx = S.own_ox[ol] + f32_to_f64(pv[u].x), ry = S.own_oy[ol] + f32_to_f64(pv[u].y),
+                                 rz = S.own_oz[ol] + f32_to_f64(pv[u].z);
                     const double d2 = rx * rx + ry * ry + rz * rz;
                     bool in = owner[u] >= 0 && !(d2 > G.radius2) && d2 < prune_d2;
                     if (kFilter) {
@@ -464,7 +464,7 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
                     const int ol = owner[u] < 0 ? 0 : owner[u];
                     const double vx = __shfl_sync(0xffffffffu, ox, ol), vy = __shfl_sync(0xffffffffu, oy, ol),
                                  vz = __shfl_sync(0xffffffffu, oz, ol);
-                    const double rx = vx + (double) pv[u].x, ry = vy + (double) pv[u].y, rz = vz + (double) pv[u].z;
+                    const double rx = vx + f32_to_f64(pv[u].x), ry = vy + f32_to_f64(pv[u].y), rz = vz + f32_to_f64(pv[u].z);
                     const double d2 = rx * rx + ry * ry + rz * rz;
                     bool in = owner[u] >= 0 && !(d2 > G.radius2) && d2 < prune_d2;
                     if (kFilter) {
@@ -550,22 +550,29 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
     __syncwarp();   // S.far is read before the next query's selection rewrites it
 }
 
+// 1.0 / n for the neighbor counts (n <= 32): a table of the correctly rounded quotients instead of I2F + MUFU.RCP64H + Newton
+__constant__ double c_inv_count[33] = {0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10,
+                                       1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19,
+                                       1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28,
+                                       1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32};
+__device__ __forceinline__ double inv_count(int n) { return (n >= 1 && n <= 32) ? c_inv_count[n] : 1.0 / (double) n; }
+
 // TNeighborhood::ComputeNeighborhood + ComputeNeighborhoodInfo (neighborhood.h:226-257, 286-316) from the moments: one
 // THREAD per neighborhood (the epilogue of a tile of queries runs lane-per-query).
 __device__ __forceinline__ NeighborhoodDesc describe_from_sums(const NeighborSums &s) {
-    const double inv = 1.0 / (double) s.n;
+    const double inv = inv_count(s.n);
     const double mx = s.sx * inv, my = s.sy * inv, mz = s.sz * inv;
     const Eig3 e = sym_eig3_fast(s.sxx * inv - mx * mx, s.sxy * inv - mx * my, s.sxz * inv - mx * mz,
                                  s.syy * inv - my * my, s.syz * inv - my * mz, s.szz * inv - mz * mz);
     NeighborhoodDesc d;
     d.normal = e.normal;
-    d.a2D = (sqrt(e.sv1) - sqrt(e.sv2)) / sqrt(e.sv0);
+    d.a2D = (sqrt(e.sv1) - sqrt(e.sv2)) * rsqrt(e.sv0);   // (:302; one MUFU seed less than a division by sqrt)
     d.far_rel = V3{s.fx, s.fy, s.fz};
     d.far_d2 = s.fd2;
     return d;
 }
 __device__ __forceinline__ NeighborhoodDescFull describe_full_from_sums(const NeighborSums &s) {
-    const double inv = 1.0 / (double) s.n;
+    const double inv = inv_count(s.n);
     const double mx = s.sx * inv, my = s.sy * inv, mz = s.sz * inv;
     NeighborhoodDescFull d;
     d.cov[0] = s.sxx * inv - mx * mx;

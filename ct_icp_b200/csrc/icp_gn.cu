@@ -184,16 +184,19 @@ struct __align__(16) TileScratch {
     double rows[kTileMax][13];   // u[0..11], -scalar
 };
 
+// keypoints per warp tile for `span` keypoints over the grid's warps (an integer division: once per kernel, not per iteration)
+__device__ __forceinline__ int gn_tile_width(int span, int warps_total) {
+    const int W = warps_total > 0 ? (span + warps_total - 1) / warps_total : 1;
+    return W < kTileMax ? (W < 1 ? 1 : W) : kTileMax;
+}
+
 __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const int *stencil,
-                                                const float4 *__restrict__ keypoints, int lo, int hi, int warp_global,
+                                                const float4 *__restrict__ keypoints, int lo, int hi, int W, int warp_global,
                                                 int warps_total, const GnPose &pose, TileScratch &T, int lane,
                                                 GnWarpAcc &A, void *bulk = nullptr, bool rigid = false) {
     const GatherConfig &G = cfg.G;
     const GnParams &P = cfg.P;
-    const int span = hi - lo;
-    if (span <= 0) return;
-    int W = (span + warps_total - 1) / warps_total;
-    W = W < kTileMax ? W : kTileMax;
+    if (hi <= lo) return;
     const int need = P.kmin > 5 ? P.kmin : 5;   // ct_icp.cpp:769 ; neighborhood.h:227
     const double inv_res = 1.0 / G.L.res;
     const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
@@ -224,7 +227,7 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
             warp_gather_sums<false>(G, P.bucket_scale, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts, V3{0, 0, 0}, bulk);
             if (lane == 0) {
                 double *o = T.sums[j];
-                o[0] = (double) s.n; o[1] = (double) spts;
+                o[0] = __hiloint2double((int) spts, s.n);   // two integers in one slot: no int <-> double conversion
                 if (s.n >= need) {
                     o[2] = s.sx; o[3] = s.sy; o[4] = s.sz;
                     o[5] = s.sxx; o[6] = s.sxy; o[7] = s.sxz; o[8] = s.syy; o[9] = s.syz; o[10] = s.szz;
@@ -238,9 +241,9 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
         if (lane < wt) {
             const double *o = T.sums[lane];
             NeighborSums mine;
-            mine.n = (int) o[0];
+            mine.n = __double2loint(o[0]);
             A.n_kp += 1;
-            A.n_stencil += (unsigned) o[1];
+            A.n_stencil += (unsigned) __double2hiint(o[0]);
             if (mine.n >= need) {
                 A.n_valid += 1;
                 mine.sx = o[2]; mine.sy = o[3]; mine.sz = o[4];
@@ -299,11 +302,11 @@ __device__ __forceinline__ void gn_store_warp_row(double *row, const GnWarpAcc &
     const int n_used = __reduce_add_sync(0xffffffffu, A.n_used), n_kp = __reduce_add_sync(0xffffffffu, A.n_kp),
               n_valid = __reduce_add_sync(0xffffffffu, A.n_valid);
     if (lane == 0) {
-        row[kAccUsed] = (double) n_used;
+        row[kAccUsed] = i32_to_f64(n_used);
         row[kAccSumSq] = sum_sq;
-        row[kAccStencil] = (double) n_stencil;
-        row[kAccKeypoints] = (double) n_kp;
-        row[kAccValidNb] = (double) n_valid;
+        row[kAccStencil] = i32_to_f64((int) n_stencil);
+        row[kAccKeypoints] = i32_to_f64(n_kp);
+        row[kAccValidNb] = i32_to_f64(n_valid);
         row[95] = 0;
     }
 }
@@ -404,7 +407,8 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
         const int K = *d_num_keypoints;
         const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
         const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-        gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gridDim.x + blockIdx.x, gridDim.x * kGatherWarps, pose,
+        gn_gather_tiles(cfg, stencil, keypoints, lo, hi, gn_tile_width(hi - lo, gridDim.x * kGatherWarps),
+                        w * gridDim.x + blockIdx.x, gridDim.x * kGatherWarps, pose,
                         sh.tile[w], lane, A, bulk_ptr, P.rigid_first && __ldcg(&st->iter) == 0);
     }
     // block reduction (fixed order → run-to-run deterministic)
@@ -489,6 +493,14 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
 #endif
     long long t_loop = 0, t_solve = 0;
     if (solver_cta && threadIdx.x == 0) t_loop = clock64();
+    // this rank's keypoint range and the tile width: constant over the iterations (integer divisions)
+    const int K = *d_num_keypoints;
+    int kp_lo = 0, kp_hi = K;
+    if (P.shard_world > 1) {
+        kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
+        kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+    }
+    const int tile_w = gn_tile_width(kp_hi - kp_lo, gather_ctas * kGatherWarps);
     for (int it = 0; it < num_iters; ++it) {
         // `done` is uniform over the grid: published before the previous grid barrier (the solver CTA reads its own copy)
         if (solver_cta) {
@@ -504,14 +516,8 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             if (sh.done) break;
             if (!(P.debug_flags & 2)) {
                 const GnPose &pose = sh.pose;
-                const int K = *d_num_keypoints;
-                int lo = 0, hi = K;
-                if (P.shard_world > 1) {   // (64-bit divisions: only when the keypoints are sharded)
-                    lo = (int) ((long long) K * P.shard_rank / P.shard_world);
-                    hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-                }
                 // warp index interleaved over the CTAs: a keypoint set smaller than the grid spreads over all SMs
-                gn_gather_tiles(cfg, stencil, keypoints, lo, hi, w * gather_ctas + (blockIdx.x - 1),
+                gn_gather_tiles(cfg, stencil, keypoints, kp_lo, kp_hi, tile_w, w * gather_ctas + (blockIdx.x - 1),
                                 gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A, bulk_ptr, P.rigid_first && it == 0);
             }
             gn_store_warp_row(sh.acc[w], A, lane);

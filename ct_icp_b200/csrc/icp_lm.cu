@@ -103,7 +103,7 @@ struct __align__(16) LmTile {
     double sums[kLmTileMax][14];   // n, stencil points, Σ rel (3), Σ rel rel^T (6), farthest kept (3)
 };
 __device__ __forceinline__ void lm_store_sums(double *o, const NeighborSums &s, unsigned spts, int need) {
-    o[0] = (double) s.n; o[1] = (double) spts;
+    o[0] = __hiloint2double((int) spts, s.n);   // two integers in one slot: no int <-> double conversion (XU pipe, se3.cuh)
     if (s.n >= need) {
         o[2] = s.sx; o[3] = s.sy; o[4] = s.sz;
         o[5] = s.sxx; o[6] = s.sxy; o[7] = s.sxz; o[8] = s.syy; o[9] = s.syz; o[10] = s.szz;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void lm_store_sums(double *o, const NeighborSums &s, 
 }
 __device__ __forceinline__ NeighborSums lm_load_sums(const double *o) {
     NeighborSums s;
-    s.n = (int) o[0];
+    s.n = __double2loint(o[0]);
     s.sx = o[2]; s.sy = o[3]; s.sz = o[4];
     s.sxx = o[5]; s.sxy = o[6]; s.sxz = o[7]; s.syy = o[8]; s.syz = o[9]; s.szz = o[10];
     s.fx = o[11]; s.fy = o[12]; s.fz = o[13]; s.fd2 = 0;
@@ -198,7 +198,7 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
             const int kp = t0 + lane;
             const NeighborSums mine = lm_load_sums(T.sums[lane]);
             n_kp += 1;
-            n_pts += (unsigned long long) T.sums[lane][1];
+            n_pts += (unsigned long long) (unsigned) __double2hiint(T.sums[lane][0]);
             if (mine.n >= need) {
                 const NeighborhoodDesc nd = describe_from_sums(mine);
                 // (the normal flip test at :578 is a no-op: BeginTr - BeginTr)
@@ -306,7 +306,7 @@ __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmPara
             const int kp = t0 + lane;
             const NeighborSums mine = lm_load_sums(T.sums[lane]);
             n_kp += 1;
-            n_pts += (unsigned long long) T.sums[lane][1];
+            n_pts += (unsigned long long) (unsigned) __double2hiint(T.sums[lane][0]);
             int valid = 0;
             if (mine.n >= need) {
                 const NeighborhoodDescFull nd = describe_full_from_sums(mine);

@@ -214,12 +214,42 @@ CT_HD V3 ct_transform(Q4 qb, V3 tb, Q4 qe, V3 te, double alpha, V3 raw) {
 }
 CT_HD V3 ct_transform_c(Q4 qb, V3 tb, Q4 qe, V3 te, double alpha, V3 raw, const SlerpConsts &c) {
     Q4 q = qslerp_c(qb, qe, alpha, c);
+#ifdef __CUDA_ARCH__
+    const double inv = rsqrt(qdot(q, q));   // one MUFU seed instead of sqrt + reciprocal (<= 1 ulp apart)
+#else
     const double inv = 1.0 / sqrt(qdot(q, q));
+#endif
     q = Q4{q.x * inv, q.y * inv, q.z * inv, q.w * inv};
     V3 t = (1.0 - alpha) * tb + alpha * te;
     return qrot(q, raw) + t;
 }
 #ifdef __CUDACC__
+// ---- conversions without the XU pipe ---------------------------------------------------------------------------------
+// Measured on B200 (profiles/r02a: sm__inst_executed_pipe_xu at 41 % of peak over a kernel that is 57 % barrier wait):
+// F2F.F64.F32 / I2F.F64 / F2I.F64 and the 64-bit MUFU seeds share a narrow pipe — ~100 such instructions per
+// keypoint-iteration kept it ~95 % busy while the gather ran, with the fp64 FMA pipe at 4 %. These do the same conversions
+// with integer / fp64-add instructions (exact, all values):
+// float → double: re-bias the exponent, shift the mantissa. Branch-free: fp32 denormals (|x| < 1.2e-38 — no coordinate or
+// offset in metres is one) become zero, inf / nan become huge finite values (never inside a search radius).
+__device__ __forceinline__ double f32_to_f64(float f) {
+    const unsigned u = __float_as_uint(f);
+    const unsigned mag = u & 0x7fffffffu;
+    const bool tiny = mag < 0x00800000u;
+    const unsigned hi = (u & 0x80000000u) | (tiny ? 0u : (mag >> 3) + 0x38000000u);
+    return __hiloint2double((int) hi, tiny ? 0 : (int) (u << 29));
+}
+// int32 → double: 2^52 + 2^31 + i is exact, its low word is i ^ 0x80000000
+__device__ __forceinline__ double i32_to_f64(int i) {
+    return __hiloint2double(0x43300000, i ^ (int) 0x80000000) - 4503601774854144.0;
+}
+// floor of a double in [0, 2^31): rounding-down add of 2^52 leaves floor(x) in the low word
+__device__ __forceinline__ int f64_floor_nonneg(double x) { return __double2loint(__dadd_rd(x, 4503599627370496.0)); }
+// C truncation int(x) for |x| < 2^31
+__device__ __forceinline__ int f64_trunc(double x) {
+    const int k = f64_floor_nonneg(fabs(x));
+    return x < 0.0 ? -k : k;
+}
+
 // A scan point lives on the device as fp32 (x, y, z, alpha) — what LiDAR drivers emit — plus an OPTIONAL residual plane
 // `lo` = value - (double)(float)value (also fp32): hi + lo reproduces an fp64 input to ~2^-48 relative, i.e. exactly as far
 // as voxel assignment and the 1e-4 m tolerance are concerned. lo == nullptr: the scan is float32-representable.
@@ -228,7 +258,7 @@ struct RawPoint {
 };
 __device__ __forceinline__ RawPoint load_raw(const float4 *hi, const float4 *lo, size_t i) {
     const float4 h = hi[i];
-    RawPoint r{(double) h.x, (double) h.y, (double) h.z, (double) h.w};
+    RawPoint r{f32_to_f64(h.x), f32_to_f64(h.y), f32_to_f64(h.z), f32_to_f64(h.w)};
     if (lo) {
         const float4 l = lo[i];
         r.x += (double) l.x; r.y += (double) l.y; r.z += (double) l.z; r.alpha += (double) l.w;

@@ -30,50 +30,36 @@ struct SolveScratch {
 
 // Solve the 12x12 SPD system held in S.A / S.b; x → S.x.
 // Eigen's A.ldlt().solve(b) (ct_icp.cpp:914) is replaced by Gauss-Jordan elimination in natural order on the augmented
-// matrix [A | b] IN SHARED MEMORY: at pivot p the 12 x 13 entries are updated by all 32 lanes at once (five entries per
-// lane: entry (r, c) becomes A[p][c] / A[p][p] on the pivot row and A[r][c] - (A[r][p] / A[p][p]) A[p][c] elsewhere), so a
-// pivot step is one reciprocal, ~15 shared loads, 10 FMAs and 5 stores per lane, and no back-substitution is needed.
-// (Round 1 kept row r in 13 registers of lane r and broadcast the pivot row with 13 fp64 shuffles per step: ~3.5k
-// instructions on one warp per solve — the serial tail of every ICP iteration; this form is ~0.5k.)
-// The system is symmetric positive definite (JTJ/n plus the diagonal regularisers), for which elimination without pivoting
-// is backward stable; the result agrees with a pivoted LDL^T to ~1e-13 relative.
+// matrix [A | b] (no back-substitution). The system is symmetric positive definite (JTJ/n plus the diagonal regularisers),
+// for which elimination without pivoting is backward stable; the result agrees with a pivoted LDL^T to ~1e-13 relative.
+// History of the serial tail this sits in: round 1 kept rows in registers but broadcast all 13 columns at every step and
+// back-substituted (~3.5k instructions); the first round-2 form updated the matrix in shared memory (5 entries per lane and
+// pivot, two barriers per pivot: ~0.5k instructions but 3.9k cycles per solve — every pivot waits for a store -> barrier ->
+// load round trip); this one is ~0.5k instructions with only shuffle latency between pivots.
 static __device__ __forceinline__ void warp_ldlt_solve12(SolveScratch &S, int lane) {
-    if (lane < 12) S.A[lane][12] = S.b[lane];   // augmented column
-    int er[5], ec[5];
+    // Gauss-Jordan on the augmented 12 x 13 system, IN REGISTERS: lane r holds row r; step p broadcasts the pivot row's
+    // remaining entries by shuffles, every lane forms the reciprocal of the pivot itself, and each row is updated with
+    // fully unrolled, compile-time column indices. (The shared-memory form before it paid two barriers plus a
+    // store -> load round trip per pivot: 3.9k cycles per solve on B200; the stamps are in profiles/.) Same operations on the
+    // same operands as before: the pivot row is scaled by 1 / pivot, row r loses (a_rp / pivot) x the OLD pivot row.
+    const int r = lane < 12 ? lane : 0;   // lanes 12..31 mirror row 0 (their results are discarded)
+    double a[13];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int e = lane + 32 * k;            // 156 entries: rows of 13
-        er[k] = e < 156 ? e / 13 : 0;
-        ec[k] = e < 156 ? e % 13 : 0;
-    }
-    __syncwarp();
-    // The reciprocal of pivot p + 1 is started during step p: every lane predicts the entry (p+1, p+1) with the very
-    // expression its owner uses below, so the division's latency overlaps the store / barrier / load of the update instead
-    // of heading every step's dependency chain.
-    auto guarded_rcp = [](double pd) { return (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0; };   // pseudo-inverse like Eigen's D
-    double inv = guarded_rcp(S.A[0][0]);
-#pragma unroll 1
+    for (int c = 0; c < 12; ++c) a[c] = S.A[r][c];
+    a[12] = S.b[r];
+#pragma unroll
     for (int p = 0; p < 12; ++p) {
-        double next_inv = 0.0;
-        if (p < 11) {
-            const double f = S.A[p + 1][p] * inv;
-            next_inv = guarded_rcp(S.A[p + 1][p + 1] - f * S.A[p][p + 1]);
-        }
-        double nv[5];
+        const double pd = __shfl_sync(0xffffffffu, a[p], p);
+        const double inv = (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0;   // pseudo-inverse like Eigen's D
+        const bool is_p = lane == p;
+        const double f = a[p] * inv;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const double arc = S.A[er[k]][ec[k]], arp = S.A[er[k]][p], apc = S.A[p][ec[k]];
-            const double f = arp * inv;
-            nv[k] = er[k] == p ? apc * inv : arc - f * apc;
+        for (int c = p + 1; c < 13; ++c) {
+            const double apc = __shfl_sync(0xffffffffu, a[c], p);
+            a[c] = is_p ? apc * inv : a[c] - f * apc;
         }
-        __syncwarp();   // every lane has read the old matrix
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-            if (lane + 32 * k < 156) S.A[er[k]][ec[k]] = nv[k];
-        __syncwarp();
-        inv = next_inv;
     }
-    if (lane < 12) S.x[lane] = S.A[lane][12];
+    if (lane < 12) S.x[lane] = a[12];
     __syncwarp();
 }
 

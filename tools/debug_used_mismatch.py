@@ -35,19 +35,25 @@ for k, s in enumerate(seq[:frames]):
     for name, od in ods.items():
         sums[name] = od.RegisterFrame(s["xyz"], s["t"], s["frame_idx"])
     so, se = sums["orc"], sums["eng"]
-    print("frame %2d  residuals orc %d eng %d | iters orc %d eng %d | keypoints %d %d" % (
-        k, so.number_of_residuals, se.number_of_residuals, so.icp_summary.num_iters, se.icp_summary.num_iters,
-        so.num_keypoints, se.num_keypoints))
-    if so.number_of_residuals != se.number_of_residuals:
+    from conftest import frame_diff  # noqa: E402
+    dt, dr = frame_diff(so.frame, se.frame)
+    print("frame %2d  residuals orc %d eng %d | keypoints %d %d | map %d %d | pose diff %.3e m %.3e rad" % (
+        k, so.number_of_residuals, se.number_of_residuals, so.num_keypoints, se.num_keypoints, ods["orc"].MapSize(),
+        ods["eng"].MapSize(), dt, dr))
+    if so.number_of_residuals != se.number_of_residuals and first_bad is None:
         first_bad = k
-        break
+        kps = {name: od.keypoints() for name, od in ods.items()}
+        final = {name: sums[name].frame for name in ods}
+        init = {name: sums[name].initial_frame.copy() for name in ods}
+        if len(sys.argv) <= 2:   # a third argument: keep going over the whole sequence (pose differences after the first flip)
+            break
 if first_bad is None:
     print("no mismatch in %d frames" % frames)
     sys.exit(0)
-kps = {name: od.keypoints() for name, od in ods.items()}
+if len(sys.argv) > 2:
+    sys.exit(0)
 print("keypoint records identical (raw, timestamp):", np.array_equal(kps["orc"]["raw"], kps["eng"]["raw"]),
       np.array_equal(kps["orc"]["timestamp"], kps["eng"]["timestamp"]))
-final = {name: sums[name].frame for name in ods}
 
 # pass 2: fresh arms up to the frame before → the maps the bad frame was registered against
 ods2 = {name: b.odometry(opts(b)) for name, b in (("orc", orc), ("eng", eng))}
@@ -87,7 +93,6 @@ o = opts(eng)
 k = first_bad
 traj = ods2["orc"].Trajectory()
 prev = traj[-1] if traj else None
-init = {name: sums[name].initial_frame for name in ods}
 print("initial estimates (end tr):", list(init["orc"].end_pose.tr)[:3], list(init["eng"].end_pose.tr)[:3])
 for n_it in range(1, 17):
     res = {}

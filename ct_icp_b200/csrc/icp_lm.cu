@@ -60,6 +60,10 @@ struct LmParams {
     double threshold_linearity, threshold_planarity, outlier_distance, weight_neighborhood;
 };
 
+// std::pow(x, power_planarity) of the residual weights: the shipped configurations use 2.0 — x * x is that power correctly
+// rounded (what glibc's pow returns for it too), without pow's ~300 instructions in the lane-per-keypoint phase
+__device__ __forceinline__ double pow_weight(double x, double p) { return p == 2.0 ? x * x : pow(x, p); }
+
 struct LmState {
     double x[14];        // current point: qb(4) qe(4) tb(3) te(3)   (Ceres program order of the parameter blocks)
     double cand[14];     // candidate point
@@ -202,7 +206,7 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
             if (mine.n >= need) {
                 const NeighborhoodDesc nd = describe_from_sums(mine);
                 // (the normal flip test at :578 is a no-op: BeginTr - BeginTr)
-                double weight = pow(nd.a2D, P.power_planarity);
+                double weight = pow_weight(nd.a2D, P.power_planarity);
                 const double far_dist = sqrt(nd.far_rel.x * nd.far_rel.x + nd.far_rel.y * nd.far_rel.y + nd.far_rel.z * nd.far_rel.z);
                 weight = P.lambda_weight * weight +
                          P.lambda_neighborhood * exp(-far_dist / (P.max_dist_to_plane * P.min_number_neighbors));   // :582-587
@@ -315,8 +319,8 @@ __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmPara
                 else if (nd.linearity > P.threshold_linearity) cls = LINEAR;
                 if (!P.use_lines && cls == LINEAR) cls = P.threshold_planarity < nd.planarity ? PLANAR : VOLUMIC;   // :1243-1248
                 double weight;
-                if (cls == LINEAR) weight = pow(fabs(nd.linearity), P.power_planarity);
-                else if (cls == PLANAR) weight = pow(fabs(nd.planarity), P.power_planarity);
+                if (cls == LINEAR) weight = pow_weight(fabs(nd.linearity), P.power_planarity);
+                else if (cls == PLANAR) weight = pow_weight(fabs(nd.planarity), P.power_planarity);
                 else weight = P.weight_neighborhood;
                 const V3 d = P.use_barycenter ? nd.mean_rel : nd.far_rel;   // point - world_point
                 double distance;
@@ -589,7 +593,7 @@ struct LmScratch {
     double U[12][12], gu[12];
     double cost;
     double step[12], delta[12];
-    double hs[12];   // rows of H step (model cost change), one per lane
+    double neg[12], proj[14];   // -gradient and x ⊞ (-gradient) of the gradient-norm test
     SolveScratch solve;
     int flag;
 };
@@ -671,6 +675,10 @@ __device__ double norm14(const double *v, int simple = 0) {
     return sqrt(s);
 }
 
+// the 12x12 solve as a call: its 26 live doubles per lane get their own register allocation instead of spilling inside the
+// persistent kernel's 128-register budget (measured: the inlined form made a minimizer step 53k cycles instead of 30k)
+__device__ __noinline__ void lm_solve12(SolveScratch &S, int lane) { warp_ldlt_solve12(S, lane); }
+
 // phase 0: the accumulator holds the evaluation at lm->x (start of ceres::Solve: IterationZero).
 // phase 1: the accumulator holds the evaluation at lm->cand.
 // One warp; the 12x12 solves are warp-collective, the scalar logic runs on lane 0.
@@ -680,11 +688,38 @@ __device__ double norm14(const double *v, int simple = 0) {
 // so the ranks' exchange counters stay in step.
 // The minimizer step on the evaluation held in S.acc (already reduced over this rank's CTAs and, when sharded, over the
 // ranks). ONE WARP; the 12x12 solves are warp-collective, the scalar logic runs on lane 0.
+// x ⊞ delta for the two quaternion blocks (lanes 0, 1) and the six translation components (lanes 2..7) at once
+__device__ __forceinline__ void lm_plus_warp(const double *x, const double *delta, double *out, int lane) {
+    if (lane < 2) {
+        const double *q = x + 4 * lane, *d = delta + 3 * lane;
+        const Q4 r = quat_plus(Q4{q[0], q[1], q[2], q[3]}, d[0], d[1], d[2]);
+        double *o = out + 4 * lane;
+        o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+    } else if (lane < 8) {
+        const int k = lane - 2;
+        out[8 + k] = x[8 + k] + delta[6 + k];
+    }
+    __syncwarp();
+}
+// norm over the problem's parameter blocks, one component per lane (all lanes return the value)
+__device__ __forceinline__ double norm14_warp(const double *v, int simple, int lane) {
+    const bool mine = lane < 14 && (!simple || (lane >= 4 && lane < 8) || lane >= 11);
+    return sqrt(warp_sum(mine ? v[lane] * v[lane] : 0.0));
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmScratch &S, IcpState *st, LmState *lm, int lane) {
     const double min_relative_decrease = 1e-3, function_tolerance = 1e-6, gradient_tolerance = 1e-10,
                  parameter_tolerance = 1e-8, min_radius = 1e-32, max_radius = 1e16, min_lm_diagonal = 1e-6,
                  max_lm_diagonal = 1e32;
     const int R = lm->num_residuals_global;
+    // The scalar bookkeeping of TrustRegionMinimizer is a few dozen numbers: every loop over the 12 tangent directions /
+    // 14 parameters runs one element per lane (reductions by shuffles), lane 0 keeps only the branchy decisions. (The
+    // first cut ran them as serial loops on lane 0 against shared memory: 30k cycles per step on B200.)
 
     // unpack the evaluation: U = J^T J, gu = J^T r, cost (+ regularisers at the evaluated point)
     for (int e = lane; e < 78; e += 32) {
@@ -704,38 +739,33 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
 
     // adopt an evaluation as the current linearisation point (EvaluateGradientAndJacobian)
     auto adopt = [&](bool first) {
+        for (int e = lane; e < 144; e += 32) lm->U[e / 12][e % 12] = S.U[e / 12][e % 12];
         if (lane < 12) {
-            for (int j = 0; j < 12; ++j) lm->U[lane][j] = S.U[lane][j];
             lm->gu[lane] = S.gu[lane];
+            S.neg[lane] = -S.gu[lane];
             if (first) lm->scaling[lane] = 1.0 / (1.0 + sqrt(S.U[lane][lane]));   // jacobi_scaling, iteration 0 only
         }
+        if (lane == 0) lm->x_cost = S.cost;
         __syncwarp();
+        lm_plus_warp(lm->x, S.neg, S.proj, lane);
+        const double gmax = warp_max(lane < 14 ? fabs(lm->x[lane] - S.proj[lane]) : 0.0);
+        const double xn = norm14_warp(lm->x, P.simple, lane);
         if (lane == 0) {
-            lm->x_cost = S.cost;
-            double neg_g[12], proj[14];
-            for (int j = 0; j < 12; ++j) neg_g[j] = -lm->gu[j];
-            lm_plus(lm->x, neg_g, proj);
-            double gmax = 0;
-            for (int i = 0; i < 14; ++i) gmax = fmax(gmax, fabs(lm->x[i] - proj[i]));
             lm->gradient_max_norm = gmax;
+            lm->x_norm = xn;
+            lm->step_is_successful = 1;
         }
         __syncwarp();
     };
 
     if (phase == 0) {
         adopt(true);
-        if (lane == 0) {
-            lm->x_norm = norm14(lm->x, P.simple);
-            lm->step_is_successful = 1;
-        }
-        __syncwarp();
     } else {
         // ComputeCandidatePointAndEvaluateCost happened in k_lm_eval; now the tolerance tests and the step decision
+        const double dx = lane < 14 ? lm->x[lane] - lm->cand[lane] : 0.0;
+        const double step_norm = sqrt(warp_sum(dx * dx));
         if (lane == 0) {
             const double candidate_cost = S.cost;
-            double step_norm = 0;
-            for (int i = 0; i < 14; ++i) step_norm += (lm->x[i] - lm->cand[i]) * (lm->x[i] - lm->cand[i]);
-            step_norm = sqrt(step_norm);
             const double cost_change = lm->x_cost - candidate_cost;
             if (step_norm <= parameter_tolerance * (lm->x_norm + parameter_tolerance)) {
                 S.flag = 1;   // ParameterToleranceReached
@@ -751,7 +781,8 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
                 }
                 if (relative_decrease > min_relative_decrease) {
                     S.flag = 2;   // successful step
-                    lm->radius = lm->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3.0));
+                    const double q3 = 2.0 * relative_decrease - 1.0;   // std::pow(·, 3) with an int exponent: repeated products
+                    lm->radius = lm->radius / fmax(1.0 / 3.0, 1.0 - q3 * q3 * q3);
                     lm->radius = fmin(max_radius, lm->radius);
                     lm->decrease_factor = 2.0;
                     lm->reuse_diagonal = 0;
@@ -773,22 +804,17 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
             if (lane < 14) lm->x[lane] = lm->cand[lane];
             __syncwarp();
             adopt(false);
-            if (lane == 0) {
-                lm->x_norm = norm14(lm->x, P.simple);
-                lm->step_is_successful = 1;
-            }
-            __syncwarp();
         }
     }
 
     // main loop of TrustRegionMinimizer::Minimize until a candidate needs evaluating or the solve terminates
     for (int guard = 0; guard < 64; ++guard) {
+        const bool improved = lm->step_is_successful && lm->x_cost < lm->minimum_cost;   // FinalizeIterationAndCheck…
+        __syncwarp();
+        if (improved && lane < 14) lm->best[lane] = lm->x[lane];
         if (lane == 0) {
             S.flag = 0;
-            if (lm->step_is_successful && lm->x_cost < lm->minimum_cost) {   // FinalizeIterationAndCheck…
-                lm->minimum_cost = lm->x_cost;
-                for (int i = 0; i < 14; ++i) lm->best[i] = lm->x[i];
-            }
+            if (improved) lm->minimum_cost = lm->x_cost;
             if (lm->iteration >= P.ls_max_num_iters) S.flag = 1;
             else if (lm->step_is_successful && lm->gradient_max_norm <= gradient_tolerance) S.flag = 1;
             else if (lm->radius <= min_radius) S.flag = 1;
@@ -800,40 +826,45 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
             return;
         }
         // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
-        if (lane < 12) {
+        if (lane < 12 && !lm->reuse_diagonal) {
             const double sl = lm->scaling[lane];
-            if (!lm->reuse_diagonal) {
-                const double d = lm->U[lane][lane] * sl * sl;
-                lm->diagonal[lane] = fmin(fmax(d, min_lm_diagonal), max_lm_diagonal);
-            }
-            for (int j = 0; j < 12; ++j) S.solve.A[lane][j] = lm->U[lane][j] * sl * lm->scaling[j];
-            S.solve.b[lane] = lm->gu[lane] * sl;
+            const double d = lm->U[lane][lane] * sl * sl;
+            lm->diagonal[lane] = fmin(fmax(d, min_lm_diagonal), max_lm_diagonal);
         }
         __syncwarp();
-        if (lane < 12) S.solve.A[lane][lane] += lm->diagonal[lane] / lm->radius;
+        {
+            const double inv_radius_num = lm->radius;
+            for (int e = lane; e < 144; e += 32) {
+                const int i = e / 12, j = e - 12 * i;
+                double v = lm->U[i][j] * lm->scaling[i] * lm->scaling[j];
+                if (i == j) v += lm->diagonal[i] / inv_radius_num;
+                S.solve.A[i][j] = v;
+            }
+            if (lane < 12) S.solve.b[lane] = lm->gu[lane] * lm->scaling[lane];
+        }
         __syncwarp();
-        warp_ldlt_solve12(S.solve, lane);   // (J'J + D^2) y = J'r
+        lm_solve12(S.solve, lane);   // (J'J + D^2) y = J'r
         if (lane < 12) S.step[lane] = -S.solve.x[lane];
         __syncwarp();
-        if (lane < 12) {   // row `lane` of H step, the twelve rows at once (same order of operations as a serial loop)
+        // model_cost_change = -(J step)'(f + J step / 2) = -step'g - step'H step / 2   (scaled quantities)
+        double sg_l = 0, shs_l = 0;
+        bool finite_l = true;
+        if (lane < 12) {   // row `lane` of H step, the twelve rows at once
             double hs = 0;
             for (int b = 0; b < 12; ++b) hs += lm->U[lane][b] * lm->scaling[lane] * lm->scaling[b] * S.step[b];
-            S.hs[lane] = hs;
+            sg_l = S.step[lane] * lm->gu[lane] * lm->scaling[lane];
+            shs_l = S.step[lane] * hs;
+            finite_l = isfinite(S.step[lane]);
+            S.delta[lane] = S.step[lane] * lm->scaling[lane];
         }
-        __syncwarp();
+        const double sg = warp_sum(sg_l), shs = warp_sum(shs_l);
+        const bool finite = __all_sync(0xffffffffu, finite_l);
+        const double mcc = -sg - 0.5 * shs;
+        const bool valid_step = finite && mcc > 0.0;
         if (lane == 0) {
             lm->reuse_diagonal = 1;
-            bool finite = true;
-            for (int j = 0; j < 12; ++j) finite = finite && isfinite(S.step[j]);
-            // model_cost_change = -(J step)'(f + J step / 2) = -step'g - step'H step / 2   (scaled quantities)
-            double sg = 0, shs = 0;
-            for (int a = 0; a < 12; ++a) {
-                sg += S.step[a] * lm->gu[a] * lm->scaling[a];
-                shs += S.step[a] * S.hs[a];
-            }
-            const double mcc = -sg - 0.5 * shs;
             lm->model_cost_change = mcc;
-            if (!(finite && mcc > 0.0)) {   // HandleInvalidStep
+            if (!valid_step) {   // HandleInvalidStep
                 lm->num_invalid += 1;
                 if (lm->num_invalid >= 5) {
                     lm->usable = 0;
@@ -846,11 +877,10 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
                 }
             } else {
                 lm->num_invalid = 0;
-                for (int j = 0; j < 12; ++j) S.delta[j] = S.step[j] * lm->scaling[j];
-                lm_plus(lm->x, S.delta, lm->cand);
             }
         }
         __syncwarp();
+        if (valid_step) lm_plus_warp(lm->x, S.delta, lm->cand, lane);
         if (S.flag == 1) {
             if (lane == 0) lm->done = 1;
             return;

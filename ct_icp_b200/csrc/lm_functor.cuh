@@ -31,7 +31,11 @@ __device__ __forceinline__ Dual dsqrt(Dual x) {
     const double r = sqrt(x.a);
     return {r, x.d / (2.0 * r)};
 }
-__device__ __forceinline__ Dual dsin(Dual x) { return {sin(x.a), cos(x.a) * x.d}; }
+// (the slerp angles of one sweep are far below 0.5 rad: polynomials of se3.cuh, libm beyond)
+__device__ __forceinline__ Dual dsin(Dual x) {
+    const bool small = fabs(x.a) <= 0.5;
+    return {small ? sin_upto_half(x.a) : sin(x.a), (small ? cos_upto_half(x.a) : cos(x.a)) * x.d};
+}
 __device__ __forceinline__ Dual dacos(Dual x) { return {acos(x.a), -x.d / sqrt(1.0 - x.a * x.a)}; }
 
 struct DQuat {
@@ -77,8 +81,15 @@ __device__ __forceinline__ void quat_plus_column(const double q[4], int j, doubl
 CT_HD Q4 quat_plus(Q4 q, double dx, double dy, double dz) {
     const double n = sqrt(dx * dx + dy * dy + dz * dz);
     if (n > 0.0) {
-        const double s = sin(n) / n;
-        return qmul(Q4{s * dx, s * dy, s * dz, cos(n)}, q);
+#ifdef __CUDA_ARCH__
+        // an LM step's rotation is far below 0.5 rad: polynomials (se3.cuh) instead of libm's argument reduction
+        const bool small = n <= 0.5;
+        const double s = (small ? sin_upto_half(n) : sin(n)) / n;
+        const double c = small ? cos_upto_half(n) : cos(n);
+#else
+        const double s = sin(n) / n, c = cos(n);
+#endif
+        return qmul(Q4{s * dx, s * dy, s * dz, c}, q);
     }
     return q;
 }

@@ -588,7 +588,27 @@ k_lm_reduce(const double *__restrict__ partials, int nblocks, double *__restrict
 }
 
 // ---- the minimizer ------------------------------------------------------------------------------------------
+// what the regularisers read of the registration state: constant over a frame, kept next to the minimizer's scratch so
+// that the serial step never waits for global memory (each of its ~25 reads of `st` was a dependent L2 round trip)
+struct LmRegs {
+    int has_motion_model;
+    double beta_location, beta_orientation, beta_cv, beta_small;
+    double prev_tb[3], prev_te[3], prev_qe[4];
+};
+__device__ __forceinline__ void lm_load_regs(LmRegs &r, const IcpState *st, int lane) {   // one warp; independent loads
+    if (lane == 0) r.has_motion_model = st->has_motion_model;
+    if (lane == 1) r.beta_location = st->beta_location;
+    if (lane == 2) r.beta_orientation = st->beta_orientation;
+    if (lane == 3) r.beta_cv = st->beta_cv;
+    if (lane == 4) r.beta_small = st->beta_small;
+    if (lane >= 5 && lane < 8) r.prev_tb[lane - 5] = st->prev_tb[lane - 5];
+    if (lane >= 8 && lane < 11) r.prev_te[lane - 8] = st->prev_te[lane - 8];
+    if (lane >= 11 && lane < 15) r.prev_qe[lane - 11] = st->prev_qe[lane - 11];
+    __syncwarp();
+}
+
 struct LmScratch {
+    LmRegs regs;
     double acc[kAcc];
     double U[12][12], gu[12];
     double cost;
@@ -600,7 +620,7 @@ struct LmScratch {
 
 // regularisers (PreviousFrameMotionModel::AddConstraintsToCeresProblem, motion_model.cpp:12-61), no loss function:
 // adds their J^T J, J^T r and cost at the point p to (U, gu, cost). Serial (lane 0).
-__device__ void add_regularisers(const IcpState *st, int R, const double *p, double U[12][12], double gu[12], double &cost) {
+__device__ void add_regularisers(const LmRegs *st, int R, const double *p, double U[12][12], double gu[12], double &cost) {
     if (!st->has_motion_model) return;
     const double *qb = p, *tb = p + 8, *te = p + 11;
     if (st->beta_location > 0.) {   // LocationConsistencyFunctor on begin_t
@@ -732,7 +752,7 @@ __device__ __forceinline__ void lm_step_device(const LmParams &P, int phase, LmS
     if (lane == 0) {
         S.cost = S.acc[kAccCost];
         if (!P.simple)   // AddConstraintsToCeresProblem only with CONTINUOUS_TIME (ct_icp.cpp:613)
-            add_regularisers(st, R, phase == 0 ? lm->x : lm->cand, S.U, S.gu, S.cost);
+            add_regularisers(&S.regs, R, phase == 0 ? lm->x : lm->cand, S.U, S.gu, S.cost);
         S.flag = 0;
     }
     __syncwarp();
@@ -928,6 +948,7 @@ k_lm_step(LmParams P, int phase, const double *__restrict__ partials, int nblock
         if (!ok) return;
     }
     if (w != 0) return;
+    lm_load_regs(S.regs, st, lane);
     lm_step_device(P, phase, S, st, lm, lane);
 }
 
@@ -1052,6 +1073,7 @@ k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoint
     unsigned int peer_seq = 0;
     if (solver) {
         if (kPeers) peer_seq = *links.seq;
+        if (w == 1) lm_load_regs(sh.solver.S.regs, st, lane);
         if (tid == 0) lm_begin_device(st, lm, stats);
         __syncthreads();
         lm_publish(lm_g, lm, tid);

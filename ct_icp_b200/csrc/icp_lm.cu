@@ -695,9 +695,8 @@ __device__ double norm14(const double *v, int simple = 0) {
     return sqrt(s);
 }
 
-// the 12x12 solve as a call: its 26 live doubles per lane get their own register allocation instead of spilling inside the
-// persistent kernel's 128-register budget (measured: the inlined form made a minimizer step 53k cycles instead of 30k)
-__device__ __noinline__ void lm_solve12(SolveScratch &S, int lane) { warp_ldlt_solve12(S, lane); }
+// the minimizer step is bound by instruction fetch (see small_solve.cuh): the compact shared-memory form of the solve
+__device__ __forceinline__ void lm_solve12(SolveScratch &S, int lane) { warp_ldlt_solve12_compact(S, lane); }
 
 // phase 0: the accumulator holds the evaluation at lm->x (start of ceres::Solve: IterationZero).
 // phase 1: the accumulator holds the evaluation at lm->cand.

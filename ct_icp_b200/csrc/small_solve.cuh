@@ -63,5 +63,41 @@ static __device__ __forceinline__ void warp_ldlt_solve12(SolveScratch &S, int la
     __syncwarp();
 }
 
+// The same elimination on the augmented matrix in shared memory, as a 12-trip loop (five entries per lane and pivot): ~60
+// instructions of code instead of ~500. For callers whose serial tail is bound by INSTRUCTION FETCH rather than latency —
+// the CERES minimizer step runs ~1k instructions once per evaluation on one warp, cold in the 32 KB L1.5 I-cache every time
+// (the workers' code streams through the cache in between): measured 30k cycles per step with this form, 53k with the
+// unrolled register form above inlined, 61k with it as a call (profiles/README.md).
+static __device__ __forceinline__ void warp_ldlt_solve12_compact(SolveScratch &S, int lane) {
+    if (lane < 12) S.A[lane][12] = S.b[lane];   // augmented column
+    int er[5], ec[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int e = lane + 32 * k;            // 156 entries: rows of 13
+        er[k] = e < 156 ? e / 13 : 0;
+        ec[k] = e < 156 ? e % 13 : 0;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int p = 0; p < 12; ++p) {
+        const double pd = S.A[p][p];
+        const double inv = (fabs(pd) > 2.2250738585072014e-308) ? 1.0 / pd : 0.0;   // pseudo-inverse like Eigen's D
+        double nv[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double arc = S.A[er[k]][ec[k]], arp = S.A[er[k]][p], apc = S.A[p][ec[k]];
+            const double f = arp * inv;
+            nv[k] = er[k] == p ? apc * inv : arc - f * apc;
+        }
+        __syncwarp();   // every lane has read the old matrix
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (lane + 32 * k < 156) S.A[er[k]][ec[k]] = nv[k];
+        __syncwarp();
+    }
+    if (lane < 12) S.x[lane] = S.A[lane][12];
+    __syncwarp();
+}
+
 
 }  // namespace cticp

@@ -8,14 +8,16 @@
 #   6. the bench line with the extra workloads and the CPU baselines                                [all only]
 # usage (on the box): bash tools/gpu_check.sh <tag> [pytest|bench|quick|all]
 TAG=${1:-x}; WHAT=${2:-all}
-mkdir -p gpurun_out
+mkdir -p gpurun_out; rm -f gpurun_out/parity_worst.*.json
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/${TAG}_gpu.txt 2>&1
 RC=0
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 if [ "$WHAT" != "bench" ]; then
   timeout 1500 python -m pytest tests -m gpu -q -n 6 --tb=short -p no:cacheprovider > gpurun_out/${TAG}_pytest.log 2>&1
   RC=$?
   echo "rc=$RC" >> gpurun_out/${TAG}_pytest.log
   tail -40 gpurun_out/${TAG}_pytest.log
+  python tools/summarize_parity.py gpurun_out gpurun_out/${TAG}_parity_worst.json > gpurun_out/${TAG}_parity_worst.txt 2>&1
   if [ $RC -ne 0 ]; then
     # which switch breaks it? a fast subset under each fallback
     SUB="sequence_small or gn_register or gn_normal or ceres_register_matches_oracle or robust_register or neighborhoods"
@@ -60,7 +62,9 @@ PY
       --workload kitti64_ceres 2>&1 | grep "LM loop, solver CTA" | tail -6 | tee -a gpurun_out/${TAG}_solver_cta_stamps.log
 fi
 if [ "$WHAT" = "all" ]; then
-  echo "---- profile"; bash tools/gpu_profile.sh ${TAG} kitti64_gn 2>&1 | tail -12
+  echo "---- profile"; bash tools/gpu_profile.sh ${TAG} kitti64_gn 2>&1 | tail -14
+  # dense workload (K ~ 32k: 14 keypoints per warp tile): 9 frames, the capture is the GN launch of the last one
+  echo "---- profile dense128"; bash tools/gpu_profile.sh ${TAG}_dense dense128_gn 9 7 2>&1 | tail -14
   echo "---- A/B"; timeout 2400 bash tools/ab_variants.sh run gpurun_out/${TAG}_ab 2>&1 | tail -12
   echo "---- sanitizer"; timeout 2400 bash tools/gpu_sanitize.sh ${TAG} 2>&1 | tail -12
   echo "---- full bench"; timeout 1500 python bench.py > gpurun_out/${TAG}_bench_full.json 2> gpurun_out/${TAG}_bench_full.err

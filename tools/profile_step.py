@@ -13,13 +13,13 @@ from ct_icp_b200 import synthetic as syn  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=26)
-ap.add_argument("--sensor", default="hdl64e", help="hdl64e (the bench workload: suburb scene) | hdl64 (street scene) | dense128")
+ap.add_argument("--sensor", default="workload", help="workload (the bench workload's sensor on the suburb scene) | hdl64 (street scene) | dense128 (street scene)")
 ap.add_argument("--workload", default="kitti64_gn", choices=sorted(bench.WORKLOADS))
 args = ap.parse_args()
 eng = ct_icp_b200.engine()
 bench._WORKLOAD = args.workload
-if args.sensor == "hdl64e":
-    seq = bench.make_scans(args.frames, "HDL64E")
+if args.sensor == "workload":
+    seq = bench.make_scans(args.frames, bench.WORKLOADS[args.workload][0])
 else:
     seq = syn.make_sequence(args.frames, {"hdl64": syn.HDL64, "dense128": syn.DENSE128}[args.sensor], seed=1234)
 od = eng.odometry(bench.make_options(eng))

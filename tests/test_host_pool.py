@@ -29,3 +29,16 @@ def test_peer_exchange_protocol_model():
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "PEER PROTOCOL OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_engine_math_header_on_the_host():
+    """csrc/se3.cuh + device_map.cuh compile with plain g++: the polynomial sin / cos, the slerp with hoisted constants, the
+    reciprocal voxel coordinate, and models of the device's conversion tricks against their exact definitions."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = os.path.join(ROOT, "tests", "cpp", "se3_math_test")
+    r = subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-I", "/usr/local/cuda/include", "-I",
+                        os.path.join(ROOT, "ct_icp_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cpp", "se3_math_test.cpp"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SE3 MATH OK" in r.stdout, r.stdout + r.stderr

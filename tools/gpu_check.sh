@@ -69,6 +69,6 @@ if [ "$WHAT" = "all" ]; then
   echo "---- sanitizer"; timeout 2400 bash tools/gpu_sanitize.sh ${TAG} 2>&1 | tail -12
   echo "---- full bench"; timeout 1500 python bench.py > gpurun_out/${TAG}_bench_full.json 2> gpurun_out/${TAG}_bench_full.err
   echo "full bench rc=$?"; tail -3 gpurun_out/${TAG}_bench_full.err; cat gpurun_out/${TAG}_bench_full.json
-  echo "---- reference arm"; timeout 900 python bench.py --impl reference --steps 20 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
+  echo "---- reference arm"; timeout 900 python bench.py --impl reference > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
   cat gpurun_out/${TAG}_bench_reference.json | cut -c1-600
 fi

@@ -225,10 +225,11 @@ CT_HD V3 ct_transform_c(Q4 qb, V3 tb, Q4 qe, V3 te, double alpha, V3 raw, const 
 }
 #ifdef __CUDACC__
 // ---- conversions without the XU pipe ---------------------------------------------------------------------------------
-// Measured on B200 (profiles/r02a: sm__inst_executed_pipe_xu at 41 % of peak over a kernel that is 57 % barrier wait):
-// F2F.F64.F32 / I2F.F64 / F2I.F64 and the 64-bit MUFU seeds share a narrow pipe — ~100 such instructions per
-// keypoint-iteration kept it ~95 % busy while the gather ran, with the fp64 FMA pipe at 4 %. These do the same conversions
-// with integer / fp64-add instructions (exact, all values):
+// F2F.F64.F32 / I2F.F64 / F2I.F64 and the 64-bit MUFU seeds of divisions and square roots execute on the XU pipe: few lanes
+// per clock and a long latency, and every one of them sits ON the dependent chain of a keypoint (the gather kernels are
+// bound by that chain, not by any pipe's throughput: profiles/README.md). The first round-2 build executed ~100 of them per
+// keypoint-iteration; these helpers do the same conversions with integer / fp64-add instructions (exact, all values),
+// worth 8 % of the GN loop together with the polynomial sin / cos and the 1/n table:
 // float → double: re-bias the exponent, shift the mantissa. Branch-free: fp32 denormals (|x| < 1.2e-38 — no coordinate or
 // offset in metres is one) become zero, inf / nan become huge finite values (never inside a search radius).
 __device__ __forceinline__ double f32_to_f64(float f) {

@@ -344,8 +344,47 @@ int Engine::HostTeamSize(int ranks_on_node) {
 }
 
 // ---- host fork-join pool -------------------------------------------------------------------------------------
+// The CPUs of the caller's socket (those the process may use): the team is kept on ONE socket. Measured on the 2 x 32-core
+// host of the B200 box (profiles/README.md): a team scattered over both sockets packs a 130k-point scan in 145-175 us,
+// the same team confined to either socket in 100-110 us (the pinned staging buffer and the caller's arrays are then
+// local to everyone, and the parts' barrier does not cross the socket link).
+static bool SocketCpuSet(cpu_set_t *out) {
+    const char *env = getenv("CTICP_HOST_AFFINITY");
+    if (env && atoi(env) == 0) return false;
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return false;
+    const int me = sched_getcpu();
+    if (me < 0) return false;
+    auto package_of = [](int cpu) {
+        char path[128];
+        snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/physical_package_id", cpu);
+        FILE *f = fopen(path, "r");
+        int id = -1;
+        if (f) {
+            if (fscanf(f, "%d", &id) != 1) id = -1;
+            fclose(f);
+        }
+        return id;
+    };
+    const int mine = package_of(me);
+    if (mine < 0) return false;
+    CPU_ZERO(out);
+    int count = 0, others = 0;
+    for (int c = 0; c < CPU_SETSIZE; ++c) {
+        if (!CPU_ISSET(c, &allowed)) continue;
+        if (package_of(c) == mine) { CPU_SET(c, out); ++count; }
+        else ++others;
+    }
+    return count >= 2 && others > 0;   // single-socket machines: nothing to do
+}
+
 HostPool::HostPool(int threads) {
-    for (int i = 1; i < threads; ++i) workers_.emplace_back([this, i] { Worker(i); });
+    cpu_set_t socket;
+    const bool pin = threads > 1 && SocketCpuSet(&socket);
+    for (int i = 1; i < threads; ++i) {
+        workers_.emplace_back([this, i] { Worker(i); });
+        if (pin) pthread_setaffinity_np(workers_.back().native_handle(), sizeof(socket), &socket);   // best effort
+    }
 }
 HostPool::~HostPool() {
     {
@@ -447,20 +486,46 @@ namespace {
 // not by this core — keeping it out of the CPU caches took the H2D copy from ~12 GB/s, snooped dirty lines, to PCIe
 // speed); for float64 sources also the residual plane lo = value - hi, and whether any coordinate needs it
 template <typename XT>
-inline void PackPoint(XT x, XT y, XT z, double a, float4 *dst, float4 *dst_lo, bool *any_lo) {
+inline void PackPoint(XT x, XT y, XT z, double a, float4 *dst, bool *any_lo) {
     const float fx = (float) x, fy = (float) y, fz = (float) z, fa = (float) a;
     _mm_stream_ps(reinterpret_cast<float *>(dst), _mm_set_ps(fa, fz, fy, fx));
     if constexpr (std::is_same<XT, double>::value) {
-        const float lx = (float) (x - (double) fx), ly = (float) (y - (double) fy), lz = (float) (z - (double) fz);
-        _mm_stream_ps(reinterpret_cast<float *>(dst_lo), _mm_set_ps((float) (a - (double) fa), lz, ly, lx));
-        if (lx != 0.f || ly != 0.f || lz != 0.f) *any_lo = true;
+        // does any coordinate need the residual plane? (float64 arrays usually hold float32 values: then nothing more is
+        // computed, stored or uploaded; otherwise PackLoPlane makes a second pass)
+        if ((double) fx != x || (double) fy != y || (double) fz != z) *any_lo = true;
     }
 }
 }  // namespace
 
-// returns whether the scan needs its residual plane (float64 coordinates that are not float32-representable); dst_lo is
-// written iff the coordinates are float64
-bool Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst, float4 *dst_lo) {
+// The residual plane of a float64 scan (value - (double)(float)value per component, alpha included): second pass, only for
+// scans that need it.
+void Engine::PackLoPlane(const ScanView &scan, double bts, double ets, float4 *dst_lo) {
+    const double mn = std::min(bts, ets), mx = std::max(bts, ets);
+    const bool spans = mx > mn;
+    const double inv = spans ? 1.0 / (mx - mn) : 0.0;
+    const char *px = static_cast<const char *>(scan.xyz), *pt = static_cast<const char *>(scan.t);
+    const size_t xs = scan.xyz_stride, ts = scan.t_stride;
+    DispatchScanTypes(scan, [&](auto xt, auto tt) {
+        using XT = typename decltype(xt)::type;
+        using TT = typename decltype(tt)::type;
+        pool_->ParallelFor(scan.n, [&](size_t b, size_t e, int) {
+            for (size_t i = b; i < e; ++i) {
+                const char *p = px + i * xs;
+                const double x = (double) LoadUnaligned<XT>(p), y = (double) LoadUnaligned<XT>(p + sizeof(XT)),
+                             z = (double) LoadUnaligned<XT>(p + 2 * sizeof(XT));
+                const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
+                const double a = spans ? (ti - mn) * inv : 1.0;
+                _mm_stream_ps(reinterpret_cast<float *>(dst_lo + i),
+                              _mm_set_ps((float) (a - (double) (float) a), (float) (z - (double) (float) z),
+                                         (float) (y - (double) (float) y), (float) (x - (double) (float) x)));
+            }
+            _mm_sfence();
+        });
+    });
+}
+
+// returns whether the scan needs its residual plane (float64 coordinates that are not float32-representable)
+bool Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst) {
     std::atomic<bool> needs_lo{false};
     const double mn = std::min(bts, ets), mx = std::max(bts, ets);
     const double inv = (mx > mn) ? 1.0 / (mx - mn) : 0.0;
@@ -477,7 +542,7 @@ bool Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst,
                 const XT x = LoadUnaligned<XT>(p), y = LoadUnaligned<XT>(p + sizeof(XT)), z = LoadUnaligned<XT>(p + 2 * sizeof(XT));
                 const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
                 const double a = spans ? (ti - mn) * inv : 1.0;
-                PackPoint<XT>(x, y, z, a, dst + i, dst_lo + i, &any);
+                PackPoint<XT>(x, y, z, a, dst + i, &any);
             }
             _mm_sfence();
             if (any) needs_lo.store(true, std::memory_order_relaxed);
@@ -498,11 +563,13 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
     const size_t n = scan.n;
     const int parts = pool_->PartsFor(n);
     const int rounds = parts == 1 ? 1 : kRounds;
-    const size_t pieces = (size_t) rounds * (size_t) parts;
+    // with a team of four or more, part 0 (the caller's thread) packs nothing: it only enqueues the copy of each round the
+    // moment the round is complete — its driver calls would otherwise sit on the packing's critical path
+    const int first_packer = parts >= 4 ? 1 : 0, packers = parts - first_packer;
+    const size_t pieces = (size_t) rounds * (size_t) packers;
     const char *px = static_cast<const char *>(scan.xyz), *pt = static_cast<const char *>(scan.t);
     const size_t xs = scan.xyz_stride, ts = scan.t_stride;
     float4 *dst = pipe_->Staging();
-    float4 *dst_lo = scan.xyz_dtype == CTICP_DTYPE_FLOAT64 ? pipe_->StagingLo() : nullptr;   // residual plane (PackPoint)
     std::atomic<bool> needs_lo{false};
     double mns[64], mxs[64];
     std::atomic<int> arrived{0};
@@ -548,13 +615,13 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
             int issued = 0;
             auto issue_ready = [&](bool wait_all) {   // part 0 only
                 while (issued < rounds) {
-                    if (round_done[issued].load(std::memory_order_acquire) < nparts) {
+                    if (round_done[issued].load(std::memory_order_acquire) < packers) {
                         if (!wait_all) return;
                         _mm_pause();
                         continue;
                     }
                     try {
-                        pipe_->UploadRange(piece_begin((size_t) issued * nparts), piece_begin((size_t) (issued + 1) * nparts));
+                        pipe_->UploadRange(piece_begin((size_t) issued * packers), piece_begin((size_t) (issued + 1) * packers));
                     } catch (...) {
                         failed.store(true);
                     }
@@ -562,15 +629,15 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
                 }
             };
             bool any = false;
-            for (int r = 0; r < rounds; ++r) {
-                const size_t piece = (size_t) r * nparts + part;
+            for (int r = 0; r < rounds && part >= first_packer; ++r) {
+                const size_t piece = (size_t) r * packers + (size_t) (part - first_packer);
                 const size_t b = piece_begin(piece), e = piece_begin(piece + 1);
                 for (size_t i = b; i < e; ++i) {
                     const char *p = px + i * xs;
                     const XT x = LoadUnaligned<XT>(p), y = LoadUnaligned<XT>(p + sizeof(XT)), z = LoadUnaligned<XT>(p + 2 * sizeof(XT));
                     const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
                     const double a = spans ? (ti - mn) * inv : 1.0;
-                    PackPoint<XT>(x, y, z, a, dst + i, dst_lo + i, &any);
+                    PackPoint<XT>(x, y, z, a, dst + i, &any);
                 }
                 _mm_sfence();
                 if (any) needs_lo.store(true, std::memory_order_relaxed);
@@ -580,8 +647,13 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
             if (part == 0) issue_ready(true);
         });
     });
-    // float64 coordinates that float32 cannot hold: the residual plane follows (one more copy; float32 scans never get here)
-    if (needs_lo.load()) pipe_->UploadLo(n);
+    // float64 coordinates that float32 cannot hold: the residual plane follows (a second pass + one more copy; scans of
+    // float32 values never get here)
+    if (needs_lo.load()) {
+        const double bts = pose_timestamps ? pose_timestamps[0] : *mn_out, ets = pose_timestamps ? pose_timestamps[1] : *mx_out;
+        PackLoPlane(scan, bts, ets, pipe_->StagingLo());
+        pipe_->UploadLo(n);
+    }
     if (debug) cudaEventRecord(ev_[5], stream_);
     if (failed.load()) throw CudaError("cudaMemcpyAsync (scan upload)");
 }
@@ -620,8 +692,9 @@ int64_t Engine::StageFrame(const ScanView &scan) {
     sc.n = n;
     MinMaxTimestamps(scan, &sc.t_min, &sc.t_max);
     CT_CUDA_CHECK(cudaStreamSynchronize(stream_));   // the pinned staging buffer may still feed a previous copy
-    float4 *stage_lo = scan.xyz_dtype == CTICP_DTYPE_FLOAT64 ? pipe_->StagingLo() : nullptr;
-    const bool needs_lo = PackScan(scan, sc.t_min, sc.t_max, pipe_->Staging(), stage_lo);
+    const bool needs_lo = PackScan(scan, sc.t_min, sc.t_max, pipe_->Staging());
+    float4 *stage_lo = needs_lo ? pipe_->StagingLo() : nullptr;
+    if (needs_lo) PackLoPlane(scan, sc.t_min, sc.t_max, stage_lo);
     CT_CUDA_CHECK(cudaMalloc(&sc.d_points, sizeof(float4) * n));
     CT_CUDA_CHECK(cudaMemcpyAsync(sc.d_points, pipe_->Staging(), sizeof(float4) * n, cudaMemcpyHostToDevice, stream_));
     if (needs_lo) {

@@ -143,7 +143,8 @@ private:
     void ResolvePoints(int which, const float4 **out_pts, const float4 **out_lo, const double **out_world, size_t *out_count);
     void IngestImpl(const ScanView &scan,
                     const FrameInfo &info, int64_t staged_slot);
-    bool PackScan(const ScanView &scan, double bts, double ets, float4 *dst, float4 *dst_lo);
+    bool PackScan(const ScanView &scan, double bts, double ets, float4 *dst);
+    void PackLoPlane(const ScanView &scan, double bts, double ets, float4 *dst_lo);
     // one parallel region: timestamp min/max → team barrier → (x, y, z, alpha) packing in rounds, the H2D copy of a
     // round enqueued as soon as the round is complete (the copy engine runs while the later rounds are still packed)
     void PackAndUpload(const ScanView &scan, const double *pose_timestamps, double *mn_out, double *mx_out);

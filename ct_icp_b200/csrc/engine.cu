@@ -581,6 +581,8 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
     auto piece_begin = [&](size_t piece) { return piece >= pieces ? n : (n * piece / pieces) & ~size_t(3); };
     pipe_->UploadBegin(n);
     if (debug) cudaEventRecord(ev_[4], stream_);
+    const auto t_region = hclock::now();
+    double dbg_barrier_ms = 0, dbg_round_ms[kRounds] = {0, 0, 0, 0};   // part 0's view (CTICP_DEBUG_TIMERS)
 
     DispatchScanTypes(scan, [&](auto xt, auto tt) {
         using XT = typename decltype(xt)::type;
@@ -607,6 +609,7 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
             double smn = INFINITY, smx = -INFINITY;
             for (int i = 0; i < nparts; ++i) { smn = std::min(smn, mns[i]); smx = std::max(smx, mxs[i]); }
             if (part == 0) { *mn_out = smn; *mx_out = smx; }
+            if (part == 0 && debug) dbg_barrier_ms = ms_since(t_region);
             const double bts = pose_timestamps ? pose_timestamps[0] : smn, ets = pose_timestamps ? pose_timestamps[1] : smx;
             const double mn = std::min(bts, ets), mx = std::max(bts, ets);
             const bool spans = mx > mn;
@@ -620,6 +623,7 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
                         _mm_pause();
                         continue;
                     }
+                    if (debug) dbg_round_ms[issued] = ms_since(t_region);
                     try {
                         pipe_->UploadRange(piece_begin((size_t) issued * packers), piece_begin((size_t) (issued + 1) * packers));
                     } catch (...) {
@@ -654,7 +658,12 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
         PackLoPlane(scan, bts, ets, pipe_->StagingLo());
         pipe_->UploadLo(n);
     }
-    if (debug) cudaEventRecord(ev_[5], stream_);
+    if (debug) {
+        cudaEventRecord(ev_[5], stream_);
+        fprintf(stderr, "[cticp] pack region (%d parts, %d packers): min/max + barrier at %.3f ms, rounds complete at %.3f %.3f %.3f %.3f, "
+                "region end %.3f ms\n", parts, packers, dbg_barrier_ms, dbg_round_ms[0], dbg_round_ms[1], dbg_round_ms[2],
+                dbg_round_ms[3], ms_since(t_region));
+    }
     if (failed.load()) throw CudaError("cudaMemcpyAsync (scan upload)");
 }
 

@@ -495,6 +495,13 @@ inline void PackPoint(XT x, XT y, XT z, double a, float4 *dst, bool *any_lo) {
         if ((double) fx != x || (double) fy != y || (double) fz != z) *any_lo = true;
     }
 }
+// The common layout — contiguous float64 x, y, z and contiguous float64 timestamps (numpy's default) — has an AVX2 packer
+// (host_pack.cpp: a plain C++ translation unit, nvcc's front end does not see the AVX intrinsics)
+inline bool F64FastPath(const ScanView &scan) {
+    static const bool avx2 = HostPackHasAvx2();
+    return avx2 && scan.xyz_dtype == CTICP_DTYPE_FLOAT64 && scan.t_dtype == CTICP_DTYPE_FLOAT64 && scan.xyz_stride == 24 &&
+           scan.t_stride == 8 && (reinterpret_cast<uintptr_t>(scan.xyz) & 7) == 0 && (reinterpret_cast<uintptr_t>(scan.t) & 7) == 0;
+}
 }  // namespace
 
 // The residual plane of a float64 scan (value - (double)(float)value per component, alpha included): second pass, only for
@@ -532,12 +539,19 @@ bool Engine::PackScan(const ScanView &scan, double bts, double ets, float4 *dst)
     const char *px = static_cast<const char *>(scan.xyz), *pt = static_cast<const char *>(scan.t);
     const size_t xs = scan.xyz_stride, ts = scan.t_stride;
     const bool spans = mx > mn;
+    const bool fast = F64FastPath(scan);
     DispatchScanTypes(scan, [&](auto xt, auto tt) {
         using XT = typename decltype(xt)::type;
         using TT = typename decltype(tt)::type;
         pool_->ParallelFor(scan.n, [&](size_t b, size_t e, int) {
             bool any = false;
-            for (size_t i = b; i < e; ++i) {
+            if (fast) {   // slices cut on multiples of four points (the 32-byte stores need the alignment)
+                const size_t bb = b & ~size_t(3), ee = e == scan.n ? e : e & ~size_t(3);
+                if (ee > bb)
+                    PackBlockF64Avx2(static_cast<const double *>(scan.xyz), static_cast<const double *>(scan.t), bb, ee, mn, inv,
+                                     spans, dst, &any);
+            }
+            for (size_t i = b; i < e && !fast; ++i) {
                 const char *p = px + i * xs;
                 const XT x = LoadUnaligned<XT>(p), y = LoadUnaligned<XT>(p + sizeof(XT)), z = LoadUnaligned<XT>(p + 2 * sizeof(XT));
                 const double ti = (double) LoadUnaligned<TT>(pt + i * ts);
@@ -581,6 +595,7 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
     auto piece_begin = [&](size_t piece) { return piece >= pieces ? n : (n * piece / pieces) & ~size_t(3); };
     pipe_->UploadBegin(n);
     if (debug) cudaEventRecord(ev_[4], stream_);
+    const bool fast = F64FastPath(scan);
     const auto t_region = hclock::now();
     double dbg_barrier_ms = 0, dbg_round_ms[kRounds] = {0, 0, 0, 0};   // part 0's view (CTICP_DEBUG_TIMERS)
 
@@ -636,7 +651,10 @@ void Engine::PackAndUpload(const ScanView &scan, const double *pose_timestamps, 
             for (int r = 0; r < rounds && part >= first_packer; ++r) {
                 const size_t piece = (size_t) r * packers + (size_t) (part - first_packer);
                 const size_t b = piece_begin(piece), e = piece_begin(piece + 1);
-                for (size_t i = b; i < e; ++i) {
+                if (fast && e > b)
+                    PackBlockF64Avx2(static_cast<const double *>(scan.xyz), static_cast<const double *>(scan.t), b, e, mn, inv, spans,
+                                     dst, &any);
+                for (size_t i = b; i < e && !fast; ++i) {
                     const char *p = px + i * xs;
                     const XT x = LoadUnaligned<XT>(p), y = LoadUnaligned<XT>(p + sizeof(XT)), z = LoadUnaligned<XT>(p + 2 * sizeof(XT));
                     const double ti = (double) LoadUnaligned<TT>(pt + i * ts);

@@ -50,6 +50,12 @@ struct ScanView {
     size_t n = 0;
 };
 
+// host_pack.cpp: (x, y, z, alpha) packing of points [b, e) of a contiguous float64 scan with AVX2; b a multiple of 4.
+// *any_lo is set when some coordinate is not float32-representable (never cleared).
+bool HostPackHasAvx2();
+void PackBlockF64Avx2(const double *xyz, const double *t, size_t b, size_t e, double mn, double inv, bool spans, float4 *dst,
+                      bool *any_lo);
+
 // Minimal fork-join pool for the host passes over a scan (timestamp min/max, float4 packing): the only O(N) host
 // work of RegisterFrame. After a job the workers keep polling for the next one for ~1 ms before they go to sleep on a
 // condition variable (what OpenMP runtimes do by default, cf. GOMP_SPINCOUNT): when frames arrive back to back the

@@ -8,6 +8,9 @@
 #include <cstdio>
 #include <thread>
 #include <vector>
+#include <cstdlib>
+#include <cstring>
+#include <random>
 
 #include "engine.h"
 
@@ -52,6 +55,40 @@ int main() {
             EXPECT(arrived.load() == threads);
             EXPECT(sum.load() == (long long) threads * (threads + 1) / 2);
             if (rep % 50 == 49) std::this_thread::sleep_for(std::chrono::milliseconds(3));   // workers go to sleep
+        }
+    }
+    // the AVX2 packer of contiguous float64 scans (host_pack.cpp) against the scalar definition: float32-representable
+    // and not, spans / no span, ragged ends, NaN
+    if (cticp::HostPackHasAvx2()) {
+        std::mt19937_64 rng(3);
+        std::uniform_real_distribution<double> u(-80.0, 80.0);
+        for (int trial = 0; trial < 60; ++trial) {
+            const size_t n = 4 * (size_t) (1 + trial * 7) + (size_t) (trial % 4);
+            std::vector<double> xyz(3 * n), t(n);
+            for (size_t i = 0; i < n; ++i) {
+                for (int d = 0; d < 3; ++d) xyz[3 * i + d] = trial % 3 ? (double) (float) u(rng) : u(rng);
+                t[i] = 100.0 + 0.1 * (double) i / (double) n;
+            }
+            if (trial == 7) xyz[5] = std::nan("");
+            const bool spans = trial % 5 != 0;
+            const double mn = 100.0, inv = spans ? 10.0 : 0.0;
+            float *got = static_cast<float *>(aligned_alloc(64, 16 * n)), *want = static_cast<float *>(aligned_alloc(64, 16 * n));
+            bool any_got = false, any_want = false;
+            cticp::PackBlockF64Avx2(xyz.data(), t.data(), 0, n, mn, inv, spans, reinterpret_cast<float4 *>(got), &any_got);
+            for (size_t i = 0; i < n; ++i) {
+                const double a = spans ? (t[i] - mn) * inv : 1.0;
+                for (int d = 0; d < 3; ++d) {
+                    want[4 * i + d] = (float) xyz[3 * i + d];
+                    if ((double) want[4 * i + d] != xyz[3 * i + d]) any_want = true;
+                }
+                want[4 * i + 3] = (float) a;
+            }
+            if (std::memcmp(got, want, 16 * n) != 0 || any_got != any_want) {
+                std::printf("PackBlockF64Avx2 mismatch in trial %d (n = %zu, any %d / %d)\n", trial, n, (int) any_got, (int) any_want);
+                return 1;
+            }
+            free(got);
+            free(want);
         }
     }
     std::printf("HOST POOL OK\n");

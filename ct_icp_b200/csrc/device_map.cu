@@ -8,6 +8,7 @@
 
 #include <cooperative_groups.h>
 #include "gather.cuh"
+#include "frame_policy.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -274,12 +275,33 @@ struct FusedUpdateArgs {
     uint32_t *touched;
     const double *frame_origins;
     int frame_ordinal;
+    // speculative launch (frame_policy.h): pose pair, eviction centre and the evict / insert decision come from the verdict
+    // k_frame_policy left on the device; the by-value fields above are then ignored
+    const FrameVerdict *verdict;
+    double *frame_origins_mut;
 };
 __global__ void __launch_bounds__(kInsertWarps * 32)
 k_map_update_fused(FusedUpdateArgs a) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ CommitScratch sc;
+    if (a.verdict) {
+        const FrameVerdict &v = *a.verdict;
+        const int action = v.action;
+        if (action != kFrameEvict && action != kFrameInsert) return;   // uniform over the grid (before any barrier)
+        a.qb = Q4{v.state.qb[0], v.state.qb[1], v.state.qb[2], v.state.qb[3]};
+        a.qe = Q4{v.state.qe[0], v.state.qe[1], v.state.qe[2], v.state.qe[3]};
+        a.tb = V3{v.state.tb[0], v.state.tb[1], v.state.tb[2]};
+        a.te = V3{v.state.te[0], v.state.te[1], v.state.te[2]};
+        a.sc = v.sc;
+        a.location = a.te;   // trajectory_.back().end_pose.tr (odometry.cpp:942)
+        a.do_insert = action == kFrameInsert;
+        // frame_poses.front().tr of this insert (odometry.cpp:949); read by insert_commit_dev behind the grid barriers
+        if (a.do_insert && a.frame_origins_mut && blockIdx.x == 0 && threadIdx.x == 0) {
+            double *o = a.frame_origins_mut + 3 * (size_t) a.frame_ordinal;
+            o[0] = a.tb.x; o[1] = a.tb.y; o[2] = a.tb.z;
+        }
+    }
     const int n = *a.d_n;
     // phase 1: world points of the frame; eviction on every level; reset the per-level touched counters
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -456,27 +478,36 @@ void DeviceMap::InsertDevice(const double *d_world_xyz, const int *d_n, size_t n
     dirty_ = true;
 }
 
+void DeviceMap::EnsureFrameOrigin() {
+    if (frame_count_ >= (1u << 24) - 2) throw CapacityError("more than 2^24 frames inserted into one map");
+    if (with_normals_ && frame_count_ >= frame_capacity_) {
+        const size_t cap = std::max<size_t>(4096, frame_capacity_ * 2);
+        double *fresh = nullptr;
+        CT_CUDA_CHECK(cudaMalloc(&fresh, sizeof(double) * 3 * cap));
+        if (frame_count_)
+            CT_CUDA_CHECK(cudaMemcpyAsync(fresh, d_frame_origins_, sizeof(double) * 3 * frame_count_,
+                                          cudaMemcpyDeviceToDevice, stream_));
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        cudaFree(d_frame_origins_);
+        d_frame_origins_ = fresh;
+        frame_capacity_ = cap;
+    }
+}
+
 void DeviceMap::UpdateFused(const float4 *d_frame, const float4 *d_frame_lo, const int *d_n, size_t n_upper, double *d_world, const Q4 &qb,
                             const V3 &tb, const Q4 &qe, const V3 &te, bool do_remove, V3 location, double max_distance,
-                            bool do_insert, V3 origin) {
+                            bool do_insert, V3 origin, const FrameVerdict *d_verdict) {
     if (n_upper == 0) return;
     EnsureScratch(n_upper);
     int frame_ordinal = 0;
-    if (do_insert) {
-        if (frame_count_ >= (1u << 24) - 2) throw CapacityError("more than 2^24 frames inserted into one map");
+    if (d_verdict) {
+        // speculative: whether this launch inserts is decided on the device; the slot of the frame's origin is reserved
+        // now and kept by CommitSpeculativeInsert(true)
+        EnsureFrameOrigin();
+        frame_ordinal = (int) frame_count_;
+    } else if (do_insert) {
+        EnsureFrameOrigin();
         if (with_normals_) {
-            if (frame_count_ >= frame_capacity_) {
-                const size_t cap = std::max<size_t>(4096, frame_capacity_ * 2);
-                double *fresh = nullptr;
-                CT_CUDA_CHECK(cudaMalloc(&fresh, sizeof(double) * 3 * cap));
-                if (frame_count_)
-                    CT_CUDA_CHECK(cudaMemcpyAsync(fresh, d_frame_origins_, sizeof(double) * 3 * frame_count_,
-                                                  cudaMemcpyDeviceToDevice, stream_));
-                CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
-                cudaFree(d_frame_origins_);
-                d_frame_origins_ = fresh;
-                frame_capacity_ = cap;
-            }
             const double o[3] = {origin.x, origin.y, origin.z};
             CT_CUDA_CHECK(cudaMemcpyAsync(d_frame_origins_ + 3 * frame_count_, o, sizeof(o), cudaMemcpyHostToDevice, stream_));
         }
@@ -509,6 +540,8 @@ void DeviceMap::UpdateFused(const float4 *d_frame, const float4 *d_frame_lo, con
     a.touched = d_touched_;
     a.frame_origins = d_frame_origins_;
     a.frame_ordinal = frame_ordinal;
+    a.verdict = d_verdict;
+    a.frame_origins_mut = with_normals_ ? d_frame_origins_ : nullptr;
     void *args[] = {&a};
     CT_CUDA_CHECK(cudaLaunchCooperativeKernel((void *) k_map_update_fused, dim3(fused_grid_), dim3(kInsertWarps * 32), args, 0, stream_));
     launches_ += 1;

@@ -17,6 +17,8 @@ struct CapacityError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+struct FrameVerdict;   // frame_policy.h
+
 class DeviceMap {
 public:
     // with_normals: maintain the per-voxel normals that RadiusSearchInPlace's sensor_location filter reads (map.h:482-490)
@@ -35,7 +37,14 @@ public:
     void RemoveFar(V3 location, double distance);
     // one cooperative launch: world points of the sub-sampled frame under the pose pair (→ d_world), RemoveFar, InsertDevice
     void UpdateFused(const float4 *d_frame, const float4 *d_frame_lo, const int *d_n, size_t n_upper, double *d_world, const Q4 &qb, const V3 &tb,
-                     const Q4 &qe, const V3 &te, bool do_remove, V3 location, double max_distance, bool do_insert, V3 origin);
+                     const Q4 &qe, const V3 &te, bool do_remove, V3 location, double max_distance, bool do_insert, V3 origin,
+                     const FrameVerdict *d_verdict = nullptr);
+    // d_verdict != nullptr (frame_policy.h): a SPECULATIVE launch — the pose pair, the eviction centre and whether the frame
+    // is evicted / inserted at all are read from the verdict on the device (the by-value pose arguments are ignored). The
+    // caller reports the outcome it read back from the verdict:
+    void CommitSpeculativeInsert(bool inserted) {
+        if (inserted) ++frame_count_;
+    }
     void Clear();
 
     // counters (synchronises the stream when stale)
@@ -68,6 +77,7 @@ private:
     void RebuildLevel(size_t i, uint64_t new_cap);
     void FreeLevel(MapLevel &L);
     void EnsureScratch(size_t n_upper);
+    void EnsureFrameOrigin();
 
     cticp_map_options options_;
     cudaStream_t stream_;

@@ -32,6 +32,65 @@ struct NvtxRange {
 };
 
 using hclock = std::chrono::steady_clock;
+
+// ---- the tail of a plain registration, decided on the device (frame_policy.h) ------------------------------------------
+// One warp. AssessRegistration (odometry.cpp:604-684, the branch without robust_registration) and UpdateMap's insertion
+// policy (:903-925) on the registration state the ICP kernel left in HBM; the verdict goes to device memory (read by the
+// speculative k_map_update_fused enqueued right behind) and to mapped pinned host memory, sequence number last.
+__global__ void __launch_bounds__(32) k_frame_policy(const IcpState *__restrict__ st, const int *__restrict__ counts,
+                                                     FramePolicyIn in, FrameVerdict *dv, FrameVerdict *hv) {
+    __shared__ FrameVerdict v;
+    const int lane = threadIdx.x;
+    {
+        const int *src = reinterpret_cast<const int *>(st);
+        int *dst = reinterpret_cast<int *>(&v.state);
+        for (int i = lane; i < (int) (sizeof(IcpState) / sizeof(int)); i += 32) dst[i] = __ldcg(src + i);
+    }
+    if (lane < 4) v.counts[lane] = __ldcg(counts + lane);
+    __syncwarp();
+    if (lane == 0) {
+        const IcpState &S = v.state;
+        const Q4 qb{S.qb[0], S.qb[1], S.qb[2], S.qb[3]}, qe{S.qe[0], S.qe[1], S.qe[2], S.qe[3]};
+        const V3 tb{S.tb[0], S.tb[1], S.tb[2]}, te{S.te[0], S.te[1], S.te[2]};
+        const double ego = angular_distance_deg(qb, qe);   // EgoAngularDistance(summary.frame)
+        const double rel_dist = norm(te - tb);             // summary.relative_distance (odometry.cpp:433)
+        bool ok;
+        if (rel_dist > in.distance_error_threshold) ok = false;
+        else if (in.relative_orientation > in.orientation_error_threshold || ego > in.orientation_error_threshold) ok = false;
+        else ok = !S.failed;
+        bool add = true;   // UpdateMap, the branch without robust_registration
+        if (in.has_insertions) add = (ego > in.insertion_ego_rotation_threshold) ? (in.skipped_enough != 0) : true;
+        v.add_points_policy = add ? 1 : 0;
+        if (in.do_no_insert) add = false;
+        if (in.always_insert) add = true;
+        int action;
+        if (S.failed == 2 || S.failed == 3) action = kFrameSkip;          // the host raises an exception
+        else if (!ok && in.quit_on_error) action = kFrameSkip;            // early return (odometry.cpp:437-441)
+        else if (add && v.counts[1] > in.room_for) action = kFrameDeferred;
+        else action = add ? kFrameInsert : kFrameEvict;
+        v.assess_ok = ok ? 1 : 0;
+        v.action = action;
+        v.pad0 = 0;
+        v.ego_orientation = ego;
+        v.relative_distance = rel_dist;
+        v.sc = slerp_consts(qb, qe);
+        v.seq = in.seq;
+        v.pad1 = 0;
+    }
+    __syncwarp();
+    constexpr int kWords = (int) (sizeof(FrameVerdict) / sizeof(int));
+    constexpr int kSeqWord = (int) (offsetof(FrameVerdict, seq) / sizeof(int));
+    const int *src = reinterpret_cast<const int *>(&v);
+    int *d = reinterpret_cast<int *>(dv);
+    volatile int *h = reinterpret_cast<volatile int *>(hv);
+    for (int i = lane; i < kWords; i += 32) {
+        d[i] = src[i];
+        if (i != kSeqWord) h[i] = src[i];
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) h[kSeqWord] = (int) in.seq;
+}
 static double ms_since(hclock::time_point t0) {
     return std::chrono::duration<double, std::milli>(hclock::now() - t0).count();
 }
@@ -105,6 +164,7 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
     next_robust_level_ = options_.robust_minimal_level;
     if (const char *e = getenv("CTICP_FUSED_SAMPLING")) fused_sampling_ = atoi(e) != 0;
     if (const char *e = getenv("CTICP_FUSED_MAP_UPDATE")) fused_map_update_ = atoi(e) != 0;
+    if (const char *e = getenv("CTICP_DEVICE_TAIL")) device_tail_ = atoi(e) != 0;
 
     {
         pool_ = std::make_unique<HostPool>(HostTeamSize(1));
@@ -119,6 +179,13 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
     icp_ = std::make_unique<IcpSolver>(stream_);
     CT_CUDA_CHECK(cudaMalloc(&d_state_, sizeof(IcpState)));
     CT_CUDA_CHECK(cudaMallocHost(&h_state_, sizeof(IcpState)));
+    CT_CUDA_CHECK(cudaMalloc(&d_verdict_, sizeof(FrameVerdict)));
+    CT_CUDA_CHECK(cudaMemsetAsync(d_verdict_, 0, sizeof(FrameVerdict), stream_));
+    CT_CUDA_CHECK(cudaHostAlloc(&h_verdict_, sizeof(FrameVerdict), cudaHostAllocMapped));
+    memset(h_verdict_, 0, sizeof(FrameVerdict));
+    CT_CUDA_CHECK(cudaHostGetDevicePointer((void **) &h_verdict_dev_, h_verdict_, 0));
+    CT_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
+    CT_CUDA_CHECK(cudaEventCreateWithFlags(&ev_state_up_, cudaEventDisableTiming));
     CT_CUDA_CHECK(cudaMalloc(&d_kp_world_, sizeof(double) * 3 * max_pts));
     for (auto &e : ev_) CT_CUDA_CHECK(cudaEventCreate(&e));
     for (auto &e : timer_ev_) CT_CUDA_CHECK(cudaEventCreate(&e));
@@ -134,6 +201,10 @@ Engine::~Engine() {
     map_.reset();
     cudaFree(d_state_);
     cudaFreeHost(h_state_);
+    cudaFree(d_verdict_);
+    cudaFreeHost(h_verdict_);
+    if (ev_state_up_) cudaEventDestroy(ev_state_up_);
+    if (aux_stream_) cudaStreamDestroy(aux_stream_);
     cudaFree(d_kp_world_);
     for (auto &e : ev_) cudaEventDestroy(e);
     for (auto &e : timer_ev_) cudaEventDestroy(e);
@@ -805,7 +876,15 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
         S.prev_qe[3] = pf.end_pose.pose.q.w;
     }
     icp_state_refresh_slerp(S);
-    CT_CUDA_CHECK(cudaMemcpyAsync(d_state_, h_state_, sizeof(IcpState), cudaMemcpyHostToDevice, stream_));
+    tail_launched_ = false;
+    if (tail_armed_) {
+        // nothing on stream_ touches d_state_ until the ICP kernel (the previous frame's readers completed before its verdict
+        // arrived): the state goes up on the second stream while the sampler is still running
+        CT_CUDA_CHECK(cudaMemcpyAsync(d_state_, h_state_, sizeof(IcpState), cudaMemcpyHostToDevice, aux_stream_));
+        CT_CUDA_CHECK(cudaEventRecord(ev_state_up_, aux_stream_));
+        CT_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_state_up_, 0));
+    } else
+        CT_CUDA_CHECK(cudaMemcpyAsync(d_state_, h_state_, sizeof(IcpState), cudaMemcpyHostToDevice, stream_));
     CT_CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
     icp_->set_keypoints_lo(pipe_->d_keypoints_lo());
     switch (options.solver) {
@@ -823,13 +902,34 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
             throw UnsupportedError("Unsupported Solver Type");
     }
     CT_CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
-    CT_CUDA_CHECK(cudaMemcpyAsync(h_state_, d_state_, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
-    pipe_->QueueCountsReadback();
-    CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (tail_armed_) {
+        // device tail (frame_policy.h): verdict + speculative map update behind the ICP kernel; the host waits for the
+        // verdict's sequence number in mapped pinned memory, not for the stream
+        tail_armed_ = false;
+        tail_in_.seq = ++verdict_seq_;
+        k_frame_policy<<<1, 32, 0, stream_>>>(d_state_, pipe_->d_counts(), tail_in_, d_verdict_, h_verdict_dev_);
+        CT_CUDA_CHECK(cudaGetLastError());
+        tail_launches_ += 1;
+        {
+            NvtxRange range_map("cticp.map_update");
+            map_->UpdateFused(pipe_->d_frame(), pipe_->d_frame_lo(), pipe_->d_count_frame(), pipe_->n(), pipe_->d_frame_world_mut(),
+                              Q4{0, 0, 0, 1}, V3{0, 0, 0}, Q4{0, 0, 0, 1}, V3{0, 0, 0}, true, V3{0, 0, 0}, options_.max_distance,
+                              true, V3{0, 0, 0}, d_verdict_);
+        }
+        tail_launched_ = true;
+        WaitVerdict(tail_in_.seq);
+        memcpy(h_state_, &h_verdict_->state, sizeof(IcpState));
+        pipe_->SetHostCounts(h_verdict_->counts);
+        timing_.d2h_bytes += sizeof(FrameVerdict);
+    } else {
+        CT_CUDA_CHECK(cudaMemcpyAsync(h_state_, d_state_, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
+        pipe_->QueueCountsReadback();
+        CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        timing_.d2h_bytes += sizeof(IcpState) + sizeof(int) * 4;
+    }
     staging_in_flight_ = false;
     icp_->CollectGatherTiming();
     timing_.h2d_bytes += sizeof(IcpState);
-    timing_.d2h_bytes += sizeof(IcpState) + sizeof(int) * 4;
 
     if (getenv("CTICP_DEBUG_TIMERS"))
         fprintf(stderr, "[cticp] GN loop, solver CTA (SM cycles over %d iterations, needs a -DCTICP_DEBUG_TIMERS build): loop %llu, "
@@ -866,6 +966,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
     // persistent launch (solver GN), else the whole iteration is reported as neighborhood time
     {
         float icp_ms = 0.f;
+        if (tail_launched_) cudaEventSynchronize(ev_[2]);   // (complete: the verdict's kernel ran behind it)
         if (cudaEventElapsedTime(&icp_ms, ev_[1], ev_[2]) != cudaSuccess) {
             cudaGetLastError();
             icp_ms = 0.f;
@@ -879,6 +980,44 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
         rs.icp.avg_duration_neighborhood = rs.icp.avg_duration_iter - rs.icp.avg_duration_solve;
     }
     FireEvent(CTICP_EVENT_ITERATION_COMPLETED, rs, info);   // odometry.cpp:600
+}
+
+// Spin on the verdict's sequence number (written by k_frame_policy after a system-wide fence). The stream is polled now
+// and then: a faulted kernel must surface as an error, not as a hang.
+void Engine::WaitVerdict(unsigned seq) {
+    volatile unsigned *flag = &h_verdict_->seq;
+    for (unsigned long spins = 1;; ++spins) {
+        if (*flag == seq) break;
+        if ((spins & 0xfffu) == 0) {
+            const cudaError_t q = cudaStreamQuery(stream_);
+            if (q == cudaSuccess) {
+                if (*flag == seq) break;
+                throw std::runtime_error("the frame verdict never arrived although the stream is idle");
+            }
+            if (q != cudaErrorNotReady) CT_CUDA_CHECK(q);
+        }
+        _mm_pause();
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+}
+
+// What UpdateMap (below) does on the host around its launch, for a map update the device has already decided and run.
+void Engine::AdoptDeviceMapUpdate(Summary &s) {
+    const FrameVerdict &v = *h_verdict_;
+    const bool inserted = v.action == kFrameInsert;
+    tracker_.cum_orientation += s.relative_orientation;
+    tracker_.cum_distance += s.relative_distance;
+    s.points_added = v.add_points_policy != 0;
+    map_->CommitSpeculativeInsert(inserted);
+    frame_world_valid_ = true;
+    if (inserted) {
+        tracker_.skipped_frames = 0;
+        tracker_.cum_orientation = 0;
+        tracker_.cum_distance = 0;
+        tracker_.total_insertions++;
+    } else
+        tracker_.skipped_frames++;
+    map_->QueueCounterReadback();
 }
 
 // AssessRegistration, odometry.cpp:604-684
@@ -1058,7 +1197,8 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     if (n > pipe_->MaxPoints()) throw CapacityError("scan has more points than max_points_per_frame");
     memset(&timing_, 0, sizeof(timing_));
     icp_->reset_timing();
-    const int launches0 = map_->launches() + pipe_->launches() + icp_->launches();
+    const int launches0 = map_->launches() + pipe_->launches() + icp_->launches() + tail_launches_;
+    tail_armed_ = tail_launched_ = false;
     last_all_world_valid_ = last_kp_world_valid_ = frame_world_valid_ = false;
     egress_valid_[0] = egress_valid_[1] = egress_valid_[2] = false;
     if (egress_pending_) {   // the previous frame's egress still reads d_raw / d_frame_world / the keypoints
@@ -1133,13 +1273,40 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
             const double sample_voxel_size = k < options_.init_num_frames ? options_.init_sample_voxel_size
                                                                           : options_.sample_voxel_size;
             auto t0 = hclock::now();
+            // NB trajectory_[k] is still the INITIAL estimate here (odometry.cpp:429-431)
+            const double relative_orientation =
+                angular_distance_deg(trajectory_[k - 1].end_pose.pose.q, trajectory_[k].end_pose.pose.q);
+            if (device_tail_ && fused_map_update_ && !callback_ && options_.motion_compensation == CTICP_MC_CONTINUOUS &&
+                pipe_->n() > 0) {
+                // the tail of this registration is decided on the device (frame_policy.h)
+                FramePolicyIn &in = tail_in_;
+                in = FramePolicyIn{};
+                in.distance_error_threshold = options_.distance_error_threshold;
+                in.orientation_error_threshold = options_.orientation_error_threshold;
+                in.relative_orientation = relative_orientation;
+                in.insertion_ego_rotation_threshold = options_.insertion_ego_rotation_threshold;
+                in.quit_on_error = options_.quit_on_error ? 1 : 0;
+                in.has_insertions = tracker_.total_insertions > 0;
+                in.skipped_enough = tracker_.skipped_frames > options_.insertion_threshold_frames_skipped;
+                in.do_no_insert = options_.do_no_insert ? 1 : 0;
+                in.always_insert = options_.always_insert ? 1 : 0;
+                // F is still on the device: room for the previous frame's count with head-room (a frame beyond it is
+                // deferred to the host-side UpdateMap). Before the ICP is enqueued — a grown table is a new table.
+                const size_t prev_f = (size_t) std::max(0, pipe_->h_counts()[1]);
+                size_t room = std::min(pipe_->n(), prev_f + prev_f / 2 + 4096);
+                if (const char *e = getenv("CTICP_TAIL_ROOM")) room = std::min(room, (size_t) std::max(0, atoi(e)));   // test hook: force the deferred path
+                map_->EnsureRoomFor(room);
+                in.room_for = (int) room;
+                tail_armed_ = true;
+            }
             TryRegister(info, ct_icp_options, summary, sample_voxel_size, mm, 0);
             summary.t_try_register = ms_since(t0);
-            // NB trajectory_[k] is still the INITIAL estimate here (odometry.cpp:429-431)
-            summary.relative_orientation = angular_distance_deg(trajectory_[k - 1].end_pose.pose.q, trajectory_[k].end_pose.pose.q);
+            summary.relative_orientation = relative_orientation;
             summary.ego_orientation = EgoAngularDistance(summary.frame);
             summary.relative_distance = norm(summary.frame.end_pose.pose.t - summary.frame.begin_pose.pose.t);
-            if (!AssessRegistration(summary)) {
+            bool assessed = AssessRegistration(summary);
+            if (tail_launched_) assessed = h_verdict_->assess_ok != 0;   // the device acted on ITS evaluation of the same formulas
+            if (!assessed) {
                 summary.success = false;
                 if (options_.quit_on_error) early_return = true;
             }
@@ -1167,7 +1334,10 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
             if (summary_points_mask_) EnqueueEgress(f, ran_icp);
         }
         ComputeSummaryMetrics(summary, k);
-        UpdateMap(summary, k);
+        if (tail_launched_ && h_verdict_->action != kFrameDeferred)
+            AdoptDeviceMapUpdate(summary);   // evicted / inserted already, behind the ICP kernel
+        else
+            UpdateMap(summary, k);
         if (fused_map_update_ && summary_points_mask_) EnqueueEgress(f, ran_icp);   // (the fused update wrote d_frame_world)
         if (callback_) {   // odometry.cpp:491
             const bool fw = frame_world_valid_, aw = last_all_world_valid_, kw = last_kp_world_valid_;
@@ -1184,7 +1354,7 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
         staging_in_flight_ = false;
     }
 
-    timing_.kernel_launches = map_->launches() + pipe_->launches() + icp_->launches() - launches0;
+    timing_.kernel_launches = map_->launches() + pipe_->launches() + icp_->launches() + tail_launches_ - launches0;
     if (out) {
         FillSummary(summary, out);
         out->num_all_corrected_points = n;

@@ -18,6 +18,7 @@
 #include "device_map.h"
 #include "frame_pipeline.h"
 #include "icp.h"
+#include "frame_policy.h"
 
 namespace cticp {
 
@@ -182,6 +183,23 @@ private:
     void RobustRegistration(const FrameInfo &info, Summary &rs, const MotionModel *mm);
     void ComputeSummaryMetrics(Summary &s, int k);
     void UpdateMap(Summary &s, int registered_fid);
+    // The tail of a plain registration decided on the device (frame_policy.h): TryRegister enqueues k_frame_policy and a
+    // speculative k_map_update_fused right behind the ICP kernel, then waits for the verdict in mapped pinned memory — no
+    // copy-engine operation and no host round trip between the ICP loop and the map update.
+    bool device_tail_ = true;      // CTICP_DEVICE_TAIL=0: AssessRegistration / UpdateMap on the host for every frame
+    bool tail_armed_ = false;      // the coming TryRegister enqueues the device tail (tail_in_ is filled)
+    bool tail_launched_ = false;   // the last TryRegister did: h_verdict_ holds this frame's verdict
+    FramePolicyIn tail_in_{};
+    FrameVerdict *d_verdict_ = nullptr;
+    FrameVerdict *h_verdict_ = nullptr;       // mapped pinned memory
+    FrameVerdict *h_verdict_dev_ = nullptr;   // its device address
+    unsigned verdict_seq_ = 0;
+    int tail_launches_ = 0;
+    void WaitVerdict(unsigned seq);
+    void AdoptDeviceMapUpdate(Summary &s);
+    // the registration state goes up on a second stream while the sampler runs (the ICP kernel waits for its event)
+    cudaStream_t aux_stream_ = nullptr;
+    cudaEvent_t ev_state_up_ = nullptr;
     void FillSummary(const Summary &s, cticp_summary *out) const;
     // grid-size hint for the ICP kernels: the keypoint count is only known on the device when they are enqueued, so
     // the host sizes the grid from the previous registration (keypoint counts change slowly) with 25% head-room;

@@ -64,6 +64,11 @@ public:
 
     void QueueCountsReadback();   // h_counts()[0..2] = N, F, K after the next stream sync
     const int *h_counts() const { return h_counts_; }
+    // the same four counters, brought back by another route (the frame verdict, frame_policy.h)
+    void SetHostCounts(const int *c) {
+        for (int i = 0; i < 4; ++i) h_counts_[i] = c[i];
+    }
+    const int *d_counts() const { return d_counts_; }
 
     const float4 *d_raw() const { return d_raw_; }
     const float4 *d_frame() const { return d_frame_; }

@@ -272,7 +272,7 @@ void Engine::EnqueueEgress(const HostFrame &f, bool ran_icp) {
     const Q4 qb = f.begin_pose.pose.q, qe = f.end_pose.pose.q;
     const V3 tb = f.begin_pose.pose.t, te = f.end_pose.pose.t;
     const size_t n_all = pipe_->n(), n_frame = (size_t) pipe_->h_counts()[1];
-    const size_t n_kp = ran_icp ? (size_t) pipe_->h_counts()[2] : 0;
+    const size_t n_kp = (ran_icp && keypoints_in_summary_) ? (size_t) pipe_->h_counts()[2] : 0;
     cudaStream_t es = egress_stream_;
     if (summary_points_mask_ & (1 << CTICP_POINTS_ALL_CORRECTED)) {
         pipe_->TransformAll(qb, tb, qe, te, es);
@@ -848,6 +848,7 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
         pipe_->QueueCountsReadback();
         CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
         staging_in_flight_ = false;
+        keypoints_in_summary_ = true;   // the hook receives the sampled keypoints (odometry.cpp:568)
         FireEvent(CTICP_EVENT_BEFORE_ITERATION, rs, info);
     }
     if (at_startup) {
@@ -936,9 +937,11 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
                 "reduce+solve %llu = reduce %llu + rest %llu (12x12 solve %llu, pose update %llu)\n", (int) S.iter,
                 (unsigned long long) S.cycles_total, (unsigned long long) S.cycles_solve, (unsigned long long) S.dbg_t[0],
                 (unsigned long long) S.dbg_t[1], (unsigned long long) S.dbg_t[2], (unsigned long long) S.dbg_t[3]);
+    if (getenv("CTICP_DEBUG_TIMERS") && options.solver == CTICP_SOLVER_GN) icp_->PrintWarpStamps((int) S.iter);
     rs.sample_size = pipe_->h_counts()[2];
     last_num_keypoints_ = (size_t) std::max(0, pipe_->h_counts()[2]);
     rs.icp.success = !S.failed;
+    keypoints_in_summary_ = rs.icp.success;   // registration_summary.keypoints is only assigned after a successful ICP (odometry.cpp:584-597)
     rs.icp.num_residuals_used = S.n_used;
     rs.icp.num_iters = S.iter;
     rs.success = rs.icp.success;
@@ -1199,6 +1202,7 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
     icp_->reset_timing();
     const int launches0 = map_->launches() + pipe_->launches() + icp_->launches() + tail_launches_;
     tail_armed_ = tail_launched_ = false;
+    keypoints_in_summary_ = false;
     last_all_world_valid_ = last_kp_world_valid_ = frame_world_valid_ = false;
     egress_valid_[0] = egress_valid_[1] = egress_valid_[2] = false;
     if (egress_pending_) {   // the previous frame's egress still reads d_raw / d_frame_world / the keypoints
@@ -1359,7 +1363,7 @@ void Engine::RegisterCommon(const ScanView &scan, uint32_t frame_id, const cticp
         FillSummary(summary, out);
         out->num_all_corrected_points = n;
         out->num_corrected_points = (uint64_t) pipe_->h_counts()[1];
-        out->num_keypoints = ran_icp ? (uint64_t) pipe_->h_counts()[2] : 0;
+        out->num_keypoints = (ran_icp && keypoints_in_summary_) ? (uint64_t) pipe_->h_counts()[2] : 0;
         out->odometry_total = ms_since(t_start);
         out->odometry_initialization = t_initialization;
         out->odometry_try_register = summary.t_try_register;
@@ -1445,7 +1449,7 @@ void Engine::ResolvePoints(int which, const float4 **out_pts, const float4 **out
             count = pipe_->n();
             break;
         case CTICP_POINTS_KEYPOINTS:
-            count = last_info_.registered_fid > 0 ? (size_t) pipe_->h_counts()[2] : 0;
+            count = (last_info_.registered_fid > 0 && keypoints_in_summary_) ? (size_t) pipe_->h_counts()[2] : 0;
             if (count && !last_kp_world_valid_) {
                 pipe_->TransformInto(pipe_->d_keypoints(), pipe_->d_keypoints_lo(), pipe_->d_count_keypoints(), f.begin_pose.pose.q,
                                      f.begin_pose.pose.t, f.end_pose.pose.q, f.end_pose.pose.t, d_kp_world_);

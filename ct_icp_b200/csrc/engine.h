@@ -208,6 +208,7 @@ private:
         return last_num_keypoints_ ? std::min(pipe_->n(), last_num_keypoints_ + last_num_keypoints_ / 4 + 64) : pipe_->n();
     }
     size_t last_num_keypoints_ = 0;
+    bool keypoints_in_summary_ = false;   // the last TryRegister's ICP succeeded: RegistrationSummary::keypoints is filled
     static uint64_t ShuffleCounter(int registered_fid, int purpose) {
         return (uint64_t(uint32_t(registered_fid)) << 8) | uint64_t(purpose & 0xff);
     }

@@ -247,9 +247,11 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
         double ox = 0, oy = 0, oz = 0;   // my voxel's origin relative to the query (fp64)
         double sdn = 0;                  // kFilter: to_sensor . voxel normal
         int has_normal = 0;
+        int cx = 0, cy = 0, cz = 0;      // my voxel's coordinates
         if (s < nst) {
             int dx, dy, dz;
             stencil_lookup(stencil, s, G.r, dx, dy, dz);
+            cx = kx + dx; cy = ky + dy; cz = kz + dz;
             uint32_t c = 0;
             const int found = map_find(L, pack_voxel(kx + dx, ky + dy, kz + dz), &c);
             if (found >= 0) {
@@ -267,6 +269,22 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
             oy = i32_to_f64(ky + dy) * L.res - q.y;
             oz = i32_to_f64(kz + dz) * L.res - q.z;
         }
+        pts_total += (unsigned) __reduce_add_sync(0xffffffffu, cnt);   // (statistics: every point of the stencil, map.h:470-506)
+#ifndef CTICP_NO_VOXEL_PRUNE
+        // Exact prune: a voxel whose box lies farther than the radius from the query cannot hold a candidate (every one of
+        // its points would fail the radius test below), so its points are not loaded. Voxel c of Voxel::Coordinates'
+        // truncation holds offsets in [0, res) for c > 0, (-res, 0] for c < 0 and (-res, res) for c == 0 (types.h:65-86);
+        // a margin of 1e-6 res covers the rounding of the fp32 offsets and of the quotient that assigned the voxel.
+        if (cnt > 0) {
+            const double m = 1e-6 * L.res;
+            const double ax = ox + (cx > 0 ? 0.0 : -L.res) - m, bx = ox + (cx < 0 ? 0.0 : L.res) + m;
+            const double ay = oy + (cy > 0 ? 0.0 : -L.res) - m, by = oy + (cy < 0 ? 0.0 : L.res) + m;
+            const double az = oz + (cz > 0 ? 0.0 : -L.res) - m, bz = oz + (cz < 0 ? 0.0 : L.res) + m;
+            const double gx = ax > 0 ? ax : (bx < 0 ? -bx : 0.0), gy = ay > 0 ? ay : (by < 0 ? -by : 0.0),
+                         gz = az > 0 ? az : (bz < 0 ? -bz : 0.0);
+            if (gx * gx + gy * gy + gz * gz > G.radius2) cnt = 0;
+        }
+#endif
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -275,7 +293,6 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         const int excl = incl - cnt;
-        pts_total += (unsigned) total;
 
 #ifdef CTICP_SEL_BULK
         bool staged = false;

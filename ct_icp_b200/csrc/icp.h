@@ -59,9 +59,9 @@ struct PeerLinksHost {
 // the environment has CTICP_DEBUG_TIMERS. (%globaltimer proved far too slow to read: it tripled the kernel time; only
 // differences taken on the same SM are meaningful.)
 #ifdef CTICP_DEBUG_TIMERS
-#define CT_STAMP(expr) expr
+#define CT_STAMP(...) __VA_ARGS__
 #else
-#define CT_STAMP(expr)
+#define CT_STAMP(...)
 #endif
 
 struct GnParams {
@@ -75,6 +75,7 @@ struct GnParams {
     int debug_flags;               // profiling only (env CTICP_DEBUG_FLAGS): 1 = skip the solve, 2 = skip the gather work
     double bucket_scale;           // 32 / radius^2: d2 → histogram bucket of the k-nearest selection (gather_select.cuh)
     const float4 *kp_lo;           // residual plane of the keypoints (nullptr: float32-representable; load_raw, se3.cuh)
+    unsigned long long *dbg_warp;  // -DCTICP_DEBUG_TIMERS builds with CTICP_DEBUG_TIMERS set: per-warp phase stamps (icp_gn.cu)
     int rigid_first;               // motion compensation NONE / CONSTANT_VELOCITY: the keypoints enter the first iteration
                                    // transformed by the END pose alone (TransformPoint, odometry.cpp:171-184), afterwards GN
                                    // interpolates like always (ct_icp.cpp:964-966)
@@ -116,6 +117,9 @@ public:
     int gather_launches() const { return gather_launches_; }
     void set_time_gather(bool on) { time_gather_ = on; }
     void set_persistent(bool on) { use_persistent_ = on; }
+    // -DCTICP_DEBUG_TIMERS builds: per-warp cycles of the gather phases (A pose + voxel, B gather + selection, C epilogue, D rows)
+    // of the last persistent GN loop, mean / p90 / max over the warps per iteration, on stderr
+    void PrintWarpStamps(int iters);
     void CollectGatherTiming();   // after a stream sync: accumulates the event pairs recorded since the last call
     // multi-GPU: d_acc_[0..kAcc) ← Σ over ranks of d_acc_, in place: over the NVLink peer mailboxes when they are
     // connected (k_peer_allreduce, peer_exchange.cuh), else ncclAllReduce (nccl_shard.cu). d_state receives the
@@ -142,6 +146,8 @@ private:
     cudaStream_t stream_;
     const float4 *kp_lo_ = nullptr;
     double *d_partials_ = nullptr;
+    unsigned long long *d_dbg_warp_ = nullptr;   // [kDbgIters][warps][kDbgSlots]
+    int dbg_warps_ = 0;
     int partial_blocks_ = 0;
     double *d_sys_ = nullptr;      // 12*12 + 12 + 4 debug output of the solve kernel
     double *d_acc_ = nullptr;      // reduced accumulator (multi-GPU all-reduce buffer)

@@ -5,8 +5,10 @@
 //   k_gn_solve  : one block — deterministic reduction of the per-block partials, 1/n normalisation, motion-model
 //                 regularisers, pivoted LDL^T solve of the 12x12 system, Euler-ZYX pose update, stop test.
 // Reference: DoRegisterGaussNewton, src/ct_icp/ct_icp.cpp:709-996 (serial per-keypoint loop :753-857).
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include <cooperative_groups.h>
 
@@ -171,7 +173,9 @@ struct GnWarpAcc {
     double sum_sq = 0;               // per-lane partial counters from here on
     unsigned n_stencil = 0;
     int n_used = 0, n_kp = 0, n_valid = 0;
+    CT_STAMP(long long dbg[4] = {0, 0, 0, 0};)   // cycles in phases A, B, C, D
 };
+constexpr int kDbgIters = 8, kDbgSlots = 6;
 
 constexpr int kTileMax = 16;   // keypoints per warp tile (phases A / C cost 1/W per keypoint: 16 is deep in the flat part)
 
@@ -205,6 +209,7 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
 
     for (int t0 = lo + warp_global * W; t0 < hi; t0 += warps_total * W) {
         const int wt = (hi - t0) < W ? (hi - t0) : W;
+        CT_STAMP(const long long t_a = clock64();)
         // ---- A: world_kpts[i] = InterpolatePose(begin, end, t_i) * raw_i  (ct_icp.cpp:964-966, types.h:361-366)
         V3 p{0, 0, 0};
         int kx = 0, ky = 0, kz = 0;
@@ -217,6 +222,7 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
             ky = voxel_coord_rcp(p.y, G.L.res, inv_res);
             kz = voxel_coord_rcp(p.z, G.L.res, inv_res);
         }
+        CT_STAMP(const long long t_b = clock64();)
         // ---- B
         for (int j = 0; j < wt; ++j) {
             const V3 q{__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j)};
@@ -236,6 +242,7 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
             }
         }
         __syncwarp();
+        CT_STAMP(const long long t_c = clock64();)
         // ---- C (ct_icp.cpp:769-850)
         bool used = false;
         if (lane < wt) {
@@ -278,6 +285,7 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
             }
         }
         // ---- D: A += u u^T, b -= u scalar, in keypoint order (deterministic)
+        CT_STAMP(const long long t_d = clock64();)
         unsigned mask = __ballot_sync(0xffffffffu, used);
         __syncwarp();
         while (mask) {
@@ -289,6 +297,8 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
             if (i2 < kAccUsed) A.a2 += u[pi2] * u[pj2];
         }
         __syncwarp();   // the rows are consumed before the next tile rewrites them
+        CT_STAMP(const long long t_e = clock64();
+                 A.dbg[0] += t_b - t_a; A.dbg[1] += t_c - t_b; A.dbg[2] += t_d - t_c; A.dbg[3] += t_e - t_d;)
     }
 }
 
@@ -507,6 +517,7 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             if (sh.state.done) break;
         } else {
             GnWarpAcc A;
+            CT_STAMP(const long long t_it = clock64();)
             if (threadIdx.x == 0) {   // phases A / C read the pose from shared memory: 34 registers less to keep live
                 const int done = __ldcg(&st->done);   // issued with the pose loads: one round trip, not two
                 sh.pose = load_pose(st);
@@ -520,6 +531,7 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 gn_gather_tiles(cfg, stencil, keypoints, kp_lo, kp_hi, tile_w, w * gather_ctas + (blockIdx.x - 1),
                                 gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A, bulk_ptr, P.rigid_first && it == 0);
             }
+            CT_STAMP(const long long t_g = clock64();)
             gn_store_warp_row(sh.acc[w], A, lane);
             __syncthreads();
             if (threadIdx.x < kAcc) {
@@ -528,8 +540,21 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 for (int ww = 0; ww < kGatherWarps; ++ww) s += sh.acc[ww][threadIdx.x];
                 __stcg(&partials[(size_t) (blockIdx.x - 1) * kAcc + threadIdx.x], s);
             }
+            CT_STAMP(if (P.dbg_warp && lane == 0 && it < kDbgIters) {
+                unsigned long long *o = P.dbg_warp + ((size_t) it * (gather_ctas * kGatherWarps) + (w * gather_ctas + (blockIdx.x - 1))) * kDbgSlots;
+                o[0] = (unsigned long long) A.dbg[0]; o[1] = (unsigned long long) A.dbg[1];
+                o[2] = (unsigned long long) A.dbg[2]; o[3] = (unsigned long long) A.dbg[3];
+                o[4] = (unsigned long long) (t_g - t_it);          // pose fetch + tiles
+                o[5] = (unsigned long long) (clock64() - t_it);    // ... + row store + CTA reduction
+            })
         }
+        CT_STAMP(const long long t_bar = clock64();)
         grid.sync();
+        CT_STAMP(if (!solver_cta && P.dbg_warp && lane == 0 && w == 0 && it < kDbgIters) {
+            // (slot 5 of this CTA's first warp is overwritten with the wait at the barrier that follows the gather)
+            unsigned long long *o = P.dbg_warp + ((size_t) it * (gather_ctas * kGatherWarps) + (blockIdx.x - 1)) * kDbgSlots;
+            o[5] = (unsigned long long) (clock64() - t_bar);
+        })
         if (solver_cta) {
             const long long t_begin = threadIdx.x == 0 ? clock64() : 0;
             gn_reduce_rows(sh, partials, gather_ctas, lane, w);
@@ -762,6 +787,36 @@ static int GatherBlocks(size_t k_hint, int max_blocks, int kp_per_cta) {
     return (int) std::max<size_t>(1, std::min(want, (size_t) max_blocks));
 }
 
+void IcpSolver::PrintWarpStamps(int iters) {
+#ifdef CTICP_DEBUG_TIMERS
+    if (!d_dbg_warp_ || dbg_warps_ <= 0) return;
+    const int W = dbg_warps_;
+    std::vector<unsigned long long> h((size_t) kDbgIters * W * kDbgSlots);
+    CT_CUDA_CHECK(cudaMemcpy(h.data(), d_dbg_warp_, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+    static const char *names[kDbgSlots] = {"A pose+voxel", "B gather+select", "C epilogue", "D rows", "fetch+tiles", "barrier wait (per CTA)"};
+    for (int it = 0; it < std::min(iters, kDbgIters); ++it) {
+        fprintf(stderr, "[cticp] GN gather warps, iteration %d (SM cycles; %d warps):", it, W);
+        for (int sl = 0; sl < kDbgSlots; ++sl) {
+            std::vector<unsigned long long> v;
+            for (int w = 0; w < W; ++w) {
+                const unsigned long long x = h[((size_t) it * W + w) * kDbgSlots + sl];
+                const unsigned long long busy = h[((size_t) it * W + w) * kDbgSlots + 4];
+                if (sl == 5 ? (w < W / kGatherWarps) : busy != 0) v.push_back(x);
+            }
+            if (v.empty()) continue;
+            std::sort(v.begin(), v.end());
+            double mean = 0;
+            for (auto x : v) mean += (double) x;
+            mean /= (double) v.size();
+            fprintf(stderr, "  %s mean %.0f p50 %llu p90 %llu max %llu;", names[sl], mean, v[v.size() / 2], v[v.size() * 9 / 10], v.back());
+        }
+        fprintf(stderr, "\n");
+    }
+#else
+    (void) iters;
+#endif
+}
+
 void IcpSolver::CollectGatherTiming() {
     for (int i = 0; i < ev_used_; ++i) {
         float ms = 0.f;
@@ -803,6 +858,19 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         double *parts = d_partials_;
         int iters = num_iters;
         PeerLinks links = peers ? PeerLinksOf(links_host_) : PeerLinks{};
+#ifdef CTICP_DEBUG_TIMERS
+        if (getenv("CTICP_DEBUG_TIMERS")) {
+            const int warps = (grid - 1) * kGatherWarps;
+            if (warps > dbg_warps_) {
+                CT_CUDA_CHECK(cudaStreamSynchronize(stream_));
+                cudaFree(d_dbg_warp_);
+                CT_CUDA_CHECK(cudaMalloc(&d_dbg_warp_, sizeof(unsigned long long) * kDbgIters * warps * kDbgSlots));
+            }
+            dbg_warps_ = warps;
+            CT_CUDA_CHECK(cudaMemsetAsync(d_dbg_warp_, 0, sizeof(unsigned long long) * kDbgIters * warps * kDbgSlots, stream_));
+            cfg.P.dbg_warp = d_dbg_warp_;
+        }
+#endif
         void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters, &links};
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);

@@ -146,3 +146,42 @@ def test_moment_reduction_partition():
         covered += list(range(part * 11, part * 11 + (11 if part < 2 else 10)))
     assert covered == list(range(32))
     assert [lane // 3 for lane in range(27)] == [v for v in range(9) for _ in range(3)]
+
+
+# ---- the exact voxel prune in front of the selection (gather_select.cuh, warp_gather_sums) -------------------------------
+def voxel_box_gap2(q, c, res):
+    """Squared distance from the query to the box that voxel c's points can occupy under Voxel::Coordinates' truncation
+    (include/SlamCore/types.h:65-86): offsets in [0, res) for c > 0, (-res, 0] for c < 0, (-res, res) for c == 0 — with
+    the device code's margin of 1e-6 res."""
+    o = c * res - q
+    m = 1e-6 * res
+    a = o + np.where(c > 0, 0.0, -res) - m
+    b = o + np.where(c < 0, 0.0, res) + m
+    g = np.where(a > 0, a, np.where(b < 0, -b, 0.0))
+    return float((g * g).sum())
+
+
+@pytest.mark.parametrize("res,radius", [(1.0, 0.8), (0.8, 0.75), (0.2, 0.8), (1.0, 0.25)])
+def test_voxel_prune_never_drops_an_in_radius_point(res, radius):
+    rng = np.random.default_rng(5)
+    r = int(np.ceil(radius / res))
+    pruned = kept = 0
+    for _ in range(3000):
+        q = rng.uniform(-3 * res, 3 * res, 3)
+        if rng.random() < 0.2:
+            q[rng.integers(3)] = rng.choice([-res, 0.0, res]) + rng.choice([-1e-12, 0.0, 1e-12])   # on a voxel boundary
+        k = np.trunc(q / res).astype(np.int64)
+        c = k + rng.integers(-r, r + 1, 3)
+        pts = (c * res) + rng.uniform(-res, res, (64, 3))
+        pts = pts[np.all(np.trunc(pts / res).astype(np.int64) == c, axis=1)]   # the points the map files under voxel c
+        if len(pts) == 0:
+            continue
+        # stored as fp32 offsets from the voxel origin (device_map.cuh)
+        pts = c * res + (pts - c * res).astype(np.float32).astype(np.float64)
+        d2 = ((pts - q) ** 2).sum(axis=1)
+        if voxel_box_gap2(q, c, res) > radius * radius:
+            pruned += 1
+            assert not (d2 <= radius * radius).any()
+        else:
+            kept += 1
+    assert pruned > 100 and kept > 100

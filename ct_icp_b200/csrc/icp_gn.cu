@@ -152,62 +152,75 @@ __device__ __noinline__ void warp_gn_solve(const double *acc, SolveScratch &S, I
     }
 }
 
-// ---- the gather half of an iteration: tiles of keypoints per warp --------------------------------------------------
-// A warp owns a TILE of W consecutive keypoints (W = ceil(K / warps in the grid), at most 32: one keypoint per warp
-// while the grid has spare warps — the loop is then bound by the latency of one keypoint —, several when K exceeds the
-// grid, where throughput counts). Per tile:
+// ---- the gather half of an iteration: tiles of keypoints, grabbed by the warps of a CTA ---------------------------------
+// A CTA owns a contiguous, balanced RANGE of the keypoints (static: keypoints c K / G .. (c + 1) K / G of G gather CTAs).
+// Inside the CTA the warps grab TILES of W consecutive keypoints of that range from a shared-memory counter until the range
+// is exhausted (W = ceil(range / 32), at most 16: one keypoint per grab while the range is no longer than two rounds of the
+// CTA's warps, several when throughput counts). Per tile:
 //   A  lane j < W : keypoint j's world position from the pose pair (slerp: two sin, one rsqrt) and its voxel (three
 //                   fp64 divisions)                                                  [once per keypoint, not per lane]
 //   B  all lanes  : for j = 0..W-1 the warp-cooperative gather + selection of gather_select.cuh; lane j keeps the moments
-//   C  lane j < W : covariance → closed-form eigen → normal, a2D, residual, 12-vector Jacobian row
-//   D  all lanes  : the rows of the tile (through shared memory) into the 90 accumulators, three per lane.
-// Round 1 ran A and C redundantly on all 32 lanes of the warp for every keypoint (~1.5k of its ~2.9k warp instructions
-// per keypoint-iteration); here they cost 1/W of that.
+//   C  lane j < W : covariance → closed-form eigen → normal, a2D, residual, 12-vector Jacobian row → the CTA's row table
+// and, when every row of the range is there, the CTA reduces the rows IN KEYPOINT ORDER into the 90 accumulators
+// (gn_cta_reduce_rows): the result does not depend on which warp computed which row, so the work can be handed out
+// dynamically — a warp whose keypoint has a sparse stencil takes the next one while a neighbour is still busy with a
+// dense one — and the registration stays bit-reproducible. Measured before this (profiles/r03b_warp_stamps.log, K = 2430 on
+// 2352 gather warps, static tiles of two): a tile took 9.5k cycles at the median, 17k at p90 and 26k at the maximum, and
+// every iteration waited for that maximum while half of the warps had no tile at all.
 struct GnPose {
     Q4 qb, qe;
     V3 tb, te;
     SlerpConsts sc;
 };
 struct GnWarpAcc {
-    double a0 = 0, a1 = 0, a2 = 0;   // entries lane, lane+32, lane+64 of [A upper | b]
-    double sum_sq = 0;               // per-lane partial counters from here on
-    unsigned n_stencil = 0;
+    double sum_sq = 0;               // (unused since the rows are reduced by the CTA; kept for the launch-per-step variants)
+    unsigned n_stencil = 0;          // per-lane partial counters
     int n_used = 0, n_kp = 0, n_valid = 0;
     CT_STAMP(long long dbg[4] = {0, 0, 0, 0};)   // cycles in phases A, B, C, D
 };
 constexpr int kDbgIters = 8, kDbgSlots = 6;
 
 constexpr int kTileMax = 16;   // keypoints per warp tile (phases A / C cost 1/W per keypoint: 16 is deep in the flat part)
+constexpr int kRowCap = 256;   // rows of a CTA's range held in shared memory at a time (longer ranges go in chunks)
+constexpr int kRowParts = 5;   // the row reduction splits the rows over 5 x 96 threads
 
-// Per-warp shared memory of a tile: the gather's staging area, the moments of each keypoint of the tile (phase B hands
-// them to phase C through here instead of through 27 registers that would stay live across the gather), and the tile's
-// Jacobian rows.
+// Per-warp shared memory of a tile: the gather's staging area and the moments of each keypoint of the tile (phase B hands
+// them to phase C through here instead of through 27 registers that would stay live across the gather).
 struct __align__(16) TileScratch {
     SelScratch sel;
     double sums[kTileMax][14];   // NeighborSums of keypoint j: n, stencil points, s*, f*
-    double rows[kTileMax][13];   // u[0..11], -scalar
+};
+// Per-CTA row table of the current chunk of the CTA's range
+struct __align__(16) CtaRows {
+    double u[kRowCap][13];       // u[0..11], -scalar of keypoint (chunk base + r); valid iff used[r]
+    unsigned char used[kRowCap];
+    double red[kRowParts][kAcc];
+    int next;                    // tile counter of the chunk
 };
 
-// keypoints per warp tile for `span` keypoints over the grid's warps (an integer division: once per kernel, not per iteration)
-__device__ __forceinline__ int gn_tile_width(int span, int warps_total) {
-    const int W = warps_total > 0 ? (span + warps_total - 1) / warps_total : 1;
+// keypoints per tile for a CTA range of `span` keypoints
+__device__ __forceinline__ int gn_tile_width(int span) {
+    const int W = (span + 2 * CTICP_GATHER_WARPS - 1) / (2 * CTICP_GATHER_WARPS);
     return W < kTileMax ? (W < 1 ? 1 : W) : kTileMax;
 }
 
+// The tiles of the chunk [lo, hi) of this CTA's range (hi - lo <= kRowCap); R.next must be 0 and visible (barrier) on entry.
 __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const int *stencil,
-                                                const float4 *__restrict__ keypoints, int lo, int hi, int W, int warp_global,
-                                                int warps_total, const GnPose &pose, TileScratch &T, int lane,
+                                                const float4 *__restrict__ keypoints, int lo, int hi, int W,
+                                                const GnPose &pose, TileScratch &T, CtaRows &R, int lane,
                                                 GnWarpAcc &A, void *bulk = nullptr, bool rigid = false) {
     const GatherConfig &G = cfg.G;
     const GnParams &P = cfg.P;
     if (hi <= lo) return;
     const int need = P.kmin > 5 ? P.kmin : 5;   // ct_icp.cpp:769 ; neighborhood.h:227
     const double inv_res = 1.0 / G.L.res;
-    const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
-    const int pi0 = c_pair_i[i0], pj0 = c_pair_j[i0], pi1 = c_pair_i[i1], pj1 = c_pair_j[i1];
-    const int pi2 = i2 < kAccUsed ? c_pair_i[i2] : 0, pj2 = i2 < kAccUsed ? c_pair_j[i2] : 0;
 
-    for (int t0 = lo + warp_global * W; t0 < hi; t0 += warps_total * W) {
+    while (true) {
+        int j0 = 0;
+        if (lane == 0) j0 = atomicAdd(&R.next, W);
+        j0 = __shfl_sync(0xffffffffu, j0, 0);
+        const int t0 = lo + j0;
+        if (t0 >= hi) break;
         const int wt = (hi - t0) < W ? (hi - t0) : W;
         CT_STAMP(const long long t_a = clock64();)
         // ---- A: world_kpts[i] = InterpolatePose(begin, end, t_i) * raw_i  (ct_icp.cpp:964-966, types.h:361-366)
@@ -244,8 +257,8 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
         __syncwarp();
         CT_STAMP(const long long t_c = clock64();)
         // ---- C (ct_icp.cpp:769-850)
-        bool used = false;
         if (lane < wt) {
+            bool used = false;
             const double *o = T.sums[lane];
             NeighborSums mine;
             mine.n = __double2loint(o[0]);
@@ -272,7 +285,7 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
                     const V3 ob = qrot(pose.qb, raw), oe = qrot(pose.qe, raw);   // :813-816
                     const double a = kraw.alpha, am = 1.0 - a;
                     const V3 cb = cross(ob, nw), ce = cross(oe, nw);
-                    double *u = T.rows[lane];
+                    double *u = R.u[j0 + lane];
                     u[0] = am * cb.x; u[1] = am * cb.y; u[2] = am * cb.z;
                     u[3] = am * nw.x; u[4] = am * nw.y; u[5] = am * nw.z;
                     u[6] = a * ce.x;  u[7] = a * ce.y;  u[8] = a * ce.z;
@@ -280,50 +293,63 @@ __device__ __forceinline__ void gn_gather_tiles(const GatherLaunch &cfg, const i
                     u[12] = -scalar;   // b -= u * scalar (:849)
                     used = true;
                     A.n_used += 1;
-                    A.sum_sq += scalar * scalar;
                 }
             }
+            R.used[j0 + lane] = used ? 1 : 0;
         }
-        // ---- D: A += u u^T, b -= u scalar, in keypoint order (deterministic)
-        CT_STAMP(const long long t_d = clock64();)
-        unsigned mask = __ballot_sync(0xffffffffu, used);
-        __syncwarp();
-        while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const double *u = T.rows[j];
-            A.a0 += u[pi0] * u[pj0];
-            A.a1 += u[pi1] * u[pj1];
-            if (i2 < kAccUsed) A.a2 += u[pi2] * u[pj2];
-        }
-        __syncwarp();   // the rows are consumed before the next tile rewrites them
+        __syncwarp();   // the moments are consumed before the next tile rewrites them
         CT_STAMP(const long long t_e = clock64();
-                 A.dbg[0] += t_b - t_a; A.dbg[1] += t_c - t_b; A.dbg[2] += t_d - t_c; A.dbg[3] += t_e - t_d;)
+                 A.dbg[0] += t_b - t_a; A.dbg[1] += t_c - t_b; A.dbg[2] += t_e - t_c;)
     }
 }
 
-// per-warp accumulators → one row of `kAcc` doubles per warp in shared memory (counters reduced over the lanes)
+// A += u u^T, b -= u scalar over the rows [0, n) of the chunk, in keypoint order within each of kRowParts interleaved
+// classes, the classes then in fixed order: deterministic whatever warp wrote a row. Thread t < kRowParts * kAcc handles
+// accumulator t % kAcc (entries 0..89: pairs of [A upper | b]; 90: rows used; 91: Σ scalar²) of class t / kAcc. The sum
+// of the chunk is ADDED to `carry` of the threads < kAcc. Called by all threads of the CTA; barriers inside.
+__device__ __forceinline__ void gn_cta_reduce_rows(CtaRows &R, int n, double &carry) {
+    const int t = threadIdx.x;
+    const int a = t % kAcc, part = t / kAcc;
+    __syncthreads();   // every row of the chunk is written
+    if (part < kRowParts && a <= kAccSumSq) {
+        const int pi = a < kAccUsed ? c_pair_i[a] : 12, pj = a < kAccUsed ? c_pair_j[a] : 12;
+        double s = 0;
+        if (a == kAccUsed) {
+            int c = 0;
+            for (int r = part; r < n; r += kRowParts) c += R.used[r];
+            s = i32_to_f64(c);
+        } else {
+            for (int r = part; r < n; r += kRowParts)
+                if (R.used[r]) s += R.u[r][pi] * R.u[r][pj];
+        }
+        R.red[part][a] = s;
+    }
+    __syncthreads();
+    if (t < kAcc && a <= kAccSumSq) {
+        double s = R.red[0][a];
+#pragma unroll
+        for (int q = 1; q < kRowParts; ++q) s += R.red[q][a];
+        carry += s;
+    }
+}
+
+// per-warp counters → the warp's row of `kAcc` doubles in shared memory (the accumulators come from gn_cta_reduce_rows)
 __device__ __forceinline__ void gn_store_warp_row(double *row, const GnWarpAcc &A, int lane) {
-    row[lane] = A.a0;
-    row[lane + 32] = A.a1;
-    if (lane + 64 < kAccUsed) row[lane + 64] = A.a2;
-    const double sum_sq = warp_sum(A.sum_sq);
     const unsigned n_stencil = __reduce_add_sync(0xffffffffu, A.n_stencil);
-    const int n_used = __reduce_add_sync(0xffffffffu, A.n_used), n_kp = __reduce_add_sync(0xffffffffu, A.n_kp),
-              n_valid = __reduce_add_sync(0xffffffffu, A.n_valid);
+    const int n_kp = __reduce_add_sync(0xffffffffu, A.n_kp), n_valid = __reduce_add_sync(0xffffffffu, A.n_valid);
     if (lane == 0) {
-        row[kAccUsed] = i32_to_f64(n_used);
-        row[kAccSumSq] = sum_sq;
         row[kAccStencil] = i32_to_f64((int) n_stencil);
         row[kAccKeypoints] = i32_to_f64(n_kp);
         row[kAccValidNb] = i32_to_f64(n_valid);
-        row[95] = 0;
     }
 }
 
+// The gather half of an iteration for one CTA: its range [c_lo, c_hi) of the keypoints in chunks of kRowCap rows →
+// this CTA's partial row (kAcc doubles) in global memory. `R.next` is reset here; all threads call.
 // shared memory of the GN kernels (dynamic: the staging areas alone are 70 KB)
 struct GnShared {
     TileScratch tile[kGatherWarps];
+    CtaRows rows;
     GnPose pose;
     double acc[kGatherWarps][kAcc];
     int stencil[kMaxStencil];
@@ -377,6 +403,36 @@ __device__ __forceinline__ void gn_reduce_rows(GnShared &sh, const double *__res
     __syncthreads();
 }
 
+// The gather half of an iteration for one CTA: its range [c_lo, c_hi) of the keypoints, in chunks of kRowCap rows →
+// the CTA's partial row (kAcc doubles) at `partial_out` (global). On entry sh.pose is valid and sh.rows.next == 0, both
+// visible to the CTA (the thread that fetched the pose set them before a barrier). All threads call.
+__device__ __forceinline__ void gn_cta_gather(const GatherLaunch &cfg, const int *stencil, const float4 *__restrict__ keypoints,
+                                              int c_lo, int c_hi, GnShared &sh, int lane, int w, double *partial_out,
+                                              GnWarpAcc &A, void *bulk, bool rigid) {
+    const int W = gn_tile_width(c_hi - c_lo);
+    double carry = 0;
+    for (int base = c_lo;; base += kRowCap) {
+        const int top = (c_hi - base) > kRowCap ? base + kRowCap : c_hi;
+        gn_gather_tiles(cfg, stencil, keypoints, base, top, W, sh.pose, sh.tile[w], sh.rows, lane, A, bulk, rigid);
+        gn_cta_reduce_rows(sh.rows, top > base ? top - base : 0, carry);
+        if (top >= c_hi) break;
+        if (threadIdx.x == 0) sh.rows.next = 0;
+        __syncthreads();
+    }
+    gn_store_warp_row(sh.acc[w], A, lane);
+    __syncthreads();
+    if (threadIdx.x < kAcc) {
+        const int t = threadIdx.x;
+        double s = 0;
+        if (t <= kAccSumSq) s = carry;
+        else if (t == kAccStencil || t == kAccKeypoints || t == kAccValidNb) {
+#pragma unroll
+            for (int ww = 0; ww < kGatherWarps; ++ww) s += sh.acc[ww][t];
+        }
+        __stcg(partial_out + t, s);
+    }
+}
+
 __device__ __forceinline__ GnPose load_pose(const IcpState *st) {
     GnPose p;
     p.qb = Q4{__ldcg(&st->qb[0]), __ldcg(&st->qb[1]), __ldcg(&st->qb[2]), __ldcg(&st->qb[3])};
@@ -409,26 +465,23 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
     sel_bulk_init(bulk, &sh.mbar[w], lane);
     bulk_ptr = &bulk;
 #endif
-    if (active) {
+    {
         const int *stencil = stencil_table_fill(sh.stencil, cfg.G.r);
-        if (threadIdx.x == 0) sh.pose = load_pose(st);
+        if (threadIdx.x == 0) {
+            sh.pose = load_pose(st);
+            sh.rows.next = 0;
+        }
         __syncthreads();
-        const GnPose &pose = sh.pose;
-        const int K = *d_num_keypoints;
-        const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
-        const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-        gn_gather_tiles(cfg, stencil, keypoints, lo, hi, gn_tile_width(hi - lo, gridDim.x * kGatherWarps),
-                        w * gridDim.x + blockIdx.x, gridDim.x * kGatherWarps, pose,
-                        sh.tile[w], lane, A, bulk_ptr, P.rigid_first && __ldcg(&st->iter) == 0);
-    }
-    // block reduction (fixed order → run-to-run deterministic)
-    gn_store_warp_row(sh.acc[w], A, lane);
-    __syncthreads();
-    if (threadIdx.x < kAcc) {
-        double s = 0;
-#pragma unroll
-        for (int ww = 0; ww < kGatherWarps; ++ww) s += sh.acc[ww][threadIdx.x];
-        partials[(size_t) blockIdx.x * kAcc + threadIdx.x] = s;
+        int c_lo = 0, c_hi = 0;   // inactive (the registration has converged): an empty range, a zero partial row
+        if (active) {
+            const int K = *d_num_keypoints;
+            const int lo = (int) ((long long) K * P.shard_rank / P.shard_world);
+            const int hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+            c_lo = lo + (int) ((long long) (hi - lo) * blockIdx.x / gridDim.x);
+            c_hi = lo + (int) ((long long) (hi - lo) * (blockIdx.x + 1) / gridDim.x);
+        }
+        gn_cta_gather(cfg, stencil, keypoints, c_lo, c_hi, sh, lane, w, partials + (size_t) blockIdx.x * kAcc, A, bulk_ptr,
+                      active && P.rigid_first && __ldcg(&st->iter) == 0);
     }
     // ---- last CTA to finish reduces the partials (fixed order) and takes the Gauss-Newton step -----------------
     __threadfence();
@@ -510,7 +563,12 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
         kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
         kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
     }
-    const int tile_w = gn_tile_width(kp_hi - kp_lo, gather_ctas * kGatherWarps);
+    // this CTA's balanced share of the range
+    int c_lo = 0, c_hi = 0;
+    if (!solver_cta) {
+        c_lo = kp_lo + (int) ((long long) (kp_hi - kp_lo) * (blockIdx.x - 1) / gather_ctas);
+        c_hi = kp_lo + (int) ((long long) (kp_hi - kp_lo) * blockIdx.x / gather_ctas);
+    }
     for (int it = 0; it < num_iters; ++it) {
         // `done` is uniform over the grid: published before the previous grid barrier (the solver CTA reads its own copy)
         if (solver_cta) {
@@ -522,30 +580,23 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 const int done = __ldcg(&st->done);   // issued with the pose loads: one round trip, not two
                 sh.pose = load_pose(st);
                 sh.done = done;
+                sh.rows.next = 0;
             }
             __syncthreads();
             if (sh.done) break;
-            if (!(P.debug_flags & 2)) {
-                const GnPose &pose = sh.pose;
-                // warp index interleaved over the CTAs: a keypoint set smaller than the grid spreads over all SMs
-                gn_gather_tiles(cfg, stencil, keypoints, kp_lo, kp_hi, tile_w, w * gather_ctas + (blockIdx.x - 1),
-                                gather_ctas * kGatherWarps, pose, sh.tile[w], lane, A, bulk_ptr, P.rigid_first && it == 0);
-            }
+            CT_STAMP(const long long t_g0 = clock64();)
+            // (CTICP_DEBUG_FLAGS & 2, timing only: an empty range — the barriers and the reduction without the gather work)
+            const bool skip = (P.debug_flags & 2) != 0;
+            gn_cta_gather(cfg, stencil, keypoints, skip ? 0 : c_lo, skip ? 0 : c_hi, sh, lane, w,
+                          partials + (size_t) (blockIdx.x - 1) * kAcc, A, bulk_ptr, P.rigid_first && it == 0);
             CT_STAMP(const long long t_g = clock64();)
-            gn_store_warp_row(sh.acc[w], A, lane);
-            __syncthreads();
-            if (threadIdx.x < kAcc) {
-                double s = 0;
-#pragma unroll
-                for (int ww = 0; ww < kGatherWarps; ++ww) s += sh.acc[ww][threadIdx.x];
-                __stcg(&partials[(size_t) (blockIdx.x - 1) * kAcc + threadIdx.x], s);
-            }
             CT_STAMP(if (P.dbg_warp && lane == 0 && it < kDbgIters) {
                 unsigned long long *o = P.dbg_warp + ((size_t) it * (gather_ctas * kGatherWarps) + (w * gather_ctas + (blockIdx.x - 1))) * kDbgSlots;
                 o[0] = (unsigned long long) A.dbg[0]; o[1] = (unsigned long long) A.dbg[1];
-                o[2] = (unsigned long long) A.dbg[2]; o[3] = (unsigned long long) A.dbg[3];
-                o[4] = (unsigned long long) (t_g - t_it);          // pose fetch + tiles
-                o[5] = (unsigned long long) (clock64() - t_it);    // ... + row store + CTA reduction
+                o[2] = (unsigned long long) A.dbg[2];
+                o[3] = (unsigned long long) (t_g0 - t_it);         // pose fetch + barrier
+                o[4] = (unsigned long long) (t_g - t_it);          // pose fetch + tiles + CTA row reduction
+                o[5] = 0;
             })
         }
         CT_STAMP(const long long t_bar = clock64();)
@@ -793,7 +844,7 @@ void IcpSolver::PrintWarpStamps(int iters) {
     const int W = dbg_warps_;
     std::vector<unsigned long long> h((size_t) kDbgIters * W * kDbgSlots);
     CT_CUDA_CHECK(cudaMemcpy(h.data(), d_dbg_warp_, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
-    static const char *names[kDbgSlots] = {"A pose+voxel", "B gather+select", "C epilogue", "D rows", "fetch+tiles", "barrier wait (per CTA)"};
+    static const char *names[kDbgSlots] = {"A pose+voxel", "B gather+select", "C epilogue", "pose fetch", "fetch+tiles+row reduction", "barrier wait (per CTA)"};
     for (int it = 0; it < std::min(iters, kDbgIters); ++it) {
         fprintf(stderr, "[cticp] GN gather warps, iteration %d (SM cycles; %d warps):", it, W);
         for (int sl = 0; sl < kDbgSlots; ++sl) {

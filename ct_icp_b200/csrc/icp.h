@@ -152,7 +152,8 @@ private:
     double *d_sys_ = nullptr;      // 12*12 + 12 + 4 debug output of the solve kernel
     double *d_acc_ = nullptr;      // reduced accumulator (multi-GPU all-reduce buffer)
     unsigned int *d_ticket_ = nullptr;   // last-CTA-done counter of k_gn_iterate
-    unsigned int *d_sync_words_ = nullptr;   // arrive counter + epoch of k_gn_persistent
+    unsigned int *d_sync_words_ = nullptr;   // two sets of (arrive counter, epoch) of k_gn_persistent, alternating per launch
+    int sync_set_ = 0;
     // solver CERES (icp_lm.cu)
     void *d_lm_state_ = nullptr, *d_lm_stats_ = nullptr, *d_lm_blocks_ = nullptr;
     int *d_lm_sel_ = nullptr;

@@ -155,8 +155,8 @@ __device__ __noinline__ void warp_gn_solve(const double *acc, SolveScratch &S, I
 // ---- the gather half of an iteration: tiles of keypoints, grabbed by the warps of a CTA ---------------------------------
 // A CTA owns a contiguous, balanced RANGE of the keypoints (static: keypoints c K / G .. (c + 1) K / G of G gather CTAs).
 // Inside the CTA the warps grab TILES of W consecutive keypoints of that range from a shared-memory counter until the range
-// is exhausted (W = ceil(range / 32), at most 16: one keypoint per grab while the range is no longer than two rounds of the
-// CTA's warps, several when throughput counts). Per tile:
+// is exhausted (one keypoint per grab while the range is no longer than two rounds of the CTA's warps, else ceil(range / warps), at
+// most 16, when throughput counts). Per tile:
 //   A  lane j < W : keypoint j's world position from the pose pair (slerp: two sin, one rsqrt) and its voxel (three
 //                   fp64 divisions)                                                  [once per keypoint, not per lane]
 //   B  all lanes  : for j = 0..W-1 the warp-cooperative gather + selection of gather_select.cuh; lane j keeps the moments
@@ -200,8 +200,12 @@ struct __align__(16) CtaRows {
 
 // keypoints per tile for a CTA range of `span` keypoints
 __device__ __forceinline__ int gn_tile_width(int span) {
-    const int W = (span + 2 * CTICP_GATHER_WARPS - 1) / (2 * CTICP_GATHER_WARPS);
-    return W < kTileMax ? (W < 1 ? 1 : W) : kTileMax;
+    // one keypoint per grab while the range is at most two rounds of the CTA's warps (the loop is bound by the slowest
+    // keypoint there: balance counts); beyond that one tile per warp, as wide as it gets (throughput: the lane-per-keypoint
+    // phases cost 1/W per keypoint — measured on the dense workload, K = 32k: tiles of 7 cost 6 % more than tiles of 14)
+    if (span <= 2 * CTICP_GATHER_WARPS) return 1;
+    const int W = (span + CTICP_GATHER_WARPS - 1) / CTICP_GATHER_WARPS;
+    return W < kTileMax ? W : kTileMax;
 }
 
 // The tiles of the chunk [lo, hi) of this CTA's range (hi - lo <= kRowCap); R.next must be 0 and visible (barrier) on entry.
@@ -500,6 +504,33 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
     warp_gn_solve(sh.acc[0], sh.solve, st, P, mode, sys_out, lane);
 }
 
+// ---- synchronisation of the persistent loop: two flags instead of two grid-wide barriers per iteration ------------------
+// The loop's dependencies are asymmetric: the solver CTA needs every gather CTA's partial row; a gather CTA needs the solver
+// CTA's new pose — it never needs the OTHER gather CTAs. So a gather CTA only ARRIVES (fence + one atomic, no wait) and then
+// polls the epoch word the solver CTA bumps after publishing the state, and the solver CTA polls the arrival counter. Per
+// iteration that is one L2 round trip on each side instead of two cg::grid.sync() (measured 2.0 us each on 148 CTAs,
+// profiles/r03c_coop_launch_cost.txt: 8k of the ~47k cycles of an iteration) plus the separate fetch of the pose.
+// The launch stays cooperative: the CTAs must be co-resident for the polls to make progress. Every poll is bounded: a
+// protocol error ends the kernel with st->failed = 2 instead of hanging the device.
+// Two sets of words alternate between launches; the solver CTA of a launch zeroes the set of the NEXT launch (nobody touches
+// it meanwhile), so no memset sits between the sampler and this kernel.
+#ifndef CTICP_GN_GRID_BARRIERS
+#define CTICP_GN_FLAG_SYNC 1
+#endif
+struct LoopSync {
+    unsigned int *arrive;   // += 1 by every gather CTA at the end of its gather
+    unsigned int *epoch;    // = iterations published by the solver CTA
+    unsigned int *next_arrive, *next_epoch;   // the other set
+};
+constexpr long long kLoopSyncTimeout = 4000000000LL;   // SM cycles (~2 s)
+__device__ __forceinline__ bool loop_wait_at_least(const unsigned int *word, unsigned int want) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned int *>(word) < want)
+        if (clock64() - t0 > kLoopSyncTimeout) return false;
+    __threadfence();
+    return true;
+}
+
 // ---- persistent variant: the WHOLE Gauss-Newton loop in one cooperative launch --------------------------------
 // CTA 0 is the solver CTA (deterministic reduction of the partials + 12x12 solve + pose update, by the same warp on
 // the same SM every iteration, so its instructions stay in that SM's instruction cache: executed cold, the serial tail
@@ -513,12 +544,20 @@ k_gn_iterate(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *
 template <bool kPeers>
 __global__ void __launch_bounds__(kGatherWarps * 32, 1)
 k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
-                IcpState *st, double *__restrict__ partials, int num_iters, PeerLinks links) {
+                IcpState *st, double *__restrict__ partials, int num_iters, PeerLinks links, LoopSync sync) {
+#ifndef CTICP_GN_FLAG_SYNC
     cg::grid_group grid = cg::this_grid();
+#endif
     GnShared &sh = *reinterpret_cast<GnShared *>(gn_smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const GnParams &P = cfg.P;
     const bool solver_cta = blockIdx.x == 0;
+#ifdef CTICP_GN_FLAG_SYNC
+    if (solver_cta && threadIdx.x == 0) {   // the next launch's words (idle during this launch)
+        *sync.next_arrive = 0u;
+        *sync.next_epoch = 0u;
+    }
+#endif
     unsigned int peer_seq = 0;   // sequence number of the last exchange (solver CTA only)
     if (kPeers && solver_cta) peer_seq = *links.seq;
     const int gather_ctas = gridDim.x - 1;
@@ -577,9 +616,15 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             GnWarpAcc A;
             CT_STAMP(const long long t_it = clock64();)
             if (threadIdx.x == 0) {   // phases A / C read the pose from shared memory: 34 registers less to keep live
+#ifdef CTICP_GN_FLAG_SYNC
+                // the state of iteration `it` is published (it == 0: uploaded by the host before the launch)
+                const bool ok = it == 0 || loop_wait_at_least(sync.epoch, (unsigned int) it);
+#else
+                const bool ok = true;
+#endif
                 const int done = __ldcg(&st->done);   // issued with the pose loads: one round trip, not two
                 sh.pose = load_pose(st);
-                sh.done = done;
+                sh.done = ok ? done : 1;
                 sh.rows.next = 0;
             }
             __syncthreads();
@@ -590,6 +635,11 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             gn_cta_gather(cfg, stencil, keypoints, skip ? 0 : c_lo, skip ? 0 : c_hi, sh, lane, w,
                           partials + (size_t) (blockIdx.x - 1) * kAcc, A, bulk_ptr, P.rigid_first && it == 0);
             CT_STAMP(const long long t_g = clock64();)
+#ifdef CTICP_GN_FLAG_SYNC
+            __threadfence();   // (the writers of the partial row)
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(sync.arrive, 1u);
+#endif
             CT_STAMP(if (P.dbg_warp && lane == 0 && it < kDbgIters) {
                 unsigned long long *o = P.dbg_warp + ((size_t) it * (gather_ctas * kGatherWarps) + (w * gather_ctas + (blockIdx.x - 1))) * kDbgSlots;
                 o[0] = (unsigned long long) A.dbg[0]; o[1] = (unsigned long long) A.dbg[1];
@@ -598,9 +648,30 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                 o[4] = (unsigned long long) (t_g - t_it);          // pose fetch + tiles + CTA row reduction
                 o[5] = 0;
             })
+#ifdef CTICP_GN_FLAG_SYNC
+            if (it == num_iters - 1) break;   // nothing left to wait for: the solver CTA finishes the registration alone
+#endif
         }
         CT_STAMP(const long long t_bar = clock64();)
+#ifdef CTICP_GN_FLAG_SYNC
+        if (solver_cta) {
+            if (threadIdx.x == 0) sh.flag = loop_wait_at_least(sync.arrive, (unsigned int) (gather_ctas * (it + 1))) ? 1 : 0;
+            __syncthreads();
+            if (!sh.flag) {   // a gather CTA never arrived: give up (the host raises "Error During Optimization")
+                if (threadIdx.x == 0) {
+                    sh.state.failed = 2;
+                    sh.state.done = 1;
+                    st->failed = 2;
+                    st->done = 1;
+                    __threadfence();
+                    atomicExch(sync.epoch, 0x7fffffffu);
+                }
+                break;
+            }
+        }
+#else
         grid.sync();
+#endif
         CT_STAMP(if (!solver_cta && P.dbg_warp && lane == 0 && w == 0 && it < kDbgIters) {
             // (slot 5 of this CTA's first warp is overwritten with the wait at the barrier that follows the gather)
             unsigned long long *o = P.dbg_warp + ((size_t) it * (gather_ctas * kGatherWarps) + (blockIdx.x - 1)) * kDbgSlots;
@@ -646,10 +717,21 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
                     ws->dbg_t[1] += (unsigned long long) (clock64() - t_rest);
                     __stcg(&st->dbg_t[1], ws->dbg_t[1]);
                 })
+#ifdef CTICP_GN_FLAG_SYNC
+                __threadfence();   // (the lanes that wrote the state)
+                __syncwarp();
+                if (lane == 0) atomicExch(sync.epoch, (unsigned int) (it + 1));
+#endif
             }
+#ifdef CTICP_GN_FLAG_SYNC
+            __syncthreads();   // warp 0 is done with sh.acc / sh.state before the next iteration's reduction
+#else
             __threadfence();
+#endif
         }
+#ifndef CTICP_GN_FLAG_SYNC
         grid.sync();
+#endif
     }
     if (kPeers && solver_cta && threadIdx.x == 0) *links.seq = peer_seq;
 }
@@ -786,7 +868,8 @@ IcpSolver::IcpSolver(cudaStream_t stream) : stream_(stream) {
     CT_CUDA_CHECK(cudaMalloc(&d_acc_, sizeof(double) * kAcc));
     CT_CUDA_CHECK(cudaMalloc(&d_ticket_, sizeof(unsigned int)));
     CT_CUDA_CHECK(cudaMemset(d_ticket_, 0, sizeof(unsigned int)));
-    CT_CUDA_CHECK(cudaMalloc(&d_sync_words_, sizeof(unsigned int) * 2));
+    CT_CUDA_CHECK(cudaMalloc(&d_sync_words_, sizeof(unsigned int) * 128));   // two sets of (arrive, epoch), a 128-byte line each
+    CT_CUDA_CHECK(cudaMemset(d_sync_words_, 0, sizeof(unsigned int) * 128));
     for (int i = 0; i < kMaxEvents; ++i) {
         CT_CUDA_CHECK(cudaEventCreate(&ev_begin_[i]));
         CT_CUDA_CHECK(cudaEventCreate(&ev_end_[i]));
@@ -922,7 +1005,13 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
             cfg.P.dbg_warp = d_dbg_warp_;
         }
 #endif
-        void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters, &links};
+        LoopSync sync;
+        sync.arrive = d_sync_words_ + 64 * sync_set_;
+        sync.epoch = sync.arrive + 32;
+        sync.next_arrive = d_sync_words_ + 64 * (sync_set_ ^ 1);
+        sync.next_epoch = sync.next_arrive + 32;
+        sync_set_ ^= 1;
+        void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters, &links, &sync};
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
         CT_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kGatherWarps * 32), args, sizeof(GnShared), stream_));

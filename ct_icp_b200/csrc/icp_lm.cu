@@ -123,14 +123,28 @@ __device__ __forceinline__ NeighborSums lm_load_sums(const double *o) {
     return s;
 }
 
-// One warp's share of the residual assembly of solver CERES (ct_icp.cpp:561-604). warp_global / warps_total: this warp's
-// index among all gathering warps of the launch (interleaved over the CTAs by the callers).
+// The tiles of a CTA's share of the keypoints: CTA `cta` of `num_ctas` owns a contiguous, balanced range; its
+// `warps_per_cta` warps grab tiles of W consecutive keypoints from the shared-memory counter `next` (0 and visible on entry)
+// until the range is exhausted — a warp whose keypoint has a sparse stencil takes the next one while a neighbour is still busy
+// with a dense one. The blocks are written by keypoint index, so the result does not depend on who assembled them.
+__device__ __forceinline__ int lm_tile_width(int span, int warps_per_cta) {
+    if (span <= 2 * warps_per_cta) return 1;
+    const int W = (span + warps_per_cta - 1) / warps_per_cta;
+    return W < kLmTileMax ? W : kLmTileMax;
+}
+__device__ __forceinline__ int lm_grab_tile(int *next, int W, int lane) {
+    int j0 = 0;
+    if (lane == 0) j0 = atomicAdd(next, W);
+    return __shfl_sync(0xffffffffu, j0, 0);
+}
+
+// One warp's share of the residual assembly of solver CERES (ct_icp.cpp:561-604).
 template <bool kDB>
 __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmParams &P, const int *stencil,
                                                 const float4 *__restrict__ keypoints, int K, const IcpState *st,
                                                 ResidualBlock *__restrict__ blocks, unsigned long long *stats,
-                                                const DistanceStrategy *__restrict__ D, LmTile &T, int warp_global,
-                                                int warps_total, int lane) {
+                                                const DistanceStrategy *__restrict__ D, LmTile &T, int cta, int num_ctas,
+                                                int warps_per_cta, int *next, int lane) {
     const Q4 qb{__ldcg(&st->qb[0]), __ldcg(&st->qb[1]), __ldcg(&st->qb[2]), __ldcg(&st->qb[3])},
         qe{__ldcg(&st->qe[0]), __ldcg(&st->qe[1]), __ldcg(&st->qe[2]), __ldcg(&st->qe[3])};
     const V3 tb{__ldcg(&st->tb[0]), __ldcg(&st->tb[1]), __ldcg(&st->tb[2])}, te{__ldcg(&st->te[0]), __ldcg(&st->te[1]), __ldcg(&st->te[2])};
@@ -139,11 +153,14 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
     // keypoint-sharded mode: this rank assembles the blocks of its contiguous chunk only
     const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
     const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-    int W = (kp_hi - kp_lo + warps_total - 1) / warps_total;
-    W = W < kLmTileMax ? (W < 1 ? 1 : W) : kLmTileMax;
+    const int c_lo = kp_lo + (int) ((long long) (kp_hi - kp_lo) * cta / num_ctas);
+    const int c_hi = kp_lo + (int) ((long long) (kp_hi - kp_lo) * (cta + 1) / num_ctas);
+    const int W = lm_tile_width(c_hi - c_lo, warps_per_cta);
     const int need = P.kmin > 5 ? P.kmin : 5;   // :574 ; neighborhood.h:227
-    for (int t0 = kp_lo + warp_global * W; t0 < kp_hi; t0 += warps_total * W) {
-        const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
+    while (true) {
+        const int t0 = c_lo + lm_grab_tile(next, W, lane);
+        if (t0 >= c_hi) break;
+        const int wt = (c_hi - t0) < W ? (c_hi - t0) : W;
         // ---- lane j: transform_keypoints() (ct_icp.cpp:516-531) and, for the distance-based strategy, this
         // keypoint's radius → map level + stencil (neighborhood_strategy.h:121-126, map.h:416-432)
         V3 p{0, 0, 0};
@@ -254,12 +271,14 @@ k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, c
             const DistanceStrategy *__restrict__ D) {
     __shared__ LmTile s_tile[kLmWarps];
     __shared__ int s_stencil[kMaxStencil];
+    __shared__ int s_next;
     if (st->done) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int *stencil = kDB ? nullptr : stencil_table_fill(s_stencil, G0.r);
+    if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
     lm_gather_tiles<kDB>(G0, P, stencil, keypoints, *d_num_keypoints, st, blocks, stats, D, s_tile[w],
-                         w * (int) gridDim.x + (int) blockIdx.x, (int) gridDim.x * kLmWarps, lane);
+                         (int) blockIdx.x, (int) gridDim.x, kLmWarps, &s_next, lane);
 }
 
 // Solver ROBUST's per-keypoint assembly (ct_icp.cpp:1229-1289): same gather, the neighborhood is classified planar /
@@ -270,8 +289,8 @@ k_lm_gather(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoints, c
 __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmParams &P, const int *stencil,
                                                 const float4 *__restrict__ keypoints, int K, const IcpState *st,
                                                 ResidualBlock *__restrict__ blocks, unsigned char *__restrict__ classes,
-                                                unsigned long long *stats, LmTile &T, int warp_global, int warps_total,
-                                                int lane) {
+                                                unsigned long long *stats, LmTile &T, int cta, int num_ctas,
+                                                int warps_per_cta, int *next, int lane) {
     enum { NONE = 0, LINEAR = 1, PLANAR = 2, VOLUMIC = 3 };
     const Q4 qb{__ldcg(&st->qb[0]), __ldcg(&st->qb[1]), __ldcg(&st->qb[2]), __ldcg(&st->qb[3])},
         qe{__ldcg(&st->qe[0]), __ldcg(&st->qe[1]), __ldcg(&st->qe[2]), __ldcg(&st->qe[3])};
@@ -281,12 +300,15 @@ __device__ __noinline__ void rb_gather_tiles(const GatherConfig &G, const LmPara
     // keypoint-sharded mode: this rank assembles the blocks of its contiguous chunk only
     const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
     const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
-    int W = (kp_hi - kp_lo + warps_total - 1) / warps_total;
-    W = W < kLmTileMax ? (W < 1 ? 1 : W) : kLmTileMax;
+    const int c_lo = kp_lo + (int) ((long long) (kp_hi - kp_lo) * cta / num_ctas);
+    const int c_hi = kp_lo + (int) ((long long) (kp_hi - kp_lo) * (cta + 1) / num_ctas);
+    const int W = lm_tile_width(c_hi - c_lo, warps_per_cta);
     const int need = P.kmin;   // :1238 (kmin >= 5 is enforced by the host, so the neighborhood is always describable)
     const double inv_res = 1.0 / G.L.res;
-    for (int t0 = kp_lo + warp_global * W; t0 < kp_hi; t0 += warps_total * W) {
-        const int wt = (kp_hi - t0) < W ? (kp_hi - t0) : W;
+    while (true) {
+        const int t0 = c_lo + lm_grab_tile(next, W, lane);
+        if (t0 >= c_hi) break;
+        const int wt = (c_hi - t0) < W ? (c_hi - t0) : W;
         V3 p{0, 0, 0};
         int kx = 0, ky = 0, kz = 0;
         if (lane < wt) {
@@ -389,12 +411,14 @@ k_rb_gather(GatherConfig G, LmParams P, const float4 *__restrict__ keypoints, co
             unsigned long long *stats) {
     __shared__ LmTile s_tile[kLmWarps];
     __shared__ int s_stencil[kMaxStencil];
+    __shared__ int s_next;
     if (st->done) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int *stencil = stencil_table_fill(s_stencil, G.r);
+    if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
     rb_gather_tiles(G, P, stencil, keypoints, *d_num_keypoints, st, blocks, classes, stats, s_tile[w],
-                    w * (int) gridDim.x + (int) blockIdx.x, (int) gridDim.x * kLmWarps, lane);
+                    (int) blockIdx.x, (int) gridDim.x, kLmWarps, &s_next, lane);
 }
 
 // GetProblem (ct_icp.cpp:409-424) + seeding of the LM state for this ICP iteration. One CTA.
@@ -1039,6 +1063,7 @@ struct __align__(16) LmPShared {
     };
     int stencil[kMaxStencil];
     int flag;
+    int next;   // tile counter of the residual assembly (lm_grab_tile)
 };
 static_assert(sizeof(LmPShared) <= 227 * 1024, "k_lm_persistent: dynamic shared memory of one CTA (sm_100: 227 KB)");
 extern __shared__ __align__(16) unsigned char lm_smem_raw[];
@@ -1088,13 +1113,15 @@ k_lm_persistent(GatherConfig G0, LmParams P, const float4 *__restrict__ keypoint
         if (__ldcg(&st->done)) break;   // uniform: written before a grid barrier
         // ---- residual assembly (workers)
         if (!solver) {
-            const int wg = w * workers + wi, warps_total = workers * kLmPWarps;
+            // (every warp of this CTA left the previous assembly before the grid barriers in between)
+            if (tid == 0) sh.next = 0;
+            __syncthreads();
             if (kMode == 2)
-                rb_gather_tiles(G0, P, stencil, keypoints, K, st, blocks, classes, stats, sh.tile[w], wg, warps_total, lane);
+                rb_gather_tiles(G0, P, stencil, keypoints, K, st, blocks, classes, stats, sh.tile[w], wi, workers, kLmPWarps, &sh.next, lane);
             else if (kMode == 1)
-                lm_gather_tiles<true>(G0, P, stencil, keypoints, K, st, blocks, stats, D, sh.tile[w], wg, warps_total, lane);
+                lm_gather_tiles<true>(G0, P, stencil, keypoints, K, st, blocks, stats, D, sh.tile[w], wi, workers, kLmPWarps, &sh.next, lane);
             else
-                lm_gather_tiles<false>(G0, P, stencil, keypoints, K, st, blocks, stats, D, sh.tile[w], wg, warps_total, lane);
+                lm_gather_tiles<false>(G0, P, stencil, keypoints, K, st, blocks, stats, D, sh.tile[w], wi, workers, kLmPWarps, &sh.next, lane);
         }
         grid.sync();
         LM_STAMP(1)

@@ -14,11 +14,14 @@
 #   timers      -DCTICP_DEBUG_TIMERS        clock64 stamps in the solver CTA of k_gn_persistent (built here, not benchmarked)
 #   selv1       -DCTICP_SEL_V1              the selection's first cut (owner by binary search over shuffles, separate histogram
 #                                           pass, butterfly sums): what the default path of gather_select.cuh replaced
+#   gridsync    -DCTICP_GN_GRID_BARRIERS    k_gn_persistent with two cg::grid.sync() per iteration instead of the arrive / epoch flags
+#   noprune     -DCTICP_NO_VOXEL_PRUNE      the gather loads every voxel of the stencil (no box-vs-radius prune)
 set -u
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 VARIANTS=("selv1:-DCTICP_SEL_V1" "bulk:-DCTICP_SEL_BULK" "prefetch2:-DCTICP_SEL_PREFETCH=2" "prefetch6:-DCTICP_SEL_PREFETCH=6 -DCTICP_SEL_CAP=224"
           "warps8:-DCTICP_GATHER_WARPS=8" "warps20:-DCTICP_GATHER_WARPS=20 -DCTICP_SEL_CAP=128 -DCTICP_SEL_PREFETCH=2"
-          "warps24:-DCTICP_GATHER_WARPS=24 -DCTICP_SEL_CAP=96 -DCTICP_SEL_PREFETCH=2" "timers:-DCTICP_DEBUG_TIMERS")
+          "warps24:-DCTICP_GATHER_WARPS=24 -DCTICP_SEL_CAP=96 -DCTICP_SEL_PREFETCH=2" "timers:-DCTICP_DEBUG_TIMERS"
+          "gridsync:-DCTICP_GN_GRID_BARRIERS" "noprune:-DCTICP_NO_VOXEL_PRUNE")
 case "${1:-}" in
 build)
     for v in "${VARIANTS[@]}"; do

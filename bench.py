@@ -246,7 +246,7 @@ CPU_SAMPLE_NOTE = ("CPU oracle restating the reference's RegisterFrame with the 
 
 def load_traffic():
     """dram bytes per launch of the GN kernel from the committed ncu capture summary (profiles/), if any."""
-    for name in ("r02_gn_persistent_ncu_summary.json", "gather_kernel_ncu_summary.json"):
+    for name in ("r03_gn_persistent_ncu_summary.json", "r02_gn_persistent_ncu_summary.json", "gather_kernel_ncu_summary.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 return json.load(f).get("dram_bytes_per_launch")

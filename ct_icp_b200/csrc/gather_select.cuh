@@ -226,7 +226,8 @@ template <bool kFilter>
 __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double bucket_scale, const int *stencil,
                                                  const V3 &q, int kx, int ky, int kz, int need, int lane,
                                                  SelScratch &S, NeighborSums &out, unsigned &stencil_points,
-                                                 V3 to_sensor = V3{0, 0, 0}, void *bulk_ptr = nullptr) {
+                                                 V3 to_sensor = V3{0, 0, 0}, void *bulk_ptr = nullptr,
+                                                 double *ranked = nullptr, int n_ranked = 0) {
 #ifdef CTICP_SEL_BULK
     SelBulk *bulk = static_cast<SelBulk *>(bulk_ptr);   // nullptr: this caller uses the load path
 #endif
@@ -527,6 +528,43 @@ __device__ __forceinline__ void warp_gather_sums(const GatherConfig &G, double b
                 if (flag == 2) { S.far[0] = x; S.far[1] = y; S.far[2] = z; S.far[3] = d; }
             }
         }
+    }
+    if (ranked) {
+        // ranked[3 i .. 3 i + 2]: position (relative to the query) of the i-th farthest kept neighbor, i < n_ranked — the head
+        // of the reference's neighbor list, which comes out of its max-heap farthest first (map.h:508-513). Only solver CERES
+        // with num_closest_neighbors > 1 asks for more than points[0] (ct_icp.cpp:593-601): an O(M^2 / 32) ranking of the kept
+        // candidates by (d2, scan order) descending, off every default path.
+        for (int base = 0; base < fill; base += 32) {
+            const int i = base + lane;
+            bool kept_i = false;
+            double di = 0;
+            if (i < fill) {
+                di = S.d2[i];
+#ifdef CTICP_SEL_V1
+                const int b = sel_bucket(di, bucket_scale);
+#else
+                const int b = (int) S.bkt[i];
+#endif
+                kept_i = b < P.xstar || (b == P.xstar && S.eflag[i] != 0);
+            }
+            int rank = 0;
+            for (int j = 0; j < fill; ++j) {
+                const double dj = S.d2[j];
+#ifdef CTICP_SEL_V1
+                const int bj = sel_bucket(dj, bucket_scale);
+#else
+                const int bj = (int) S.bkt[j];
+#endif
+                const bool kept_j = bj < P.xstar || (bj == P.xstar && S.eflag[j] != 0);
+                rank += (int) (kept_j && ((dj > di) || (dj == di && j > i)));
+            }
+            if (kept_i && rank < n_ranked) {
+                ranked[3 * rank] = S.rx[i];
+                ranked[3 * rank + 1] = S.ry[i];
+                ranked[3 * rank + 2] = S.rz[i];
+            }
+        }
+        __syncwarp();
     }
 #ifdef CTICP_SEL_V1
 #pragma unroll

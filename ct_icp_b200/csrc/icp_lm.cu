@@ -45,6 +45,7 @@ struct LmParams {
     double radius;
     double lambda_weight, lambda_neighborhood, power_planarity, max_dist_to_plane;
     int max_num_residuals, min_number_neighbors, num_iters_icp;
+    int ncn;               // num_closest_neighbors (solver CERES, ct_icp.cpp:554,593-601): residual blocks per keypoint
     double bucket_scale;   // 32 / radius^2 (gather_select.cuh)
     double threshold_orientation_norm, threshold_translation_norm;
     // least squares
@@ -102,9 +103,13 @@ struct DistanceStrategy {
 // lane j does keypoint j's scalar work (transform, per-keypoint radius, covariance → eigen → weight with its pow / exp,
 // the 144-byte residual block) and the whole warp does the gather + k-nearest selection of each keypoint in turn.
 constexpr int kLmTileMax = 16;
+constexpr int kMaxNcn = 4;         // num_closest_neighbors supported (the reference's configurations all use 1)
+constexpr int kRankTile = 4;
 struct __align__(16) LmTile {
     SelScratch sel;
     double sums[kLmTileMax][14];   // n, stencil points, Σ rel (3), Σ rel rel^T (6), farthest kept (3)
+    double ranked[kRankTile][kMaxNcn][3];    // num_closest_neighbors > 1 (tiles of at most kRankTile keypoints then): the head
+                                             // of each keypoint's neighbor list, farthest first
 };
 __device__ __forceinline__ void lm_store_sums(double *o, const NeighborSums &s, unsigned spts, int need) {
     o[0] = __hiloint2double((int) spts, s.n);   // two integers in one slot: no int <-> double conversion (XU pipe, se3.cuh)
@@ -155,7 +160,8 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
     const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
     const int c_lo = kp_lo + (int) ((long long) (kp_hi - kp_lo) * cta / num_ctas);
     const int c_hi = kp_lo + (int) ((long long) (kp_hi - kp_lo) * (cta + 1) / num_ctas);
-    const int W = lm_tile_width(c_hi - c_lo, warps_per_cta);
+    int W = lm_tile_width(c_hi - c_lo, warps_per_cta);
+    if (P.ncn > 1 && W > kRankTile) W = kRankTile;
     const int need = P.kmin > 5 ? P.kmin : 5;   // :574 ; neighborhood.h:227
     while (true) {
         const int t0 = c_lo + lm_grab_tile(next, W, lane);
@@ -206,11 +212,13 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
             }
             NeighborSums s;
             unsigned spts = 0;
+            double *ranked = P.ncn > 1 ? &T.ranked[j][0][0] : nullptr;
             if (kDB && D->filter)
                 warp_gather_sums<true>(G, sc_j, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts,
-                                       V3{te.x - q.x, te.y - q.y, te.z - q.z});
+                                       V3{te.x - q.x, te.y - q.y, te.z - q.z}, nullptr, ranked, P.ncn);
             else
-                warp_gather_sums<false>(G, sc_j, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts);
+                warp_gather_sums<false>(G, sc_j, stencil, q, qx, qy, qz, need, lane, T.sel, s, spts, V3{0, 0, 0}, nullptr,
+                                        ranked, P.ncn);
             if (lane == 0) lm_store_sums(T.sums[j], s, spts, need);
         }
         __syncwarp();
@@ -244,9 +252,16 @@ __device__ __noinline__ void lm_gather_tiles(const GatherConfig &G0, const LmPar
                 rb.valid = 1;
                 for (int i = 0; i < 6; ++i) rb.info[i] = 0.0;
                 rb.kind = kResPlane | (P.simple ? kResSimple : 0);
-                blocks[kp] = rb;
+                blocks[(size_t) P.ncn * kp] = rb;
+                // num_closest_neighbors > 1 (ct_icp.cpp:593-601): the same normal, weight and raw point against the next
+                // neighbors of the list (farthest first), block ncn * k + i
+                for (int i = 1; i < P.ncn; ++i) {
+                    const double *r = T.ranked[lane][i];
+                    rb.ref[0] = p.x + r[0]; rb.ref[1] = p.y + r[1]; rb.ref[2] = p.z + r[2];
+                    blocks[(size_t) P.ncn * kp + i] = rb;
+                }
             } else {
-                blocks[kp].valid = 0;
+                for (int i = 0; i < P.ncn; ++i) blocks[(size_t) P.ncn * kp + i].valid = 0;
             }
         }
         __syncwarp();
@@ -441,8 +456,9 @@ __device__ __forceinline__ void lm_select_device(const LmParams &P, int mode, in
     if (tid < 32) s_warp[tid] = 0;
     __syncthreads();
     const int limit = P.max_num_residuals > 0 ? P.max_num_residuals : 0x7fffffff;
-    const int kp_lo = (int) ((long long) K * P.shard_rank / P.shard_world);
-    const int kp_hi = (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
+    // (block slots ncn * k + i of this rank's keypoints, in slot order: builder.SetResidualBlock, ct_icp.cpp:598)
+    const int kp_lo = P.ncn * (int) ((long long) K * P.shard_rank / P.shard_world);
+    const int kp_hi = P.ncn * (int) ((long long) K * (P.shard_rank + 1) / P.shard_world);
     int before = 0, total_valid = -1;   // valid blocks on lower ranks / on all ranks
     if (P.shard_world > 1 && mode == 0) {
         total_valid = 0;
@@ -1278,8 +1294,11 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     const bool robust = opt.solver == CTICP_SOLVER_ROBUST;
     if (!robust && opt.distance != CTICP_DIST_POINT_TO_PLANE)
         throw UnsupportedError("solver CERES: only POINT_TO_PLANE is built (SURVEY §8)");
-    if (!robust && opt.num_closest_neighbors != 1)
-        throw UnsupportedError("solver CERES: num_closest_neighbors != 1 is not built");
+    // ct_icp.cpp:593-601 indexes neighborhood.points[i] for i < num_closest_neighbors: defined only while a described
+    // neighborhood has at least that many points (>= max(min_number_neighbors, 5))
+    const int ncn = robust ? 1 : opt.num_closest_neighbors;
+    if (ncn < 1 || ncn > kMaxNcn || ncn > std::max(opt.min_number_neighbors, 5))
+        throw UnsupportedError("solver CERES: num_closest_neighbors must be in [1, min(4, min_number_neighbors)]");
     if (robust && opt.min_number_neighbors < 5)
         throw UnsupportedError("solver ROBUST: min_number_neighbors < 5 (neighborhoods the reference cannot describe, "
                                "neighborhood.h:227, and then reads stale) is not built");
@@ -1289,9 +1308,10 @@ void IcpSolver::EnqueueCeres(const DeviceMap &map, const cticp_icp_options &opt,
     const bool sharded = nccl_comm != nullptr && shard_world > 1;
     const double sum = std::abs(opt.weight_alpha) + std::abs(opt.weight_neighborhood);
     if (!(sum > 0.0)) throw std::invalid_argument("weight_alpha + weight_neighborhood <= 0");
-    EnsureLmBuffers(k_capacity);
+    EnsureLmBuffers(k_capacity * (size_t) ncn);
 
     LmParams P{};
+    P.ncn = ncn;
     map.SearchParams(map.Options().default_radius, &P.level, &P.r);
     P.radius = map.Options().default_radius;
     P.bucket_scale = (double) kSelBuckets / (P.radius * P.radius);

@@ -483,6 +483,61 @@ def test_ceres_register_matches_oracle(orc, eng, loss):
     print(loss, "pose diff %.3e m %.3e rad" % (dt, dr))
 
 
+@pytest.mark.parametrize("ncn,max_res", [(2, 700), (3, 1000), (4, -1)])
+def test_ceres_num_closest_neighbors(orc, eng, ncn, max_res):
+    """num_closest_neighbors > 1 (src/ct_icp/ct_icp.cpp:554,593-601): every keypoint contributes ncn residual blocks,
+    anchored on points[0..ncn) of its neighbor list (farthest first), block slots ncn * k + i; GetProblem keeps the first
+    max_num_residuals of them in slot order."""
+    map_xyz, kp, frame, prev = _registration_case(orc, eng, "CERES")
+    mo, me = orc.voxel_map(small_map_options(orc, cap=1 << 18)), eng.voxel_map(small_map_options(eng, cap=1 << 18))
+    mo.insert(map_xyz); me.insert(map_xyz)
+    io = orc.default_icp_options()
+    io.solver = abi.SOLVER["CERES"]
+    io.loss_function = abi.LOSS["CAUCHY"]
+    io.min_number_neighbors = 10
+    io.num_closest_neighbors = ncn
+    io.num_iters_icp = 3
+    io.ls_max_num_iters = 5
+    io.ls_num_threads = 4
+    io.max_num_residuals = max_res
+    io.threshold_orientation_norm = 1e-9
+    io.threshold_translation_norm = 1e-9
+    mm = orc.default_odometry_options().default_motion_model
+    st = abi.StrategyOptions(0, 20, 8, 0)
+    _fill_world(orc, kp, frame)
+    kpo, kpe = kp.copy(), kp.copy()
+    fo, fe = frame.copy(), frame.copy()
+    so = mo.icp_register(io, kpo, fo, prev, mm, st)
+    se = me.icp_register(io, kpe, fe, prev, mm, st)
+    assert so.success and se.success
+    assert so.num_residuals_used == se.num_residuals_used
+    if max_res > 0:
+        assert se.num_residuals_used == max_res
+    else:
+        assert se.num_residuals_used % ncn == 0 and se.num_residuals_used > len(kp)
+    dt, dr = frame_diff(fo, fe)
+    assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (ncn, dt, dr)
+    # and it is a different problem from ncn = 1
+    io.num_closest_neighbors = 1
+    f1 = frame.copy()
+    s1 = me.icp_register(io, kp.copy(), f1, prev, mm, st)
+    assert s1.success and frame_diff(f1, fe, log=False)[0] > 1e-7
+
+
+def test_ceres_num_closest_neighbors_out_of_range(orc, eng):
+    map_xyz, kp, frame, prev = _registration_case(orc, eng, "CERES")
+    me = eng.voxel_map(small_map_options(eng, cap=1 << 18))
+    me.insert(map_xyz)
+    io = eng.default_icp_options()
+    io.solver = abi.SOLVER["CERES"]
+    io.min_number_neighbors = 10
+    io.num_closest_neighbors = 5
+    mm = eng.default_odometry_options().default_motion_model
+    st = abi.StrategyOptions(0, 20, 8, 0)
+    with pytest.raises(Exception):
+        me.icp_register(io, kp.copy(), frame.copy(), prev, mm, st)
+
+
 def test_odometry_sequence_hdl64_ceres(orc, eng, seq_hdl64):
     """config 3: driving_config.yaml (solver CERES, Cauchy loss, 5 x 5 iterations, 900 residuals) as device LM/IRLS."""
     seq = seq_hdl64[:24]

@@ -10,7 +10,8 @@ frames are registered untimed.
   value       scans/s with the packed scans already resident in HBM (cticp_odometry_register_staged), timed per step
               with CUDA events on the engine's stream, L2 flushed (untimed 256 MiB memset) between steps
   e2e         scans/s through cticp_odometry_register_frame with HOST numpy buffers: host packing into pinned memory, H2D
-              of the scan, all kernels, D2H of poses / counters; wall clock per step incl. the map-update tail
+              of the scan, all kernels, the frame verdict (poses / counters / decisions, written by the device into mapped
+              pinned memory); wall clock per step incl. the map-update tail
   e2e_dropin  the same call with the reference's full RegistrationSummary contract (src/ct_icp/odometry.cpp:462-486,597):
               corrected_points, all_corrected_points and keypoints are transformed, copied back and assembled into
               caller-owned arrays of 64-byte WPoint3D records inside the timed region

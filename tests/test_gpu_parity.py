@@ -571,7 +571,7 @@ def test_multigpu_sharded_registration_matches_single_gpu(p2p, mode):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, CTICP_CHECK_FRAMES="8", CTICP_P2P=p2p)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29517 + mode),   # (the two parametrisations may run side by side under xdist)
                         os.path.join(root, "tools", "multigpu_check.py")], capture_output=True, text=True, env=env,
                        timeout=600)
     assert "MULTIGPU OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

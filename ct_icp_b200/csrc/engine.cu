@@ -48,48 +48,9 @@ __global__ void __launch_bounds__(32) k_frame_policy(const IcpState *__restrict_
     }
     if (lane < 4) v.counts[lane] = __ldcg(counts + lane);
     __syncwarp();
-    if (lane == 0) {
-        const IcpState &S = v.state;
-        const Q4 qb{S.qb[0], S.qb[1], S.qb[2], S.qb[3]}, qe{S.qe[0], S.qe[1], S.qe[2], S.qe[3]};
-        const V3 tb{S.tb[0], S.tb[1], S.tb[2]}, te{S.te[0], S.te[1], S.te[2]};
-        const double ego = angular_distance_deg(qb, qe);   // EgoAngularDistance(summary.frame)
-        const double rel_dist = norm(te - tb);             // summary.relative_distance (odometry.cpp:433)
-        bool ok;
-        if (rel_dist > in.distance_error_threshold) ok = false;
-        else if (in.relative_orientation > in.orientation_error_threshold || ego > in.orientation_error_threshold) ok = false;
-        else ok = !S.failed;
-        bool add = true;   // UpdateMap, the branch without robust_registration
-        if (in.has_insertions) add = (ego > in.insertion_ego_rotation_threshold) ? (in.skipped_enough != 0) : true;
-        v.add_points_policy = add ? 1 : 0;
-        if (in.do_no_insert) add = false;
-        if (in.always_insert) add = true;
-        int action;
-        if (S.failed == 2 || S.failed == 3) action = kFrameSkip;          // the host raises an exception
-        else if (!ok && in.quit_on_error) action = kFrameSkip;            // early return (odometry.cpp:437-441)
-        else if (add && v.counts[1] > in.room_for) action = kFrameDeferred;
-        else action = add ? kFrameInsert : kFrameEvict;
-        v.assess_ok = ok ? 1 : 0;
-        v.action = action;
-        v.pad0 = 0;
-        v.ego_orientation = ego;
-        v.relative_distance = rel_dist;
-        v.sc = slerp_consts(qb, qe);
-        v.seq = in.seq;
-        v.pad1 = 0;
-    }
+    if (lane == 0) frame_policy_decide(v, in);
     __syncwarp();
-    constexpr int kWords = (int) (sizeof(FrameVerdict) / sizeof(int));
-    constexpr int kSeqWord = (int) (offsetof(FrameVerdict, seq) / sizeof(int));
-    const int *src = reinterpret_cast<const int *>(&v);
-    int *d = reinterpret_cast<int *>(dv);
-    volatile int *h = reinterpret_cast<volatile int *>(hv);
-    for (int i = lane; i < kWords; i += 32) {
-        d[i] = src[i];
-        if (i != kSeqWord) h[i] = src[i];
-    }
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0) h[kSeqWord] = (int) in.seq;
+    frame_verdict_publish(v, dv, hv, lane);
 }
 static double ms_since(hclock::time_point t0) {
     return std::chrono::duration<double, std::milli>(hclock::now() - t0).count();
@@ -165,6 +126,7 @@ Engine::Engine(const cticp_odometry_options &options, int device) : options_(opt
     if (const char *e = getenv("CTICP_FUSED_SAMPLING")) fused_sampling_ = atoi(e) != 0;
     if (const char *e = getenv("CTICP_FUSED_MAP_UPDATE")) fused_map_update_ = atoi(e) != 0;
     if (const char *e = getenv("CTICP_DEVICE_TAIL")) device_tail_ = atoi(e) != 0;
+    if (const char *e = getenv("CTICP_TAIL_IN_KERNEL")) tail_in_kernel_ = atoi(e) != 0;
 
     {
         pool_ = std::make_unique<HostPool>(HostTeamSize(1));
@@ -888,10 +850,22 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
         CT_CUDA_CHECK(cudaMemcpyAsync(d_state_, h_state_, sizeof(IcpState), cudaMemcpyHostToDevice, stream_));
     CT_CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
     icp_->set_keypoints_lo(pipe_->d_keypoints_lo());
+    FrameTailArgs tail{};
+    bool verdict_by_icp_kernel = false;
+    if (tail_armed_) {
+        tail_in_.seq = ++verdict_seq_;
+        tail.in = tail_in_;
+        tail.counts = pipe_->d_counts();
+        tail.dv = d_verdict_;
+        tail.hv = h_verdict_dev_;
+        tail.enabled = 1;
+    }
     switch (options.solver) {
         case CTICP_SOLVER_GN:
-            icp_->EnqueueGaussNewton(*map_, options, pipe_->d_keypoints(), pipe_->d_count_keypoints(), KeypointHint(),
-                                     options.num_iters_icp, d_state_, shard_rank_, shard_world_, nccl_comm_);
+            verdict_by_icp_kernel =
+                icp_->EnqueueGaussNewton(*map_, options, pipe_->d_keypoints(), pipe_->d_count_keypoints(), KeypointHint(),
+                                         options.num_iters_icp, d_state_, shard_rank_, shard_world_, nccl_comm_,
+                                         (tail_armed_ && tail_in_kernel_) ? &tail : nullptr);
             break;
         case CTICP_SOLVER_CERES:
         case CTICP_SOLVER_ROBUST:
@@ -907,10 +881,11 @@ void Engine::TryRegister(const FrameInfo &info, cticp_icp_options &options, Summ
         // device tail (frame_policy.h): verdict + speculative map update behind the ICP kernel; the host waits for the
         // verdict's sequence number in mapped pinned memory, not for the stream
         tail_armed_ = false;
-        tail_in_.seq = ++verdict_seq_;
-        k_frame_policy<<<1, 32, 0, stream_>>>(d_state_, pipe_->d_counts(), tail_in_, d_verdict_, h_verdict_dev_);
-        CT_CUDA_CHECK(cudaGetLastError());
-        tail_launches_ += 1;
+        if (!verdict_by_icp_kernel) {   // (k_gn_persistent's solver CTA writes the verdict itself)
+            k_frame_policy<<<1, 32, 0, stream_>>>(d_state_, pipe_->d_counts(), tail_in_, d_verdict_, h_verdict_dev_);
+            CT_CUDA_CHECK(cudaGetLastError());
+            tail_launches_ += 1;
+        }
         {
             NvtxRange range_map("cticp.map_update");
             map_->UpdateFused(pipe_->d_frame(), pipe_->d_frame_lo(), pipe_->d_count_frame(), pipe_->n(), pipe_->d_frame_world_mut(),

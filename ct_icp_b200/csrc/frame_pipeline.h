@@ -114,6 +114,11 @@ private:
     double *d_frame_world_ = nullptr, *d_all_world_ = nullptr;
     uint32_t *d_tile2_ = nullptr, *d_src2_ = nullptr;   // second selection of the fused sampler
     int fused_grid_ = 0;
+    // k_sample_fused leaves the hash grid and selection 1's flag / tile arrays clean for the next frame (CTICP_SAMPLE_PRECLEAR=0:
+    // every launch clears them itself): the capacity / word count that are clean right now
+    bool preclear_ = true;
+    uint32_t clean_cap_ = 0;
+    size_t clean_words_ = 0;
     uint32_t *d_adaptive_ = nullptr;   // tile counters + flags + src of the band-major position space
     size_t adaptive_capacity_ = 0;
     int launches_ = 0;

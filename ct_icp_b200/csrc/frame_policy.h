@@ -16,6 +16,8 @@
 // Covers the plain registration path (robust_registration = 0, no callbacks, motion compensation CONTINUOUS, fused map
 // update); every other configuration keeps the host-side tail (engine.cu UpdateMap).
 #pragma once
+#include <cstddef>
+
 #include "icp.h"
 #include "se3.cuh"
 
@@ -52,5 +54,66 @@ struct FrameVerdict {
     unsigned seq;            // written last (host copy: after a system-wide fence)
     unsigned pad1;
 };
+
+// What a kernel that ends a registration is given to decide the frame's tail itself (k_gn_persistent: its solver CTA holds
+// the final state in shared memory and writes the verdict before the kernel ends — no k_frame_policy launch, and the host
+// sees the poses one kernel boundary earlier)
+struct FrameTailArgs {
+    FramePolicyIn in;
+    const int *counts;    // FramePipeline counters (N, F, K, -)
+    FrameVerdict *dv;     // device copy
+    FrameVerdict *hv;     // mapped pinned host copy (device address)
+    int enabled;
+};
+
+#ifdef __CUDACC__
+// AssessRegistration (odometry.cpp:604-684, the branch without robust_registration) and UpdateMap's insertion policy
+// (:903-925) on v.state / v.counts; fills the rest of the verdict. One thread.
+__device__ __forceinline__ void frame_policy_decide(FrameVerdict &v, const FramePolicyIn &in) {
+    const IcpState &S = v.state;
+    const Q4 qb{S.qb[0], S.qb[1], S.qb[2], S.qb[3]}, qe{S.qe[0], S.qe[1], S.qe[2], S.qe[3]};
+    const V3 tb{S.tb[0], S.tb[1], S.tb[2]}, te{S.te[0], S.te[1], S.te[2]};
+    const double ego = angular_distance_deg(qb, qe);   // EgoAngularDistance(summary.frame)
+    const double rel_dist = norm(te - tb);             // summary.relative_distance (odometry.cpp:433)
+    bool ok;
+    if (rel_dist > in.distance_error_threshold) ok = false;
+    else if (in.relative_orientation > in.orientation_error_threshold || ego > in.orientation_error_threshold) ok = false;
+    else ok = !S.failed;
+    bool add = true;   // UpdateMap, the branch without robust_registration
+    if (in.has_insertions) add = (ego > in.insertion_ego_rotation_threshold) ? (in.skipped_enough != 0) : true;
+    v.add_points_policy = add ? 1 : 0;
+    if (in.do_no_insert) add = false;
+    if (in.always_insert) add = true;
+    int action;
+    if (S.failed == 2 || S.failed == 3) action = kFrameSkip;          // the host raises an exception
+    else if (!ok && in.quit_on_error) action = kFrameSkip;            // early return (odometry.cpp:437-441)
+    else if (add && v.counts[1] > in.room_for) action = kFrameDeferred;
+    else action = add ? kFrameInsert : kFrameEvict;
+    v.assess_ok = ok ? 1 : 0;
+    v.action = action;
+    v.pad0 = 0;
+    v.ego_orientation = ego;
+    v.relative_distance = rel_dist;
+    v.sc = slerp_consts(qb, qe);
+    v.seq = in.seq;
+    v.pad1 = 0;
+}
+// One warp: the verdict `v` (shared memory, complete and visible to the warp) → device memory and mapped pinned host memory,
+// the sequence number last, after a system-wide fence.
+__device__ __forceinline__ void frame_verdict_publish(const FrameVerdict &v, FrameVerdict *dv, FrameVerdict *hv, int lane) {
+    constexpr int kWords = (int) (sizeof(FrameVerdict) / sizeof(int));
+    constexpr int kSeqWord = (int) (offsetof(FrameVerdict, seq) / sizeof(int));
+    const int *src = reinterpret_cast<const int *>(&v);
+    int *d = reinterpret_cast<int *>(dv);
+    volatile int *h = reinterpret_cast<volatile int *>(hv);
+    for (int i = lane; i < kWords; i += 32) {
+        d[i] = src[i];
+        if (i != kSeqWord) h[i] = src[i];
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) h[kSeqWord] = src[kSeqWord];
+}
+#endif
 
 }  // namespace cticp

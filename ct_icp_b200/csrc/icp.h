@@ -81,6 +81,8 @@ struct GnParams {
                                    // interpolates like always (ct_icp.cpp:964-966)
 };
 
+struct FrameTailArgs;   // frame_policy.h
+
 class IcpSolver {
 public:
     explicit IcpSolver(cudaStream_t stream);
@@ -88,9 +90,13 @@ public:
 
     // d_keypoints: float4 (raw xyz fp32, alpha fp32); d_num_keypoints: device int; upper bound for grid sizing.
     // Enqueues `num_iters` GN iterations on the stream; state is read back by the caller.
-    void EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options &opt, const float4 *d_keypoints,
+    // tail != nullptr: the frame's tail (frame_policy.h) is decided by the kernel that ends the loop when that is the
+    // persistent one — returns true then (the verdict is written by k_gn_persistent's solver CTA); false: the caller
+    // launches k_frame_policy itself.
+    bool EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options &opt, const float4 *d_keypoints,
                             const int *d_num_keypoints, size_t k_upper, int num_iters, IcpState *d_state,
-                            int shard_rank = 0, int shard_world = 1, void *nccl_comm = nullptr);
+                            int shard_rank = 0, int shard_world = 1, void *nccl_comm = nullptr,
+                            const FrameTailArgs *tail = nullptr);
 
     // solver CERES reproduced as a device Levenberg-Marquardt / IRLS loop (icp_lm.cu)
     // k_hint sizes the grids (estimate of the keypoint count), k_capacity the per-keypoint buffers (upper bound)

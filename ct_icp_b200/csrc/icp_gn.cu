@@ -14,6 +14,7 @@
 
 #include "gather_select.cuh"
 #include "icp.h"
+#include "frame_policy.h"
 #include "peer_exchange.cuh"
 #include "small_solve.cuh"
 
@@ -360,6 +361,7 @@ struct GnShared {
     SolveScratch solve;
     IcpState dummy;
     IcpState state;   // persistent kernel, solver CTA: the registration state lives here; `st` (global) is its published copy
+    FrameVerdict verdict;   // persistent kernel, solver CTA: the frame's tail decided at the end of the loop (frame_policy.h)
     int flag;
     int done;         // gather CTAs: the published `done` flag, fetched together with the pose (one memory round trip)
     unsigned long long mbar[kGatherWarps];   // -DCTICP_SEL_BULK: one mbarrier per warp for the bulk copies
@@ -544,7 +546,8 @@ __device__ __forceinline__ bool loop_wait_at_least(const unsigned int *word, uns
 template <bool kPeers>
 __global__ void __launch_bounds__(kGatherWarps * 32, 1)
 k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const int *__restrict__ d_num_keypoints,
-                IcpState *st, double *__restrict__ partials, int num_iters, PeerLinks links, LoopSync sync) {
+                IcpState *st, double *__restrict__ partials, int num_iters, PeerLinks links, LoopSync sync,
+                FrameTailArgs tail) {
 #ifndef CTICP_GN_FLAG_SYNC
     cg::grid_group grid = cg::this_grid();
 #endif
@@ -734,6 +737,21 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
 #endif
     }
     if (kPeers && solver_cta && threadIdx.x == 0) *links.seq = peer_seq;
+    // ---- the tail of the registration (frame_policy.h): AssessRegistration + the insertion policy on the final state, the
+    // verdict to HBM (the speculative map update launched behind this kernel reads it) and to mapped pinned host memory
+    if (solver_cta && tail.enabled) {
+        __syncthreads();   // sh.state is final
+        if (w == 0) {
+            const int *src = reinterpret_cast<const int *>(&sh.state);
+            int *dst = reinterpret_cast<int *>(&sh.verdict.state);
+            for (int i = lane; i < (int) (sizeof(IcpState) / sizeof(int)); i += 32) dst[i] = src[i];
+            if (lane < 4) sh.verdict.counts[lane] = __ldcg(tail.counts + lane);
+            __syncwarp();
+            if (lane == 0) frame_policy_decide(sh.verdict, tail.in);
+            __syncwarp();
+            frame_verdict_publish(sh.verdict, tail.dv, tail.hv, lane);
+        }
+    }
 }
 
 // Stand-alone exchange for the launch-per-step paths (solvers CERES / ROBUST: one per LM evaluation; GN with
@@ -959,9 +977,9 @@ void IcpSolver::CollectGatherTiming() {
     ev_used_ = 0;
 }
 
-void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options &opt, const float4 *d_keypoints,
+bool IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options &opt, const float4 *d_keypoints,
                                    const int *d_num_keypoints, size_t k_upper, int num_iters, IcpState *d_state,
-                                   int shard_rank, int shard_world, void *nccl_comm) {
+                                   int shard_rank, int shard_world, void *nccl_comm, const FrameTailArgs *tail) {
     if (opt.max_number_neighbors > 32 || opt.max_number_neighbors < 1)
         throw std::invalid_argument("max_number_neighbors must be in [1, 32]");
     GatherLaunch cfg;
@@ -1011,14 +1029,16 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         sync.next_arrive = d_sync_words_ + 64 * (sync_set_ ^ 1);
         sync.next_epoch = sync.next_arrive + 32;
         sync_set_ ^= 1;
-        void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters, &links, &sync};
+        FrameTailArgs tail_args{};
+        if (tail) tail_args = *tail;
+        void *args[] = {&cfg, &kp, &nk, &d_state, &parts, &iters, &links, &sync, &tail_args};
         const bool timed = time_gather_ && ev_used_ < kMaxEvents;
         if (timed) cudaEventRecord(ev_begin_[ev_used_], stream_);
         CT_CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kGatherWarps * 32), args, sizeof(GnShared), stream_));
         if (timed) cudaEventRecord(ev_end_[ev_used_++], stream_);
         gather_launches_ += 1;
         launches_ += 1;
-        return;
+        return tail != nullptr;
     }
     const int blocks = GatherBlocks(k_share, num_sms_, kp_per_cta_);
     EnsurePartials(blocks + 1);
@@ -1037,6 +1057,7 @@ void IcpSolver::EnqueueGaussNewton(const DeviceMap &map, const cticp_icp_options
         }
     }
     CT_CUDA_CHECK(cudaGetLastError());
+    return false;
 }
 
 void IcpSolver::NormalEquations(const DeviceMap &map, const cticp_icp_options &opt, const float4 *d_keypoints,

@@ -53,8 +53,14 @@ def test_device_tail_equals_host_tail(eng, seq_small, solver):
         _, host = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
     with _env(CTICP_DEVICE_TAIL=1, CTICP_TAIL_ROOM=16):   # every frame has more than 16 points: always deferred to the host
         _, deferred = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
+    with _env(CTICP_DEVICE_TAIL=1, CTICP_TAIL_IN_KERNEL=0):   # the verdict always by the separate k_frame_policy launch
+        _, separate = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
+    with _env(CTICP_SAMPLE_PRECLEAR=0):   # every k_sample_fused launch clears its own grid / flags
+        _, own_clear = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
     _same_run(dev, host)
     _same_run(dev, deferred)
+    _same_run(dev, separate)
+    _same_run(dev, own_clear)
     assert all(s.success for s, _ in dev)
 
 
@@ -110,3 +116,26 @@ def test_device_tail_quit_on_error(orc, eng, seq_small):
         runs.append((sizes, oks))
     assert runs[0] == runs[1]
     assert not all(runs[1][1][1:])
+
+
+def test_sampler_preclear_with_varying_scan_sizes(orc, eng, seq_small):
+    """k_sample_fused leaves its hash grid and flag arrays clean for the NEXT frame (frame_pipeline.cu): scans whose size
+    jumps up and down between frames take both paths (pre-cleared / own clear, a larger grid than the one left clean) and
+    must keep selecting exactly the oracle's points."""
+    strides = [1, 3, 1, 2, 1, 4, 1, 1]
+    runs = []
+    for b in (orc, eng):
+        od = b.odometry(_sequence_options(b, "GN", init_num_frames=3))
+        out = []
+        for s, k in zip(seq_small, strides):
+            sm = od.RegisterFrame(np.ascontiguousarray(s["xyz"][::k]), np.ascontiguousarray(s["t"][::k]), s["frame_idx"])
+            out.append((sm, od.MapSize()))
+        runs.append(out)
+    for i, ((so, mo), (se, me)) in enumerate(zip(*runs)):
+        assert bool(so.success) == bool(se.success), i
+        assert so.num_corrected_points == se.num_corrected_points, i
+        assert so.num_keypoints == se.num_keypoints, i
+        assert mo == me, i
+        if so.success:
+            dt, dr = frame_diff(so.frame, se.frame)
+            assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (i, dt, dr)

@@ -187,8 +187,10 @@ private:
     // speculative k_map_update_fused right behind the ICP kernel, then waits for the verdict in mapped pinned memory — no
     // copy-engine operation and no host round trip between the ICP loop and the map update.
     bool device_tail_ = true;      // CTICP_DEVICE_TAIL=0: AssessRegistration / UpdateMap on the host for every frame
-    bool tail_in_kernel_ = true;   // CTICP_TAIL_IN_KERNEL=0: always a separate k_frame_policy launch (solver GN's persistent
-                                   // kernel otherwise decides the tail itself, at the end of its loop)
+    bool tail_in_kernel_ = false;  // CTICP_TAIL_IN_KERNEL=1: solver GN's persistent kernel decides the tail itself at the end of
+                                   // its loop instead of a separate k_frame_policy launch (three launches per frame; measured
+                                   // neutral, profiles/r03h_bench*.json: 0.2479 vs 0.2483 ms per step — the default keeps the
+                                   // policy in its own one-warp kernel, the same for every solver)
     bool tail_armed_ = false;      // the coming TryRegister enqueues the device tail (tail_in_ is filled)
     bool tail_launched_ = false;   // the last TryRegister did: h_verdict_ holds this frame's verdict
     FramePolicyIn tail_in_{};

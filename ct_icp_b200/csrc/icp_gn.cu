@@ -972,6 +972,9 @@ void IcpSolver::PrintWarpStamps(int iters) {
 void IcpSolver::CollectGatherTiming() {
     for (int i = 0; i < ev_used_; ++i) {
         float ms = 0.f;
+        // (the caller may have learnt the result from the frame verdict, which the device writes before — or, with
+        // CTICP_TAIL_IN_KERNEL=1, from inside — the kernel this event follows)
+        cudaEventSynchronize(ev_end_[i]);
         if (cudaEventElapsedTime(&ms, ev_begin_[i], ev_end_[i]) == cudaSuccess) gather_ms_ += ms;
     }
     ev_used_ = 0;

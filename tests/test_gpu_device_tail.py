@@ -53,13 +53,13 @@ def test_device_tail_equals_host_tail(eng, seq_small, solver):
         _, host = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
     with _env(CTICP_DEVICE_TAIL=1, CTICP_TAIL_ROOM=16):   # every frame has more than 16 points: always deferred to the host
         _, deferred = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
-    with _env(CTICP_DEVICE_TAIL=1, CTICP_TAIL_IN_KERNEL=0):   # the verdict always by the separate k_frame_policy launch
-        _, separate = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
+    with _env(CTICP_DEVICE_TAIL=1, CTICP_TAIL_IN_KERNEL=1):   # solver GN: the verdict written by k_gn_persistent's solver CTA
+        _, in_kernel = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
     with _env(CTICP_SAMPLE_PRECLEAR=0):   # every k_sample_fused launch clears its own grid / flags
         _, own_clear = _run_sequence(eng, seq_small, solver=solver, init_num_frames=3)
     _same_run(dev, host)
     _same_run(dev, deferred)
-    _same_run(dev, separate)
+    _same_run(dev, in_kernel)
     _same_run(dev, own_clear)
     assert all(s.success for s, _ in dev)
 

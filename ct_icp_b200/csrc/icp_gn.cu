@@ -174,7 +174,7 @@ struct GnPose {
     SlerpConsts sc;
 };
 struct GnWarpAcc {
-    double sum_sq = 0;               // (unused since the rows are reduced by the CTA; kept for the launch-per-step variants)
+    double sum_sq = 0;               // (unused: Σ scalar² comes out of the CTA's row reduction, accumulator kAccSumSq)
     unsigned n_stencil = 0;          // per-lane partial counters
     int n_used = 0, n_kp = 0, n_valid = 0;
     CT_STAMP(long long dbg[4] = {0, 0, 0, 0};)   // cycles in phases A, B, C, D
@@ -536,9 +536,10 @@ __device__ __forceinline__ bool loop_wait_at_least(const unsigned int *word, uns
 // ---- persistent variant: the WHOLE Gauss-Newton loop in one cooperative launch --------------------------------
 // CTA 0 is the solver CTA (deterministic reduction of the partials + 12x12 solve + pose update, by the same warp on
 // the same SM every iteration, so its instructions stay in that SM's instruction cache: executed cold, the serial tail
-// costs tens of microseconds per iteration, warm a few); CTAs 1..G gather. Two grid-wide barriers per iteration replace
-// two kernel launches. While the gather CTAs work on iteration 0, the solver warp runs the solve once on a dummy system
-// to pull its code into the instruction cache.
+// costs tens of microseconds per iteration, warm a few); CTAs 1..G gather. The two sides meet through the arrive / epoch
+// words above (-DCTICP_GN_GRID_BARRIERS: two grid-wide barriers per iteration, the round's earlier form). While the gather
+// CTAs work on iteration 0, the solver warp runs the solve once on a dummy system to pull its code into the instruction
+// cache. With `tail.enabled` the solver CTA also decides the frame's tail after the loop (frame_policy.h).
 //
 // kPeers (multi-GPU, keypoints sharded): between its reduction and its solve the solver CTA exchanges the accumulator
 // with the other ranks' solver CTAs through NVLink peer memory (peer_exchange.cuh) — the all-reduce of SURVEY §8e

@@ -525,10 +525,11 @@ struct LoopSync {
     unsigned int *next_arrive, *next_epoch;   // the other set
 };
 constexpr long long kLoopSyncTimeout = 4000000000LL;   // SM cycles (~2 s)
-__device__ __forceinline__ bool loop_wait_at_least(const unsigned int *word, unsigned int want) {
+__device__ __forceinline__ bool loop_wait_at_least(const unsigned int *word, unsigned int want,
+                                                   long long timeout = kLoopSyncTimeout) {
     const long long t0 = clock64();
     while (*reinterpret_cast<const volatile unsigned int *>(word) < want)
-        if (clock64() - t0 > kLoopSyncTimeout) return false;
+        if (clock64() - t0 > timeout) return false;
     __threadfence();
     return true;
 }
@@ -622,7 +623,9 @@ k_gn_persistent(GatherLaunch cfg, const float4 *__restrict__ keypoints, const in
             if (threadIdx.x == 0) {   // phases A / C read the pose from shared memory: 34 registers less to keep live
 #ifdef CTICP_GN_FLAG_SYNC
                 // the state of iteration `it` is published (it == 0: uploaded by the host before the launch)
-                const bool ok = it == 0 || loop_wait_at_least(sync.epoch, (unsigned int) it);
+                // (sharded: the solver CTA may itself be waiting for a late peer rank, up to PeerLinks::timeout_cycles)
+                const bool ok = it == 0 || loop_wait_at_least(sync.epoch, (unsigned int) it,
+                                                              kLoopSyncTimeout + (kPeers ? links.timeout_cycles : 0LL));
 #else
                 const bool ok = true;
 #endif
